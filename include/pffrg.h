@@ -1,0 +1,151 @@
+/* pffrg.h -- C ABI of libpffrg: the B200-native pf-FRG flow-equation core.
+ *
+ * This is the drop-in boundary for SpinParser's FrgCore plugin seam. The reference host code (task/lattice/model
+ * parsing, symmetry reduction, measurements, HDF5 output) stays as it is and drives a flow core through
+ *     FrgCore *FrgCoreFactory::newFrgCore(identifier, spinModel, measurements, options)   src/FrgCoreFactory.hpp:40
+ *     virtual void FrgCore::computeStep()                                                  src/FrgCore.hpp:77
+ *     virtual void FrgCore::finalizeStep(float newCutoff)                                  src/FrgCore.hpp:86
+ *     EffectiveAction::{cutoff, isDiverged()} and the vertex arrays the measurements read  src/EffectiveAction.hpp:40-59
+ * Each entry point below names the reference interface it replaces. INTEGRATION.md shows the adapter class
+ * (`B200FrgCore : FrgCore`) a SpinParser maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain C types only; the caller owns every host buffer it passes; the library owns all device memory.
+ *  - every function returns PFFRG_OK (0) or a negative error code; pffrg_last_error() describes the last failure.
+ *  - a handle is driven by one host thread; one handle per GPU (one process per GPU for multi-GPU runs).
+ *  - host arrays use the REFERENCE memory layout and either float (the reference's type) or double:
+ *        v2   [Nw]                                     src/SU2/SU2VertexSingleParticle.hpp
+ *        v4_c [su][t][rid], su = so(so+1)/2+uo, so>=uo src/SU2/SU2VertexTwoParticle.hpp:595-605 (SU2: c = S,D; XYZ: X,Y,Z,D)
+ *        v4   [su][t][mu][nu][rid]                     src/TRI/TRIVertexTwoParticle.hpp:65-71    (TRI: one array)
+ *    All arithmetic on the device is FP64.
+ *  - there is no CPU fallback: every compute entry point fails with PFFRG_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PFFRG_H
+#define PFFRG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFFRG_ABI_VERSION 1
+
+typedef enum pffrg_status
+{
+	PFFRG_OK = 0,
+	PFFRG_ERR_ARGUMENT = -1,   /* invalid descriptor / null pointer / wrong size */
+	PFFRG_ERR_CUDA = -2,       /* CUDA runtime or launch failure, or no usable GPU */
+	PFFRG_ERR_NCCL = -3,       /* NCCL failure */
+	PFFRG_ERR_STATE = -4,      /* call sequence violated (e.g. compute before set_state) */
+	PFFRG_ERR_UNSUPPORTED = -5 /* problem exceeds a compiled-in limit */
+} pffrg_status;
+
+/* identifier strings of FrgCoreFactory::newFrgCore, src/FrgCoreFactory.cpp:25-51 */
+typedef enum pffrg_core { PFFRG_CORE_SU2 = 0, PFFRG_CORE_XYZ = 1, PFFRG_CORE_TRI = 2 } pffrg_core;
+typedef enum pffrg_dtype { PFFRG_F32 = 0, PFFRG_F64 = 1 } pffrg_dtype;
+
+/* Problem description: everything the hot path reads from FrgCommon::{frequency(),lattice()} (src/FrgCommon.hpp:26-49)
+ * and the core options of src/SU2/SU2FrgCore.cpp:20-29. All tables are copied during pffrg_create. */
+typedef struct pffrg_desc
+{
+	int32_t abi_version;          /* PFFRG_ABI_VERSION */
+	int32_t core;                 /* pffrg_core */
+	int32_t n_frequencies;        /* Nw: FrequencyDiscretization::size */
+	const double *frequencies;    /* [Nw] strictly ascending positive mesh points (FrequencyDiscretization::_data) */
+	int32_t n_sites;              /* L: Lattice::size (number of representative sites) */
+	const int32_t *sites_rid;     /* [L]   Lattice::getSites()[j].rid                  src/Lattice.hpp:491 */
+	const int32_t *sites_perm;    /* [L*3] Lattice::getSites()[j].spinPermutation[k]  (0=X 1=Y 2=Z) */
+	const int32_t *inverted_rid;  /* [L]   Lattice::getInvertedSites()[j].rid          src/Lattice.hpp:481 */
+	const int32_t *inverted_perm; /* [L*3] */
+	const int32_t *overlap_offsets; /* [L+1] prefix sums of Lattice::getOverlap(rid).size  src/Lattice.hpp:46-150,470 */
+	const int32_t *overlap_rid1;  /* [overlap_offsets[L]] LatticeOverlap::rid1 */
+	const int32_t *overlap_rid2;  /* [overlap_offsets[L]] LatticeOverlap::rid2 */
+	const int32_t *overlap_perm1; /* [overlap_offsets[L]*3] transformed{X,Y,Z}1 */
+	const int32_t *overlap_perm2; /* [overlap_offsets[L]*3] transformed{X,Y,Z}2 */
+	int32_t n_range;              /* number of sites j in Lattice::getRange(0)         src/Lattice.hpp:503-523 */
+	const int32_t *range_fwd_rid; /* [n_range] Lattice::symmetryTransform(zero, j)     src/Lattice.hpp:397-402 */
+	const int32_t *range_inv_rid; /* [n_range] Lattice::symmetryTransform(j, zero) */
+	double spin_length;           /* SU2 option "spin" (ignored by XYZ/TRI)            src/SU2/SU2FrgCore.cpp:20,25 */
+	int32_t device;               /* CUDA device ordinal for this handle */
+} pffrg_desc;
+
+typedef struct pffrg_context *pffrg_handle;
+
+/* per-step statistics (replaces the LoadManager's per-rank timing gather, src/lib/LoadManager.hpp:636-665) */
+typedef struct pffrg_stats
+{
+	double ms_v2_flow;      /* device time of the self-energy flow kernel */
+	double ms_node_table;   /* device time of the quadrature node table kernel */
+	double ms_v4_flow;      /* device time of the vertex flow kernel (the hot kernel) */
+	double ms_finalize;     /* device time of the last finalize (Euler update + exchange) */
+	double ms_exchange;     /* device time of the NCCL exchange inside the last finalize */
+	int64_t kernel_evals;   /* quadrature nodes (kernel evaluations) this rank processed in the last step, all 3 channels */
+	int64_t kernel_evals_t; /* of which t-channel evaluations */
+	int64_t items;          /* work items (frequency triples) this rank processed */
+	double alg_bytes;       /* algorithmic gather+output bytes of this rank's share */
+	double alg_flops;       /* algorithmic FP64 flops of this rank's share */
+	int32_t launches;       /* kernels launched by the last compute_step + finalize_step */
+} pffrg_stats;
+
+/* library / environment ------------------------------------------------------------------------------------------ */
+int pffrg_abi_version(void);
+/* description of the last error on this thread (never NULL) */
+const char *pffrg_last_error(void);
+/* number of usable CUDA devices (0 when there is no GPU; never fails) */
+int pffrg_device_count(void);
+
+/* lifetime: replaces FrgCoreFactory::newFrgCore + the {SU2,XYZ,TRI}FrgCore constructors/destructors
+ * (src/FrgCoreFactory.cpp:25-51, src/SU2/SU2FrgCore.cpp:17-87) ------------------------------------------------------ */
+int pffrg_create(const pffrg_desc *desc, pffrg_handle *out);
+int pffrg_destroy(pffrg_handle h);
+
+/* sizes of the host arrays in reference layout */
+int pffrg_num_vertex_arrays(pffrg_handle h);     /* 2 (SU2) / 4 (XYZ) / 1 (TRI) */
+int64_t pffrg_vertex_array_length(pffrg_handle h); /* elements per array: NF*L (SU2/XYZ), NF*16*L (TRI) */
+int64_t pffrg_num_items(pffrg_handle h);         /* NF = Nw*Nw*(Nw+1)/2 work items */
+
+/* multi-GPU: replaces HMP::LoadManager's MPI distribution and broadcasts (src/lib/LoadManager.hpp:581-649,240).
+ * One process per GPU. Rank 0 calls pffrg_comm_unique_id and ships the id to all ranks by any host transport
+ * (the reference would use MPI_Bcast); then every rank calls pffrg_comm_init. Without these calls the handle is a
+ * single-GPU core. Work items are split into contiguous, cost-balanced ranges (pffrg_item_range). */
+#define PFFRG_UNIQUE_ID_BYTES 128
+int pffrg_comm_unique_id(void *id_out /* PFFRG_UNIQUE_ID_BYTES */);
+int pffrg_comm_init(pffrg_handle h, const void *id, int rank, int n_ranks);
+int pffrg_item_range(pffrg_handle h, int64_t *begin, int64_t *end); /* this rank's items in the current step */
+
+/* state transfer: replaces direct access to {SU2,XYZ,TRI}EffectiveAction's arrays and EffectiveAction::cutoff
+ * (src/SU2/SU2EffectiveAction.hpp:38-60, src/EffectiveAction.hpp:59). `v4` holds pffrg_num_vertex_arrays pointers. */
+int pffrg_set_state(pffrg_handle h, double cutoff, const void *v2, const void *const *v4, int dtype);
+int pffrg_get_state(pffrg_handle h, double *cutoff, void *v2, void *const *v4, int dtype);
+/* the flow of the last compute_step (FrgCore::flow(), src/FrgCore.hpp:103-106); gathers from all ranks when needed */
+int pffrg_get_flow(pffrg_handle h, void *v2_flow, void *const *v4_flow, int dtype);
+
+/* FrgCore::computeStep (src/SU2/SU2FrgCore.cpp:89-109): self-energy flow, then vertex flow of this rank's items.
+ * *diverged (optional) is set to 1 when the flow contains NaN (EffectiveAction::isDiverged,
+ * src/SU2/SU2EffectiveAction.hpp:212-230); divergence is not an error. */
+int pffrg_compute_step(pffrg_handle h, int *diverged);
+/* FrgCore::finalizeStep (src/SU2/SU2FrgCore.cpp:111-137): state += (new_cutoff - cutoff) * flow, cutoff = new_cutoff,
+ * then the updated vertex is exchanged between ranks (ncclBroadcast group == the reference's MPI_Bcast). */
+int pffrg_finalize_step(pffrg_handle h, double new_cutoff);
+/* block until all device work of this handle has finished */
+int pffrg_synchronize(pffrg_handle h);
+
+/* restrict the next compute_step to an explicit item range (tests, bounded benchmarks); end<=begin restores the default */
+int pffrg_set_item_range(pffrg_handle h, int64_t begin, int64_t end);
+
+int pffrg_get_stats(pffrg_handle h, pffrg_stats *out);
+
+/* raw CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events */
+void *pffrg_stream(pffrg_handle h);
+
+/* page-locked host memory for the arrays passed to set_state / get_state / get_flow (plain memory works too, but
+ * transfers from pinned buffers run at full PCIe speed). Returns NULL on failure. */
+void *pffrg_host_alloc(size_t bytes);
+void pffrg_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

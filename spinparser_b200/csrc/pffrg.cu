@@ -1,0 +1,633 @@
+// pffrg.cu -- host side of libpffrg: the C ABI of include/pffrg.h on top of the kernels in pffrg_kernels.cuh.
+//
+// One handle = one GPU. The handle owns the device copies of the problem tables, the vertex state (v2, v4), the flow of
+// the last step, and the per-step quadrature node table. Multi-GPU runs use one process per GPU: work items are split
+// into contiguous cost-balanced ranges (replacing the dynamic master/worker chunking of src/lib/LoadManager.hpp:796-852),
+// and after the Euler update every rank broadcasts its slice of the updated vertex (ncclBroadcast group on the compute
+// stream; replaces the MPI_Bcast of src/lib/LoadManager.hpp:240 issued from src/SU2/SU2FrgCore.cpp:136).
+#include "pffrg.h"
+#include "pffrg_kernels.cuh"
+
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <tuple>
+#include <vector>
+
+using namespace pffrg;
+
+namespace
+{
+	thread_local std::string g_lastError = "no error";
+
+	int fail(int code, const char *fmt, ...)
+	{
+		char buf[1024];
+		va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+		g_lastError = buf;
+		return code;
+	}
+
+#define CUDA_TRY(expr)                                                                                                   \
+	do {                                                                                                                 \
+		cudaError_t e_ = (expr);                                                                                         \
+		if (e_ != cudaSuccess) return fail(PFFRG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+#define NCCL_TRY(expr)                                                                                                   \
+	do {                                                                                                                 \
+		ncclResult_t r_ = (expr);                                                                                        \
+		if (r_ != ncclSuccess) return fail(PFFRG_ERR_NCCL, "%s failed: %s (%s:%d)", #expr, ncclGetErrorString(r_), __FILE__, __LINE__); \
+	} while (0)
+
+	template <typename T> struct DeviceArray
+	{
+		T *p = nullptr; size_t n = 0;
+		cudaError_t alloc(size_t count) { release(); n = count; return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)); }
+		cudaError_t upload(const std::vector<T> &h) { cudaError_t e = alloc(h.size()); if (e != cudaSuccess || h.empty()) return e; return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice); }
+		void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+	};
+
+	// per-core constants of the cost / byte / flop model
+	struct CoreModel { int C, arrays, ladderTerms, localTerms, rpaTerms; };
+	CoreModel modelOf(int core)
+	{
+		if (core == SU2) return { 2, 2, 10, 16, 2 };
+		if (core == XYZ) return { 4, 4, 32, 64, 4 };
+		return { 16, 1, 512, 1024, 128 };
+	}
+}
+
+struct pffrg_context
+{
+	int core = 0, nw = 0, L = 0, Lp = 0, RL = 0, C = 0, nArrays = 0, device = 0;
+	int64_t nf = 0;
+	int64_t overlapTotal = 0, uniquePairs = 0;
+	double spin = 0.5;
+	std::vector<double> mesh;
+
+	// device tables
+	DeviceArray<double> dMesh;
+	DeviceArray<int> dSitesRid, dInvRid, dSitesPerm, dInvPerm, dRngFwd, dRngInv, dSlotOff;
+	DeviceArray<int4> dTasks;
+	DeviceArray<uint2> dPairs;
+	// state
+	DeviceArray<double> dV4, dFlow4, dV2, dFlow2, dCutoff;
+	DeviceArray<int> dCount; DeviceArray<double> dNodeW, dNodeWt;
+	DeviceArray<int> dNan;
+	int *hNan = nullptr;
+	int nodeStride = 0;
+
+	// launch configuration of the flow kernel
+	int nb = 32, groups = 1, threads = 32, nslots = 1; size_t smemBytes = 0;
+
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[8] = {};
+	bool haveState = false, haveFlow = false, flowGathered = true;
+	double cutoff = 0.0;
+
+	// partition
+	int rank = 0, nRanks = 1;
+	ncclComm_t comm = nullptr;
+	std::vector<int64_t> bounds; // [nRanks + 1] item boundaries of the current step
+	int64_t userBegin = 0, userEnd = 0;
+	int64_t curBegin = 0, curEnd = 0;
+
+	pffrg_stats stats = {};
+
+	Problem problem() const
+	{
+		Problem P;
+		P.nw = nw; P.L = L; P.Lp = Lp; P.RL = RL; P.nf = (int)nf;
+		P.mesh = dMesh.p; P.sites_rid = dSitesRid.p; P.inv_rid = dInvRid.p; P.sites_perm = dSitesPerm.p; P.inv_perm = dInvPerm.p;
+		P.rpa_tasks = dTasks.p; P.rpa_slot_off = dSlotOff.p; P.rpa_pairs = dPairs.p;
+		P.nrange = (int)dRngFwd.n; P.rng_fwd = dRngFwd.p; P.rng_inv = dRngInv.p; P.spin = spin;
+		return P;
+	}
+	NodeTable nodeTable() const { NodeTable N; N.count = dCount.p; N.wp = dNodeW.p; N.wt = dNodeWt.p; N.stride = nodeStride; return N; }
+	size_t v4Elements() const { return (size_t)nf * RL; }
+};
+
+namespace
+{
+	int packPerm(const int32_t *p) { return (p[0] & 3) | ((p[1] & 3) << 2) | ((p[2] & 3) << 4); }
+
+	template <int CORE, int NB> size_t flowSmemBytes(int nw, int L, int groups) { return FlowSmem<CORE, NB>(nw, L, groups).total; }
+	size_t flowSmemBytes(int core, int nb, int nw, int L, int groups)
+	{
+		if (core == SU2) return nb == 32 ? flowSmemBytes<SU2, 32>(nw, L, groups) : nb == 16 ? flowSmemBytes<SU2, 16>(nw, L, groups) : flowSmemBytes<SU2, 8>(nw, L, groups);
+		if (core == XYZ) return nb == 32 ? flowSmemBytes<XYZ, 32>(nw, L, groups) : nb == 16 ? flowSmemBytes<XYZ, 16>(nw, L, groups) : flowSmemBytes<XYZ, 8>(nw, L, groups);
+		return 0;
+	}
+
+	template <int CORE, int NB>
+	cudaError_t launchFlow(pffrg_context *h, int64_t begin, int64_t count)
+	{
+		auto kernel = v4FlowKernel<CORE, NB>;
+		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes);
+		if (e != cudaSuccess) return e;
+		FlowConfig cfg; cfg.groups = h->groups; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes;
+		kernel<<<(unsigned)count, h->threads, h->smemBytes, h->stream>>>(h->problem(), h->nodeTable(), cfg, h->dV4.p, h->dFlow4.p, (int)begin, h->dNan.p);
+		return cudaGetLastError();
+	}
+
+	cudaError_t launchFlowDispatch(pffrg_context *h, int64_t begin, int64_t count)
+	{
+		if (count <= 0) return cudaSuccess;
+		if (h->core == SU2) return h->nb == 32 ? launchFlow<SU2, 32>(h, begin, count) : h->nb == 16 ? launchFlow<SU2, 16>(h, begin, count) : launchFlow<SU2, 8>(h, begin, count);
+		if (h->core == XYZ) return h->nb == 32 ? launchFlow<XYZ, 32>(h, begin, count) : h->nb == 16 ? launchFlow<XYZ, 16>(h, begin, count) : launchFlow<XYZ, 8>(h, begin, count);
+		return cudaErrorNotSupported;
+	}
+
+	// RPA pair list: per representative site the (rid1, perm1, rid2, perm2) tuples of Lattice::getOverlap(rid), identical
+	// tuples merged into integer multiplicities, sorted so that equal (rid1, perm1) are adjacent ("groups": operand A is
+	// loaded once per group). Tasks (one per rid) are dealt to the RPA slots longest-first.
+	void buildRpa(const pffrg_desc *d, int core, int nslots, std::vector<uint2> &pairs, std::vector<int4> &tasks, std::vector<int> &slotOff, int64_t &unique)
+	{
+		const int L = d->n_sites;
+		std::vector<int4> perRid;
+		for (int rid = 0; rid < L; ++rid)
+		{
+			std::map<std::tuple<int, int, int, int>, int> mult;
+			for (int i = d->overlap_offsets[rid]; i < d->overlap_offsets[rid + 1]; ++i)
+			{
+				int p1 = core == SU2 ? 0 : packPerm(d->overlap_perm1 + 3 * i), p2 = core == SU2 ? 0 : packPerm(d->overlap_perm2 + 3 * i);
+				mult[std::make_tuple(d->overlap_rid1[i], p1, d->overlap_rid2[i], p2)] += 1;
+			}
+			int begin = (int)pairs.size();
+			int lastR1 = -1, lastP1 = -1;
+			for (auto &kv : mult)
+			{
+				int r1 = std::get<0>(kv.first), p1 = std::get<1>(kv.first), r2 = std::get<2>(kv.first), p2 = std::get<3>(kv.first);
+				unsigned flag = (r1 != lastR1 || p1 != lastP1) ? 1u : 0u;
+				lastR1 = r1; lastP1 = p1;
+				uint2 w; w.x = (unsigned)r1 | ((unsigned)r2 << 8) | ((unsigned)p1 << 16) | ((unsigned)p2 << 22) | (flag << 31); w.y = (unsigned)kv.second;
+				pairs.push_back(w);
+			}
+			perRid.push_back(make_int4(rid, begin, (int)pairs.size(), 0));
+		}
+		unique = (int64_t)pairs.size();
+		std::vector<int> order(L);
+		std::iota(order.begin(), order.end(), 0);
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return perRid[a].z - perRid[a].y > perRid[b].z - perRid[b].y; });
+		std::vector<std::vector<int4>> bySlot(nslots);
+		std::vector<long> load(nslots, 0);
+		for (int r : order)
+		{
+			int best = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+			bySlot[best].push_back(perRid[r]);
+			load[best] += perRid[r].z - perRid[r].y + 8;
+		}
+		slotOff.assign(1, 0);
+		for (auto &s : bySlot) { for (auto &t : s) tasks.push_back(t); slotOff.push_back((int)tasks.size()); }
+	}
+
+	// node counts per mesh frequency at the current cutoff (host copy of what nodeTableKernel enumerates)
+	std::vector<int> hostNodeCounts(const pffrg_context *h)
+	{
+		std::vector<int> c(h->nw);
+		for (int i = 0; i < h->nw; ++i) c[i] = nodeCount(h->mesh.data(), h->nw, h->cutoff, h->mesh[i]);
+		return c;
+	}
+
+	// contiguous cost-balanced item ranges; also fills the per-rank statistics of the current step
+	void partitionItems(pffrg_context *h, const std::vector<int> &counts)
+	{
+		const CoreModel m = modelOf(h->core);
+		const int nw = h->nw; const double L = h->L;
+		const double costSU = (16.0 * m.C + m.ladderTerms) * L;
+		const double costT = (16.0 * m.C + m.localTerms) * L + 2.0 * m.rpaTerms * (double)h->uniquePairs;
+		const int64_t nf = h->nf;
+		std::vector<double> prefix((size_t)nf / nw + 1, 0.0); // cost per su block (all t of one (s,u))
+		double sumT = 0.0; for (int t = 0; t < nw; ++t) sumT += counts[t];
+		int64_t su = 0;
+		for (int so = 0; so < nw; ++so)
+			for (int uo = 0; uo <= so; ++uo, ++su)
+				prefix[su + 1] = prefix[su] + nw * (counts[so] + counts[uo]) * costSU + sumT * costT;
+		const double total = prefix.back();
+		h->bounds.assign(h->nRanks + 1, 0);
+		h->bounds[h->nRanks] = nf;
+		for (int r = 1; r < h->nRanks; ++r)
+		{
+			const double target = total * r / h->nRanks;
+			int64_t b = std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin();
+			b = std::min<int64_t>(std::max<int64_t>(b, 0), nf / nw);
+			// refine inside the su block: items of one block differ only through their t index
+			int64_t item = std::min<int64_t>(b * nw, nf);
+			if (b > 0)
+			{
+				double acc = prefix[b - 1]; const int64_t blk = b - 1;
+				int so = (int)((std::sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
+				while ((int64_t)(so + 1) * (so + 2) / 2 <= blk) ++so;
+				while ((int64_t)so * (so + 1) / 2 > blk) --so;
+				int uo = (int)(blk - (int64_t)so * (so + 1) / 2);
+				item = blk * nw;
+				for (int t = 0; t < nw && acc < target; ++t, ++item) acc += (counts[so] + counts[uo]) * costSU + counts[t] * costT;
+			}
+			h->bounds[r] = std::max(item, h->bounds[r - 1]);
+		}
+	}
+
+	void fillStats(pffrg_context *h, const std::vector<int> &counts, int64_t begin, int64_t end)
+	{
+		const CoreModel m = modelOf(h->core);
+		const int nw = h->nw;
+		int64_t nS = 0, nT = 0, nU = 0;
+		for (int64_t it = begin; it < end; ++it)
+		{
+			int64_t su = it / nw; int t = (int)(it % nw);
+			int so = (int)((std::sqrt(8.0 * su + 1.0) - 1.0) * 0.5);
+			while ((int64_t)(so + 1) * (so + 2) / 2 <= su) ++so;
+			while ((int64_t)so * (so + 1) / 2 > su) --so;
+			int uo = (int)(su - (int64_t)so * (so + 1) / 2);
+			nS += counts[so]; nT += counts[t]; nU += counts[uo];
+		}
+		const double L = h->L, C = m.C;
+		h->stats.items = end - begin;
+		h->stats.kernel_evals = nS + nT + nU;
+		h->stats.kernel_evals_t = nT;
+		h->stats.alg_bytes = (double)(nS + nT + nU) * 128.0 * L * C + (double)nT * 128.0 * C + (double)(end - begin) * L * C * 24.0;
+		const double fmaSU = 16.0 * L * C + m.ladderTerms * L;
+		const double fmaT = 16.0 * L * C + (double)m.rpaTerms * h->overlapTotal + m.localTerms * L;
+		h->stats.alg_flops = 2.0 * ((double)(nS + nU) * fmaSU + (double)nT * fmaT);
+	}
+
+	int exchangeSlices(pffrg_context *h, double *buffer)
+	{
+		if (h->nRanks <= 1) return PFFRG_OK;
+		NCCL_TRY(ncclGroupStart());
+		for (int r = 0; r < h->nRanks; ++r)
+		{
+			size_t off = (size_t)h->bounds[r] * h->RL, cnt = (size_t)(h->bounds[r + 1] - h->bounds[r]) * h->RL;
+			if (cnt == 0) continue;
+			NCCL_TRY(ncclBroadcast(buffer + off, buffer + off, cnt, ncclDouble, r, h->comm, h->stream));
+		}
+		NCCL_TRY(ncclGroupEnd());
+		return PFFRG_OK;
+	}
+
+	template <typename T>
+	int importArrays(pffrg_context *h, const void *const *src, double *dst)
+	{
+		const size_t len = (size_t)h->nf * h->L * (h->core == TRI ? 16 : 1);
+		DeviceArray<T> staging;
+		CUDA_TRY(staging.alloc(len));
+		for (int a = 0; a < h->nArrays; ++a)
+		{
+			if (!src[a]) { staging.release(); return fail(PFFRG_ERR_ARGUMENT, "vertex array %d is null", a); }
+			CUDA_TRY(cudaMemcpyAsync(staging.p, src[a], len * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+			importKernel<T><<<1184, 256, 0, h->stream>>>(staging.p, dst, (size_t)h->nf, h->L, h->Lp, h->RL, h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
+			CUDA_TRY(cudaGetLastError());
+		}
+		CUDA_TRY(cudaStreamSynchronize(h->stream));
+		staging.release();
+		return PFFRG_OK;
+	}
+
+	template <typename T>
+	int exportArrays(pffrg_context *h, const double *src, void *const *dst)
+	{
+		const size_t len = (size_t)h->nf * h->L * (h->core == TRI ? 16 : 1);
+		DeviceArray<T> staging;
+		CUDA_TRY(staging.alloc(len));
+		for (int a = 0; a < h->nArrays; ++a)
+		{
+			if (!dst[a]) continue;
+			exportKernel<T><<<1184, 256, 0, h->stream>>>(src, staging.p, (size_t)h->nf, h->L, h->Lp, h->RL, h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
+			CUDA_TRY(cudaGetLastError());
+			CUDA_TRY(cudaMemcpyAsync(dst[a], staging.p, len * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+			CUDA_TRY(cudaStreamSynchronize(h->stream));
+		}
+		staging.release();
+		return PFFRG_OK;
+	}
+
+	template <typename T>
+	int importVector(pffrg_context *h, const void *src, double *dst, int n)
+	{
+		DeviceArray<T> staging; CUDA_TRY(staging.alloc(n));
+		CUDA_TRY(cudaMemcpyAsync(staging.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+		convertKernel<T><<<1, 128, 0, h->stream>>>(staging.p, dst, n);
+		CUDA_TRY(cudaStreamSynchronize(h->stream));
+		staging.release();
+		return PFFRG_OK;
+	}
+	template <typename T>
+	int exportVector(pffrg_context *h, const double *src, void *dst, int n)
+	{
+		DeviceArray<T> staging; CUDA_TRY(staging.alloc(n));
+		convertBackKernel<T><<<1, 128, 0, h->stream>>>(src, staging.p, n);
+		CUDA_TRY(cudaMemcpyAsync(dst, staging.p, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+		CUDA_TRY(cudaStreamSynchronize(h->stream));
+		staging.release();
+		return PFFRG_OK;
+	}
+
+	float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
+}
+
+extern "C" {
+
+int pffrg_abi_version(void) { return PFFRG_ABI_VERSION; }
+const char *pffrg_last_error(void) { return g_lastError.c_str(); }
+
+int pffrg_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
+{
+	if (!d || !out) return fail(PFFRG_ERR_ARGUMENT, "null descriptor or output pointer");
+	*out = nullptr;
+	if (d->abi_version != PFFRG_ABI_VERSION) return fail(PFFRG_ERR_ARGUMENT, "ABI version mismatch: caller %d, library %d", d->abi_version, PFFRG_ABI_VERSION);
+	if (d->core < 0 || d->core > 2) return fail(PFFRG_ERR_ARGUMENT, "unknown core %d", d->core);
+	if (d->n_frequencies < 2) return fail(PFFRG_ERR_ARGUMENT, "FrequencyDiscretization must contain at least two frequency values");
+	if (d->n_sites < 1 || d->n_range < 1) return fail(PFFRG_ERR_ARGUMENT, "empty lattice");
+	if (!d->frequencies || !d->sites_rid || !d->sites_perm || !d->inverted_rid || !d->inverted_perm || !d->overlap_offsets || !d->overlap_rid1 || !d->overlap_rid2 || !d->overlap_perm1 || !d->overlap_perm2 || !d->range_fwd_rid || !d->range_inv_rid)
+		return fail(PFFRG_ERR_ARGUMENT, "null table pointer in descriptor");
+	for (int i = 0; i < d->n_frequencies; ++i)
+		if (!(d->frequencies[i] > 0) || (i > 0 && !(d->frequencies[i] > d->frequencies[i - 1]))) return fail(PFFRG_ERR_ARGUMENT, "frequency mesh must be positive and strictly ascending (index %d)", i);
+	if (d->n_frequencies > 512) return fail(PFFRG_ERR_UNSUPPORTED, "more than 512 frequencies are not supported");
+	if (d->n_sites > 256) return fail(PFFRG_ERR_UNSUPPORTED, "more than 256 representative sites are not supported yet (got %d)", d->n_sites);
+	if (d->core == PFFRG_CORE_TRI) return fail(PFFRG_ERR_UNSUPPORTED, "the TRI core is not available in this build");
+	const int L = d->n_sites;
+	for (int j = 0; j < L; ++j)
+		if (d->sites_rid[j] < 0 || d->sites_rid[j] >= L || d->inverted_rid[j] < 0 || d->inverted_rid[j] >= L) return fail(PFFRG_ERR_ARGUMENT, "site table entry %d out of range", j);
+	if (d->overlap_offsets[0] != 0) return fail(PFFRG_ERR_ARGUMENT, "overlap_offsets[0] must be 0");
+	for (int r = 0; r < L; ++r) if (d->overlap_offsets[r + 1] < d->overlap_offsets[r]) return fail(PFFRG_ERR_ARGUMENT, "overlap_offsets not monotone");
+	for (int i = 0; i < d->overlap_offsets[L]; ++i)
+		if (d->overlap_rid1[i] < 0 || d->overlap_rid1[i] >= L || d->overlap_rid2[i] < 0 || d->overlap_rid2[i] >= L) return fail(PFFRG_ERR_ARGUMENT, "overlap entry %d out of range", i);
+	for (int j = 0; j < d->n_range; ++j)
+		if (d->range_fwd_rid[j] < 0 || d->range_fwd_rid[j] >= L || d->range_inv_rid[j] < 0 || d->range_inv_rid[j] >= L) return fail(PFFRG_ERR_ARGUMENT, "range entry %d out of range", j);
+
+	int nDev = pffrg_device_count();
+	if (nDev <= 0) return fail(PFFRG_ERR_CUDA, "no CUDA device available (libpffrg has no CPU fallback)");
+	if (d->device < 0 || d->device >= nDev) return fail(PFFRG_ERR_ARGUMENT, "device %d out of range (%d devices)", d->device, nDev);
+	CUDA_TRY(cudaSetDevice(d->device));
+	cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
+	if (prop.major < 10) return fail(PFFRG_ERR_CUDA, "device %d is sm_%d%d; libpffrg is built for sm_100a only", d->device, prop.major, prop.minor);
+
+	pffrg_context *h = new pffrg_context();
+	const CoreModel m = modelOf(d->core);
+	h->core = d->core; h->nw = d->n_frequencies; h->L = L; h->Lp = (L + 3) / 4 * 4; h->C = m.C; h->RL = m.C * h->Lp; h->nArrays = m.arrays;
+	h->nf = (int64_t)h->nw * h->nw * (h->nw + 1) / 2;
+	h->device = d->device; h->spin = d->spin_length;
+	h->mesh.assign(d->frequencies, d->frequencies + h->nw);
+	h->overlapTotal = d->overlap_offsets[L];
+	if ((double)h->nf * h->RL > 2.0e9) { delete h; return fail(PFFRG_ERR_UNSUPPORTED, "vertex too large for 32-bit row offsets"); }
+
+	// launch configuration: k groups of L threads; batch width NB chosen so that at least two CTAs fit per SM
+	h->groups = std::max(1, 256 / L);
+	h->threads = std::max(64, (h->groups * L + 31) / 32 * 32);
+	h->nb = 32;
+	while (h->nb > 8 && flowSmemBytes(h->core, h->nb, h->nw, L, h->groups) > 100 * 1024) h->nb >>= 1;
+	h->smemBytes = flowSmemBytes(h->core, h->nb, h->nw, L, h->groups);
+	if (h->smemBytes > (size_t)prop.sharedMemPerBlockOptin) { const size_t need = h->smemBytes; delete h; return fail(PFFRG_ERR_UNSUPPORTED, "flow kernel needs %zu bytes of shared memory", need); }
+	h->nslots = (h->threads / 32) * (32 / h->nb);
+
+	std::vector<uint2> pairs; std::vector<int4> tasks; std::vector<int> slotOff;
+	buildRpa(d, h->core, h->nslots, pairs, tasks, slotOff, h->uniquePairs);
+
+	std::vector<int> sitesPerm(L), invPerm(L);
+	for (int j = 0; j < L; ++j) { sitesPerm[j] = packPerm(d->sites_perm + 3 * j); invPerm[j] = packPerm(d->inverted_perm + 3 * j); }
+
+	cudaError_t e = cudaSuccess;
+	auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+	ok(h->dMesh.upload(h->mesh));
+	ok(h->dSitesRid.upload(std::vector<int>(d->sites_rid, d->sites_rid + L)));
+	ok(h->dInvRid.upload(std::vector<int>(d->inverted_rid, d->inverted_rid + L)));
+	ok(h->dSitesPerm.upload(sitesPerm)); ok(h->dInvPerm.upload(invPerm));
+	ok(h->dRngFwd.upload(std::vector<int>(d->range_fwd_rid, d->range_fwd_rid + d->n_range)));
+	ok(h->dRngInv.upload(std::vector<int>(d->range_inv_rid, d->range_inv_rid + d->n_range)));
+	ok(h->dTasks.upload(tasks)); ok(h->dSlotOff.upload(slotOff)); ok(h->dPairs.upload(pairs));
+	ok(h->dV4.alloc(h->v4Elements())); ok(h->dFlow4.alloc(h->v4Elements()));
+	ok(h->dV2.alloc(h->nw)); ok(h->dFlow2.alloc(h->nw)); ok(h->dCutoff.alloc(1));
+	h->nodeStride = 2 * h->nw + 8;
+	ok(h->dCount.alloc(h->nw)); ok(h->dNodeW.alloc((size_t)h->nw * h->nodeStride)); ok(h->dNodeWt.alloc((size_t)h->nw * h->nodeStride));
+	ok(h->dNan.alloc(1));
+	if (e == cudaSuccess) e = cudaMemset(h->dV4.p, 0, h->v4Elements() * sizeof(double));
+	if (e == cudaSuccess) e = cudaMemset(h->dFlow4.p, 0, h->v4Elements() * sizeof(double));
+	if (e == cudaSuccess) e = cudaMemset(h->dFlow2.p, 0, h->nw * sizeof(double));
+	if (e == cudaSuccess) e = cudaMemset(h->dNan.p, 0, sizeof(int));
+	if (e == cudaSuccess) e = cudaMallocHost(&h->hNan, sizeof(int));
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+	for (auto &ev : h->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+	if (e != cudaSuccess)
+	{
+		int code = fail(PFFRG_ERR_CUDA, "device setup failed: %s", cudaGetErrorString(e));
+		pffrg_destroy(h);
+		return code;
+	}
+	h->bounds = { 0, h->nf };
+	*out = h;
+	return PFFRG_OK;
+}
+
+int pffrg_destroy(pffrg_handle h)
+{
+	if (!h) return PFFRG_OK;
+	cudaSetDevice(h->device);
+	if (h->stream) cudaStreamSynchronize(h->stream);
+	if (h->comm) ncclCommDestroy(h->comm);
+	h->dMesh.release(); h->dSitesRid.release(); h->dInvRid.release(); h->dSitesPerm.release(); h->dInvPerm.release(); h->dRngFwd.release(); h->dRngInv.release();
+	h->dSlotOff.release(); h->dTasks.release(); h->dPairs.release(); h->dV4.release(); h->dFlow4.release(); h->dV2.release(); h->dFlow2.release(); h->dCutoff.release();
+	h->dCount.release(); h->dNodeW.release(); h->dNodeWt.release(); h->dNan.release();
+	if (h->hNan) cudaFreeHost(h->hNan);
+	for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+	if (h->stream) cudaStreamDestroy(h->stream);
+	delete h;
+	return PFFRG_OK;
+}
+
+int pffrg_num_vertex_arrays(pffrg_handle h) { return h ? h->nArrays : fail(PFFRG_ERR_ARGUMENT, "null handle"); }
+int64_t pffrg_vertex_array_length(pffrg_handle h) { return h ? h->nf * h->L * (h->core == TRI ? 16 : 1) : fail(PFFRG_ERR_ARGUMENT, "null handle"); }
+int64_t pffrg_num_items(pffrg_handle h) { return h ? h->nf : fail(PFFRG_ERR_ARGUMENT, "null handle"); }
+
+int pffrg_comm_unique_id(void *idOut)
+{
+	if (!idOut) return fail(PFFRG_ERR_ARGUMENT, "null id buffer");
+	static_assert(sizeof(ncclUniqueId) <= PFFRG_UNIQUE_ID_BYTES, "unique id does not fit");
+	ncclUniqueId id;
+	NCCL_TRY(ncclGetUniqueId(&id));
+	memset(idOut, 0, PFFRG_UNIQUE_ID_BYTES);
+	memcpy(idOut, &id, sizeof(id));
+	return PFFRG_OK;
+}
+
+int pffrg_comm_init(pffrg_handle h, const void *id, int rank, int nRanks)
+{
+	if (!h || !id) return fail(PFFRG_ERR_ARGUMENT, "null handle or id");
+	if (nRanks < 1 || rank < 0 || rank >= nRanks) return fail(PFFRG_ERR_ARGUMENT, "bad rank %d of %d", rank, nRanks);
+	if (h->comm) return fail(PFFRG_ERR_STATE, "communicator already initialised");
+	CUDA_TRY(cudaSetDevice(h->device));
+	ncclUniqueId uid; memcpy(&uid, id, sizeof(uid));
+	NCCL_TRY(ncclCommInitRank(&h->comm, nRanks, uid, rank));
+	h->rank = rank; h->nRanks = nRanks;
+	h->bounds.assign(nRanks + 1, 0); h->bounds[nRanks] = h->nf;
+	return PFFRG_OK;
+}
+
+int pffrg_item_range(pffrg_handle h, int64_t *begin, int64_t *end)
+{
+	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");
+	if (begin) *begin = h->curBegin;
+	if (end) *end = h->curEnd;
+	return PFFRG_OK;
+}
+
+int pffrg_set_item_range(pffrg_handle h, int64_t begin, int64_t end)
+{
+	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");
+	if (end > begin && (begin < 0 || end > h->nf)) return fail(PFFRG_ERR_ARGUMENT, "item range [%lld, %lld) outside [0, %lld)", (long long)begin, (long long)end, (long long)h->nf);
+	h->userBegin = begin; h->userEnd = end;
+	return PFFRG_OK;
+}
+
+int pffrg_set_state(pffrg_handle h, double cutoff, const void *v2, const void *const *v4, int dtype)
+{
+	if (!h || !v2 || !v4) return fail(PFFRG_ERR_ARGUMENT, "null argument");
+	if (dtype != PFFRG_F32 && dtype != PFFRG_F64) return fail(PFFRG_ERR_ARGUMENT, "unknown dtype %d", dtype);
+	CUDA_TRY(cudaSetDevice(h->device));
+	int rc = dtype == PFFRG_F64 ? importArrays<double>(h, v4, h->dV4.p) : importArrays<float>(h, v4, h->dV4.p);
+	if (rc != PFFRG_OK) return rc;
+	rc = dtype == PFFRG_F64 ? importVector<double>(h, v2, h->dV2.p, h->nw) : importVector<float>(h, v2, h->dV2.p, h->nw);
+	if (rc != PFFRG_OK) return rc;
+	h->cutoff = cutoff;
+	setScalarKernel<<<1, 1, 0, h->stream>>>(h->dCutoff.p, cutoff);
+	CUDA_TRY(cudaStreamSynchronize(h->stream));
+	h->haveState = true; h->haveFlow = false;
+	return PFFRG_OK;
+}
+
+int pffrg_get_state(pffrg_handle h, double *cutoff, void *v2, void *const *v4, int dtype)
+{
+	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");
+	if (!h->haveState) return fail(PFFRG_ERR_STATE, "no state has been set");
+	if (dtype != PFFRG_F32 && dtype != PFFRG_F64) return fail(PFFRG_ERR_ARGUMENT, "unknown dtype %d", dtype);
+	CUDA_TRY(cudaSetDevice(h->device));
+	if (cutoff) *cutoff = h->cutoff;
+	if (v2) { int rc = dtype == PFFRG_F64 ? exportVector<double>(h, h->dV2.p, v2, h->nw) : exportVector<float>(h, h->dV2.p, v2, h->nw); if (rc != PFFRG_OK) return rc; }
+	if (v4) { int rc = dtype == PFFRG_F64 ? exportArrays<double>(h, h->dV4.p, v4) : exportArrays<float>(h, h->dV4.p, v4); if (rc != PFFRG_OK) return rc; }
+	return PFFRG_OK;
+}
+
+int pffrg_get_flow(pffrg_handle h, void *v2flow, void *const *v4flow, int dtype)
+{
+	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");
+	if (!h->haveFlow) return fail(PFFRG_ERR_STATE, "no flow has been computed");
+	if (dtype != PFFRG_F32 && dtype != PFFRG_F64) return fail(PFFRG_ERR_ARGUMENT, "unknown dtype %d", dtype);
+	CUDA_TRY(cudaSetDevice(h->device));
+	if (!h->flowGathered)
+	{
+		int rc = exchangeSlices(h, h->dFlow4.p);
+		if (rc != PFFRG_OK) return rc;
+		h->flowGathered = true;
+	}
+	if (v2flow) { int rc = dtype == PFFRG_F64 ? exportVector<double>(h, h->dFlow2.p, v2flow, h->nw) : exportVector<float>(h, h->dFlow2.p, v2flow, h->nw); if (rc != PFFRG_OK) return rc; }
+	if (v4flow) { int rc = dtype == PFFRG_F64 ? exportArrays<double>(h, h->dFlow4.p, v4flow) : exportArrays<float>(h, h->dFlow4.p, v4flow); if (rc != PFFRG_OK) return rc; }
+	return PFFRG_OK;
+}
+
+int pffrg_compute_step(pffrg_handle h, int *diverged)
+{
+	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");
+	if (!h->haveState) return fail(PFFRG_ERR_STATE, "compute_step before set_state");
+	CUDA_TRY(cudaSetDevice(h->device));
+	const std::vector<int> counts = hostNodeCounts(h);
+	partitionItems(h, counts);
+	int64_t begin = h->bounds[h->rank], end = h->bounds[h->rank + 1];
+	if (h->userEnd > h->userBegin) { begin = h->userBegin; end = h->userEnd; }
+	h->curBegin = begin; h->curEnd = end;
+	fillStats(h, counts, begin, end);
+
+	const Problem P = h->problem();
+	CUDA_TRY(cudaMemsetAsync(h->dNan.p, 0, sizeof(int), h->stream));
+	CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+	const size_t smemV2 = sizeof(double) * (h->nw + 128);
+	if (h->core == SU2) v2FlowKernel<SU2><<<h->nw, 128, smemV2, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->dFlow2.p);
+	else if (h->core == XYZ) v2FlowKernel<XYZ><<<h->nw, 128, smemV2, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->dFlow2.p);
+	else v2FlowKernel<TRI><<<h->nw, 128, smemV2, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->dFlow2.p);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+	nodeTableKernel<<<(h->nw + 63) / 64, 64, sizeof(double) * 3 * h->nw, h->stream>>>(P, h->nodeTable(), h->dV2.p, h->dFlow2.p, h->dCutoff.p);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+	CUDA_TRY(launchFlowDispatch(h, begin, end - begin));
+	CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
+	h->stats.launches = 3;
+	if (h->nRanks > 1 && !(h->userEnd > h->userBegin)) NCCL_TRY(ncclAllReduce(h->dNan.p, h->dNan.p, 1, ncclInt, ncclMax, h->comm, h->stream));
+	CUDA_TRY(cudaMemcpyAsync(h->hNan, h->dNan.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	CUDA_TRY(cudaStreamSynchronize(h->stream));
+	h->stats.ms_v2_flow = elapsed(h->ev[0], h->ev[1]);
+	h->stats.ms_node_table = elapsed(h->ev[1], h->ev[2]);
+	h->stats.ms_v4_flow = elapsed(h->ev[2], h->ev[3]);
+	h->haveFlow = true;
+	h->flowGathered = (h->nRanks <= 1);
+	if (diverged) *diverged = *h->hNan ? 1 : 0;
+	return PFFRG_OK;
+}
+
+int pffrg_finalize_step(pffrg_handle h, double newCutoff)
+{
+	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");
+	if (!h->haveFlow) return fail(PFFRG_ERR_STATE, "finalize_step before compute_step");
+	CUDA_TRY(cudaSetDevice(h->device));
+	CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
+	// every rank updates the self energy (its flow is computed redundantly) and its own slice of the vertex
+	eulerKernel<<<1, 128, 0, h->stream>>>(h->dV2.p, h->dFlow2.p, (size_t)h->nw, h->dCutoff.p, newCutoff);
+	CUDA_TRY(cudaGetLastError());
+	const size_t off = (size_t)h->curBegin * h->RL, cnt = (size_t)(h->curEnd - h->curBegin) * h->RL;
+	if (cnt > 0)
+	{
+		eulerKernel<<<1184, 256, 0, h->stream>>>(h->dV4.p + off, h->dFlow4.p + off, cnt, h->dCutoff.p, newCutoff);
+		CUDA_TRY(cudaGetLastError());
+	}
+	setScalarKernel<<<1, 1, 0, h->stream>>>(h->dCutoff.p, newCutoff);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
+	if (h->nRanks > 1 && !(h->userEnd > h->userBegin)) { int rc = exchangeSlices(h, h->dV4.p); if (rc != PFFRG_OK) return rc; }
+	CUDA_TRY(cudaEventRecord(h->ev[6], h->stream));
+	CUDA_TRY(cudaStreamSynchronize(h->stream));
+	h->stats.ms_finalize = elapsed(h->ev[4], h->ev[6]);
+	h->stats.ms_exchange = elapsed(h->ev[5], h->ev[6]);
+	h->stats.launches += 3;
+	h->cutoff = newCutoff;
+	h->haveFlow = false;
+	return PFFRG_OK;
+}
+
+int pffrg_synchronize(pffrg_handle h)
+{
+	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");
+	CUDA_TRY(cudaSetDevice(h->device));
+	CUDA_TRY(cudaStreamSynchronize(h->stream));
+	return PFFRG_OK;
+}
+
+int pffrg_get_stats(pffrg_handle h, pffrg_stats *out)
+{
+	if (!h || !out) return fail(PFFRG_ERR_ARGUMENT, "null argument");
+	*out = h->stats;
+	return PFFRG_OK;
+}
+
+void *pffrg_stream(pffrg_handle h) { return h ? (void *)h->stream : nullptr; }
+
+void *pffrg_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); fail(PFFRG_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+	return p;
+}
+void pffrg_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+} // extern "C"

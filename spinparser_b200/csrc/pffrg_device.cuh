@@ -1,0 +1,224 @@
+// pffrg_device.cuh -- device-side building blocks of the pf-FRG flow kernels (sm_100a, FP64).
+//
+// Everything here restates, for the GPU, semantics fixed by the reference (file:line relative to the SpinParser tree):
+//   frequency mesh search / lerp          src/FrequencyDiscretization.hpp:253-351
+//   self-energy access (odd, clamped)     src/SU2/SU2VertexSingleParticle.hpp:73-87
+//   access buffers (sector map + lerps)   src/SU2/SU2VertexTwoParticle.hpp:399-490, src/TRI/TRIVertexTwoParticle.hpp:401-504
+// The arithmetic expressions keep the reference's operation order where it decides which mesh cell a frequency falls
+// into; summation order elsewhere is free (parity tolerance 1e-10, round-off head-room ~1e-15).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pffrg
+{
+	enum Core : int { SU2 = 0, XYZ = 1, TRI = 2 };
+	enum Channel : int { CH_S = 0, CH_T = 1, CH_U = 2, CH_NONE = 3 };
+
+	__host__ __device__ constexpr int channelsOf(int core) { return core == SU2 ? 2 : (core == XYZ ? 4 : 16); }
+
+	// ---- frequency mesh -------------------------------------------------------------------------------------------
+	// first index i in [1, nw) with mesh[i] > w, or nw if none (the linear scans of FrequencyDiscretization.hpp:264-267,
+	// 290-293, 338-347 as a binary search)
+	__host__ __device__ __forceinline__ int firstGreater(const double *mesh, int nw, double w)
+	{
+		int lo = 1, hi = nw;
+		while (lo < hi)
+		{
+			int mid = (lo + hi) >> 1;
+			if (mesh[mid] > w) hi = mid; else lo = mid + 1;
+		}
+		return lo;
+	}
+
+	// FrequencyDiscretization::interpolateOffset, :326-351
+	__host__ __device__ __forceinline__ void interpolateOffset(const double *mesh, int nw, double w, int &lower, int &upper, double &bias)
+	{
+		if (w <= mesh[0]) { lower = 0; upper = 0; bias = 0.0; return; }
+		int i = firstGreater(mesh, nw, w);
+		if (i >= nw) { lower = nw - 1; upper = nw - 1; bias = 0.0; return; }
+		upper = i; lower = i - 1;
+		bias = (w - mesh[lower]) / (mesh[upper] - mesh[lower]);
+	}
+
+	// FrequencyDiscretization::offset, :306-316: first i >= 1 with mesh[i] >= w
+	__host__ __device__ __forceinline__ int exactOffset(const double *mesh, int nw, double w)
+	{
+		if (w <= mesh[0]) return 0;
+		int lo = 1, hi = nw;
+		while (lo < hi)
+		{
+			int mid = (lo + hi) >> 1;
+			if (mesh[mid] >= w) hi = mid; else lo = mid + 1;
+		}
+		return lo < nw ? lo : nw - 1;
+	}
+
+	// mesh value at a signed index (negative half mirrored: value(-i-1) = -mesh[i], :187-192)
+	__host__ __device__ __forceinline__ double meshValue(const double *mesh, int index) { return index >= 0 ? mesh[index] : -mesh[-index - 1]; }
+
+	// FrequencyDiscretization::lesser / greater, :253-296, signed-index form, including the quirk for |w| <= mesh[0]
+	__host__ __device__ __forceinline__ int meshGreaterPos(const double *mesh, int nw, double w)
+	{
+		if (w <= mesh[0]) return 0;
+		int i = firstGreater(mesh, nw, w);
+		return i < nw ? i : nw - 1;
+	}
+	__host__ __device__ __forceinline__ int meshLesserPos(const double *mesh, int nw, double w)
+	{
+		if (w <= mesh[0]) return 0;
+		int i = firstGreater(mesh, nw, w);
+		return i < nw ? i - 1 : nw - 1;
+	}
+	__host__ __device__ __forceinline__ int meshLesser(const double *mesh, int nw, double w)
+	{
+		return w < 0 ? -(meshGreaterPos(mesh, nw, -w) + 1) : meshLesserPos(mesh, nw, w);
+	}
+	__host__ __device__ __forceinline__ int meshGreater(const double *mesh, int nw, double w)
+	{
+		return w < 0 ? -(meshLesserPos(mesh, nw, -w) + 1) : meshGreaterPos(mesh, nw, w);
+	}
+
+	// {SU2,XYZ,TRI}VertexSingleParticle::getValue, src/SU2/SU2VertexSingleParticle.hpp:73-87
+	__host__ __device__ __forceinline__ double selfEnergy(const double *mesh, int nw, const double *v2, double w)
+	{
+		double sign = 1.0;
+		if (w < 0) { w = -w; sign = -1.0; }
+		int lo, up; double bias;
+		interpolateOffset(mesh, nw, w, lo, up, bias);
+		return sign * ((1 - bias) * v2[lo] + bias * v2[up]);
+	}
+
+	// ---- quadrature node lists ---------------------------------------------------------------------------------------
+	// Number of kernel evaluations of one channel with transfer frequency x at cutoff L: the conventional single-scale
+	// terms (src/SU2/SU2FrgCore.cpp:351-371) plus the nodes of the three Katanin segments (:378-392) as enumerated by
+	// ImplicitIntegrator (src/lib/Integrator.hpp:138-287).
+	__host__ __device__ inline int nodeCount(const double *mesh, int nw, double cutoff, double x)
+	{
+		int n = 1;
+		if (x > 2.0 * cutoff) n += 1;
+		if (-(x + cutoff) > -mesh[nw - 1])
+		{
+			int umax = meshLesser(mesh, nw, -(x + cutoff));
+			n += (umax != -nw) ? (umax + nw) + 2 : 2;
+		}
+		if (x - cutoff > cutoff)
+		{
+			int umin = meshGreater(mesh, nw, cutoff - x), umax = meshLesser(mesh, nw, -cutoff);
+			n += (umax >= umin) ? (umax - umin) + 3 : 2;
+		}
+		if (cutoff < mesh[nw - 1])
+		{
+			int umin = meshGreater(mesh, nw, cutoff);
+			n += (umin != nw - 1) ? (nw - 1 - umin) + 2 : 2;
+		}
+		return n;
+	}
+
+	// ---- access buffers --------------------------------------------------------------------------------------------------
+	// Four interpolation supports of one vertex access: row index (su*Nw + t), weight, and the symmetry flags that decide
+	// signs and the site/spin maps at gather time.
+	struct __align__(8) AccessBuffer
+	{
+		double w[4];
+		int row[4];
+		int flags; // bit0: site/pair exchange, bit1: TRI zeta_mu*zeta_nu factor, bit(4+k): support k reads the s<->u mirrored entry
+		int pad;
+	};
+	constexpr int AB_EXCHANGE = 1, AB_TZ = 2;
+	__host__ __device__ __forceinline__ int abSwapped(int flags, int k) { return (flags >> (4 + k)) & 1; }
+
+	__host__ __device__ __forceinline__ int rowIndex(int nw, int so, int to, int uo, int k, int &flags)
+	{
+		if (so < uo) { flags |= 1 << (4 + k); return (uo * (uo + 1) / 2 + so) * nw + to; }
+		return (so * (so + 1) / 2 + uo) * nw + to;
+	}
+
+	// generateAccessBuffer(s, t, u, channel): SU2VertexTwoParticle.hpp:399-490 (XYZ identical), TRIVertexTwoParticle.hpp:401-504
+	template <int CORE>
+	__host__ __device__ inline void makeAccessBuffer(const double *mesh, int nw, double s, double t, double u, int channel, AccessBuffer &ab)
+	{
+		int flags = 0;
+		if (CORE == TRI)
+		{
+			if (s < 0) { s = -s; flags ^= AB_EXCHANGE; }
+			if (t < 0) { t = -t; flags ^= AB_TZ; }
+			if (u < 0) { u = -u; flags ^= AB_EXCHANGE; flags ^= AB_TZ; }
+		}
+		else
+		{
+			if (s < 0 && u < 0) { s = -s; u = -u; }
+			else
+			{
+				if (s < 0) { s = -s; flags |= AB_EXCHANGE; }
+				else if (u < 0) { u = -u; flags |= AB_EXCHANGE; }
+			}
+			if (t < 0) t = -t;
+		}
+		int l1, u1, l2, u2; double b1, b2;
+		if (channel == CH_S)
+		{
+			int es = exactOffset(mesh, nw, s);
+			interpolateOffset(mesh, nw, t, l1, u1, b1);
+			interpolateOffset(mesh, nw, u, l2, u2, b2);
+			ab.w[0] = (1 - b2) * (1 - b1); ab.row[0] = rowIndex(nw, es, l1, l2, 0, flags);
+			ab.w[1] = (1 - b2) * b1;       ab.row[1] = rowIndex(nw, es, u1, l2, 1, flags);
+			ab.w[2] = b2 * (1 - b1);       ab.row[2] = rowIndex(nw, es, l1, u2, 2, flags);
+			ab.w[3] = b2 * b1;             ab.row[3] = rowIndex(nw, es, u1, u2, 3, flags);
+		}
+		else if (channel == CH_T)
+		{
+			int et = exactOffset(mesh, nw, t);
+			interpolateOffset(mesh, nw, s, l1, u1, b1);
+			interpolateOffset(mesh, nw, u, l2, u2, b2);
+			ab.w[0] = (1 - b2) * (1 - b1); ab.row[0] = rowIndex(nw, l1, et, l2, 0, flags);
+			ab.w[1] = (1 - b2) * b1;       ab.row[1] = rowIndex(nw, u1, et, l2, 1, flags);
+			ab.w[2] = b2 * (1 - b1);       ab.row[2] = rowIndex(nw, l1, et, u2, 2, flags);
+			ab.w[3] = b2 * b1;             ab.row[3] = rowIndex(nw, u1, et, u2, 3, flags);
+		}
+		else
+		{
+			int eu = exactOffset(mesh, nw, u);
+			interpolateOffset(mesh, nw, s, l1, u1, b1);
+			interpolateOffset(mesh, nw, t, l2, u2, b2);
+			ab.w[0] = (1 - b2) * (1 - b1); ab.row[0] = rowIndex(nw, l1, l2, eu, 0, flags);
+			ab.w[1] = (1 - b2) * b1;       ab.row[1] = rowIndex(nw, u1, l2, eu, 1, flags);
+			ab.w[2] = b2 * (1 - b1);       ab.row[2] = rowIndex(nw, l1, u2, eu, 2, flags);
+			ab.w[3] = b2 * b1;             ab.row[3] = rowIndex(nw, u1, u2, eu, 3, flags);
+		}
+		ab.flags = flags;
+		ab.pad = 0;
+	}
+
+	// TRIVertexTwoParticle::_zeta, src/TRI/TRIVertexTwoParticle.hpp:674-677
+	__host__ __device__ __forceinline__ double zeta(int c) { return c <= 2 ? -1.0 : 1.0; }
+
+	// sign of support k for OUTPUT channel c (SU2VertexTwoParticle.hpp:377,616-632; XYZ :393,:640-655; TRI :412-443,:643-666)
+	template <int CORE>
+	__host__ __device__ __forceinline__ double supportSign(int flags, int k, int c)
+	{
+		if (CORE == SU2) return (c == 1 && abSwapped(flags, k)) ? -1.0 : 1.0;
+		if (CORE == XYZ) return (c == 3 && abSwapped(flags, k)) ? -1.0 : 1.0;
+		int mu = c >> 2, nu = c & 3;
+		double sgn = 1.0;
+		if (flags & AB_TZ) sgn *= zeta(mu) * zeta(nu);
+		if (abSwapped(flags, k)) sgn *= (flags & AB_EXCHANGE) ? -zeta(mu) : -zeta(nu);
+		return sgn;
+	}
+
+	// stored channel read by output channel c at a site with spin permutation perm (packed 2 bits per component)
+	// XYZVertexTwoParticle.hpp:401-404, TRIVertexTwoParticle.hpp:378-382
+	template <int CORE>
+	__host__ __device__ __forceinline__ int storedChannel(int flags, int c, int perm)
+	{
+		if (CORE == SU2) return c;
+		if (CORE == XYZ) return c < 3 ? ((perm >> (2 * c)) & 3) : 3;
+		int mu = c >> 2, nu = c & 3;
+		int m = (flags & AB_EXCHANGE) ? nu : mu, n = (flags & AB_EXCHANGE) ? mu : nu;
+		if (m < 3) m = (perm >> (2 * m)) & 3;
+		if (n < 3) n = (perm >> (2 * n)) & 3;
+		return 4 * m + n;
+	}
+	constexpr int PERM_IDENTITY = 0 | (1 << 2) | (2 << 4);
+}

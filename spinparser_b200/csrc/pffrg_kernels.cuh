@@ -1,0 +1,662 @@
+// pffrg_kernels.cuh -- the CUDA kernels of the pf-FRG flow step (sm_100a, FP64 throughout).
+//
+//   K2 v2FlowKernel      d/dLambda Sigma(w)            src/SU2/SU2FrgCore.cpp:139-169 (XYZ :164-193, TRI :122-151)
+//   K0 nodeTableKernel   quadrature nodes + weights    src/SU2/SU2FrgCore.cpp:337-424 x src/lib/Integrator.hpp:138-287
+//   K1 v4FlowKernel      d/dLambda Gamma(s,t,u; all r) src/SU2/SU2FrgCore.cpp:171-431 (XYZ :195-571, TRI :153-3001)
+//   K3 eulerKernel       state += dLambda * flow        src/SU2/SU2FrgCore.cpp:111-134
+//
+// Device layout of the two-particle vertex ("vertex-major"): v4[row][c][Lp] with row = su*Nw + t the work-item index,
+// c the vertex channel and Lp = L rounded up to 4 doubles, so one interpolation support of one channel is a contiguous,
+// 32-byte aligned run of L doubles and a whole support row is RL = C*Lp doubles.
+#pragma once
+
+#include "pffrg_device.cuh"
+
+namespace pffrg
+{
+	constexpr double TWO_PI = 2.0 * 3.14159265358979323846;
+
+	struct Problem
+	{
+		int nw, L, Lp, RL, nf;
+		const double *mesh;      // [nw]
+		const int *sites_rid;    // [L]
+		const int *inv_rid;      // [L]
+		const int *sites_perm;   // [L] packed 2 bits per spin component
+		const int *inv_perm;     // [L]
+		const int4 *rpa_tasks;   // {rid, pairBegin, pairEnd, 0}, grouped by RPA slot
+		const int *rpa_slot_off; // [nslots + 1]
+		const uint2 *rpa_pairs;  // x: r1 | r2<<8 | perm1<<16 | perm2<<22 | newGroup<<31 ; y: multiplicity
+		int nrange;
+		const int *rng_fwd;      // [nrange]
+		const int *rng_inv;      // [nrange]
+		double spin;
+	};
+
+	struct NodeTable
+	{
+		int *count;   // [nw]
+		double *wp;   // [nw][stride] integration frequency w'
+		double *wt;   // [nw][stride] trapezoid weight x propagator factor
+		int stride;
+	};
+
+	// ================================================================================================================
+	// K2: self-energy flow. One CTA per mesh frequency, threads over the sites in range of the reference site.
+	// ================================================================================================================
+	// getValue(0, j, s, t, u, channel None) with the 8-support trilinear nesting of SU2VertexTwoParticle.hpp:270-297
+	// for a DIAGONAL channel c (density-like channels flip sign under s<->u, spin-like do not).
+	template <int CORE>
+	__device__ inline double vertexValueNone(const Problem &P, const double *mesh, const double *__restrict__ v4, int fwdRid, int invRid, double s, double t, double u, int c)
+	{
+		bool exchange = false;
+		if (CORE == TRI)
+		{
+			if (s < 0) { s = -s; exchange = !exchange; }
+			if (t < 0) t = -t;
+			if (u < 0) { u = -u; exchange = !exchange; }
+		}
+		else
+		{
+			if (s < 0 && u < 0) { s = -s; u = -u; }
+			else if (s < 0) { s = -s; exchange = true; }
+			else if (u < 0) { u = -u; exchange = true; }
+			if (t < 0) t = -t;
+		}
+		const int site = exchange ? invRid : fwdRid;
+		const bool densityLike = (CORE == SU2) ? (c == 1) : (CORE == XYZ ? (c == 3) : (c == 15));
+		int ls, us, lt, ut, lu, uu; double bs, bt, bu;
+		interpolateOffset(mesh, P.nw, s, ls, us, bs);
+		interpolateOffset(mesh, P.nw, t, lt, ut, bt);
+		interpolateOffset(mesh, P.nw, u, lu, uu, bu);
+		auto at = [&](int so, int to, int uo) -> double
+		{
+			int flags = 0;
+			int row = rowIndex(P.nw, so, to, uo, 0, flags);
+			double v = v4[(size_t)row * P.RL + c * P.Lp + site];
+			return (flags && densityLike) ? -v : v;
+		};
+		return (1 - bu) * ((1 - bt) * ((1 - bs) * at(ls, lt, lu) + bs * at(us, lt, lu)) + bt * ((1 - bs) * at(ls, ut, lu) + bs * at(us, ut, lu)))
+		     + bu * ((1 - bt) * ((1 - bs) * at(ls, lt, uu) + bs * at(us, lt, uu)) + bt * ((1 - bs) * at(ls, ut, uu) + bs * at(us, ut, uu)));
+	}
+
+	template <int CORE>
+	__global__ void __launch_bounds__(128) v2FlowKernel(Problem P, const double *__restrict__ v4, const double *__restrict__ v2, const double *cutoffPtr, double *__restrict__ v2flow)
+	{
+		extern __shared__ double smem[];
+		double *mesh = smem;           // [nw]
+		double *red = smem + P.nw;     // [blockDim]
+		for (int i = threadIdx.x; i < P.nw; i += blockDim.x) mesh[i] = P.mesh[i];
+		__syncthreads();
+		const double cutoff = *cutoffPtr;
+		const double w = mesh[blockIdx.x];
+		const int dens = CORE == SU2 ? 1 : (CORE == XYZ ? 3 : 15);
+
+		double sum = 0.0;
+		for (int j = threadIdx.x; j < P.nrange; j += blockDim.x)
+		{
+			sum += vertexValueNone<CORE>(P, mesh, v4, P.rng_fwd[j], P.rng_inv[j], w + cutoff, 0.0, w - cutoff, dens);
+			sum -= vertexValueNone<CORE>(P, mesh, v4, P.rng_fwd[j], P.rng_inv[j], w - cutoff, 0.0, w + cutoff, dens);
+		}
+		red[threadIdx.x] = sum;
+		__syncthreads();
+		for (int s = blockDim.x >> 1; s > 0; s >>= 1)
+		{
+			if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+			__syncthreads();
+		}
+		if (threadIdx.x == 0)
+		{
+			double value = 0.0;
+			auto local = [&](int c) { return vertexValueNone<CORE>(P, mesh, v4, 0, 0, w + cutoff, w - cutoff, 0.0, c) - vertexValueNone<CORE>(P, mesh, v4, 0, 0, w - cutoff, w + cutoff, 0.0, c); };
+			if (CORE == SU2)
+			{
+				value -= 4.0 * P.spin * red[0];
+				value += 0.75 * local(0);
+				value += local(1);
+			}
+			else
+			{
+				value -= 2.0 * red[0];
+				for (int k = 0; k < 4; ++k) value += local(CORE == XYZ ? k : 5 * k);
+			}
+			value /= (TWO_PI * (cutoff + selfEnergy(mesh, P.nw, v2, cutoff)));
+			v2flow[blockIdx.x] = value;
+		}
+	}
+
+	// ================================================================================================================
+	// K0: quadrature node table. For every mesh frequency x (the transfer frequency of a channel) the list of integration
+	// frequencies w' and total weights W such that the channel's contribution is sum_k W_k * Kernel(w'_k):
+	//   conventional single-scale terms  P(L, L+x), [x > 2L] P(L, L-x)                       SU2FrgCore.cpp:351-371
+	//   three Katanin segments           0.5 * trapezoid weight * Sdot(w')/(G(w')^2 G(x+w'))  :343-347,:378-392
+	// The node enumeration follows ImplicitIntegrator::integrateWithObscure{Right,,Left}Boundar{y,ies}.
+	// ================================================================================================================
+	__global__ void nodeTableKernel(Problem P, NodeTable N, const double *__restrict__ v2, const double *__restrict__ v2flow, const double *cutoffPtr)
+	{
+		extern __shared__ double smem[];
+		double *mesh = smem, *sv2 = smem + P.nw, *sflow = smem + 2 * P.nw;
+		for (int i = threadIdx.x; i < P.nw; i += blockDim.x) { mesh[i] = P.mesh[i]; sv2[i] = v2[i]; sflow[i] = v2flow[i]; }
+		__syncthreads();
+		const int xi = blockIdx.x * blockDim.x + threadIdx.x;
+		if (xi >= P.nw) return;
+		const int nw = P.nw;
+		const double cutoff = *cutoffPtr, x = mesh[xi];
+		double *wp = N.wp + (size_t)xi * N.stride, *wt = N.wt + (size_t)xi * N.stride;
+		int n = 0;
+		auto G = [&](double w) { return w + selfEnergy(mesh, nw, sv2, w); };
+		auto bubble = [&](double w1, double w2) { return 1.0 / (G(w1) * G(w2)); };
+		auto katanin = [&](double w1, double w2) { double d = G(w1); return selfEnergy(mesh, nw, sflow, w1) / (d * d * G(w2)); };
+		auto emitK = [&](double w, double weight) { wp[n] = w; wt[n] = weight * katanin(w, x + w); ++n; };
+		auto MV = [&](int i) { return meshValue(mesh, i); };
+
+		wp[n] = cutoff; wt[n] = bubble(cutoff, cutoff + x); ++n;
+		if (x > 2.0 * cutoff) { wp[n] = -cutoff; wt[n] = bubble(cutoff, cutoff - x); ++n; }
+
+		// [-w_max, -(x+L)]  integrateWithObscureRightBoundary, Integrator.hpp:188-225
+		if (-(x + cutoff) > -mesh[nw - 1])
+		{
+			const double max = -(x + cutoff);
+			int umin = -nw;
+			const int umax = meshLesser(mesh, nw, max);
+			if (umin != umax)
+			{
+				emitK(MV(umin), 0.5 * (MV(umin + 1) - MV(umin)));
+				while (++umin != umax) emitK(MV(umin), 0.5 * (MV(umin + 1) - MV(umin - 1)));
+				emitK(MV(umin), 0.5 * (max - MV(umin - 1)));
+				emitK(max, 0.5 * (max - MV(umin)));
+			}
+			else
+			{
+				emitK(max, 0.5 * (max - MV(umin)));
+				emitK(MV(umin), 0.5 * (max - MV(umin)));
+			}
+		}
+		// [L-x, -L]  integrateWithObscureBoundaries, Integrator.hpp:239-287
+		if (x - cutoff > cutoff)
+		{
+			const double min = cutoff - x, max = -cutoff;
+			int umin = meshGreater(mesh, nw, min);
+			const int umax = meshLesser(mesh, nw, max);
+			if (umax >= umin)
+			{
+				emitK(min, 0.5 * (MV(umin) - min));
+				if (umax != umin)
+				{
+					emitK(MV(umin), 0.5 * (MV(umin + 1) - min));
+					while (++umin != umax) emitK(MV(umin), 0.5 * (MV(umin + 1) - MV(umin - 1)));
+					emitK(MV(umin), 0.5 * (max - MV(umin - 1)));
+				}
+				else emitK(MV(umin), 0.5 * (max - min));
+				emitK(max, 0.5 * (max - MV(umin)));
+			}
+			else
+			{
+				emitK(max, 0.5 * (max - min));
+				emitK(min, 0.5 * (max - min));
+			}
+		}
+		// [L, w_max]  integrateWithObscureLeftBoundary, Integrator.hpp:138-174
+		if (cutoff < mesh[nw - 1])
+		{
+			const double min = cutoff;
+			const int max = nw - 1;
+			int umin = meshGreater(mesh, nw, min);
+			if (umin != max)
+			{
+				emitK(min, 0.5 * (MV(umin) - min));
+				emitK(MV(umin), 0.5 * (MV(umin + 1) - min));
+				while (++umin != max) emitK(MV(umin), 0.5 * (MV(umin + 1) - MV(umin - 1)));
+				emitK(MV(umin), 0.5 * (MV(umin) - MV(umin - 1)));
+			}
+			else
+			{
+				emitK(min, 0.5 * (MV(umin) - min));
+				emitK(MV(umin), 0.5 * (MV(umin) - min));
+			}
+		}
+		N.count[xi] = n;
+	}
+
+	// ================================================================================================================
+	// K1: vertex flow. One CTA per work item (s,t,u). Threads are organised as k groups of L: thread (g, j) owns
+	// representative site j and evaluates the quadrature nodes g, g+k, ... of the current batch:
+	//   phase 0   one thread per (node, access buffer): sector map + two lerps -> table in shared memory
+	//   phase 0b  (t channel) site-0 values of the four u-type buffers          SU2FrgCore.cpp:269-284
+	//   phase 1   gather 4 buffers x 4 supports x C channels for site j (coalesced across j), bilinear forms in registers,
+	//             weighted accumulation into per-thread registers; t channel: stage the RPA operands, transposed, in smem
+	//   phase 2   (t channel) RPA lattice sum: lanes = nodes, warps/sub-warps = representative sites; operand A is held in a
+	//             register per (rid, r1) group, pairs carry integer multiplicities                :250-266
+	//   epilogue  deterministic reduction over groups, 1/2pi, NaN flag, coalesced store of the item's C x L flow values
+	// ================================================================================================================
+	struct FlowConfig
+	{
+		int groups;      // k
+		int nslots;      // RPA slots = warps * (32 / NB)
+		int smemBytes;
+	};
+
+	template <int CORE> struct RpaStage { static constexpr int buffers = (CORE == TRI) ? 4 : 2; };
+
+	__host__ __device__ inline size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+	template <int CORE, int NB>
+	struct FlowSmem
+	{
+		static constexpr int C = channelsOf(CORE);
+		static constexpr int NBP = NB + 1;
+		size_t mesh, bw, bW, ab, loc, st, part, rpa, total;
+		__host__ __device__ FlowSmem(int nw, int L, int groups)
+		{
+			size_t o = 0;
+			mesh = o; o += sizeof(double) * nw;
+			bw = o; o += sizeof(double) * NB;
+			bW = o; o += sizeof(double) * NB;
+			ab = o; o += sizeof(AccessBuffer) * NB * 8;
+			loc = o; o += sizeof(double) * NB * 4 * C;
+			st = o; o += sizeof(double) * RpaStage<CORE>::buffers * C * L * NBP;
+			part = o; o += sizeof(double) * groups * C * L;
+			rpa = o; o += sizeof(double) * C * L;
+			total = alignUp(o, 16);
+		}
+	};
+
+	// gather one access buffer for site j: out[c] = sum_k sign_k(c) w_k v4[row_k][stored(c)][site]
+	template <int CORE>
+	__device__ __forceinline__ void gatherSite(const Problem &P, const double *__restrict__ v4, const AccessBuffer &ab, int siteFwd, int siteInv, int permFwd, int permInv, double (&out)[channelsOf(CORE)])
+	{
+		constexpr int C = channelsOf(CORE);
+		const int flags = ab.flags;
+		const bool exchange = flags & AB_EXCHANGE;
+		const int site = exchange ? siteInv : siteFwd;
+		const int perm = exchange ? permInv : permFwd;
+		#pragma unroll
+		for (int c = 0; c < C; ++c) out[c] = 0.0;
+		#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			// weight of the support for channels that are even / odd under the s<->u frequency exchange
+			const double wEven = ab.w[k];
+			const double wOdd = abSwapped(flags, k) ? -wEven : wEven;
+			const double *base = v4 + (size_t)ab.row[k] * P.RL + site;
+			#pragma unroll
+			for (int c = 0; c < C; ++c)
+			{
+				// SU2/XYZ: only the density channel is odd (SU2VertexTwoParticle.hpp:622-625); TRI: factor -zeta of the second
+				// (first, if exchanged) spin index (TRIVertexTwoParticle.hpp:649-657), i.e. odd iff that index is the density one
+				const bool odd = (CORE == SU2) ? (c == 1) : (CORE == XYZ ? (c == 3) : (exchange ? ((c >> 2) == 3) : ((c & 3) == 3)));
+				const int sc = storedChannel<CORE>(flags, c, perm);
+				out[c] += (odd ? wOdd : wEven) * __ldg(base + sc * P.Lp);
+			}
+		}
+		if (CORE == TRI)
+		{
+			// zeta_mu * zeta_nu for every sign change of t or u (TRIVertexTwoParticle.hpp:414-443): flips exactly the mixed spin-density channels
+			if (flags & AB_TZ)
+			{
+				#pragma unroll
+				for (int c = 0; c < C; ++c) if (((c >> 2) == 3) != ((c & 3) == 3)) out[c] = -out[c];
+			}
+		}
+	}
+
+	// frequency arguments of access buffer b of channel ch at integration frequency wp
+	// S: SU2FrgCore.cpp:202-206, T: :233-239 (+ locals :269-275), U: :309-313
+	struct ItemFrequencies { double s, t, u, w1p, w1, w2p, w2; };
+
+	template <int CORE>
+	__device__ __forceinline__ void bufferArguments(const ItemFrequencies &f, int ch, int b, double wp, double &as, double &at, double &au, int &exact)
+	{
+		if (ch == CH_S)
+		{
+			exact = CH_S; as = f.s;
+			switch (b)
+			{
+			case 0: at = -f.w1 - wp; au = -f.w2 - wp; break;
+			case 1: at = f.w1p + wp; au = -f.w2p - wp; break;
+			case 2: at = f.w2 + wp; au = f.w1 + wp; break;
+			default: at = -f.w2p - wp; au = f.w1p + wp; break;
+			}
+		}
+		else if (ch == CH_U)
+		{
+			exact = CH_U; au = f.u;
+			switch (b)
+			{
+			case 0: as = f.w1 + wp; at = wp - f.w2p; break;
+			case 1: as = f.w1p + wp; at = f.w2 - wp; break;
+			case 2: as = f.w2p - wp; at = -f.w1 - wp; break;
+			default: as = f.w2 - wp; at = f.w1p + wp; break;
+			}
+		}
+		else
+		{
+			switch (b)
+			{
+			case 0: exact = CH_T; as = f.w1 - wp; at = f.t; au = f.w1p + wp; break;
+			case 1: exact = CH_T; as = f.w2p - wp; at = f.t; au = -f.w2 - wp; break;
+			case 2: exact = CH_T; as = f.w1p + wp; at = f.t; au = f.w1 - wp; break;
+			case 3: exact = CH_T; as = f.w2 + wp; at = f.t; au = wp - f.w2p; break;
+			// site-0 buffers, paired with gathered buffers 0..3 in this order
+			case 4: exact = CH_U; as = f.w2p - wp; at = -f.w2 - wp; au = f.t; break;
+			case 5: exact = CH_U; as = f.w1 - wp; at = -f.w1p - wp; au = -f.t; break;
+			case 6: exact = CH_U; as = f.w2 + wp; at = wp - f.w2p; au = f.t; break;
+			default: exact = CH_U; as = f.w1p + wp; at = wp - f.w1; au = -f.t; break;
+			}
+		}
+	}
+
+	// bilinear forms of the s and u kernels; A[b][c] gathered buffers at one site
+	template <int CORE>
+	__device__ __forceinline__ void ladderTerms(int ch, const double (&A)[4][channelsOf(CORE)], double (&K)[channelsOf(CORE)])
+	{
+		if (CORE == SU2)
+		{
+			// SU2FrgCore.cpp:216-226 (s) and :323-333 (u); the u channel's overall minus sign (:366,370,376) is applied by the caller
+			const double ss = A[0][0] * A[1][0] + A[2][0] * A[3][0];
+			const double cross = A[0][1] * A[1][0] + A[2][1] * A[3][0] + A[0][0] * A[1][1] + A[2][0] * A[3][1];
+			K[0] = (ch == CH_S ? -0.5 : 0.5) * ss + cross;
+			K[1] = 0.1875 * ss + A[0][1] * A[1][1] + A[2][1] * A[3][1];
+		}
+		else if (CORE == XYZ)
+		{
+			// XYZFrgCore.cpp:240-274 (s) and :437-471 (u, which carries its own signs)
+			#pragma unroll
+			for (int a = 0; a < 3; ++a)
+			{
+				const int b = (a + 1) % 3, c = (a + 2) % 3;
+				double diag = 0.0, crs = 0.0;
+				#pragma unroll
+				for (int p = 0; p < 4; p += 2)
+				{
+					diag += A[p][3] * A[p + 1][a] + A[p][a] * A[p + 1][3];
+					crs += A[p][c] * A[p + 1][b] + A[p][b] * A[p + 1][c];
+				}
+				K[a] = (ch == CH_S) ? (diag - crs) : (-diag - crs);
+			}
+			double d = 0.0;
+			#pragma unroll
+			for (int p = 0; p < 4; p += 2) d += A[p][3] * A[p + 1][3] + A[p][0] * A[p + 1][0] + A[p][1] * A[p + 1][1] + A[p][2] * A[p + 1][2];
+			K[3] = (ch == CH_S) ? d : -d;
+		}
+	}
+
+	// site-0 ("chalice") terms of the t kernel: SU2FrgCore.cpp:286-302, XYZFrgCore.cpp:350-416; B[n][c] local values
+	template <int CORE>
+	__device__ __forceinline__ void chaliceTerms(const double (&A)[4][channelsOf(CORE)], const double *B /* [4][C] */, double (&K)[channelsOf(CORE)])
+	{
+		constexpr int C = channelsOf(CORE);
+		#pragma unroll
+		for (int c = 0; c < C; ++c) K[c] = 0.0;
+		if (CORE == SU2)
+		{
+			#pragma unroll
+			for (int n = 0; n < 4; ++n)
+			{
+				const double bs = B[n * C + 0], bd = B[n * C + 1];
+				K[0] += A[n][0] * (0.25 * bs - bd);
+				K[1] += A[n][1] * (-bd - 0.75 * bs);
+			}
+		}
+		else if (CORE == XYZ)
+		{
+			#pragma unroll
+			for (int n = 0; n < 4; ++n)
+			{
+				const double bx = B[n * C + 0], by = B[n * C + 1], bz = B[n * C + 2], bd = B[n * C + 3];
+				K[0] += A[n][0] * (-bd + by + bz - bx);
+				K[1] += A[n][1] * (-bd + bx + bz - by);
+				K[2] += A[n][2] * (-bd + bx + by - bz);
+				K[3] += A[n][3] * (-bd - bx - by - bz);
+			}
+		}
+	}
+
+	template <int CORE, int NB>
+	__global__ void v4FlowKernel(Problem P, NodeTable N, FlowConfig cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
+	{
+		constexpr int C = channelsOf(CORE);
+		constexpr int NBP = NB + 1;
+		constexpr int SUBS = 32 / NB; // RPA sub-warps per warp
+		extern __shared__ __align__(16) unsigned char smemRaw[];
+		const FlowSmem<CORE, NB> lay(P.nw, P.L, cfg.groups);
+		double *mesh = reinterpret_cast<double *>(smemRaw + lay.mesh);
+		double *bw = reinterpret_cast<double *>(smemRaw + lay.bw);
+		double *bW = reinterpret_cast<double *>(smemRaw + lay.bW);
+		AccessBuffer *abTable = reinterpret_cast<AccessBuffer *>(smemRaw + lay.ab);
+		double *loc = reinterpret_cast<double *>(smemRaw + lay.loc);
+		double *st = reinterpret_cast<double *>(smemRaw + lay.st);
+		double *part = reinterpret_cast<double *>(smemRaw + lay.part);
+		double *rpaOut = reinterpret_cast<double *>(smemRaw + lay.rpa);
+
+		const int tid = threadIdx.x, nthreads = blockDim.x;
+		const int L = P.L, nw = P.nw;
+		for (int i = tid; i < nw; i += nthreads) mesh[i] = P.mesh[i];
+		for (int i = tid; i < C * L; i += nthreads) rpaOut[i] = 0.0;
+
+		// work item -> (s, t, u), expandIterator SU2VertexTwoParticle.hpp:136-158
+		const int item = itemBegin + blockIdx.x;
+		const int su = item / nw, ti = item - su * nw;
+		int so = (int)((sqrt(8.0 * su + 1.0) - 1.0) * 0.5);
+		while ((so + 1) * (so + 2) / 2 <= su) ++so;
+		while (so * (so + 1) / 2 > su) --so;
+		const int uo = su - so * (so + 1) / 2;
+		__syncthreads();
+		ItemFrequencies f;
+		f.s = mesh[so]; f.t = mesh[ti]; f.u = mesh[uo];
+		f.w1p = 0.5 * (f.s + f.t + f.u); f.w1 = 0.5 * (f.s - f.t + f.u); f.w2p = 0.5 * (f.s - f.t - f.u); f.w2 = 0.5 * (f.s + f.t - f.u);
+
+		const int g = tid / L, j = tid - g * L;
+		const bool worker = g < cfg.groups;
+		int siteFwd = 0, siteInv = 0, permFwd = PERM_IDENTITY, permInv = PERM_IDENTITY;
+		if (worker) { siteFwd = P.sites_rid[j]; siteInv = P.inv_rid[j]; permFwd = P.sites_perm[j]; permInv = P.inv_perm[j]; }
+
+		double acc[C];
+		#pragma unroll
+		for (int c = 0; c < C; ++c) acc[c] = 0.0;
+
+		const int xIndex[3] = { so, ti, uo };
+		// channel order S, U, T keeps the shared-memory heavy t channel last
+		#pragma unroll 1
+		for (int pass = 0; pass < 3; ++pass)
+		{
+			const int ch = pass == 0 ? CH_S : (pass == 1 ? CH_U : CH_T);
+			const int xi = xIndex[ch];
+			const int nNodes = N.count[xi];
+			const double *nodeW = N.wp + (size_t)xi * N.stride, *nodeWt = N.wt + (size_t)xi * N.stride;
+			const int nbuf = ch == CH_T ? 8 : 4;
+			// SU2: the u channel enters with a minus sign (SU2FrgCore.cpp:366,370,376); XYZ/TRI kernels carry it themselves
+			const double chSign = (CORE == SU2 && ch == CH_U) ? -1.0 : 1.0;
+
+			#pragma unroll 1
+			for (int b0 = 0; b0 < nNodes; b0 += NB)
+			{
+				const int nb = min(NB, nNodes - b0);
+				__syncthreads(); // previous batch fully consumed
+				// ---- phase 0: access buffers
+				for (int idx = tid; idx < nb * nbuf; idx += nthreads)
+				{
+					const int node = idx / nbuf, b = idx - node * nbuf;
+					const double wp = nodeW[b0 + node];
+					if (b == 0) { bw[node] = wp; bW[node] = chSign * nodeWt[b0 + node]; }
+					double as, at, au; int exact;
+					bufferArguments<CORE>(f, ch, b, wp, as, at, au, exact);
+					makeAccessBuffer<CORE>(mesh, nw, as, at, au, exact, abTable[node * 8 + b]);
+				}
+				__syncthreads();
+				if (ch == CH_T)
+				{
+					// ---- phase 0b: site-0 values of buffers 4..7 (getValueLocal)
+					for (int idx = tid; idx < nb * 4 * C; idx += nthreads)
+					{
+						const int node = idx / (4 * C), r = idx - node * 4 * C, n = r / C, c = r - n * C;
+						const AccessBuffer &ab = abTable[node * 8 + 4 + n];
+						const int sc = storedChannel<CORE>(ab.flags, c, PERM_IDENTITY);
+						double v = 0.0;
+						#pragma unroll
+						for (int k = 0; k < 4; ++k) v += supportSign<CORE>(ab.flags, k, c) * ab.w[k] * __ldg(v4 + (size_t)ab.row[k] * P.RL + sc * P.Lp);
+						loc[idx] = v;
+					}
+					__syncthreads();
+				}
+				// ---- phase 1: gathers + bilinear forms
+				if (worker)
+				{
+					for (int node = g; node < nb; node += cfg.groups)
+					{
+						double A[4][C];
+						#pragma unroll
+						for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, abTable[node * 8 + b], siteFwd, siteInv, permFwd, permInv, A[b]);
+						const double W = bW[node];
+						double K[C];
+						if (ch != CH_T)
+						{
+							ladderTerms<CORE>(ch, A, K);
+						}
+						else
+						{
+							chaliceTerms<CORE>(A, loc + node * 4 * C, K);
+							// stage the RPA operands transposed: st[buffer][c][site][node]
+							if (CORE == SU2)
+							{
+								// operands are buffers 2 and 3; prefactors 2S (spin) and 8S (density), SU2FrgCore.cpp:257-266
+								st[((0 * C + 0) * L + j) * NBP + node] = W * 2.0 * P.spin * A[2][0];
+								st[((0 * C + 1) * L + j) * NBP + node] = W * 8.0 * P.spin * A[2][1];
+								st[((1 * C + 0) * L + j) * NBP + node] = A[3][0];
+								st[((1 * C + 1) * L + j) * NBP + node] = A[3][1];
+							}
+							else if (CORE == XYZ)
+							{
+								// operands are buffers 0 and 1, prefactor 4, XYZFrgCore.cpp:297-322
+								#pragma unroll
+								for (int c = 0; c < C; ++c)
+								{
+									st[((0 * C + c) * L + j) * NBP + node] = W * 4.0 * A[0][c];
+									st[((1 * C + c) * L + j) * NBP + node] = A[1][c];
+								}
+							}
+						}
+						#pragma unroll
+						for (int c = 0; c < C; ++c) acc[c] += W * K[c];
+					}
+				}
+				if (ch == CH_T)
+				{
+					__syncthreads();
+					// ---- phase 2: RPA lattice sum  R_c[rid] = sum_i A_c[rid1_i] * B_c[rid2_i]
+					const int lane = tid & 31, wid = tid >> 5;
+					const int sub = lane / NB, node = lane - sub * NB;
+					const int slot = wid * SUBS + sub;
+					const bool active = node < nb;
+					const unsigned subMask = (NB == 32) ? 0xffffffffu : (((1u << (NB & 31)) - 1u) << (sub * NB));
+					if (slot < cfg.nslots)
+					{
+						for (int ti2 = P.rpa_slot_off[slot]; ti2 < P.rpa_slot_off[slot + 1]; ++ti2)
+						{
+							const int4 task = P.rpa_tasks[ti2];
+							double r[C], a[C], ts[C];
+							#pragma unroll
+							for (int c = 0; c < C; ++c) { r[c] = 0.0; a[c] = 0.0; ts[c] = 0.0; }
+							if (active)
+							{
+								for (int i = task.y; i < task.z; ++i)
+								{
+									const uint2 pw = __ldg(P.rpa_pairs + i);
+									if (pw.x >> 31)
+									{
+										const int r1 = pw.x & 0xff, p1 = (pw.x >> 16) & 0x3f;
+										#pragma unroll
+										for (int c = 0; c < C; ++c)
+										{
+											r[c] += a[c] * ts[c]; ts[c] = 0.0;
+											const int sc = (CORE == XYZ && c < 3) ? ((p1 >> (2 * c)) & 3) : c;
+											a[c] = st[((0 * C + sc) * L + r1) * NBP + node];
+										}
+									}
+									const int r2 = (pw.x >> 8) & 0xff, p2 = (pw.x >> 22) & 0x3f;
+									const double m = (double)(int)pw.y;
+									#pragma unroll
+									for (int c = 0; c < C; ++c)
+									{
+										const int sc = (CORE == XYZ && c < 3) ? ((p2 >> (2 * c)) & 3) : c;
+										ts[c] += m * st[((1 * C + sc) * L + r2) * NBP + node];
+									}
+								}
+								#pragma unroll
+								for (int c = 0; c < C; ++c) r[c] += a[c] * ts[c];
+							}
+							__syncwarp(subMask);
+							#pragma unroll
+							for (int c = 0; c < C; ++c)
+							{
+								double v = r[c];
+								#pragma unroll
+								for (int o = NB >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(subMask, v, o);
+								if (node == 0) rpaOut[c * L + task.x] += v;
+							}
+						}
+					}
+				}
+			}
+		}
+
+		// ---- epilogue
+		__syncthreads();
+		if (worker)
+		{
+			#pragma unroll
+			for (int c = 0; c < C; ++c) part[(g * C + c) * L + j] = acc[c];
+		}
+		__syncthreads();
+		bool bad = false;
+		for (int e = tid; e < C * L; e += nthreads)
+		{
+			double v = rpaOut[e];
+			for (int gg = 0; gg < cfg.groups; ++gg) v += part[gg * C * L + e];
+			v /= TWO_PI;
+			const int c = e / L, jj = e - c * L;
+			flow[(size_t)item * P.RL + c * P.Lp + jj] = v;
+			bad |= (v != v);
+		}
+		if (bad) atomicOr(nanFlag, 1);
+	}
+
+	// ================================================================================================================
+	// K3: Euler update, and the reference-layout <-> device-layout transposes used by set_state / get_state / get_flow
+	// ================================================================================================================
+	__global__ void eulerKernel(double *__restrict__ x, const double *__restrict__ flow, size_t n, const double *cutoffPtr, double newCutoff)
+	{
+		const double step = newCutoff - *cutoffPtr;
+		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] += step * flow[i];
+	}
+
+	__global__ void setScalarKernel(double *p, double v) { *p = v; }
+
+	// reference array (one channel, [row][L], or TRI [row][16][L]) -> device layout; T = float or double
+	template <typename T>
+	__global__ void importKernel(const T *__restrict__ src, double *__restrict__ dst, size_t rows, int L, int Lp, int RL, int cFirst, int cCount)
+	{
+		const size_t n = rows * cCount * L;
+		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		{
+			const size_t row = i / ((size_t)cCount * L);
+			const int r = (int)(i - row * cCount * L), c = r / L, j = r - c * L;
+			dst[row * RL + (size_t)(cFirst + c) * Lp + j] = (double)src[i];
+		}
+	}
+	template <typename T>
+	__global__ void exportKernel(const double *__restrict__ src, T *__restrict__ dst, size_t rows, int L, int Lp, int RL, int cFirst, int cCount)
+	{
+		const size_t n = rows * cCount * L;
+		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		{
+			const size_t row = i / ((size_t)cCount * L);
+			const int r = (int)(i - row * cCount * L), c = r / L, j = r - c * L;
+			dst[i] = (T)src[row * RL + (size_t)(cFirst + c) * Lp + j];
+		}
+	}
+	template <typename T>
+	__global__ void convertKernel(const T *__restrict__ src, double *__restrict__ dst, int n) { for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (double)src[i]; }
+	template <typename T>
+	__global__ void convertBackKernel(const double *__restrict__ src, T *__restrict__ dst, int n) { for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (T)src[i]; }
+}

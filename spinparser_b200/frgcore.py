@@ -1,0 +1,257 @@
+"""Host-side mirror of SpinParser's flow-core plugin surface on top of ``libpffrg``.
+
+Names, argument meaning and error behaviour follow the reference (file:line relative to the SpinParser tree):
+
+* :class:`FrgCoreFactory` -- ``FrgCoreFactory::newFrgCore(identifier, ...)``, ``src/FrgCoreFactory.cpp:25-51``: the string
+  identifiers ``"SU2" | "XYZ" | "TRI"``; any other identifier raises (the reference throws
+  ``Exception::Type::InitializationError``).
+* :class:`FrgCore` -- ``src/FrgCore.hpp:29-141``: ``computeStep()``, ``finalizeStep(newCutoff)``, ``flowingFunctional()``,
+  ``flow()``.
+* :class:`EffectiveAction` -- ``src/EffectiveAction.hpp:40-59`` + ``src/SU2/SU2EffectiveAction.hpp:19-233``: ``cutoff``, the
+  vertex arrays in the reference's memory layout, ``isDiverged()``.
+* :class:`ProblemTables` -- what the hot path reads from ``FrgCommon::lattice()`` / ``FrgCommon::frequency()``
+  (``src/FrgCommon.hpp:26-49``), produced by the reference's own ``LatticeModelFactory`` on the host.
+
+All numerics run on the GPU inside ``libpffrg.so``; this file only moves buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Mapping, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import PffrgError, check, lib
+
+N_ARRAYS = {"SU2": 2, "XYZ": 4, "TRI": 1}
+N_CHANNELS = {"SU2": 2, "XYZ": 4, "TRI": 16}
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+@dataclass
+class ProblemTables:
+    """Frequency mesh and symmetry-reduced lattice tables (inputs of the hot path, uploaded once)."""
+
+    frequencies: np.ndarray            # [Nw] FrequencyDiscretization::_data (positive half)
+    sites_rid: np.ndarray              # [L]   Lattice::getSites()
+    sites_perm: np.ndarray             # [L,3]
+    inverted_rid: np.ndarray           # [L]   Lattice::getInvertedSites()
+    inverted_perm: np.ndarray          # [L,3]
+    overlap_offsets: np.ndarray        # [L+1] CSR of Lattice::getOverlap(rid)
+    overlap_rid1: np.ndarray
+    overlap_rid2: np.ndarray
+    overlap_perm1: np.ndarray          # [n,3]
+    overlap_perm2: np.ndarray          # [n,3]
+    range_fwd_rid: np.ndarray          # [n_range] symmetryTransform(zero, j)
+    range_inv_rid: np.ndarray          # [n_range] symmetryTransform(j, zero)
+    extra: Dict[str, np.ndarray] = field(default_factory=dict)
+
+    @classmethod
+    def from_pfd(cls, d: Mapping[str, np.ndarray]) -> "ProblemTables":
+        """Build from a PFD dump written by the host side (keys ``frequency`` and ``lattice/*``)."""
+        return cls(
+            frequencies=np.ascontiguousarray(d["frequency"], dtype=np.float64),
+            sites_rid=_i32(d["lattice/sites_rid"]), sites_perm=_i32(d["lattice/sites_perm"]),
+            inverted_rid=_i32(d["lattice/invertedSites_rid"]), inverted_perm=_i32(d["lattice/invertedSites_perm"]),
+            overlap_offsets=_i32(d["lattice/overlap_offsets"]),
+            overlap_rid1=_i32(d["lattice/overlap_rid1"]), overlap_rid2=_i32(d["lattice/overlap_rid2"]),
+            overlap_perm1=_i32(d["lattice/overlap_perm1"]), overlap_perm2=_i32(d["lattice/overlap_perm2"]),
+            range_fwd_rid=_i32(d["lattice/range0_fwd_rid"]), range_inv_rid=_i32(d["lattice/range0_inv_rid"]),
+        )
+
+    @property
+    def n_frequencies(self) -> int:
+        return int(self.frequencies.shape[0])
+
+    @property
+    def n_sites(self) -> int:
+        return int(self.sites_rid.shape[0])
+
+    @property
+    def n_items(self) -> int:
+        nw = self.n_frequencies
+        return nw * nw * (nw + 1) // 2
+
+
+class EffectiveAction:
+    """Host copy of a vertex set in the reference's memory layout (float64 or float32)."""
+
+    def __init__(self, core: str, n_frequencies: int, n_sites: int, dtype=np.float64):
+        self.core = core
+        self.cutoff = 0.0
+        nf = n_frequencies * n_frequencies * (n_frequencies + 1) // 2
+        length = nf * n_sites * (16 if core == "TRI" else 1)
+        self.v2 = np.zeros(n_frequencies, dtype=dtype)
+        self.v4 = [np.zeros(length, dtype=dtype) for _ in range(N_ARRAYS[core])]
+
+    def isDiverged(self) -> bool:
+        """NaN scan, ``SU2EffectiveAction::isDiverged`` (src/SU2/SU2EffectiveAction.hpp:212-230)."""
+        return bool(np.isnan(self.v2).any() or any(np.isnan(a).any() for a in self.v4))
+
+
+class FrgCore:
+    """One flow core bound to one GPU (``FrgCore``, src/FrgCore.hpp:29-141)."""
+
+    def __init__(self, identifier: str, tables: ProblemTables, options: Optional[Mapping[str, str]] = None, device: int = 0):
+        if identifier not in _capi.CORE_IDS:
+            raise PffrgError(-1, f"FRG core identifier '{identifier}' is invalid.")
+        self.identifier = identifier
+        self.tables = tables
+        # core options as in src/SU2/SU2FrgCore.cpp:20-29 and src/XYZ/XYZFrgCore.cpp:22-27
+        self.spinLength = 0.5
+        self.normalization = None
+        for key, value in (options or {}).items():
+            if key == "spin" and identifier == "SU2":
+                self.spinLength = float(value)
+            elif key == "normalization":
+                self.normalization = float(value)
+            else:
+                raise PffrgError(-1, f"Unknown spin model option '{key}'.")
+        if self.normalization is None:
+            self.normalization = 2.0 * self.spinLength if identifier == "SU2" else 1.0
+
+        t = tables
+        self._keep = t  # the descriptor borrows the numpy buffers during create only
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        desc = _capi.Desc(
+            _capi.ABI_VERSION, _capi.CORE_IDS[identifier],
+            t.n_frequencies, t.frequencies.ctypes.data_as(C.POINTER(C.c_double)),
+            t.n_sites, ip(t.sites_rid), ip(t.sites_perm), ip(t.inverted_rid), ip(t.inverted_perm),
+            ip(t.overlap_offsets), ip(t.overlap_rid1), ip(t.overlap_rid2), ip(t.overlap_perm1), ip(t.overlap_perm2),
+            len(t.range_fwd_rid), ip(t.range_fwd_rid), ip(t.range_inv_rid),
+            float(self.spinLength), int(device),
+        )
+        handle = C.c_void_p()
+        check(lib.pffrg_create(C.byref(desc), C.byref(handle)))
+        self._h = handle
+        self.n_arrays = lib.pffrg_num_vertex_arrays(self._h)
+        self.array_length = int(lib.pffrg_vertex_array_length(self._h))
+        self.n_items = int(lib.pffrg_num_items(self._h))
+        self.diverged = False
+
+    # ---- lifetime ------------------------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.pffrg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- multi-GPU ---------------------------------------------------------------------------------------------------
+    @staticmethod
+    def uniqueId() -> bytes:
+        buf = C.create_string_buffer(_capi.UNIQUE_ID_BYTES)
+        check(lib.pffrg_comm_unique_id(buf))
+        return buf.raw
+
+    def initCommunicator(self, unique_id: bytes, rank: int, n_ranks: int) -> None:
+        buf = C.create_string_buffer(unique_id, _capi.UNIQUE_ID_BYTES)
+        check(lib.pffrg_comm_init(self._h, buf, rank, n_ranks))
+
+    def itemRange(self):
+        b, e = C.c_int64(), C.c_int64()
+        check(lib.pffrg_item_range(self._h, C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def setItemRange(self, begin: int, end: int) -> None:
+        check(lib.pffrg_set_item_range(self._h, begin, end))
+
+    # ---- state -----------------------------------------------------------------------------------------------------
+    def _ptrs(self, arrays: Sequence[np.ndarray]):
+        if len(arrays) != self.n_arrays:
+            raise PffrgError(-1, f"expected {self.n_arrays} vertex arrays, got {len(arrays)}")
+        for a in arrays:
+            if a.size != self.array_length or not a.flags.c_contiguous:
+                raise PffrgError(-1, "vertex array has the wrong size or is not contiguous")
+        return (C.c_void_p * self.n_arrays)(*[a.ctypes.data for a in arrays])
+
+    @staticmethod
+    def _dtype_code(dtype) -> int:
+        dtype = np.dtype(dtype)
+        if dtype == np.float64:
+            return _capi.F64
+        if dtype == np.float32:
+            return _capi.F32
+        raise PffrgError(-1, f"unsupported dtype {dtype}")
+
+    def setState(self, cutoff: float, v2: np.ndarray, v4: Sequence[np.ndarray]) -> None:
+        code = self._dtype_code(v2.dtype)
+        if any(a.dtype != v2.dtype for a in v4) or v2.size != self.tables.n_frequencies:
+            raise PffrgError(-1, "state arrays must share one dtype and match the mesh size")
+        check(lib.pffrg_set_state(self._h, float(cutoff), v2.ctypes.data, self._ptrs(v4), code))
+
+    def setInitialCondition(self, bare_couplings: Sequence[np.ndarray], cutoff: float) -> None:
+        """Initial condition of ``SU2EffectiveAction`` (src/SU2/SU2EffectiveAction.hpp:38-60) and the XYZ/TRI equivalents:
+        every frequency entry of channel c at representative r is ``bare_couplings[c][r]`` (already divided by the
+        normalization and, for XYZ/TRI, multiplied by 1/4); the self energy starts at zero."""
+        ea = EffectiveAction(self.identifier, self.tables.n_frequencies, self.tables.n_sites)
+        L = self.tables.n_sites
+        if self.identifier == "TRI":
+            block = np.zeros((16, L))
+            for c, values in enumerate(bare_couplings):
+                block[c] = values
+            ea.v4[0][:] = np.tile(block.reshape(-1), self.n_items)
+        else:
+            for c, values in enumerate(bare_couplings):
+                ea.v4[c][:] = np.tile(np.asarray(values, dtype=np.float64), self.n_items)
+        self.setState(cutoff, ea.v2, ea.v4)
+
+    def flowingFunctional(self, dtype=np.float64) -> EffectiveAction:
+        """Download the current state (``FrgCore::flowingFunctional``, src/FrgCore.hpp:93-96)."""
+        ea = EffectiveAction(self.identifier, self.tables.n_frequencies, self.tables.n_sites, dtype)
+        cutoff = C.c_double()
+        check(lib.pffrg_get_state(self._h, C.byref(cutoff), ea.v2.ctypes.data, self._ptrs(ea.v4), self._dtype_code(dtype)))
+        ea.cutoff = cutoff.value
+        return ea
+
+    def flow(self, dtype=np.float64) -> EffectiveAction:
+        """Download the flow of the last ``computeStep`` (``FrgCore::flow``, src/FrgCore.hpp:103-106)."""
+        ea = EffectiveAction(self.identifier, self.tables.n_frequencies, self.tables.n_sites, dtype)
+        check(lib.pffrg_get_flow(self._h, ea.v2.ctypes.data, self._ptrs(ea.v4), self._dtype_code(dtype)))
+        return ea
+
+    # ---- the two virtuals of the reference interface ---------------------------------------------------------------------
+    def computeStep(self) -> bool:
+        """``FrgCore::computeStep`` (src/SU2/SU2FrgCore.cpp:89-109). Returns the divergence flag the reference obtains from
+        ``_flow->isDiverged()`` right afterwards (src/SpinParser.cpp:151)."""
+        flag = C.c_int(0)
+        check(lib.pffrg_compute_step(self._h, C.byref(flag)))
+        self.diverged = bool(flag.value)
+        return self.diverged
+
+    def finalizeStep(self, newCutoff: float) -> None:
+        """``FrgCore::finalizeStep`` (src/SU2/SU2FrgCore.cpp:111-137)."""
+        check(lib.pffrg_finalize_step(self._h, float(newCutoff)))
+
+    def synchronize(self) -> None:
+        check(lib.pffrg_synchronize(self._h))
+
+    def stats(self) -> Dict[str, float]:
+        s = _capi.Stats()
+        check(lib.pffrg_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    @property
+    def stream(self) -> int:
+        return int(lib.pffrg_stream(self._h) or 0)
+
+
+class FrgCoreFactory:
+    """``FrgCoreFactory::newFrgCore`` (src/FrgCoreFactory.cpp:25-51)."""
+
+    @staticmethod
+    def newFrgCore(identifier: str, tables: ProblemTables, options: Optional[Mapping[str, str]] = None, device: int = 0) -> FrgCore:
+        return FrgCore(identifier, tables, options, device)
+
+
+def device_count() -> int:
+    return int(lib.pffrg_device_count())

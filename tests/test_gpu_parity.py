@@ -1,0 +1,60 @@
+"""Parity of the CUDA path (through the C ABI) against dumps of the unmodified reference in FP64 (tests/golden/*.f64.pfd)."""
+import numpy as np
+import pytest
+
+from conftest import assert_parity, dumped_steps, golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["su2_square_r3_nw10", "su2_kagome_r4_nw8", "su2_kagome_r7_nw6", "xyz_honeycomb_kitaev_r3_nw10", "xyz_kagome_r4_nw8"]
+
+
+def _core(d):
+    from spinparser_b200 import FrgCoreFactory, ProblemTables
+    name = bytes(d["core"]).decode()
+    opts = {"spin": str(float(d["spinLength"]))} if name == "SU2" else {}
+    return name, FrgCoreFactory.newFrgCore(name, ProblemTables.from_pfd(d), opts)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_one_step_flow_matches_reference(case):
+    d = golden(case)
+    name, core = _core(d)
+    n = core.n_arrays
+    cut = d["cutoff"]
+    for step in dumped_steps(d):
+        pre = f"step{step}/"
+        state = [np.ascontiguousarray(d[pre + f"state/v4_{c}"]) for c in range(n)]
+        core.setState(float(d[pre + "state/cutoff"]), np.ascontiguousarray(d[pre + "state/v2"]), state)
+        diverged = core.computeStep()
+        assert not diverged
+        flow = core.flow()
+        assert_parity(flow.v2, d[pre + "flow/v2"], f"{case} step {step} v2 flow")
+        for c in range(n):
+            assert_parity(flow.v4[c], d[pre + f"flow/v4_{c}"], f"{case} step {step} v4 flow channel {c}")
+        # Euler update against the reference's own next state where it was dumped
+        if step + 1 < len(cut):
+            core.finalizeStep(float(cut[step + 1]))
+            new = core.flowingFunctional()
+            assert new.cutoff == float(cut[step + 1])
+            want = [state[c] + (float(cut[step + 1]) - float(cut[step])) * d[pre + f"flow/v4_{c}"] for c in range(n)]
+            for c in range(n):
+                assert_parity(new.v4[c], want[c], f"{case} step {step} Euler channel {c}")
+    core.close()
+
+
+@pytest.mark.parametrize("case", ["su2_square_r3_nw10", "xyz_honeycomb_kitaev_r3_nw10"])
+def test_float32_host_arrays_round_trip(case):
+    d = golden(case)
+    name, core = _core(d)
+    n = core.n_arrays
+    rng = np.random.default_rng(7)
+    v2 = rng.uniform(0, 0.5, core.tables.n_frequencies).astype(np.float32)
+    v4 = [rng.uniform(-1, 1, core.array_length).astype(np.float32) for _ in range(n)]
+    core.setState(1.25, v2, v4)
+    back = core.flowingFunctional(np.float32)
+    assert back.cutoff == 1.25
+    assert np.array_equal(back.v2, v2)
+    for c in range(n):
+        assert np.array_equal(back.v4[c], v4[c])
+    core.close()
