@@ -81,6 +81,7 @@ struct pffrg_context
 	DeviceArray<double> dV4, dFlow4, dV2, dFlow2, dCutoff;
 	DeviceArray<int> dCount; DeviceArray<double> dNodeW, dNodeWt;
 	DeviceArray<int> dNan;
+	DeviceArray<double> dStaging; // one reference-layout array, reused by set_state / get_state / get_flow
 	int *hNan = nullptr;
 	int nodeStride = 0;
 
@@ -276,17 +277,16 @@ namespace
 	int importArrays(pffrg_context *h, const void *const *src, double *dst)
 	{
 		const size_t len = (size_t)h->nf * h->L * (h->core == TRI ? 16 : 1);
-		DeviceArray<T> staging;
-		CUDA_TRY(staging.alloc(len));
+		if (h->dStaging.n < len) CUDA_TRY(h->dStaging.alloc(len));
+		T *staging = reinterpret_cast<T *>(h->dStaging.p);
 		for (int a = 0; a < h->nArrays; ++a)
 		{
-			if (!src[a]) { staging.release(); return fail(PFFRG_ERR_ARGUMENT, "vertex array %d is null", a); }
-			CUDA_TRY(cudaMemcpyAsync(staging.p, src[a], len * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-			importKernel<T><<<1184, 256, 0, h->stream>>>(staging.p, dst, (size_t)h->nf, h->L, h->Lp, h->RL, h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
+			if (!src[a]) return fail(PFFRG_ERR_ARGUMENT, "vertex array %d is null", a);
+			CUDA_TRY(cudaMemcpyAsync(staging, src[a], len * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+			importKernel<T><<<1184, 256, 0, h->stream>>>(staging, dst, (size_t)h->nf, h->L, h->Lp, h->RL, h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
 			CUDA_TRY(cudaGetLastError());
 		}
 		CUDA_TRY(cudaStreamSynchronize(h->stream));
-		staging.release();
 		return PFFRG_OK;
 	}
 
@@ -294,17 +294,16 @@ namespace
 	int exportArrays(pffrg_context *h, const double *src, void *const *dst)
 	{
 		const size_t len = (size_t)h->nf * h->L * (h->core == TRI ? 16 : 1);
-		DeviceArray<T> staging;
-		CUDA_TRY(staging.alloc(len));
+		if (h->dStaging.n < len) CUDA_TRY(h->dStaging.alloc(len));
+		T *staging = reinterpret_cast<T *>(h->dStaging.p);
 		for (int a = 0; a < h->nArrays; ++a)
 		{
 			if (!dst[a]) continue;
-			exportKernel<T><<<1184, 256, 0, h->stream>>>(src, staging.p, (size_t)h->nf, h->L, h->Lp, h->RL, h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
+			exportKernel<T><<<1184, 256, 0, h->stream>>>(src, staging, (size_t)h->nf, h->L, h->Lp, h->RL, h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
 			CUDA_TRY(cudaGetLastError());
-			CUDA_TRY(cudaMemcpyAsync(dst[a], staging.p, len * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+			CUDA_TRY(cudaMemcpyAsync(dst[a], staging, len * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
 			CUDA_TRY(cudaStreamSynchronize(h->stream));
 		}
-		staging.release();
 		return PFFRG_OK;
 	}
 
@@ -440,7 +439,7 @@ int pffrg_destroy(pffrg_handle h)
 	if (h->comm) ncclCommDestroy(h->comm);
 	h->dMesh.release(); h->dSitesRid.release(); h->dInvRid.release(); h->dSitesPerm.release(); h->dInvPerm.release(); h->dRngFwd.release(); h->dRngInv.release();
 	h->dSlotOff.release(); h->dTasks.release(); h->dPairs.release(); h->dV4.release(); h->dFlow4.release(); h->dV2.release(); h->dFlow2.release(); h->dCutoff.release();
-	h->dCount.release(); h->dNodeW.release(); h->dNodeWt.release(); h->dNan.release();
+	h->dCount.release(); h->dNodeW.release(); h->dNodeWt.release(); h->dNan.release(); h->dStaging.release();
 	if (h->hNan) cudaFreeHost(h->hNan);
 	for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
 	if (h->stream) cudaStreamDestroy(h->stream);

@@ -133,12 +133,16 @@ class FrgCore:
         self.array_length = int(lib.pffrg_vertex_array_length(self._h))
         self.n_items = int(lib.pffrg_num_items(self._h))
         self.diverged = False
+        self._pinned: List[int] = []
 
     # ---- lifetime ------------------------------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None):
             lib.pffrg_destroy(self._h)
             self._h = None
+            for ptr in self._pinned:
+                lib.pffrg_host_free(ptr)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -205,8 +209,34 @@ class FrgCore:
                 ea.v4[c][:] = np.tile(np.asarray(values, dtype=np.float64), self.n_items)
         self.setState(cutoff, ea.v2, ea.v4)
 
-    def flowingFunctional(self, dtype=np.float64) -> EffectiveAction:
+    def pinnedEffectiveAction(self, dtype=np.float64) -> EffectiveAction:
+        """An :class:`EffectiveAction` whose arrays live in page-locked host memory (``pffrg_host_alloc``), for full-speed
+        transfers in ``setState`` / ``flowingFunctional(into=...)``. The buffers are released with the core."""
+        ea = EffectiveAction.__new__(EffectiveAction)
+        ea.core, ea.cutoff = self.identifier, 0.0
+        dtype = np.dtype(dtype)
+
+        def pinned(n):
+            ptr = lib.pffrg_host_alloc(n * dtype.itemsize)
+            if not ptr:
+                raise PffrgError(-2, lib.pffrg_last_error().decode())
+            self._pinned.append(ptr)
+            ctype = C.c_double if dtype == np.float64 else C.c_float
+            a = np.ctypeslib.as_array((ctype * n).from_address(ptr))
+            a[:] = 0
+            return a
+
+        ea.v2 = pinned(self.tables.n_frequencies)
+        ea.v4 = [pinned(self.array_length) for _ in range(self.n_arrays)]
+        return ea
+
+    def flowingFunctional(self, dtype=np.float64, into: Optional[EffectiveAction] = None) -> EffectiveAction:
         """Download the current state (``FrgCore::flowingFunctional``, src/FrgCore.hpp:93-96)."""
+        if into is not None:
+            cutoff = C.c_double()
+            check(lib.pffrg_get_state(self._h, C.byref(cutoff), into.v2.ctypes.data, self._ptrs(into.v4), self._dtype_code(into.v2.dtype)))
+            into.cutoff = cutoff.value
+            return into
         ea = EffectiveAction(self.identifier, self.tables.n_frequencies, self.tables.n_sites, dtype)
         cutoff = C.c_double()
         check(lib.pffrg_get_state(self._h, C.byref(cutoff), ea.v2.ctypes.data, self._ptrs(ea.v4), self._dtype_code(dtype)))

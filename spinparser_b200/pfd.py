@@ -40,7 +40,7 @@ def write_pfd(path: str, arrays: Mapping[str, np.ndarray]) -> None:
     with open(path, "wb") as f:
         f.write(b"PFD1")
         for name, a in arrays.items():
-            a = np.ascontiguousarray(a)
+            a = np.asarray(a, order="C")
             if a.dtype not in _CODES:
                 raise TypeError(f"{name}: unsupported dtype {a.dtype}")
             nb = name.encode()
