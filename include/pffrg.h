@@ -87,6 +87,8 @@ typedef struct pffrg_stats
 	double alg_bytes;       /* algorithmic gather+output bytes of this rank's share */
 	double alg_flops;       /* algorithmic FP64 flops of this rank's share */
 	int32_t launches;       /* kernels launched by the last compute_step + finalize_step */
+	int32_t jit_rpa;        /* 1 when the lattice-specialised (run-time compiled) flow kernel is in use */
+	double jit_compile_ms;  /* time spent generating + compiling it in pffrg_create */
 } pffrg_stats;
 
 /* library / environment ------------------------------------------------------------------------------------------ */
@@ -139,6 +141,10 @@ int pffrg_get_stats(pffrg_handle h, pffrg_stats *out);
 
 /* raw CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events */
 void *pffrg_stream(pffrg_handle h);
+
+/* Generate and compile (NVRTC, sm_100a) the lattice-specialised flow kernel for a problem without touching a GPU:
+ * a build-time check that the run-time compiled path works for this lattice. *cubin_bytes receives the code size. */
+int pffrg_jit_compile_check(const pffrg_desc *desc, int64_t *cubin_bytes);
 
 /* page-locked host memory for the arrays passed to set_state / get_state / get_flow (plain memory works too, but
  * transfers from pinned buffers run at full PCIe speed). Returns NULL on failure. */

@@ -23,7 +23,7 @@ SYMBOLS = [
     "pffrg_num_vertex_arrays", "pffrg_vertex_array_length", "pffrg_num_items", "pffrg_comm_unique_id",
     "pffrg_comm_init", "pffrg_item_range", "pffrg_set_state", "pffrg_get_state", "pffrg_get_flow",
     "pffrg_compute_step", "pffrg_finalize_step", "pffrg_synchronize", "pffrg_set_item_range", "pffrg_get_stats",
-    "pffrg_stream", "pffrg_host_alloc", "pffrg_host_free",
+    "pffrg_stream", "pffrg_host_alloc", "pffrg_host_free", "pffrg_jit_compile_check",
 ]
 
 
@@ -54,7 +54,7 @@ class Stats(C.Structure):
         ("ms_v2_flow", C.c_double), ("ms_node_table", C.c_double), ("ms_v4_flow", C.c_double),
         ("ms_finalize", C.c_double), ("ms_exchange", C.c_double),
         ("kernel_evals", C.c_int64), ("kernel_evals_t", C.c_int64), ("items", C.c_int64),
-        ("alg_bytes", C.c_double), ("alg_flops", C.c_double), ("launches", C.c_int32),
+        ("alg_bytes", C.c_double), ("alg_flops", C.c_double), ("launches", C.c_int32), ("jit_rpa", C.c_int32), ("jit_compile_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -94,6 +94,7 @@ def _load() -> C.CDLL:
     lib.pffrg_host_alloc.argtypes = [C.c_size_t]
     lib.pffrg_host_alloc.restype = vp
     lib.pffrg_host_free.argtypes = [vp]
+    lib.pffrg_jit_compile_check.argtypes = [C.POINTER(Desc), C.POINTER(C.c_int64)]
     if lib.pffrg_abi_version() != ABI_VERSION:
         raise ImportError(f"libpffrg ABI {lib.pffrg_abi_version()} != binding ABI {ABI_VERSION}")
     return lib

@@ -7,6 +7,7 @@
 // stream; replaces the MPI_Bcast of src/lib/LoadManager.hpp:240 issued from src/SU2/SU2FrgCore.cpp:136).
 #include "pffrg.h"
 #include "pffrg_kernels.cuh"
+#include "pffrg_jit.hpp"
 
 #include <nccl.h>
 
@@ -15,6 +16,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
+#include <cstdlib>
 #include <map>
 #include <numeric>
 #include <string>
@@ -76,7 +79,11 @@ struct pffrg_context
 	DeviceArray<double> dMesh;
 	DeviceArray<int> dSitesRid, dInvRid, dSitesPerm, dInvPerm, dRngFwd, dRngInv, dSlotOff;
 	DeviceArray<int4> dTasks;
-	DeviceArray<uint2> dPairs;
+	DeviceArray<unsigned> dWords;
+	// lattice-specialised flow kernel (NVRTC), see pffrg_jit.cpp
+	cudaLibrary_t jitLibrary = nullptr;
+	cudaKernel_t jitKernel = nullptr;
+	double jitCompileMs = 0.0;
 	// state
 	DeviceArray<double> dV4, dFlow4, dV2, dFlow2, dCutoff;
 	DeviceArray<int> dCount; DeviceArray<double> dNodeW, dNodeWt;
@@ -86,7 +93,7 @@ struct pffrg_context
 	int nodeStride = 0;
 
 	// launch configuration of the flow kernel
-	int nb = 32, groups = 1, threads = 32, nslots = 1; size_t smemBytes = 0;
+	int nb = 32, groups = 1, stride = 1, threads = 32, nslots = 1; size_t smemBytes = 0;
 
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[8] = {};
@@ -107,7 +114,7 @@ struct pffrg_context
 		Problem P;
 		P.nw = nw; P.L = L; P.Lp = Lp; P.RL = RL; P.nf = (int)nf;
 		P.mesh = dMesh.p; P.sites_rid = dSitesRid.p; P.inv_rid = dInvRid.p; P.sites_perm = dSitesPerm.p; P.inv_perm = dInvPerm.p;
-		P.rpa_tasks = dTasks.p; P.rpa_slot_off = dSlotOff.p; P.rpa_pairs = dPairs.p;
+		P.rpa_tasks = dTasks.p; P.rpa_slot_off = dSlotOff.p; P.rpa_words = dWords.p;
 		P.nrange = (int)dRngFwd.n; P.rng_fwd = dRngFwd.p; P.rng_inv = dRngInv.p; P.spin = spin;
 		return P;
 	}
@@ -133,47 +140,90 @@ namespace
 		auto kernel = v4FlowKernel<CORE, NB>;
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes);
 		if (e != cudaSuccess) return e;
-		FlowConfig cfg; cfg.groups = h->groups; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes;
+		FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes;
 		kernel<<<(unsigned)count, h->threads, h->smemBytes, h->stream>>>(h->problem(), h->nodeTable(), cfg, h->dV4.p, h->dFlow4.p, (int)begin, h->dNan.p);
 		return cudaGetLastError();
 	}
 
+	RpaProgram buildRpaProgram(const pffrg_desc *d, int core, int nb, int warps);
+
 	cudaError_t launchFlowDispatch(pffrg_context *h, int64_t begin, int64_t count)
 	{
 		if (count <= 0) return cudaSuccess;
+		if (h->jitKernel)
+		{
+			Problem P = h->problem(); NodeTable N = h->nodeTable();
+			FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes;
+			const double *v4 = h->dV4.p; double *flow = h->dFlow4.p; int itemBegin = (int)begin; int *nan = h->dNan.p;
+			void *args[] = { &P, &N, &cfg, &v4, &flow, &itemBegin, &nan };
+			return cudaLaunchKernel((const void *)h->jitKernel, dim3((unsigned)count), dim3(h->threads), args, h->smemBytes, h->stream);
+		}
 		if (h->core == SU2) return h->nb == 32 ? launchFlow<SU2, 32>(h, begin, count) : h->nb == 16 ? launchFlow<SU2, 16>(h, begin, count) : launchFlow<SU2, 8>(h, begin, count);
 		if (h->core == XYZ) return h->nb == 32 ? launchFlow<XYZ, 32>(h, begin, count) : h->nb == 16 ? launchFlow<XYZ, 16>(h, begin, count) : launchFlow<XYZ, 8>(h, begin, count);
 		return cudaErrorNotSupported;
 	}
 
-	// RPA pair list: per representative site the (rid1, perm1, rid2, perm2) tuples of Lattice::getOverlap(rid), identical
-	// tuples merged into integer multiplicities, sorted so that equal (rid1, perm1) are adjacent ("groups": operand A is
-	// loaded once per group). Tasks (one per rid) are dealt to the RPA slots longest-first.
-	void buildRpa(const pffrg_desc *d, int core, int nslots, std::vector<uint2> &pairs, std::vector<int4> &tasks, std::vector<int> &slotOff, int64_t &unique)
+	// Compile and load the lattice-specialised kernel. Controlled by the environment: PFFRG_JIT=0 disables it,
+	// PFFRG_JIT_MAX_TERMS (default 60000) bounds the straight-line code size (compile time grows with it).
+	int setupJit(pffrg_context *h, const pffrg_desc *d)
+	{
+		const char *env = getenv("PFFRG_JIT");
+		if (env && atoi(env) == 0) return PFFRG_OK;
+		long maxTerms = 60000;
+		if (const char *e = getenv("PFFRG_JIT_MAX_TERMS")) maxTerms = atol(e);
+		if (h->nb < 16) return PFFRG_OK;
+		const auto t0 = std::chrono::steady_clock::now();
+		RpaProgram prog = buildRpaProgram(d, h->core, h->nb, h->threads / 32);
+		if ((long)prog.terms.size() > maxTerms) return PFFRG_OK;
+		std::vector<char> cubin;
+		const std::string err = compileFlowKernel(h->core, h->nb, h->threads, 2, generateRpaSource(prog), cubin);
+		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the specialised flow kernel failed: %s", err.c_str());
+		CUDA_TRY(cudaLibraryLoadData(&h->jitLibrary, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+		CUDA_TRY(cudaLibraryGetKernel(&h->jitKernel, h->jitLibrary, "pffrg_v4flow_jit"));
+		CUDA_TRY(cudaFuncSetAttribute((const void *)h->jitKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+		h->jitCompileMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		return PFFRG_OK;
+	}
+
+	// (rid1, perm1, perm2, rid2) -> multiplicity of the overlap terms of one representative site (Lattice::getOverlap(rid),
+	// src/Lattice.hpp:46-150); SU2 ignores the spin permutations
+	std::map<std::tuple<int, int, int, int>, int> mergedOverlap(const pffrg_desc *d, int core, int rid)
+	{
+		std::map<std::tuple<int, int, int, int>, int> mult;
+		for (int i = d->overlap_offsets[rid]; i < d->overlap_offsets[rid + 1]; ++i)
+		{
+			int p1 = core == SU2 ? 0 : packPerm(d->overlap_perm1 + 3 * i), p2 = core == SU2 ? 0 : packPerm(d->overlap_perm2 + 3 * i);
+			mult[std::make_tuple(d->overlap_rid1[i], p1, p2, d->overlap_rid2[i])] += 1;
+		}
+		return mult;
+	}
+
+	// Term stream of the generic RPA phase (rpaGeneric): per representative site the merged overlap terms, sorted so that
+	// equal (rid1, perm1, perm2) are adjacent; each such group starts with a header word, followed by one word per term.
+	// Tasks (one per rid) are dealt to the RPA slots longest-first.
+	void buildRpa(const pffrg_desc *d, int core, int nslots, int nbp, std::vector<unsigned> &words, std::vector<int4> &tasks, std::vector<int> &slotOff, int64_t &unique)
 	{
 		const int L = d->n_sites;
 		std::vector<int4> perRid;
+		unique = 0;
 		for (int rid = 0; rid < L; ++rid)
 		{
-			std::map<std::tuple<int, int, int, int>, int> mult;
-			for (int i = d->overlap_offsets[rid]; i < d->overlap_offsets[rid + 1]; ++i)
-			{
-				int p1 = core == SU2 ? 0 : packPerm(d->overlap_perm1 + 3 * i), p2 = core == SU2 ? 0 : packPerm(d->overlap_perm2 + 3 * i);
-				mult[std::make_tuple(d->overlap_rid1[i], p1, d->overlap_rid2[i], p2)] += 1;
-			}
-			int begin = (int)pairs.size();
-			int lastR1 = -1, lastP1 = -1;
+			const auto mult = mergedOverlap(d, core, rid);
+			const int begin = (int)words.size();
+			int lastR1 = -1, lastP1 = -1, lastP2 = -1;
 			for (auto &kv : mult)
 			{
-				int r1 = std::get<0>(kv.first), p1 = std::get<1>(kv.first), r2 = std::get<2>(kv.first), p2 = std::get<3>(kv.first);
-				unsigned flag = (r1 != lastR1 || p1 != lastP1) ? 1u : 0u;
-				lastR1 = r1; lastP1 = p1;
-				uint2 w; w.x = (unsigned)r1 | ((unsigned)r2 << 8) | ((unsigned)p1 << 16) | ((unsigned)p2 << 22) | (flag << 31); w.y = (unsigned)kv.second;
-				pairs.push_back(w);
+				const int r1 = std::get<0>(kv.first), p1 = std::get<1>(kv.first), p2 = std::get<2>(kv.first), r2 = std::get<3>(kv.first);
+				if (r1 != lastR1 || p1 != lastP1 || p2 != lastP2)
+				{
+					words.push_back(0x80000000u | (unsigned)(r1 * nbp) | ((unsigned)p1 << 16) | ((unsigned)p2 << 22));
+					lastR1 = r1; lastP1 = p1; lastP2 = p2;
+				}
+				words.push_back((unsigned)(r2 * nbp) | ((unsigned)std::min(kv.second, 32767) << 16));
 			}
-			perRid.push_back(make_int4(rid, begin, (int)pairs.size(), 0));
+			unique += (int64_t)mult.size();
+			perRid.push_back(make_int4(rid, begin, (int)words.size(), 0));
 		}
-		unique = (int64_t)pairs.size();
 		std::vector<int> order(L);
 		std::iota(order.begin(), order.end(), 0);
 		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return perRid[a].z - perRid[a].y > perRid[b].z - perRid[b].y; });
@@ -186,7 +236,38 @@ namespace
 			load[best] += perRid[r].z - perRid[r].y + 8;
 		}
 		slotOff.assign(1, 0);
-		for (auto &s : bySlot) { for (auto &t : s) tasks.push_back(t); slotOff.push_back((int)tasks.size()); }
+		for (auto &sl : bySlot) { for (auto &t : sl) tasks.push_back(t); slotOff.push_back((int)tasks.size()); }
+	}
+
+	// the RPA sum as a list of multiply-adds over staged operands [channel][rid], for the code generator
+	RpaProgram buildRpaProgram(const pffrg_desc *d, int core, int nb, int warps)
+	{
+		const int L = d->n_sites, C = channelsOf(core);
+		RpaProgram p;
+		p.nb = nb; p.warps = warps;
+		p.operandStride = nb + 1;
+		p.operandBOffset = (long)C * L * (nb + 1);
+		p.outputCopyStride = (long)C * L;
+		if (core == SU2)
+		{
+			// both channels share the term structure: run them as two lane groups of one warp
+			p.variants = 2; p.lanesPerVariant = 16; p.nOutputs = L;
+			p.variantOperandStride = (long)L * (nb + 1); p.variantOutputStride = L;
+			for (int rid = 0; rid < L; ++rid)
+				for (auto &kv : mergedOverlap(d, core, rid)) p.terms.push_back({ rid, std::get<0>(kv.first), std::get<3>(kv.first), kv.second });
+		}
+		else
+		{
+			p.variants = 1; p.lanesPerVariant = std::min(nb, 32); p.nOutputs = C * L;
+			for (int rid = 0; rid < L; ++rid)
+				for (auto &kv : mergedOverlap(d, core, rid))
+				{
+					const int r1 = std::get<0>(kv.first), p1 = std::get<1>(kv.first), p2 = std::get<2>(kv.first), r2 = std::get<3>(kv.first);
+					for (int c = 0; c < 3; ++c) p.terms.push_back({ c * L + rid, ((p1 >> (2 * c)) & 3) * L + r1, ((p2 >> (2 * c)) & 3) * L + r2, kv.second });
+					p.terms.push_back({ 3 * L + rid, 3 * L + r1, 3 * L + r2, kv.second });
+				}
+		}
+		return p;
 	}
 
 	// node counts per mesh frequency at the current cutoff (host copy of what nodeTableKernel enumerates)
@@ -377,7 +458,7 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 
 	pffrg_context *h = new pffrg_context();
 	const CoreModel m = modelOf(d->core);
-	h->core = d->core; h->nw = d->n_frequencies; h->L = L; h->Lp = (L + 3) / 4 * 4; h->C = m.C; h->RL = m.C * h->Lp; h->nArrays = m.arrays;
+	h->core = d->core; h->nw = d->n_frequencies; h->L = L; h->Lp = (L + 15) / 16 * 16; h->C = m.C; h->RL = m.C * h->Lp; h->nArrays = m.arrays;
 	h->nf = (int64_t)h->nw * h->nw * (h->nw + 1) / 2;
 	h->device = d->device; h->spin = d->spin_length;
 	h->mesh.assign(d->frequencies, d->frequencies + h->nw);
@@ -385,16 +466,20 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	if ((double)h->nf * h->RL > 2.0e9) { delete h; return fail(PFFRG_ERR_UNSUPPORTED, "vertex too large for 32-bit row offsets"); }
 
 	// launch configuration: k groups of L threads; batch width NB chosen so that at least two CTAs fit per SM
-	h->groups = std::max(1, 256 / L);
-	h->threads = std::max(64, (h->groups * L + 31) / 32 * 32);
+	// a group of threads covers the L sites of one quadrature node; groups are padded to whole warps when that idles at
+	// most a quarter of the lanes (then every warp gathers from one node only: fewer cache lines per load, uniform table reads)
+	const int padded = (L + 31) / 32 * 32;
+	h->stride = (padded - L) * 4 <= padded ? padded : L;
+	h->groups = std::max(1, 256 / h->stride);
+	h->threads = std::max(64, (h->groups * h->stride + 31) / 32 * 32);
 	h->nb = 32;
 	while (h->nb > 8 && flowSmemBytes(h->core, h->nb, h->nw, L, h->groups) > 100 * 1024) h->nb >>= 1;
 	h->smemBytes = flowSmemBytes(h->core, h->nb, h->nw, L, h->groups);
 	if (h->smemBytes > (size_t)prop.sharedMemPerBlockOptin) { const size_t need = h->smemBytes; delete h; return fail(PFFRG_ERR_UNSUPPORTED, "flow kernel needs %zu bytes of shared memory", need); }
 	h->nslots = (h->threads / 32) * (32 / h->nb);
 
-	std::vector<uint2> pairs; std::vector<int4> tasks; std::vector<int> slotOff;
-	buildRpa(d, h->core, h->nslots, pairs, tasks, slotOff, h->uniquePairs);
+	std::vector<unsigned> words; std::vector<int4> tasks; std::vector<int> slotOff;
+	buildRpa(d, h->core, h->nslots, h->nb + 1, words, tasks, slotOff, h->uniquePairs);
 
 	std::vector<int> sitesPerm(L), invPerm(L);
 	for (int j = 0; j < L; ++j) { sitesPerm[j] = packPerm(d->sites_perm + 3 * j); invPerm[j] = packPerm(d->inverted_perm + 3 * j); }
@@ -407,7 +492,7 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	ok(h->dSitesPerm.upload(sitesPerm)); ok(h->dInvPerm.upload(invPerm));
 	ok(h->dRngFwd.upload(std::vector<int>(d->range_fwd_rid, d->range_fwd_rid + d->n_range)));
 	ok(h->dRngInv.upload(std::vector<int>(d->range_inv_rid, d->range_inv_rid + d->n_range)));
-	ok(h->dTasks.upload(tasks)); ok(h->dSlotOff.upload(slotOff)); ok(h->dPairs.upload(pairs));
+	ok(h->dTasks.upload(tasks)); ok(h->dSlotOff.upload(slotOff)); ok(h->dWords.upload(words));
 	ok(h->dV4.alloc(h->v4Elements())); ok(h->dFlow4.alloc(h->v4Elements()));
 	ok(h->dV2.alloc(h->nw)); ok(h->dFlow2.alloc(h->nw)); ok(h->dCutoff.alloc(1));
 	h->nodeStride = 2 * h->nw + 8;
@@ -427,6 +512,8 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 		return code;
 	}
 	h->bounds = { 0, h->nf };
+	const int jitStatus = setupJit(h, d);
+	if (jitStatus != PFFRG_OK) { pffrg_destroy(h); return jitStatus; }
 	*out = h;
 	return PFFRG_OK;
 }
@@ -438,7 +525,8 @@ int pffrg_destroy(pffrg_handle h)
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->comm) ncclCommDestroy(h->comm);
 	h->dMesh.release(); h->dSitesRid.release(); h->dInvRid.release(); h->dSitesPerm.release(); h->dInvPerm.release(); h->dRngFwd.release(); h->dRngInv.release();
-	h->dSlotOff.release(); h->dTasks.release(); h->dPairs.release(); h->dV4.release(); h->dFlow4.release(); h->dV2.release(); h->dFlow2.release(); h->dCutoff.release();
+	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release();
+	if (h->jitLibrary) cudaLibraryUnload(h->jitLibrary); h->dV4.release(); h->dFlow4.release(); h->dV2.release(); h->dFlow2.release(); h->dCutoff.release();
 	h->dCount.release(); h->dNodeW.release(); h->dNodeWt.release(); h->dNan.release(); h->dStaging.release();
 	if (h->hNan) cudaFreeHost(h->hNan);
 	for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -616,10 +704,31 @@ int pffrg_get_stats(pffrg_handle h, pffrg_stats *out)
 {
 	if (!h || !out) return fail(PFFRG_ERR_ARGUMENT, "null argument");
 	*out = h->stats;
+	out->jit_rpa = h->jitKernel ? 1 : 0;
+	out->jit_compile_ms = h->jitCompileMs;
 	return PFFRG_OK;
 }
 
 void *pffrg_stream(pffrg_handle h) { return h ? (void *)h->stream : nullptr; }
+
+int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
+{
+	if (!d || d->n_sites < 1 || d->n_sites > 256 || d->core < 0 || d->core > 1 || !d->overlap_offsets) return fail(PFFRG_ERR_ARGUMENT, "bad descriptor");
+	// same launch configuration as pffrg_create
+	const int L = d->n_sites, padded = (L + 31) / 32 * 32;
+	const int stride = (padded - L) * 4 <= padded ? padded : L;
+	const int groups = std::max(1, 256 / stride);
+	const int threads = std::max(64, (groups * stride + 31) / 32 * 32);
+	int nb = 32;
+	while (nb > 8 && flowSmemBytes(d->core, nb, d->n_frequencies, L, groups) > 100 * 1024) nb >>= 1;
+	if (nb < 16) return fail(PFFRG_ERR_UNSUPPORTED, "lattice too large for the specialised kernel");
+	RpaProgram prog = buildRpaProgram(d, d->core, nb, threads / 32);
+	std::vector<char> cubin;
+	const std::string err = compileFlowKernel(d->core, nb, threads, 2, generateRpaSource(prog), cubin);
+	if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
+	if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
+	return PFFRG_OK;
+}
 
 void *pffrg_host_alloc(size_t bytes)
 {

@@ -8,8 +8,10 @@
 // into; summation order elsewhere is free (parity tolerance 1e-10, round-off head-room ~1e-15).
 #pragma once
 
+#ifndef __CUDACC_RTC__
 #include <cstdint>
 #include <cuda_runtime.h>
+#endif
 
 namespace pffrg
 {
@@ -119,12 +121,12 @@ namespace pffrg
 	// ---- access buffers --------------------------------------------------------------------------------------------------
 	// Four interpolation supports of one vertex access: row index (su*Nw + t), weight, and the symmetry flags that decide
 	// signs and the site/spin maps at gather time.
-	struct __align__(8) AccessBuffer
+	struct __align__(16) AccessBuffer
 	{
 		double w[4];
 		int row[4];
 		int flags; // bit0: site/pair exchange, bit1: TRI zeta_mu*zeta_nu factor, bit(4+k): support k reads the s<->u mirrored entry
-		int pad;
+		int pad[3];
 	};
 	constexpr int AB_EXCHANGE = 1, AB_TZ = 2;
 	__host__ __device__ __forceinline__ int abSwapped(int flags, int k) { return (flags >> (4 + k)) & 1; }
@@ -188,7 +190,6 @@ namespace pffrg
 			ab.w[3] = b2 * b1;             ab.row[3] = rowIndex(nw, u1, u2, eu, 3, flags);
 		}
 		ab.flags = flags;
-		ab.pad = 0;
 	}
 
 	// TRIVertexTwoParticle::_zeta, src/TRI/TRIVertexTwoParticle.hpp:674-677

@@ -1,0 +1,34 @@
+// pffrg_jit.hpp -- interface of the lattice-specialised RPA code generator (see pffrg_jit.cpp)
+#pragma once
+
+#include <string>
+#include <vector>
+
+namespace pffrg
+{
+	// one multiply-add of the RPA sum: out[o] += mult * A[a] * B[b]; a, b index the staged operands [channel][rid]
+	struct RpaTerm { int out, a, b, mult; };
+
+	struct RpaProgram
+	{
+		std::vector<RpaTerm> terms; // for ONE variant
+		int nOutputs = 0;           // outputs per variant
+		int variants = 1;           // lanes are split into `variants` groups running the same code on shifted operands (SU2: the two channels)
+		int lanesPerVariant = 32;   // nodes per warp
+		int nb = 32;                // nodes per batch
+		int warps = 8;              // warps per CTA
+		long operandStride = 33;    // doubles between consecutive operand indices in the staging area (NB + 1)
+		long operandBOffset = 0;    // doubles from operand A's staging buffer to operand B's
+		long variantOperandStride = 0, variantOutputStride = 0;
+		long outputCopyStride = 0;  // doubles between the two output copies of the kernel (C * L)
+		int maxAccumulators = 8;    // outputs accumulated in registers at a time
+		int chunk = 32;             // B operands cached in registers at a time
+	};
+
+	// CUDA source of `__device__ void pffrg::rpaSpecialised(int warp, int lane, int nb, const double *st, double *rpaOut)`
+	std::string generateRpaSource(const RpaProgram &program);
+
+	// compile the vertex-flow kernel (embedded source + the generated RPA function) for sm_100a; returns an empty string on
+	// success and the compiler log otherwise. The kernel is `pffrg_v4flow_jit` with v4FlowKernel's parameter list.
+	std::string compileFlowKernel(int core, int nb, int threads, int minBlocks, const std::string &rpaSource, std::vector<char> &cubin);
+}

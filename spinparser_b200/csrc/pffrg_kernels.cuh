@@ -24,9 +24,9 @@ namespace pffrg
 		const int *inv_rid;      // [L]
 		const int *sites_perm;   // [L] packed 2 bits per spin component
 		const int *inv_perm;     // [L]
-		const int4 *rpa_tasks;   // {rid, pairBegin, pairEnd, 0}, grouped by RPA slot
+		const int4 *rpa_tasks;   // {rid, wordBegin, wordEnd, 0}, ordered by RPA slot
 		const int *rpa_slot_off; // [nslots + 1]
-		const uint2 *rpa_pairs;  // x: r1 | r2<<8 | perm1<<16 | perm2<<22 | newGroup<<31 ; y: multiplicity
+		const unsigned *rpa_words; // term stream of the generic RPA phase, see rpaGeneric
 		int nrange;
 		const int *rng_fwd;      // [nrange]
 		const int *rng_inv;      // [nrange]
@@ -219,26 +219,37 @@ namespace pffrg
 	}
 
 	// ================================================================================================================
-	// K1: vertex flow. One CTA per work item (s,t,u). Threads are organised as k groups of L: thread (g, j) owns
-	// representative site j and evaluates the quadrature nodes g, g+k, ... of the current batch:
+	// K1: vertex flow. One CTA per work item (s,t,u). Threads are organised as k groups: thread (g, j) owns representative
+	// site j and evaluates the quadrature nodes g, g+k, ... of the current batch of NB nodes:
 	//   phase 0   one thread per (node, access buffer): sector map + two lerps -> table in shared memory
 	//   phase 0b  (t channel) site-0 values of the four u-type buffers          SU2FrgCore.cpp:269-284
 	//   phase 1   gather 4 buffers x 4 supports x C channels for site j (coalesced across j), bilinear forms in registers,
 	//             weighted accumulation into per-thread registers; t channel: stage the RPA operands, transposed, in smem
-	//   phase 2   (t channel) RPA lattice sum: lanes = nodes, warps/sub-warps = representative sites; operand A is held in a
-	//             register per (rid, r1) group, pairs carry integer multiplicities                :250-266
+	//   phase 2   (t channel) RPA lattice sum R_c[rid] = sum_i A_c[rid1_i] B_c[rid2_i] (SU2FrgCore.cpp:250-266), lanes = nodes.
+	//             Two implementations:
+	//             - generic: warps/sub-warps walk a word stream of the (deduplicated, grouped) overlap terms
+	//             - specialised (JIT = true): straight-line code generated for the lattice at handle creation and compiled
+	//               with NVRTC (pffrg_jit.cpp); operands are cached in registers, multiplicities are immediates
 	//   epilogue  deterministic reduction over groups, 1/2pi, NaN flag, coalesced store of the item's C x L flow values
 	// ================================================================================================================
 	struct FlowConfig
 	{
 		int groups;      // k
-		int nslots;      // RPA slots = warps * (32 / NB)
+		int stride;      // threads per group: L, or L rounded up to whole warps
+		int nslots;      // RPA slots of the generic phase 2 = warps * (32 / NB)
 		int smemBytes;
 	};
 
 	template <int CORE> struct RpaStage { static constexpr int buffers = (CORE == TRI) ? 4 : 2; };
 
 	__host__ __device__ inline size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+	// RPA staging area.
+	//  generic:      st[buffer][plane][rid][node] of double2, plane p holding channels 2p and 2p+1 (one conflict-free 128-bit
+	//                load per lane (= node) and plane)
+	//  specialised:  st[buffer][channel][rid][node] of double
+	template <int C, int NBP>
+	__device__ __forceinline__ int stageIndex(int L, int buffer, int plane, int rid, int node) { return ((buffer * (C / 2) + plane) * L + rid) * NBP + node; }
 
 	template <int CORE, int NB>
 	struct FlowSmem
@@ -252,11 +263,13 @@ namespace pffrg
 			mesh = o; o += sizeof(double) * nw;
 			bw = o; o += sizeof(double) * NB;
 			bW = o; o += sizeof(double) * NB;
+			o = alignUp(o, 16);
 			ab = o; o += sizeof(AccessBuffer) * NB * 8;
 			loc = o; o += sizeof(double) * NB * 4 * C;
+			o = alignUp(o, 16);
 			st = o; o += sizeof(double) * RpaStage<CORE>::buffers * C * L * NBP;
 			part = o; o += sizeof(double) * groups * C * L;
-			rpa = o; o += sizeof(double) * C * L;
+			rpa = o; o += sizeof(double) * C * L * 2; // two copies: the specialised SU2 code runs two node groups concurrently
 			total = alignUp(o, 16);
 		}
 	};
@@ -266,6 +279,11 @@ namespace pffrg
 	__device__ __forceinline__ void gatherSite(const Problem &P, const double *__restrict__ v4, const AccessBuffer &ab, int siteFwd, int siteInv, int permFwd, int permInv, double (&out)[channelsOf(CORE)])
 	{
 		constexpr int C = channelsOf(CORE);
+		// the table entry is 64 bytes, 16-byte aligned: four 128-bit shared loads
+		const double2 w01 = *reinterpret_cast<const double2 *>(&ab.w[0]), w23 = *reinterpret_cast<const double2 *>(&ab.w[2]);
+		const int4 rows = *reinterpret_cast<const int4 *>(&ab.row[0]);
+		const double wk[4] = { w01.x, w01.y, w23.x, w23.y };
+		const int rk[4] = { rows.x, rows.y, rows.z, rows.w };
 		const int flags = ab.flags;
 		const bool exchange = flags & AB_EXCHANGE;
 		const int site = exchange ? siteInv : siteFwd;
@@ -276,9 +294,9 @@ namespace pffrg
 		for (int k = 0; k < 4; ++k)
 		{
 			// weight of the support for channels that are even / odd under the s<->u frequency exchange
-			const double wEven = ab.w[k];
+			const double wEven = wk[k];
 			const double wOdd = abSwapped(flags, k) ? -wEven : wEven;
-			const double *base = v4 + (size_t)ab.row[k] * P.RL + site;
+			const double *base = v4 + (size_t)rk[k] * P.RL + site;
 			#pragma unroll
 			for (int c = 0; c < C; ++c)
 			{
@@ -412,12 +430,109 @@ namespace pffrg
 		}
 	}
 
+#ifdef PFFRG_JIT_RPA
+	// generated per lattice (pffrg_jit.cpp): the RPA sum of one batch for the outputs owned by `warp`
+	__device__ void rpaSpecialised(int warp, int lane, int nb, const double *st, double *rpaOut);
+#endif
+
+	// generic phase 2: one RPA slot (a warp, or a sub-warp of NB lanes) walks the term stream of its representative sites.
+	// Stream words: header (bit 31 set): rid1*(NB+1) | perm1<<16 | perm2<<22 -> flush the open group, load operand A;
+	//               term   (bit 31 clear): rid2*(NB+1) | multiplicity<<16     -> t += m * B[rid2]
 	template <int CORE, int NB>
-	__global__ void v4FlowKernel(Problem P, NodeTable N, FlowConfig cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
+	__device__ __forceinline__ void rpaGeneric(const Problem &P, const FlowConfig &cfg, const double *st, double *rpaOut, int tid, int nb)
 	{
 		constexpr int C = channelsOf(CORE);
 		constexpr int NBP = NB + 1;
-		constexpr int SUBS = 32 / NB; // RPA sub-warps per warp
+		constexpr int SUBS = 32 / NB;
+		const int L = P.L;
+		const int lane = tid & 31, wid = tid >> 5;
+		const int sub = lane / NB, node = lane - sub * NB;
+		const int slot = wid * SUBS + sub;
+		const bool active = node < nb;
+		const unsigned subMask = (NB == 32) ? 0xffffffffu : (((1u << (NB & 31)) - 1u) << (sub * NB));
+		if (slot >= cfg.nslots) return;
+		// lane-private base addresses: operand A = staged buffer 0, operand B = staged buffer 1, plane 0, this lane's node
+		const double2 *stA = reinterpret_cast<const double2 *>(st) + node;
+		const double2 *stB = stA + (C / 2) * L * NBP;
+		const int planeStride = L * NBP;
+		for (int ti = P.rpa_slot_off[slot]; ti < P.rpa_slot_off[slot + 1]; ++ti)
+		{
+			const int4 task = P.rpa_tasks[ti]; // {rid, wordBegin, wordEnd, 0}
+			double r[C], a[C], t[C];
+			#pragma unroll
+			for (int c = 0; c < C; ++c) { r[c] = 0.0; a[c] = 0.0; t[c] = 0.0; }
+			int perms = 0;
+			auto flush = [&]()
+			{
+				if (CORE == XYZ)
+				{
+					const int p1 = perms & 0x3f, p2 = (perms >> 6) & 0x3f;
+					#pragma unroll
+					for (int c = 0; c < 3; ++c)
+					{
+						const int c1 = (p1 >> (2 * c)) & 3, c2 = (p2 >> (2 * c)) & 3;
+						const double ac = c1 == 0 ? a[0] : (c1 == 1 ? a[1] : a[2]);
+						const double tc = c2 == 0 ? t[0] : (c2 == 1 ? t[1] : t[2]);
+						r[c] += ac * tc;
+					}
+					r[3] += a[3] * t[3];
+				}
+				else
+				{
+					#pragma unroll
+					for (int c = 0; c < C; ++c) r[c] += a[c] * t[c];
+				}
+				#pragma unroll
+				for (int c = 0; c < C; ++c) t[c] = 0.0;
+			};
+			if (active)
+			{
+				#pragma unroll 2
+				for (int i = task.y; i < task.z; ++i)
+				{
+					const unsigned w = __ldg(P.rpa_words + i);
+					if (w >> 31)
+					{
+						flush();
+						perms = (w >> 16) & 0xfff;
+						#pragma unroll
+						for (int pl = 0; pl < C / 2; ++pl)
+						{
+							const double2 av = stA[(w & 0xffffu) + pl * planeStride];
+							a[2 * pl] = av.x; a[2 * pl + 1] = av.y;
+						}
+					}
+					else
+					{
+						const double m = (double)(int)(w >> 16);
+						const double2 *pb = stB + (w & 0xffffu);
+						#pragma unroll
+						for (int pl = 0; pl < C / 2; ++pl)
+						{
+							const double2 b = pb[pl * planeStride];
+							t[2 * pl] += m * b.x; t[2 * pl + 1] += m * b.y;
+						}
+					}
+				}
+				flush();
+			}
+			__syncwarp(subMask);
+			#pragma unroll
+			for (int c = 0; c < C; ++c)
+			{
+				double v = r[c];
+				#pragma unroll
+				for (int o = NB >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(subMask, v, o);
+				if (node == 0) rpaOut[c * L + task.x] += v;
+			}
+		}
+	}
+
+	template <int CORE, int NB, bool JIT>
+	__device__ __forceinline__ void v4FlowBody(const Problem &P, const NodeTable &N, const FlowConfig &cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
+	{
+		constexpr int C = channelsOf(CORE);
+		constexpr int NBP = NB + 1;
 		extern __shared__ __align__(16) unsigned char smemRaw[];
 		const FlowSmem<CORE, NB> lay(P.nw, P.L, cfg.groups);
 		double *mesh = reinterpret_cast<double *>(smemRaw + lay.mesh);
@@ -432,7 +547,7 @@ namespace pffrg
 		const int tid = threadIdx.x, nthreads = blockDim.x;
 		const int L = P.L, nw = P.nw;
 		for (int i = tid; i < nw; i += nthreads) mesh[i] = P.mesh[i];
-		for (int i = tid; i < C * L; i += nthreads) rpaOut[i] = 0.0;
+		for (int i = tid; i < 2 * C * L; i += nthreads) rpaOut[i] = 0.0;
 
 		// work item -> (s, t, u), expandIterator SU2VertexTwoParticle.hpp:136-158
 		const int item = itemBegin + blockIdx.x;
@@ -446,8 +561,8 @@ namespace pffrg
 		f.s = mesh[so]; f.t = mesh[ti]; f.u = mesh[uo];
 		f.w1p = 0.5 * (f.s + f.t + f.u); f.w1 = 0.5 * (f.s - f.t + f.u); f.w2p = 0.5 * (f.s - f.t - f.u); f.w2 = 0.5 * (f.s + f.t - f.u);
 
-		const int g = tid / L, j = tid - g * L;
-		const bool worker = g < cfg.groups;
+		const int g = tid / cfg.stride, j = tid - g * cfg.stride;
+		const bool worker = g < cfg.groups && j < L;
 		int siteFwd = 0, siteInv = 0, permFwd = PERM_IDENTITY, permInv = PERM_IDENTITY;
 		if (worker) { siteFwd = P.sites_rid[j]; siteInv = P.inv_rid[j]; permFwd = P.sites_perm[j]; permInv = P.inv_perm[j]; }
 
@@ -455,13 +570,12 @@ namespace pffrg
 		#pragma unroll
 		for (int c = 0; c < C; ++c) acc[c] = 0.0;
 
-		const int xIndex[3] = { so, ti, uo };
 		// channel order S, U, T keeps the shared-memory heavy t channel last
 		#pragma unroll 1
 		for (int pass = 0; pass < 3; ++pass)
 		{
 			const int ch = pass == 0 ? CH_S : (pass == 1 ? CH_U : CH_T);
-			const int xi = xIndex[ch];
+			const int xi = ch == CH_S ? so : (ch == CH_T ? ti : uo);
 			const int nNodes = N.count[xi];
 			const double *nodeW = N.wp + (size_t)xi * N.stride, *nodeWt = N.wt + (size_t)xi * N.stride;
 			const int nbuf = ch == CH_T ? 8 : 4;
@@ -516,23 +630,33 @@ namespace pffrg
 						else
 						{
 							chaliceTerms<CORE>(A, loc + node * 4 * C, K);
-							// stage the RPA operands transposed: st[buffer][c][site][node]
-							if (CORE == SU2)
+							// stage the RPA operands, transposed. SU2: operands are buffers 2 and 3 with prefactors 2S (spin) and 8S
+							// (density), SU2FrgCore.cpp:257-266; XYZ: buffers 0 and 1 with prefactor 4, XYZFrgCore.cpp:297-322.
+							// The node weight W and the prefactor are folded into operand A.
+							double opA[C], opB[C];
+							#pragma unroll
+							for (int c = 0; c < C; ++c)
 							{
-								// operands are buffers 2 and 3; prefactors 2S (spin) and 8S (density), SU2FrgCore.cpp:257-266
-								st[((0 * C + 0) * L + j) * NBP + node] = W * 2.0 * P.spin * A[2][0];
-								st[((0 * C + 1) * L + j) * NBP + node] = W * 8.0 * P.spin * A[2][1];
-								st[((1 * C + 0) * L + j) * NBP + node] = A[3][0];
-								st[((1 * C + 1) * L + j) * NBP + node] = A[3][1];
+								if (CORE == SU2) { opA[c] = W * (c == 0 ? 2.0 : 8.0) * P.spin * A[2][c]; opB[c] = A[3][c]; }
+								else { opA[c] = W * 4.0 * A[0][c]; opB[c] = A[1][c]; }
 							}
-							else if (CORE == XYZ)
+							if (JIT)
 							{
-								// operands are buffers 0 and 1, prefactor 4, XYZFrgCore.cpp:297-322
 								#pragma unroll
 								for (int c = 0; c < C; ++c)
 								{
-									st[((0 * C + c) * L + j) * NBP + node] = W * 4.0 * A[0][c];
-									st[((1 * C + c) * L + j) * NBP + node] = A[1][c];
+									st[((0 * C + c) * L + j) * NBP + node] = opA[c];
+									st[((1 * C + c) * L + j) * NBP + node] = opB[c];
+								}
+							}
+							else
+							{
+								double2 *st2 = reinterpret_cast<double2 *>(st);
+								#pragma unroll
+								for (int pl = 0; pl < C / 2; ++pl)
+								{
+									st2[stageIndex<C, NBP>(L, 0, pl, j, node)] = make_double2(opA[2 * pl], opA[2 * pl + 1]);
+									st2[stageIndex<C, NBP>(L, 1, pl, j, node)] = make_double2(opB[2 * pl], opB[2 * pl + 1]);
 								}
 							}
 						}
@@ -543,59 +667,12 @@ namespace pffrg
 				if (ch == CH_T)
 				{
 					__syncthreads();
-					// ---- phase 2: RPA lattice sum  R_c[rid] = sum_i A_c[rid1_i] * B_c[rid2_i]
-					const int lane = tid & 31, wid = tid >> 5;
-					const int sub = lane / NB, node = lane - sub * NB;
-					const int slot = wid * SUBS + sub;
-					const bool active = node < nb;
-					const unsigned subMask = (NB == 32) ? 0xffffffffu : (((1u << (NB & 31)) - 1u) << (sub * NB));
-					if (slot < cfg.nslots)
-					{
-						for (int ti2 = P.rpa_slot_off[slot]; ti2 < P.rpa_slot_off[slot + 1]; ++ti2)
-						{
-							const int4 task = P.rpa_tasks[ti2];
-							double r[C], a[C], ts[C];
-							#pragma unroll
-							for (int c = 0; c < C; ++c) { r[c] = 0.0; a[c] = 0.0; ts[c] = 0.0; }
-							if (active)
-							{
-								for (int i = task.y; i < task.z; ++i)
-								{
-									const uint2 pw = __ldg(P.rpa_pairs + i);
-									if (pw.x >> 31)
-									{
-										const int r1 = pw.x & 0xff, p1 = (pw.x >> 16) & 0x3f;
-										#pragma unroll
-										for (int c = 0; c < C; ++c)
-										{
-											r[c] += a[c] * ts[c]; ts[c] = 0.0;
-											const int sc = (CORE == XYZ && c < 3) ? ((p1 >> (2 * c)) & 3) : c;
-											a[c] = st[((0 * C + sc) * L + r1) * NBP + node];
-										}
-									}
-									const int r2 = (pw.x >> 8) & 0xff, p2 = (pw.x >> 22) & 0x3f;
-									const double m = (double)(int)pw.y;
-									#pragma unroll
-									for (int c = 0; c < C; ++c)
-									{
-										const int sc = (CORE == XYZ && c < 3) ? ((p2 >> (2 * c)) & 3) : c;
-										ts[c] += m * st[((1 * C + sc) * L + r2) * NBP + node];
-									}
-								}
-								#pragma unroll
-								for (int c = 0; c < C; ++c) r[c] += a[c] * ts[c];
-							}
-							__syncwarp(subMask);
-							#pragma unroll
-							for (int c = 0; c < C; ++c)
-							{
-								double v = r[c];
-								#pragma unroll
-								for (int o = NB >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(subMask, v, o);
-								if (node == 0) rpaOut[c * L + task.x] += v;
-							}
-						}
-					}
+					// ---- phase 2: RPA lattice sum
+#ifdef PFFRG_JIT_RPA
+					if (JIT) rpaSpecialised(tid >> 5, tid & 31, nb, st, rpaOut);
+					else
+#endif
+					rpaGeneric<CORE, NB>(P, cfg, st, rpaOut, tid, nb);
 				}
 			}
 		}
@@ -611,7 +688,7 @@ namespace pffrg
 		bool bad = false;
 		for (int e = tid; e < C * L; e += nthreads)
 		{
-			double v = rpaOut[e];
+			double v = rpaOut[e] + rpaOut[C * L + e];
 			for (int gg = 0; gg < cfg.groups; ++gg) v += part[gg * C * L + e];
 			v /= TWO_PI;
 			const int c = e / L, jj = e - c * L;
@@ -620,6 +697,14 @@ namespace pffrg
 		}
 		if (bad) atomicOr(nanFlag, 1);
 	}
+
+#ifndef PFFRG_JIT_RPA
+	template <int CORE, int NB>
+	__global__ void v4FlowKernel(Problem P, NodeTable N, FlowConfig cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
+	{
+		v4FlowBody<CORE, NB, false>(P, N, cfg, v4, flow, itemBegin, nanFlag);
+	}
+#endif
 
 	// ================================================================================================================
 	// K3: Euler update, and the reference-layout <-> device-layout transposes used by set_state / get_state / get_flow

@@ -78,6 +78,26 @@ class ProblemTables:
         return nw * nw * (nw + 1) // 2
 
 
+def make_descriptor(identifier: str, t: ProblemTables, spin_length: float = 0.5, device: int = 0) -> "_capi.Desc":
+    """``pffrg_desc`` borrowing the numpy buffers of ``t`` (which must outlive the call that consumes the descriptor)."""
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    return _capi.Desc(
+        _capi.ABI_VERSION, _capi.CORE_IDS[identifier],
+        t.n_frequencies, t.frequencies.ctypes.data_as(C.POINTER(C.c_double)),
+        t.n_sites, ip(t.sites_rid), ip(t.sites_perm), ip(t.inverted_rid), ip(t.inverted_perm),
+        ip(t.overlap_offsets), ip(t.overlap_rid1), ip(t.overlap_rid2), ip(t.overlap_perm1), ip(t.overlap_perm2),
+        len(t.range_fwd_rid), ip(t.range_fwd_rid), ip(t.range_inv_rid),
+        float(spin_length), int(device),
+    )
+
+
+def jit_compile_check(identifier: str, tables: ProblemTables) -> int:
+    """Generate + compile the lattice-specialised kernel without a GPU; returns the cubin size in bytes."""
+    size = C.c_int64(0)
+    check(lib.pffrg_jit_compile_check(C.byref(make_descriptor(identifier, tables)), C.byref(size)))
+    return size.value
+
+
 class EffectiveAction:
     """Host copy of a vertex set in the reference's memory layout (float64 or float32)."""
 
@@ -115,17 +135,7 @@ class FrgCore:
         if self.normalization is None:
             self.normalization = 2.0 * self.spinLength if identifier == "SU2" else 1.0
 
-        t = tables
-        self._keep = t  # the descriptor borrows the numpy buffers during create only
-        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
-        desc = _capi.Desc(
-            _capi.ABI_VERSION, _capi.CORE_IDS[identifier],
-            t.n_frequencies, t.frequencies.ctypes.data_as(C.POINTER(C.c_double)),
-            t.n_sites, ip(t.sites_rid), ip(t.sites_perm), ip(t.inverted_rid), ip(t.inverted_perm),
-            ip(t.overlap_offsets), ip(t.overlap_rid1), ip(t.overlap_rid2), ip(t.overlap_perm1), ip(t.overlap_perm2),
-            len(t.range_fwd_rid), ip(t.range_fwd_rid), ip(t.range_inv_rid),
-            float(self.spinLength), int(device),
-        )
+        desc = make_descriptor(identifier, tables, self.spinLength, device)
         handle = C.c_void_p()
         check(lib.pffrg_create(C.byref(desc), C.byref(handle)))
         self._h = handle
