@@ -175,8 +175,13 @@ namespace
 		const auto t0 = std::chrono::steady_clock::now();
 		RpaProgram prog = buildRpaProgram(d, h->core, h->nb, h->threads / 32);
 		if ((long)prog.terms.size() > maxTerms) return PFFRG_OK;
+		// tuning knobs of the generated code (defaults chosen on B200)
+		int minBlocks = 2;
+		if (const char *e = getenv("PFFRG_JIT_CHUNK")) prog.chunk = std::max(4, atoi(e));
+		if (const char *e = getenv("PFFRG_JIT_ACC")) prog.maxAccumulators = std::max(1, atoi(e));
+		if (const char *e = getenv("PFFRG_JIT_MINBLOCKS")) minBlocks = std::max(1, atoi(e));
 		std::vector<char> cubin;
-		const std::string err = compileFlowKernel(h->core, h->nb, h->threads, 2, generateRpaSource(prog), cubin);
+		const std::string err = compileFlowKernel(h->core, h->nb, h->threads, minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the specialised flow kernel failed: %s", err.c_str());
 		CUDA_TRY(cudaLibraryLoadData(&h->jitLibrary, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
 		CUDA_TRY(cudaLibraryGetKernel(&h->jitKernel, h->jitLibrary, "pffrg_v4flow_jit"));
@@ -724,7 +729,7 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	if (nb < 16) return fail(PFFRG_ERR_UNSUPPORTED, "lattice too large for the specialised kernel");
 	RpaProgram prog = buildRpaProgram(d, d->core, nb, threads / 32);
 	std::vector<char> cubin;
-	const std::string err = compileFlowKernel(d->core, nb, threads, 2, generateRpaSource(prog), cubin);
+	const std::string err = compileFlowKernel(d->core, nb, threads, 2, KernelSizes{ L, (L + 15) / 16 * 16, channelsOf(d->core) * ((L + 15) / 16 * 16), d->n_frequencies }, generateRpaSource(prog), cubin);
 	if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
 	if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
 	return PFFRG_OK;

@@ -123,9 +123,10 @@ namespace pffrg
 	// signs and the site/spin maps at gather time.
 	struct __align__(16) AccessBuffer
 	{
-		double w[4];
-		int row[4];
-		int flags; // bit0: site/pair exchange, bit1: TRI zeta_mu*zeta_nu factor, bit(4+k): support k reads the s<->u mirrored entry
+		double w[4];     // weight for channels that are even under the s<->u frequency exchange
+		double wOdd[4];  // weight for channels that are odd under it (sign flipped where the mirrored entry is read)
+		int row[4];      // row index su*Nw + t
+		int flags;       // bit0: site/pair exchange, bit1: TRI zeta_mu*zeta_nu factor, bit(4+k): support k reads the s<->u mirrored entry
 		int pad[3];
 	};
 	constexpr int AB_EXCHANGE = 1, AB_TZ = 2;
@@ -190,6 +191,7 @@ namespace pffrg
 			ab.w[3] = b2 * b1;             ab.row[3] = rowIndex(nw, u1, u2, eu, 3, flags);
 		}
 		ab.flags = flags;
+		for (int k = 0; k < 4; ++k) ab.wOdd[k] = abSwapped(flags, k) ? -ab.w[k] : ab.w[k];
 	}
 
 	// TRIVertexTwoParticle::_zeta, src/TRI/TRIVertexTwoParticle.hpp:674-677

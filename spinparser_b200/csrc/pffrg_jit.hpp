@@ -28,7 +28,9 @@ namespace pffrg
 	// CUDA source of `__device__ void pffrg::rpaSpecialised(int warp, int lane, int nb, const double *st, double *rpaOut)`
 	std::string generateRpaSource(const RpaProgram &program);
 
+	struct KernelSizes { int L, Lp, RL, nw; }; // baked into the run-time compiled kernel as constants
+
 	// compile the vertex-flow kernel (embedded source + the generated RPA function) for sm_100a; returns an empty string on
 	// success and the compiler log otherwise. The kernel is `pffrg_v4flow_jit` with v4FlowKernel's parameter list.
-	std::string compileFlowKernel(int core, int nb, int threads, int minBlocks, const std::string &rpaSource, std::vector<char> &cubin);
+	std::string compileFlowKernel(int core, int nb, int threads, int minBlocks, const KernelSizes &sizes, const std::string &rpaSource, std::vector<char> &cubin);
 }

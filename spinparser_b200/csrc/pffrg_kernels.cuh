@@ -33,6 +33,20 @@ namespace pffrg
 		double spin;
 	};
 
+	// Problem sizes: run-time values in the precompiled kernels, compile-time constants in the run-time compiled one
+	// (pffrg_jit.cpp defines PFFRG_CONST_*), which turns the address arithmetic of the gathers into immediates.
+#ifdef PFFRG_CONST_L
+	__device__ __forceinline__ constexpr int sizeL(const Problem &) { return PFFRG_CONST_L; }
+	__device__ __forceinline__ constexpr int sizeLp(const Problem &) { return PFFRG_CONST_LP; }
+	__device__ __forceinline__ constexpr int sizeRL(const Problem &) { return PFFRG_CONST_RL; }
+	__device__ __forceinline__ constexpr int sizeNw(const Problem &) { return PFFRG_CONST_NW; }
+#else
+	__device__ __forceinline__ int sizeL(const Problem &P) { return P.L; }
+	__device__ __forceinline__ int sizeLp(const Problem &P) { return P.Lp; }
+	__device__ __forceinline__ int sizeRL(const Problem &P) { return P.RL; }
+	__device__ __forceinline__ int sizeNw(const Problem &P) { return P.nw; }
+#endif
+
 	struct NodeTable
 	{
 		int *count;   // [nw]
@@ -261,8 +275,8 @@ namespace pffrg
 		{
 			size_t o = 0;
 			mesh = o; o += sizeof(double) * nw;
-			bw = o; o += sizeof(double) * NB;
-			bW = o; o += sizeof(double) * NB;
+			bw = o; o += 0;
+			bW = o; o += sizeof(double) * NB * 2;
 			o = alignUp(o, 16);
 			ab = o; o += sizeof(AccessBuffer) * NB * 8;
 			loc = o; o += sizeof(double) * NB * 4 * C;
@@ -279,10 +293,12 @@ namespace pffrg
 	__device__ __forceinline__ void gatherSite(const Problem &P, const double *__restrict__ v4, const AccessBuffer &ab, int siteFwd, int siteInv, int permFwd, int permInv, double (&out)[channelsOf(CORE)])
 	{
 		constexpr int C = channelsOf(CORE);
-		// the table entry is 64 bytes, 16-byte aligned: four 128-bit shared loads
+		// the table entry is 16-byte aligned: 128-bit shared loads
 		const double2 w01 = *reinterpret_cast<const double2 *>(&ab.w[0]), w23 = *reinterpret_cast<const double2 *>(&ab.w[2]);
+		const double2 o01 = *reinterpret_cast<const double2 *>(&ab.wOdd[0]), o23 = *reinterpret_cast<const double2 *>(&ab.wOdd[2]);
 		const int4 rows = *reinterpret_cast<const int4 *>(&ab.row[0]);
 		const double wk[4] = { w01.x, w01.y, w23.x, w23.y };
+		const double ok[4] = { o01.x, o01.y, o23.x, o23.y };
 		const int rk[4] = { rows.x, rows.y, rows.z, rows.w };
 		const int flags = ab.flags;
 		const bool exchange = flags & AB_EXCHANGE;
@@ -293,18 +309,18 @@ namespace pffrg
 		#pragma unroll
 		for (int k = 0; k < 4; ++k)
 		{
-			// weight of the support for channels that are even / odd under the s<->u frequency exchange
-			const double wEven = wk[k];
-			const double wOdd = abSwapped(flags, k) ? -wEven : wEven;
-			const double *base = v4 + (size_t)rk[k] * P.RL + site;
+			const double *base = v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + (unsigned)site);
 			#pragma unroll
 			for (int c = 0; c < C; ++c)
 			{
-				// SU2/XYZ: only the density channel is odd (SU2VertexTwoParticle.hpp:622-625); TRI: factor -zeta of the second
-				// (first, if exchanged) spin index (TRIVertexTwoParticle.hpp:649-657), i.e. odd iff that index is the density one
-				const bool odd = (CORE == SU2) ? (c == 1) : (CORE == XYZ ? (c == 3) : (exchange ? ((c >> 2) == 3) : ((c & 3) == 3)));
+				// SU2/XYZ: only the density channel is odd under s<->u (SU2VertexTwoParticle.hpp:622-625); TRI: factor -zeta of the
+				// second (first, if exchanged) spin index (TRIVertexTwoParticle.hpp:649-657), i.e. odd iff that index is the density one
 				const int sc = storedChannel<CORE>(flags, c, perm);
-				out[c] += (odd ? wOdd : wEven) * __ldg(base + sc * P.Lp);
+				double w;
+				if (CORE == SU2) w = (c == 1) ? ok[k] : wk[k];
+				else if (CORE == XYZ) w = (c == 3) ? ok[k] : wk[k];
+				else w = (exchange ? ((c >> 2) == 3) : ((c & 3) == 3)) ? ok[k] : wk[k];
+				out[c] += w * __ldg(base + sc * sizeLp(P));
 			}
 		}
 		if (CORE == TRI)
@@ -444,7 +460,7 @@ namespace pffrg
 		constexpr int C = channelsOf(CORE);
 		constexpr int NBP = NB + 1;
 		constexpr int SUBS = 32 / NB;
-		const int L = P.L;
+		const int L = sizeL(P);
 		const int lane = tid & 31, wid = tid >> 5;
 		const int sub = lane / NB, node = lane - sub * NB;
 		const int slot = wid * SUBS + sub;
@@ -534,9 +550,8 @@ namespace pffrg
 		constexpr int C = channelsOf(CORE);
 		constexpr int NBP = NB + 1;
 		extern __shared__ __align__(16) unsigned char smemRaw[];
-		const FlowSmem<CORE, NB> lay(P.nw, P.L, cfg.groups);
+		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups);
 		double *mesh = reinterpret_cast<double *>(smemRaw + lay.mesh);
-		double *bw = reinterpret_cast<double *>(smemRaw + lay.bw);
 		double *bW = reinterpret_cast<double *>(smemRaw + lay.bW);
 		AccessBuffer *abTable = reinterpret_cast<AccessBuffer *>(smemRaw + lay.ab);
 		double *loc = reinterpret_cast<double *>(smemRaw + lay.loc);
@@ -545,7 +560,7 @@ namespace pffrg
 		double *rpaOut = reinterpret_cast<double *>(smemRaw + lay.rpa);
 
 		const int tid = threadIdx.x, nthreads = blockDim.x;
-		const int L = P.L, nw = P.nw;
+		const int L = sizeL(P), nw = sizeNw(P);
 		for (int i = tid; i < nw; i += nthreads) mesh[i] = P.mesh[i];
 		for (int i = tid; i < 2 * C * L; i += nthreads) rpaOut[i] = 0.0;
 
@@ -570,35 +585,43 @@ namespace pffrg
 		#pragma unroll
 		for (int c = 0; c < C; ++c) acc[c] = 0.0;
 
-		// channel order S, U, T keeps the shared-memory heavy t channel last
+		// Two passes: the s and u channels together (their nodes form one list; without the t channel's site-0 buffers a
+		// batch holds 2*NB nodes), then the shared-memory heavy t channel in batches of NB nodes.
 		#pragma unroll 1
-		for (int pass = 0; pass < 3; ++pass)
+		for (int pass = 0; pass < 2; ++pass)
 		{
-			const int ch = pass == 0 ? CH_S : (pass == 1 ? CH_U : CH_T);
-			const int xi = ch == CH_S ? so : (ch == CH_T ? ti : uo);
-			const int nNodes = N.count[xi];
-			const double *nodeW = N.wp + (size_t)xi * N.stride, *nodeWt = N.wt + (size_t)xi * N.stride;
-			const int nbuf = ch == CH_T ? 8 : 4;
-			// SU2: the u channel enters with a minus sign (SU2FrgCore.cpp:366,370,376); XYZ/TRI kernels carry it themselves
-			const double chSign = (CORE == SU2 && ch == CH_U) ? -1.0 : 1.0;
+			const bool tPass = pass == 1;
+			const int nFirst = N.count[tPass ? ti : so];               // nodes of the s (or t) channel
+			const int nNodes = tPass ? nFirst : nFirst + N.count[uo];  // ... followed by those of the u channel
+			const double *nodeW0 = N.wp + (size_t)(tPass ? ti : so) * N.stride, *nodeWt0 = N.wt + (size_t)(tPass ? ti : so) * N.stride;
+			const double *nodeW1 = N.wp + (size_t)uo * N.stride, *nodeWt1 = N.wt + (size_t)uo * N.stride;
+			const int nbuf = tPass ? 8 : 4;
+			const int batch = tPass ? NB : 2 * NB;
 
 			#pragma unroll 1
-			for (int b0 = 0; b0 < nNodes; b0 += NB)
+			for (int b0 = 0; b0 < nNodes; b0 += batch)
 			{
-				const int nb = min(NB, nNodes - b0);
+				const int nb = min(batch, nNodes - b0);
 				__syncthreads(); // previous batch fully consumed
 				// ---- phase 0: access buffers
 				for (int idx = tid; idx < nb * nbuf; idx += nthreads)
 				{
 					const int node = idx / nbuf, b = idx - node * nbuf;
-					const double wp = nodeW[b0 + node];
-					if (b == 0) { bw[node] = wp; bW[node] = chSign * nodeWt[b0 + node]; }
+					const int gn = b0 + node;
+					const int ch = tPass ? CH_T : (gn < nFirst ? CH_S : CH_U);
+					const double wp = gn < nFirst ? nodeW0[gn] : nodeW1[gn - nFirst];
+					if (b == 0)
+					{
+						// SU2: the u channel enters with a minus sign (SU2FrgCore.cpp:366,370,376); XYZ/TRI kernels carry it themselves
+						const double wt = gn < nFirst ? nodeWt0[gn] : nodeWt1[gn - nFirst];
+						bW[node] = (CORE == SU2 && ch == CH_U) ? -wt : wt;
+					}
 					double as, at, au; int exact;
 					bufferArguments<CORE>(f, ch, b, wp, as, at, au, exact);
-					makeAccessBuffer<CORE>(mesh, nw, as, at, au, exact, abTable[node * 8 + b]);
+					makeAccessBuffer<CORE>(mesh, nw, as, at, au, exact, abTable[node * nbuf + b]);
 				}
 				__syncthreads();
-				if (ch == CH_T)
+				if (tPass)
 				{
 					// ---- phase 0b: site-0 values of buffers 4..7 (getValueLocal)
 					for (int idx = tid; idx < nb * 4 * C; idx += nthreads)
@@ -608,7 +631,7 @@ namespace pffrg
 						const int sc = storedChannel<CORE>(ab.flags, c, PERM_IDENTITY);
 						double v = 0.0;
 						#pragma unroll
-						for (int k = 0; k < 4; ++k) v += supportSign<CORE>(ab.flags, k, c) * ab.w[k] * __ldg(v4 + (size_t)ab.row[k] * P.RL + sc * P.Lp);
+						for (int k = 0; k < 4; ++k) v += supportSign<CORE>(ab.flags, k, c) * ab.w[k] * __ldg(v4 + (size_t)ab.row[k] * sizeRL(P) + sc * sizeLp(P));
 						loc[idx] = v;
 					}
 					__syncthreads();
@@ -620,12 +643,12 @@ namespace pffrg
 					{
 						double A[4][C];
 						#pragma unroll
-						for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, abTable[node * 8 + b], siteFwd, siteInv, permFwd, permInv, A[b]);
+						for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, abTable[node * nbuf + b], siteFwd, siteInv, permFwd, permInv, A[b]);
 						const double W = bW[node];
 						double K[C];
-						if (ch != CH_T)
+						if (!tPass)
 						{
-							ladderTerms<CORE>(ch, A, K);
+							ladderTerms<CORE>((b0 + node) < nFirst ? CH_S : CH_U, A, K);
 						}
 						else
 						{
@@ -664,7 +687,7 @@ namespace pffrg
 						for (int c = 0; c < C; ++c) acc[c] += W * K[c];
 					}
 				}
-				if (ch == CH_T)
+				if (tPass)
 				{
 					__syncthreads();
 					// ---- phase 2: RPA lattice sum
@@ -692,7 +715,7 @@ namespace pffrg
 			for (int gg = 0; gg < cfg.groups; ++gg) v += part[gg * C * L + e];
 			v /= TWO_PI;
 			const int c = e / L, jj = e - c * L;
-			flow[(size_t)item * P.RL + c * P.Lp + jj] = v;
+			flow[(size_t)item * sizeRL(P) + c * sizeLp(P) + jj] = v;
 			bad |= (v != v);
 		}
 		if (bad) atomicOr(nanFlag, 1);
