@@ -146,6 +146,13 @@ void *pffrg_stream(pffrg_handle h);
  * a build-time check that the run-time compiled path works for this lattice. *cubin_bytes receives the code size. */
 int pffrg_jit_compile_check(const pffrg_desc *desc, int64_t *cubin_bytes);
 
+/* Bilinear term tables of the TRI core as the kernels use them, derived from the spin algebra (not stored): replaces the
+ * machine-generated statement lists of src/TRI/TRIFrgCore.cpp:198-711 (region 0, pp ladder), :2389-2902 (1, ph ladder),
+ * :1298-1811 (2, chalice), :1855-2368 (3, inverse chalice), :739-1252 (4, RPA; indices before the overlap's spin permutations).
+ * Writes up to `capacity` rows {out channel, sign, first factor channel, second factor channel} and returns the number of
+ * terms per buffer pair (256, or 64 for the RPA). Used by the parity tests to compare against the reference term by term. */
+int pffrg_tri_terms(int region, int32_t *terms, int capacity);
+
 /* page-locked host memory for the arrays passed to set_state / get_state / get_flow (plain memory works too, but
  * transfers from pinned buffers run at full PCIe speed). Returns NULL on failure. */
 void *pffrg_host_alloc(size_t bytes);

@@ -351,7 +351,10 @@ static double gather_local(const pfo_problem *p, const double *const *v4, const 
 	static const int ident[3] = { 0, 1, 2 };
 	double value = 0.0;
 	int sc = stored_channel(p, ab, c, ident);
-	for (int k = 0; k < ab->n; ++k) value += ab_sign(p, ab, k, c) * ab->w[k] * v4_elem(p, v4, ab->off[k], sc, 0);
+	/* TRI: getValueLocal swaps (s1, s2) under pairExchange BEFORE it indexes the sign table (TRIVertexTwoParticle.hpp:349-353),
+	 * unlike getValueSuperbundle (:385), which indexes it with the unswapped output pair */
+	int csign = (p->core == PFO_TRI && ab->exchange) ? 4 * (c % 4) + c / 4 : c;
+	for (int k = 0; k < ab->n; ++k) value += ab_sign(p, ab, k, csign) * ab->w[k] * v4_elem(p, v4, ab->off[k], sc, 0);
 	return value;
 }
 

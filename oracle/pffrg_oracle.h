@@ -6,7 +6,7 @@
  *
  * Parity pin: this restatement is checked (tests/test_oracle_port.py) against dumps of the UNMODIFIED reference
  * compiled in FP64 (oracle/_ref/oracle64, built by oracle/Makefile from /root/reference/src) that are committed
- * under tests/golden/, and through them against the reference's own golden files test/scripted/assets/*.ref.
+ * under tests/golden/, and through them against the reference's own golden files test/scripted/assets/test_reference{1,2,3}.ref.
  *
  * All arrays are in the reference's memory layout (file:line relative to /root/reference):
  *   v2   [Nw]                                    src/SU2/SU2VertexSingleParticle.hpp:100-102

@@ -131,7 +131,7 @@ namespace
 	{
 		if (core == SU2) return nb == 32 ? flowSmemBytes<SU2, 32>(nw, L, groups) : nb == 16 ? flowSmemBytes<SU2, 16>(nw, L, groups) : flowSmemBytes<SU2, 8>(nw, L, groups);
 		if (core == XYZ) return nb == 32 ? flowSmemBytes<XYZ, 32>(nw, L, groups) : nb == 16 ? flowSmemBytes<XYZ, 16>(nw, L, groups) : flowSmemBytes<XYZ, 8>(nw, L, groups);
-		return 0;
+		return nb == 32 ? flowSmemBytes<TRI, 32>(nw, L, groups) : nb == 16 ? flowSmemBytes<TRI, 16>(nw, L, groups) : nb == 8 ? flowSmemBytes<TRI, 8>(nw, L, groups) : flowSmemBytes<TRI, 4>(nw, L, groups);
 	}
 
 	template <int CORE, int NB>
@@ -160,7 +160,7 @@ namespace
 		}
 		if (h->core == SU2) return h->nb == 32 ? launchFlow<SU2, 32>(h, begin, count) : h->nb == 16 ? launchFlow<SU2, 16>(h, begin, count) : launchFlow<SU2, 8>(h, begin, count);
 		if (h->core == XYZ) return h->nb == 32 ? launchFlow<XYZ, 32>(h, begin, count) : h->nb == 16 ? launchFlow<XYZ, 16>(h, begin, count) : launchFlow<XYZ, 8>(h, begin, count);
-		return cudaErrorNotSupported;
+		return h->nb == 32 ? launchFlow<TRI, 32>(h, begin, count) : h->nb == 16 ? launchFlow<TRI, 16>(h, begin, count) : h->nb == 8 ? launchFlow<TRI, 8>(h, begin, count) : launchFlow<TRI, 4>(h, begin, count);
 	}
 
 	// Compile and load the lattice-specialised kernel. Controlled by the environment: PFFRG_JIT=0 disables it,
@@ -171,7 +171,7 @@ namespace
 		if (env && atoi(env) == 0) return PFFRG_OK;
 		long maxTerms = 60000;
 		if (const char *e = getenv("PFFRG_JIT_MAX_TERMS")) maxTerms = atol(e);
-		if (h->nb < 16) return PFFRG_OK;
+		if (h->nb < 16 || h->core == TRI) return PFFRG_OK; // TRI: table-driven RPA phase (rpaTri), precompiled kernels
 		const auto t0 = std::chrono::steady_clock::now();
 		RpaProgram prog = buildRpaProgram(d, h->core, h->nb, h->threads / 32);
 		if ((long)prog.terms.size() > maxTerms) return PFFRG_OK;
@@ -443,7 +443,6 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 		if (!(d->frequencies[i] > 0) || (i > 0 && !(d->frequencies[i] > d->frequencies[i - 1]))) return fail(PFFRG_ERR_ARGUMENT, "frequency mesh must be positive and strictly ascending (index %d)", i);
 	if (d->n_frequencies > 512) return fail(PFFRG_ERR_UNSUPPORTED, "more than 512 frequencies are not supported");
 	if (d->n_sites > 256) return fail(PFFRG_ERR_UNSUPPORTED, "more than 256 representative sites are not supported yet (got %d)", d->n_sites);
-	if (d->core == PFFRG_CORE_TRI) return fail(PFFRG_ERR_UNSUPPORTED, "the TRI core is not available in this build");
 	const int L = d->n_sites;
 	for (int j = 0; j < L; ++j)
 		if (d->sites_rid[j] < 0 || d->sites_rid[j] >= L || d->inverted_rid[j] < 0 || d->inverted_rid[j] >= L) return fail(PFFRG_ERR_ARGUMENT, "site table entry %d out of range", j);
@@ -477,8 +476,11 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	h->stride = (padded - L) * 4 <= padded ? padded : L;
 	h->groups = std::max(1, 256 / h->stride);
 	h->threads = std::max(64, (h->groups * h->stride + 31) / 32 * 32);
+	// SU2/XYZ: two CTAs per SM (100 KB each); the TRI core stages four 16-channel RPA operand buffers and runs one CTA per SM
 	h->nb = 32;
-	while (h->nb > 8 && flowSmemBytes(h->core, h->nb, h->nw, L, h->groups) > 100 * 1024) h->nb >>= 1;
+	const int minNb = h->core == TRI ? 4 : 8;
+	const size_t smemTarget = h->core == TRI ? 200 * 1024 : 100 * 1024;
+	while (h->nb > minNb && flowSmemBytes(h->core, h->nb, h->nw, L, h->groups) > smemTarget) h->nb >>= 1;
 	h->smemBytes = flowSmemBytes(h->core, h->nb, h->nw, L, h->groups);
 	if (h->smemBytes > (size_t)prop.sharedMemPerBlockOptin) { const size_t need = h->smemBytes; delete h; return fail(PFFRG_ERR_UNSUPPORTED, "flow kernel needs %zu bytes of shared memory", need); }
 	h->nslots = (h->threads / 32) * (32 / h->nb);
@@ -733,6 +735,35 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
 	if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
 	return PFFRG_OK;
+}
+
+int pffrg_tri_terms(int region, int32_t *terms, int capacity)
+{
+	// region 0: pp ladder, 1: ph ladder, 2: chalice, 3: inverse chalice (rows {out, sign, first, second}), 4: RPA (rows {out, sign, mu*4+k, k*4+nu})
+	if (region < 0 || region > 4 || (!terms && capacity > 0)) return fail(PFFRG_ERR_ARGUMENT, "bad region or null buffer");
+	int n = 0;
+	auto emit = [&](const tri::Term &t, int first, int second)
+	{
+		if (t.exponent & 1) return false; // an imaginary coefficient would mean the algebra is inconsistent
+		if (n < capacity) { terms[4 * n] = t.out; terms[4 * n + 1] = (int)t.sign; terms[4 * n + 2] = first; terms[4 * n + 3] = second; }
+		++n;
+		return true;
+	};
+	bool consistent = true;
+	if (region == 4)
+	{
+		for (int mu = 0; mu < 4; ++mu) for (int k = 0; k < 4; ++k) for (int nu = 0; nu < 4; ++nu) consistent &= emit(tri::rpa(mu, k, nu), 4 * mu + k, 4 * k + nu);
+	}
+	else
+		for (int c1 = 0; c1 < 16; ++c1)
+			for (int c2 = 0; c2 < 16; ++c2)
+			{
+				const int a = c1 >> 2, b = c1 & 3, g = c2 >> 2, dd = c2 & 3;
+				const tri::Term t = region == 0 ? tri::ladder<false>(a, b, g, dd) : region == 1 ? tri::ladder<true>(a, b, g, dd) : region == 2 ? tri::chalice(a, b, g, dd) : tri::inverseChalice(a, b, g, dd);
+				consistent &= emit(t, c1, c2);
+			}
+	if (!consistent) return fail(PFFRG_ERR_STATE, "TRI spin algebra produced an imaginary coefficient");
+	return n;
 }
 
 void *pffrg_host_alloc(size_t bytes)

@@ -224,4 +224,58 @@ namespace pffrg
 		return 4 * m + n;
 	}
 	constexpr int PERM_IDENTITY = 0 | (1 << 2) | (2 << 4);
+
+	// ---- spin algebra of the TRI core ------------------------------------------------------------------------------------
+	// The TRI vertex is Gamma = sum_{mu,nu} Gamma^{mu nu} Theta^{mu nu}, Theta^{mu nu} = c_{mu nu} sigma^mu (x) sigma^nu with
+	// sigma^{0,1,2} the Pauli matrices, sigma^3 (the "density" component d) the identity, and c = i for the mixed spin-density
+	// components, 1 otherwise (which keeps every Gamma^{mu nu} real for time-reversal invariant models). Every bilinear term of
+	// the flow equations is the coefficient of Theta^{mu nu} in a product of two such operators:
+	//   pp ladder        + [ (sigma^g sigma^a) (x) (sigma^d sigma^b) ]         A^{ab} B^{gd}   (src/TRI/TRIFrgCore.cpp:198-711)
+	//   ph ladder        - [ (sigma^g sigma^a) (x) (sigma^b sigma^d) ]         A^{ab} B^{gd}   (:2389-2902)
+	//   chalice          - [ sigma^a (x) (sigma^d sigma^b sigma^g) ]           A^{ab} B0^{gd}  (:1298-1811), B0 = site-0 value
+	//   inverse chalice  - [ (sigma^d sigma^a sigma^g) (x) sigma^b ]           A^{ab} B0^{gd}  (:1855-2368)
+	//   RPA              + 2 c_{mu k} c_{k nu} / c_{mu nu}                      A^{mu k}[r1] B^{k nu}[r2]  (:739-1252)
+	// Products of Pauli matrices only generate phases i^n, so the whole algebra is integer arithmetic modulo 4 and can be
+	// evaluated at compile time. tests/test_tri_tables.py checks the resulting tables term by term against the reference file.
+	namespace tri
+	{
+		__host__ __device__ constexpr int enc(int a) { return (a + 1) & 3; }                     // d -> 0, x -> 1, y -> 2, z -> 3
+		// sigma^a sigma^b = i^mulPhase(a,b) sigma^mulIndex(a,b)
+		__host__ __device__ constexpr int mulIndex(int a, int b) { return ((enc(a) ^ enc(b)) + 3) & 3; }
+		__host__ __device__ constexpr int mulPhase(int a, int b) { return (a == 3 || b == 3 || a == b) ? 0 : (((b - a + 3) % 3 == 1) ? 1 : 3); }
+		__host__ __device__ constexpr int mixed(int a, int b) { return ((a == 3) != (b == 3)) ? 1 : 0; } // c_{ab} = i^mixed(a,b)
+		// i^e for e even -> +-1 (odd exponents do not occur; the host-side table export asserts that)
+		__host__ __device__ constexpr double phaseSign(int e) { return ((e & 3) == 0) ? 1.0 : -1.0; }
+
+		struct Term { int out; int exponent; double sign; };
+
+		// ladder term A^{ab} B^{gd} -> Theta^{mu nu}; PH = particle-hole (u channel), else particle-particle (s channel)
+		template <bool PH>
+		__host__ __device__ constexpr Term ladder(int a, int b, int g, int d)
+		{
+			const int mu = mulIndex(g, a), nu = mulIndex(b, d);
+			const int e = mixed(a, b) + mixed(g, d) + mulPhase(g, a) + (PH ? mulPhase(b, d) : mulPhase(d, b)) + 4 - mixed(mu, nu);
+			return { 4 * mu + nu, e & 3, PH ? -phaseSign(e) : phaseSign(e) };
+		}
+		// chalice term A^{ab} B0^{gd} -> Theta^{a nu}, nu from sigma^d sigma^b sigma^g
+		__host__ __device__ constexpr Term chalice(int a, int b, int g, int d)
+		{
+			const int m1 = mulIndex(d, b), nu = mulIndex(m1, g);
+			const int e = mixed(a, b) + mixed(g, d) + mulPhase(d, b) + mulPhase(m1, g) + 4 - mixed(a, nu);
+			return { 4 * a + nu, e & 3, -phaseSign(e) };
+		}
+		// inverse chalice term A^{ab} B0^{gd} -> Theta^{mu b}, mu from sigma^d sigma^a sigma^g
+		__host__ __device__ constexpr Term inverseChalice(int a, int b, int g, int d)
+		{
+			const int m1 = mulIndex(d, a), mu = mulIndex(m1, g);
+			const int e = mixed(a, b) + mixed(g, d) + mulPhase(d, a) + mulPhase(m1, g) + 4 - mixed(mu, b);
+			return { 4 * mu + b, e & 3, -phaseSign(e) };
+		}
+		// RPA term A^{mu k} B^{k nu} -> Theta^{mu nu} (the factor 2 = tr(sigma sigma) is applied by the caller)
+		__host__ __device__ constexpr Term rpa(int mu, int k, int nu)
+		{
+			const int e = mixed(mu, k) + mixed(k, nu) + 4 - mixed(mu, nu);
+			return { 4 * mu + nu, e & 3, phaseSign(e) };
+		}
+	}
 }

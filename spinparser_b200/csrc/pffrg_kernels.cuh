@@ -270,7 +270,7 @@ namespace pffrg
 	{
 		static constexpr int C = channelsOf(CORE);
 		static constexpr int NBP = NB + 1;
-		size_t mesh, bw, bW, ab, loc, st, part, rpa, total;
+		size_t mesh, bw, bW, ab, loc, wmat, st, part, rpa, total;
 		__host__ __device__ FlowSmem(int nw, int L, int groups)
 		{
 			size_t o = 0;
@@ -280,6 +280,8 @@ namespace pffrg
 			o = alignUp(o, 16);
 			ab = o; o += sizeof(AccessBuffer) * NB * 8;
 			loc = o; o += sizeof(double) * NB * 4 * C;
+			o = alignUp(o, 16);
+			wmat = o; o += (CORE == TRI) ? sizeof(double) * NB * 4 * 32 : 0; // TRI: contracted site-0 matrices, see triLocalMatrices
 			o = alignUp(o, 16);
 			st = o; o += sizeof(double) * RpaStage<CORE>::buffers * C * L * NBP;
 			part = o; o += sizeof(double) * groups * C * L;
@@ -446,6 +448,209 @@ namespace pffrg
 		}
 	}
 
+	// ---- TRI bilinear forms (src/TRI/TRIFrgCore.cpp:198-711, :1298-2368, :2389-2902), generated from the spin algebra in
+	// pffrg_device.cuh at compile time: after unrolling, every sign is an immediate and every index a register name.
+	// pp / ph ladder of one buffer pair: K^{mu nu} += sum_{ab,gd} sign A^{ab} B^{gd}, 256 multiply-adds
+	template <bool PH>
+	__device__ __forceinline__ void triLadder(const double (&A)[16], const double (&B)[16], double (&K)[16])
+	{
+		#pragma unroll
+		for (int c1 = 0; c1 < 16; ++c1)
+		{
+			#pragma unroll
+			for (int c2 = 0; c2 < 16; ++c2)
+			{
+				const tri::Term t = tri::ladder<PH>(c1 >> 2, c1 & 3, c2 >> 2, c2 & 3);
+				K[t.out] = fma(t.sign * A[c1], B[c2], K[t.out]);
+			}
+		}
+	}
+
+	// The chalice terms multiply a gathered buffer with a site-0 value B0^{gd} that is the same for all sites of a node, so the
+	// sum over (g, d) is done once per node: K^{a nu} += sum_b A^{ab} Wc[a == d][b][nu] (chalice), K^{mu b} += sum_a A^{ab}
+	// Wi[b == d][a][mu] (inverse chalice). The signs depend on the spectator index only through its type (spin / density).
+	// W layout per (node, local buffer n): [type][4][4]; n = 0, 2 chalice (paired with gathered buffers 0, 2), n = 1, 3 inverse.
+	__device__ inline void triLocalMatrices(const double *loc /* [16] */, bool inverse, double *W /* [2][4][4] */, int entry)
+	{
+		// entry = type * 16 + 4 * (b or a) + (nu or mu)
+		const int type = entry >> 4, x = (entry >> 2) & 3, o = entry & 3;
+		const int spectator = type ? 3 : 0;
+		double v = 0.0;
+		for (int g = 0; g < 4; ++g)
+			for (int d = 0; d < 4; ++d)
+			{
+				const tri::Term t = inverse ? tri::inverseChalice(x, spectator, g, d) : tri::chalice(spectator, x, g, d);
+				const int want = inverse ? 4 * o + spectator : 4 * spectator + o;
+				if (t.out == want) v += t.sign * loc[4 * g + d];
+			}
+		W[entry] = v;
+	}
+	__device__ __forceinline__ void triChaliceApply(const double (&A)[16], const double *W, double (&K)[16])
+	{
+		#pragma unroll
+		for (int a = 0; a < 4; ++a)
+		{
+			#pragma unroll
+			for (int b = 0; b < 4; ++b)
+			{
+				#pragma unroll
+				for (int nu = 0; nu < 4; ++nu) K[4 * a + nu] = fma(A[4 * a + b], W[(a == 3 ? 16 : 0) + 4 * b + nu], K[4 * a + nu]);
+			}
+		}
+	}
+	__device__ __forceinline__ void triInverseChaliceApply(const double (&A)[16], const double *W, double (&K)[16])
+	{
+		#pragma unroll
+		for (int b = 0; b < 4; ++b)
+		{
+			#pragma unroll
+			for (int a = 0; a < 4; ++a)
+			{
+				#pragma unroll
+				for (int mu = 0; mu < 4; ++mu) K[4 * mu + b] = fma(A[4 * a + b], W[(b == 3 ? 16 : 0) + 4 * a + mu], K[4 * mu + b]);
+			}
+		}
+	}
+
+	__device__ __forceinline__ double (&acc16(double *p))[16] { return *reinterpret_cast<double (*)[16]>(p); }
+
+	// phase 1 of the TRI core for thread (g, j): the four gathered buffers are processed as the pairs (0,1) and (2,3) so that
+	// only two of them are live at a time (16 channels each)
+	template <int NB>
+	__device__ __forceinline__ void triPhase1(const Problem &P, const FlowConfig &cfg, const double *__restrict__ v4, const AccessBuffer *abTable, const double *bW, const double *wmat,
+		double *st, double (&acc)[16], int g, int j, int nb, int nbuf, bool tPass, int b0, int nFirst, int siteFwd, int siteInv, int permFwd, int permInv)
+	{
+		constexpr int NBP = NB + 1;
+		const int L = sizeL(P);
+		for (int node = g; node < nb; node += cfg.groups)
+		{
+			const double W = bW[node];
+			const bool phLadder = !tPass && (b0 + node) >= nFirst;
+			double K[16];
+			#pragma unroll
+			for (int c = 0; c < 16; ++c) K[c] = 0.0;
+			#pragma unroll 1
+			for (int pr = 0; pr < 2; ++pr)
+			{
+				double A0[16], A1[16];
+				gatherSite<TRI>(P, v4, abTable[node * nbuf + 2 * pr], siteFwd, siteInv, permFwd, permInv, A0);
+				gatherSite<TRI>(P, v4, abTable[node * nbuf + 2 * pr + 1], siteFwd, siteInv, permFwd, permInv, A1);
+				if (!tPass)
+				{
+					if (phLadder) triLadder<true>(A0, A1, K); else triLadder<false>(A0, A1, K);
+				}
+				else
+				{
+					triChaliceApply(A0, wmat + (node * 4 + 2 * pr) * 32, K);
+					triInverseChaliceApply(A1, wmat + (node * 4 + 2 * pr + 1) * 32, K);
+					// RPA operands of the pairs (0,1) and (2,3); the prefactor 2 (TRIFrgCore.cpp:741-746) and the node weight are folded into A
+					#pragma unroll
+					for (int c = 0; c < 16; ++c)
+					{
+						st[(((2 * pr) * 16 + c) * L + j) * NBP + node] = 2.0 * W * A0[c];
+						st[(((2 * pr + 1) * 16 + c) * L + j) * NBP + node] = A1[c];
+					}
+				}
+			}
+			#pragma unroll
+			for (int c = 0; c < 16; ++c) acc[c] += W * K[c];
+		}
+	}
+
+	// TRI RPA phase (src/TRI/TRIFrgCore.cpp:733-1252): R^{mu nu}[rid] = sum_i sum_k eta(mu,k,nu) A^{p1 mu, p1 k}[rid1_i] B^{p2 k, p2 nu}[rid2_i]
+	// for the buffer pairs (0,1) and (2,3), p1/p2 the overlap's spin permutations. Same word stream and slot scheme as
+	// rpaGeneric; operands are staged per channel (st[buffer][channel][rid][node]) so that the permutations become address
+	// offsets: operand A is loaded permuted, the B sum is accumulated permuted, and the contraction is 64 multiply-adds
+	// per group of terms sharing (rid1, p1, p2).
+	template <int NB>
+	__device__ __forceinline__ void rpaTri(const Problem &P, const FlowConfig &cfg, const double *st, double *rpaOut, int tid, int nb)
+	{
+		constexpr int NBP = NB + 1;
+		constexpr int SUBS = 32 / NB;
+		const int L = sizeL(P);
+		const int lane = tid & 31, wid = tid >> 5;
+		const int sub = lane / NB, node = lane - sub * NB;
+		const int slot = wid * SUBS + sub;
+		const bool active = node < nb;
+		const unsigned subMask = (NB == 32) ? 0xffffffffu : (((1u << (NB & 31)) - 1u) << (sub * NB));
+		if (slot >= cfg.nslots) return;
+		const int chStride = L * NBP;
+		for (int ti = P.rpa_slot_off[slot]; ti < P.rpa_slot_off[slot + 1]; ++ti)
+		{
+			const int4 task = P.rpa_tasks[ti];
+			double r[16];
+			#pragma unroll
+			for (int c = 0; c < 16; ++c) r[c] = 0.0;
+			if (active)
+			{
+				#pragma unroll 1
+				for (int pair = 0; pair < 2; ++pair)
+				{
+					const double *stA = st + (size_t)(2 * pair) * 16 * chStride + node;
+					const double *stB = stA + 16 * chStride;
+					double a[16], t[16];
+					int offB[16];
+					#pragma unroll
+					for (int c = 0; c < 16; ++c) { a[c] = 0.0; t[c] = 0.0; offB[c] = 0; }
+					auto flush = [&]()
+					{
+						#pragma unroll
+						for (int mu = 0; mu < 4; ++mu)
+						{
+							#pragma unroll
+							for (int k = 0; k < 4; ++k)
+							{
+								#pragma unroll
+								for (int nu = 0; nu < 4; ++nu) r[4 * mu + nu] = fma(tri::rpa(mu, k, nu).sign * a[4 * mu + k], t[4 * k + nu], r[4 * mu + nu]);
+							}
+						}
+						#pragma unroll
+						for (int c = 0; c < 16; ++c) t[c] = 0.0;
+					};
+					#pragma unroll 1
+					for (int i = task.y; i < task.z; ++i)
+					{
+						const unsigned w = __ldg(P.rpa_words + i);
+						if (w >> 31)
+						{
+							flush();
+							const int p1 = (w >> 16) & 0x3f, p2 = (w >> 22) & 0x3f;
+							const int q1[4] = { p1 & 3, (p1 >> 2) & 3, (p1 >> 4) & 3, 3 }, q2[4] = { p2 & 3, (p2 >> 2) & 3, (p2 >> 4) & 3, 3 };
+							const double *pa = stA + (w & 0xffffu);
+							#pragma unroll
+							for (int m = 0; m < 4; ++m)
+							{
+								#pragma unroll
+								for (int n = 0; n < 4; ++n)
+								{
+									a[4 * m + n] = pa[(4 * q1[m] + q1[n]) * chStride];
+									offB[4 * m + n] = (4 * q2[m] + q2[n]) * chStride;
+								}
+							}
+						}
+						else
+						{
+							const double m = (double)(int)(w >> 16);
+							const double *pb = stB + (w & 0xffffu);
+							#pragma unroll
+							for (int c = 0; c < 16; ++c) t[c] = fma(m, pb[offB[c]], t[c]);
+						}
+					}
+					flush();
+				}
+			}
+			__syncwarp(subMask);
+			#pragma unroll
+			for (int c = 0; c < 16; ++c)
+			{
+				double v = r[c];
+				#pragma unroll
+				for (int o = NB >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(subMask, v, o);
+				if (node == 0) rpaOut[c * L + task.x] += v;
+			}
+		}
+	}
+
 #ifdef PFFRG_JIT_RPA
 	// generated per lattice (pffrg_jit.cpp): the RPA sum of one batch for the outputs owned by `warp`
 	__device__ void rpaSpecialised(int warp, int lane, int nb, const double *st, double *rpaOut);
@@ -555,6 +760,7 @@ namespace pffrg
 		double *bW = reinterpret_cast<double *>(smemRaw + lay.bW);
 		AccessBuffer *abTable = reinterpret_cast<AccessBuffer *>(smemRaw + lay.ab);
 		double *loc = reinterpret_cast<double *>(smemRaw + lay.loc);
+		double *wmat = reinterpret_cast<double *>(smemRaw + lay.wmat);
 		double *st = reinterpret_cast<double *>(smemRaw + lay.st);
 		double *part = reinterpret_cast<double *>(smemRaw + lay.part);
 		double *rpaOut = reinterpret_cast<double *>(smemRaw + lay.rpa);
@@ -629,15 +835,31 @@ namespace pffrg
 						const int node = idx / (4 * C), r = idx - node * 4 * C, n = r / C, c = r - n * C;
 						const AccessBuffer &ab = abTable[node * 8 + 4 + n];
 						const int sc = storedChannel<CORE>(ab.flags, c, PERM_IDENTITY);
+						// TRI: getValueLocal swaps the spin indices under pair exchange BEFORE indexing the sign table
+						// (TRIVertexTwoParticle.hpp:349-353), unlike getValueSuperbundle (:385)
+						const int cs = (CORE == TRI && (ab.flags & AB_EXCHANGE)) ? (4 * (c & 3) + (c >> 2)) : c;
 						double v = 0.0;
 						#pragma unroll
-						for (int k = 0; k < 4; ++k) v += supportSign<CORE>(ab.flags, k, c) * ab.w[k] * __ldg(v4 + (size_t)ab.row[k] * sizeRL(P) + sc * sizeLp(P));
+						for (int k = 0; k < 4; ++k) v += supportSign<CORE>(ab.flags, k, cs) * ab.w[k] * __ldg(v4 + (size_t)ab.row[k] * sizeRL(P) + sc * sizeLp(P));
 						loc[idx] = v;
 					}
 					__syncthreads();
+					if (CORE == TRI)
+					{
+						for (int idx = tid; idx < nb * 4 * 32; idx += nthreads)
+						{
+							const int node = idx >> 7, n = (idx >> 5) & 3;
+							triLocalMatrices(loc + (node * 4 + n) * 16, (n & 1) != 0, wmat + (node * 4 + n) * 32, idx & 31);
+						}
+						__syncthreads();
+					}
 				}
 				// ---- phase 1: gathers + bilinear forms
-				if (worker)
+				if constexpr (CORE == TRI)
+				{
+					if (worker) triPhase1<NB>(P, cfg, v4, abTable, bW, wmat, st, acc16(acc), g, j, nb, nbuf, tPass, b0, nFirst, siteFwd, siteInv, permFwd, permInv);
+				}
+				else if (worker)
 				{
 					for (int node = g; node < nb; node += cfg.groups)
 					{
@@ -695,7 +917,8 @@ namespace pffrg
 					if (JIT) rpaSpecialised(tid >> 5, tid & 31, nb, st, rpaOut);
 					else
 #endif
-					rpaGeneric<CORE, NB>(P, cfg, st, rpaOut, tid, nb);
+					if constexpr (CORE == TRI) rpaTri<NB>(P, cfg, st, rpaOut, tid, nb);
+					else rpaGeneric<CORE, NB>(P, cfg, st, rpaOut, tid, nb);
 				}
 			}
 		}
@@ -723,7 +946,7 @@ namespace pffrg
 
 #ifndef PFFRG_JIT_RPA
 	template <int CORE, int NB>
-	__global__ void v4FlowKernel(Problem P, NodeTable N, FlowConfig cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
+	__global__ void __launch_bounds__(256) v4FlowKernel(Problem P, NodeTable N, FlowConfig cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
 	{
 		v4FlowBody<CORE, NB, false>(P, N, cfg, v4, flow, itemBegin, nanFlag);
 	}

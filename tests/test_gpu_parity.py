@@ -6,7 +6,8 @@ from conftest import assert_parity, dumped_steps, golden
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["su2_square_r3_nw10", "su2_kagome_r4_nw8", "su2_kagome_r7_nw6", "xyz_honeycomb_kitaev_r3_nw10", "xyz_kagome_r4_nw8"]
+CASES = ["su2_square_r3_nw10", "su2_kagome_r4_nw8", "su2_kagome_r7_nw6", "xyz_honeycomb_kitaev_r3_nw10", "xyz_kagome_r4_nw8",
+         "tri_honeycomb_kg_r3_nw8", "tri_kagome_dm_r3_nw6"]
 
 
 def _core(d):
@@ -43,7 +44,7 @@ def test_one_step_flow_matches_reference(case):
     core.close()
 
 
-@pytest.mark.parametrize("case", ["su2_square_r3_nw10", "xyz_honeycomb_kitaev_r3_nw10"])
+@pytest.mark.parametrize("case", ["su2_square_r3_nw10", "xyz_honeycomb_kitaev_r3_nw10", "tri_kagome_dm_r3_nw6"])
 def test_float32_host_arrays_round_trip(case):
     d = golden(case)
     name, core = _core(d)
