@@ -37,6 +37,7 @@ WORKLOADS = {
     "square_r4_su2_nw32": "square-Heisenberg (SU2, square r=4, L=9, Nw=32, 16896 items)",
     "pyrochlore_r8_su2_nw64": "pyrochlore-Heisenberg (SU2, pyrochlore r=8, L=103, Nw=64, 133120 items, 27.4M vertex entries)",
     "honeycomb_kitaev_r7_xyz_nw64": "honeycomb-Kitaev (XYZ, honeycomb r=7, L=18, Nw=64, 133120 items, 9.6M vertex entries)",
+    "kagome_dm_r7_tri_nw64": "kagome-DM (TRI, kagome r=7, L=34, Nw=64, 133120 items, 72.4M vertex entries)",
 }
 N_CH = {"SU2": 2, "XYZ": 4, "TRI": 16}
 
@@ -88,6 +89,17 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def profiled_traffic(workload):
+    """DRAM bytes per launch of the flow kernel from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_summary.json, written by tools/ncu_summary.py), or None when there is none."""
+    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        rec = json.load(f).get(workload)
+    return rec.get("dram_bytes_per_launch") if rec else None
 
 
 def load_tables(workload):
@@ -299,6 +311,7 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = 1.0 / float(e2e_t.mean()) if args.e2e_steps else None
     state_bytes = 8 * (nw + C * L * nf)
+    state_dev_mb = 8e-6 * C * ((L + 3) // 4 * 4) * nf
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -310,14 +323,14 @@ def main():
                        "cutoff": [cutoffs[first_timed], cutoffs[first_timed + args.steps - 1]],
                        "state": "seeded synthetic vertex" if args.synthetic_state else f"physical: flow run on the GPU from the bare couplings for {args.start_step + args.warmup} steps ({t_setup:.1f} s, untimed)",
                        "parallelism": f"work items sharded over {world} GPU(s), vertex replicated, ncclBroadcast exchange of the updated slices",
-                       "l2": "flushed between timed iterations (256 MiB write; state 66 MB < 126 MB L2)", "timing": "CUDA events on the library stream per step, max over ranks"},
+                       "l2": f"flushed between timed iterations (256 MiB write; device vertex {state_dev_mb:.0f} MB vs 126 MB L2)", "timing": "CUDA events on the library stream per step, max over ranks"},
             "vertex_entries_per_s": C * L * nf * value,
             "kernel_evals_per_step": evals,
             "alg_gb_per_step": alg_bytes / 1e9, "alg_gflop_per_step": alg_flops / 1e9,
             "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
             "breakdown_ms": {k: statistics.mean(st[k] for _, _, st in records) for k in ("ms_v2_flow", "ms_node_table", "ms_v4_flow", "ms_finalize", "ms_exchange")},
-            "roofline": {"bound": "hbm", "kernel": "pffrg::v4FlowKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "note": "achieved = algorithmic gather+output bytes (SURVEY 8d) / kernel time; the 66 MB vertex is L2 resident, so DRAM traffic is far below the algorithmic bytes",
+            "roofline": {"bound": "hbm", "kernel": "pffrg::v4FlowKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.workload),
+                         "peak_source": peak_src, "note": "achieved = algorithmic gather+output bytes (SURVEY 8d: 128*L*C per kernel evaluation + 24*L*C per item) / kernel time, per GPU; gathers that hit in L2 do not reach DRAM, so `traffic` (ncu dram bytes per launch) is far below the algorithmic bytes and frac can exceed 1",
                          "fp64_tflops_achieved": alg_flops / world / (kernel_ms_avg * 1e-3) / 1e12},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
                     "what": "setState(pinned host arrays) + computeStep + finalizeStep + flowingFunctional(download) per step, wall clock, max over ranks"},

@@ -116,6 +116,11 @@ int64_t pffrg_num_items(pffrg_handle h);         /* NF = Nw*Nw*(Nw+1)/2 work ite
 int pffrg_comm_unique_id(void *id_out /* PFFRG_UNIQUE_ID_BYTES */);
 int pffrg_comm_init(pffrg_handle h, const void *id, int rank, int n_ranks);
 int pffrg_item_range(pffrg_handle h, int64_t *begin, int64_t *end); /* this rank's items in the current step */
+/* The partition itself, as a pure host function (no GPU needed): bounds[r] .. bounds[r+1] are the work items of rank r at
+ * `cutoff`; `rpa_terms` = number of distinct overlap terms (after merging duplicates; overlap_offsets[L] is a fine estimate).
+ * Item costs follow the exact quadrature node counts of src/lib/Integrator.hpp:138-287, so every rank gets the same load. */
+int pffrg_plan_partition(int core, int n_frequencies, const double *frequencies, int n_sites, int64_t rpa_terms, double cutoff,
+                         int n_ranks, int64_t *bounds /* [n_ranks + 1] */);
 
 /* state transfer: replaces direct access to {SU2,XYZ,TRI}EffectiveAction's arrays and EffectiveAction::cutoff
  * (src/SU2/SU2EffectiveAction.hpp:38-60, src/EffectiveAction.hpp:59). `v4` holds pffrg_num_vertex_arrays pointers. */

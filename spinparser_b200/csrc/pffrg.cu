@@ -10,6 +10,7 @@
 #include "pffrg_jit.hpp"
 
 #include <nccl.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -30,6 +31,44 @@ namespace
 {
 	thread_local std::string g_lastError = "no error";
 
+	// NCCL is bound at run time, on the first multi-GPU call: a single-GPU core needs no NCCL at all, and a host process
+	// that already carries an NCCL (e.g. the one bundled with PyTorch) shares it instead of loading a second copy.
+	// PFFRG_NCCL_LIB overrides the library name.
+	struct NcclApi
+	{
+		ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+		ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+		ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+		ncclResult_t (*GroupStart)() = nullptr;
+		ncclResult_t (*GroupEnd)() = nullptr;
+		ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+		ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+		const char *(*GetErrorString)(ncclResult_t) = nullptr;
+		std::string error;
+		bool ok = false;
+	};
+	NcclApi &nccl()
+	{
+		static NcclApi api = [] {
+			NcclApi a;
+			const char *name = getenv("PFFRG_NCCL_LIB");
+			void *lib = dlopen(name ? name : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+			if (!lib) { a.error = std::string("cannot load NCCL: ") + dlerror(); return a; }
+			auto sym = [&](const char *n) { void *p = dlsym(lib, n); if (!p && a.error.empty()) a.error = std::string("NCCL symbol missing: ") + n; return p; };
+			a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+			a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+			a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+			a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
+			a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
+			a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
+			a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+			a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+			a.ok = a.error.empty();
+			return a;
+		}();
+		return api;
+	}
+
 	int fail(int code, const char *fmt, ...)
 	{
 		char buf[1024];
@@ -46,7 +85,7 @@ namespace
 #define NCCL_TRY(expr)                                                                                                   \
 	do {                                                                                                                 \
 		ncclResult_t r_ = (expr);                                                                                        \
-		if (r_ != ncclSuccess) return fail(PFFRG_ERR_NCCL, "%s failed: %s (%s:%d)", #expr, ncclGetErrorString(r_), __FILE__, __LINE__); \
+		if (r_ != ncclSuccess) return fail(PFFRG_ERR_NCCL, "%s failed: %s (%s:%d)", #expr, nccl().GetErrorString(r_), __FILE__, __LINE__); \
 	} while (0)
 
 	template <typename T> struct DeviceArray
@@ -125,6 +164,15 @@ struct pffrg_context
 namespace
 {
 	int packPerm(const int32_t *p) { return (p[0] & 3) | ((p[1] & 3) << 2) | ((p[2] & 3) << 4); }
+
+	// sites per channel run in the device layout: L rounded up so that every run starts on a 32-byte sector
+	// (PFFRG_SITE_ALIGN overrides the granularity in doubles, for layout experiments)
+	int paddedSites(int L)
+	{
+		int align = 4;
+		if (const char *e = getenv("PFFRG_SITE_ALIGN")) align = std::max(1, atoi(e));
+		return (L + align - 1) / align * align;
+	}
 
 	template <int CORE, int NB> size_t flowSmemBytes(int nw, int L, int groups) { return FlowSmem<CORE, NB>(nw, L, groups).total; }
 	size_t flowSmemBytes(int core, int nb, int nw, int L, int groups)
@@ -283,14 +331,15 @@ namespace
 		return c;
 	}
 
-	// contiguous cost-balanced item ranges; also fills the per-rank statistics of the current step
-	void partitionItems(pffrg_context *h, const std::vector<int> &counts)
+	// Contiguous cost-balanced item ranges (replaces the dynamic master/worker chunking of src/lib/LoadManager.hpp:796-852).
+	// Items are ordered su-major, t-minor; the cost of item (so, uo, t) is n(so) + n(uo) ladder evaluations and n(t)
+	// t-channel evaluations, n(x) the quadrature node count of transfer frequency x at the current cutoff.
+	std::vector<int64_t> planPartition(int core, int nw, double L, double rpaTerms, const std::vector<int> &counts, int nRanks)
 	{
-		const CoreModel m = modelOf(h->core);
-		const int nw = h->nw; const double L = h->L;
+		const CoreModel m = modelOf(core);
 		const double costSU = (16.0 * m.C + m.ladderTerms) * L;
-		const double costT = (16.0 * m.C + m.localTerms) * L + 2.0 * m.rpaTerms * (double)h->uniquePairs;
-		const int64_t nf = h->nf;
+		const double costT = (16.0 * m.C + m.localTerms) * L + 2.0 * m.rpaTerms * rpaTerms;
+		const int64_t nf = (int64_t)nw * nw * (nw + 1) / 2;
 		std::vector<double> prefix((size_t)nf / nw + 1, 0.0); // cost per su block (all t of one (s,u))
 		double sumT = 0.0; for (int t = 0; t < nw; ++t) sumT += counts[t];
 		int64_t su = 0;
@@ -298,11 +347,11 @@ namespace
 			for (int uo = 0; uo <= so; ++uo, ++su)
 				prefix[su + 1] = prefix[su] + nw * (counts[so] + counts[uo]) * costSU + sumT * costT;
 		const double total = prefix.back();
-		h->bounds.assign(h->nRanks + 1, 0);
-		h->bounds[h->nRanks] = nf;
-		for (int r = 1; r < h->nRanks; ++r)
+		std::vector<int64_t> bounds(nRanks + 1, 0);
+		bounds[nRanks] = nf;
+		for (int r = 1; r < nRanks; ++r)
 		{
-			const double target = total * r / h->nRanks;
+			const double target = total * r / nRanks;
 			int64_t b = std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin();
 			b = std::min<int64_t>(std::max<int64_t>(b, 0), nf / nw);
 			// refine inside the su block: items of one block differ only through their t index
@@ -317,8 +366,14 @@ namespace
 				item = blk * nw;
 				for (int t = 0; t < nw && acc < target; ++t, ++item) acc += (counts[so] + counts[uo]) * costSU + counts[t] * costT;
 			}
-			h->bounds[r] = std::max(item, h->bounds[r - 1]);
+			bounds[r] = std::max(item, bounds[r - 1]);
 		}
+		return bounds;
+	}
+
+	void partitionItems(pffrg_context *h, const std::vector<int> &counts)
+	{
+		h->bounds = planPartition(h->core, h->nw, h->L, (double)h->uniquePairs, counts, h->nRanks);
 	}
 
 	void fillStats(pffrg_context *h, const std::vector<int> &counts, int64_t begin, int64_t end)
@@ -348,14 +403,14 @@ namespace
 	int exchangeSlices(pffrg_context *h, double *buffer)
 	{
 		if (h->nRanks <= 1) return PFFRG_OK;
-		NCCL_TRY(ncclGroupStart());
+		NCCL_TRY(nccl().GroupStart());
 		for (int r = 0; r < h->nRanks; ++r)
 		{
 			size_t off = (size_t)h->bounds[r] * h->RL, cnt = (size_t)(h->bounds[r + 1] - h->bounds[r]) * h->RL;
 			if (cnt == 0) continue;
-			NCCL_TRY(ncclBroadcast(buffer + off, buffer + off, cnt, ncclDouble, r, h->comm, h->stream));
+			NCCL_TRY(nccl().Broadcast(buffer + off, buffer + off, cnt, ncclDouble, r, h->comm, h->stream));
 		}
-		NCCL_TRY(ncclGroupEnd());
+		NCCL_TRY(nccl().GroupEnd());
 		return PFFRG_OK;
 	}
 
@@ -462,7 +517,7 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 
 	pffrg_context *h = new pffrg_context();
 	const CoreModel m = modelOf(d->core);
-	h->core = d->core; h->nw = d->n_frequencies; h->L = L; h->Lp = (L + 15) / 16 * 16; h->C = m.C; h->RL = m.C * h->Lp; h->nArrays = m.arrays;
+	h->core = d->core; h->nw = d->n_frequencies; h->L = L; h->Lp = paddedSites(L); h->C = m.C; h->RL = m.C * h->Lp; h->nArrays = m.arrays;
 	h->nf = (int64_t)h->nw * h->nw * (h->nw + 1) / 2;
 	h->device = d->device; h->spin = d->spin_length;
 	h->mesh.assign(d->frequencies, d->frequencies + h->nw);
@@ -530,7 +585,7 @@ int pffrg_destroy(pffrg_handle h)
 	if (!h) return PFFRG_OK;
 	cudaSetDevice(h->device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
-	if (h->comm) ncclCommDestroy(h->comm);
+	if (h->comm) nccl().CommDestroy(h->comm);
 	h->dMesh.release(); h->dSitesRid.release(); h->dInvRid.release(); h->dSitesPerm.release(); h->dInvPerm.release(); h->dRngFwd.release(); h->dRngInv.release();
 	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release();
 	if (h->jitLibrary) cudaLibraryUnload(h->jitLibrary); h->dV4.release(); h->dFlow4.release(); h->dV2.release(); h->dFlow2.release(); h->dCutoff.release();
@@ -550,8 +605,9 @@ int pffrg_comm_unique_id(void *idOut)
 {
 	if (!idOut) return fail(PFFRG_ERR_ARGUMENT, "null id buffer");
 	static_assert(sizeof(ncclUniqueId) <= PFFRG_UNIQUE_ID_BYTES, "unique id does not fit");
+	if (!nccl().ok) return fail(PFFRG_ERR_NCCL, "%s", nccl().error.c_str());
 	ncclUniqueId id;
-	NCCL_TRY(ncclGetUniqueId(&id));
+	NCCL_TRY(nccl().GetUniqueId(&id));
 	memset(idOut, 0, PFFRG_UNIQUE_ID_BYTES);
 	memcpy(idOut, &id, sizeof(id));
 	return PFFRG_OK;
@@ -564,7 +620,8 @@ int pffrg_comm_init(pffrg_handle h, const void *id, int rank, int nRanks)
 	if (h->comm) return fail(PFFRG_ERR_STATE, "communicator already initialised");
 	CUDA_TRY(cudaSetDevice(h->device));
 	ncclUniqueId uid; memcpy(&uid, id, sizeof(uid));
-	NCCL_TRY(ncclCommInitRank(&h->comm, nRanks, uid, rank));
+	if (!nccl().ok) return fail(PFFRG_ERR_NCCL, "%s", nccl().error.c_str());
+	NCCL_TRY(nccl().CommInitRank(&h->comm, nRanks, uid, rank));
 	h->rank = rank; h->nRanks = nRanks;
 	h->bounds.assign(nRanks + 1, 0); h->bounds[nRanks] = h->nf;
 	return PFFRG_OK;
@@ -658,7 +715,7 @@ int pffrg_compute_step(pffrg_handle h, int *diverged)
 	CUDA_TRY(launchFlowDispatch(h, begin, end - begin));
 	CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
 	h->stats.launches = 3;
-	if (h->nRanks > 1 && !(h->userEnd > h->userBegin)) NCCL_TRY(ncclAllReduce(h->dNan.p, h->dNan.p, 1, ncclInt, ncclMax, h->comm, h->stream));
+	if (h->nRanks > 1 && !(h->userEnd > h->userBegin)) NCCL_TRY(nccl().AllReduce(h->dNan.p, h->dNan.p, 1, ncclInt, ncclMax, h->comm, h->stream));
 	CUDA_TRY(cudaMemcpyAsync(h->hNan, h->dNan.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	CUDA_TRY(cudaStreamSynchronize(h->stream));
 	h->stats.ms_v2_flow = elapsed(h->ev[0], h->ev[1]);
@@ -731,9 +788,19 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	if (nb < 16) return fail(PFFRG_ERR_UNSUPPORTED, "lattice too large for the specialised kernel");
 	RpaProgram prog = buildRpaProgram(d, d->core, nb, threads / 32);
 	std::vector<char> cubin;
-	const std::string err = compileFlowKernel(d->core, nb, threads, 2, KernelSizes{ L, (L + 15) / 16 * 16, channelsOf(d->core) * ((L + 15) / 16 * 16), d->n_frequencies }, generateRpaSource(prog), cubin);
+	const std::string err = compileFlowKernel(d->core, nb, threads, 2, KernelSizes{ L, paddedSites(L), channelsOf(d->core) * paddedSites(L), d->n_frequencies }, generateRpaSource(prog), cubin);
 	if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
 	if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
+	return PFFRG_OK;
+}
+
+int pffrg_plan_partition(int core, int nFrequencies, const double *frequencies, int nSites, int64_t rpaTerms, double cutoff, int nRanks, int64_t *bounds)
+{
+	if (core < 0 || core > 2 || nFrequencies < 2 || !frequencies || nSites < 1 || nRanks < 1 || !bounds) return fail(PFFRG_ERR_ARGUMENT, "bad argument");
+	std::vector<int> counts(nFrequencies);
+	for (int i = 0; i < nFrequencies; ++i) counts[i] = nodeCount(frequencies, nFrequencies, cutoff, frequencies[i]);
+	const std::vector<int64_t> b = planPartition(core, nFrequencies, nSites, (double)rpaTerms, counts, nRanks);
+	std::copy(b.begin(), b.end(), bounds);
 	return PFFRG_OK;
 }
 

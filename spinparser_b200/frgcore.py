@@ -293,5 +293,13 @@ class FrgCoreFactory:
         return FrgCore(identifier, tables, options, device)
 
 
+def plan_partition(identifier: str, tables: ProblemTables, cutoff: float, n_ranks: int) -> List[int]:
+    """Work-item boundaries of an ``n_ranks``-GPU run at ``cutoff`` (``pffrg_plan_partition``; pure host logic, no GPU)."""
+    bounds = (C.c_int64 * (n_ranks + 1))()
+    check(lib.pffrg_plan_partition(_capi.CORE_IDS[identifier], tables.n_frequencies, tables.frequencies.ctypes.data_as(C.POINTER(C.c_double)),
+                                   tables.n_sites, int(tables.overlap_offsets[-1]), float(cutoff), int(n_ranks), bounds))
+    return list(bounds)
+
+
 def device_count() -> int:
     return int(lib.pffrg_device_count())

@@ -1,0 +1,103 @@
+"""Multi-GPU host logic on the CPU: the work-item partition (pffrg_plan_partition) and the exchange pattern of the sharded
+step, exercised with world_size-2 `gloo` process groups. The flow values come from the oracle here (this container has no
+GPU); the `-m gpu` suite and bench.py run the same pattern with the CUDA kernels and NCCL.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+
+
+def _tables(case):
+    from spinparser_b200 import ProblemTables
+    d = golden(case)
+    return d, ProblemTables.from_pfd(d)
+
+
+@pytest.mark.parametrize("case,core", [("su2_square_r3_nw10", "SU2"), ("xyz_kagome_r4_nw8", "XYZ"), ("tri_kagome_dm_r3_nw6", "TRI")])
+@pytest.mark.parametrize("ranks", [1, 2, 3, 8])
+def test_partition_is_contiguous_complete_and_balanced(case, core, ranks):
+    from spinparser_b200.frgcore import plan_partition
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_port import OraclePort
+    d, tables = _tables(case)
+    port = OraclePort(d)
+    nw, nf = tables.n_frequencies, tables.n_items
+    for cutoff in (float(d["cutoff"][0]), float(d["cutoff"][20]), float(d["cutoff"][-1])):
+        bounds = plan_partition(core, tables, cutoff, ranks)
+        assert bounds[0] == 0 and bounds[-1] == nf and all(a <= b for a, b in zip(bounds, bounds[1:]))
+        # balance against the exact node counts of the oracle (the unit of SURVEY.md 8d)
+        n = np.array([port.node_count(cutoff, float(w)) for w in port.mesh], dtype=np.float64)
+        so, uo = np.tril_indices(nw)
+        order = np.argsort(so * (so + 1) // 2 + uo)
+        so, uo = so[order], uo[order]
+        per_item = (n[so][:, None] + n[uo][:, None] + 4.0 * n[None, :]).reshape(-1)  # t-channel nodes are the expensive ones
+        loads = np.array([per_item[a:b].sum() for a, b in zip(bounds, bounds[1:])])
+        if ranks > 1 and nf >= 50 * ranks:
+            assert loads.max() <= 1.35 * loads.mean(), (cutoff, bounds, loads)
+
+
+def _worker(rank, world, port_no, case, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_port import OraclePort
+    from spinparser_b200 import ProblemTables
+    from spinparser_b200.frgcore import plan_partition
+    from spinparser_b200.pfd import read_pfd
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = read_pfd(os.path.join(ROOT, "tests", "golden", case + ".f64.pfd"))
+    tables = ProblemTables.from_pfd(d)
+    port = OraclePort(d)
+    pre = "step10/"
+    cutoff, new_cutoff = float(d["cutoff"][10]), float(d["cutoff"][11])
+    v2 = np.ascontiguousarray(d[pre + "state/v2"])
+    v4 = [np.ascontiguousarray(d[pre + f"state/v4_{c}"]) for c in range(port.n_arrays)]
+    # every rank computes the (tiny) self-energy flow redundantly: no exchange for it
+    f2 = port.v2_flow(cutoff, v2, v4)
+    bounds = plan_partition(port.core, tables, cutoff, world)
+    begin, end = bounds[rank], bounds[rank + 1]
+    mine = port.v4_flow(cutoff, v2, f2, v4, np.arange(begin, end, dtype=np.int32))
+    per_item = port.array_len // port.nf
+    new_state = []
+    for c in range(port.n_arrays):
+        # Euler update of the own slice, then every rank broadcasts its slice (the pattern of pffrg_finalize_step)
+        state = torch.from_numpy(v4[c].copy())
+        lo, hi = begin * per_item, end * per_item
+        state[lo:hi] += (new_cutoff - cutoff) * torch.from_numpy(mine[c][lo:hi])
+        for r in range(world):
+            a, b = bounds[r] * per_item, bounds[r + 1] * per_item
+            if b > a:
+                piece = state[a:b].clone()
+                dist.broadcast(piece, src=r)
+                state[a:b] = piece
+        new_state.append(state.numpy())
+    diverged = torch.tensor([int(any(np.isnan(a).any() for a in mine))])
+    dist.all_reduce(diverged, op=dist.ReduceOp.MAX)
+    np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.stack(new_state))
+    assert int(diverged) == 0
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["su2_square_r3_nw10", "xyz_honeycomb_kitaev_r3_nw10"])
+def test_two_rank_sharded_step_reproduces_the_reference_state(case, tmp_path):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port_no = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port_no, case, str(tmp_path)), nprocs=2, join=True)
+    d = golden(case)
+    got = [np.load(tmp_path / f"rank{r}.npy") for r in range(2)]
+    assert np.array_equal(got[0], got[1]), "ranks disagree after the exchange"
+    n = got[0].shape[0]
+    step = float(d["cutoff"][11]) - float(d["cutoff"][10])
+    for c in range(n):
+        want = d["step10/state/v4_%d" % c] + step * d["step10/flow/v4_%d" % c]
+        np.testing.assert_allclose(got[0][c], want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
