@@ -162,6 +162,10 @@ int pffrg_tri_terms(int region, int32_t *terms, int capacity);
  * transfers from pinned buffers run at full PCIe speed). Returns NULL on failure. */
 void *pffrg_host_alloc(size_t bytes);
 void pffrg_host_free(void *p);
+/* page-lock memory the caller already owns (e.g. the `new float[]` vertex arrays of src/SU2/SU2VertexTwoParticle.hpp:76-77)
+ * in place, so that set_state / get_state / get_flow on them run at full PCIe speed without a staging copy on the host. */
+int pffrg_host_register(void *p, size_t bytes);
+int pffrg_host_unregister(void *p);
 
 #ifdef __cplusplus
 }

@@ -69,7 +69,13 @@
 #undef PI
 #undef __EPSILON
 #include "TaskFileParser.cpp"
+#ifdef HARNESS_B200_FACTORY
+// the product's factory (spinparser_b200/host/FrgCoreFactory_b200.cpp) instead of the reference's: same harness, same
+// reference host code, flow cores running on the GPU through libpffrg -- the end-to-end drop-in test
+#include "FrgCoreFactory_b200.cpp"
+#else
 #include "FrgCoreFactory.cpp"
+#endif
 #include "SU2/SU2FrgCore.cpp"
 #include "SU2/SU2MeasurementCorrelation.cpp"
 #include "XYZ/XYZFrgCore.cpp"

@@ -23,7 +23,7 @@ SYMBOLS = [
     "pffrg_num_vertex_arrays", "pffrg_vertex_array_length", "pffrg_num_items", "pffrg_comm_unique_id",
     "pffrg_comm_init", "pffrg_item_range", "pffrg_set_state", "pffrg_get_state", "pffrg_get_flow",
     "pffrg_compute_step", "pffrg_finalize_step", "pffrg_synchronize", "pffrg_set_item_range", "pffrg_get_stats",
-    "pffrg_stream", "pffrg_host_alloc", "pffrg_host_free", "pffrg_jit_compile_check", "pffrg_tri_terms", "pffrg_plan_partition",
+    "pffrg_stream", "pffrg_host_alloc", "pffrg_host_free", "pffrg_host_register", "pffrg_host_unregister", "pffrg_jit_compile_check", "pffrg_tri_terms", "pffrg_plan_partition",
 ]
 
 
@@ -94,6 +94,8 @@ def _load() -> C.CDLL:
     lib.pffrg_host_alloc.argtypes = [C.c_size_t]
     lib.pffrg_host_alloc.restype = vp
     lib.pffrg_host_free.argtypes = [vp]
+    lib.pffrg_host_register.argtypes = [vp, C.c_size_t]
+    lib.pffrg_host_unregister.argtypes = [vp]
     lib.pffrg_jit_compile_check.argtypes = [C.POINTER(Desc), C.POINTER(C.c_int64)]
     lib.pffrg_tri_terms.argtypes = [C.c_int, _ip, C.c_int]
     lib.pffrg_plan_partition.argtypes = [C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_double, C.c_int, C.POINTER(C.c_int64)]

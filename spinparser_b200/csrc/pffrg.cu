@@ -841,4 +841,17 @@ void *pffrg_host_alloc(size_t bytes)
 }
 void pffrg_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+int pffrg_host_register(void *p, size_t bytes)
+{
+	if (!p || !bytes) return fail(PFFRG_ERR_ARGUMENT, "null pointer or empty range");
+	CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+	return PFFRG_OK;
+}
+int pffrg_host_unregister(void *p)
+{
+	if (!p) return fail(PFFRG_ERR_ARGUMENT, "null pointer");
+	CUDA_TRY(cudaHostUnregister(p));
+	return PFFRG_OK;
+}
+
 } // extern "C"
