@@ -33,9 +33,32 @@ CASES = {
 }
 
 
+# End-to-end cases for the C++ drop-in adapter (tests/test_host_adapter.py): the same tasks built from THIS repository's
+# resource files (oracle/res, which travel to the GPU box; /root/reference/res does not), full flow with the correlation
+# measurement. Only the measurement output and the final state are kept.
+E2E_CASES = ["e2e_su2_square_r3_nw10", "e2e_xyz_honeycomb_kitaev_r3_nw10", "e2e_tri_kagome_dm_r3_nw6"]
+
+
+def make_e2e(cases):
+    sys.path.insert(0, ROOT)
+    from spinparser_b200.pfd import read_pfd, write_pfd
+    for case in cases:
+        task = os.path.join(HERE, "tasks", case + ".xml")
+        for binary, suffix in (("oracle64", "f64"), ("oracle32", "f32")):
+            out = os.path.join(HERE, f"{case}.{suffix}.pfd")
+            cmd = [os.path.join(ROOT, "oracle", "_ref", binary), "-r", os.path.join(ROOT, "oracle", "res"), task, "--out", out, "--no-lattice"]
+            print(" ".join(cmd))
+            subprocess.run(cmd, check=True, cwd=HERE)
+            d = read_pfd(out)
+            keep = {k: v for k, v in d.items() if k.startswith(("h5/", "final/")) or k in ("core", "cutoff", "frequency", "finalStep")}
+            write_pfd(out, keep)
+            print(case, suffix, os.path.getsize(out) // 1024, "KiB")
+
+
 def main(argv):
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
-    cases = argv or list(CASES)
+    make_e2e([c for c in (argv or E2E_CASES) if c in E2E_CASES])
+    cases = [c for c in (argv or list(CASES)) if c in CASES]
     for case in cases:
         task = os.path.join(HERE, "tasks", case + ".xml")
         steps = ",".join(str(s) for s in CASES[case])

@@ -1,0 +1,101 @@
+"""End-to-end drop-in test of the C++ adapter (spinparser_b200/host/B200FrgCore.hpp).
+
+`oracle/_ref/spinparser{64,32}_b200` is the reference's own host code (task-file parser, lattice builder, correlation
+measurement, HDF5 output captured by the shim) compiled with the product's FrgCoreFactory_b200.cpp, i.e. with flow cores
+whose computeStep()/finalizeStep() run on the GPU through libpffrg. The complete flow (53 cutoffs) of three small tasks
+-- one per core -- must reproduce the measurement output of the unmodified reference (tests/golden/e2e_*.pfd, written
+by tests/golden/make_fixtures.py from oracle64 / oracle32):
+
+    FP64 host arrays:  |d| <= 1e-8 |x| + 1e-10 max|x|   per correlation dataset   (north star: 1e-8 on the susceptibility flow)
+    FP32 host arrays:  |d| <= 1e-5                       (the reference's own tolerance, test/scripted/assets/test_eval.py:14)
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+CASES = ["e2e_su2_square_r3_nw10", "e2e_xyz_honeycomb_kitaev_r3_nw10", "e2e_tri_kagome_dm_r3_nw6"]
+
+
+def _run(binary, case, backend, tmp_path, extra=()):
+    from spinparser_b200.pfd import read_pfd
+    exe = os.path.join(REF, binary)
+    assert os.path.exists(exe), f"{exe} is missing: run __graft_entry__.build() where /root/reference is mounted"
+    out = str(tmp_path / f"{case}.{backend}.pfd")
+    env = dict(os.environ, SPINPARSER_BACKEND=backend)
+    cmd = [exe, "-r", os.path.join(ROOT, "oracle", "res"), os.path.join(GOLDEN, "tasks", case + ".xml"), "--out", out, "--no-lattice", *extra]
+    proc = subprocess.run(cmd, env=env, cwd=str(tmp_path), capture_output=True, text=True)
+    return proc, (read_pfd(out) if proc.returncode == 0 else None)
+
+
+def _compare(got, want, rel, floor_rel, floor_abs=0.0):
+    keys = [k for k in want if k.startswith("h5/") and k.endswith("/data") and "/data/measurement_" in k]
+    assert len(keys) >= 100
+    worst = 0.0
+    for k in keys:
+        a, b = np.asarray(got[k], dtype=np.float64), np.asarray(want[k], dtype=np.float64)
+        assert a.shape == b.shape, k
+        scale = np.abs(b).max()
+        tol = rel * np.abs(b) + floor_rel * scale + floor_abs
+        err = np.abs(a - b)
+        assert (err <= tol).all(), f"{k}: max deviation {err.max():.3e} (scale {scale:.3e})"
+        if scale > 0:
+            worst = max(worst, float(err.max() / scale))
+    for k in want:
+        if k.endswith("@cutoff"):
+            assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
+    assert float(got["finalStep"]) == float(want["finalStep"])
+    return worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_reference_driver_with_gpu_cores_fp64(case, tmp_path):
+    proc, got = _run("spinparser64_b200", case, "b200", tmp_path)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    want = golden(case)
+    worst = _compare(got, want, rel=1e-8, floor_rel=1e-10)
+    # the final vertex (after 52 Euler steps on the GPU, downloaded into the reference's arrays)
+    for k in want:
+        if k.startswith("final/v"):
+            b = np.asarray(want[k])
+            assert np.abs(np.asarray(got[k]) - b).max() <= 1e-9 * np.abs(b).max() + 1e-300, k
+    print(f"{case}: worst norm-wise deviation of the correlation flow {worst:.2e}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_reference_driver_with_gpu_cores_fp32_host(case, tmp_path):
+    """The as-shipped single-precision host build: float arrays at the boundary, FP64 on the device."""
+    proc, got = _run("spinparser32_b200", case, "b200", tmp_path)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    _compare(got, golden(case, "f32"), rel=0.0, floor_rel=0.0, floor_abs=1e-5)
+
+
+def test_factory_replacement_keeps_stock_behaviour(tmp_path):
+    """backend=cpu through the product's factory is bit-identical to the reference's own factory."""
+    case = CASES[0]
+    proc, got = _run("spinparser64_b200", case, "cpu", tmp_path)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    want = golden(case)
+    for k in want:
+        if k.startswith(("h5/", "final/")):
+            assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
+
+
+def test_b200_backend_fails_loudly_without_gpu(tmp_path):
+    from spinparser_b200.frgcore import device_count
+    if device_count() > 0:
+        pytest.skip("a GPU is present")
+    proc, _ = _run("spinparser64_b200", CASES[0], "b200", tmp_path)
+    assert proc.returncode != 0
+    assert "no CUDA device available" in proc.stderr
+
+
+def test_unknown_backend_and_identifier_are_rejected(tmp_path):
+    proc, _ = _run("spinparser64_b200", CASES[0], "tpu", tmp_path)
+    assert proc.returncode != 0 and "Unknown FRG core backend" in proc.stderr
