@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--cpu-stride", type=int, default=16, help="CPU baseline: time every n-th work item")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--items", type=int, default=0, help="profiling runs: restrict every step to the first N work items (not a benchmark)")
     ap.add_argument("--synthetic-state", action="store_true", help="start from a seeded synthetic vertex at --start-step instead of running the flow there (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -224,6 +225,8 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         core.initCommunicator(ids[0], rank, world)
 
+    if args.items > 0:
+        core.setItemRange(0, min(args.items, nf))
     stream = torch.cuda.ExternalStream(core.stream, device=torch.device("cuda", local))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
 
@@ -321,6 +324,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "cutoff_steps": [first_timed, first_timed + args.steps - 1],
                        "cutoff": [cutoffs[first_timed], cutoffs[first_timed + args.steps - 1]],
+                       **({"PROFILING_ONLY_item_range": [0, args.items]} if args.items > 0 else {}),
                        "state": "seeded synthetic vertex" if args.synthetic_state else f"physical: flow run on the GPU from the bare couplings for {args.start_step + args.warmup} steps ({t_setup:.1f} s, untimed)",
                        "parallelism": f"work items sharded over {world} GPU(s), vertex replicated, ncclBroadcast exchange of the updated slices",
                        "l2": f"flushed between timed iterations (256 MiB write; device vertex {state_dev_mb:.0f} MB vs 126 MB L2)", "timing": "CUDA events on the library stream per step, max over ranks"},
@@ -329,6 +333,7 @@ def main():
             "alg_gb_per_step": alg_bytes / 1e9, "alg_gflop_per_step": alg_flops / 1e9,
             "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
             "breakdown_ms": {k: statistics.mean(st[k] for _, _, st in records) for k in ("ms_v2_flow", "ms_node_table", "ms_v4_flow", "ms_finalize", "ms_exchange")},
+            "launch_shape": {k: records[0][2][k] for k in ("jit_rpa", "threads", "smem_bytes", "node_batch", "rpa_batch", "rpa_warps", "min_blocks", "jit_compile_ms")},
             "roofline": {"bound": "hbm", "kernel": "pffrg::v4FlowKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.workload),
                          "peak_source": peak_src, "note": "achieved = algorithmic gather+output bytes (SURVEY 8d: 128*L*C per kernel evaluation + 24*L*C per item) / kernel time, per GPU; gathers that hit in L2 do not reach DRAM, so `traffic` (ncu dram bytes per launch) is far below the algorithmic bytes and frac can exceed 1",
                          "fp64_tflops_achieved": alg_flops / world / (kernel_ms_avg * 1e-3) / 1e12},

@@ -89,6 +89,12 @@ typedef struct pffrg_stats
 	int32_t launches;       /* kernels launched by the last compute_step + finalize_step */
 	int32_t jit_rpa;        /* 1 when the lattice-specialised (run-time compiled) flow kernel is in use */
 	double jit_compile_ms;  /* time spent generating + compiling it in pffrg_create */
+	int32_t threads;        /* launch shape of the flow kernel: threads per CTA, */
+	int32_t smem_bytes;     /*   dynamic shared memory per CTA, */
+	int32_t node_batch;     /*   quadrature nodes per gather batch, */
+	int32_t rpa_batch;      /*   t-channel nodes staged per RPA phase, */
+	int32_t rpa_warps;      /*   warps sharing the RPA instruction stream(s), */
+	int32_t min_blocks;     /*   CTAs per SM the kernel was compiled for */
 } pffrg_stats;
 
 /* library / environment ------------------------------------------------------------------------------------------ */

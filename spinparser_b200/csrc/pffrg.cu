@@ -119,6 +119,7 @@ struct pffrg_context
 	DeviceArray<int> dSitesRid, dInvRid, dSitesPerm, dInvPerm, dRngFwd, dRngInv, dSlotOff;
 	DeviceArray<int4> dTasks;
 	DeviceArray<unsigned> dWords;
+	DeviceArray<unsigned short> dMeshStart; int meshShift = 52, meshKeyBase = 0, meshKeys = 0;
 	// lattice-specialised flow kernel (NVRTC), see pffrg_jit.cpp
 	cudaLibrary_t jitLibrary = nullptr;
 	cudaKernel_t jitKernel = nullptr;
@@ -132,7 +133,7 @@ struct pffrg_context
 	int nodeStride = 0;
 
 	// launch configuration of the flow kernel
-	int nb = 32, groups = 1, stride = 1, threads = 32, nslots = 1; size_t smemBytes = 0;
+	int nb = 32, nbt = 32, rpaWarps = 8, minBlocks = 2, groups = 1, stride = 1, threads = 32, nslots = 1; size_t smemBytes = 0;
 
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[8] = {};
@@ -155,6 +156,7 @@ struct pffrg_context
 		P.mesh = dMesh.p; P.sites_rid = dSitesRid.p; P.inv_rid = dInvRid.p; P.sites_perm = dSitesPerm.p; P.inv_perm = dInvPerm.p;
 		P.rpa_tasks = dTasks.p; P.rpa_slot_off = dSlotOff.p; P.rpa_words = dWords.p;
 		P.nrange = (int)dRngFwd.n; P.rng_fwd = dRngFwd.p; P.rng_inv = dRngInv.p; P.spin = spin;
+		P.meshIndex.start = dMeshStart.p; P.meshIndex.shift = meshShift; P.meshIndex.keyBase = meshKeyBase; P.meshIndex.nKeys = meshKeys;
 		return P;
 	}
 	NodeTable nodeTable() const { NodeTable N; N.count = dCount.p; N.wp = dNodeW.p; N.wt = dNodeWt.p; N.stride = nodeStride; return N; }
@@ -174,12 +176,70 @@ namespace
 		return (L + align - 1) / align * align;
 	}
 
-	template <int CORE, int NB> size_t flowSmemBytes(int nw, int L, int groups) { return FlowSmem<CORE, NB>(nw, L, groups).total; }
-	size_t flowSmemBytes(int core, int nb, int nw, int L, int groups)
+	// Bucket index over the mesh (MeshIndex, pffrg_device.cuh): buckets = runs of equal leading bits of the IEEE representation,
+	// as fine as possible with at most 2048 buckets between the first and the last mesh value.
+	std::vector<unsigned short> buildMeshIndex(const std::vector<double> &mesh, int &shift, int &keyBase, int &nKeys)
 	{
-		if (core == SU2) return nb == 32 ? flowSmemBytes<SU2, 32>(nw, L, groups) : nb == 16 ? flowSmemBytes<SU2, 16>(nw, L, groups) : flowSmemBytes<SU2, 8>(nw, L, groups);
-		if (core == XYZ) return nb == 32 ? flowSmemBytes<XYZ, 32>(nw, L, groups) : nb == 16 ? flowSmemBytes<XYZ, 16>(nw, L, groups) : flowSmemBytes<XYZ, 8>(nw, L, groups);
-		return nb == 32 ? flowSmemBytes<TRI, 32>(nw, L, groups) : nb == 16 ? flowSmemBytes<TRI, 16>(nw, L, groups) : nb == 8 ? flowSmemBytes<TRI, 8>(nw, L, groups) : flowSmemBytes<TRI, 4>(nw, L, groups);
+		auto bits = [](double x) { long long b; memcpy(&b, &x, 8); return b; };
+		auto value = [](long long b) { double x; memcpy(&x, &b, 8); return x; };
+		const int nw = (int)mesh.size();
+		for (shift = 52 - 5; ; ++shift)
+		{
+			keyBase = (int)(bits(mesh.front()) >> shift);
+			nKeys = (int)(bits(mesh.back()) >> shift) - keyBase + 1;
+			if (nKeys <= 2048) break;
+		}
+		std::vector<unsigned short> start(nKeys + 1);
+		for (int k = 0; k <= nKeys; ++k) start[k] = (unsigned short)firstGreater(mesh.data(), nw, value((long long)(keyBase + k) << shift));
+		return start;
+	}
+
+	template <int CORE, int NB> size_t flowSmemBytes(int nw, int L, int groups, int nbt) { return FlowSmem<CORE, NB>(nw, L, groups, nbt).total; }
+	// nbt = nodes staged per RPA phase (0: same as the gather batch nb)
+	size_t flowSmemBytes(int core, int nb, int nw, int L, int groups, int nbt = 0)
+	{
+		if (nbt <= 0) nbt = nb;
+		if (core == SU2) return nb == 32 ? flowSmemBytes<SU2, 32>(nw, L, groups, nbt) : nb == 16 ? flowSmemBytes<SU2, 16>(nw, L, groups, nbt) : flowSmemBytes<SU2, 8>(nw, L, groups, nbt);
+		if (core == XYZ) return nb == 32 ? flowSmemBytes<XYZ, 32>(nw, L, groups, nbt) : nb == 16 ? flowSmemBytes<XYZ, 16>(nw, L, groups, nbt) : flowSmemBytes<XYZ, 8>(nw, L, groups, nbt);
+		return nb == 32 ? flowSmemBytes<TRI, 32>(nw, L, groups, nbt) : nb == 16 ? flowSmemBytes<TRI, 16>(nw, L, groups, nbt) : nb == 8 ? flowSmemBytes<TRI, 8>(nw, L, groups, nbt) : flowSmemBytes<TRI, 4>(nw, L, groups, nbt);
+	}
+
+	// Launch shape of the lattice-specialised kernel. The RPA phase runs as ONE instruction stream shared by `nodeGroups`
+	// warps (one per SM sub-partition when there are four), each on its own group of 16 (SU2) or 32 staged nodes, so the
+	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Preference: four node groups with
+	// two CTAs per SM, then four groups with one CTA per SM, then fewer groups. Environment overrides for tuning runs:
+	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_TILES, PFFRG_JIT_MINBLOCKS.
+	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; };
+	JitShape chooseJitShape(int core, int nw, int L, int groups, int warps, size_t smemMax)
+	{
+		const int lanes = core == SU2 ? 16 : 32;
+		JitShape best = { 0, 0, 0, 0, 0 };
+		const size_t half = (smemMax + 1024) / 2 - 1024; // two CTAs per SM (1 KB per CTA is reserved by the driver)
+		for (int pass = 0; pass < 6 && !best.nb; ++pass)
+		{
+			const int nodeGroups = pass < 2 ? 4 : (pass < 4 ? 2 : 1);
+			const size_t limit = (pass & 1) ? smemMax : half;
+			const int nbt = nodeGroups * lanes, nb = std::min(32, nbt);
+			const size_t smem = flowSmemBytes(core, nb, nw, L, groups, nbt);
+			if (smem <= limit) best = { nb, nbt, std::min(warps, nodeGroups), (pass & 1) ? 1 : 2, smem };
+		}
+		if (const char *e = getenv("PFFRG_JIT_NBT"))
+		{
+			const int nbt = std::max(lanes, atoi(e) / lanes * lanes);
+			int nb = std::min(32, nbt);
+			if (const char *f = getenv("PFFRG_JIT_NB")) nb = atoi(f);
+			if ((nb == 8 || nb == 16 || nb == 32) && nbt % nb == 0)
+			{
+				const size_t smem = flowSmemBytes(core, nb, nw, L, groups, nbt);
+				if (smem <= smemMax) best = { nb, nbt, std::min(warps, nbt / lanes), smem <= half ? 2 : 1, smem };
+			}
+		}
+		if (best.nb)
+		{
+			if (const char *e = getenv("PFFRG_JIT_TILES")) best.rpaWarps = std::min(warps, std::max(1, atoi(e)) * (best.nbt / lanes));
+			if (const char *e = getenv("PFFRG_JIT_MINBLOCKS")) best.minBlocks = std::max(1, atoi(e));
+		}
+		return best;
 	}
 
 	template <int CORE, int NB>
@@ -193,7 +253,7 @@ namespace
 		return cudaGetLastError();
 	}
 
-	RpaProgram buildRpaProgram(const pffrg_desc *d, int core, int nb, int warps);
+	RpaProgram buildRpaProgram(const pffrg_desc *d, int core, int nbt, int rpaWarps);
 
 	cudaError_t launchFlowDispatch(pffrg_context *h, int64_t begin, int64_t count)
 	{
@@ -213,26 +273,27 @@ namespace
 
 	// Compile and load the lattice-specialised kernel. Controlled by the environment: PFFRG_JIT=0 disables it,
 	// PFFRG_JIT_MAX_TERMS (default 60000) bounds the straight-line code size (compile time grows with it).
-	int setupJit(pffrg_context *h, const pffrg_desc *d)
+	int setupJit(pffrg_context *h, const pffrg_desc *d, size_t smemMax)
 	{
 		const char *env = getenv("PFFRG_JIT");
 		if (env && atoi(env) == 0) return PFFRG_OK;
 		long maxTerms = 60000;
 		if (const char *e = getenv("PFFRG_JIT_MAX_TERMS")) maxTerms = atol(e);
-		if (h->nb < 16 || h->core == TRI) return PFFRG_OK; // TRI: table-driven RPA phase (rpaTri), precompiled kernels
+		if (h->core == TRI) return PFFRG_OK; // TRI: table-driven RPA phase (rpaTri), precompiled kernels
+		const JitShape shape = chooseJitShape(h->core, h->nw, h->L, h->groups, h->threads / 32, smemMax);
+		if (!shape.nb) return PFFRG_OK;
 		const auto t0 = std::chrono::steady_clock::now();
-		RpaProgram prog = buildRpaProgram(d, h->core, h->nb, h->threads / 32);
+		RpaProgram prog = buildRpaProgram(d, h->core, shape.nbt, shape.rpaWarps);
 		if ((long)prog.terms.size() > maxTerms) return PFFRG_OK;
 		// tuning knobs of the generated code (defaults chosen on B200)
-		int minBlocks = 2;
 		if (const char *e = getenv("PFFRG_JIT_CHUNK")) prog.chunk = std::max(4, atoi(e));
 		if (const char *e = getenv("PFFRG_JIT_ACC")) prog.maxAccumulators = std::max(1, atoi(e));
-		if (const char *e = getenv("PFFRG_JIT_MINBLOCKS")) minBlocks = std::max(1, atoi(e));
 		std::vector<char> cubin;
-		const std::string err = compileFlowKernel(h->core, h->nb, h->threads, minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
+		const std::string err = compileFlowKernel(h->core, shape.nb, shape.nbt, h->threads, shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the specialised flow kernel failed: %s", err.c_str());
 		CUDA_TRY(cudaLibraryLoadData(&h->jitLibrary, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
 		CUDA_TRY(cudaLibraryGetKernel(&h->jitKernel, h->jitLibrary, "pffrg_v4flow_jit"));
+		h->nb = shape.nb; h->nbt = shape.nbt; h->rpaWarps = shape.rpaWarps; h->minBlocks = shape.minBlocks; h->smemBytes = shape.smem;
 		CUDA_TRY(cudaFuncSetAttribute((const void *)h->jitKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
 		h->jitCompileMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 		return PFFRG_OK;
@@ -293,7 +354,7 @@ namespace
 	}
 
 	// the RPA sum as a list of multiply-adds over staged operands [channel][rid], for the code generator
-	RpaProgram buildRpaProgram(const pffrg_desc *d, int core, int nb, int warps)
+	RpaProgram buildRpaProgram(const pffrg_desc *d, int core, int nb /* nodes per RPA phase */, int warps /* RPA warps */)
 	{
 		const int L = d->n_sites, C = channelsOf(core);
 		RpaProgram p;
@@ -529,7 +590,9 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	// most a quarter of the lanes (then every warp gathers from one node only: fewer cache lines per load, uniform table reads)
 	const int padded = (L + 31) / 32 * 32;
 	h->stride = (padded - L) * 4 <= padded ? padded : L;
-	h->groups = std::max(1, 256 / h->stride);
+	int threadTarget = 256; // PFFRG_THREADS: tuning override (values above 256 only work with the run-time compiled kernel)
+	if (const char *e = getenv("PFFRG_THREADS")) threadTarget = std::min(1024, std::max(64, atoi(e)));
+	h->groups = std::max(1, threadTarget / h->stride);
 	h->threads = std::max(64, (h->groups * h->stride + 31) / 32 * 32);
 	// SU2/XYZ: two CTAs per SM (100 KB each); the TRI core stages four 16-channel RPA operand buffers and runs one CTA per SM
 	h->nb = 32;
@@ -549,6 +612,7 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	cudaError_t e = cudaSuccess;
 	auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
 	ok(h->dMesh.upload(h->mesh));
+	ok(h->dMeshStart.upload(buildMeshIndex(h->mesh, h->meshShift, h->meshKeyBase, h->meshKeys)));
 	ok(h->dSitesRid.upload(std::vector<int>(d->sites_rid, d->sites_rid + L)));
 	ok(h->dInvRid.upload(std::vector<int>(d->inverted_rid, d->inverted_rid + L)));
 	ok(h->dSitesPerm.upload(sitesPerm)); ok(h->dInvPerm.upload(invPerm));
@@ -574,7 +638,7 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 		return code;
 	}
 	h->bounds = { 0, h->nf };
-	const int jitStatus = setupJit(h, d);
+	const int jitStatus = setupJit(h, d, (size_t)prop.sharedMemPerBlockOptin);
 	if (jitStatus != PFFRG_OK) { pffrg_destroy(h); return jitStatus; }
 	*out = h;
 	return PFFRG_OK;
@@ -587,7 +651,7 @@ int pffrg_destroy(pffrg_handle h)
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->comm) nccl().CommDestroy(h->comm);
 	h->dMesh.release(); h->dSitesRid.release(); h->dInvRid.release(); h->dSitesPerm.release(); h->dInvPerm.release(); h->dRngFwd.release(); h->dRngInv.release();
-	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release();
+	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release(); h->dMeshStart.release();
 	if (h->jitLibrary) cudaLibraryUnload(h->jitLibrary); h->dV4.release(); h->dFlow4.release(); h->dV2.release(); h->dFlow2.release(); h->dCutoff.release();
 	h->dCount.release(); h->dNodeW.release(); h->dNodeWt.release(); h->dNan.release(); h->dStaging.release();
 	if (h->hNan) cudaFreeHost(h->hNan);
@@ -770,6 +834,8 @@ int pffrg_get_stats(pffrg_handle h, pffrg_stats *out)
 	*out = h->stats;
 	out->jit_rpa = h->jitKernel ? 1 : 0;
 	out->jit_compile_ms = h->jitCompileMs;
+	out->threads = h->threads; out->smem_bytes = (int32_t)h->smemBytes; out->node_batch = h->nb; out->rpa_batch = h->jitKernel ? h->nbt : h->nb;
+	out->rpa_warps = h->jitKernel ? h->rpaWarps : h->threads / 32; out->min_blocks = h->jitKernel ? h->minBlocks : (h->core == TRI ? 1 : 2);
 	return PFFRG_OK;
 }
 
@@ -783,12 +849,11 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	const int stride = (padded - L) * 4 <= padded ? padded : L;
 	const int groups = std::max(1, 256 / stride);
 	const int threads = std::max(64, (groups * stride + 31) / 32 * 32);
-	int nb = 32;
-	while (nb > 8 && flowSmemBytes(d->core, nb, d->n_frequencies, L, groups) > 100 * 1024) nb >>= 1;
-	if (nb < 16) return fail(PFFRG_ERR_UNSUPPORTED, "lattice too large for the specialised kernel");
-	RpaProgram prog = buildRpaProgram(d, d->core, nb, threads / 32);
+	const JitShape shape = chooseJitShape(d->core, d->n_frequencies, L, groups, threads / 32, 227 * 1024);
+	if (!shape.nb) return fail(PFFRG_ERR_UNSUPPORTED, "lattice too large for the specialised kernel");
+	RpaProgram prog = buildRpaProgram(d, d->core, shape.nbt, shape.rpaWarps);
 	std::vector<char> cubin;
-	const std::string err = compileFlowKernel(d->core, nb, threads, 2, KernelSizes{ L, paddedSites(L), channelsOf(d->core) * paddedSites(L), d->n_frequencies }, generateRpaSource(prog), cubin);
+	const std::string err = compileFlowKernel(d->core, shape.nb, shape.nbt, threads, shape.minBlocks, KernelSizes{ L, paddedSites(L), channelsOf(d->core) * paddedSites(L), d->n_frequencies }, generateRpaSource(prog), cubin);
 	if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
 	if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
 	return PFFRG_OK;

@@ -194,6 +194,123 @@ namespace pffrg
 		for (int k = 0; k < 4; ++k) ab.wOdd[k] = abSwapped(flags, k) ? -ab.w[k] : ab.w[k];
 	}
 
+	// ---- access buffers from shared interpolation records ------------------------------------------------------------
+	// The 4 (s, u channel) or 8 (t channel) access buffers of one quadrature node use only FOUR distinct interpolated
+	// frequencies q0..q3 (up to sign) next to the item's own on-mesh frequency, e.g. for the s channel
+	// (src/SU2/SU2FrgCore.cpp:202-206) q = {w1+w', w2+w', w1p+w', w2p+w'} and the buffers read (t,u) = (-q0,-q1), (q2,-q3),
+	// (q1,q0), (-q3,q2). So the mesh searches are done once per (node, q) -- LerpRecord -- and the buffers are assembled
+	// from two records each without any search. (-a-b == -(a+b) and a-b == -(b-a) hold exactly in IEEE arithmetic, so the
+	// interpolation arguments are bit-identical to the reference's.)
+	struct __align__(16) LerpRecord
+	{
+		double bias;
+		short lower, upper;
+		short neg, pos; // q < 0, q > 0
+	};
+
+	// Bucket index over the frequency mesh: start[k] = firstGreater(lower edge of bucket k), buckets being runs of equal
+	// leading bits of the IEEE representation (monotone for positive doubles). A search touches start[k], start[k+1] and,
+	// for the usual meshes, at most one mesh value instead of log2(Nw) dependent shared-memory loads.
+	struct MeshIndex
+	{
+		const unsigned short *start; // [nKeys + 1]
+		int shift;                   // key = (bits >> shift) - keyBase
+		int keyBase;
+		int nKeys;
+	};
+
+	__device__ __forceinline__ int firstGreaterIndexed(const double *mesh, int nw, const MeshIndex &ix, double w)
+	{
+		const long long key = (long long)(__double_as_longlong(w) >> ix.shift) - ix.keyBase;
+		if (key >= ix.nKeys) return nw;
+		int a = ix.start[key], b = ix.start[key + 1];
+		while (a < b)
+		{
+			const int mid = (a + b) >> 1;
+			if (mesh[mid] > w) b = mid; else a = mid + 1;
+		}
+		return a;
+	}
+
+	// interpolateOffset(|q|) through the bucket index (same results as interpolateOffset above)
+	__device__ __forceinline__ void makeLerpRecord(const double *mesh, int nw, const MeshIndex &ix, double q, LerpRecord &r)
+	{
+		r.neg = q < 0 ? 1 : 0; r.pos = q > 0 ? 1 : 0;
+		const double w = fabs(q);
+		if (w <= mesh[0]) { r.lower = 0; r.upper = 0; r.bias = 0.0; return; }
+		const int i = firstGreaterIndexed(mesh, nw, ix, w);
+		if (i >= nw) { r.lower = (short)(nw - 1); r.upper = (short)(nw - 1); r.bias = 0.0; return; }
+		r.upper = (short)i; r.lower = (short)(i - 1);
+		r.bias = (w - mesh[i - 1]) / (mesh[i] - mesh[i - 1]);
+	}
+
+	// interpolated frequency q (0..3) of channel ch at integration frequency wp; f = {w1p, w1, w2p, w2} of the item
+	__device__ __forceinline__ double nodeQuantity(int ch, int q, double w1p, double w1, double w2p, double w2, double wp)
+	{
+		if (ch == CH_S) return q == 0 ? w1 + wp : (q == 1 ? w2 + wp : (q == 2 ? w1p + wp : w2p + wp));
+		if (ch == CH_U) return q == 0 ? w1 + wp : (q == 1 ? wp - w2p : (q == 2 ? w1p + wp : w2 - wp));
+		return q == 0 ? w1 - wp : (q == 1 ? w1p + wp : (q == 2 ? w2p - wp : w2 + wp));
+	}
+
+	// (channel, buffer) -> which records form the two interpolated arguments: q1 | flip1 << 2 | q2 << 3 | flip2 << 5 | exactNegative << 6.
+	// s channel: (first, second) = (t, u); u channel and the t channel's site-0 buffers 4..7: (s, t); t channel buffers 0..3: (s, u).
+	__host__ __device__ constexpr unsigned long long packRecipes(const int (&t)[8]) { unsigned long long p = 0; for (int i = 0; i < 8; ++i) p |= (unsigned long long)t[i] << (7 * i); return p; }
+	__device__ __forceinline__ int bufferRecipe(int ch, int b)
+	{
+		constexpr int F = 4, G = 32, N = 64;
+		constexpr int recS[8] = { 0 | F | (1 << 3) | G, 2 | (3 << 3) | G, 1 | (0 << 3), 3 | F | (2 << 3), 0, 0, 0, 0 };
+		constexpr int recU[8] = { 0 | (1 << 3), 2 | (3 << 3), 1 | F | (0 << 3) | G, 3 | (2 << 3), 0, 0, 0, 0 };
+		constexpr int recT[8] = { 0 | (1 << 3), 2 | (3 << 3) | G, 1 | (0 << 3), 3 | (2 << 3) | G,
+		                          2 | (3 << 3) | G, 0 | (1 << 3) | G | N, 3 | (2 << 3) | G, 1 | (0 << 3) | G | N };
+		constexpr unsigned long long pS = packRecipes(recS), pU = packRecipes(recU), pT = packRecipes(recT);
+		const unsigned long long p = ch == CH_S ? pS : (ch == CH_U ? pU : pT);
+		return (int)((p >> (7 * b)) & 127u);
+	}
+
+	// generateAccessBuffer (SU2VertexTwoParticle.hpp:399-490, TRIVertexTwoParticle.hpp:401-504) from two interpolation records;
+	// `exactIndex` is the mesh index of the on-mesh argument (offset() of a mesh value is its own index, FrequencyDiscretization.hpp:306-316)
+	template <int CORE>
+	__device__ __forceinline__ void assembleAccessBuffer(int nw, int ch, int b, int exactIndex, const LerpRecord *rec /* [4] */, AccessBuffer &ab)
+	{
+		const int recipe = bufferRecipe(ch, b);
+		const LerpRecord r1 = rec[recipe & 3], r2 = rec[(recipe >> 3) & 3];
+		const bool neg1 = (recipe & 4) ? r1.pos != 0 : r1.neg != 0, neg2 = (recipe & 32) ? r2.pos != 0 : r2.neg != 0;
+		const bool local = ch == CH_T && b >= 4;
+		bool sNeg, tNeg, uNeg;
+		if (ch == CH_S) { sNeg = false; tNeg = neg1; uNeg = neg2; }
+		else if (ch == CH_T && !local) { sNeg = neg1; tNeg = false; uNeg = neg2; }
+		else { sNeg = neg1; tNeg = neg2; uNeg = (recipe & 64) != 0; }
+		int flags = 0;
+		if (CORE == TRI)
+		{
+			if (sNeg) flags ^= AB_EXCHANGE;
+			if (tNeg) flags ^= AB_TZ;
+			if (uNeg) { flags ^= AB_EXCHANGE; flags ^= AB_TZ; }
+		}
+		else if (sNeg != uNeg) flags |= AB_EXCHANGE;
+		const int l1 = r1.lower, u1 = r1.upper, l2 = r2.lower, u2 = r2.upper;
+		const double b1 = r1.bias, b2 = r2.bias;
+		ab.w[0] = (1 - b2) * (1 - b1); ab.w[1] = (1 - b2) * b1; ab.w[2] = b2 * (1 - b1); ab.w[3] = b2 * b1;
+		if (ch == CH_S)
+		{
+			ab.row[0] = rowIndex(nw, exactIndex, l1, l2, 0, flags); ab.row[1] = rowIndex(nw, exactIndex, u1, l2, 1, flags);
+			ab.row[2] = rowIndex(nw, exactIndex, l1, u2, 2, flags); ab.row[3] = rowIndex(nw, exactIndex, u1, u2, 3, flags);
+		}
+		else if (ch == CH_T && !local)
+		{
+			ab.row[0] = rowIndex(nw, l1, exactIndex, l2, 0, flags); ab.row[1] = rowIndex(nw, u1, exactIndex, l2, 1, flags);
+			ab.row[2] = rowIndex(nw, l1, exactIndex, u2, 2, flags); ab.row[3] = rowIndex(nw, u1, exactIndex, u2, 3, flags);
+		}
+		else
+		{
+			ab.row[0] = rowIndex(nw, l1, l2, exactIndex, 0, flags); ab.row[1] = rowIndex(nw, u1, l2, exactIndex, 1, flags);
+			ab.row[2] = rowIndex(nw, l1, u2, exactIndex, 2, flags); ab.row[3] = rowIndex(nw, u1, u2, exactIndex, 3, flags);
+		}
+		ab.flags = flags;
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) ab.wOdd[k] = abSwapped(flags, k) ? -ab.w[k] : ab.w[k];
+	}
+
 	// TRIVertexTwoParticle::_zeta, src/TRI/TRIVertexTwoParticle.hpp:674-677
 	__host__ __device__ __forceinline__ double zeta(int c) { return c <= 2 ? -1.0 : 1.0; }
 

@@ -15,8 +15,8 @@ namespace pffrg
 		int nOutputs = 0;           // outputs per variant
 		int variants = 1;           // lanes are split into `variants` groups running the same code on shifted operands (SU2: the two channels)
 		int lanesPerVariant = 32;   // nodes per warp
-		int nb = 32;                // nodes per batch
-		int warps = 8;              // warps per CTA
+		int nb = 32;                // nodes per RPA phase (the kernel's NBT)
+		int warps = 8;              // warps taking part in the RPA phase (the first `warps` of the CTA)
 		long operandStride = 33;    // doubles between consecutive operand indices in the staging area (NB + 1)
 		long operandBOffset = 0;    // doubles from operand A's staging buffer to operand B's
 		long variantOperandStride = 0, variantOutputStride = 0;
@@ -32,5 +32,5 @@ namespace pffrg
 
 	// compile the vertex-flow kernel (embedded source + the generated RPA function) for sm_100a; returns an empty string on
 	// success and the compiler log otherwise. The kernel is `pffrg_v4flow_jit` with v4FlowKernel's parameter list.
-	std::string compileFlowKernel(int core, int nb, int threads, int minBlocks, const KernelSizes &sizes, const std::string &rpaSource, std::vector<char> &cubin);
+	std::string compileFlowKernel(int core, int nb, int nbt, int threads, int minBlocks, const KernelSizes &sizes, const std::string &rpaSource, std::vector<char> &cubin);
 }

@@ -31,6 +31,7 @@ namespace pffrg
 		const int *rng_fwd;      // [nrange]
 		const int *rng_inv;      // [nrange]
 		double spin;
+		MeshIndex meshIndex;     // bucket index over the mesh (global memory, L1 resident)
 	};
 
 	// Problem sizes: run-time values in the precompiled kernels, compile-time constants in the run-time compiled one
@@ -270,22 +271,28 @@ namespace pffrg
 	{
 		static constexpr int C = channelsOf(CORE);
 		static constexpr int NBP = NB + 1;
-		size_t mesh, bw, bW, ab, loc, wmat, st, part, rpa, total;
-		__host__ __device__ FlowSmem(int nw, int L, int groups)
+		size_t mesh, bw, bW, lerp, ab, loc, wmat, st, part, rpa, total;
+		int rpaCopies;
+		// nbt = nodes staged per RPA phase (a multiple of NB; NB itself in the precompiled kernels)
+		__host__ __device__ FlowSmem(int nw, int L, int groups, int nbt = NB)
 		{
 			size_t o = 0;
 			mesh = o; o += sizeof(double) * nw;
 			bw = o; o += 0;
 			bW = o; o += sizeof(double) * NB * 2;
 			o = alignUp(o, 16);
+			lerp = o; o += sizeof(LerpRecord) * NB * 2 * 4; // four interpolation records per node, see assembleAccessBuffer
 			ab = o; o += sizeof(AccessBuffer) * NB * 8;
 			loc = o; o += sizeof(double) * NB * 4 * C;
 			o = alignUp(o, 16);
 			wmat = o; o += (CORE == TRI) ? sizeof(double) * NB * 4 * 32 : 0; // TRI: contracted site-0 matrices, see triLocalMatrices
 			o = alignUp(o, 16);
-			st = o; o += sizeof(double) * RpaStage<CORE>::buffers * C * L * NBP;
+			st = o; o += sizeof(double) * RpaStage<CORE>::buffers * C * L * (nbt + 1);
 			part = o; o += sizeof(double) * groups * C * L;
-			rpa = o; o += sizeof(double) * C * L * 2; // two copies: the specialised SU2 code runs two node groups concurrently
+			// one copy of the RPA outputs per node group of the specialised code (16 nodes for SU2, which runs its two channels as
+			// lane halves, 32 otherwise): single writer per address, summed in the epilogue
+			rpaCopies = nbt / (CORE == SU2 ? 16 : 32); if (rpaCopies < 2) rpaCopies = 2;
+			rpa = o; o += sizeof(double) * C * L * rpaCopies;
 			total = alignUp(o, 16);
 		}
 	};
@@ -749,15 +756,17 @@ namespace pffrg
 		}
 	}
 
-	template <int CORE, int NB, bool JIT>
+	template <int CORE, int NB, int NBT, bool JIT>
 	__device__ __forceinline__ void v4FlowBody(const Problem &P, const NodeTable &N, const FlowConfig &cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
 	{
 		constexpr int C = channelsOf(CORE);
-		constexpr int NBP = NB + 1;
+		constexpr int NBP = NBT + 1; // node stride of the RPA staging area
+		static_assert(NBT % NB == 0 && (JIT || NBT == NB), "the precompiled kernels stage one gather batch per RPA phase");
 		extern __shared__ __align__(16) unsigned char smemRaw[];
-		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups);
+		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT);
 		double *mesh = reinterpret_cast<double *>(smemRaw + lay.mesh);
 		double *bW = reinterpret_cast<double *>(smemRaw + lay.bW);
+		LerpRecord *lerp = reinterpret_cast<LerpRecord *>(smemRaw + lay.lerp);
 		AccessBuffer *abTable = reinterpret_cast<AccessBuffer *>(smemRaw + lay.ab);
 		double *loc = reinterpret_cast<double *>(smemRaw + lay.loc);
 		double *wmat = reinterpret_cast<double *>(smemRaw + lay.wmat);
@@ -768,7 +777,7 @@ namespace pffrg
 		const int tid = threadIdx.x, nthreads = blockDim.x;
 		const int L = sizeL(P), nw = sizeNw(P);
 		for (int i = tid; i < nw; i += nthreads) mesh[i] = P.mesh[i];
-		for (int i = tid; i < 2 * C * L; i += nthreads) rpaOut[i] = 0.0;
+		for (int i = tid; i < lay.rpaCopies * C * L; i += nthreads) rpaOut[i] = 0.0;
 
 		// work item -> (s, t, u), expandIterator SU2VertexTwoParticle.hpp:136-158
 		const int item = itemBegin + blockIdx.x;
@@ -808,23 +817,31 @@ namespace pffrg
 			for (int b0 = 0; b0 < nNodes; b0 += batch)
 			{
 				const int nb = min(batch, nNodes - b0);
+				// t channel: NBT / NB consecutive gather batches are staged side by side before one RPA phase runs over all of them
+				const int stageOff = tPass ? b0 % NBT : 0;
 				__syncthreads(); // previous batch fully consumed
-				// ---- phase 0: access buffers
-				for (int idx = tid; idx < nb * nbuf; idx += nthreads)
+				// ---- phase 0: access buffers. Step A: the four interpolated frequencies of every node (one mesh search each)
+				for (int idx = tid; idx < nb * 4; idx += nthreads)
 				{
-					const int node = idx / nbuf, b = idx - node * nbuf;
+					const int node = idx >> 2, q = idx & 3;
 					const int gn = b0 + node;
 					const int ch = tPass ? CH_T : (gn < nFirst ? CH_S : CH_U);
 					const double wp = gn < nFirst ? nodeW0[gn] : nodeW1[gn - nFirst];
-					if (b == 0)
+					if (q == 0)
 					{
 						// SU2: the u channel enters with a minus sign (SU2FrgCore.cpp:366,370,376); XYZ/TRI kernels carry it themselves
 						const double wt = gn < nFirst ? nodeWt0[gn] : nodeWt1[gn - nFirst];
 						bW[node] = (CORE == SU2 && ch == CH_U) ? -wt : wt;
 					}
-					double as, at, au; int exact;
-					bufferArguments<CORE>(f, ch, b, wp, as, at, au, exact);
-					makeAccessBuffer<CORE>(mesh, nw, as, at, au, exact, abTable[node * nbuf + b]);
+					makeLerpRecord(mesh, nw, P.meshIndex, nodeQuantity(ch, q, f.w1p, f.w1, f.w2p, f.w2, wp), lerp[idx]);
+				}
+				__syncthreads();
+				// step B: assemble the buffers (sector map, weights, rows) from two records each
+				for (int idx = tid; idx < nb * nbuf; idx += nthreads)
+				{
+					const int node = idx / nbuf, b = idx - node * nbuf;
+					const int ch = tPass ? CH_T : ((b0 + node) < nFirst ? CH_S : CH_U);
+					assembleAccessBuffer<CORE>(nw, ch, b, ch == CH_S ? so : (ch == CH_T ? ti : uo), lerp + 4 * node, abTable[idx]);
 				}
 				__syncthreads();
 				if (tPass)
@@ -890,8 +907,8 @@ namespace pffrg
 								#pragma unroll
 								for (int c = 0; c < C; ++c)
 								{
-									st[((0 * C + c) * L + j) * NBP + node] = opA[c];
-									st[((1 * C + c) * L + j) * NBP + node] = opB[c];
+									st[((0 * C + c) * L + j) * NBP + stageOff + node] = opA[c];
+									st[((1 * C + c) * L + j) * NBP + stageOff + node] = opB[c];
 								}
 							}
 							else
@@ -909,12 +926,12 @@ namespace pffrg
 						for (int c = 0; c < C; ++c) acc[c] += W * K[c];
 					}
 				}
-				if (tPass)
+				if (tPass && (stageOff + batch == NBT || b0 + batch >= nNodes))
 				{
 					__syncthreads();
-					// ---- phase 2: RPA lattice sum
+					// ---- phase 2: RPA lattice sum over the stageOff + nb staged nodes
 #ifdef PFFRG_JIT_RPA
-					if (JIT) rpaSpecialised(tid >> 5, tid & 31, nb, st, rpaOut);
+					if (JIT) rpaSpecialised(tid >> 5, tid & 31, stageOff + nb, st, rpaOut);
 					else
 #endif
 					if constexpr (CORE == TRI) rpaTri<NB>(P, cfg, st, rpaOut, tid, nb);
@@ -934,7 +951,8 @@ namespace pffrg
 		bool bad = false;
 		for (int e = tid; e < C * L; e += nthreads)
 		{
-			double v = rpaOut[e] + rpaOut[C * L + e];
+			double v = 0.0;
+			for (int k = 0; k < lay.rpaCopies; ++k) v += rpaOut[k * C * L + e];
 			for (int gg = 0; gg < cfg.groups; ++gg) v += part[gg * C * L + e];
 			v /= TWO_PI;
 			const int c = e / L, jj = e - c * L;
@@ -948,7 +966,7 @@ namespace pffrg
 	template <int CORE, int NB>
 	__global__ void __launch_bounds__(256) v4FlowKernel(Problem P, NodeTable N, FlowConfig cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
 	{
-		v4FlowBody<CORE, NB, false>(P, N, cfg, v4, flow, itemBegin, nanFlag);
+		v4FlowBody<CORE, NB, NB, false>(P, N, cfg, v4, flow, itemBegin, nanFlag);
 	}
 #endif
 
