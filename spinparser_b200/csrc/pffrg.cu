@@ -288,6 +288,7 @@ namespace
 		// tuning knobs of the generated code (defaults chosen on B200)
 		if (const char *e = getenv("PFFRG_JIT_CHUNK")) prog.chunk = std::max(4, atoi(e));
 		if (const char *e = getenv("PFFRG_JIT_ACC")) prog.maxAccumulators = std::max(1, atoi(e));
+		if (const char *e = getenv("PFFRG_JIT_PREFETCH")) prog.prefetch = std::max(1, atoi(e));
 		std::vector<char> cubin;
 		const std::string err = compileFlowKernel(h->core, shape.nb, shape.nbt, h->threads, shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the specialised flow kernel failed: %s", err.c_str());

@@ -121,16 +121,22 @@ namespace pffrg
 	// ---- access buffers --------------------------------------------------------------------------------------------------
 	// Four interpolation supports of one vertex access: row index (su*Nw + t), weight, and the symmetry flags that decide
 	// signs and the site/spin maps at gather time.
+	// 80 bytes = an odd number of 16-byte words: consecutive threads write consecutive entries without bank conflicts.
 	struct __align__(16) AccessBuffer
 	{
-		double w[4];     // weight for channels that are even under the s<->u frequency exchange
-		double wOdd[4];  // weight for channels that are odd under it (sign flipped where the mirrored entry is read)
+		double w[4];     // interpolation weights; channels that are odd under the s<->u frequency exchange use -w[k] where
+		                 // support k reads the mirrored entry (oddWeight)
 		int row[4];      // row index su*Nw + t
 		int flags;       // bit0: site/pair exchange, bit1: TRI zeta_mu*zeta_nu factor, bit(4+k): support k reads the s<->u mirrored entry
-		int pad[3];
+		int pad[7];
 	};
 	constexpr int AB_EXCHANGE = 1, AB_TZ = 2;
 	__host__ __device__ __forceinline__ int abSwapped(int flags, int k) { return (flags >> (4 + k)) & 1; }
+	// weight of support k for a channel that is odd under s<->u: sign bit flipped iff the support is mirrored
+	__device__ __forceinline__ double oddWeight(double w, int flags, int k)
+	{
+		return __hiloint2double(__double2hiint(w) ^ (int)(((unsigned)flags >> (4 + k)) << 31), __double2loint(w));
+	}
 
 	__host__ __device__ __forceinline__ int rowIndex(int nw, int so, int to, int uo, int k, int &flags)
 	{
@@ -191,7 +197,6 @@ namespace pffrg
 			ab.w[3] = b2 * b1;             ab.row[3] = rowIndex(nw, u1, u2, eu, 3, flags);
 		}
 		ab.flags = flags;
-		for (int k = 0; k < 4; ++k) ab.wOdd[k] = abSwapped(flags, k) ? -ab.w[k] : ab.w[k];
 	}
 
 	// ---- access buffers from shared interpolation records ------------------------------------------------------------
@@ -307,8 +312,6 @@ namespace pffrg
 			ab.row[2] = rowIndex(nw, l1, u2, exactIndex, 2, flags); ab.row[3] = rowIndex(nw, u1, u2, exactIndex, 3, flags);
 		}
 		ab.flags = flags;
-		#pragma unroll
-		for (int k = 0; k < 4; ++k) ab.wOdd[k] = abSwapped(flags, k) ? -ab.w[k] : ab.w[k];
 	}
 
 	// TRIVertexTwoParticle::_zeta, src/TRI/TRIVertexTwoParticle.hpp:674-677

@@ -23,6 +23,7 @@ namespace pffrg
 		long outputCopyStride = 0;  // doubles between the two output copies of the kernel (C * L)
 		int maxAccumulators = 8;    // outputs accumulated in registers at a time
 		int chunk = 32;             // B operands cached in registers at a time
+		int prefetch = 8;           // A operands in flight (software pipeline depth of the generated code)
 	};
 
 	// CUDA source of `__device__ void pffrg::rpaSpecialised(int warp, int lane, int nb, const double *st, double *rpaOut)`

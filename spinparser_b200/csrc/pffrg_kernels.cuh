@@ -304,12 +304,11 @@ namespace pffrg
 		constexpr int C = channelsOf(CORE);
 		// the table entry is 16-byte aligned: 128-bit shared loads
 		const double2 w01 = *reinterpret_cast<const double2 *>(&ab.w[0]), w23 = *reinterpret_cast<const double2 *>(&ab.w[2]);
-		const double2 o01 = *reinterpret_cast<const double2 *>(&ab.wOdd[0]), o23 = *reinterpret_cast<const double2 *>(&ab.wOdd[2]);
 		const int4 rows = *reinterpret_cast<const int4 *>(&ab.row[0]);
-		const double wk[4] = { w01.x, w01.y, w23.x, w23.y };
-		const double ok[4] = { o01.x, o01.y, o23.x, o23.y };
-		const int rk[4] = { rows.x, rows.y, rows.z, rows.w };
 		const int flags = ab.flags;
+		const double wk[4] = { w01.x, w01.y, w23.x, w23.y };
+		const double ok[4] = { oddWeight(w01.x, flags, 0), oddWeight(w01.y, flags, 1), oddWeight(w23.x, flags, 2), oddWeight(w23.y, flags, 3) };
+		const int rk[4] = { rows.x, rows.y, rows.z, rows.w };
 		const bool exchange = flags & AB_EXCHANGE;
 		const int site = exchange ? siteInv : siteFwd;
 		const int perm = exchange ? permInv : permFwd;
@@ -660,7 +659,7 @@ namespace pffrg
 
 #ifdef PFFRG_JIT_RPA
 	// generated per lattice (pffrg_jit.cpp): the RPA sum of one batch for the outputs owned by `warp`
-	__device__ void rpaSpecialised(int warp, int lane, int nb, const double *st, double *rpaOut);
+	static __device__ __forceinline__ void rpaSpecialised(int warp, int lane, int nb, const double *st, double *rpaOut);
 #endif
 
 	// generic phase 2: one RPA slot (a warp, or a sub-warp of NB lanes) walks the term stream of its representative sites.
