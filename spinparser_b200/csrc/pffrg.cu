@@ -206,8 +206,7 @@ namespace
 
 	// Launch shape of the lattice-specialised kernel. The RPA phase runs as ONE instruction stream shared by `nodeGroups`
 	// warps (one per SM sub-partition when there are four), each on its own group of 16 (SU2) or 32 staged nodes, so the
-	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Preference: four node groups with
-	// two CTAs per SM, then four groups with one CTA per SM, then fewer groups. Environment overrides for tuning runs:
+	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Environment overrides for tuning runs:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_TILES, PFFRG_JIT_MINBLOCKS.
 	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; };
 	JitShape chooseJitShape(int core, int nw, int L, int groups, int warps, size_t smemMax)
@@ -215,13 +214,21 @@ namespace
 		const int lanes = core == SU2 ? 16 : 32;
 		JitShape best = { 0, 0, 0, 0, 0 };
 		const size_t half = (smemMax + 1024) / 2 - 1024; // two CTAs per SM (1 KB per CTA is reserved by the driver)
+		// (node groups, CTAs per SM) in order of preference (measured on B200: two resident CTAs beat a larger RPA batch)
+		const int order[6][2] = { { 4, 2 }, { 2, 2 }, { 4, 1 }, { 2, 1 }, { 1, 2 }, { 1, 1 } };
 		for (int pass = 0; pass < 6 && !best.nb; ++pass)
 		{
-			const int nodeGroups = pass < 2 ? 4 : (pass < 4 ? 2 : 1);
-			const size_t limit = (pass & 1) ? smemMax : half;
-			const int nbt = nodeGroups * lanes, nb = std::min(32, nbt);
-			const size_t smem = flowSmemBytes(core, nb, nw, L, groups, nbt);
-			if (smem <= limit) best = { nb, nbt, std::min(warps, nodeGroups), (pass & 1) ? 1 : 2, smem };
+			const int nodeGroups = order[pass][0], ctas = order[pass][1];
+			const int nbt = nodeGroups * lanes;
+			// all warps (up to eight) take part in the RPA phase: warps beyond the node groups run further output tiles
+			// (measured: pyrochlore-r8 316 ms with 4 RPA warps / one stream, 272 ms with 8 warps / two streams)
+			const int rpaWarps = std::min(warps, 8) / nodeGroups * nodeGroups;
+			// a smaller gather batch shrinks the access-buffer tables when the staged operands leave little room
+			for (int nb = std::min(32, nbt); nb >= 8 && !best.nb; nb >>= 1)
+			{
+				const size_t smem = flowSmemBytes(core, nb, nw, L, groups, nbt);
+				if (smem <= (ctas == 2 ? half : smemMax)) best = { nb, nbt, rpaWarps, ctas, smem };
+			}
 		}
 		if (const char *e = getenv("PFFRG_JIT_NBT"))
 		{
@@ -231,7 +238,7 @@ namespace
 			if ((nb == 8 || nb == 16 || nb == 32) && nbt % nb == 0)
 			{
 				const size_t smem = flowSmemBytes(core, nb, nw, L, groups, nbt);
-				if (smem <= smemMax) best = { nb, nbt, std::min(warps, nbt / lanes), smem <= half ? 2 : 1, smem };
+				if (smem <= smemMax) best = { nb, nbt, std::min(warps, 8) / (nbt / lanes) * (nbt / lanes), smem <= half ? 2 : 1, smem };
 			}
 		}
 		if (best.nb)

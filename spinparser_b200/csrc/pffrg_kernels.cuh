@@ -288,7 +288,8 @@ namespace pffrg
 			wmat = o; o += (CORE == TRI) ? sizeof(double) * NB * 4 * 32 : 0; // TRI: contracted site-0 matrices, see triLocalMatrices
 			o = alignUp(o, 16);
 			st = o; o += sizeof(double) * RpaStage<CORE>::buffers * C * L * (nbt + 1);
-			part = o; o += sizeof(double) * groups * C * L;
+			// the per-group partial sums of the epilogue reuse the staging area (dead by then; groups <= 32 < buffers * (nbt + 1))
+			part = st;
 			// one copy of the RPA outputs per node group of the specialised code (16 nodes for SU2, which runs its two channels as
 			// lane halves, 32 otherwise): single writer per address, summed in the epilogue
 			rpaCopies = nbt / (CORE == SU2 ? 16 : 32); if (rpaCopies < 2) rpaCopies = 2;
