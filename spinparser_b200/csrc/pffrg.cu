@@ -220,9 +220,9 @@ namespace
 		{
 			const int nodeGroups = order[pass][0], ctas = order[pass][1];
 			const int nbt = nodeGroups * lanes;
-			// all warps (up to eight) take part in the RPA phase: warps beyond the node groups run further output tiles
-			// (measured: pyrochlore-r8 316 ms with 4 RPA warps / one stream, 272 ms with 8 warps / two streams)
-			const int rpaWarps = std::min(warps, 8) / nodeGroups * nodeGroups;
+			// two output tiles (instruction streams) per node group, at least four RPA warps. Measured: pyrochlore-r8 (4 groups)
+			// 316 ms with one tile, 272 ms with two; honeycomb-r7 XYZ (2 groups) 32.7 ms with two tiles, 43.1 ms with four
+			const int rpaWarps = std::min(warps, std::max(4, 2 * nodeGroups)) / nodeGroups * nodeGroups;
 			// a smaller gather batch shrinks the access-buffer tables when the staged operands leave little room
 			for (int nb = std::min(32, nbt); nb >= 8 && !best.nb; nb >>= 1)
 			{
@@ -238,7 +238,7 @@ namespace
 			if ((nb == 8 || nb == 16 || nb == 32) && nbt % nb == 0)
 			{
 				const size_t smem = flowSmemBytes(core, nb, nw, L, groups, nbt);
-				if (smem <= smemMax) best = { nb, nbt, std::min(warps, 8) / (nbt / lanes) * (nbt / lanes), smem <= half ? 2 : 1, smem };
+				if (smem <= smemMax) best = { nb, nbt, std::min(warps, std::max(4, 2 * (nbt / lanes))) / (nbt / lanes) * (nbt / lanes), smem <= half ? 2 : 1, smem };
 			}
 		}
 		if (best.nb)
@@ -323,7 +323,16 @@ namespace
 	// Term stream of the generic RPA phase (rpaGeneric): per representative site the merged overlap terms, sorted so that
 	// equal (rid1, perm1, perm2) are adjacent; each such group starts with a header word, followed by one word per term.
 	// Tasks (one per rid) are dealt to the RPA slots longest-first.
-	void buildRpa(const pffrg_desc *d, int core, int nslots, int nbp, std::vector<unsigned> &words, std::vector<int4> &tasks, std::vector<int> &slotOff, int64_t &unique)
+	// index of a packed spin permutation in the order of tri8Perm (pffrg_kernels.cuh)
+	int permIndex(int packed)
+	{
+		for (int p = 0; p < 6; ++p)
+			if (tri8Perm(p, 0) == (packed & 3) && tri8Perm(p, 1) == ((packed >> 2) & 3) && tri8Perm(p, 2) == ((packed >> 4) & 3)) return p;
+		return 0;
+	}
+
+	// `nbp` = stride of one representative site in the staging area (doubles); tri8 selects the header format of rpaTri8
+	void buildRpa(const pffrg_desc *d, int core, int nslots, int nbp, bool tri8, std::vector<unsigned> &words, std::vector<int4> &tasks, std::vector<int> &slotOff, int64_t &unique)
 	{
 		const int L = d->n_sites;
 		std::vector<int4> perRid;
@@ -338,7 +347,8 @@ namespace
 				const int r1 = std::get<0>(kv.first), p1 = std::get<1>(kv.first), p2 = std::get<2>(kv.first), r2 = std::get<3>(kv.first);
 				if (r1 != lastR1 || p1 != lastP1 || p2 != lastP2)
 				{
-					words.push_back(0x80000000u | (unsigned)(r1 * nbp) | ((unsigned)p1 << 16) | ((unsigned)p2 << 22));
+					if (tri8) words.push_back(0x80000000u | (unsigned)(r1 * nbp) | ((unsigned)permIndex(p1) << 16) | ((unsigned)permIndex(p2) << 19));
+					else words.push_back(0x80000000u | (unsigned)(r1 * nbp) | ((unsigned)p1 << 16) | ((unsigned)p2 << 22));
 					lastR1 = r1; lastP1 = p1; lastP2 = p2;
 				}
 				words.push_back((unsigned)(r2 * nbp) | ((unsigned)std::min(kv.second, 32767) << 16));
@@ -607,12 +617,15 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	const int minNb = h->core == TRI ? 4 : 8;
 	const size_t smemTarget = h->core == TRI ? 200 * 1024 : 100 * 1024;
 	while (h->nb > minNb && flowSmemBytes(h->core, h->nb, h->nw, L, h->groups) > smemTarget) h->nb >>= 1;
+	// PFFRG_NB: force the gather batch of the precompiled kernels (tests exercise every kernel variant on small lattices)
+	if (const char *e = getenv("PFFRG_NB")) { const int v = atoi(e); if ((v == 32 || v == 16 || v == 8 || (v == 4 && h->core == TRI)) && v <= h->nb) h->nb = v; }
 	h->smemBytes = flowSmemBytes(h->core, h->nb, h->nw, L, h->groups);
 	if (h->smemBytes > (size_t)prop.sharedMemPerBlockOptin) { const size_t need = h->smemBytes; delete h; return fail(PFFRG_ERR_UNSUPPORTED, "flow kernel needs %zu bytes of shared memory", need); }
-	h->nslots = (h->threads / 32) * (32 / h->nb);
+	const bool tri8 = h->core == TRI && h->nb == 8; // rpaTri8: one task stream per warp, staging layout with TRI8_RID_STRIDE
+	h->nslots = tri8 ? h->threads / 32 : (h->threads / 32) * (32 / h->nb);
 
 	std::vector<unsigned> words; std::vector<int4> tasks; std::vector<int> slotOff;
-	buildRpa(d, h->core, h->nslots, h->nb + 1, words, tasks, slotOff, h->uniquePairs);
+	buildRpa(d, h->core, h->nslots, tri8 ? TRI8_RID_STRIDE : h->nb + 1, tri8, words, tasks, slotOff, h->uniquePairs);
 
 	std::vector<int> sitesPerm(L), invPerm(L);
 	for (int j = 0; j < L; ++j) { sitesPerm[j] = packPerm(d->sites_perm + 3 * j); invPerm[j] = packPerm(d->inverted_perm + 3 * j); }

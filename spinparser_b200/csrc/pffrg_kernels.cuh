@@ -266,6 +266,13 @@ namespace pffrg
 	template <int C, int NBP>
 	__device__ __forceinline__ int stageIndex(int L, int buffer, int plane, int rid, int node) { return ((buffer * (C / 2) + plane) * L + rid) * NBP + node; }
 
+	// Staging layout of the TRI core with NB = 8 (rpaTri8): st[buffer][rid][channel][node], channel stride NB + 1 = 9 doubles
+	// (compile-time, so spin permutations become immediate offsets), rid stride 16 * 9 + 1 doubles (odd multiple of one bank
+	// pair: the transposed stores of phase 1 are conflict free), buffer stride = 4 mod 8 doubles so that the two buffer pairs
+	// a warp reads at the same time fall into disjoint bank halves.
+	constexpr int TRI8_NBP = 9, TRI8_RID_STRIDE = 16 * TRI8_NBP + 1;
+	__host__ __device__ inline int tri8BufferStride(int L) { int bs = L * TRI8_RID_STRIDE; while ((bs & 7) != 4) ++bs; return bs; }
+
 	template <int CORE, int NB>
 	struct FlowSmem
 	{
@@ -287,9 +294,10 @@ namespace pffrg
 			o = alignUp(o, 16);
 			wmat = o; o += (CORE == TRI) ? sizeof(double) * NB * 4 * 32 : 0; // TRI: contracted site-0 matrices, see triLocalMatrices
 			o = alignUp(o, 16);
-			st = o; o += sizeof(double) * RpaStage<CORE>::buffers * C * L * (nbt + 1);
-			// the per-group partial sums of the epilogue reuse the staging area (dead by then; groups <= 32 < buffers * (nbt + 1))
-			part = st;
+			// the per-group partial sums of the epilogue reuse the staging area (dead by then)
+			const size_t stBytes = (CORE == TRI && NB == 8) ? sizeof(double) * 4 * tri8BufferStride(L) : sizeof(double) * RpaStage<CORE>::buffers * C * L * (nbt + 1);
+			const size_t partBytes = sizeof(double) * groups * C * L;
+			st = o; part = o; o += stBytes > partBytes ? stBytes : partBytes;
 			// one copy of the RPA outputs per node group of the specialised code (16 nodes for SU2, which runs its two channels as
 			// lane halves, 32 otherwise): single writer per address, summed in the epilogue
 			rpaCopies = nbt / (CORE == SU2 ? 16 : 32); if (rpaCopies < 2) rpaCopies = 2;
@@ -551,11 +559,20 @@ namespace pffrg
 					triChaliceApply(A0, wmat + (node * 4 + 2 * pr) * 32, K);
 					triInverseChaliceApply(A1, wmat + (node * 4 + 2 * pr + 1) * 32, K);
 					// RPA operands of the pairs (0,1) and (2,3); the prefactor 2 (TRIFrgCore.cpp:741-746) and the node weight are folded into A
-					#pragma unroll
-					for (int c = 0; c < 16; ++c)
+					if (NB == 8)
 					{
-						st[(((2 * pr) * 16 + c) * L + j) * NBP + node] = 2.0 * W * A0[c];
-						st[(((2 * pr + 1) * 16 + c) * L + j) * NBP + node] = A1[c];
+						double *s0 = st + (2 * pr) * tri8BufferStride(L) + j * TRI8_RID_STRIDE + node, *s1 = s0 + tri8BufferStride(L);
+						#pragma unroll
+						for (int c = 0; c < 16; ++c) { s0[c * TRI8_NBP] = 2.0 * W * A0[c]; s1[c * TRI8_NBP] = A1[c]; }
+					}
+					else
+					{
+						#pragma unroll
+						for (int c = 0; c < 16; ++c)
+						{
+							st[(((2 * pr) * 16 + c) * L + j) * NBP + node] = 2.0 * W * A0[c];
+							st[(((2 * pr + 1) * 16 + c) * L + j) * NBP + node] = A1[c];
+						}
 					}
 				}
 			}
@@ -654,6 +671,134 @@ namespace pffrg
 				#pragma unroll
 				for (int o = NB >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(subMask, v, o);
 				if (node == 0) rpaOut[c * L + task.x] += v;
+			}
+		}
+	}
+
+	// ---- TRI RPA phase for NB = 8: a warp works on one representative site at a time with lanes = 8 nodes x 2 buffer pairs x
+	// 2 halves of the output index mu (lane = node | pair << 3 | half << 4), so all lanes follow the same term stream and every
+	// shared-memory access is an immediate offset from two lane-constant bases. Per group of terms sharing (rid1, p1, p2):
+	// 8 loads of A^{mu k} (this lane's two mu), per term 16 loads of B^{k nu} accumulated into t, then 32 multiply-adds
+	// r^{mu nu} += eta(mu,k,nu) a^{mu k} t^{k nu}. Stream words (built by buildRpa with TRI8 offsets):
+	//   header (bit 31 set): rid1 * RID_STRIDE | p1 << 16 | p2 << 19   (p = index of the spin permutation in tri8Perm)
+	//   term (bit 31 clear): rid2 * RID_STRIDE | multiplicity << 16
+	__host__ __device__ constexpr int tri8Perm(int p, int i) { return i == 3 ? 3 : (p == 0 ? i : p == 1 ? (i == 0 ? 0 : 3 - i) : p == 2 ? (i == 2 ? 2 : 1 - i) : p == 3 ? (i + 1) % 3 : p == 4 ? (i + 2) % 3 : 2 - i); }
+	// eta(mu, k, nu) = -1 iff mu and nu are of the same kind (spin / density) and k is of the other kind
+	__host__ __device__ constexpr bool tri8EtaClosedFormOk()
+	{
+		for (int mu = 0; mu < 4; ++mu) for (int k = 0; k < 4; ++k) for (int nu = 0; nu < 4; ++nu)
+		{
+			const bool minus = ((mu == 3) == (nu == 3)) && ((k == 3) != (mu == 3));
+			if ((tri::rpa(mu, k, nu).sign < 0) != minus || (tri::rpa(mu, k, nu).exponent & 1)) return false;
+		}
+		return true;
+	}
+	static_assert(tri8EtaClosedFormOk(), "closed form of the RPA sign table does not match the spin algebra");
+
+	__device__ __forceinline__ double flipSignIf(double x, unsigned mask) { return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x)); }
+
+	template <int P1>
+	__device__ __forceinline__ void tri8LoadA(const double *pa, int half, double (&a)[2][4])
+	{
+		// rows: this lane's mu = 2 * half and 2 * half + 1 (mu = 3 is the density index, not permuted)
+		const double *row0 = pa + (half ? tri8Perm(P1, 2) : tri8Perm(P1, 0)) * 4 * TRI8_NBP;
+		const double *row1 = pa + (half ? 3 : tri8Perm(P1, 1)) * 4 * TRI8_NBP;
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) { a[0][k] = row0[tri8Perm(P1, k) * TRI8_NBP]; a[1][k] = row1[tri8Perm(P1, k) * TRI8_NBP]; }
+	}
+	template <int P2>
+	__device__ __forceinline__ void tri8AccumulateB(const double *pb, double m, double (&t)[16])
+	{
+		#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			#pragma unroll
+			for (int nu = 0; nu < 4; ++nu) t[4 * k + nu] = fma(m, pb[(4 * tri8Perm(P2, k) + tri8Perm(P2, nu)) * TRI8_NBP], t[4 * k + nu]);
+		}
+	}
+
+	__device__ __forceinline__ void rpaTri8(const Problem &P, const double *st, double *rpaOut, int tid, int nb)
+	{
+		const int L = sizeL(P);
+		const int lane = tid & 31, wid = tid >> 5;
+		const int node = lane & 7, pair = (lane >> 3) & 1, half = lane >> 4;
+		const bool active = node < nb;
+		const int BS = tri8BufferStride(L);
+		const double *stA = st + (2 * pair) * BS + node, *stB = stA + BS;
+		const unsigned maskHalf = half ? 0x80000000u : 0u, maskNotHalf = half ? 0u : 0x80000000u;
+		for (int ti = P.rpa_slot_off[wid]; ti < P.rpa_slot_off[wid + 1]; ++ti)
+		{
+			const int4 task = P.rpa_tasks[ti]; // {rid, wordBegin, wordEnd, 0}
+			double r[2][4], a[2][4], t[16];
+			#pragma unroll
+			for (int i = 0; i < 4; ++i) { r[0][i] = 0.0; r[1][i] = 0.0; a[0][i] = 0.0; a[1][i] = 0.0; }
+			#pragma unroll
+			for (int c = 0; c < 16; ++c) t[c] = 0.0;
+			int p2 = 0;
+			auto flush = [&]()
+			{
+				// slot 0: mu is a spin index; slot 1: mu = 1 (spin, half 0) or 3 (density, half 1)
+				const double a13s = flipSignIf(a[1][3], maskNotHalf);
+				double a1d[3];
+				#pragma unroll
+				for (int k = 0; k < 3; ++k) a1d[k] = flipSignIf(a[1][k], maskHalf);
+				#pragma unroll
+				for (int nu = 0; nu < 3; ++nu)
+				{
+					r[0][nu] = fma(a[0][0], t[nu], fma(a[0][1], t[4 + nu], fma(a[0][2], t[8 + nu], fma(-a[0][3], t[12 + nu], r[0][nu]))));
+					r[1][nu] = fma(a[1][0], t[nu], fma(a[1][1], t[4 + nu], fma(a[1][2], t[8 + nu], fma(a13s, t[12 + nu], r[1][nu]))));
+				}
+				r[0][3] = fma(a[0][0], t[3], fma(a[0][1], t[7], fma(a[0][2], t[11], fma(a[0][3], t[15], r[0][3]))));
+				r[1][3] = fma(a1d[0], t[3], fma(a1d[1], t[7], fma(a1d[2], t[11], fma(a[1][3], t[15], r[1][3]))));
+				#pragma unroll
+				for (int c = 0; c < 16; ++c) t[c] = 0.0;
+			};
+			#pragma unroll 1
+			for (int i = task.y; i < task.z; ++i)
+			{
+				const unsigned w = __ldg(P.rpa_words + i);
+				if (w >> 31)
+				{
+					flush();
+					const double *pa = stA + (w & 0xffffu);
+					p2 = (w >> 19) & 7;
+					switch ((w >> 16) & 7)
+					{
+					case 0: tri8LoadA<0>(pa, half, a); break;
+					case 1: tri8LoadA<1>(pa, half, a); break;
+					case 2: tri8LoadA<2>(pa, half, a); break;
+					case 3: tri8LoadA<3>(pa, half, a); break;
+					case 4: tri8LoadA<4>(pa, half, a); break;
+					default: tri8LoadA<5>(pa, half, a); break;
+					}
+				}
+				else
+				{
+					const double m = (double)(int)(w >> 16);
+					const double *pb = stB + (w & 0xffffu);
+					switch (p2)
+					{
+					case 0: tri8AccumulateB<0>(pb, m, t); break;
+					case 1: tri8AccumulateB<1>(pb, m, t); break;
+					case 2: tri8AccumulateB<2>(pb, m, t); break;
+					case 3: tri8AccumulateB<3>(pb, m, t); break;
+					case 4: tri8AccumulateB<4>(pb, m, t); break;
+					default: tri8AccumulateB<5>(pb, m, t); break;
+					}
+				}
+			}
+			flush();
+			#pragma unroll
+			for (int s = 0; s < 2; ++s)
+			{
+				#pragma unroll
+				for (int nu = 0; nu < 4; ++nu)
+				{
+					double v = active ? r[s][nu] : 0.0;
+					v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+					v += __shfl_xor_sync(0xffffffffu, v, 8); // the two buffer pairs
+					if ((lane & 15) == 0) rpaOut[(4 * (2 * half + s) + nu) * L + task.x] += v;
+				}
 			}
 		}
 	}
@@ -811,14 +956,17 @@ namespace pffrg
 			const double *nodeW0 = N.wp + (size_t)(tPass ? ti : so) * N.stride, *nodeWt0 = N.wt + (size_t)(tPass ? ti : so) * N.stride;
 			const double *nodeW1 = N.wp + (size_t)uo * N.stride, *nodeWt1 = N.wt + (size_t)uo * N.stride;
 			const int nbuf = tPass ? 8 : 4;
-			const int batch = tPass ? NB : 2 * NB;
+			// nodes per gather batch: a whole number of rounds of the k thread groups where possible
+			const int batchMax = tPass ? NB : 2 * NB;
+			const int batch = cfg.groups <= batchMax ? batchMax / cfg.groups * cfg.groups : batchMax;
+			int staged = 0; // t channel: nodes staged for the next RPA phase
 
 			#pragma unroll 1
 			for (int b0 = 0; b0 < nNodes; b0 += batch)
 			{
 				const int nb = min(batch, nNodes - b0);
-				// t channel: NBT / NB consecutive gather batches are staged side by side before one RPA phase runs over all of them
-				const int stageOff = tPass ? b0 % NBT : 0;
+				// t channel: consecutive gather batches are staged side by side (up to NBT nodes) before one RPA phase runs over all of them
+				const int stageOff = staged;
 				__syncthreads(); // previous batch fully consumed
 				// ---- phase 0: access buffers. Step A: the four interpolated frequencies of every node (one mesh search each)
 				for (int idx = tid; idx < nb * 4; idx += nthreads)
@@ -926,16 +1074,19 @@ namespace pffrg
 						for (int c = 0; c < C; ++c) acc[c] += W * K[c];
 					}
 				}
-				if (tPass && (stageOff + batch == NBT || b0 + batch >= nNodes))
+				if (tPass) staged += nb;
+				if (tPass && (staged + batch > NBT || b0 + batch >= nNodes))
 				{
 					__syncthreads();
-					// ---- phase 2: RPA lattice sum over the stageOff + nb staged nodes
+					// ---- phase 2: RPA lattice sum over the staged nodes
 #ifdef PFFRG_JIT_RPA
-					if (JIT) rpaSpecialised(tid >> 5, tid & 31, stageOff + nb, st, rpaOut);
+					if (JIT) rpaSpecialised(tid >> 5, tid & 31, staged, st, rpaOut);
 					else
 #endif
-					if constexpr (CORE == TRI) rpaTri<NB>(P, cfg, st, rpaOut, tid, nb);
-					else rpaGeneric<CORE, NB>(P, cfg, st, rpaOut, tid, nb);
+					if constexpr (CORE == TRI && NB == 8) rpaTri8(P, st, rpaOut, tid, staged);
+					else if constexpr (CORE == TRI) rpaTri<NB>(P, cfg, st, rpaOut, tid, staged);
+					else rpaGeneric<CORE, NB>(P, cfg, st, rpaOut, tid, staged);
+					staged = 0;
 				}
 			}
 		}

@@ -17,8 +17,19 @@ def _core(d):
     return name, FrgCoreFactory.newFrgCore(name, ProblemTables.from_pfd(d), opts)
 
 
+# kernel variants: the run-time compiled lattice-specialised kernel (default for SU2/XYZ), the precompiled generic kernels
+# (PFFRG_JIT=0) and their smaller gather batches (PFFRG_NB; NB = 8 selects the TRI core's rpaTri8 phase, which large
+# lattices use)
+VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16"}]
+
+
+@pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
 @pytest.mark.parametrize("case", CASES)
-def test_one_step_flow_matches_reference(case):
+def test_one_step_flow_matches_reference(case, variant, monkeypatch):
+    if case.startswith("tri") and "PFFRG_JIT_NBT" in variant:
+        pytest.skip("the TRI core has no run-time compiled variant")
+    for k, x in variant.items():
+        monkeypatch.setenv(k, x)
     d = golden(case)
     name, core = _core(d)
     n = core.n_arrays

@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r1g_pytest_gpu.log 2>&1; tail -3 gpurun_out/r1g_pytest_gpu.log
-for wl in cubic_r7_su2_nw64 honeycomb_kitaev_r7_xyz_nw64 pyrochlore_r8_su2_nw64 square_r4_su2_nw32; do bash tools/gpu_sweep.sh r1g $wl "X=1"; done
-bash tools/gpu_sweep.sh r1g pyrochlore_r8_su2_nw64 "PFFRG_JIT_TILES=2" "PFFRG_THREADS=512"
+python -m pytest tests -m gpu -q > gpurun_out/r1i_pytest_gpu.log 2>&1; tail -8 gpurun_out/r1i_pytest_gpu.log
+bash tools/gpu_ncu.sh r1i kagome_dm_r7_tri_nw64:3000
