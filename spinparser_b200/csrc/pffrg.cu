@@ -331,8 +331,7 @@ namespace
 		return 0;
 	}
 
-	// `nbp` = stride of one representative site in the staging area (doubles); tri8 selects the header format of rpaTri8
-	void buildRpa(const pffrg_desc *d, int core, int nslots, int nbp, bool tri8, std::vector<unsigned> &words, std::vector<int4> &tasks, std::vector<int> &slotOff, int64_t &unique)
+	void buildRpa(const pffrg_desc *d, int core, int nslots, int nbp, std::vector<unsigned> &words, std::vector<int4> &tasks, std::vector<int> &slotOff, int64_t &unique)
 	{
 		const int L = d->n_sites;
 		std::vector<int4> perRid;
@@ -347,8 +346,7 @@ namespace
 				const int r1 = std::get<0>(kv.first), p1 = std::get<1>(kv.first), p2 = std::get<2>(kv.first), r2 = std::get<3>(kv.first);
 				if (r1 != lastR1 || p1 != lastP1 || p2 != lastP2)
 				{
-					if (tri8) words.push_back(0x80000000u | (unsigned)(r1 * nbp) | ((unsigned)permIndex(p1) << 16) | ((unsigned)permIndex(p2) << 19));
-					else words.push_back(0x80000000u | (unsigned)(r1 * nbp) | ((unsigned)p1 << 16) | ((unsigned)p2 << 22));
+					words.push_back(0x80000000u | (unsigned)(r1 * nbp) | ((unsigned)p1 << 16) | ((unsigned)p2 << 22));
 					lastR1 = r1; lastP1 = p1; lastP2 = p2;
 				}
 				words.push_back((unsigned)(r2 * nbp) | ((unsigned)std::min(kv.second, 32767) << 16));
@@ -369,6 +367,65 @@ namespace
 		}
 		slotOff.assign(1, 0);
 		for (auto &sl : bySlot) { for (auto &t : sl) tasks.push_back(t); slotOff.push_back((int)tasks.size()); }
+	}
+
+	// Term stream of rpaTri8 (pffrg_kernels.cuh): per representative site the merged overlap terms sorted into runs of equal spin
+	// permutations (p1, p2); inside a run, groups of equal rid1 (header word + one word per term). Each task = one rid:
+	// {rid, position of its run descriptors, number of runs}; tasks are dealt to the warps longest-first.
+	void buildRpaTri8(const pffrg_desc *d, int nWarps, std::vector<unsigned> &words, std::vector<int4> &tasks, std::vector<int> &slotOff, int64_t &unique)
+	{
+		const int L = d->n_sites;
+		struct Entry { int p1, p2, r1, r2, mult; };
+		std::vector<int4> perRid; std::vector<long> cost;
+		unique = 0;
+		for (int rid = 0; rid < L; ++rid)
+		{
+			std::vector<Entry> entries;
+			for (auto &kv : mergedOverlap(d, TRI, rid))
+				entries.push_back({ permIndex(std::get<1>(kv.first)), permIndex(std::get<2>(kv.first)), std::get<0>(kv.first), std::get<3>(kv.first), kv.second });
+			unique += (int64_t)entries.size();
+			std::stable_sort(entries.begin(), entries.end(), [](const Entry &a, const Entry &b) { return std::make_tuple(a.p1, a.p2, a.r1, a.r2) < std::make_tuple(b.p1, b.p2, b.r1, b.r2); });
+			std::vector<unsigned> descriptors, body;
+			std::vector<size_t> descriptorBodyOffset;
+			size_t i = 0;
+			while (i < entries.size())
+			{
+				size_t j = i;
+				while (j < entries.size() && entries[j].p1 == entries[i].p1 && entries[j].p2 == entries[i].p2) ++j;
+				unsigned groups = 0;
+				descriptorBodyOffset.push_back(body.size());
+				for (size_t k = i; k < j;)
+				{
+					size_t m = k;
+					while (m < j && entries[m].r1 == entries[k].r1 && m - k < 1024) ++m;
+					body.push_back((unsigned)(entries[k].r1 * TRI8_RID_STRIDE) | ((unsigned)(m - k - 1) << 22));
+					for (size_t t = k; t < m; ++t) body.push_back((unsigned)(entries[t].r2 * TRI8_RID_STRIDE) | ((unsigned)std::min(entries[t].mult, 32767) << 16));
+					++groups; k = m;
+				}
+				body.push_back(0u); body.push_back(1u << 16); // dummy group: target of the software pipeline's last prefetch
+				descriptors.push_back((unsigned)entries[i].p1 | ((unsigned)entries[i].p2 << 3) | (groups << 6));
+				i = j;
+			}
+			const int first = (int)words.size();
+			const size_t bodyBase = words.size() + 2 * descriptors.size();
+			for (size_t q = 0; q < descriptors.size(); ++q) { words.push_back(descriptors[q]); words.push_back((unsigned)(bodyBase + descriptorBodyOffset[q])); }
+			words.insert(words.end(), body.begin(), body.end());
+			perRid.push_back(make_int4(rid, first, (int)descriptors.size(), 0));
+			cost.push_back((long)body.size() + 16 * (long)descriptors.size() + 8);
+		}
+		std::vector<int> order(L);
+		std::iota(order.begin(), order.end(), 0);
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+		std::vector<std::vector<int4>> byWarp(nWarps);
+		std::vector<long> load(nWarps, 0);
+		for (int r : order)
+		{
+			const int best = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+			byWarp[best].push_back(perRid[r]);
+			load[best] += cost[r];
+		}
+		slotOff.assign(1, 0);
+		for (auto &w : byWarp) { for (auto &t : w) tasks.push_back(t); slotOff.push_back((int)tasks.size()); }
 	}
 
 	// the RPA sum as a list of multiply-adds over staged operands [channel][rid], for the code generator
@@ -625,7 +682,8 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	h->nslots = tri8 ? h->threads / 32 : (h->threads / 32) * (32 / h->nb);
 
 	std::vector<unsigned> words; std::vector<int4> tasks; std::vector<int> slotOff;
-	buildRpa(d, h->core, h->nslots, tri8 ? TRI8_RID_STRIDE : h->nb + 1, tri8, words, tasks, slotOff, h->uniquePairs);
+	if (tri8) buildRpaTri8(d, h->nslots, words, tasks, slotOff, h->uniquePairs);
+	else buildRpa(d, h->core, h->nslots, h->nb + 1, words, tasks, slotOff, h->uniquePairs);
 
 	std::vector<int> sitesPerm(L), invPerm(L);
 	for (int j = 0; j < L; ++j) { sitesPerm[j] = packPerm(d->sites_perm + 3 * j); invPerm[j] = packPerm(d->inverted_perm + 3 * j); }

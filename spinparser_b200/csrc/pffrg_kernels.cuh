@@ -679,9 +679,9 @@ namespace pffrg
 	// 2 halves of the output index mu (lane = node | pair << 3 | half << 4), so all lanes follow the same term stream and every
 	// shared-memory access is an immediate offset from two lane-constant bases. Per group of terms sharing (rid1, p1, p2):
 	// 8 loads of A^{mu k} (this lane's two mu), per term 16 loads of B^{k nu} accumulated into t, then 32 multiply-adds
-	// r^{mu nu} += eta(mu,k,nu) a^{mu k} t^{k nu}. Stream words (built by buildRpa with TRI8 offsets):
-	//   header (bit 31 set): rid1 * RID_STRIDE | p1 << 16 | p2 << 19   (p = index of the spin permutation in tri8Perm)
-	//   term (bit 31 clear): rid2 * RID_STRIDE | multiplicity << 16
+	// r^{mu nu} += eta(mu,k,nu) a^{mu k} t^{k nu}. The groups of a representative site are sorted into runs of equal (p1, p2)
+	// (p = index of the spin permutation in tri8Perm), each run is executed by code specialised on the two permutations
+	// (tri8Run; stream built by buildRpaTri8 in pffrg.cu).
 	__host__ __device__ constexpr int tri8Perm(int p, int i) { return i == 3 ? 3 : (p == 0 ? i : p == 1 ? (i == 0 ? 0 : 3 - i) : p == 2 ? (i == 2 ? 2 : 1 - i) : p == 3 ? (i + 1) % 3 : p == 4 ? (i + 2) % 3 : 2 - i); }
 	// eta(mu, k, nu) = -1 iff mu and nu are of the same kind (spin / density) and k is of the other kind
 	__host__ __device__ constexpr bool tri8EtaClosedFormOk()
@@ -706,17 +706,98 @@ namespace pffrg
 		#pragma unroll
 		for (int k = 0; k < 4; ++k) { a[0][k] = row0[tri8Perm(P1, k) * TRI8_NBP]; a[1][k] = row1[tri8Perm(P1, k) * TRI8_NBP]; }
 	}
+	// first term of a group: t^{k nu} = multiplicity * B^{p2 k, p2 nu}[rid2]
 	template <int P2>
-	__device__ __forceinline__ void tri8AccumulateB(const double *pb, double m, double (&t)[16])
+	__device__ __forceinline__ void tri8LoadB(const double *stB, unsigned word, double (&t)[16])
 	{
+		const double *pb = stB + (word & 0xffffu);
+		const unsigned mult = word >> 16;
 		#pragma unroll
 		for (int k = 0; k < 4; ++k)
 		{
 			#pragma unroll
-			for (int nu = 0; nu < 4; ++nu) t[4 * k + nu] = fma(m, pb[(4 * tri8Perm(P2, k) + tri8Perm(P2, nu)) * TRI8_NBP], t[4 * k + nu]);
+			for (int nu = 0; nu < 4; ++nu) t[4 * k + nu] = pb[(4 * tri8Perm(P2, k) + tri8Perm(P2, nu)) * TRI8_NBP];
+		}
+		if (mult != 1)
+		{
+			const double m = (double)(int)mult;
+			#pragma unroll
+			for (int c = 0; c < 16; ++c) t[c] *= m;
 		}
 	}
 
+	// One run of groups that share the spin permutations (P1, P2). Words: per group a header  rid1 * RID_STRIDE | (terms - 1) << 22
+	// followed by `terms` words  rid2 * RID_STRIDE | multiplicity << 16. The operands of group g + 1 are loaded before the
+	// multiply-adds of group g are issued (software pipeline; the loop-carried state is a, t and the two stream words).
+	template <int P1, int P2>
+	__device__ __forceinline__ void tri8Run(const unsigned *__restrict__ words, int nGroups, const double *stA, const double *stB, int half,
+		unsigned maskHalf, unsigned maskNotHalf, double (&r)[2][4])
+	{
+		unsigned hw = __ldg(words), tw = __ldg(words + 1);
+		double a[2][4], t[16];
+		tri8LoadA<P1>(stA + (hw & 0xffffu), half, a);
+		tri8LoadB<P2>(stB, tw, t);
+		#pragma unroll 1
+		for (int g = 0; g < nGroups; ++g)
+		{
+			// further terms of this group (rare: only where the symmetry reduction merged several sites)
+			const int extra = (int)(hw >> 22);
+			for (int k = 0; k < extra; ++k)
+			{
+				const unsigned w = __ldg(words + 2 + k);
+				const double *pb = stB + (w & 0xffffu);
+				const double m = (double)(int)(w >> 16);
+				#pragma unroll
+				for (int kk = 0; kk < 4; ++kk)
+				{
+					#pragma unroll
+					for (int nu = 0; nu < 4; ++nu) t[4 * kk + nu] = fma(m, pb[(4 * tri8Perm(P2, kk) + tri8Perm(P2, nu)) * TRI8_NBP], t[4 * kk + nu]);
+				}
+			}
+			words += 2 + extra;
+			// operands of the next group (the stream is padded with one dummy group, so the loads of the last iteration are harmless)
+			const unsigned hwNext = __ldg(words), twNext = __ldg(words + 1);
+			double aNext[2][4], tNext[16];
+			tri8LoadA<P1>(stA + (hwNext & 0xffffu), half, aNext);
+			tri8LoadB<P2>(stB, twNext, tNext);
+			// r^{mu nu} += eta(mu,k,nu) a^{mu k} t^{k nu}. Slot 0: mu is a spin index; slot 1: mu = 1 (spin, half 0) or 3 (density, half 1)
+			const double a13s = flipSignIf(a[1][3], maskNotHalf);
+			double a1d[3];
+			#pragma unroll
+			for (int k = 0; k < 3; ++k) a1d[k] = flipSignIf(a[1][k], maskHalf);
+			#pragma unroll
+			for (int nu = 0; nu < 3; ++nu)
+			{
+				r[0][nu] = fma(a[0][0], t[nu], fma(a[0][1], t[4 + nu], fma(a[0][2], t[8 + nu], fma(-a[0][3], t[12 + nu], r[0][nu]))));
+				r[1][nu] = fma(a[1][0], t[nu], fma(a[1][1], t[4 + nu], fma(a[1][2], t[8 + nu], fma(a13s, t[12 + nu], r[1][nu]))));
+			}
+			r[0][3] = fma(a[0][0], t[3], fma(a[0][1], t[7], fma(a[0][2], t[11], fma(a[0][3], t[15], r[0][3]))));
+			r[1][3] = fma(a1d[0], t[3], fma(a1d[1], t[7], fma(a1d[2], t[11], fma(a[1][3], t[15], r[1][3]))));
+			hw = hwNext;
+			#pragma unroll
+			for (int i = 0; i < 4; ++i) { a[0][i] = aNext[0][i]; a[1][i] = aNext[1][i]; }
+			#pragma unroll
+			for (int c = 0; c < 16; ++c) t[c] = tNext[c];
+		}
+	}
+
+	template <int P1>
+	__device__ __forceinline__ void tri8RunP1(int p2, const unsigned *__restrict__ words, int nGroups, const double *stA, const double *stB, int half,
+		unsigned maskHalf, unsigned maskNotHalf, double (&r)[2][4])
+	{
+		switch (p2)
+		{
+		case 0: tri8Run<P1, 0>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+		case 1: tri8Run<P1, 1>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+		case 2: tri8Run<P1, 2>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+		case 3: tri8Run<P1, 3>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+		case 4: tri8Run<P1, 4>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+		default: tri8Run<P1, 5>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+		}
+	}
+
+	// Task = one representative site: {rid, first run descriptor, number of runs}. Run descriptors (P.rpa_words[first ...], two words
+	// each): p1 | p2 << 3 | groups << 6, and the position of the run's group words.
 	__device__ __forceinline__ void rpaTri8(const Problem &P, const double *st, double *rpaOut, int tid, int nb)
 	{
 		const int L = sizeL(P);
@@ -728,66 +809,26 @@ namespace pffrg
 		const unsigned maskHalf = half ? 0x80000000u : 0u, maskNotHalf = half ? 0u : 0x80000000u;
 		for (int ti = P.rpa_slot_off[wid]; ti < P.rpa_slot_off[wid + 1]; ++ti)
 		{
-			const int4 task = P.rpa_tasks[ti]; // {rid, wordBegin, wordEnd, 0}
-			double r[2][4], a[2][4], t[16];
+			const int4 task = P.rpa_tasks[ti]; // {rid, first run descriptor, number of runs, 0}
+			double r[2][4];
 			#pragma unroll
-			for (int i = 0; i < 4; ++i) { r[0][i] = 0.0; r[1][i] = 0.0; a[0][i] = 0.0; a[1][i] = 0.0; }
-			#pragma unroll
-			for (int c = 0; c < 16; ++c) t[c] = 0.0;
-			int p2 = 0;
-			auto flush = [&]()
-			{
-				// slot 0: mu is a spin index; slot 1: mu = 1 (spin, half 0) or 3 (density, half 1)
-				const double a13s = flipSignIf(a[1][3], maskNotHalf);
-				double a1d[3];
-				#pragma unroll
-				for (int k = 0; k < 3; ++k) a1d[k] = flipSignIf(a[1][k], maskHalf);
-				#pragma unroll
-				for (int nu = 0; nu < 3; ++nu)
-				{
-					r[0][nu] = fma(a[0][0], t[nu], fma(a[0][1], t[4 + nu], fma(a[0][2], t[8 + nu], fma(-a[0][3], t[12 + nu], r[0][nu]))));
-					r[1][nu] = fma(a[1][0], t[nu], fma(a[1][1], t[4 + nu], fma(a[1][2], t[8 + nu], fma(a13s, t[12 + nu], r[1][nu]))));
-				}
-				r[0][3] = fma(a[0][0], t[3], fma(a[0][1], t[7], fma(a[0][2], t[11], fma(a[0][3], t[15], r[0][3]))));
-				r[1][3] = fma(a1d[0], t[3], fma(a1d[1], t[7], fma(a1d[2], t[11], fma(a[1][3], t[15], r[1][3]))));
-				#pragma unroll
-				for (int c = 0; c < 16; ++c) t[c] = 0.0;
-			};
+			for (int i = 0; i < 4; ++i) { r[0][i] = 0.0; r[1][i] = 0.0; }
 			#pragma unroll 1
-			for (int i = task.y; i < task.z; ++i)
+			for (int q = 0; q < task.z; ++q)
 			{
-				const unsigned w = __ldg(P.rpa_words + i);
-				if (w >> 31)
+				const unsigned desc = __ldg(P.rpa_words + task.y + 2 * q), pos = __ldg(P.rpa_words + task.y + 2 * q + 1);
+				const int p2 = (desc >> 3) & 7, nGroups = (int)(desc >> 6);
+				const unsigned *words = P.rpa_words + pos;
+				switch (desc & 7)
 				{
-					flush();
-					const double *pa = stA + (w & 0xffffu);
-					p2 = (w >> 19) & 7;
-					switch ((w >> 16) & 7)
-					{
-					case 0: tri8LoadA<0>(pa, half, a); break;
-					case 1: tri8LoadA<1>(pa, half, a); break;
-					case 2: tri8LoadA<2>(pa, half, a); break;
-					case 3: tri8LoadA<3>(pa, half, a); break;
-					case 4: tri8LoadA<4>(pa, half, a); break;
-					default: tri8LoadA<5>(pa, half, a); break;
-					}
-				}
-				else
-				{
-					const double m = (double)(int)(w >> 16);
-					const double *pb = stB + (w & 0xffffu);
-					switch (p2)
-					{
-					case 0: tri8AccumulateB<0>(pb, m, t); break;
-					case 1: tri8AccumulateB<1>(pb, m, t); break;
-					case 2: tri8AccumulateB<2>(pb, m, t); break;
-					case 3: tri8AccumulateB<3>(pb, m, t); break;
-					case 4: tri8AccumulateB<4>(pb, m, t); break;
-					default: tri8AccumulateB<5>(pb, m, t); break;
-					}
+				case 0: tri8RunP1<0>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+				case 1: tri8RunP1<1>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+				case 2: tri8RunP1<2>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+				case 3: tri8RunP1<3>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+				case 4: tri8RunP1<4>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+				default: tri8RunP1<5>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
 				}
 			}
-			flush();
 			#pragma unroll
 			for (int s = 0; s < 2; ++s)
 			{
@@ -958,7 +999,8 @@ namespace pffrg
 			const int nbuf = tPass ? 8 : 4;
 			// nodes per gather batch: a whole number of rounds of the k thread groups where possible
 			const int batchMax = tPass ? NB : 2 * NB;
-			const int batch = cfg.groups <= batchMax ? batchMax / cfg.groups * cfg.groups : batchMax;
+			// (not in the run-time compiled kernel: its RPA phase costs the same for any number of staged nodes, so NBT is filled exactly)
+			const int batch = (!JIT && cfg.groups <= batchMax) ? batchMax / cfg.groups * cfg.groups : batchMax;
 			int staged = 0; // t channel: nodes staged for the next RPA phase
 
 			#pragma unroll 1
