@@ -393,22 +393,27 @@ namespace
 				size_t j = i;
 				while (j < entries.size() && entries[j].p1 == entries[i].p1 && entries[j].p2 == entries[i].p2) ++j;
 				unsigned groups = 0;
+				while (body.size() & 3) body.push_back(0u); // records are read in pairs as 16-byte words
 				descriptorBodyOffset.push_back(body.size());
+				std::vector<unsigned> extras;
 				for (size_t k = i; k < j;)
 				{
 					size_t m = k;
 					while (m < j && entries[m].r1 == entries[k].r1 && m - k < 1024) ++m;
 					body.push_back((unsigned)(entries[k].r1 * TRI8_RID_STRIDE) | ((unsigned)(m - k - 1) << 22));
-					for (size_t t = k; t < m; ++t) body.push_back((unsigned)(entries[t].r2 * TRI8_RID_STRIDE) | ((unsigned)std::min(entries[t].mult, 32767) << 16));
+					for (size_t t = k; t < m; ++t)
+						(t == k ? body : extras).push_back((unsigned)(entries[t].r2 * TRI8_RID_STRIDE) | ((unsigned)std::min(entries[t].mult, 32767) << 16));
 					++groups; k = m;
 				}
-				body.push_back(0u); body.push_back(1u << 16); // dummy group: target of the software pipeline's last prefetch
+				if (groups & 1) { body.push_back(0u); body.push_back(0u); } // odd run: a record with multiplicity 0 completes the last pair
+				body.insert(body.end(), extras.begin(), extras.end());
 				descriptors.push_back((unsigned)entries[i].p1 | ((unsigned)entries[i].p2 << 3) | (groups << 6));
 				i = j;
 			}
 			const int first = (int)words.size();
-			const size_t bodyBase = words.size() + 2 * descriptors.size();
+			const size_t bodyBase = (words.size() + 2 * descriptors.size() + 3) / 4 * 4;
 			for (size_t q = 0; q < descriptors.size(); ++q) { words.push_back(descriptors[q]); words.push_back((unsigned)(bodyBase + descriptorBodyOffset[q])); }
+			words.resize(bodyBase, 0u);
 			words.insert(words.end(), body.begin(), body.end());
 			perRid.push_back(make_int4(rid, first, (int)descriptors.size(), 0));
 			cost.push_back((long)body.size() + 16 * (long)descriptors.size() + 8);

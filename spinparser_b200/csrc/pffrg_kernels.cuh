@@ -726,73 +726,88 @@ namespace pffrg
 		}
 	}
 
-	// One run of groups that share the spin permutations (P1, P2). Words: per group a header  rid1 * RID_STRIDE | (terms - 1) << 22
-	// followed by `terms` words  rid2 * RID_STRIDE | multiplicity << 16. The operands of group g + 1 are loaded before the
-	// multiply-adds of group g are issued (software pipeline; the loop-carried state is a, t and the two stream words).
+	// further terms of a group (rare: only where the symmetry reduction merged several sites)
+	template <int P2>
+	__device__ __forceinline__ void tri8ExtraTerms(const unsigned *__restrict__ words, int extra, const double *stB, double (&t)[16])
+	{
+		for (int k = 0; k < extra; ++k)
+		{
+			const unsigned w = __ldg(words + k);
+			const double *pb = stB + (w & 0xffffu);
+			const double m = (double)(int)(w >> 16);
+			#pragma unroll
+			for (int kk = 0; kk < 4; ++kk)
+			{
+				#pragma unroll
+				for (int nu = 0; nu < 4; ++nu) t[4 * kk + nu] = fma(m, pb[(4 * tri8Perm(P2, kk) + tri8Perm(P2, nu)) * TRI8_NBP], t[4 * kk + nu]);
+			}
+		}
+	}
+
+	// r^{mu nu} += eta(mu,k,nu) a^{mu k} t^{k nu}. Slot 0: mu is a spin index; slot 1: mu = 1 (spin, half 0) or 3 (density, half 1)
+	__device__ __forceinline__ void tri8Contract(const double (&a)[2][4], const double (&t)[16], unsigned maskHalf, unsigned maskNotHalf, double (&r)[2][4])
+	{
+		const double a13s = flipSignIf(a[1][3], maskNotHalf);
+		double a1d[3];
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) a1d[k] = flipSignIf(a[1][k], maskHalf);
+		#pragma unroll
+		for (int nu = 0; nu < 3; ++nu)
+		{
+			r[0][nu] = fma(a[0][0], t[nu], fma(a[0][1], t[4 + nu], fma(a[0][2], t[8 + nu], fma(-a[0][3], t[12 + nu], r[0][nu]))));
+			r[1][nu] = fma(a[1][0], t[nu], fma(a[1][1], t[4 + nu], fma(a[1][2], t[8 + nu], fma(a13s, t[12 + nu], r[1][nu]))));
+		}
+		r[0][3] = fma(a[0][0], t[3], fma(a[0][1], t[7], fma(a[0][2], t[11], fma(a[0][3], t[15], r[0][3]))));
+		r[1][3] = fma(a1d[0], t[3], fma(a1d[1], t[7], fma(a1d[2], t[11], fma(a[1][3], t[15], r[1][3]))));
+	}
+
+	// One run of groups that share the spin permutations (P1, P2). Stream: nGroups + 1 records of two words (8-byte aligned)
+	//   rid1 * RID_STRIDE | (terms - 1) << 22,   rid2 * RID_STRIDE | multiplicity << 16      (first term of the group)
+	// followed by the further terms of all groups in order. Two groups are processed per iteration on separate accumulators
+	// (16 independent chains of multiply-adds); a run with an odd number of groups ends with a record of multiplicity 0.
+	// The records of the next pair are fetched one iteration ahead.
 	template <int P1, int P2>
 	__device__ __forceinline__ void tri8Run(const unsigned *__restrict__ words, int nGroups, const double *stA, const double *stB, int half,
-		unsigned maskHalf, unsigned maskNotHalf, double (&r)[2][4])
+		unsigned maskHalf, unsigned maskNotHalf, double (&r0)[2][4], double (&r1)[2][4])
 	{
-		unsigned hw = __ldg(words), tw = __ldg(words + 1);
-		double a[2][4], t[16];
-		tri8LoadA<P1>(stA + (hw & 0xffffu), half, a);
-		tri8LoadB<P2>(stB, tw, t);
+		const uint4 *records = reinterpret_cast<const uint4 *>(words); // one pair of records
+		const int nPairs = (nGroups + 1) >> 1;
+		const unsigned *extras = words + 4 * nPairs;
+		uint4 rec = __ldg(records);
 		#pragma unroll 1
-		for (int g = 0; g < nGroups; ++g)
+		for (int p = 0; p < nPairs; ++p)
 		{
-			// further terms of this group (rare: only where the symmetry reduction merged several sites)
-			const int extra = (int)(hw >> 22);
-			for (int k = 0; k < extra; ++k)
+			const uint4 cur = rec;
+			if (p + 1 < nPairs) rec = __ldg(records + p + 1);
+			double a0[2][4], t0[16], a1[2][4], t1[16];
+			tri8LoadA<P1>(stA + (cur.x & 0xffffu), half, a0);
+			tri8LoadB<P2>(stB, cur.y, t0);
+			tri8LoadA<P1>(stA + (cur.z & 0xffffu), half, a1);
+			tri8LoadB<P2>(stB, cur.w, t1);
+			const int extra0 = (int)(cur.x >> 22), extra1 = (int)(cur.z >> 22);
+			if (extra0 | extra1)
 			{
-				const unsigned w = __ldg(words + 2 + k);
-				const double *pb = stB + (w & 0xffffu);
-				const double m = (double)(int)(w >> 16);
-				#pragma unroll
-				for (int kk = 0; kk < 4; ++kk)
-				{
-					#pragma unroll
-					for (int nu = 0; nu < 4; ++nu) t[4 * kk + nu] = fma(m, pb[(4 * tri8Perm(P2, kk) + tri8Perm(P2, nu)) * TRI8_NBP], t[4 * kk + nu]);
-				}
+				tri8ExtraTerms<P2>(extras, extra0, stB, t0);
+				tri8ExtraTerms<P2>(extras + extra0, extra1, stB, t1);
+				extras += extra0 + extra1;
 			}
-			words += 2 + extra;
-			// operands of the next group (the stream is padded with one dummy group, so the loads of the last iteration are harmless)
-			const unsigned hwNext = __ldg(words), twNext = __ldg(words + 1);
-			double aNext[2][4], tNext[16];
-			tri8LoadA<P1>(stA + (hwNext & 0xffffu), half, aNext);
-			tri8LoadB<P2>(stB, twNext, tNext);
-			// r^{mu nu} += eta(mu,k,nu) a^{mu k} t^{k nu}. Slot 0: mu is a spin index; slot 1: mu = 1 (spin, half 0) or 3 (density, half 1)
-			const double a13s = flipSignIf(a[1][3], maskNotHalf);
-			double a1d[3];
-			#pragma unroll
-			for (int k = 0; k < 3; ++k) a1d[k] = flipSignIf(a[1][k], maskHalf);
-			#pragma unroll
-			for (int nu = 0; nu < 3; ++nu)
-			{
-				r[0][nu] = fma(a[0][0], t[nu], fma(a[0][1], t[4 + nu], fma(a[0][2], t[8 + nu], fma(-a[0][3], t[12 + nu], r[0][nu]))));
-				r[1][nu] = fma(a[1][0], t[nu], fma(a[1][1], t[4 + nu], fma(a[1][2], t[8 + nu], fma(a13s, t[12 + nu], r[1][nu]))));
-			}
-			r[0][3] = fma(a[0][0], t[3], fma(a[0][1], t[7], fma(a[0][2], t[11], fma(a[0][3], t[15], r[0][3]))));
-			r[1][3] = fma(a1d[0], t[3], fma(a1d[1], t[7], fma(a1d[2], t[11], fma(a[1][3], t[15], r[1][3]))));
-			hw = hwNext;
-			#pragma unroll
-			for (int i = 0; i < 4; ++i) { a[0][i] = aNext[0][i]; a[1][i] = aNext[1][i]; }
-			#pragma unroll
-			for (int c = 0; c < 16; ++c) t[c] = tNext[c];
+			tri8Contract(a0, t0, maskHalf, maskNotHalf, r0);
+			tri8Contract(a1, t1, maskHalf, maskNotHalf, r1);
 		}
 	}
 
 	template <int P1>
 	__device__ __forceinline__ void tri8RunP1(int p2, const unsigned *__restrict__ words, int nGroups, const double *stA, const double *stB, int half,
-		unsigned maskHalf, unsigned maskNotHalf, double (&r)[2][4])
+		unsigned maskHalf, unsigned maskNotHalf, double (&r)[2][4], double (&rr)[2][4])
 	{
 		switch (p2)
 		{
-		case 0: tri8Run<P1, 0>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
-		case 1: tri8Run<P1, 1>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
-		case 2: tri8Run<P1, 2>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
-		case 3: tri8Run<P1, 3>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
-		case 4: tri8Run<P1, 4>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
-		default: tri8Run<P1, 5>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+		case 0: tri8Run<P1, 0>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
+		case 1: tri8Run<P1, 1>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
+		case 2: tri8Run<P1, 2>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
+		case 3: tri8Run<P1, 3>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
+		case 4: tri8Run<P1, 4>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
+		default: tri8Run<P1, 5>(words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
 		}
 	}
 
@@ -810,9 +825,9 @@ namespace pffrg
 		for (int ti = P.rpa_slot_off[wid]; ti < P.rpa_slot_off[wid + 1]; ++ti)
 		{
 			const int4 task = P.rpa_tasks[ti]; // {rid, first run descriptor, number of runs, 0}
-			double r[2][4];
+			double r[2][4], rr[2][4]; // two accumulator sets (even / odd groups), summed below
 			#pragma unroll
-			for (int i = 0; i < 4; ++i) { r[0][i] = 0.0; r[1][i] = 0.0; }
+			for (int i = 0; i < 4; ++i) { r[0][i] = 0.0; r[1][i] = 0.0; rr[0][i] = 0.0; rr[1][i] = 0.0; }
 			#pragma unroll 1
 			for (int q = 0; q < task.z; ++q)
 			{
@@ -821,12 +836,12 @@ namespace pffrg
 				const unsigned *words = P.rpa_words + pos;
 				switch (desc & 7)
 				{
-				case 0: tri8RunP1<0>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
-				case 1: tri8RunP1<1>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
-				case 2: tri8RunP1<2>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
-				case 3: tri8RunP1<3>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
-				case 4: tri8RunP1<4>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
-				default: tri8RunP1<5>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r); break;
+				case 0: tri8RunP1<0>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
+				case 1: tri8RunP1<1>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
+				case 2: tri8RunP1<2>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
+				case 3: tri8RunP1<3>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
+				case 4: tri8RunP1<4>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
+				default: tri8RunP1<5>(p2, words, nGroups, stA, stB, half, maskHalf, maskNotHalf, r, rr); break;
 				}
 			}
 			#pragma unroll
@@ -835,7 +850,7 @@ namespace pffrg
 				#pragma unroll
 				for (int nu = 0; nu < 4; ++nu)
 				{
-					double v = active ? r[s][nu] : 0.0;
+					double v = active ? r[s][nu] + rr[s][nu] : 0.0;
 					v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
 					v += __shfl_xor_sync(0xffffffffu, v, 8); // the two buffer pairs
 					if ((lane & 15) == 0) rpaOut[(4 * (2 * half + s) + nu) * L + task.x] += v;
