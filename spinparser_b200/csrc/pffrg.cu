@@ -521,16 +521,19 @@ namespace
 	{
 		const CoreModel m = modelOf(h->core);
 		const int nw = h->nw;
+		int64_t sumT = 0; for (int t = 0; t < nw; ++t) sumT += counts[t];
+		std::vector<int64_t> prefixT(nw + 1, 0); for (int t = 0; t < nw; ++t) prefixT[t + 1] = prefixT[t] + counts[t];
 		int64_t nS = 0, nT = 0, nU = 0;
-		for (int64_t it = begin; it < end; ++it)
-		{
-			int64_t su = it / nw; int t = (int)(it % nw);
-			int so = (int)((std::sqrt(8.0 * su + 1.0) - 1.0) * 0.5);
-			while ((int64_t)(so + 1) * (so + 2) / 2 <= su) ++so;
-			while ((int64_t)so * (so + 1) / 2 > su) --so;
-			int uo = (int)(su - (int64_t)so * (so + 1) / 2);
-			nS += counts[so]; nT += counts[t]; nU += counts[uo];
-		}
+		// items are ordered su-major, t-minor: whole (s,u) blocks contribute nw * (n(so) + n(uo)) ladder and sum_t n(t) t-channel evaluations
+		int64_t su = 0;
+		for (int so = 0; so < nw; ++so)
+			for (int uo = 0; uo <= so; ++uo, ++su)
+			{
+				const int64_t lo = std::max<int64_t>(begin, su * nw), hi = std::min<int64_t>(end, (su + 1) * nw);
+				if (hi <= lo) continue;
+				nS += (hi - lo) * counts[so]; nU += (hi - lo) * counts[uo];
+				nT += prefixT[hi - su * nw] - prefixT[lo - su * nw];
+			}
 		const double L = h->L, C = m.C;
 		h->stats.items = end - begin;
 		h->stats.kernel_evals = nS + nT + nU;
@@ -846,7 +849,6 @@ int pffrg_compute_step(pffrg_handle h, int *diverged)
 	int64_t begin = h->bounds[h->rank], end = h->bounds[h->rank + 1];
 	if (h->userEnd > h->userBegin) { begin = h->userBegin; end = h->userEnd; }
 	h->curBegin = begin; h->curEnd = end;
-	fillStats(h, counts, begin, end);
 
 	const Problem P = h->problem();
 	CUDA_TRY(cudaMemsetAsync(h->dNan.p, 0, sizeof(int), h->stream));
@@ -857,7 +859,7 @@ int pffrg_compute_step(pffrg_handle h, int *diverged)
 	else v2FlowKernel<TRI><<<h->nw, 128, smemV2, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->dFlow2.p);
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
-	nodeTableKernel<<<(h->nw + 63) / 64, 64, sizeof(double) * 3 * h->nw, h->stream>>>(P, h->nodeTable(), h->dV2.p, h->dFlow2.p, h->dCutoff.p);
+	nodeTableKernel<<<h->nw, 128, sizeof(double) * (3 * h->nw + 2 * h->nodeStride), h->stream>>>(P, h->nodeTable(), h->dV2.p, h->dFlow2.p, h->dCutoff.p);
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
 	CUDA_TRY(launchFlowDispatch(h, begin, end - begin));
@@ -865,6 +867,7 @@ int pffrg_compute_step(pffrg_handle h, int *diverged)
 	h->stats.launches = 3;
 	if (h->nRanks > 1 && !(h->userEnd > h->userBegin)) NCCL_TRY(nccl().AllReduce(h->dNan.p, h->dNan.p, 1, ncclInt, ncclMax, h->comm, h->stream));
 	CUDA_TRY(cudaMemcpyAsync(h->hNan, h->dNan.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	fillStats(h, counts, begin, end); // host work overlaps with the kernels
 	CUDA_TRY(cudaStreamSynchronize(h->stream));
 	h->stats.ms_v2_flow = elapsed(h->ev[0], h->ev[1]);
 	h->stats.ms_node_table = elapsed(h->ev[1], h->ev[2]);

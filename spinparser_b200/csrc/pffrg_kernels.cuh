@@ -147,90 +147,112 @@ namespace pffrg
 	//   three Katanin segments           0.5 * trapezoid weight * Sdot(w')/(G(w')^2 G(x+w'))  :343-347,:378-392
 	// The node enumeration follows ImplicitIntegrator::integrateWithObscure{Right,,Left}Boundar{y,ies}.
 	// ================================================================================================================
-	__global__ void nodeTableKernel(Problem P, NodeTable N, const double *__restrict__ v2, const double *__restrict__ v2flow, const double *cutoffPtr)
+	// One CTA per transfer frequency x. Thread 0 enumerates the nodes (integration frequency and trapezoid weight; cheap), then
+	// all threads evaluate the propagator factors (three self-energy interpolations each) in parallel.
+	__global__ void __launch_bounds__(128) nodeTableKernel(Problem P, NodeTable N, const double *__restrict__ v2, const double *__restrict__ v2flow, const double *cutoffPtr)
 	{
 		extern __shared__ double smem[];
-		double *mesh = smem, *sv2 = smem + P.nw, *sflow = smem + 2 * P.nw;
-		for (int i = threadIdx.x; i < P.nw; i += blockDim.x) { mesh[i] = P.mesh[i]; sv2[i] = v2[i]; sflow[i] = v2flow[i]; }
-		__syncthreads();
-		const int xi = blockIdx.x * blockDim.x + threadIdx.x;
-		if (xi >= P.nw) return;
 		const int nw = P.nw;
+		double *mesh = smem, *sv2 = smem + nw, *sflow = smem + 2 * nw;
+		double *nodeW = smem + 3 * nw, *nodeT = nodeW + N.stride; // integration frequency, trapezoid weight (negative: conventional term)
+		__shared__ int count;
+		for (int i = threadIdx.x; i < nw; i += blockDim.x) { mesh[i] = P.mesh[i]; sv2[i] = v2[i]; sflow[i] = v2flow[i]; }
+		__syncthreads();
+		const int xi = blockIdx.x;
 		const double cutoff = *cutoffPtr, x = mesh[xi];
-		double *wp = N.wp + (size_t)xi * N.stride, *wt = N.wt + (size_t)xi * N.stride;
-		int n = 0;
-		auto G = [&](double w) { return w + selfEnergy(mesh, nw, sv2, w); };
-		auto bubble = [&](double w1, double w2) { return 1.0 / (G(w1) * G(w2)); };
-		auto katanin = [&](double w1, double w2) { double d = G(w1); return selfEnergy(mesh, nw, sflow, w1) / (d * d * G(w2)); };
-		auto emitK = [&](double w, double weight) { wp[n] = w; wt[n] = weight * katanin(w, x + w); ++n; };
 		auto MV = [&](int i) { return meshValue(mesh, i); };
-
-		wp[n] = cutoff; wt[n] = bubble(cutoff, cutoff + x); ++n;
-		if (x > 2.0 * cutoff) { wp[n] = -cutoff; wt[n] = bubble(cutoff, cutoff - x); ++n; }
-
-		// [-w_max, -(x+L)]  integrateWithObscureRightBoundary, Integrator.hpp:188-225
-		if (-(x + cutoff) > -mesh[nw - 1])
+		if (threadIdx.x == 0)
 		{
-			const double max = -(x + cutoff);
-			int umin = -nw;
-			const int umax = meshLesser(mesh, nw, max);
-			if (umin != umax)
+			int n = 0;
+			auto emitK = [&](double w, double weight) { nodeW[n] = w; nodeT[n] = weight; ++n; };
+			// conventional single-scale terms carry no quadrature weight; they are marked by NaN in nodeT
+			nodeW[n] = cutoff; nodeT[n] = __longlong_as_double(0x7ff8000000000000ll); ++n;
+			if (x > 2.0 * cutoff) { nodeW[n] = -cutoff; nodeT[n] = __longlong_as_double(0x7ff8000000000000ll); ++n; }
+
+			// [-w_max, -(x+L)]  integrateWithObscureRightBoundary, Integrator.hpp:188-225
+			if (-(x + cutoff) > -mesh[nw - 1])
 			{
-				emitK(MV(umin), 0.5 * (MV(umin + 1) - MV(umin)));
-				while (++umin != umax) emitK(MV(umin), 0.5 * (MV(umin + 1) - MV(umin - 1)));
-				emitK(MV(umin), 0.5 * (max - MV(umin - 1)));
-				emitK(max, 0.5 * (max - MV(umin)));
-			}
-			else
-			{
-				emitK(max, 0.5 * (max - MV(umin)));
-				emitK(MV(umin), 0.5 * (max - MV(umin)));
-			}
-		}
-		// [L-x, -L]  integrateWithObscureBoundaries, Integrator.hpp:239-287
-		if (x - cutoff > cutoff)
-		{
-			const double min = cutoff - x, max = -cutoff;
-			int umin = meshGreater(mesh, nw, min);
-			const int umax = meshLesser(mesh, nw, max);
-			if (umax >= umin)
-			{
-				emitK(min, 0.5 * (MV(umin) - min));
-				if (umax != umin)
+				const double max = -(x + cutoff);
+				int umin = -nw;
+				const int umax = meshLesser(mesh, nw, max);
+				if (umin != umax)
 				{
-					emitK(MV(umin), 0.5 * (MV(umin + 1) - min));
+					emitK(MV(umin), 0.5 * (MV(umin + 1) - MV(umin)));
 					while (++umin != umax) emitK(MV(umin), 0.5 * (MV(umin + 1) - MV(umin - 1)));
 					emitK(MV(umin), 0.5 * (max - MV(umin - 1)));
+					emitK(max, 0.5 * (max - MV(umin)));
 				}
-				else emitK(MV(umin), 0.5 * (max - min));
-				emitK(max, 0.5 * (max - MV(umin)));
+				else
+				{
+					emitK(max, 0.5 * (max - MV(umin)));
+					emitK(MV(umin), 0.5 * (max - MV(umin)));
+				}
 			}
-			else
+			// [L-x, -L]  integrateWithObscureBoundaries, Integrator.hpp:239-287
+			if (x - cutoff > cutoff)
 			{
-				emitK(max, 0.5 * (max - min));
-				emitK(min, 0.5 * (max - min));
+				const double min = cutoff - x, max = -cutoff;
+				int umin = meshGreater(mesh, nw, min);
+				const int umax = meshLesser(mesh, nw, max);
+				if (umax >= umin)
+				{
+					emitK(min, 0.5 * (MV(umin) - min));
+					if (umax != umin)
+					{
+						emitK(MV(umin), 0.5 * (MV(umin + 1) - min));
+						while (++umin != umax) emitK(MV(umin), 0.5 * (MV(umin + 1) - MV(umin - 1)));
+						emitK(MV(umin), 0.5 * (max - MV(umin - 1)));
+					}
+					else emitK(MV(umin), 0.5 * (max - min));
+					emitK(max, 0.5 * (max - MV(umin)));
+				}
+				else
+				{
+					emitK(max, 0.5 * (max - min));
+					emitK(min, 0.5 * (max - min));
+				}
 			}
+			// [L, w_max]  integrateWithObscureLeftBoundary, Integrator.hpp:138-174
+			if (cutoff < mesh[nw - 1])
+			{
+				const double min = cutoff;
+				const int max = nw - 1;
+				int umin = meshGreater(mesh, nw, min);
+				if (umin != max)
+				{
+					emitK(min, 0.5 * (MV(umin) - min));
+					emitK(MV(umin), 0.5 * (MV(umin + 1) - min));
+					while (++umin != max) emitK(MV(umin), 0.5 * (MV(umin + 1) - MV(umin - 1)));
+					emitK(MV(umin), 0.5 * (MV(umin) - MV(umin - 1)));
+				}
+				else
+				{
+					emitK(min, 0.5 * (MV(umin) - min));
+					emitK(MV(umin), 0.5 * (MV(umin) - min));
+				}
+			}
+			count = n;
+			N.count[xi] = n;
 		}
-		// [L, w_max]  integrateWithObscureLeftBoundary, Integrator.hpp:138-174
-		if (cutoff < mesh[nw - 1])
+		__syncthreads();
+		auto G = [&](double w) { return w + selfEnergy(mesh, nw, sv2, w); };
+		double *wp = N.wp + (size_t)xi * N.stride, *wt = N.wt + (size_t)xi * N.stride;
+		for (int k = threadIdx.x; k < count; k += blockDim.x)
 		{
-			const double min = cutoff;
-			const int max = nw - 1;
-			int umin = meshGreater(mesh, nw, min);
-			if (umin != max)
+			const double w = nodeW[k], weight = nodeT[k];
+			wp[k] = w;
+			if (weight != weight)
 			{
-				emitK(min, 0.5 * (MV(umin) - min));
-				emitK(MV(umin), 0.5 * (MV(umin + 1) - min));
-				while (++umin != max) emitK(MV(umin), 0.5 * (MV(umin + 1) - MV(umin - 1)));
-				emitK(MV(umin), 0.5 * (MV(umin) - MV(umin - 1)));
+				// conventional terms P(L, L+x) and P(L, L-x), SU2FrgCore.cpp:351-371
+				wt[k] = 1.0 / (G(cutoff) * G(w > 0 ? cutoff + x : cutoff - x));
 			}
 			else
 			{
-				emitK(min, 0.5 * (MV(umin) - min));
-				emitK(MV(umin), 0.5 * (MV(umin) - min));
+				// Katanin term: trapezoid weight * Sdot(w) / (G(w)^2 G(x + w)), SU2FrgCore.cpp:343-347
+				const double d = G(w);
+				wt[k] = weight * (selfEnergy(mesh, nw, sflow, w) / (d * d * G(x + w)));
 			}
 		}
-		N.count[xi] = n;
 	}
 
 	// ================================================================================================================

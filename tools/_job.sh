@@ -1,2 +1,7 @@
-bash tools/gpu_sweep.sh r1p cubic_r7_su2_nw64 "X=1" "PFFRG_THREADS=128 PFFRG_JIT_NBT=32 PFFRG_JIT_NB=16 PFFRG_JIT_MINBLOCKS=4" "PFFRG_THREADS=128 PFFRG_JIT_NBT=32 PFFRG_JIT_NB=32 PFFRG_JIT_MINBLOCKS=3" "PFFRG_THREADS=192 PFFRG_JIT_NBT=32 PFFRG_JIT_NB=32 PFFRG_JIT_MINBLOCKS=3" "PFFRG_THREADS=128 PFFRG_JIT_NBT=64 PFFRG_JIT_NB=32 PFFRG_JIT_MINBLOCKS=2" "PFFRG_THREADS=384 PFFRG_JIT_MINBLOCKS=1 PFFRG_JIT_NBT=128"
-bash tools/gpu_sweep.sh r1p honeycomb_kitaev_r7_xyz_nw64 "X=1" "PFFRG_THREADS=128 PFFRG_JIT_NBT=32 PFFRG_JIT_NB=16 PFFRG_JIT_MINBLOCKS=4" "PFFRG_THREADS=128 PFFRG_JIT_NBT=64 PFFRG_JIT_NB=16 PFFRG_JIT_MINBLOCKS=2"
+python -m pytest tests -m gpu -q > gpurun_out/r1r_pytest_gpu.log 2>&1; tail -4 gpurun_out/r1r_pytest_gpu.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r1r_bench_cubic.json 2> gpurun_out/r1r_bench_cubic.err
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/r1r_bench_cubic.json").read().strip().splitlines()[-1])
+print("cubic value", round(d["value"],3), "ms/step", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["value"],2), d["breakdown_ms"])
+PY
