@@ -142,6 +142,13 @@ int pffrg_compute_step(pffrg_handle h, int *diverged);
 /* FrgCore::finalizeStep (src/SU2/SU2FrgCore.cpp:111-137): state += (new_cutoff - cutoff) * flow, cutoff = new_cutoff,
  * then the updated vertex is exchanged between ranks (ncclBroadcast group == the reference's MPI_Bcast). */
 int pffrg_finalize_step(pffrg_handle h, double new_cutoff);
+/* Static spin-spin correlations chi_c[rid] of the CURRENT state, computed on the device: replaces the work item of
+ * {SU2,XYZ,TRI}MeasurementCorrelation::_calculateCorrelation (src/SU2/SU2MeasurementCorrelation.cpp:77-160; XYZ :98-205, TRI
+ * :147-296), which the reference runs single-threaded once per cutoff step. `chi` receives channels x representatives doubles,
+ * channel-major ("ValueSuperbundle" order: SU2 {spin, density}, XYZ {x, y, z, density}, TRI 4*mu+nu); the caller maps
+ * representatives to lattice sites with Lattice::symmetryTransform exactly as src/SU2/SU2MeasurementCorrelation.cpp:161-176 does. */
+int pffrg_num_channels(pffrg_handle h);          /* 2 (SU2) / 4 (XYZ) / 16 (TRI) */
+int pffrg_measure_correlation(pffrg_handle h, double *chi /* [pffrg_num_channels * n_sites] */);
 /* block until all device work of this handle has finished */
 int pffrg_synchronize(pffrg_handle h);
 

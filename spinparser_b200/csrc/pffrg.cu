@@ -7,6 +7,7 @@
 // stream; replaces the MPI_Bcast of src/lib/LoadManager.hpp:240 issued from src/SU2/SU2FrgCore.cpp:136).
 #include "pffrg.h"
 #include "pffrg_kernels.cuh"
+#include "pffrg_measure.cuh"
 #include "pffrg_jit.hpp"
 
 #include <nccl.h>
@@ -129,6 +130,7 @@ struct pffrg_context
 	DeviceArray<int> dCount; DeviceArray<double> dNodeW, dNodeWt;
 	DeviceArray<int> dNan;
 	DeviceArray<double> dStaging; // one reference-layout array, reused by set_state / get_state / get_flow
+	DeviceArray<double> dChiPartial, dChi; DeviceArray<int> dChiCount; // correlation measurement (allocated on first use)
 	int *hNan = nullptr;
 	int nodeStride = 0;
 
@@ -741,6 +743,7 @@ int pffrg_destroy(pffrg_handle h)
 	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release(); h->dMeshStart.release();
 	if (h->jitLibrary) cudaLibraryUnload(h->jitLibrary); h->dV4.release(); h->dFlow4.release(); h->dV2.release(); h->dFlow2.release(); h->dCutoff.release();
 	h->dCount.release(); h->dNodeW.release(); h->dNodeWt.release(); h->dNan.release(); h->dStaging.release();
+	h->dChiPartial.release(); h->dChi.release(); h->dChiCount.release();
 	if (h->hNan) cudaFreeHost(h->hNan);
 	for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
 	if (h->stream) cudaStreamDestroy(h->stream);
@@ -907,6 +910,34 @@ int pffrg_finalize_step(pffrg_handle h, double newCutoff)
 	return PFFRG_OK;
 }
 
+int pffrg_num_channels(pffrg_handle h) { return h ? h->C : fail(PFFRG_ERR_ARGUMENT, "null handle"); }
+
+int pffrg_measure_correlation(pffrg_handle h, double *chi)
+{
+	if (!h || !chi) return fail(PFFRG_ERR_ARGUMENT, "null argument");
+	if (!h->haveState) return fail(PFFRG_ERR_STATE, "measure_correlation before set_state");
+	CUDA_TRY(cudaSetDevice(h->device));
+	const int entries = h->C * h->L;
+	if (!h->dChi.p)
+	{
+		CUDA_TRY(h->dChiPartial.alloc((size_t)h->nodeStride * entries));
+		CUDA_TRY(h->dChi.alloc(entries));
+		CUDA_TRY(h->dChiCount.alloc(1));
+	}
+	const Problem P = h->problem();
+	const int groups = std::max(1, 256 / h->L);
+	const size_t smem = sizeof(double) * ((size_t)2 * h->nw + 2 * h->nodeStride + (size_t)groups * entries);
+	if (h->core == SU2) { CUDA_TRY(cudaFuncSetAttribute(correlationKernel<SU2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); correlationKernel<SU2><<<h->nodeStride, 256, smem, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->nodeStride, h->dChiPartial.p, h->dChiCount.p); }
+	else if (h->core == XYZ) { CUDA_TRY(cudaFuncSetAttribute(correlationKernel<XYZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); correlationKernel<XYZ><<<h->nodeStride, 256, smem, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->nodeStride, h->dChiPartial.p, h->dChiCount.p); }
+	else { CUDA_TRY(cudaFuncSetAttribute(correlationKernel<TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); correlationKernel<TRI><<<h->nodeStride, 256, smem, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->nodeStride, h->dChiPartial.p, h->dChiCount.p); }
+	CUDA_TRY(cudaGetLastError());
+	correlationSumKernel<<<(entries + 127) / 128, 128, 0, h->stream>>>(h->dChiPartial.p, h->dChiCount.p, entries, h->dChi.p);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpyAsync(chi, h->dChi.p, sizeof(double) * entries, cudaMemcpyDeviceToHost, h->stream));
+	CUDA_TRY(cudaStreamSynchronize(h->stream));
+	return PFFRG_OK;
+}
+
 int pffrg_synchronize(pffrg_handle h)
 {
 	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");
@@ -959,7 +990,7 @@ int pffrg_plan_partition(int core, int nFrequencies, const double *frequencies, 
 int pffrg_tri_terms(int region, int32_t *terms, int capacity)
 {
 	// region 0: pp ladder, 1: ph ladder, 2: chalice, 3: inverse chalice (rows {out, sign, first, second}), 4: RPA (rows {out, sign, mu*4+k, k*4+nu})
-	if (region < 0 || region > 4 || (!terms && capacity > 0)) return fail(PFFRG_ERR_ARGUMENT, "bad region or null buffer");
+	if (region < 0 || region > 5 || (!terms && capacity > 0)) return fail(PFFRG_ERR_ARGUMENT, "bad region or null buffer");
 	int n = 0;
 	auto emit = [&](const tri::Term &t, int first, int second)
 	{
@@ -969,7 +1000,22 @@ int pffrg_tri_terms(int region, int32_t *terms, int capacity)
 		return true;
 	};
 	bool consistent = true;
-	if (region == 4)
+	if (region == 5)
+	{
+		// egg diagram of the correlation measurement: rows {out channel, 4 * coefficient, a, b}
+		for (int c = 0; c < 16; ++c)
+			for (int ab = 0; ab < 16; ++ab)
+			{
+				const int mu = c >> 2, nu = c & 3;
+				if ((mu == 3) != (nu == 3)) continue;
+				const tri::Term t = tri::egg(mu, nu, ab >> 2, ab & 3);
+				if (t.sign == 0.0) continue;
+				if (t.exponent & 1) { consistent = false; continue; }
+				if (n < capacity) { terms[4 * n] = c; terms[4 * n + 1] = (int)(4.0 * t.sign); terms[4 * n + 2] = ab >> 2; terms[4 * n + 3] = ab & 3; }
+				++n;
+			}
+	}
+	else if (region == 4)
 	{
 		for (int mu = 0; mu < 4; ++mu) for (int k = 0; k < 4; ++k) for (int nu = 0; nu < 4; ++nu) consistent &= emit(tri::rpa(mu, k, nu), 4 * mu + k, 4 * k + nu);
 	}

@@ -272,6 +272,14 @@ class FrgCore:
         """``FrgCore::finalizeStep`` (src/SU2/SU2FrgCore.cpp:111-137)."""
         check(lib.pffrg_finalize_step(self._h, float(newCutoff)))
 
+    def measureCorrelation(self) -> np.ndarray:
+        """Static correlations ``chi[c, rid]`` of the current state, computed on the device (replaces the work item of
+        ``SU2MeasurementCorrelation::_calculateCorrelation``, src/SU2/SU2MeasurementCorrelation.cpp:77-160, and the XYZ/TRI
+        equivalents). Use :func:`correlation_datasets` to arrange them like the reference's ``.obs`` datasets."""
+        chi = np.zeros((N_CHANNELS[self.identifier], self.tables.n_sites), dtype=np.float64)
+        check(lib.pffrg_measure_correlation(self._h, chi.ctypes.data_as(C.POINTER(C.c_double))))
+        return chi
+
     def synchronize(self) -> None:
         check(lib.pffrg_synchronize(self._h))
 
@@ -291,6 +299,25 @@ class FrgCoreFactory:
     @staticmethod
     def newFrgCore(identifier: str, tables: ProblemTables, options: Optional[Mapping[str, str]] = None, device: int = 0) -> FrgCore:
         return FrgCore(identifier, tables, options, device)
+
+
+def correlation_datasets(identifier: str, chi: np.ndarray, range_rid: Sequence[np.ndarray], range_perm: Sequence[np.ndarray]) -> Dict[str, np.ndarray]:
+    """Arrange ``chi[c, rid]`` like the datasets the reference writes (row b = basis site b, column k = k-th site in range of b):
+    ``range_rid[b][k]``, ``range_perm[b][k]`` = ``Lattice::symmetryTransform(b, j_k, x, y, z)`` and the transformed spin components
+    (src/SU2/SU2MeasurementCorrelation.cpp:161-176, src/XYZ/XYZMeasurementCorrelation.cpp:206-225, src/TRI/TRIMeasurementCorrelation.cpp:297-330)."""
+    rid = np.stack([np.asarray(r) for r in range_rid])
+    perm = np.stack([np.asarray(p).reshape(-1, 3) for p in range_perm])
+    if identifier == "SU2":
+        return {"SU2CorZZ": chi[0][rid], "SU2CorDD": chi[1][rid]}
+    if identifier == "XYZ":
+        out = {f"XYZCor{n}{n}": chi[perm[..., k], rid] for k, n in enumerate("XYZ")}
+        out["XYZCorDD"] = chi[3][rid]
+        return out
+    out = {"TRICorDD": chi[15][rid]}
+    for a, na in enumerate("XYZ"):
+        for b, nb in enumerate("XYZ"):
+            out[f"TRICor{na}{nb}"] = chi[4 * perm[..., a] + perm[..., b], rid]
+    return out
 
 
 def plan_partition(identifier: str, tables: ProblemTables, cutoff: float, n_ranks: int) -> List[int]:

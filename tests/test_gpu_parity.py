@@ -70,3 +70,33 @@ def test_float32_host_arrays_round_trip(case):
     for c in range(n):
         assert np.array_equal(back.v4[c], v4[c])
     core.close()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_device_correlation_measurement_matches_reference(case):
+    """K5: chi(Lambda) computed on the device against the datasets the unmodified reference wrote for the same state
+    (tests/golden/*.f64.pfd, `h5/obs/<Core>Cor<mu nu>/data/measurement_<step>/data`). North-star tolerance 1e-8 relative with an
+    absolute floor of 1e-10 of the largest correlation (off-site values of symmetry-forbidden components are round-off)."""
+    from spinparser_b200.frgcore import correlation_datasets
+    d = golden(case)
+    name, core = _core(d)
+    n = core.n_arrays
+    n_basis = int(d["lattice/nBasis"])
+    rid = [d[f"lattice/range{b}_fwd_rid"] for b in range(n_basis)]
+    perm = [d[f"lattice/range{b}_fwd_perm"] for b in range(n_basis)]
+    checked = 0
+    for step in dumped_steps(d):
+        pre = f"step{step}/"
+        state = [np.ascontiguousarray(d[pre + f"state/v4_{c}"]) for c in range(n)]
+        core.setState(float(d[pre + "state/cutoff"]), np.ascontiguousarray(d[pre + "state/v2"]), state)
+        got = correlation_datasets(name, core.measureCorrelation(), rid, perm)
+        scale = max(np.abs(d[f"h5/obs/{key}/data/measurement_{step}/data"]).max() for key in got)
+        for key, values in got.items():
+            want = d[f"h5/obs/{key}/data/measurement_{step}/data"]
+            assert values.shape == want.shape, key
+            assert float(d[f"h5/obs/{key}/data/measurement_{step}@cutoff"][0]) == float(d[pre + "state/cutoff"])
+            err = np.abs(values - want)
+            assert (err <= 1e-8 * np.abs(want) + 1e-10 * scale).all(), f"{case} step {step} {key}: max deviation {err.max():.3e} (scale {scale:.3e})"
+            checked += 1
+    assert checked >= 4
+    core.close()

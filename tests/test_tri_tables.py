@@ -72,3 +72,44 @@ def test_tri_tables_match_reference_term_by_term():
     ours = _ours()
     for name in ref:
         assert ours[name] == ref[name], name
+
+
+# ---- egg diagram of the TRI correlation measurement (csrc/pffrg_measure.cuh, tri::egg) against
+# src/TRI/TRIMeasurementCorrelation.cpp:204-243: rows {output channel, 4 * coefficient, a, b}
+EGG_REFERENCE_FILE = "/root/reference/src/TRI/TRIMeasurementCorrelation.cpp"
+EGG_DIGEST = "c4af60e6ceb48742afa72324a32dee8cf6da9a5957d0097e38cc363db192c372"
+
+
+def _egg_ours():
+    from spinparser_b200 import _capi
+    n = _capi.lib.pffrg_tri_terms(5, None, 0)
+    buf = np.zeros((n, 4), dtype=np.int32)
+    assert _capi.lib.pffrg_tri_terms(5, buf.ctypes.data_as(C.POINTER(C.c_int32)), n) == n
+    return sorted(tuple(int(x) for x in row) for row in buf)
+
+
+def _egg_from_reference():
+    import re
+    idx = {"x": 0, "y": 1, "z": 2, "d": 3}
+    rows = []
+    for m in re.finditer(r"ret\.bundle\((\d+)\)\[0\] ([+-])= ([0-9.]+)f \* v(\w)(\w);", open(EGG_REFERENCE_FILE).read()):
+        sign = 1 if m.group(2) == "+" else -1
+        rows.append((int(m.group(1)), int(round(4 * sign * float(m.group(3)))), idx[m.group(4)], idx[m.group(5)]))
+    return sorted(rows)
+
+
+def _rows_digest(rows):
+    return hashlib.sha256(np.asarray(rows, dtype=np.int32).tobytes()).hexdigest()
+
+
+def test_tri_egg_table_matches_committed_digest():
+    rows = _egg_ours()
+    assert len(rows) == 40
+    assert _rows_digest(rows) == EGG_DIGEST
+
+
+@pytest.mark.skipif(not os.path.exists(EGG_REFERENCE_FILE), reason="reference tree not present (GPU box)")
+def test_tri_egg_table_matches_reference_term_by_term():
+    ref = _egg_from_reference()
+    assert len(ref) == 40 and _rows_digest(ref) == EGG_DIGEST, "committed digest is stale"
+    assert _egg_ours() == ref
