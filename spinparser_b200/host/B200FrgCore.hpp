@@ -155,17 +155,24 @@ namespace b200
 		int device = 0;
 		bool syncState = true;  // copy the updated state into the reference's host arrays after every finalizeStep
 		bool syncFlow = false;  // copy the full vertex flow into _flow after every computeStep
+		bool deviceMeasurement = true; // correlation measurements on the GPU (B200MeasurementCorrelation) instead of the reference's host code
 		static AdapterOptions extract(std::map<std::string, std::string> &options)
 		{
 			AdapterOptions a;
 			if (const char *e = getenv("SPINPARSER_B200_DEVICE")) a.device = atoi(e);
 			if (const char *e = getenv("SPINPARSER_B200_SYNC_STATE")) a.syncState = atoi(e) != 0;
 			if (const char *e = getenv("SPINPARSER_B200_SYNC_FLOW")) a.syncFlow = atoi(e) != 0;
+			if (const char *e = getenv("SPINPARSER_B200_MEASUREMENT")) a.deviceMeasurement = std::string(e) != "host";
 			auto take = [&](const char *key, std::string &out) { auto it = options.find(key); if (it == options.end()) return false; out = it->second; options.erase(it); return true; };
 			std::string v;
 			if (take("device", v)) a.device = std::stoi(v);
 			if (take("syncState", v)) a.syncState = (v == "true" || v == "1");
 			if (take("syncFlow", v)) a.syncFlow = (v == "true" || v == "1");
+			if (take("measurement", v))
+			{
+				if (v != "host" && v != "device") throw Exception(Exception::Type::InitializationError, "Unknown measurement backend '" + v + "'.");
+				a.deviceMeasurement = v == "device";
+			}
 			take("backend", v);
 			return a;
 		}
@@ -245,6 +252,16 @@ namespace b200
 			void *v4[4] = { _state.v4[0], _state.v4[1], _state.v4[2], _state.v4[3] };
 			double cutoff = 0.0;
 			check(pffrg_get_state(_handle, &cutoff, _state.v2, v4, dtype()), "pffrg_get_state");
+		}
+
+		// correlations chi[c * L + rid] of `state` (the flowing functional), computed on the device; uploads the state first when
+		// the host copy is the newer one (post-processing of deferred measurements reads checkpoints into the host arrays)
+		void measureCorrelation(const EffectiveAction &state, std::vector<double> &chi)
+		{
+			if (&state != this->_flowingFunctional) throw Exception(Exception::Type::ArgumentError, "B200FrgCore::measureCorrelation: only the flowing functional can be measured");
+			if (!_deviceCurrent || !((double)state.cutoff == _deviceCutoff)) uploadState();
+			chi.assign(size_t(pffrg_num_channels(_handle)) * FrgCommon::lattice().size, 0.0);
+			check(pffrg_measure_correlation(_handle, chi.data()), "pffrg_measure_correlation");
 		}
 
 		// tell the core that the host arrays were modified without changing the cutoff

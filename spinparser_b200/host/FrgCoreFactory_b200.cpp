@@ -13,6 +13,7 @@
 #include "XYZ/XYZMeasurementCorrelation.hpp"
 #include "TRI/TRIMeasurementCorrelation.hpp"
 #include "B200FrgCore.hpp"
+#include "B200MeasurementCorrelation.hpp"
 
 FrgCore *FrgCoreFactory::newFrgCore(const std::string &identifier, const SpinModel &model, const std::vector<MeasurementSpecification> &measurements, const std::map<std::string, std::string> &options)
 {
@@ -22,23 +23,32 @@ FrgCore *FrgCoreFactory::newFrgCore(const std::string &identifier, const SpinMod
 		throw Exception(Exception::Type::ArgumentError, "Spin model identifier '" + identifier + "' does not exist.");
 	}
 
-	std::vector<Measurement *> measurementObjects;
-	for (const MeasurementSpecification &specification : measurements)
-	{
-		if (specification.identifier != "correlation") throw Exception(Exception::Type::InitializationError, "Measurement: Unknown measurement type '" + identifier + "'.");
-		Measurement *m = nullptr;
-		if (identifier == "SU2") m = new SU2MeasurementCorrelation(specification.output, specification.minCutoff, specification.maxCutoff, specification.defer);
-		else if (identifier == "XYZ") m = new XYZMeasurementCorrelation(specification.output, specification.minCutoff, specification.maxCutoff, specification.defer);
-		else m = new TRIMeasurementCorrelation(specification.output, specification.minCutoff, specification.maxCutoff, specification.defer);
-		Log::log << Log::LogLevel::Info << "Added measurement [correlation]." << Log::endl;
-		measurementObjects.push_back(m);
-	}
-
 	std::string backend = "cpu";
 	if (const char *env = getenv("SPINPARSER_BACKEND")) backend = env;
 	auto chosen = options.find("backend");
 	if (chosen != options.end()) backend = chosen->second;
 	if (backend != "cpu" && backend != "b200") throw Exception(Exception::Type::InitializationError, "Unknown FRG core backend '" + backend + "'.");
+	std::map<std::string, std::string> probe = options;
+	const bool deviceMeasurement = backend == "b200" && b200::AdapterOptions::extract(probe).deviceMeasurement;
+
+	std::vector<Measurement *> measurementObjects;
+	for (const MeasurementSpecification &specification : measurements)
+	{
+		if (specification.identifier != "correlation") throw Exception(Exception::Type::InitializationError, "Measurement: Unknown measurement type '" + identifier + "'.");
+		Measurement *m = nullptr;
+		if (deviceMeasurement)
+		{
+			// the susceptibility integral runs on the GPU; same .obs output
+			if (identifier == "SU2") m = new b200::B200MeasurementCorrelation<SU2FrgCore>(specification.output, specification.minCutoff, specification.maxCutoff, specification.defer);
+			else if (identifier == "XYZ") m = new b200::B200MeasurementCorrelation<XYZFrgCore>(specification.output, specification.minCutoff, specification.maxCutoff, specification.defer);
+			else m = new b200::B200MeasurementCorrelation<TRIFrgCore>(specification.output, specification.minCutoff, specification.maxCutoff, specification.defer);
+		}
+		else if (identifier == "SU2") m = new SU2MeasurementCorrelation(specification.output, specification.minCutoff, specification.maxCutoff, specification.defer);
+		else if (identifier == "XYZ") m = new XYZMeasurementCorrelation(specification.output, specification.minCutoff, specification.maxCutoff, specification.defer);
+		else m = new TRIMeasurementCorrelation(specification.output, specification.minCutoff, specification.maxCutoff, specification.defer);
+		Log::log << Log::LogLevel::Info << "Added measurement [correlation]." << Log::endl;
+		measurementObjects.push_back(m);
+	}
 
 	if (backend == "b200")
 	{

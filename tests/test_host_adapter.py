@@ -21,12 +21,12 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 CASES = ["e2e_su2_square_r3_nw10", "e2e_xyz_honeycomb_kitaev_r3_nw10", "e2e_tri_kagome_dm_r3_nw6"]
 
 
-def _run(binary, case, backend, tmp_path, extra=()):
+def _run(binary, case, backend, tmp_path, extra=(), measurement="device"):
     from spinparser_b200.pfd import read_pfd
     exe = os.path.join(REF, binary)
     assert os.path.exists(exe), f"{exe} is missing: run __graft_entry__.build() where /root/reference is mounted"
     out = str(tmp_path / f"{case}.{backend}.pfd")
-    env = dict(os.environ, SPINPARSER_BACKEND=backend)
+    env = dict(os.environ, SPINPARSER_BACKEND=backend, SPINPARSER_B200_MEASUREMENT=measurement)
     cmd = [exe, "-r", os.path.join(ROOT, "oracle", "res"), os.path.join(GOLDEN, "tasks", case + ".xml"), "--out", out, "--no-lattice", *extra]
     proc = subprocess.run(cmd, env=env, cwd=str(tmp_path), capture_output=True, text=True)
     return proc, (read_pfd(out) if proc.returncode == 0 else None)
@@ -53,9 +53,12 @@ def _compare(got, want, rel, floor_rel, floor_abs=0.0):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("measurement", ["device", "host"])
 @pytest.mark.parametrize("case", CASES)
-def test_reference_driver_with_gpu_cores_fp64(case, tmp_path):
-    proc, got = _run("spinparser64_b200", case, "b200", tmp_path)
+def test_reference_driver_with_gpu_cores_fp64(case, measurement, tmp_path):
+    """measurement = device: B200MeasurementCorrelation (susceptibility integral on the GPU, own .obs writer);
+    host: the reference's own measurement classes reading the downloaded state."""
+    proc, got = _run("spinparser64_b200", case, "b200", tmp_path, measurement=measurement)
     assert proc.returncode == 0, proc.stderr[-2000:]
     want = golden(case)
     worst = _compare(got, want, rel=1e-8, floor_rel=1e-10)
