@@ -99,7 +99,7 @@ def profiled_traffic(workload):
         return None
     with open(path) as f:
         rec = json.load(f).get(workload)
-    return rec.get("dram_bytes_per_launch") if rec else None
+    return rec.get("dram_bytes_per_launch") if rec and not rec.get("captured_items") else None
 
 
 def load_tables(workload):
@@ -318,6 +318,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
+        from spinparser_b200._capi import lib as _lib
+        fp64_peak = float(_lib.pffrg_fp64_peak(local))  # measured here: 16-chain DFMA loop on every SM
         achieved = alg_bytes / world / (kernel_ms_avg * 1e-3) / 1e9  # per GPU: this rank's share over its kernel time
         line = {
             "metric": "pf-FRG cutoff steps/s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -336,7 +338,8 @@ def main():
             "launch_shape": {k: records[0][2][k] for k in ("jit_rpa", "threads", "smem_bytes", "node_batch", "rpa_batch", "rpa_warps", "min_blocks", "jit_compile_ms")},
             "roofline": {"bound": "hbm", "kernel": "pffrg::v4FlowKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.workload),
                          "peak_source": peak_src, "note": "achieved = algorithmic gather+output bytes (SURVEY 8d: 128*L*C per kernel evaluation + 24*L*C per item) / kernel time, per GPU; gathers that hit in L2 do not reach DRAM, so `traffic` (ncu dram bytes per launch) is far below the algorithmic bytes and frac can exceed 1",
-                         "fp64_tflops_achieved": alg_flops / world / (kernel_ms_avg * 1e-3) / 1e12},
+                         "fp64_tflops_achieved": alg_flops / world / (kernel_ms_avg * 1e-3) / 1e12,
+                         "fp64_tflops_peak_measured": fp64_peak, "fp64_frac": alg_flops / world / (kernel_ms_avg * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
                     "what": "setState(pinned host arrays) + computeStep + finalizeStep + flowingFunctional(download) per step, wall clock, max over ranks"},
             "gpu_launches": 6 * args.steps,

@@ -171,6 +171,10 @@ int pffrg_jit_compile_check(const pffrg_desc *desc, int64_t *cubin_bytes);
  * terms per buffer pair (256, or 64 for the RPA). Used by the parity tests to compare against the reference term by term. */
 int pffrg_tri_terms(int region, int32_t *terms, int capacity);
 
+/* measured FP64 multiply-add peak of a device in TFLOP/s (a 16-chain DFMA loop on every SM; ~10 ms): the denominator of the
+ * FP64 roofline bench.py reports next to the HBM one. Returns a negative value on failure. */
+double pffrg_fp64_peak(int device);
+
 /* page-locked host memory for the arrays passed to set_state / get_state / get_flow (plain memory works too, but
  * transfers from pinned buffers run at full PCIe speed). Returns NULL on failure. */
 void *pffrg_host_alloc(size_t bytes);

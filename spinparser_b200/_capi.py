@@ -23,7 +23,7 @@ SYMBOLS = [
     "pffrg_num_vertex_arrays", "pffrg_vertex_array_length", "pffrg_num_items", "pffrg_comm_unique_id",
     "pffrg_comm_init", "pffrg_item_range", "pffrg_set_state", "pffrg_get_state", "pffrg_get_flow",
     "pffrg_compute_step", "pffrg_finalize_step", "pffrg_synchronize", "pffrg_num_channels", "pffrg_measure_correlation", "pffrg_set_item_range", "pffrg_get_stats",
-    "pffrg_stream", "pffrg_host_alloc", "pffrg_host_free", "pffrg_host_register", "pffrg_host_unregister", "pffrg_jit_compile_check", "pffrg_tri_terms", "pffrg_plan_partition",
+    "pffrg_stream", "pffrg_fp64_peak", "pffrg_host_alloc", "pffrg_host_free", "pffrg_host_register", "pffrg_host_unregister", "pffrg_jit_compile_check", "pffrg_tri_terms", "pffrg_plan_partition",
 ]
 
 
@@ -94,6 +94,8 @@ def _load() -> C.CDLL:
     lib.pffrg_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.pffrg_stream.argtypes = [vp]
     lib.pffrg_stream.restype = vp
+    lib.pffrg_fp64_peak.argtypes = [C.c_int]
+    lib.pffrg_fp64_peak.restype = C.c_double
     lib.pffrg_host_alloc.argtypes = [C.c_size_t]
     lib.pffrg_host_alloc.restype = vp
     lib.pffrg_host_free.argtypes = [vp]

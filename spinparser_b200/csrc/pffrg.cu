@@ -675,6 +675,7 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	// most a quarter of the lanes (then every warp gathers from one node only: fewer cache lines per load, uniform table reads)
 	const int padded = (L + 31) / 32 * 32;
 	h->stride = (padded - L) * 4 <= padded ? padded : L;
+	if (const char *e = getenv("PFFRG_PAD_GROUPS")) h->stride = atoi(e) ? padded : L; // tuning override
 	int threadTarget = 256; // PFFRG_THREADS: tuning override (values above 256 only work with the run-time compiled kernel)
 	if (const char *e = getenv("PFFRG_THREADS")) threadTarget = std::min(1024, std::max(64, atoi(e)));
 	h->groups = std::max(1, threadTarget / h->stride);
@@ -1029,6 +1030,31 @@ int pffrg_tri_terms(int region, int32_t *terms, int capacity)
 			}
 	if (!consistent) return fail(PFFRG_ERR_STATE, "TRI spin algebra produced an imaginary coefficient");
 	return n;
+}
+
+double pffrg_fp64_peak(int device)
+{
+	if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); fail(PFFRG_ERR_CUDA, "cudaSetDevice(%d) failed", device); return -1.0; }
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+	double *out = nullptr; cudaEvent_t e0, e1;
+	if (cudaMalloc(&out, sizeof(double)) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	const int blocks = prop.multiProcessorCount * 8, iterations = 20000;
+	double best = 0.0;
+	for (int rep = 0; rep < 4; ++rep)
+	{
+		cudaEventRecord(e0);
+		fp64PeakKernel<<<blocks, 256>>>(out, iterations, 1.0000001, 0.9999999);
+		cudaEventRecord(e1);
+		cudaEventSynchronize(e1);
+		float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+		const double tflops = 2.0 * 16.0 * iterations * 256.0 * blocks / (ms * 1e-3) / 1e12;
+		if (rep > 0 && tflops > best) best = tflops;
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+	if (cudaGetLastError() != cudaSuccess) { fail(PFFRG_ERR_CUDA, "FP64 probe failed"); return -1.0; }
+	return best;
 }
 
 void *pffrg_host_alloc(size_t bytes)

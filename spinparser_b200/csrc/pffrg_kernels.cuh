@@ -1211,6 +1211,23 @@ namespace pffrg
 
 	__global__ void setScalarKernel(double *p, double v) { *p = v; }
 
+	// FP64 multiply-add throughput probe (pffrg_fp64_peak): 16 independent chains per thread, nothing but DFMA in the loop
+	__global__ void __launch_bounds__(256) fp64PeakKernel(double *out, int iterations, double a, double b)
+	{
+		double x[16];
+		#pragma unroll
+		for (int i = 0; i < 16; ++i) x[i] = a + i + threadIdx.x;
+		for (int it = 0; it < iterations; ++it)
+		{
+			#pragma unroll
+			for (int i = 0; i < 16; ++i) x[i] = fma(x[i], b, a);
+		}
+		double s = 0.0;
+		#pragma unroll
+		for (int i = 0; i < 16; ++i) s += x[i];
+		if (s == 1.2345) out[0] = s; // never true: keeps the chains alive
+	}
+
 	// reference array (one channel, [row][L], or TRI [row][16][L]) -> device layout; T = float or double
 	template <typename T>
 	__global__ void importKernel(const T *__restrict__ src, double *__restrict__ dst, size_t rows, int L, int Lp, int RL, int cFirst, int cCount)

@@ -1,1 +1,3 @@
-python -m pytest tests/test_host_adapter.py -m gpu -q > gpurun_out/r1t_pytest_gpu.log 2>&1; tail -30 gpurun_out/r1t_pytest_gpu.log | cut -c1-250
+bash tools/gpu_sweep.sh r1u honeycomb_kitaev_r7_xyz_nw64 "X=1" "PFFRG_PAD_GROUPS=1" "PFFRG_PAD_GROUPS=1 PFFRG_THREADS=512 PFFRG_JIT_MINBLOCKS=1"
+bash tools/gpu_sweep.sh r1u kagome_dm_r7_tri_nw64 "PFFRG_PAD_GROUPS=1"
+bash tools/gpu_sweep.sh r1u square_r4_su2_nw32 "X=1" "PFFRG_PAD_GROUPS=1"

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise `ncu --set full` reports of the flow kernel into profiles/ (run here, on the machine without a GPU).
 
-    python tools/ncu_summary.py <workload> <report.ncu-rep> [<round tag>]
+    python tools/ncu_summary.py <workload> <report.ncu-rep> [<round tag> [<captured items>]]
 
 Writes profiles/<tag>_<workload>_flow_kernel.csv (selected raw metrics, one line per captured launch) and updates
 profiles/ncu_summary.json[workload] with the per-launch averages bench.py reports as `roofline.traffic`.
@@ -22,11 +22,12 @@ METRICS = [
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
     "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__block_size", "launch__grid_size",
     "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
 ]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "second": 1.0}
 
 
-def main(workload, report, tag="r1"):
+def main(workload, report, tag="r1", items=0):
     raw = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], check=True, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     header, units, data = rows[0], rows[1], rows[2:]
@@ -57,6 +58,10 @@ def main(workload, report, tag="r1"):
         "issue_active_pct": avg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
         "warps_active_pct": avg("sm__warps_active.avg.pct_of_peak_sustained_active"),
         "registers_per_thread": avg("launch__registers_per_thread"),
+        "l1_lsu_wavefronts_pct": avg("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") if "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed" in col else None,
+        # 0 = the whole step; otherwise the capture was restricted to the first N work items (bench.py --items) and the
+        # per-launch figures are NOT those of a full step
+        "captured_items": int(items),
     }
     with open(summary_path, "w") as f:
         json.dump(summary, f, indent=1, sort_keys=True)
