@@ -132,6 +132,11 @@ int pffrg_plan_partition(int core, int n_frequencies, const double *frequencies,
  * (src/SU2/SU2EffectiveAction.hpp:38-60, src/EffectiveAction.hpp:59). `v4` holds pffrg_num_vertex_arrays pointers. */
 int pffrg_set_state(pffrg_handle h, double cutoff, const void *v2, const void *const *v4, int dtype);
 int pffrg_get_state(pffrg_handle h, double *cutoff, void *v2, void *const *v4, int dtype);
+/* Initial condition built on the device (SU2EffectiveAction(cutoff, spinModel, core), src/SU2/SU2EffectiveAction.hpp:38-60; XYZ
+ * :37-62, TRI :38-63): every frequency entry of channel c at representative r is bare[c * n_sites + r] -- the bare coupling already
+ * divided by the normalization (and multiplied by 1/4 for XYZ/TRI) -- and the self energy is zero. Replaces building and uploading
+ * the full host arrays. */
+int pffrg_set_initial_condition(pffrg_handle h, double cutoff, const double *bare /* [pffrg_num_channels * n_sites] */);
 /* the flow of the last compute_step (FrgCore::flow(), src/FrgCore.hpp:103-106); gathers from all ranks when needed */
 int pffrg_get_flow(pffrg_handle h, void *v2_flow, void *const *v4_flow, int dtype);
 

@@ -21,7 +21,7 @@ UNIQUE_ID_BYTES = 128
 SYMBOLS = [
     "pffrg_abi_version", "pffrg_last_error", "pffrg_device_count", "pffrg_create", "pffrg_destroy",
     "pffrg_num_vertex_arrays", "pffrg_vertex_array_length", "pffrg_num_items", "pffrg_comm_unique_id",
-    "pffrg_comm_init", "pffrg_item_range", "pffrg_set_state", "pffrg_get_state", "pffrg_get_flow",
+    "pffrg_comm_init", "pffrg_item_range", "pffrg_set_state", "pffrg_set_initial_condition", "pffrg_get_state", "pffrg_get_flow",
     "pffrg_compute_step", "pffrg_finalize_step", "pffrg_synchronize", "pffrg_num_channels", "pffrg_measure_correlation", "pffrg_set_item_range", "pffrg_get_stats",
     "pffrg_stream", "pffrg_fp64_peak", "pffrg_host_alloc", "pffrg_host_free", "pffrg_host_register", "pffrg_host_unregister", "pffrg_jit_compile_check", "pffrg_tri_terms", "pffrg_plan_partition",
 ]
@@ -84,6 +84,7 @@ def _load() -> C.CDLL:
     lib.pffrg_item_range.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.pffrg_set_item_range.argtypes = [vp, C.c_int64, C.c_int64]
     lib.pffrg_set_state.argtypes = [vp, C.c_double, vp, C.POINTER(vp), C.c_int]
+    lib.pffrg_set_initial_condition.argtypes = [vp, C.c_double, _dp]
     lib.pffrg_get_state.argtypes = [vp, _dp, vp, C.POINTER(vp), C.c_int]
     lib.pffrg_get_flow.argtypes = [vp, vp, C.POINTER(vp), C.c_int]
     lib.pffrg_compute_step.argtypes = [vp, C.POINTER(C.c_int)]

@@ -814,6 +814,23 @@ int pffrg_set_state(pffrg_handle h, double cutoff, const void *v2, const void *c
 	return PFFRG_OK;
 }
 
+int pffrg_set_initial_condition(pffrg_handle h, double cutoff, const double *bare)
+{
+	if (!h || !bare) return fail(PFFRG_ERR_ARGUMENT, "null argument");
+	CUDA_TRY(cudaSetDevice(h->device));
+	const size_t entries = (size_t)h->C * h->L;
+	if (h->dStaging.n < entries) CUDA_TRY(h->dStaging.alloc(entries));
+	CUDA_TRY(cudaMemcpyAsync(h->dStaging.p, bare, entries * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	initialConditionKernel<<<1184, 256, 0, h->stream>>>(h->dV4.p, h->dStaging.p, (size_t)h->nf, h->L, h->Lp, h->RL, h->C);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemsetAsync(h->dV2.p, 0, h->nw * sizeof(double), h->stream));
+	h->cutoff = cutoff;
+	setScalarKernel<<<1, 1, 0, h->stream>>>(h->dCutoff.p, cutoff);
+	CUDA_TRY(cudaStreamSynchronize(h->stream));
+	h->haveState = true; h->haveFlow = false;
+	return PFFRG_OK;
+}
+
 int pffrg_get_state(pffrg_handle h, double *cutoff, void *v2, void *const *v4, int dtype)
 {
 	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");

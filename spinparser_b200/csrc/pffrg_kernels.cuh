@@ -1211,6 +1211,17 @@ namespace pffrg
 
 	__global__ void setScalarKernel(double *p, double v) { *p = v; }
 
+	// frequency-independent initial vertex: v4[row][c][j] = bare[c][j]
+	__global__ void initialConditionKernel(double *__restrict__ v4, const double *__restrict__ bare, size_t rows, int L, int Lp, int RL, int C)
+	{
+		const size_t n = rows * RL;
+		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		{
+			const int r = (int)(i % RL), c = r / Lp, j = r - c * Lp;
+			v4[i] = j < L ? bare[c * L + j] : 0.0;
+		}
+	}
+
 	// FP64 multiply-add throughput probe (pffrg_fp64_peak): 16 independent chains per thread, nothing but DFMA in the loop
 	__global__ void __launch_bounds__(256) fp64PeakKernel(double *out, int iterations, double a, double b)
 	{

@@ -206,18 +206,13 @@ class FrgCore:
     def setInitialCondition(self, bare_couplings: Sequence[np.ndarray], cutoff: float) -> None:
         """Initial condition of ``SU2EffectiveAction`` (src/SU2/SU2EffectiveAction.hpp:38-60) and the XYZ/TRI equivalents:
         every frequency entry of channel c at representative r is ``bare_couplings[c][r]`` (already divided by the
-        normalization and, for XYZ/TRI, multiplied by 1/4); the self energy starts at zero."""
-        ea = EffectiveAction(self.identifier, self.tables.n_frequencies, self.tables.n_sites)
-        L = self.tables.n_sites
-        if self.identifier == "TRI":
-            block = np.zeros((16, L))
-            for c, values in enumerate(bare_couplings):
-                block[c] = values
-            ea.v4[0][:] = np.tile(block.reshape(-1), self.n_items)
-        else:
-            for c, values in enumerate(bare_couplings):
-                ea.v4[c][:] = np.tile(np.asarray(values, dtype=np.float64), self.n_items)
-        self.setState(cutoff, ea.v2, ea.v4)
+        normalization and, for XYZ/TRI, multiplied by 1/4); the self energy starts at zero. Built on the device
+        (``pffrg_set_initial_condition``)."""
+        L, n_ch = self.tables.n_sites, N_CHANNELS[self.identifier]
+        bare = np.zeros((n_ch, L), dtype=np.float64)
+        for c, values in enumerate(bare_couplings):
+            bare[c] = values
+        check(lib.pffrg_set_initial_condition(self._h, float(cutoff), bare.ctypes.data_as(C.POINTER(C.c_double))))
 
     def pinnedEffectiveAction(self, dtype=np.float64) -> EffectiveAction:
         """An :class:`EffectiveAction` whose arrays live in page-locked host memory (``pffrg_host_alloc``), for full-speed

@@ -100,3 +100,22 @@ def test_device_correlation_measurement_matches_reference(case):
             checked += 1
     assert checked >= 4
     core.close()
+
+
+@pytest.mark.parametrize("case", ["su2_kagome_r4_nw8", "xyz_honeycomb_kitaev_r3_nw10", "tri_kagome_dm_r3_nw6"])
+def test_initial_condition_built_on_the_device(case):
+    """pffrg_set_initial_condition against the initial state the reference constructs (SU2EffectiveAction.hpp:38-60 etc.)."""
+    d = golden(case)
+    name, core = _core(d)
+    L = core.tables.n_sites
+    if name == "TRI":
+        bare = list(np.asarray(d["initial/v4_0"][: 16 * L]).reshape(16, L))
+    else:
+        bare = [np.asarray(d[f"initial/v4_{c}"][:L]) for c in range(core.n_arrays)]
+    core.setInitialCondition(bare, float(d["initial/cutoff"]))
+    got = core.flowingFunctional()
+    assert got.cutoff == float(d["initial/cutoff"])
+    assert np.array_equal(got.v2, d["initial/v2"])
+    for c in range(core.n_arrays):
+        assert np.array_equal(got.v4[c], d[f"initial/v4_{c}"]), c
+    core.close()
