@@ -570,7 +570,7 @@ namespace
 		{
 			if (!src[a]) return fail(PFFRG_ERR_ARGUMENT, "vertex array %d is null", a);
 			CUDA_TRY(cudaMemcpyAsync(staging, src[a], len * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-			importKernel<T><<<1184, 256, 0, h->stream>>>(staging, dst, (size_t)h->nf, h->L, h->Lp, h->RL, h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
+			importKernel<T><<<1184, 256, 0, h->stream>>>(staging, dst, (size_t)h->nf, h->L, h->Lp, h->RL, vectorWidth(h->core), h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
 			CUDA_TRY(cudaGetLastError());
 		}
 		CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -586,7 +586,7 @@ namespace
 		for (int a = 0; a < h->nArrays; ++a)
 		{
 			if (!dst[a]) continue;
-			exportKernel<T><<<1184, 256, 0, h->stream>>>(src, staging, (size_t)h->nf, h->L, h->Lp, h->RL, h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
+			exportKernel<T><<<1184, 256, 0, h->stream>>>(src, staging, (size_t)h->nf, h->L, h->Lp, h->RL, vectorWidth(h->core), h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaMemcpyAsync(dst[a], staging, len * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
 			CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -821,7 +821,7 @@ int pffrg_set_initial_condition(pffrg_handle h, double cutoff, const double *bar
 	const size_t entries = (size_t)h->C * h->L;
 	if (h->dStaging.n < entries) CUDA_TRY(h->dStaging.alloc(entries));
 	CUDA_TRY(cudaMemcpyAsync(h->dStaging.p, bare, entries * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-	initialConditionKernel<<<1184, 256, 0, h->stream>>>(h->dV4.p, h->dStaging.p, (size_t)h->nf, h->L, h->Lp, h->RL, h->C);
+	initialConditionKernel<<<1184, 256, 0, h->stream>>>(h->dV4.p, h->dStaging.p, (size_t)h->nf, h->L, h->Lp, h->RL, vectorWidth(h->core));
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemsetAsync(h->dV2.p, 0, h->nw * sizeof(double), h->stream));
 	h->cutoff = cutoff;

@@ -20,6 +20,12 @@ namespace pffrg
 
 	__host__ __device__ constexpr int channelsOf(int core) { return core == SU2 ? 2 : (core == XYZ ? 4 : 16); }
 
+	// Device layout of the vertex: v4[row][c / VW][site][c % VW] with VW = 2 for SU2 and XYZ -- the channels of a site are stored in
+	// interleaved pairs, so one 16-byte load fetches a pair and a warp reads 32 * 16 contiguous bytes -- and VW = 1 for TRI, whose
+	// gathers address single (spin-permuted) channels. A row is RL = C * Lp doubles in both cases.
+	__host__ __device__ constexpr int vectorWidth(int core) { return core == TRI ? 1 : 2; }
+	__host__ __device__ __forceinline__ int channelOffset(int vw, int c, int Lp) { return (c / vw) * (vw * Lp) + (c % vw); }
+
 	// ---- frequency mesh -------------------------------------------------------------------------------------------
 	// first index i in [1, nw) with mesh[i] > w, or nw if none (the linear scans of FrequencyDiscretization.hpp:264-267,
 	// 290-293, 338-347 as a binary search)

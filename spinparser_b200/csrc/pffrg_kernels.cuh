@@ -5,9 +5,9 @@
 //   K1 v4FlowKernel      d/dLambda Gamma(s,t,u; all r) src/SU2/SU2FrgCore.cpp:171-431 (XYZ :195-571, TRI :153-3001)
 //   K3 eulerKernel       state += dLambda * flow        src/SU2/SU2FrgCore.cpp:111-134
 //
-// Device layout of the two-particle vertex ("vertex-major"): v4[row][c][Lp] with row = su*Nw + t the work-item index,
-// c the vertex channel and Lp = L rounded up to 4 doubles, so one interpolation support of one channel is a contiguous,
-// 32-byte aligned run of L doubles and a whole support row is RL = C*Lp doubles.
+// Device layout of the two-particle vertex ("vertex-major"): v4[row][c / VW][Lp][c % VW] with row = su*Nw + t the work-item
+// index, c the vertex channel, Lp = L rounded up to 4 doubles and VW the vector width (vectorWidth: channel pairs for SU2/XYZ, single
+// channels for TRI), so one interpolation support is a contiguous, 32-byte aligned run per channel (pair) and a whole row is RL = C*Lp doubles.
 #pragma once
 
 #include "pffrg_device.cuh"
@@ -88,7 +88,7 @@ namespace pffrg
 		{
 			int flags = 0;
 			int row = rowIndex(P.nw, so, to, uo, 0, flags);
-			double v = v4[(size_t)row * P.RL + c * P.Lp + site];
+			double v = v4[(size_t)row * P.RL + channelOffset(vectorWidth(CORE), c, P.Lp) + site * vectorWidth(CORE)];
 			return (flags && densityLike) ? -v : v;
 		};
 		return (1 - bu) * ((1 - bt) * ((1 - bs) * at(ls, lt, lu) + bs * at(us, lt, lu)) + bt * ((1 - bs) * at(ls, ut, lu) + bs * at(us, ut, lu)))
@@ -343,23 +343,56 @@ namespace pffrg
 		const bool exchange = flags & AB_EXCHANGE;
 		const int site = exchange ? siteInv : siteFwd;
 		const int perm = exchange ? permInv : permFwd;
-		#pragma unroll
-		for (int c = 0; c < C; ++c) out[c] = 0.0;
-		#pragma unroll
-		for (int k = 0; k < 4; ++k)
+		if constexpr (CORE == SU2)
 		{
-			const double *base = v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + (unsigned)site);
+			// one 16-byte load per support: {spin, density} of the site
+			out[0] = 0.0; out[1] = 0.0;
 			#pragma unroll
-			for (int c = 0; c < C; ++c)
+			for (int k = 0; k < 4; ++k)
 			{
-				// SU2/XYZ: only the density channel is odd under s<->u (SU2VertexTwoParticle.hpp:622-625); TRI: factor -zeta of the
-				// second (first, if exchanged) spin index (TRIVertexTwoParticle.hpp:649-657), i.e. odd iff that index is the density one
-				const int sc = storedChannel<CORE>(flags, c, perm);
-				double w;
-				if (CORE == SU2) w = (c == 1) ? ok[k] : wk[k];
-				else if (CORE == XYZ) w = (c == 3) ? ok[k] : wk[k];
-				else w = (exchange ? ((c >> 2) == 3) : ((c & 3) == 3)) ? ok[k] : wk[k];
-				out[c] += w * __ldg(base + sc * sizeLp(P));
+				const double2 v = __ldg(reinterpret_cast<const double2 *>(v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + 2u * (unsigned)site)));
+				out[0] += wk[k] * v.x;
+				out[1] += ok[k] * v.y; // only the density channel is odd under s<->u (SU2VertexTwoParticle.hpp:622-625)
+			}
+		}
+		else if constexpr (CORE == XYZ)
+		{
+			// two 16-byte loads per support: stored {x, y} and {z, density}; the site's spin permutation (XYZVertexTwoParticle.hpp:401-404)
+			// is applied once to the interpolated values (all three spin channels carry the same weights)
+			double raw[4] = { 0.0, 0.0, 0.0, 0.0 };
+			#pragma unroll
+			for (int k = 0; k < 4; ++k)
+			{
+				const double2 *base = reinterpret_cast<const double2 *>(v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + 2u * (unsigned)site));
+				const double2 xy = __ldg(base), zd = __ldg(base + sizeLp(P));
+				raw[0] += wk[k] * xy.x; raw[1] += wk[k] * xy.y; raw[2] += wk[k] * zd.x;
+				raw[3] += ok[k] * zd.y;
+			}
+			#pragma unroll
+			for (int c = 0; c < 3; ++c)
+			{
+				const int sc = (perm >> (2 * c)) & 3;
+				out[c] = sc == 0 ? raw[0] : (sc == 1 ? raw[1] : raw[2]);
+			}
+			out[3] = raw[3];
+		}
+		else
+		{
+			#pragma unroll
+			for (int c = 0; c < C; ++c) out[c] = 0.0;
+			#pragma unroll
+			for (int k = 0; k < 4; ++k)
+			{
+				const double *base = v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + (unsigned)site);
+				#pragma unroll
+				for (int c = 0; c < C; ++c)
+				{
+					// factor -zeta of the second (first, if exchanged) spin index where the mirrored entry is read
+					// (TRIVertexTwoParticle.hpp:649-657), i.e. the weight is odd iff that index is the density one
+					const int sc = storedChannel<CORE>(flags, c, perm);
+					const double w = (exchange ? ((c >> 2) == 3) : ((c & 3) == 3)) ? ok[k] : wk[k];
+					out[c] += w * __ldg(base + sc * sizeLp(P));
+				}
 			}
 		}
 		if (CORE == TRI)
@@ -1084,7 +1117,7 @@ namespace pffrg
 						const int cs = (CORE == TRI && (ab.flags & AB_EXCHANGE)) ? (4 * (c & 3) + (c >> 2)) : c;
 						double v = 0.0;
 						#pragma unroll
-						for (int k = 0; k < 4; ++k) v += supportSign<CORE>(ab.flags, k, cs) * ab.w[k] * __ldg(v4 + (size_t)ab.row[k] * sizeRL(P) + sc * sizeLp(P));
+						for (int k = 0; k < 4; ++k) v += supportSign<CORE>(ab.flags, k, cs) * ab.w[k] * __ldg(v4 + (size_t)ab.row[k] * sizeRL(P) + channelOffset(vectorWidth(CORE), sc, sizeLp(P)));
 						loc[idx] = v;
 					}
 					__syncthreads();
@@ -1186,7 +1219,7 @@ namespace pffrg
 			for (int gg = 0; gg < cfg.groups; ++gg) v += part[gg * C * L + e];
 			v /= TWO_PI;
 			const int c = e / L, jj = e - c * L;
-			flow[(size_t)item * sizeRL(P) + c * sizeLp(P) + jj] = v;
+			flow[(size_t)item * sizeRL(P) + channelOffset(vectorWidth(CORE), c, sizeLp(P)) + jj * vectorWidth(CORE)] = v;
 			bad |= (v != v);
 		}
 		if (bad) atomicOr(nanFlag, 1);
@@ -1212,12 +1245,12 @@ namespace pffrg
 	__global__ void setScalarKernel(double *p, double v) { *p = v; }
 
 	// frequency-independent initial vertex: v4[row][c][j] = bare[c][j]
-	__global__ void initialConditionKernel(double *__restrict__ v4, const double *__restrict__ bare, size_t rows, int L, int Lp, int RL, int C)
+	__global__ void initialConditionKernel(double *__restrict__ v4, const double *__restrict__ bare, size_t rows, int L, int Lp, int RL, int vw)
 	{
 		const size_t n = rows * RL;
 		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 		{
-			const int r = (int)(i % RL), c = r / Lp, j = r - c * Lp;
+			const int r = (int)(i % RL), group = r / (vw * Lp), rem = r - group * vw * Lp, j = rem / vw, c = group * vw + rem % vw;
 			v4[i] = j < L ? bare[c * L + j] : 0.0;
 		}
 	}
@@ -1241,25 +1274,25 @@ namespace pffrg
 
 	// reference array (one channel, [row][L], or TRI [row][16][L]) -> device layout; T = float or double
 	template <typename T>
-	__global__ void importKernel(const T *__restrict__ src, double *__restrict__ dst, size_t rows, int L, int Lp, int RL, int cFirst, int cCount)
+	__global__ void importKernel(const T *__restrict__ src, double *__restrict__ dst, size_t rows, int L, int Lp, int RL, int vw, int cFirst, int cCount)
 	{
 		const size_t n = rows * cCount * L;
 		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 		{
 			const size_t row = i / ((size_t)cCount * L);
 			const int r = (int)(i - row * cCount * L), c = r / L, j = r - c * L;
-			dst[row * RL + (size_t)(cFirst + c) * Lp + j] = (double)src[i];
+			dst[row * RL + channelOffset(vw, cFirst + c, Lp) + j * vw] = (double)src[i];
 		}
 	}
 	template <typename T>
-	__global__ void exportKernel(const double *__restrict__ src, T *__restrict__ dst, size_t rows, int L, int Lp, int RL, int cFirst, int cCount)
+	__global__ void exportKernel(const double *__restrict__ src, T *__restrict__ dst, size_t rows, int L, int Lp, int RL, int vw, int cFirst, int cCount)
 	{
 		const size_t n = rows * cCount * L;
 		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 		{
 			const size_t row = i / ((size_t)cCount * L);
 			const int r = (int)(i - row * cCount * L), c = r / L, j = r - c * L;
-			dst[i] = (T)src[row * RL + (size_t)(cFirst + c) * Lp + j];
+			dst[i] = (T)src[row * RL + channelOffset(vw, cFirst + c, Lp) + j * vw];
 		}
 	}
 	template <typename T>

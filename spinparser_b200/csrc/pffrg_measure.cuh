@@ -72,7 +72,7 @@ namespace pffrg
 			const int cs = (CORE == TRI && local && exchange) ? (4 * (c & 3) + (c >> 2)) : c;
 			double v = 0.0;
 			#pragma unroll
-			for (int n = 0; n < 8; ++n) v += supportSign<CORE>(ab.flags, n, cs) * ab.w[n] * __ldg(v4 + (size_t)ab.row[n] * P.RL + sc * P.Lp + site);
+			for (int n = 0; n < 8; ++n) v += supportSign<CORE>(ab.flags, n, cs) * ab.w[n] * __ldg(v4 + (size_t)ab.row[n] * P.RL + channelOffset(vectorWidth(CORE), sc, P.Lp) + site * vectorWidth(CORE));
 			out[c] = v;
 		}
 	}
