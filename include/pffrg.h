@@ -95,6 +95,7 @@ typedef struct pffrg_stats
 	int32_t rpa_batch;      /*   t-channel nodes staged per RPA phase, */
 	int32_t rpa_warps;      /*   warps sharing the RPA instruction stream(s), */
 	int32_t min_blocks;     /*   CTAs per SM the kernel was compiled for */
+	int32_t autotuned_shapes; /* launch shapes compiled and timed in pffrg_create (0/1: no autotuning) */
 } pffrg_stats;
 
 /* library / environment ------------------------------------------------------------------------------------------ */

@@ -125,6 +125,7 @@ struct pffrg_context
 	cudaLibrary_t jitLibrary = nullptr;
 	cudaKernel_t jitKernel = nullptr;
 	double jitCompileMs = 0.0;
+	int autotuned = 0; // number of launch shapes that were timed at creation
 	// state
 	DeviceArray<double> dV4, dFlow4, dV2, dFlow2, dCutoff;
 	DeviceArray<int> dCount; DeviceArray<double> dNodeW, dNodeWt;
@@ -282,29 +283,117 @@ namespace
 
 	// Compile and load the lattice-specialised kernel. Controlled by the environment: PFFRG_JIT=0 disables it,
 	// PFFRG_JIT_MAX_TERMS (default 60000) bounds the straight-line code size (compile time grows with it).
-	int setupJit(pffrg_context *h, const pffrg_desc *d, size_t smemMax)
+	float elapsed(cudaEvent_t a, cudaEvent_t b);
+
+	// one launch shape of the run-time compiled kernel
+	struct JitCandidate { int threads, groups; JitShape shape; cudaLibrary_t library; cudaKernel_t kernel; float ms; };
+
+	// four node groups are out of reach for small CTAs; this shape runs two node groups in up to four CTAs of `warps` warps per SM
+	JitShape smallCtaShape(int core, int nw, int L, int groups, int warps, size_t smemMax)
 	{
-		const char *env = getenv("PFFRG_JIT");
-		if (env && atoi(env) == 0) return PFFRG_OK;
-		long maxTerms = 60000;
-		if (const char *e = getenv("PFFRG_JIT_MAX_TERMS")) maxTerms = atol(e);
-		if (h->core == TRI) return PFFRG_OK; // TRI: table-driven RPA phase (rpaTri), precompiled kernels
-		const JitShape shape = chooseJitShape(h->core, h->nw, h->L, h->groups, h->threads / 32, smemMax);
-		if (!shape.nb) return PFFRG_OK;
-		const auto t0 = std::chrono::steady_clock::now();
-		RpaProgram prog = buildRpaProgram(d, h->core, shape.nbt, shape.rpaWarps);
-		if ((long)prog.terms.size() > maxTerms) return PFFRG_OK;
+		const int lanes = core == SU2 ? 16 : 32, nbt = 2 * lanes, nb = 16;
+		const size_t smem = flowSmemBytes(core, nb, nw, L, groups, nbt);
+		const size_t quarter = (smemMax + 1024) / 4 - 1024;
+		if (smem > quarter) return { 0, 0, 0, 0, 0 };
+		return { nb, nbt, std::min(warps, 4), 4, smem };
+	}
+
+	int compileCandidate(pffrg_context *h, const pffrg_desc *d, JitCandidate &c)
+	{
+		RpaProgram prog = buildRpaProgram(d, h->core, c.shape.nbt, c.shape.rpaWarps);
 		// tuning knobs of the generated code (defaults chosen on B200)
 		if (const char *e = getenv("PFFRG_JIT_CHUNK")) prog.chunk = std::max(4, atoi(e));
 		if (const char *e = getenv("PFFRG_JIT_ACC")) prog.maxAccumulators = std::max(1, atoi(e));
 		if (const char *e = getenv("PFFRG_JIT_PREFETCH")) prog.prefetch = std::max(1, atoi(e));
 		std::vector<char> cubin;
-		const std::string err = compileFlowKernel(h->core, shape.nb, shape.nbt, h->threads, shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
+		const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the specialised flow kernel failed: %s", err.c_str());
-		CUDA_TRY(cudaLibraryLoadData(&h->jitLibrary, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-		CUDA_TRY(cudaLibraryGetKernel(&h->jitKernel, h->jitLibrary, "pffrg_v4flow_jit"));
-		h->nb = shape.nb; h->nbt = shape.nbt; h->rpaWarps = shape.rpaWarps; h->minBlocks = shape.minBlocks; h->smemBytes = shape.smem;
-		CUDA_TRY(cudaFuncSetAttribute((const void *)h->jitKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+		CUDA_TRY(cudaLibraryLoadData(&c.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+		CUDA_TRY(cudaLibraryGetKernel(&c.kernel, c.library, "pffrg_v4flow_jit"));
+		CUDA_TRY(cudaFuncSetAttribute((const void *)c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.shape.smem));
+		return PFFRG_OK;
+	}
+
+	void adoptCandidate(pffrg_context *h, const JitCandidate &c)
+	{
+		h->jitLibrary = c.library; h->jitKernel = c.kernel;
+		h->threads = c.threads; h->groups = c.groups;
+		h->nb = c.shape.nb; h->nbt = c.shape.nbt; h->rpaWarps = c.shape.rpaWarps; h->minBlocks = c.shape.minBlocks; h->smemBytes = c.shape.smem;
+	}
+
+	// Compile and load the lattice-specialised kernel. Controlled by the environment: PFFRG_JIT=0 disables it,
+	// PFFRG_JIT_MAX_TERMS (default 60000) bounds the straight-line code size (compile time grows with it).
+	// With PFFRG_AUTOTUNE=1 small lattices (<= PFFRG_AUTOTUNE_MAX_TERMS terms, default 12000: a few seconds of compilation per shape) are AUTOTUNED:
+	// up to three launch shapes (256-thread CTAs; 128-thread CTAs with the same RPA batch; 128-thread CTAs with two node groups,
+	// four per SM) are compiled and timed on a block of work items in the middle of the item range at a mid-mesh cutoff; the
+	// fastest stays. Which shape wins depends on the lattice (measured: cubic-r7 the third, honeycomb-r7 the second, by 3-6 %).
+	// Without it, or with an explicit shape override (PFFRG_JIT_NBT, PFFRG_THREADS), the first shape is used without timing.
+	int setupJit(pffrg_context *h, const pffrg_desc *d, size_t smemMax)
+	{
+		const char *env = getenv("PFFRG_JIT");
+		if (env && atoi(env) == 0) return PFFRG_OK;
+		long maxTerms = 60000, tuneTerms = 12000;
+		if (const char *e = getenv("PFFRG_JIT_MAX_TERMS")) maxTerms = atol(e);
+		if (const char *e = getenv("PFFRG_AUTOTUNE_MAX_TERMS")) tuneTerms = atol(e);
+		if (h->core == TRI) return PFFRG_OK; // TRI: table-driven RPA phase (rpaTri), precompiled kernels
+		const auto t0 = std::chrono::steady_clock::now();
+		std::vector<JitCandidate> candidates;
+		const JitShape first = chooseJitShape(h->core, h->nw, h->L, h->groups, h->threads / 32, smemMax);
+		if (!first.nb) return PFFRG_OK;
+		candidates.push_back({ h->threads, h->groups, first, nullptr, nullptr, 0.f });
+		const long terms = (long)buildRpaProgram(d, h->core, first.nbt, first.rpaWarps).terms.size();
+		if (terms > maxTerms) return PFFRG_OK;
+		// opt-in: the shapes differ in summation order (last-bit differences), so a run that must be reproducible bit for bit across
+		// processes -- e.g. the sharded-vs-single-GPU comparison -- keeps the first shape
+		bool tune = false;
+		if (const char *e = getenv("PFFRG_AUTOTUNE")) tune = atoi(e) != 0 && terms <= tuneTerms && !getenv("PFFRG_JIT_NBT") && !getenv("PFFRG_THREADS") && !getenv("PFFRG_JIT_MINBLOCKS");
+		if (tune && h->threads > 128)
+		{
+			const int groups = std::max(1, 128 / h->stride), threads = std::max(64, (groups * h->stride + 31) / 32 * 32);
+			if (threads < h->threads)
+			{
+				const JitShape same = chooseJitShape(h->core, h->nw, h->L, groups, threads / 32, smemMax);
+				if (same.nb) candidates.push_back({ threads, groups, same, nullptr, nullptr, 0.f });
+				const JitShape small = smallCtaShape(h->core, h->nw, h->L, groups, threads / 32, smemMax);
+				if (small.nb) candidates.push_back({ threads, groups, small, nullptr, nullptr, 0.f });
+			}
+		}
+		for (JitCandidate &c : candidates) { const int rc = compileCandidate(h, d, c); if (rc != PFFRG_OK) return rc; }
+		size_t best = 0;
+		if (candidates.size() > 1)
+		{
+			// timing run: zero vertex (timing is independent of the values), self energy zero, cutoff in the middle of the mesh
+			const double cutoff = std::sqrt(h->mesh.front() * h->mesh.back());
+			CUDA_TRY(cudaMemsetAsync(h->dV2.p, 0, h->nw * sizeof(double), h->stream));
+			setScalarKernel<<<1, 1, 0, h->stream>>>(h->dCutoff.p, cutoff);
+			nodeTableKernel<<<h->nw, 128, sizeof(double) * (3 * h->nw + 2 * h->nodeStride), h->stream>>>(h->problem(), h->nodeTable(), h->dV2.p, h->dFlow2.p, h->dCutoff.p);
+			CUDA_TRY(cudaGetLastError());
+			const int64_t count = std::min<int64_t>(h->nf, 1184), begin = (h->nf - count) / 2;
+			for (size_t k = 0; k < candidates.size(); ++k)
+			{
+				adoptCandidate(h, candidates[k]);
+				for (int rep = 0; rep < 3; ++rep)
+				{
+					CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+					CUDA_TRY(launchFlowDispatch(h, begin, count));
+					CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+					CUDA_TRY(cudaStreamSynchronize(h->stream));
+					const float ms = elapsed(h->ev[0], h->ev[1]);
+					if (rep == 1 || (rep == 2 && ms < candidates[k].ms)) candidates[k].ms = ms;
+				}
+				if (candidates[k].ms < candidates[best].ms) best = k;
+			}
+			CUDA_TRY(cudaMemsetAsync(h->dFlow4.p, 0, h->v4Elements() * sizeof(double), h->stream));
+			CUDA_TRY(cudaMemsetAsync(h->dNan.p, 0, sizeof(int), h->stream));
+			CUDA_TRY(cudaStreamSynchronize(h->stream));
+			if (getenv("PFFRG_JIT_VERBOSE"))
+				for (size_t k = 0; k < candidates.size(); ++k)
+					fprintf(stderr, "[pffrg autotune] threads %d nb %d nbt %d rpa warps %d ctas %d smem %zu: %.3f ms%s\n", candidates[k].threads, candidates[k].shape.nb, candidates[k].shape.nbt,
+						candidates[k].shape.rpaWarps, candidates[k].shape.minBlocks, candidates[k].shape.smem, candidates[k].ms, k == best ? "  <- selected" : "");
+		}
+		for (size_t k = 0; k < candidates.size(); ++k) if (k != best && candidates[k].library) cudaLibraryUnload(candidates[k].library);
+		adoptCandidate(h, candidates[best]);
+		h->autotuned = (int)candidates.size();
 		h->jitCompileMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 		return PFFRG_OK;
 	}
@@ -971,6 +1060,7 @@ int pffrg_get_stats(pffrg_handle h, pffrg_stats *out)
 	out->jit_rpa = h->jitKernel ? 1 : 0;
 	out->jit_compile_ms = h->jitCompileMs;
 	out->threads = h->threads; out->smem_bytes = (int32_t)h->smemBytes; out->node_batch = h->nb; out->rpa_batch = h->jitKernel ? h->nbt : h->nb;
+	out->autotuned_shapes = h->autotuned;
 	out->rpa_warps = h->jitKernel ? h->rpaWarps : h->threads / 32; out->min_blocks = h->jitKernel ? h->minBlocks : (h->core == TRI ? 1 : 2);
 	return PFFRG_OK;
 }

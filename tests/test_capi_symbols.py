@@ -87,3 +87,13 @@ def test_pfd_round_trip(tmp_path):
     assert list(back) == list(arrays)
     for k in arrays:
         assert back[k].dtype == np.asarray(arrays[k]).dtype and np.array_equal(back[k], arrays[k])
+
+
+def test_unknown_core_options_raise_like_the_reference_constructors():
+    # "Unknown spin model option" -- src/SU2/SU2FrgCore.cpp:27, src/XYZ/XYZFrgCore.cpp:25 (XYZ/TRI do not know `spin`)
+    from spinparser_b200 import FrgCoreFactory, PffrgError, ProblemTables
+    tables = ProblemTables.from_pfd(golden("su2_square_r3_nw10"))
+    with pytest.raises(PffrgError, match="Unknown spin model option 'foo'"):
+        FrgCoreFactory.newFrgCore("SU2", tables, {"foo": "1"})
+    with pytest.raises(PffrgError, match="Unknown spin model option 'spin'"):
+        FrgCoreFactory.newFrgCore("XYZ", tables, {"spin": "0.5"})

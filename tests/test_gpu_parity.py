@@ -20,13 +20,14 @@ def _core(d):
 # kernel variants: the run-time compiled lattice-specialised kernel (default for SU2/XYZ), the precompiled generic kernels
 # (PFFRG_JIT=0) and their smaller gather batches (PFFRG_NB; NB = 8 selects the TRI core's rpaTri8 phase, which large
 # lattices use)
-VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16"}]
+VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16"}, {"PFFRG_AUTOTUNE": "1"},
+            {"PFFRG_THREADS": "128", "PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16", "PFFRG_JIT_MINBLOCKS": "4"}]
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
 @pytest.mark.parametrize("case", CASES)
 def test_one_step_flow_matches_reference(case, variant, monkeypatch):
-    if case.startswith("tri") and "PFFRG_JIT_NBT" in variant:
+    if case.startswith("tri") and ("PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant):
         pytest.skip("the TRI core has no run-time compiled variant")
     for k, x in variant.items():
         monkeypatch.setenv(k, x)
@@ -118,4 +119,22 @@ def test_initial_condition_built_on_the_device(case):
     assert np.array_equal(got.v2, d["initial/v2"])
     for c in range(core.n_arrays):
         assert np.array_equal(got.v4[c], d[f"initial/v4_{c}"]), c
+    core.close()
+
+
+def test_call_sequence_violations_are_reported():
+    """PFFRG_ERR_STATE (-4) instead of undefined behaviour: compute / measure before a state exists, finalize before compute."""
+    from spinparser_b200 import PffrgError
+    d = golden("su2_square_r3_nw10")
+    name, core = _core(d)
+    for call in (core.computeStep, core.measureCorrelation, lambda: core.finalizeStep(1.0), core.flow, core.flowingFunctional):
+        with pytest.raises(PffrgError) as err:
+            call()
+        assert err.value.code == -4, call
+    core.setState(float(d["step0/state/cutoff"]), np.ascontiguousarray(d["step0/state/v2"]), [np.ascontiguousarray(d[f"step0/state/v4_{c}"]) for c in range(2)])
+    with pytest.raises(PffrgError) as err:
+        core.finalizeStep(1.0)
+    assert err.value.code == -4
+    with pytest.raises(PffrgError):
+        core.setState(1.0, np.zeros(3), [np.zeros(5), np.zeros(5)])  # wrong sizes are rejected on the host side
     core.close()
