@@ -265,6 +265,30 @@ namespace
 
 	RpaProgram buildRpaProgram(const pffrg_desc *d, int core, int nbt, int rpaWarps);
 
+	// threads of a CTA: `groups` groups of `stride` threads, one group per quadrature node at a time (used by pffrg_create and
+	// by the device-less pffrg_jit_compile_check, which must arrive at the same kernel)
+	struct LaunchGeometry { int stride, groups, threads; };
+	LaunchGeometry chooseGeometry(int L)
+	{
+		LaunchGeometry g;
+		const int padded = (L + 31) / 32 * 32;
+		g.stride = (padded - L) * 4 <= padded ? padded : L;
+		if (const char *e = getenv("PFFRG_PAD_GROUPS")) g.stride = atoi(e) ? padded : L; // tuning override
+		int threadTarget = 256; // PFFRG_THREADS: tuning override (values above 256 only work with the run-time compiled kernel)
+		if (const char *e = getenv("PFFRG_THREADS")) threadTarget = std::min(1024, std::max(64, atoi(e)));
+		g.groups = std::max(1, threadTarget / g.stride);
+		g.threads = std::max(64, (g.groups * g.stride + 31) / 32 * 32);
+		return g;
+	}
+
+	// tuning knobs of the generated RPA code (defaults chosen on B200)
+	void applyJitKnobs(RpaProgram &prog)
+	{
+		if (const char *e = getenv("PFFRG_JIT_CHUNK")) prog.chunk = std::max(4, atoi(e));
+		if (const char *e = getenv("PFFRG_JIT_ACC")) prog.maxAccumulators = std::max(1, atoi(e));
+		if (const char *e = getenv("PFFRG_JIT_PREFETCH")) prog.prefetch = std::max(1, atoi(e));
+	}
+
 	cudaError_t launchFlowDispatch(pffrg_context *h, int64_t begin, int64_t count)
 	{
 		if (count <= 0) return cudaSuccess;
@@ -301,10 +325,7 @@ namespace
 	int compileCandidate(pffrg_context *h, const pffrg_desc *d, JitCandidate &c)
 	{
 		RpaProgram prog = buildRpaProgram(d, h->core, c.shape.nbt, c.shape.rpaWarps);
-		// tuning knobs of the generated code (defaults chosen on B200)
-		if (const char *e = getenv("PFFRG_JIT_CHUNK")) prog.chunk = std::max(4, atoi(e));
-		if (const char *e = getenv("PFFRG_JIT_ACC")) prog.maxAccumulators = std::max(1, atoi(e));
-		if (const char *e = getenv("PFFRG_JIT_PREFETCH")) prog.prefetch = std::max(1, atoi(e));
+		applyJitKnobs(prog);
 		std::vector<char> cubin;
 		const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the specialised flow kernel failed: %s", err.c_str());
@@ -762,13 +783,8 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	// launch configuration: k groups of L threads; batch width NB chosen so that at least two CTAs fit per SM
 	// a group of threads covers the L sites of one quadrature node; groups are padded to whole warps when that idles at
 	// most a quarter of the lanes (then every warp gathers from one node only: fewer cache lines per load, uniform table reads)
-	const int padded = (L + 31) / 32 * 32;
-	h->stride = (padded - L) * 4 <= padded ? padded : L;
-	if (const char *e = getenv("PFFRG_PAD_GROUPS")) h->stride = atoi(e) ? padded : L; // tuning override
-	int threadTarget = 256; // PFFRG_THREADS: tuning override (values above 256 only work with the run-time compiled kernel)
-	if (const char *e = getenv("PFFRG_THREADS")) threadTarget = std::min(1024, std::max(64, atoi(e)));
-	h->groups = std::max(1, threadTarget / h->stride);
-	h->threads = std::max(64, (h->groups * h->stride + 31) / 32 * 32);
+	const LaunchGeometry geo = chooseGeometry(L);
+	h->stride = geo.stride; h->groups = geo.groups; h->threads = geo.threads;
 	// SU2/XYZ: two CTAs per SM (100 KB each); the TRI core stages four 16-channel RPA operand buffers and runs one CTA per SM
 	h->nb = 32;
 	const int minNb = h->core == TRI ? 4 : 8;
@@ -1071,13 +1087,13 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 {
 	if (!d || d->n_sites < 1 || d->n_sites > 256 || d->core < 0 || d->core > 1 || !d->overlap_offsets) return fail(PFFRG_ERR_ARGUMENT, "bad descriptor");
 	// same launch configuration as pffrg_create
-	const int L = d->n_sites, padded = (L + 31) / 32 * 32;
-	const int stride = (padded - L) * 4 <= padded ? padded : L;
-	const int groups = std::max(1, 256 / stride);
-	const int threads = std::max(64, (groups * stride + 31) / 32 * 32);
+	const int L = d->n_sites;
+	const LaunchGeometry geo = chooseGeometry(L);
+	const int groups = geo.groups, threads = geo.threads;
 	const JitShape shape = chooseJitShape(d->core, d->n_frequencies, L, groups, threads / 32, 227 * 1024);
 	if (!shape.nb) return fail(PFFRG_ERR_UNSUPPORTED, "lattice too large for the specialised kernel");
 	RpaProgram prog = buildRpaProgram(d, d->core, shape.nbt, shape.rpaWarps);
+	applyJitKnobs(prog);
 	std::vector<char> cubin;
 	const std::string err = compileFlowKernel(d->core, shape.nb, shape.nbt, threads, shape.minBlocks, KernelSizes{ L, paddedSites(L), channelsOf(d->core) * paddedSites(L), d->n_frequencies }, generateRpaSource(prog), cubin);
 	if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());

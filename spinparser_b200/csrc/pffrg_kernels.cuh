@@ -269,6 +269,10 @@ namespace pffrg
 	//               with NVRTC (pffrg_jit.cpp); operands are cached in registers, multiplicities are immediates
 	//   epilogue  deterministic reduction over groups, 1/2pi, NaN flag, coalesced store of the item's C x L flow values
 	// ================================================================================================================
+#ifndef PFFRG_MIRROR
+#define PFFRG_MIRROR 1 // t channel: form buffers 2, 3 from the rows loaded for buffers 0, 1 (gatherMirrored); 0 only in A/B timing runs of the run-time compiled kernel
+#endif
+
 	struct FlowConfig
 	{
 		int groups;      // k
@@ -329,80 +333,146 @@ namespace pffrg
 	};
 
 	// gather one access buffer for site j: out[c] = sum_k sign_k(c) w_k v4[row_k][stored(c)][site]
-	template <int CORE>
-	__device__ __forceinline__ void gatherSite(const Problem &P, const double *__restrict__ v4, const AccessBuffer &ab, int siteFwd, int siteInv, int permFwd, int permInv, double (&out)[channelsOf(CORE)])
+	// SU2 / XYZ: split into the loads (RawSupports: the channel pairs of the four support rows at the site) and the weighted
+	// combination, so that a second buffer reading the same rows can be formed without loading again (gatherMirrored).
+	template <int CORE> struct RawSupports { double2 v[4][CORE == XYZ ? 2 : 1]; };
+
+	struct AccessHeader
 	{
-		constexpr int C = channelsOf(CORE);
-		// the table entry is 16-byte aligned: 128-bit shared loads
-		const double2 w01 = *reinterpret_cast<const double2 *>(&ab.w[0]), w23 = *reinterpret_cast<const double2 *>(&ab.w[2]);
-		const int4 rows = *reinterpret_cast<const int4 *>(&ab.row[0]);
-		const int flags = ab.flags;
-		const double wk[4] = { w01.x, w01.y, w23.x, w23.y };
-		const double ok[4] = { oddWeight(w01.x, flags, 0), oddWeight(w01.y, flags, 1), oddWeight(w23.x, flags, 2), oddWeight(w23.y, flags, 3) };
-		const int rk[4] = { rows.x, rows.y, rows.z, rows.w };
-		const bool exchange = flags & AB_EXCHANGE;
-		const int site = exchange ? siteInv : siteFwd;
-		const int perm = exchange ? permInv : permFwd;
+		double wk[4], ok[4];
+		int rk[4];
+		int flags;
+		__device__ __forceinline__ explicit AccessHeader(const AccessBuffer &ab)
+		{
+			// the table entry is 16-byte aligned: 128-bit shared loads
+			const double2 w01 = *reinterpret_cast<const double2 *>(&ab.w[0]), w23 = *reinterpret_cast<const double2 *>(&ab.w[2]);
+			const int4 rows = *reinterpret_cast<const int4 *>(&ab.row[0]);
+			flags = ab.flags;
+			wk[0] = w01.x; wk[1] = w01.y; wk[2] = w23.x; wk[3] = w23.y;
+			ok[0] = oddWeight(w01.x, flags, 0); ok[1] = oddWeight(w01.y, flags, 1); ok[2] = oddWeight(w23.x, flags, 2); ok[3] = oddWeight(w23.y, flags, 3);
+			rk[0] = rows.x; rk[1] = rows.y; rk[2] = rows.z; rk[3] = rows.w;
+		}
+	};
+
+	template <int CORE>
+	__device__ __forceinline__ void loadSupports(const Problem &P, const double *__restrict__ v4, const AccessHeader &h, int site, RawSupports<CORE> &raw)
+	{
+		#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			const double2 *base = reinterpret_cast<const double2 *>(v4 + (size_t)((unsigned)h.rk[k] * (unsigned)sizeRL(P) + 2u * (unsigned)site));
+			raw.v[k][0] = __ldg(base);
+			if constexpr (CORE == XYZ) raw.v[k][1] = __ldg(base + sizeLp(P));
+		}
+	}
+
+	// weighted combination of the supports in the order k = 0..3 of THIS buffer; support k reads raw.v[MIRROR ? {0,2,1,3}[k] : k]
+	template <int CORE, bool MIRROR>
+	__device__ __forceinline__ void combineSupports(const AccessHeader &h, const RawSupports<CORE> &raw, int perm, double (&out)[channelsOf(CORE)])
+	{
 		if constexpr (CORE == SU2)
 		{
-			// one 16-byte load per support: {spin, density} of the site
+			// {spin, density} of the site; only the density channel is odd under s<->u (SU2VertexTwoParticle.hpp:622-625)
 			out[0] = 0.0; out[1] = 0.0;
 			#pragma unroll
 			for (int k = 0; k < 4; ++k)
 			{
-				const double2 v = __ldg(reinterpret_cast<const double2 *>(v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + 2u * (unsigned)site)));
-				out[0] += wk[k] * v.x;
-				out[1] += ok[k] * v.y; // only the density channel is odd under s<->u (SU2VertexTwoParticle.hpp:622-625)
+				const double2 v = raw.v[MIRROR ? ((k == 1) ? 2 : (k == 2) ? 1 : k) : k][0];
+				out[0] += h.wk[k] * v.x;
+				out[1] += h.ok[k] * v.y;
 			}
 		}
-		else if constexpr (CORE == XYZ)
+		else
 		{
-			// two 16-byte loads per support: stored {x, y} and {z, density}; the site's spin permutation (XYZVertexTwoParticle.hpp:401-404)
-			// is applied once to the interpolated values (all three spin channels carry the same weights)
-			double raw[4] = { 0.0, 0.0, 0.0, 0.0 };
+			// stored {x, y} and {z, density}; the site's spin permutation (XYZVertexTwoParticle.hpp:401-404) is applied once to the
+			// interpolated values (all three spin channels carry the same weights)
+			double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
 			#pragma unroll
 			for (int k = 0; k < 4; ++k)
 			{
-				const double2 *base = reinterpret_cast<const double2 *>(v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + 2u * (unsigned)site));
-				const double2 xy = __ldg(base), zd = __ldg(base + sizeLp(P));
-				raw[0] += wk[k] * xy.x; raw[1] += wk[k] * xy.y; raw[2] += wk[k] * zd.x;
-				raw[3] += ok[k] * zd.y;
+				const int kk = MIRROR ? ((k == 1) ? 2 : (k == 2) ? 1 : k) : k;
+				const double2 xy = raw.v[kk][0], zd = raw.v[kk][CORE == XYZ ? 1 : 0];
+				acc[0] += h.wk[k] * xy.x; acc[1] += h.wk[k] * xy.y; acc[2] += h.wk[k] * zd.x;
+				acc[3] += h.ok[k] * zd.y;
 			}
 			#pragma unroll
 			for (int c = 0; c < 3; ++c)
 			{
 				const int sc = (perm >> (2 * c)) & 3;
-				out[c] = sc == 0 ? raw[0] : (sc == 1 ? raw[1] : raw[2]);
+				out[c] = sc == 0 ? acc[0] : (sc == 1 ? acc[1] : acc[2]);
 			}
-			out[3] = raw[3];
+			out[3] = acc[3];
+		}
+	}
+
+	template <int CORE>
+	__device__ __forceinline__ void gatherSite(const Problem &P, const double *__restrict__ v4, const AccessBuffer &ab, int siteFwd, int siteInv, int permFwd, int permInv, double (&out)[channelsOf(CORE)])
+	{
+		constexpr int C = channelsOf(CORE);
+		if constexpr (CORE != TRI)
+		{
+			const AccessHeader h(ab);
+			const bool exchange = h.flags & AB_EXCHANGE;
+			RawSupports<CORE> raw;
+			loadSupports<CORE>(P, v4, h, exchange ? siteInv : siteFwd, raw);
+			combineSupports<CORE, false>(h, raw, exchange ? permInv : permFwd, out);
 		}
 		else
 		{
+			const AccessHeader h(ab);
+			const int flags = h.flags;
+			const bool exchange = flags & AB_EXCHANGE;
+			const int site = exchange ? siteInv : siteFwd;
+			const int perm = exchange ? permInv : permFwd;
 			#pragma unroll
 			for (int c = 0; c < C; ++c) out[c] = 0.0;
 			#pragma unroll
 			for (int k = 0; k < 4; ++k)
 			{
-				const double *base = v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + (unsigned)site);
+				const double *base = v4 + (size_t)((unsigned)h.rk[k] * (unsigned)sizeRL(P) + (unsigned)site);
 				#pragma unroll
 				for (int c = 0; c < C; ++c)
 				{
 					// factor -zeta of the second (first, if exchanged) spin index where the mirrored entry is read
 					// (TRIVertexTwoParticle.hpp:649-657), i.e. the weight is odd iff that index is the density one
 					const int sc = storedChannel<CORE>(flags, c, perm);
-					const double w = (exchange ? ((c >> 2) == 3) : ((c & 3) == 3)) ? ok[k] : wk[k];
+					const double w = (exchange ? ((c >> 2) == 3) : ((c & 3) == 3)) ? h.ok[k] : h.wk[k];
 					out[c] += w * __ldg(base + sc * sizeLp(P));
 				}
 			}
-		}
-		if (CORE == TRI)
-		{
 			// zeta_mu * zeta_nu for every sign change of t or u (TRIVertexTwoParticle.hpp:414-443): flips exactly the mixed spin-density channels
 			if (flags & AB_TZ)
 			{
 				#pragma unroll
 				for (int c = 0; c < C; ++c) if (((c >> 2) == 3) != ((c & 3) == 3)) out[c] = -out[c];
 			}
+		}
+	}
+
+	// The t channel's gathered buffers come in mirrored pairs: buffer 2 is buffer 0 with the s and u arguments exchanged, and
+	// buffer 3 is buffer 1 with (s, u) -> (-u, -s) (src/SU2/SU2FrgCore.cpp:233-239). Only s >= u is stored, so both members of
+	// a pair read the SAME four rows at the same sites -- supports 1 and 2 trade places, the weights and the mirror flags are
+	// the pair member's own. Whenever that holds (checked on the assembled tables, so it is a pure load elision: the values
+	// combined are bit-identical to what a second set of loads would return) the second buffer is formed from the first one's
+	// registers; otherwise it is gathered normally.
+	template <int CORE>
+	__device__ __forceinline__ void gatherMirrored(const Problem &P, const double *__restrict__ v4, const AccessBuffer &abFirst, const AccessBuffer &abSecond, int siteFwd, int siteInv, int permFwd, int permInv,
+		double (&outFirst)[channelsOf(CORE)], double (&outSecond)[channelsOf(CORE)])
+	{
+		static_assert(CORE != TRI, "the TRI core gathers single channels");
+		const AccessHeader h0(abFirst), h1(abSecond);
+		const bool exchange = h0.flags & AB_EXCHANGE;
+		const int site = exchange ? siteInv : siteFwd, perm = exchange ? permInv : permFwd;
+		RawSupports<CORE> raw;
+		loadSupports<CORE>(P, v4, h0, site, raw);
+		combineSupports<CORE, false>(h0, raw, perm, outFirst);
+		const bool same = ((h0.flags ^ h1.flags) & AB_EXCHANGE) == 0 && h1.rk[0] == h0.rk[0] && h1.rk[1] == h0.rk[2] && h1.rk[2] == h0.rk[1] && h1.rk[3] == h0.rk[3];
+		if (same) combineSupports<CORE, true>(h1, raw, perm, outSecond);
+		else
+		{
+			const bool exchange1 = h1.flags & AB_EXCHANGE;
+			loadSupports<CORE>(P, v4, h1, exchange1 ? siteInv : siteFwd, raw);
+			combineSupports<CORE, false>(h1, raw, exchange1 ? permInv : permFwd, outSecond);
 		}
 	}
 
@@ -1141,8 +1211,17 @@ namespace pffrg
 					for (int node = g; node < nb; node += cfg.groups)
 					{
 						double A[4][C];
-						#pragma unroll
-						for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, abTable[node * nbuf + b], siteFwd, siteInv, permFwd, permInv, A[b]);
+						if (tPass && PFFRG_MIRROR)
+						{
+							// buffers (0, 2) and (1, 3) read the same rows, see gatherMirrored
+							gatherMirrored<CORE>(P, v4, abTable[node * nbuf + 0], abTable[node * nbuf + 2], siteFwd, siteInv, permFwd, permInv, A[0], A[2]);
+							gatherMirrored<CORE>(P, v4, abTable[node * nbuf + 1], abTable[node * nbuf + 3], siteFwd, siteInv, permFwd, permInv, A[1], A[3]);
+						}
+						else
+						{
+							#pragma unroll
+							for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, abTable[node * nbuf + b], siteFwd, siteInv, permFwd, permInv, A[b]);
+						}
 						const double W = bW[node];
 						double K[C];
 						if (!tPass)
