@@ -338,7 +338,7 @@ def main():
             "alg_gb_per_step": alg_bytes / 1e9, "alg_gflop_per_step": alg_flops / 1e9,
             "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
             "breakdown_ms": {k: statistics.mean(st[k] for _, _, st in records) for k in ("ms_v2_flow", "ms_node_table", "ms_v4_flow", "ms_finalize", "ms_exchange")},
-            "launch_shape": {k: records[0][2][k] for k in ("jit_rpa", "threads", "smem_bytes", "node_batch", "rpa_batch", "rpa_warps", "min_blocks", "autotuned_shapes", "jit_compile_ms")},
+            "launch_shape": {k: records[0][2][k] for k in ("jit_rpa", "threads", "smem_bytes", "node_batch", "rpa_batch", "rpa_warps", "min_blocks", "sub_ctas", "autotuned_shapes", "jit_compile_ms")},
             "roofline": {"bound": "hbm", "kernel": "pffrg::v4FlowKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.workload),
                          "peak_source": peak_src, "note": "achieved = algorithmic gather+output bytes (SURVEY 8d: 128*L*C per kernel evaluation + 24*L*C per item) / kernel time, per GPU; gathers that hit in L2 do not reach DRAM, so `traffic` (ncu dram bytes per launch) is far below the algorithmic bytes and frac can exceed 1",
                          "fp64_tflops_achieved": alg_flops / world / (kernel_ms_avg * 1e-3) / 1e12,

@@ -96,6 +96,7 @@ typedef struct pffrg_stats
 	int32_t rpa_warps;      /*   warps sharing the RPA instruction stream(s), */
 	int32_t min_blocks;     /*   CTAs per SM the kernel was compiled for */
 	int32_t autotuned_shapes; /* launch shapes compiled and timed in pffrg_create (0/1: no autotuning) */
+	int32_t sub_ctas;       /* work items per CTA of the run-time compiled kernel (sub-CTAs sharing one RPA phase); fills the former tail padding */
 } pffrg_stats;
 
 /* library / environment ------------------------------------------------------------------------------------------ */

@@ -55,7 +55,7 @@ class Stats(C.Structure):
         ("ms_finalize", C.c_double), ("ms_exchange", C.c_double),
         ("kernel_evals", C.c_int64), ("kernel_evals_t", C.c_int64), ("items", C.c_int64),
         ("alg_bytes", C.c_double), ("alg_flops", C.c_double), ("launches", C.c_int32), ("jit_rpa", C.c_int32), ("jit_compile_ms", C.c_double),
-        ("threads", C.c_int32), ("smem_bytes", C.c_int32), ("node_batch", C.c_int32), ("rpa_batch", C.c_int32), ("rpa_warps", C.c_int32), ("min_blocks", C.c_int32), ("autotuned_shapes", C.c_int32),
+        ("threads", C.c_int32), ("smem_bytes", C.c_int32), ("node_batch", C.c_int32), ("rpa_batch", C.c_int32), ("rpa_warps", C.c_int32), ("min_blocks", C.c_int32), ("autotuned_shapes", C.c_int32), ("sub_ctas", C.c_int32),
     ]
 
     def as_dict(self):

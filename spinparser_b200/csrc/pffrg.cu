@@ -136,7 +136,8 @@ struct pffrg_context
 	int nodeStride = 0;
 
 	// launch configuration of the flow kernel
-	int nb = 32, nbt = 32, rpaWarps = 8, minBlocks = 2, groups = 1, stride = 1, threads = 32, nslots = 1; size_t smemBytes = 0;
+	int nb = 32, nbt = 32, rpaWarps = 8, minBlocks = 2, groups = 1, stride = 1, threads = 32, nslots = 1, subs = 1; size_t smemBytes = 0;
+	// (run-time compiled kernel: `threads` = all threads of a CTA = subs sub-CTAs of groups * stride threads (rounded to warps), nbt = nodes per RPA phase and sub-CTA)
 
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[8] = {};
@@ -197,21 +198,21 @@ namespace
 		return start;
 	}
 
-	template <int CORE, int NB> size_t flowSmemBytes(int nw, int L, int groups, int nbt) { return FlowSmem<CORE, NB>(nw, L, groups, nbt).total; }
+	template <int CORE, int NB> size_t flowSmemBytes(int nw, int L, int groups, int nbt, int subs) { return FlowSmem<CORE, NB>(nw, L, groups, nbt, subs).total; }
 	// nbt = nodes staged per RPA phase (0: same as the gather batch nb)
-	size_t flowSmemBytes(int core, int nb, int nw, int L, int groups, int nbt = 0)
+	size_t flowSmemBytes(int core, int nb, int nw, int L, int groups, int nbt = 0, int subs = 1)
 	{
 		if (nbt <= 0) nbt = nb;
-		if (core == SU2) return nb == 32 ? flowSmemBytes<SU2, 32>(nw, L, groups, nbt) : nb == 16 ? flowSmemBytes<SU2, 16>(nw, L, groups, nbt) : flowSmemBytes<SU2, 8>(nw, L, groups, nbt);
-		if (core == XYZ) return nb == 32 ? flowSmemBytes<XYZ, 32>(nw, L, groups, nbt) : nb == 16 ? flowSmemBytes<XYZ, 16>(nw, L, groups, nbt) : flowSmemBytes<XYZ, 8>(nw, L, groups, nbt);
-		return nb == 32 ? flowSmemBytes<TRI, 32>(nw, L, groups, nbt) : nb == 16 ? flowSmemBytes<TRI, 16>(nw, L, groups, nbt) : nb == 8 ? flowSmemBytes<TRI, 8>(nw, L, groups, nbt) : flowSmemBytes<TRI, 4>(nw, L, groups, nbt);
+		if (core == SU2) return nb == 32 ? flowSmemBytes<SU2, 32>(nw, L, groups, nbt, subs) : nb == 16 ? flowSmemBytes<SU2, 16>(nw, L, groups, nbt, subs) : flowSmemBytes<SU2, 8>(nw, L, groups, nbt, subs);
+		if (core == XYZ) return nb == 32 ? flowSmemBytes<XYZ, 32>(nw, L, groups, nbt, subs) : nb == 16 ? flowSmemBytes<XYZ, 16>(nw, L, groups, nbt, subs) : flowSmemBytes<XYZ, 8>(nw, L, groups, nbt, subs);
+		return nb == 32 ? flowSmemBytes<TRI, 32>(nw, L, groups, nbt, subs) : nb == 16 ? flowSmemBytes<TRI, 16>(nw, L, groups, nbt, subs) : nb == 8 ? flowSmemBytes<TRI, 8>(nw, L, groups, nbt, subs) : flowSmemBytes<TRI, 4>(nw, L, groups, nbt, subs);
 	}
 
 	// Launch shape of the lattice-specialised kernel. The RPA phase runs as ONE instruction stream shared by `nodeGroups`
 	// warps (one per SM sub-partition when there are four), each on its own group of 16 (SU2) or 32 staged nodes, so the
 	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Environment overrides for tuning runs:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_TILES, PFFRG_JIT_MINBLOCKS.
-	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; };
+	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; };
 	JitShape chooseJitShape(int core, int nw, int L, int groups, int warps, size_t smemMax)
 	{
 		const int lanes = core == SU2 ? 16 : 32;
@@ -258,7 +259,7 @@ namespace
 		auto kernel = v4FlowKernel<CORE, NB>;
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes);
 		if (e != cudaSuccess) return e;
-		FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes;
+		FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes; cfg.items = (int)count;
 		kernel<<<(unsigned)count, h->threads, h->smemBytes, h->stream>>>(h->problem(), h->nodeTable(), cfg, h->dV4.p, h->dFlow4.p, (int)begin, h->dNan.p);
 		return cudaGetLastError();
 	}
@@ -295,10 +296,10 @@ namespace
 		if (h->jitKernel)
 		{
 			Problem P = h->problem(); NodeTable N = h->nodeTable();
-			FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes;
+			FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes; cfg.items = (int)count;
 			const double *v4 = h->dV4.p; double *flow = h->dFlow4.p; int itemBegin = (int)begin; int *nan = h->dNan.p;
 			void *args[] = { &P, &N, &cfg, &v4, &flow, &itemBegin, &nan };
-			return cudaLaunchKernel((const void *)h->jitKernel, dim3((unsigned)count), dim3(h->threads), args, h->smemBytes, h->stream);
+			return cudaLaunchKernel((const void *)h->jitKernel, dim3((unsigned)((count + h->subs - 1) / h->subs)), dim3(h->threads), args, h->smemBytes, h->stream);
 		}
 		if (h->core == SU2) return h->nb == 32 ? launchFlow<SU2, 32>(h, begin, count) : h->nb == 16 ? launchFlow<SU2, 16>(h, begin, count) : launchFlow<SU2, 8>(h, begin, count);
 		if (h->core == XYZ) return h->nb == 32 ? launchFlow<XYZ, 32>(h, begin, count) : h->nb == 16 ? launchFlow<XYZ, 16>(h, begin, count) : launchFlow<XYZ, 8>(h, begin, count);
@@ -322,12 +323,27 @@ namespace
 		return { nb, nbt, std::min(warps, 4), 4, smem };
 	}
 
+	// A CTA of `subs` sub-CTAs (one work item each, `warps` warps each) that share ONE RPA phase over subs * nbt staged nodes:
+	// the straight-line RPA code is streamed through the instruction caches once per `subs` items. nbt / nb are per sub-CTA.
+	JitShape subCtaShape(int core, int nw, int L, int groups, int warps, int subs, int nbt, int nb, int ctas, size_t smemMax)
+	{
+		const int lanes = core == SU2 ? 16 : 32;
+		if (subs < 2 || subs > 4 || nbt % lanes || nbt % nb || warps * subs > 32) return { 0, 0, 0, 0, 0 };
+		const int nodeGroups = subs * nbt / lanes, total = warps * subs;
+		if (total < nodeGroups) return { 0, 0, 0, 0, 0 }; // every node group needs a warp
+		const size_t smem = flowSmemBytes(core, nb, nw, L, groups, nbt, subs);
+		if (smem > (smemMax + 1024) / ctas - 1024) return { 0, 0, 0, 0, 0 };
+		JitShape s = { nb, nbt, total / nodeGroups * nodeGroups, ctas, smem };
+		s.subs = subs;
+		return s;
+	}
+
 	int compileCandidate(pffrg_context *h, const pffrg_desc *d, JitCandidate &c)
 	{
-		RpaProgram prog = buildRpaProgram(d, h->core, c.shape.nbt, c.shape.rpaWarps);
+		RpaProgram prog = buildRpaProgram(d, h->core, c.shape.nbt * c.shape.subs, c.shape.rpaWarps);
 		applyJitKnobs(prog);
 		std::vector<char> cubin;
-		const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
+		const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, c.shape.subs, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the specialised flow kernel failed: %s", err.c_str());
 		CUDA_TRY(cudaLibraryLoadData(&c.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
 		CUDA_TRY(cudaLibraryGetKernel(&c.kernel, c.library, "pffrg_v4flow_jit"));
@@ -339,14 +355,14 @@ namespace
 	{
 		h->jitLibrary = c.library; h->jitKernel = c.kernel;
 		h->threads = c.threads; h->groups = c.groups;
-		h->nb = c.shape.nb; h->nbt = c.shape.nbt; h->rpaWarps = c.shape.rpaWarps; h->minBlocks = c.shape.minBlocks; h->smemBytes = c.shape.smem;
+		h->nb = c.shape.nb; h->nbt = c.shape.nbt; h->rpaWarps = c.shape.rpaWarps; h->minBlocks = c.shape.minBlocks; h->smemBytes = c.shape.smem; h->subs = c.shape.subs;
 	}
 
 	// Compile and load the lattice-specialised kernel. Controlled by the environment: PFFRG_JIT=0 disables it,
 	// PFFRG_JIT_MAX_TERMS (default 60000) bounds the straight-line code size (compile time grows with it).
 	// With PFFRG_AUTOTUNE=1 small lattices (<= PFFRG_AUTOTUNE_MAX_TERMS terms, default 12000: a few seconds of compilation per shape) are AUTOTUNED:
-	// up to three launch shapes (256-thread CTAs; 128-thread CTAs with the same RPA batch; 128-thread CTAs with two node groups,
-	// four per SM) are compiled and timed on a block of work items in the middle of the item range at a mid-mesh cutoff; the
+	// up to five launch shapes (256-thread CTAs; 128-thread CTAs with the same RPA batch; 128-thread CTAs with two node groups,
+	// four per SM; CTAs of four and of two 128-thread sub-CTAs, i.e. several work items sharing one RPA phase) are compiled and timed on a block of work items in the middle of the item range at a mid-mesh cutoff; the
 	// fastest stays. Which shape wins depends on the lattice (measured: cubic-r7 the third, honeycomb-r7 the second, by 3-6 %).
 	// Without it, or with an explicit shape override (PFFRG_JIT_NBT, PFFRG_THREADS), the first shape is used without timing.
 	int setupJit(pffrg_context *h, const pffrg_desc *d, size_t smemMax)
@@ -359,15 +375,26 @@ namespace
 		if (h->core == TRI) return PFFRG_OK; // TRI: table-driven RPA phase (rpaTri), precompiled kernels
 		const auto t0 = std::chrono::steady_clock::now();
 		std::vector<JitCandidate> candidates;
-		const JitShape first = chooseJitShape(h->core, h->nw, h->L, h->groups, h->threads / 32, smemMax);
+		JitShape first = chooseJitShape(h->core, h->nw, h->L, h->groups, h->threads / 32, smemMax);
 		if (!first.nb) return PFFRG_OK;
-		candidates.push_back({ h->threads, h->groups, first, nullptr, nullptr, 0.f });
+		int firstThreads = h->threads;
+		if (const char *e = getenv("PFFRG_SUBCTAS")) // explicit shape: PFFRG_SUBCTAS sub-CTAs of PFFRG_THREADS threads, PFFRG_JIT_NBT / PFFRG_JIT_NB per sub-CTA
+		{
+			const int subs = atoi(e);
+			if (subs > 1)
+			{
+				const JitShape fat = subCtaShape(h->core, h->nw, h->L, h->groups, h->threads / 32, subs, first.nbt, first.nb, getenv("PFFRG_JIT_MINBLOCKS") ? std::max(1, atoi(getenv("PFFRG_JIT_MINBLOCKS"))) : 1, smemMax);
+				if (!fat.nb) return fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_SUBCTAS=%d does not fit (shared memory / warps)", subs);
+				first = fat; firstThreads = h->threads * subs;
+			}
+		}
+		candidates.push_back({ firstThreads, h->groups, first, nullptr, nullptr, 0.f });
 		const long terms = (long)buildRpaProgram(d, h->core, first.nbt, first.rpaWarps).terms.size();
 		if (terms > maxTerms) return PFFRG_OK;
 		// opt-in: the shapes differ in summation order (last-bit differences), so a run that must be reproducible bit for bit across
 		// processes -- e.g. the sharded-vs-single-GPU comparison -- keeps the first shape
 		bool tune = false;
-		if (const char *e = getenv("PFFRG_AUTOTUNE")) tune = atoi(e) != 0 && terms <= tuneTerms && !getenv("PFFRG_JIT_NBT") && !getenv("PFFRG_THREADS") && !getenv("PFFRG_JIT_MINBLOCKS");
+		if (const char *e = getenv("PFFRG_AUTOTUNE")) tune = atoi(e) != 0 && terms <= tuneTerms && !getenv("PFFRG_JIT_NBT") && !getenv("PFFRG_THREADS") && !getenv("PFFRG_JIT_MINBLOCKS") && !getenv("PFFRG_SUBCTAS");
 		if (tune && h->threads > 128)
 		{
 			const int groups = std::max(1, 128 / h->stride), threads = std::max(64, (groups * h->stride + 31) / 32 * 32);
@@ -377,6 +404,14 @@ namespace
 				if (same.nb) candidates.push_back({ threads, groups, same, nullptr, nullptr, 0.f });
 				const JitShape small = smallCtaShape(h->core, h->nw, h->L, groups, threads / 32, smemMax);
 				if (small.nb) candidates.push_back({ threads, groups, small, nullptr, nullptr, 0.f });
+				// several items per CTA (sub-CTAs of 128 threads, 32 staged nodes each, sharing one RPA phase): four in one CTA per SM,
+				// two in two CTAs per SM (measured on B200: cubic-r7 20.2 -> 19.3 ms with 2 x 2, honeycomb-r7 XYZ 27.9 -> 26.2 ms with 4 x 1)
+				for (int subs : { 4, 2 })
+				{
+					JitShape fat = subCtaShape(h->core, h->nw, h->L, groups, threads / 32, subs, 32, 16, 4 / subs, smemMax);
+					if (!fat.nb && subs == 2) fat = subCtaShape(h->core, h->nw, h->L, groups, threads / 32, subs, 32, 16, 1, smemMax);
+					if (fat.nb) candidates.push_back({ threads * subs, groups, fat, nullptr, nullptr, 0.f });
+				}
 			}
 		}
 		for (JitCandidate &c : candidates) { const int rc = compileCandidate(h, d, c); if (rc != PFFRG_OK) return rc; }
@@ -409,7 +444,7 @@ namespace
 			CUDA_TRY(cudaStreamSynchronize(h->stream));
 			if (getenv("PFFRG_JIT_VERBOSE"))
 				for (size_t k = 0; k < candidates.size(); ++k)
-					fprintf(stderr, "[pffrg autotune] threads %d nb %d nbt %d rpa warps %d ctas %d smem %zu: %.3f ms%s\n", candidates[k].threads, candidates[k].shape.nb, candidates[k].shape.nbt,
+					fprintf(stderr, "[pffrg autotune] threads %d (%d sub-CTAs) nb %d nbt %d rpa warps %d ctas %d smem %zu: %.3f ms%s\n", candidates[k].threads, candidates[k].shape.subs, candidates[k].shape.nb, candidates[k].shape.nbt,
 						candidates[k].shape.rpaWarps, candidates[k].shape.minBlocks, candidates[k].shape.smem, candidates[k].ms, k == best ? "  <- selected" : "");
 		}
 		for (size_t k = 0; k < candidates.size(); ++k) if (k != best && candidates[k].library) cudaLibraryUnload(candidates[k].library);
@@ -1075,7 +1110,7 @@ int pffrg_get_stats(pffrg_handle h, pffrg_stats *out)
 	*out = h->stats;
 	out->jit_rpa = h->jitKernel ? 1 : 0;
 	out->jit_compile_ms = h->jitCompileMs;
-	out->threads = h->threads; out->smem_bytes = (int32_t)h->smemBytes; out->node_batch = h->nb; out->rpa_batch = h->jitKernel ? h->nbt : h->nb;
+	out->threads = h->threads; out->smem_bytes = (int32_t)h->smemBytes; out->node_batch = h->nb; out->rpa_batch = h->jitKernel ? h->nbt * h->subs : h->nb; out->sub_ctas = h->jitKernel ? h->subs : 1;
 	out->autotuned_shapes = h->autotuned;
 	out->rpa_warps = h->jitKernel ? h->rpaWarps : h->threads / 32; out->min_blocks = h->jitKernel ? h->minBlocks : (h->core == TRI ? 1 : 2);
 	return PFFRG_OK;
@@ -1090,12 +1125,19 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	const int L = d->n_sites;
 	const LaunchGeometry geo = chooseGeometry(L);
 	const int groups = geo.groups, threads = geo.threads;
-	const JitShape shape = chooseJitShape(d->core, d->n_frequencies, L, groups, threads / 32, 227 * 1024);
+	JitShape shape = chooseJitShape(d->core, d->n_frequencies, L, groups, threads / 32, 227 * 1024);
 	if (!shape.nb) return fail(PFFRG_ERR_UNSUPPORTED, "lattice too large for the specialised kernel");
-	RpaProgram prog = buildRpaProgram(d, d->core, shape.nbt, shape.rpaWarps);
+	int subs = 1;
+	if (const char *e = getenv("PFFRG_SUBCTAS")) subs = std::max(1, atoi(e));
+	if (subs > 1)
+	{
+		shape = subCtaShape(d->core, d->n_frequencies, L, groups, threads / 32, subs, shape.nbt, shape.nb, getenv("PFFRG_JIT_MINBLOCKS") ? std::max(1, atoi(getenv("PFFRG_JIT_MINBLOCKS"))) : 1, 227 * 1024);
+		if (!shape.nb) return fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_SUBCTAS=%d does not fit (shared memory / warps)", subs);
+	}
+	RpaProgram prog = buildRpaProgram(d, d->core, shape.nbt * shape.subs, shape.rpaWarps);
 	applyJitKnobs(prog);
 	std::vector<char> cubin;
-	const std::string err = compileFlowKernel(d->core, shape.nb, shape.nbt, threads, shape.minBlocks, KernelSizes{ L, paddedSites(L), channelsOf(d->core) * paddedSites(L), d->n_frequencies }, generateRpaSource(prog), cubin);
+	const std::string err = compileFlowKernel(d->core, shape.nb, shape.nbt, shape.subs, threads * shape.subs, shape.minBlocks, KernelSizes{ L, paddedSites(L), channelsOf(d->core) * paddedSites(L), d->n_frequencies }, generateRpaSource(prog), cubin);
 	if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
 	if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
 	return PFFRG_OK;

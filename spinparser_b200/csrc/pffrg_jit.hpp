@@ -32,6 +32,7 @@ namespace pffrg
 	struct KernelSizes { int L, Lp, RL, nw; }; // baked into the run-time compiled kernel as constants
 
 	// compile the vertex-flow kernel (embedded source + the generated RPA function) for sm_100a; returns an empty string on
-	// success and the compiler log otherwise. The kernel is `pffrg_v4flow_jit` with v4FlowKernel's parameter list.
-	std::string compileFlowKernel(int core, int nb, int nbt, int threads, int minBlocks, const KernelSizes &sizes, const std::string &rpaSource, std::vector<char> &cubin);
+	// success and the compiler log otherwise. The kernel is `pffrg_v4flow_jit` with v4FlowKernel's parameter list; `nbt` = nodes
+	// staged per RPA phase by each of the `subs` sub-CTAs of a CTA, `threads` = threads of the whole CTA.
+	std::string compileFlowKernel(int core, int nb, int nbt, int subs, int threads, int minBlocks, const KernelSizes &sizes, const std::string &rpaSource, std::vector<char> &cubin);
 }

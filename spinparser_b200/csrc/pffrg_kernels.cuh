@@ -269,17 +269,26 @@ namespace pffrg
 	//               with NVRTC (pffrg_jit.cpp); operands are cached in registers, multiplicities are immediates
 	//   epilogue  deterministic reduction over groups, 1/2pi, NaN flag, coalesced store of the item's C x L flow values
 	// ================================================================================================================
-#ifndef PFFRG_MIRROR
-#define PFFRG_MIRROR 1 // t channel: form buffers 2, 3 from the rows loaded for buffers 0, 1 (gatherMirrored); 0 only in A/B timing runs of the run-time compiled kernel
-#endif
-
 	struct FlowConfig
 	{
 		int groups;      // k
 		int stride;      // threads per group: L, or L rounded up to whole warps
 		int nslots;      // RPA slots of the generic phase 2 = warps * (32 / NB)
 		int smemBytes;
+		int items;       // work items of this launch (a CTA of SUB sub-CTAs covers SUB consecutive items; the last one may be partial)
 	};
+
+	// barrier over sub-CTA `sub` (threads a multiple of 32) of a CTA made of several sub-CTAs: named barriers 1..4
+	__device__ __forceinline__ void subCtaSync(int sub, int threads)
+	{
+		switch (sub)
+		{
+		case 0: asm volatile("bar.sync 1, %0;" :: "r"(threads) : "memory"); break;
+		case 1: asm volatile("bar.sync 2, %0;" :: "r"(threads) : "memory"); break;
+		case 2: asm volatile("bar.sync 3, %0;" :: "r"(threads) : "memory"); break;
+		default: asm volatile("bar.sync 4, %0;" :: "r"(threads) : "memory"); break;
+		}
+	}
 
 	template <int CORE> struct RpaStage { static constexpr int buffers = (CORE == TRI) ? 4 : 2; };
 
@@ -304,10 +313,12 @@ namespace pffrg
 	{
 		static constexpr int C = channelsOf(CORE);
 		static constexpr int NBP = NB + 1;
-		size_t mesh, bw, bW, lerp, ab, loc, wmat, st, part, rpa, total;
+		size_t mesh, bw, bW, lerp, ab, loc, wmat, privateBytes, st, part, partStride, rpa, staged, total;
 		int rpaCopies;
-		// nbt = nodes staged per RPA phase (a multiple of NB; NB itself in the precompiled kernels)
-		__host__ __device__ FlowSmem(int nw, int L, int groups, int nbt = NB)
+		// nbt = nodes staged per RPA phase and sub-CTA (a multiple of NB; NB itself in the precompiled kernels); subs = sub-CTAs
+		// per CTA (run-time compiled kernel only): each has its own tables (offsets below are relative to its private block of
+		// privateBytes), all share ONE staging area of subs * nbt nodes and one RPA phase
+		__host__ __device__ FlowSmem(int nw, int L, int groups, int nbt = NB, int subs = 1)
 		{
 			size_t o = 0;
 			mesh = o; o += sizeof(double) * nw;
@@ -320,159 +331,96 @@ namespace pffrg
 			o = alignUp(o, 16);
 			wmat = o; o += (CORE == TRI) ? sizeof(double) * NB * 4 * 32 : 0; // TRI: contracted site-0 matrices, see triLocalMatrices
 			o = alignUp(o, 16);
+			privateBytes = o; o *= subs;
 			// the per-group partial sums of the epilogue reuse the staging area (dead by then)
-			const size_t stBytes = (CORE == TRI && NB == 8) ? sizeof(double) * 4 * tri8BufferStride(L) : sizeof(double) * RpaStage<CORE>::buffers * C * L * (nbt + 1);
-			const size_t partBytes = sizeof(double) * groups * C * L;
+			const size_t stBytes = (CORE == TRI && NB == 8) ? sizeof(double) * 4 * tri8BufferStride(L) : sizeof(double) * RpaStage<CORE>::buffers * C * L * (subs * nbt + 1);
+			partStride = sizeof(double) * groups * C * L;
+			const size_t partBytes = partStride * subs;
 			st = o; part = o; o += stBytes > partBytes ? stBytes : partBytes;
 			// one copy of the RPA outputs per node group of the specialised code (16 nodes for SU2, which runs its two channels as
 			// lane halves, 32 otherwise): single writer per address, summed in the epilogue
-			rpaCopies = nbt / (CORE == SU2 ? 16 : 32); if (rpaCopies < 2) rpaCopies = 2;
+			rpaCopies = subs * nbt / (CORE == SU2 ? 16 : 32); if (rpaCopies < 2) rpaCopies = 2;
 			rpa = o; o += sizeof(double) * C * L * rpaCopies;
+			staged = o; if (subs > 1) o += sizeof(int) * 4; // nodes staged by each sub-CTA for the coming RPA phase
 			total = alignUp(o, 16);
 		}
 	};
 
 	// gather one access buffer for site j: out[c] = sum_k sign_k(c) w_k v4[row_k][stored(c)][site]
-	// SU2 / XYZ: split into the loads (RawSupports: the channel pairs of the four support rows at the site) and the weighted
-	// combination, so that a second buffer reading the same rows can be formed without loading again (gatherMirrored).
-	template <int CORE> struct RawSupports { double2 v[4][CORE == XYZ ? 2 : 1]; };
-
-	struct AccessHeader
-	{
-		double wk[4], ok[4];
-		int rk[4];
-		int flags;
-		__device__ __forceinline__ explicit AccessHeader(const AccessBuffer &ab)
-		{
-			// the table entry is 16-byte aligned: 128-bit shared loads
-			const double2 w01 = *reinterpret_cast<const double2 *>(&ab.w[0]), w23 = *reinterpret_cast<const double2 *>(&ab.w[2]);
-			const int4 rows = *reinterpret_cast<const int4 *>(&ab.row[0]);
-			flags = ab.flags;
-			wk[0] = w01.x; wk[1] = w01.y; wk[2] = w23.x; wk[3] = w23.y;
-			ok[0] = oddWeight(w01.x, flags, 0); ok[1] = oddWeight(w01.y, flags, 1); ok[2] = oddWeight(w23.x, flags, 2); ok[3] = oddWeight(w23.y, flags, 3);
-			rk[0] = rows.x; rk[1] = rows.y; rk[2] = rows.z; rk[3] = rows.w;
-		}
-	};
-
 	template <int CORE>
-	__device__ __forceinline__ void loadSupports(const Problem &P, const double *__restrict__ v4, const AccessHeader &h, int site, RawSupports<CORE> &raw)
+	__device__ __forceinline__ void gatherSite(const Problem &P, const double *__restrict__ v4, const AccessBuffer &ab, int siteFwd, int siteInv, int permFwd, int permInv, double (&out)[channelsOf(CORE)])
 	{
-		#pragma unroll
-		for (int k = 0; k < 4; ++k)
-		{
-			const double2 *base = reinterpret_cast<const double2 *>(v4 + (size_t)((unsigned)h.rk[k] * (unsigned)sizeRL(P) + 2u * (unsigned)site));
-			raw.v[k][0] = __ldg(base);
-			if constexpr (CORE == XYZ) raw.v[k][1] = __ldg(base + sizeLp(P));
-		}
-	}
-
-	// weighted combination of the supports in the order k = 0..3 of THIS buffer; support k reads raw.v[MIRROR ? {0,2,1,3}[k] : k]
-	template <int CORE, bool MIRROR>
-	__device__ __forceinline__ void combineSupports(const AccessHeader &h, const RawSupports<CORE> &raw, int perm, double (&out)[channelsOf(CORE)])
-	{
+		constexpr int C = channelsOf(CORE);
+		// the table entry is 16-byte aligned: 128-bit shared loads
+		const double2 w01 = *reinterpret_cast<const double2 *>(&ab.w[0]), w23 = *reinterpret_cast<const double2 *>(&ab.w[2]);
+		const int4 rows = *reinterpret_cast<const int4 *>(&ab.row[0]);
+		const int flags = ab.flags;
+		const double wk[4] = { w01.x, w01.y, w23.x, w23.y };
+		const double ok[4] = { oddWeight(w01.x, flags, 0), oddWeight(w01.y, flags, 1), oddWeight(w23.x, flags, 2), oddWeight(w23.y, flags, 3) };
+		const int rk[4] = { rows.x, rows.y, rows.z, rows.w };
+		const bool exchange = flags & AB_EXCHANGE;
+		const int site = exchange ? siteInv : siteFwd;
+		const int perm = exchange ? permInv : permFwd;
 		if constexpr (CORE == SU2)
 		{
-			// {spin, density} of the site; only the density channel is odd under s<->u (SU2VertexTwoParticle.hpp:622-625)
+			// one 16-byte load per support: {spin, density} of the site
 			out[0] = 0.0; out[1] = 0.0;
 			#pragma unroll
 			for (int k = 0; k < 4; ++k)
 			{
-				const double2 v = raw.v[MIRROR ? ((k == 1) ? 2 : (k == 2) ? 1 : k) : k][0];
-				out[0] += h.wk[k] * v.x;
-				out[1] += h.ok[k] * v.y;
+				const double2 v = __ldg(reinterpret_cast<const double2 *>(v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + 2u * (unsigned)site)));
+				out[0] += wk[k] * v.x;
+				out[1] += ok[k] * v.y; // only the density channel is odd under s<->u (SU2VertexTwoParticle.hpp:622-625)
 			}
 		}
-		else
+		else if constexpr (CORE == XYZ)
 		{
-			// stored {x, y} and {z, density}; the site's spin permutation (XYZVertexTwoParticle.hpp:401-404) is applied once to the
-			// interpolated values (all three spin channels carry the same weights)
-			double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+			// two 16-byte loads per support: stored {x, y} and {z, density}; the site's spin permutation (XYZVertexTwoParticle.hpp:401-404)
+			// is applied once to the interpolated values (all three spin channels carry the same weights)
+			double raw[4] = { 0.0, 0.0, 0.0, 0.0 };
 			#pragma unroll
 			for (int k = 0; k < 4; ++k)
 			{
-				const int kk = MIRROR ? ((k == 1) ? 2 : (k == 2) ? 1 : k) : k;
-				const double2 xy = raw.v[kk][0], zd = raw.v[kk][CORE == XYZ ? 1 : 0];
-				acc[0] += h.wk[k] * xy.x; acc[1] += h.wk[k] * xy.y; acc[2] += h.wk[k] * zd.x;
-				acc[3] += h.ok[k] * zd.y;
+				const double2 *base = reinterpret_cast<const double2 *>(v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + 2u * (unsigned)site));
+				const double2 xy = __ldg(base), zd = __ldg(base + sizeLp(P));
+				raw[0] += wk[k] * xy.x; raw[1] += wk[k] * xy.y; raw[2] += wk[k] * zd.x;
+				raw[3] += ok[k] * zd.y;
 			}
 			#pragma unroll
 			for (int c = 0; c < 3; ++c)
 			{
 				const int sc = (perm >> (2 * c)) & 3;
-				out[c] = sc == 0 ? acc[0] : (sc == 1 ? acc[1] : acc[2]);
+				out[c] = sc == 0 ? raw[0] : (sc == 1 ? raw[1] : raw[2]);
 			}
-			out[3] = acc[3];
-		}
-	}
-
-	template <int CORE>
-	__device__ __forceinline__ void gatherSite(const Problem &P, const double *__restrict__ v4, const AccessBuffer &ab, int siteFwd, int siteInv, int permFwd, int permInv, double (&out)[channelsOf(CORE)])
-	{
-		constexpr int C = channelsOf(CORE);
-		if constexpr (CORE != TRI)
-		{
-			const AccessHeader h(ab);
-			const bool exchange = h.flags & AB_EXCHANGE;
-			RawSupports<CORE> raw;
-			loadSupports<CORE>(P, v4, h, exchange ? siteInv : siteFwd, raw);
-			combineSupports<CORE, false>(h, raw, exchange ? permInv : permFwd, out);
+			out[3] = raw[3];
 		}
 		else
 		{
-			const AccessHeader h(ab);
-			const int flags = h.flags;
-			const bool exchange = flags & AB_EXCHANGE;
-			const int site = exchange ? siteInv : siteFwd;
-			const int perm = exchange ? permInv : permFwd;
 			#pragma unroll
 			for (int c = 0; c < C; ++c) out[c] = 0.0;
 			#pragma unroll
 			for (int k = 0; k < 4; ++k)
 			{
-				const double *base = v4 + (size_t)((unsigned)h.rk[k] * (unsigned)sizeRL(P) + (unsigned)site);
+				const double *base = v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + (unsigned)site);
 				#pragma unroll
 				for (int c = 0; c < C; ++c)
 				{
 					// factor -zeta of the second (first, if exchanged) spin index where the mirrored entry is read
 					// (TRIVertexTwoParticle.hpp:649-657), i.e. the weight is odd iff that index is the density one
 					const int sc = storedChannel<CORE>(flags, c, perm);
-					const double w = (exchange ? ((c >> 2) == 3) : ((c & 3) == 3)) ? h.ok[k] : h.wk[k];
+					const double w = (exchange ? ((c >> 2) == 3) : ((c & 3) == 3)) ? ok[k] : wk[k];
 					out[c] += w * __ldg(base + sc * sizeLp(P));
 				}
 			}
+		}
+		if (CORE == TRI)
+		{
 			// zeta_mu * zeta_nu for every sign change of t or u (TRIVertexTwoParticle.hpp:414-443): flips exactly the mixed spin-density channels
 			if (flags & AB_TZ)
 			{
 				#pragma unroll
 				for (int c = 0; c < C; ++c) if (((c >> 2) == 3) != ((c & 3) == 3)) out[c] = -out[c];
 			}
-		}
-	}
-
-	// The t channel's gathered buffers come in mirrored pairs: buffer 2 is buffer 0 with the s and u arguments exchanged, and
-	// buffer 3 is buffer 1 with (s, u) -> (-u, -s) (src/SU2/SU2FrgCore.cpp:233-239). Only s >= u is stored, so both members of
-	// a pair read the SAME four rows at the same sites -- supports 1 and 2 trade places, the weights and the mirror flags are
-	// the pair member's own. Whenever that holds (checked on the assembled tables, so it is a pure load elision: the values
-	// combined are bit-identical to what a second set of loads would return) the second buffer is formed from the first one's
-	// registers; otherwise it is gathered normally.
-	template <int CORE>
-	__device__ __forceinline__ void gatherMirrored(const Problem &P, const double *__restrict__ v4, const AccessBuffer &abFirst, const AccessBuffer &abSecond, int siteFwd, int siteInv, int permFwd, int permInv,
-		double (&outFirst)[channelsOf(CORE)], double (&outSecond)[channelsOf(CORE)])
-	{
-		static_assert(CORE != TRI, "the TRI core gathers single channels");
-		const AccessHeader h0(abFirst), h1(abSecond);
-		const bool exchange = h0.flags & AB_EXCHANGE;
-		const int site = exchange ? siteInv : siteFwd, perm = exchange ? permInv : permFwd;
-		RawSupports<CORE> raw;
-		loadSupports<CORE>(P, v4, h0, site, raw);
-		combineSupports<CORE, false>(h0, raw, perm, outFirst);
-		const bool same = ((h0.flags ^ h1.flags) & AB_EXCHANGE) == 0 && h1.rk[0] == h0.rk[0] && h1.rk[1] == h0.rk[2] && h1.rk[2] == h0.rk[1] && h1.rk[3] == h0.rk[3];
-		if (same) combineSupports<CORE, true>(h1, raw, perm, outSecond);
-		else
-		{
-			const bool exchange1 = h1.flags & AB_EXCHANGE;
-			loadSupports<CORE>(P, v4, h1, exchange1 ? siteInv : siteFwd, raw);
-			combineSupports<CORE, false>(h1, raw, exchange1 ? permInv : permFwd, outSecond);
 		}
 	}
 
@@ -1082,31 +1030,46 @@ namespace pffrg
 		}
 	}
 
-	template <int CORE, int NB, int NBT, bool JIT>
+	// SUB > 1 (run-time compiled kernel only): the CTA is made of SUB independent sub-CTAs, each working on its own item
+	// (consecutive items) with its own tables and its own barriers; they meet only for the RPA phase, which then runs ONE pass
+	// of the straight-line code over the nodes staged by all of them. The code of that phase is streamed through the
+	// instruction caches once per pass (it is larger than the 32 KB per-SM instruction cache), and the GPC-level instruction
+	// cache that serves those misses is what limits the kernel on small lattices (ncu: gcc__cache_requests_type_instruction at
+	// 99 % of peak on cubic-r7 with one item per CTA) -- SUB items per pass divide that traffic by SUB.
+	template <int CORE, int NB, int NBT, bool JIT, int SUB = 1>
 	__device__ __forceinline__ void v4FlowBody(const Problem &P, const NodeTable &N, const FlowConfig &cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
 	{
 		constexpr int C = channelsOf(CORE);
-		constexpr int NBP = NBT + 1; // node stride of the RPA staging area
+		constexpr int NBTT = NBT * SUB; // nodes staged per RPA phase by the whole CTA
+		constexpr int NBP = NBTT + 1;   // node stride of the RPA staging area
 		static_assert(NBT % NB == 0 && (JIT || NBT == NB), "the precompiled kernels stage one gather batch per RPA phase");
+		static_assert(SUB >= 1 && SUB <= 4 && (SUB == 1 || JIT), "sub-CTAs exist in the run-time compiled kernel only");
 		extern __shared__ __align__(16) unsigned char smemRaw[];
-		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT);
-		double *mesh = reinterpret_cast<double *>(smemRaw + lay.mesh);
-		double *bW = reinterpret_cast<double *>(smemRaw + lay.bW);
-		LerpRecord *lerp = reinterpret_cast<LerpRecord *>(smemRaw + lay.lerp);
-		AccessBuffer *abTable = reinterpret_cast<AccessBuffer *>(smemRaw + lay.ab);
-		double *loc = reinterpret_cast<double *>(smemRaw + lay.loc);
-		double *wmat = reinterpret_cast<double *>(smemRaw + lay.wmat);
+		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT, SUB);
+		const int nthreads = blockDim.x / SUB;                       // threads of one sub-CTA
+		const int sub = SUB == 1 ? 0 : threadIdx.x / nthreads;
+		const int tid = threadIdx.x - sub * nthreads;
+		unsigned char *priv = smemRaw + sub * lay.privateBytes;
+		double *mesh = reinterpret_cast<double *>(priv + lay.mesh);
+		double *bW = reinterpret_cast<double *>(priv + lay.bW);
+		LerpRecord *lerp = reinterpret_cast<LerpRecord *>(priv + lay.lerp);
+		AccessBuffer *abTable = reinterpret_cast<AccessBuffer *>(priv + lay.ab);
+		double *loc = reinterpret_cast<double *>(priv + lay.loc);
+		double *wmat = reinterpret_cast<double *>(priv + lay.wmat);
 		double *st = reinterpret_cast<double *>(smemRaw + lay.st);
-		double *part = reinterpret_cast<double *>(smemRaw + lay.part);
+		double *part = reinterpret_cast<double *>(smemRaw + lay.part + sub * lay.partStride);
 		double *rpaOut = reinterpret_cast<double *>(smemRaw + lay.rpa);
+		int *stagedCount = reinterpret_cast<int *>(smemRaw + lay.staged);
+		auto subSync = [&]() { if (SUB == 1) __syncthreads(); else subCtaSync(sub, nthreads); };
 
-		const int tid = threadIdx.x, nthreads = blockDim.x;
 		const int L = sizeL(P), nw = sizeNw(P);
 		for (int i = tid; i < nw; i += nthreads) mesh[i] = P.mesh[i];
-		for (int i = tid; i < lay.rpaCopies * C * L; i += nthreads) rpaOut[i] = 0.0;
+		for (int i = threadIdx.x; i < lay.rpaCopies * C * L; i += blockDim.x) rpaOut[i] = 0.0;
 
 		// work item -> (s, t, u), expandIterator SU2VertexTwoParticle.hpp:136-158
-		const int item = itemBegin + blockIdx.x;
+		const int itemFirst = itemBegin + blockIdx.x * SUB, itemEnd = itemBegin + cfg.items;
+		const bool valid = SUB == 1 || itemFirst + sub < itemEnd; // a sub-CTA past the end only takes part in the CTA barriers
+		const int item = valid ? itemFirst + sub : itemEnd - 1;
 		const int su = item / nw, ti = item - su * nw;
 		int so = (int)((sqrt(8.0 * su + 1.0) - 1.0) * 0.5);
 		while ((so + 1) * (so + 2) / 2 <= su) ++so;
@@ -1133,7 +1096,7 @@ namespace pffrg
 		{
 			const bool tPass = pass == 1;
 			const int nFirst = N.count[tPass ? ti : so];               // nodes of the s (or t) channel
-			const int nNodes = tPass ? nFirst : nFirst + N.count[uo];  // ... followed by those of the u channel
+			const int nNodes = !valid ? 0 : (tPass ? nFirst : nFirst + N.count[uo]);  // ... followed by those of the u channel
 			const double *nodeW0 = N.wp + (size_t)(tPass ? ti : so) * N.stride, *nodeWt0 = N.wt + (size_t)(tPass ? ti : so) * N.stride;
 			const double *nodeW1 = N.wp + (size_t)uo * N.stride, *nodeWt1 = N.wt + (size_t)uo * N.stride;
 			const int nbuf = tPass ? 8 : 4;
@@ -1141,15 +1104,29 @@ namespace pffrg
 			const int batchMax = tPass ? NB : 2 * NB;
 			// (not in the run-time compiled kernel: its RPA phase costs the same for any number of staged nodes, so NBT is filled exactly)
 			const int batch = (!JIT && cfg.groups <= batchMax) ? batchMax / cfg.groups * cfg.groups : batchMax;
-			int staged = 0; // t channel: nodes staged for the next RPA phase
+			// t channel: the nodes are worked off in rounds of `round` nodes (consecutive gather batches are staged side by side, up to
+			// NBT nodes), each followed by one RPA phase; all sub-CTAs of a CTA run the same number of rounds (CTA barriers)
+			const int round = JIT ? NBT : batch;
+			int rounds = 1;
+			if (tPass)
+			{
+				rounds = (nNodes + round - 1) / round;
+				if (SUB > 1)
+					for (int h = 0; h < SUB; ++h)
+						if (itemFirst + h < itemEnd) rounds = max(rounds, (N.count[(itemFirst + h) % nw] + round - 1) / round);
+			}
+			#pragma unroll 1
+			for (int rd = 0; rd < rounds; ++rd)
+			{
+			const int lo = tPass ? rd * round : 0, hi = tPass ? min(nNodes, lo + round) : nNodes;
+			int staged = 0; // t channel: nodes staged for the coming RPA phase
 
 			#pragma unroll 1
-			for (int b0 = 0; b0 < nNodes; b0 += batch)
+			for (int b0 = lo; b0 < hi; b0 += batch)
 			{
-				const int nb = min(batch, nNodes - b0);
-				// t channel: consecutive gather batches are staged side by side (up to NBT nodes) before one RPA phase runs over all of them
-				const int stageOff = staged;
-				__syncthreads(); // previous batch fully consumed
+				const int nb = min(batch, hi - b0);
+				const int stageOff = sub * NBT + staged;
+				subSync(); // previous batch fully consumed
 				// ---- phase 0: access buffers. Step A: the four interpolated frequencies of every node (one mesh search each)
 				for (int idx = tid; idx < nb * 4; idx += nthreads)
 				{
@@ -1165,7 +1142,7 @@ namespace pffrg
 					}
 					makeLerpRecord(mesh, nw, P.meshIndex, nodeQuantity(ch, q, f.w1p, f.w1, f.w2p, f.w2, wp), lerp[idx]);
 				}
-				__syncthreads();
+				subSync();
 				// step B: assemble the buffers (sector map, weights, rows) from two records each
 				for (int idx = tid; idx < nb * nbuf; idx += nthreads)
 				{
@@ -1173,7 +1150,7 @@ namespace pffrg
 					const int ch = tPass ? CH_T : ((b0 + node) < nFirst ? CH_S : CH_U);
 					assembleAccessBuffer<CORE>(nw, ch, b, ch == CH_S ? so : (ch == CH_T ? ti : uo), lerp + 4 * node, abTable[idx]);
 				}
-				__syncthreads();
+				subSync();
 				if (tPass)
 				{
 					// ---- phase 0b: site-0 values of buffers 4..7 (getValueLocal)
@@ -1190,7 +1167,7 @@ namespace pffrg
 						for (int k = 0; k < 4; ++k) v += supportSign<CORE>(ab.flags, k, cs) * ab.w[k] * __ldg(v4 + (size_t)ab.row[k] * sizeRL(P) + channelOffset(vectorWidth(CORE), sc, sizeLp(P)));
 						loc[idx] = v;
 					}
-					__syncthreads();
+					subSync();
 					if (CORE == TRI)
 					{
 						for (int idx = tid; idx < nb * 4 * 32; idx += nthreads)
@@ -1198,7 +1175,7 @@ namespace pffrg
 							const int node = idx >> 7, n = (idx >> 5) & 3;
 							triLocalMatrices(loc + (node * 4 + n) * 16, (n & 1) != 0, wmat + (node * 4 + n) * 32, idx & 31);
 						}
-						__syncthreads();
+						subSync();
 					}
 				}
 				// ---- phase 1: gathers + bilinear forms
@@ -1211,17 +1188,8 @@ namespace pffrg
 					for (int node = g; node < nb; node += cfg.groups)
 					{
 						double A[4][C];
-						if (tPass && PFFRG_MIRROR)
-						{
-							// buffers (0, 2) and (1, 3) read the same rows, see gatherMirrored
-							gatherMirrored<CORE>(P, v4, abTable[node * nbuf + 0], abTable[node * nbuf + 2], siteFwd, siteInv, permFwd, permInv, A[0], A[2]);
-							gatherMirrored<CORE>(P, v4, abTable[node * nbuf + 1], abTable[node * nbuf + 3], siteFwd, siteInv, permFwd, permInv, A[1], A[3]);
-						}
-						else
-						{
-							#pragma unroll
-							for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, abTable[node * nbuf + b], siteFwd, siteInv, permFwd, permInv, A[b]);
-						}
+						#pragma unroll
+						for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, abTable[node * nbuf + b], siteFwd, siteInv, permFwd, permInv, A[b]);
 						const double W = bW[node];
 						double K[C];
 						if (!tPass)
@@ -1266,35 +1234,44 @@ namespace pffrg
 					}
 				}
 				if (tPass) staged += nb;
-				if (tPass && (staged + batch > NBT || b0 + batch >= nNodes))
-				{
-					__syncthreads();
-					// ---- phase 2: RPA lattice sum over the staged nodes
+			}
+			if (tPass)
+			{
+				if (SUB > 1 && tid == 0) stagedCount[sub] = staged;
+				__syncthreads();
+				// ---- phase 2: RPA lattice sum over the staged nodes (of all sub-CTAs)
 #ifdef PFFRG_JIT_RPA
-					if (JIT) rpaSpecialised(tid >> 5, tid & 31, staged, st, rpaOut);
-					else
-#endif
-					if constexpr (CORE == TRI && NB == 8) rpaTri8(P, st, rpaOut, tid, staged);
-					else if constexpr (CORE == TRI) rpaTri<NB>(P, cfg, st, rpaOut, tid, staged);
-					else rpaGeneric<CORE, NB>(P, cfg, st, rpaOut, tid, staged);
-					staged = 0;
+				if (JIT)
+				{
+					// node group of this warp -> the sub-CTA whose nodes it works on: columns [h * NBT, h * NBT + staged_h) are live
+					constexpr int LPV = CORE == SU2 ? 16 : 32;
+					const int warp = threadIdx.x >> 5, h = SUB == 1 ? 0 : (warp % (NBTT / LPV)) / (NBT / LPV);
+					rpaSpecialised(warp, threadIdx.x & 31, SUB == 1 ? staged : h * NBT + stagedCount[h], st, rpaOut);
+					if (SUB > 1) __syncthreads(); // a faster sub-CTA may start staging its next round right away
 				}
+				else
+#endif
+				if constexpr (CORE == TRI && NB == 8) rpaTri8(P, st, rpaOut, tid, staged);
+				else if constexpr (CORE == TRI) rpaTri<NB>(P, cfg, st, rpaOut, tid, staged);
+				else rpaGeneric<CORE, NB>(P, cfg, st, rpaOut, tid, staged);
+			}
 			}
 		}
 
-		// ---- epilogue
-		__syncthreads();
+		// ---- epilogue (per sub-CTA: its own partial sums and the RPA output copies of its own node groups)
+		subSync();
 		if (worker)
 		{
 			#pragma unroll
 			for (int c = 0; c < C; ++c) part[(g * C + c) * L + j] = acc[c];
 		}
-		__syncthreads();
+		subSync();
 		bool bad = false;
-		for (int e = tid; e < C * L; e += nthreads)
+		const int copies = lay.rpaCopies / SUB, copy0 = sub * copies;
+		for (int e = tid; valid && e < C * L; e += nthreads)
 		{
 			double v = 0.0;
-			for (int k = 0; k < lay.rpaCopies; ++k) v += rpaOut[k * C * L + e];
+			for (int k = copy0; k < copy0 + copies; ++k) v += rpaOut[k * C * L + e];
 			for (int gg = 0; gg < cfg.groups; ++gg) v += part[gg * C * L + e];
 			v /= TWO_PI;
 			const int c = e / L, jj = e - c * L;

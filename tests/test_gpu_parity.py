@@ -21,13 +21,18 @@ def _core(d):
 # (PFFRG_JIT=0) and their smaller gather batches (PFFRG_NB; NB = 8 selects the TRI core's rpaTri8 phase, which large
 # lattices use)
 VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16"}, {"PFFRG_AUTOTUNE": "1"},
-            {"PFFRG_THREADS": "128", "PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16", "PFFRG_JIT_MINBLOCKS": "4"}]
+            {"PFFRG_THREADS": "128", "PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16", "PFFRG_JIT_MINBLOCKS": "4"},
+            # several work items per CTA (sub-CTAs sharing one RPA phase): 2, 3 and 4 items, a partial last CTA (550 items), and with
+            # 16 nodes per round several RPA rounds per item with sub-CTAs that run out of nodes at different times
+            {"PFFRG_SUBCTAS": "2", "PFFRG_THREADS": "128", "PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16", "PFFRG_JIT_MINBLOCKS": "2"},
+            {"PFFRG_SUBCTAS": "4", "PFFRG_THREADS": "128", "PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16"},
+            {"PFFRG_SUBCTAS": "3", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}]
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
 @pytest.mark.parametrize("case", CASES)
 def test_one_step_flow_matches_reference(case, variant, monkeypatch):
-    if case.startswith("tri") and ("PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant):
+    if case.startswith("tri") and ("PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant or "PFFRG_SUBCTAS" in variant):
         pytest.skip("the TRI core has no run-time compiled variant")
     for k, x in variant.items():
         monkeypatch.setenv(k, x)

@@ -11,7 +11,7 @@ while [ $# -gt 0 ]; do
   case "$1" in
     --tests)
       shift
-      python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/${TAG}_pytest_gpu.log
+      python -m pytest tests -m gpu -x -q --timeout 180 > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/${TAG}_pytest_gpu.log
       ;;
     --sweep)
       WL=$2; shift 2

@@ -6,7 +6,7 @@ TAG=$1; WL=$2; shift 2
 mkdir -p gpurun_out
 OUT=gpurun_out/${TAG}_sweep_${WL}.txt
 for cfg in "$@"; do
-  env $cfg timeout 900 python bench.py --workload $WL --steps 3 --warmup 3 --synthetic-state --no-cpu-baseline --e2e-steps 0 2> gpurun_out/${TAG}_sweep.err | python -c "
+  env $cfg timeout ${SWEEP_TIMEOUT:-900} python bench.py --workload $WL --steps 3 --warmup 3 --synthetic-state --no-cpu-baseline --e2e-steps 0 2> gpurun_out/${TAG}_sweep.err | python -c "
 import json,sys
 try:
     d=json.loads(sys.stdin.read().strip().splitlines()[-1])
