@@ -136,7 +136,7 @@ struct pffrg_context
 	int nodeStride = 0;
 
 	// launch configuration of the flow kernel
-	int nb = 32, nbt = 32, rpaWarps = 8, minBlocks = 2, groups = 1, stride = 1, threads = 32, nslots = 1, subs = 1; size_t smemBytes = 0;
+	int nb = 32, nbt = 32, rpaWarps = 8, minBlocks = 2, groups = 1, stride = 1, threads = 32, nslots = 1, subs = 1, cluster = 1; size_t smemBytes = 0;
 	// (run-time compiled kernel: `threads` = all threads of a CTA = subs sub-CTAs of groups * stride threads (rounded to warps), nbt = nodes per RPA phase and sub-CTA)
 
 	cudaStream_t stream = nullptr;
@@ -212,7 +212,7 @@ namespace
 	// warps (one per SM sub-partition when there are four), each on its own group of 16 (SU2) or 32 staged nodes, so the
 	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Environment overrides for tuning runs:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_TILES, PFFRG_JIT_MINBLOCKS.
-	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; };
+	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; };
 	JitShape chooseJitShape(int core, int nw, int L, int groups, int warps, size_t smemMax)
 	{
 		const int lanes = core == SU2 ? 16 : 32;
@@ -282,12 +282,17 @@ namespace
 		return g;
 	}
 
+	// outputs accumulated in registers at a time: 16 when the kernel has the whole register file of an SM for 256 threads (255
+	// registers per thread; pyrochlore-r8: 273 -> 241 ms, fewer operand loads and a shorter instruction stream), else 8
+	int defaultAccumulators(int threads, int minBlocks) { return threads * minBlocks <= 256 ? 16 : 8; }
+
 	// tuning knobs of the generated RPA code (defaults chosen on B200)
 	void applyJitKnobs(RpaProgram &prog)
 	{
 		if (const char *e = getenv("PFFRG_JIT_CHUNK")) prog.chunk = std::max(4, atoi(e));
 		if (const char *e = getenv("PFFRG_JIT_ACC")) prog.maxAccumulators = std::max(1, atoi(e));
 		if (const char *e = getenv("PFFRG_JIT_PREFETCH")) prog.prefetch = std::max(1, atoi(e));
+		if (const char *e = getenv("PFFRG_JIT_RESYNC")) prog.resync = atoi(e) != 0;
 	}
 
 	cudaError_t launchFlowDispatch(pffrg_context *h, int64_t begin, int64_t count)
@@ -299,7 +304,8 @@ namespace
 			FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes; cfg.items = (int)count;
 			const double *v4 = h->dV4.p; double *flow = h->dFlow4.p; int itemBegin = (int)begin; int *nan = h->dNan.p;
 			void *args[] = { &P, &N, &cfg, &v4, &flow, &itemBegin, &nan };
-			return cudaLaunchKernel((const void *)h->jitKernel, dim3((unsigned)((count + h->subs - 1) / h->subs)), dim3(h->threads), args, h->smemBytes, h->stream);
+			const int64_t ctas = (count + h->subs - 1) / h->subs; // padded to whole clusters (the kernel carries __cluster_dims__)
+			return cudaLaunchKernel((const void *)h->jitKernel, dim3((unsigned)((ctas + h->cluster - 1) / h->cluster * h->cluster)), dim3(h->threads), args, h->smemBytes, h->stream);
 		}
 		if (h->core == SU2) return h->nb == 32 ? launchFlow<SU2, 32>(h, begin, count) : h->nb == 16 ? launchFlow<SU2, 16>(h, begin, count) : launchFlow<SU2, 8>(h, begin, count);
 		if (h->core == XYZ) return h->nb == 32 ? launchFlow<XYZ, 32>(h, begin, count) : h->nb == 16 ? launchFlow<XYZ, 16>(h, begin, count) : launchFlow<XYZ, 8>(h, begin, count);
@@ -341,9 +347,10 @@ namespace
 	int compileCandidate(pffrg_context *h, const pffrg_desc *d, JitCandidate &c)
 	{
 		RpaProgram prog = buildRpaProgram(d, h->core, c.shape.nbt * c.shape.subs, c.shape.rpaWarps);
+		prog.maxAccumulators = defaultAccumulators(c.threads, c.shape.minBlocks);
 		applyJitKnobs(prog);
 		std::vector<char> cubin;
-		const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, c.shape.subs, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
+		const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, c.shape.subs, c.shape.cluster, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the specialised flow kernel failed: %s", err.c_str());
 		CUDA_TRY(cudaLibraryLoadData(&c.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
 		CUDA_TRY(cudaLibraryGetKernel(&c.kernel, c.library, "pffrg_v4flow_jit"));
@@ -355,7 +362,7 @@ namespace
 	{
 		h->jitLibrary = c.library; h->jitKernel = c.kernel;
 		h->threads = c.threads; h->groups = c.groups;
-		h->nb = c.shape.nb; h->nbt = c.shape.nbt; h->rpaWarps = c.shape.rpaWarps; h->minBlocks = c.shape.minBlocks; h->smemBytes = c.shape.smem; h->subs = c.shape.subs;
+		h->nb = c.shape.nb; h->nbt = c.shape.nbt; h->rpaWarps = c.shape.rpaWarps; h->minBlocks = c.shape.minBlocks; h->smemBytes = c.shape.smem; h->subs = c.shape.subs; h->cluster = c.shape.cluster;
 	}
 
 	// Compile and load the lattice-specialised kernel. Controlled by the environment: PFFRG_JIT=0 disables it,
@@ -388,21 +395,27 @@ namespace
 				first = fat; firstThreads = h->threads * subs;
 			}
 		}
+		// CTAs per thread-block cluster (they rendezvous before every RPA phase, see clusterRendezvous): pairs by default for CTAs of one
+		// work item -- measured on B200: pyrochlore-r8 243 -> 195 ms, cubic-r7 20.2 -> 18.0 ms, honeycomb-r7 XYZ 27.9 -> 25.2 ms with 2;
+		// 4 and 8 are slower again (218 / 248 ms, 19.1 / 19.8 ms), CTAs of several sub-CTAs gain nothing
+		int cluster = 2;
+		if (const char *e = getenv("PFFRG_CLUSTER")) cluster = std::min(8, std::max(1, atoi(e)));
+		first.cluster = (first.subs > 1 && !getenv("PFFRG_CLUSTER")) ? 1 : cluster;
 		candidates.push_back({ firstThreads, h->groups, first, nullptr, nullptr, 0.f });
 		const long terms = (long)buildRpaProgram(d, h->core, first.nbt, first.rpaWarps).terms.size();
 		if (terms > maxTerms) return PFFRG_OK;
 		// opt-in: the shapes differ in summation order (last-bit differences), so a run that must be reproducible bit for bit across
 		// processes -- e.g. the sharded-vs-single-GPU comparison -- keeps the first shape
 		bool tune = false;
-		if (const char *e = getenv("PFFRG_AUTOTUNE")) tune = atoi(e) != 0 && terms <= tuneTerms && !getenv("PFFRG_JIT_NBT") && !getenv("PFFRG_THREADS") && !getenv("PFFRG_JIT_MINBLOCKS") && !getenv("PFFRG_SUBCTAS");
+		if (const char *e = getenv("PFFRG_AUTOTUNE")) tune = atoi(e) != 0 && terms <= tuneTerms && !getenv("PFFRG_JIT_NBT") && !getenv("PFFRG_THREADS") && !getenv("PFFRG_JIT_MINBLOCKS") && !getenv("PFFRG_SUBCTAS") && !getenv("PFFRG_CLUSTER");
 		if (tune && h->threads > 128)
 		{
 			const int groups = std::max(1, 128 / h->stride), threads = std::max(64, (groups * h->stride + 31) / 32 * 32);
 			if (threads < h->threads)
 			{
-				const JitShape same = chooseJitShape(h->core, h->nw, h->L, groups, threads / 32, smemMax);
+				JitShape same = chooseJitShape(h->core, h->nw, h->L, groups, threads / 32, smemMax); same.cluster = cluster;
 				if (same.nb) candidates.push_back({ threads, groups, same, nullptr, nullptr, 0.f });
-				const JitShape small = smallCtaShape(h->core, h->nw, h->L, groups, threads / 32, smemMax);
+				JitShape small = smallCtaShape(h->core, h->nw, h->L, groups, threads / 32, smemMax); small.cluster = cluster;
 				if (small.nb) candidates.push_back({ threads, groups, small, nullptr, nullptr, 0.f });
 				// several items per CTA (sub-CTAs of 128 threads, 32 staged nodes each, sharing one RPA phase): four in one CTA per SM,
 				// two in two CTAs per SM (measured on B200: cubic-r7 20.2 -> 19.3 ms with 2 x 2, honeycomb-r7 XYZ 27.9 -> 26.2 ms with 4 x 1)
@@ -1134,10 +1147,13 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 		shape = subCtaShape(d->core, d->n_frequencies, L, groups, threads / 32, subs, shape.nbt, shape.nb, getenv("PFFRG_JIT_MINBLOCKS") ? std::max(1, atoi(getenv("PFFRG_JIT_MINBLOCKS"))) : 1, 227 * 1024);
 		if (!shape.nb) return fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_SUBCTAS=%d does not fit (shared memory / warps)", subs);
 	}
+	shape.cluster = shape.subs > 1 ? 1 : 2; // as in setupJit
+	if (const char *e = getenv("PFFRG_CLUSTER")) shape.cluster = std::min(8, std::max(1, atoi(e)));
 	RpaProgram prog = buildRpaProgram(d, d->core, shape.nbt * shape.subs, shape.rpaWarps);
+	prog.maxAccumulators = defaultAccumulators(threads * shape.subs, shape.minBlocks);
 	applyJitKnobs(prog);
 	std::vector<char> cubin;
-	const std::string err = compileFlowKernel(d->core, shape.nb, shape.nbt, shape.subs, threads * shape.subs, shape.minBlocks, KernelSizes{ L, paddedSites(L), channelsOf(d->core) * paddedSites(L), d->n_frequencies }, generateRpaSource(prog), cubin);
+	const std::string err = compileFlowKernel(d->core, shape.nb, shape.nbt, shape.subs, shape.cluster, threads * shape.subs, shape.minBlocks, KernelSizes{ L, paddedSites(L), channelsOf(d->core) * paddedSites(L), d->n_frequencies }, generateRpaSource(prog), cubin);
 	if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
 	if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
 	return PFFRG_OK;

@@ -24,6 +24,7 @@ namespace pffrg
 		int maxAccumulators = 8;    // outputs accumulated in registers at a time
 		int chunk = 32;             // B operands cached in registers at a time
 		int prefetch = 8;           // A operands in flight (software pipeline depth of the generated code)
+		bool resync = false;        // thread-block clusters: rendezvous again after every sub-tile of outputs (the CTAs of a cluster drift apart inside a long stream)
 	};
 
 	// CUDA source of `__device__ void pffrg::rpaSpecialised(int warp, int lane, int nb, const double *st, double *rpaOut)`
@@ -33,6 +34,6 @@ namespace pffrg
 
 	// compile the vertex-flow kernel (embedded source + the generated RPA function) for sm_100a; returns an empty string on
 	// success and the compiler log otherwise. The kernel is `pffrg_v4flow_jit` with v4FlowKernel's parameter list; `nbt` = nodes
-	// staged per RPA phase by each of the `subs` sub-CTAs of a CTA, `threads` = threads of the whole CTA.
-	std::string compileFlowKernel(int core, int nb, int nbt, int subs, int threads, int minBlocks, const KernelSizes &sizes, const std::string &rpaSource, std::vector<char> &cubin);
+	// staged per RPA phase by each of the `subs` sub-CTAs of a CTA, `threads` = threads of the whole CTA, `cluster` = CTAs per thread-block cluster (they rendezvous before every RPA phase).
+	std::string compileFlowKernel(int core, int nb, int nbt, int subs, int cluster, int threads, int minBlocks, const KernelSizes &sizes, const std::string &rpaSource, std::vector<char> &cubin);
 }

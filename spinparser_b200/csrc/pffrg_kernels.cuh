@@ -278,6 +278,19 @@ namespace pffrg
 		int items;       // work items of this launch (a CTA of SUB sub-CTAs covers SUB consecutive items; the last one may be partial)
 	};
 
+#ifndef PFFRG_CLUSTER
+#define PFFRG_CLUSTER 1 // CTAs per thread-block cluster of the run-time compiled kernel (set by the code generator together with __cluster_dims__)
+#endif
+	// Cluster-wide rendezvous before an RPA phase (PFFRG_CLUSTER > 1): the CTAs of a cluster sit on SMs of one GPC, and the
+	// straight-line RPA code is streamed from the GPC-level instruction cache; CTAs that start the stream together fetch every
+	// line from L2 once instead of once each. Relaxed arrive: no memory is exchanged, and a release would flush the L1.
+	__device__ __forceinline__ void clusterRendezvous()
+	{
+#if PFFRG_CLUSTER > 1
+		asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+#endif
+	}
+
 	// barrier over sub-CTA `sub` (threads a multiple of 32) of a CTA made of several sub-CTAs: named barriers 1..4
 	__device__ __forceinline__ void subCtaSync(int sub, int threads)
 	{
@@ -1068,7 +1081,7 @@ namespace pffrg
 
 		// work item -> (s, t, u), expandIterator SU2VertexTwoParticle.hpp:136-158
 		const int itemFirst = itemBegin + blockIdx.x * SUB, itemEnd = itemBegin + cfg.items;
-		const bool valid = SUB == 1 || itemFirst + sub < itemEnd; // a sub-CTA past the end only takes part in the CTA barriers
+		const bool valid = itemFirst + sub < itemEnd; // a sub-CTA past the end (partial last CTA, padding CTAs of a cluster) only takes part in the barriers
 		const int item = valid ? itemFirst + sub : itemEnd - 1;
 		const int su = item / nw, ti = item - su * nw;
 		int so = (int)((sqrt(8.0 * su + 1.0) - 1.0) * 0.5);
@@ -1111,9 +1124,13 @@ namespace pffrg
 			if (tPass)
 			{
 				rounds = (nNodes + round - 1) / round;
-				if (SUB > 1)
-					for (int h = 0; h < SUB; ++h)
-						if (itemFirst + h < itemEnd) rounds = max(rounds, (N.count[(itemFirst + h) % nw] + round - 1) / round);
+				if (SUB > 1 || PFFRG_CLUSTER > 1)
+				{
+					// all sub-CTAs of the CTA (and all CTAs of the cluster) meet at every RPA phase: same number of rounds for all of them
+					const int domFirst = itemBegin + (int)(blockIdx.x / PFFRG_CLUSTER * PFFRG_CLUSTER) * SUB;
+					for (int h = 0; h < SUB * PFFRG_CLUSTER; ++h)
+						if (domFirst + h < itemEnd) rounds = max(rounds, (N.count[(domFirst + h) % nw] + round - 1) / round);
+				}
 			}
 			#pragma unroll 1
 			for (int rd = 0; rd < rounds; ++rd)
@@ -1239,6 +1256,7 @@ namespace pffrg
 			{
 				if (SUB > 1 && tid == 0) stagedCount[sub] = staged;
 				__syncthreads();
+				if (JIT) clusterRendezvous();
 				// ---- phase 2: RPA lattice sum over the staged nodes (of all sub-CTAs)
 #ifdef PFFRG_JIT_RPA
 				if (JIT)

@@ -26,13 +26,15 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             # 16 nodes per round several RPA rounds per item with sub-CTAs that run out of nodes at different times
             {"PFFRG_SUBCTAS": "2", "PFFRG_THREADS": "128", "PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16", "PFFRG_JIT_MINBLOCKS": "2"},
             {"PFFRG_SUBCTAS": "4", "PFFRG_THREADS": "128", "PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16"},
-            {"PFFRG_SUBCTAS": "3", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}]
+            {"PFFRG_SUBCTAS": "3", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"},
+            # thread-block clusters whose CTAs rendezvous before every RPA phase (grid padded to whole clusters)
+            {"PFFRG_CLUSTER": "2"}, {"PFFRG_CLUSTER": "4", "PFFRG_SUBCTAS": "2", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}]
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
 @pytest.mark.parametrize("case", CASES)
 def test_one_step_flow_matches_reference(case, variant, monkeypatch):
-    if case.startswith("tri") and ("PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant or "PFFRG_SUBCTAS" in variant):
+    if case.startswith("tri") and ("PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant or "PFFRG_SUBCTAS" in variant or "PFFRG_CLUSTER" in variant):
         pytest.skip("the TRI core has no run-time compiled variant")
     for k, x in variant.items():
         monkeypatch.setenv(k, x)
@@ -58,6 +60,29 @@ def test_one_step_flow_matches_reference(case, variant, monkeypatch):
             want = [state[c] + (float(cut[step + 1]) - float(cut[step])) * d[pre + f"flow/v4_{c}"] for c in range(n)]
             for c in range(n):
                 assert_parity(new.v4[c], want[c], f"{case} step {step} Euler channel {c}")
+    core.close()
+
+
+@pytest.mark.parametrize("variant", [{}, {"PFFRG_CLUSTER": "4"}, {"PFFRG_SUBCTAS": "3", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8", "PFFRG_CLUSTER": "2"}],
+                         ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
+@pytest.mark.parametrize("case", ["su2_kagome_r4_nw8", "xyz_kagome_r4_nw8"])
+def test_item_range_with_padded_grid(case, variant, monkeypatch):
+    """A slice of the work items that is not a multiple of the cluster / sub-CTA size (what a rank of a sharded run computes): the
+    grid is padded to whole clusters, padding CTAs only take part in the barriers, and the slice equals the reference's."""
+    for k, x in variant.items():
+        monkeypatch.setenv(k, x)
+    d = golden(case)
+    name, core = _core(d)
+    L, n = core.tables.n_sites, core.n_arrays
+    step = dumped_steps(d)[-1]
+    pre = f"step{step}/"
+    core.setState(float(d[pre + "state/cutoff"]), np.ascontiguousarray(d[pre + "state/v2"]), [np.ascontiguousarray(d[pre + f"state/v4_{c}"]) for c in range(n)])
+    begin, end = 7, 7 + 101
+    core.setItemRange(begin, end)
+    assert not core.computeStep()
+    flow = core.flow()
+    for c in range(n):
+        assert_parity(flow.v4[c][begin * L:end * L], d[pre + f"flow/v4_{c}"][begin * L:end * L], f"{case} items [{begin}, {end}) channel {c}")
     core.close()
 
 
