@@ -256,11 +256,13 @@ namespace
 	template <int CORE, int NB>
 	cudaError_t launchFlow(pffrg_context *h, int64_t begin, int64_t count)
 	{
-		auto kernel = v4FlowKernel<CORE, NB>;
+		// TRI core: thread-block clusters of two CTAs (PFFRG_TRI_CLUSTER=1 switches them off), see clusterRendezvous
+		const bool pair = CORE == TRI && h->cluster == 2;
+		auto kernel = pair ? v4FlowKernelPair<CORE, NB> : v4FlowKernel<CORE, NB>;
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes);
 		if (e != cudaSuccess) return e;
 		FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes; cfg.items = (int)count;
-		kernel<<<(unsigned)count, h->threads, h->smemBytes, h->stream>>>(h->problem(), h->nodeTable(), cfg, h->dV4.p, h->dFlow4.p, (int)begin, h->dNan.p);
+		kernel<<<(unsigned)(pair ? (count + 1) / 2 * 2 : count), h->threads, h->smemBytes, h->stream>>>(h->problem(), h->nodeTable(), cfg, h->dV4.p, h->dFlow4.p, (int)begin, h->dNan.p);
 		return cudaGetLastError();
 	}
 
@@ -348,6 +350,7 @@ namespace
 	{
 		RpaProgram prog = buildRpaProgram(d, h->core, c.shape.nbt * c.shape.subs, c.shape.rpaWarps);
 		prog.maxAccumulators = defaultAccumulators(c.threads, c.shape.minBlocks);
+		prog.cluster = c.shape.cluster;
 		applyJitKnobs(prog);
 		std::vector<char> cubin;
 		const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, c.shape.subs, c.shape.cluster, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
@@ -379,7 +382,12 @@ namespace
 		long maxTerms = 60000, tuneTerms = 12000;
 		if (const char *e = getenv("PFFRG_JIT_MAX_TERMS")) maxTerms = atol(e);
 		if (const char *e = getenv("PFFRG_AUTOTUNE_MAX_TERMS")) tuneTerms = atol(e);
-		if (h->core == TRI) return PFFRG_OK; // TRI: table-driven RPA phase (rpaTri), precompiled kernels
+		if (h->core == TRI) // TRI: table-driven RPA phase (rpaTri), precompiled kernels
+		{
+			h->cluster = 2;
+			if (const char *e = getenv("PFFRG_TRI_CLUSTER")) h->cluster = atoi(e) == 2 ? 2 : 1;
+			return PFFRG_OK;
+		}
 		const auto t0 = std::chrono::steady_clock::now();
 		std::vector<JitCandidate> candidates;
 		JitShape first = chooseJitShape(h->core, h->nw, h->L, h->groups, h->threads / 32, smemMax);
@@ -1151,6 +1159,7 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	if (const char *e = getenv("PFFRG_CLUSTER")) shape.cluster = std::min(8, std::max(1, atoi(e)));
 	RpaProgram prog = buildRpaProgram(d, d->core, shape.nbt * shape.subs, shape.rpaWarps);
 	prog.maxAccumulators = defaultAccumulators(threads * shape.subs, shape.minBlocks);
+	prog.cluster = shape.cluster;
 	applyJitKnobs(prog);
 	std::vector<char> cubin;
 	const std::string err = compileFlowKernel(d->core, shape.nb, shape.nbt, shape.subs, shape.cluster, threads * shape.subs, shape.minBlocks, KernelSizes{ L, paddedSites(L), channelsOf(d->core) * paddedSites(L), d->n_frequencies }, generateRpaSource(prog), cubin);

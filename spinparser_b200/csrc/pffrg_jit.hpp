@@ -24,6 +24,7 @@ namespace pffrg
 		int maxAccumulators = 8;    // outputs accumulated in registers at a time
 		int chunk = 32;             // B operands cached in registers at a time
 		int prefetch = 8;           // A operands in flight (software pipeline depth of the generated code)
+		int cluster = 1;            // CTAs per thread-block cluster (template argument of clusterRendezvous in the generated code)
 		bool resync = false;        // thread-block clusters: rendezvous again after every sub-tile of outputs (the CTAs of a cluster drift apart inside a long stream)
 	};
 

@@ -278,17 +278,14 @@ namespace pffrg
 		int items;       // work items of this launch (a CTA of SUB sub-CTAs covers SUB consecutive items; the last one may be partial)
 	};
 
-#ifndef PFFRG_CLUSTER
-#define PFFRG_CLUSTER 1 // CTAs per thread-block cluster of the run-time compiled kernel (set by the code generator together with __cluster_dims__)
-#endif
-	// Cluster-wide rendezvous before an RPA phase (PFFRG_CLUSTER > 1): the CTAs of a cluster sit on SMs of one GPC, and the
-	// straight-line RPA code is streamed from the GPC-level instruction cache; CTAs that start the stream together fetch every
-	// line from L2 once instead of once each. Relaxed arrive: no memory is exchanged, and a release would flush the L1.
+	// Cluster-wide rendezvous before an RPA phase (CL = CTAs per thread-block cluster > 1; the kernel carries __cluster_dims__):
+	// the CTAs of a cluster sit on SMs of one GPC, and the RPA code -- far larger than the per-SM instruction cache -- is streamed
+	// from the GPC-level instruction cache; CTAs that start the stream together fetch every line once instead of once each.
+	// Relaxed arrive: no memory is exchanged, and a release would flush the L1.
+	template <int CL>
 	__device__ __forceinline__ void clusterRendezvous()
 	{
-#if PFFRG_CLUSTER > 1
-		asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
-#endif
+		if constexpr (CL > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 	}
 
 	// barrier over sub-CTA `sub` (threads a multiple of 32) of a CTA made of several sub-CTAs: named barriers 1..4
@@ -1049,7 +1046,7 @@ namespace pffrg
 	// instruction caches once per pass (it is larger than the 32 KB per-SM instruction cache), and the GPC-level instruction
 	// cache that serves those misses is what limits the kernel on small lattices (ncu: gcc__cache_requests_type_instruction at
 	// 99 % of peak on cubic-r7 with one item per CTA) -- SUB items per pass divide that traffic by SUB.
-	template <int CORE, int NB, int NBT, bool JIT, int SUB = 1>
+	template <int CORE, int NB, int NBT, bool JIT, int SUB = 1, int CL = 1>
 	__device__ __forceinline__ void v4FlowBody(const Problem &P, const NodeTable &N, const FlowConfig &cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
 	{
 		constexpr int C = channelsOf(CORE);
@@ -1124,11 +1121,11 @@ namespace pffrg
 			if (tPass)
 			{
 				rounds = (nNodes + round - 1) / round;
-				if (SUB > 1 || PFFRG_CLUSTER > 1)
+				if (SUB > 1 || CL > 1)
 				{
 					// all sub-CTAs of the CTA (and all CTAs of the cluster) meet at every RPA phase: same number of rounds for all of them
-					const int domFirst = itemBegin + (int)(blockIdx.x / PFFRG_CLUSTER * PFFRG_CLUSTER) * SUB;
-					for (int h = 0; h < SUB * PFFRG_CLUSTER; ++h)
+					const int domFirst = itemBegin + (int)(blockIdx.x / CL * CL) * SUB;
+					for (int h = 0; h < SUB * CL; ++h)
 						if (domFirst + h < itemEnd) rounds = max(rounds, (N.count[(domFirst + h) % nw] + round - 1) / round);
 				}
 			}
@@ -1256,7 +1253,7 @@ namespace pffrg
 			{
 				if (SUB > 1 && tid == 0) stagedCount[sub] = staged;
 				__syncthreads();
-				if (JIT) clusterRendezvous();
+				clusterRendezvous<CL>();
 				// ---- phase 2: RPA lattice sum over the staged nodes (of all sub-CTAs)
 #ifdef PFFRG_JIT_RPA
 				if (JIT)
@@ -1304,6 +1301,12 @@ namespace pffrg
 	__global__ void __launch_bounds__(256) v4FlowKernel(Problem P, NodeTable N, FlowConfig cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
 	{
 		v4FlowBody<CORE, NB, NB, false>(P, N, cfg, v4, flow, itemBegin, nanFlag);
+	}
+	// the same in thread-block clusters of two CTAs that rendezvous before every RPA phase (grid padded to an even number of CTAs)
+	template <int CORE, int NB>
+	__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) v4FlowKernelPair(Problem P, NodeTable N, FlowConfig cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
+	{
+		v4FlowBody<CORE, NB, NB, false, 1, 2>(P, N, cfg, v4, flow, itemBegin, nanFlag);
 	}
 #endif
 
