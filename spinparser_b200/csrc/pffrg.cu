@@ -256,13 +256,11 @@ namespace
 	template <int CORE, int NB>
 	cudaError_t launchFlow(pffrg_context *h, int64_t begin, int64_t count)
 	{
-		// TRI core: thread-block clusters of two CTAs (PFFRG_TRI_CLUSTER=1 switches them off), see clusterRendezvous
-		const bool pair = CORE == TRI && h->cluster == 2;
-		auto kernel = pair ? v4FlowKernelPair<CORE, NB> : v4FlowKernel<CORE, NB>;
+		auto kernel = v4FlowKernel<CORE, NB>;
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes);
 		if (e != cudaSuccess) return e;
 		FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes; cfg.items = (int)count;
-		kernel<<<(unsigned)(pair ? (count + 1) / 2 * 2 : count), h->threads, h->smemBytes, h->stream>>>(h->problem(), h->nodeTable(), cfg, h->dV4.p, h->dFlow4.p, (int)begin, h->dNan.p);
+		kernel<<<(unsigned)count, h->threads, h->smemBytes, h->stream>>>(h->problem(), h->nodeTable(), cfg, h->dV4.p, h->dFlow4.p, (int)begin, h->dNan.p);
 		return cudaGetLastError();
 	}
 
@@ -382,12 +380,8 @@ namespace
 		long maxTerms = 60000, tuneTerms = 12000;
 		if (const char *e = getenv("PFFRG_JIT_MAX_TERMS")) maxTerms = atol(e);
 		if (const char *e = getenv("PFFRG_AUTOTUNE_MAX_TERMS")) tuneTerms = atol(e);
-		if (h->core == TRI) // TRI: table-driven RPA phase (rpaTri), precompiled kernels
-		{
-			h->cluster = 2;
-			if (const char *e = getenv("PFFRG_TRI_CLUSTER")) h->cluster = atoi(e) == 2 ? 2 : 1;
-			return PFFRG_OK;
-		}
+		// TRI: table-driven RPA phase (rpaTri), precompiled kernels (cluster pairs were measured there too: kagome-r7 950 vs 955 ms, not kept)
+		if (h->core == TRI) return PFFRG_OK;
 		const auto t0 = std::chrono::steady_clock::now();
 		std::vector<JitCandidate> candidates;
 		JitShape first = chooseJitShape(h->core, h->nw, h->L, h->groups, h->threads / 32, smemMax);
@@ -445,7 +439,7 @@ namespace
 			setScalarKernel<<<1, 1, 0, h->stream>>>(h->dCutoff.p, cutoff);
 			nodeTableKernel<<<h->nw, 128, sizeof(double) * (3 * h->nw + 2 * h->nodeStride), h->stream>>>(h->problem(), h->nodeTable(), h->dV2.p, h->dFlow2.p, h->dCutoff.p);
 			CUDA_TRY(cudaGetLastError());
-			const int64_t count = std::min<int64_t>(h->nf, 1184), begin = (h->nf - count) / 2;
+			const int64_t count = std::min<int64_t>(h->nf, 4736), begin = (h->nf - count) / 2; // 32 items per SM: whole waves for every candidate shape
 			for (size_t k = 0; k < candidates.size(); ++k)
 			{
 				adoptCandidate(h, candidates[k]);

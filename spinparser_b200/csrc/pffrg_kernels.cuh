@@ -278,7 +278,7 @@ namespace pffrg
 		int items;       // work items of this launch (a CTA of SUB sub-CTAs covers SUB consecutive items; the last one may be partial)
 	};
 
-	// Cluster-wide rendezvous before an RPA phase (CL = CTAs per thread-block cluster > 1; the kernel carries __cluster_dims__):
+	// Cluster-wide rendezvous before an RPA phase (CL = CTAs per thread-block cluster > 1; the run-time compiled kernel carries __cluster_dims__):
 	// the CTAs of a cluster sit on SMs of one GPC, and the RPA code -- far larger than the per-SM instruction cache -- is streamed
 	// from the GPC-level instruction cache; CTAs that start the stream together fetch every line once instead of once each.
 	// Relaxed arrive: no memory is exchanged, and a release would flush the L1.
@@ -1301,12 +1301,6 @@ namespace pffrg
 	__global__ void __launch_bounds__(256) v4FlowKernel(Problem P, NodeTable N, FlowConfig cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
 	{
 		v4FlowBody<CORE, NB, NB, false>(P, N, cfg, v4, flow, itemBegin, nanFlag);
-	}
-	// the same in thread-block clusters of two CTAs that rendezvous before every RPA phase (grid padded to an even number of CTAs)
-	template <int CORE, int NB>
-	__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) v4FlowKernelPair(Problem P, NodeTable N, FlowConfig cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
-	{
-		v4FlowBody<CORE, NB, NB, false, 1, 2>(P, N, cfg, v4, flow, itemBegin, nanFlag);
 	}
 #endif
 

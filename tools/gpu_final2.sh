@@ -11,7 +11,7 @@ python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/${TAG}_pytest_gpu.lo
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; tail -n 1 gpurun_out/${TAG}_smoke.log | cut -c1-200
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_cubic_r7_su2_nw64.json 2> gpurun_out/${TAG}_bench_cubic.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
-for wl in honeycomb_kitaev_r7_xyz_nw64 square_r4_su2_nw32; do
+for wl in honeycomb_kitaev_r7_xyz_nw64 pyrochlore_r8_su2_nw64 kagome_dm_r7_tri_nw64 square_r4_su2_nw32; do
   timeout 600 python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 --synthetic-state > gpurun_out/${TAG}_bench_${wl}.json 2> gpurun_out/${TAG}_bench_${wl}.err
 done
 python - <<PY

@@ -23,6 +23,10 @@ METRICS = [
     "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__block_size", "launch__grid_size",
     "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
     "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    # instruction delivery: per-SM instruction cache (ICC), GPC-level instruction cache (GCC) and its fill path from the crossbar
+    "sm__icc_request_hit_rate.pct", "sm__icc_requests.sum.pct_of_peak_sustained_elapsed", "gcc__average_cache_request_hit_rate.pct",
+    "gcc__cache_requests_type_instruction.sum", "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",
+    "gcc__xbar2gcc_sectors.sum", "gcc__xbar2gcc_sectors.sum.pct_of_peak_sustained_elapsed",
 ]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "second": 1.0}
 
@@ -59,6 +63,9 @@ def main(workload, report, tag="r1", items=0):
         "warps_active_pct": avg("sm__warps_active.avg.pct_of_peak_sustained_active"),
         "registers_per_thread": avg("launch__registers_per_thread"),
         "l1_lsu_wavefronts_pct": avg("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") if "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed" in col else None,
+        "gcc_instruction_requests_pct": avg("gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed") if "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed" in col else None,
+        "gcc_fill_pct": avg("gcc__xbar2gcc_sectors.sum.pct_of_peak_sustained_elapsed") if "gcc__xbar2gcc_sectors.sum.pct_of_peak_sustained_elapsed" in col else None,
+        "gcc_hit_pct": avg("gcc__average_cache_request_hit_rate.pct") if "gcc__average_cache_request_hit_rate.pct" in col else None,
         # 0 = the whole step; otherwise the capture was restricted to the first N work items (bench.py --items) and the
         # per-launch figures are NOT those of a full step
         "captured_items": int(items),
