@@ -56,13 +56,22 @@ class ClockSampler:
     QUERY = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device: int):
-        self.device, self.proc, self.lines = device, None, []
+        self.device, self.proc, self.lines, self.first, self.last = device, None, [], 0, None
+
+    def mark_begin(self):
+        """Start of the timed region: samples taken before it (warm-up) are dropped."""
+        self.first = len(self.lines)
+
+    def mark_end(self):
+        """End of the timed region (the sample in flight still belongs to it)."""
+        self.last = len(self.lines) + 1
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.device)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+            time.sleep(0.5)  # nvidia-smi takes a few hundred ms to deliver its first sample
         except OSError:
             self.proc = None
 
@@ -77,7 +86,8 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        window = self.lines[self.first:self.last] or self.lines[-1:]
+        for line in window:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -277,12 +287,17 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # nvidia-smi needs a moment to come up: started ahead of two extra untimed steps, the window is marked below
+    for _ in range(2):
+        one_step(False)
+    barrier()
+    sampler.mark_begin()
     first_timed = step
     wall0 = time.perf_counter()
     records = [one_step(True) for _ in range(args.steps)]
     barrier()
     wall = time.perf_counter() - wall0
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     step_ms = torch.tensor([e0.elapsed_time(e1) for e0, e1, _ in records], dtype=torch.float64, device=f"cuda:{local}")
     kern_ms = torch.tensor([st["ms_v4_flow"] for _, _, st in records], dtype=torch.float64, device=f"cuda:{local}")
@@ -330,7 +345,7 @@ def main():
             "config": {"workload": WORKLOADS[args.workload], "cutoff_steps": [first_timed, first_timed + args.steps - 1],
                        "cutoff": [cutoffs[first_timed], cutoffs[first_timed + args.steps - 1]],
                        **({"PROFILING_ONLY_item_range": [0, args.items]} if args.items > 0 else {}),
-                       "state": "seeded synthetic vertex" if args.synthetic_state else f"physical: flow run on the GPU from the bare couplings for {args.start_step + args.warmup} steps ({t_setup:.1f} s, untimed)",
+                       "state": "seeded synthetic vertex" if args.synthetic_state else f"physical: flow run on the GPU from the bare couplings for {first_timed} steps ({t_setup:.1f} s for the first {args.start_step}, untimed)",
                        "parallelism": f"work items sharded over {world} GPU(s), vertex replicated, ncclBroadcast exchange of the updated slices",
                        "l2": f"flushed between timed iterations (256 MiB write; device vertex {state_dev_mb:.0f} MB vs 126 MB L2)", "timing": "CUDA events on the library stream per step, max over ranks"},
             "vertex_entries_per_s": C * L * nf * value,
