@@ -434,6 +434,65 @@ namespace pffrg
 		}
 	}
 
+#ifndef PFFRG_MIRROR
+#define PFFRG_MIRROR 0 // A/B switch of the run-time compiled kernel, see gatherTwo
+#endif
+	// The t channel's gathered buffers come in mirrored pairs: buffer 2 is buffer 0 with the s and u arguments exchanged, buffer 3
+	// is buffer 1 with (s, u) -> (-u, -s) (src/SU2/SU2FrgCore.cpp:233-239). Only s >= u is stored, so both members of a pair read
+	// the SAME four rows at the same sites (supports 1 and 2 trade places; weights and mirror flags are the member's own).
+	__device__ __forceinline__ bool mirroredPair(const AccessBuffer &a, const AccessBuffer &b)
+	{
+		const int4 ra = *reinterpret_cast<const int4 *>(&a.row[0]), rb = *reinterpret_cast<const int4 *>(&b.row[0]);
+		return ((a.flags ^ b.flags) & AB_EXCHANGE) == 0 && rb.x == ra.x && rb.y == ra.z && rb.z == ra.y && rb.w == ra.w;
+	}
+	// gather buffer `a` and form its mirrored partner `b` from the same loads (bit-identical to gathering b: same values, b's own
+	// weights, b's own summation order)
+	template <int CORE>
+	__device__ __forceinline__ void gatherTwo(const Problem &P, const double *__restrict__ v4, const AccessBuffer &a, const AccessBuffer &b, int siteFwd, int siteInv, int permFwd, int permInv,
+		double (&outA)[channelsOf(CORE)], double (&outB)[channelsOf(CORE)])
+	{
+		static_assert(CORE == SU2 || CORE == XYZ, "channel-pair layouts only");
+		const bool exchange = a.flags & AB_EXCHANGE;
+		const int site = exchange ? siteInv : siteFwd, perm = exchange ? permInv : permFwd;
+		double2 lo[4], hi[4];
+		#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			const double2 *base = reinterpret_cast<const double2 *>(v4 + (size_t)((unsigned)a.row[k] * (unsigned)sizeRL(P) + 2u * (unsigned)site));
+			lo[k] = __ldg(base);
+			if (CORE == XYZ) hi[k] = __ldg(base + sizeLp(P)); else hi[k] = lo[k];
+		}
+		#pragma unroll
+		for (int m = 0; m < 2; ++m)
+		{
+			const AccessBuffer &ab = m == 0 ? a : b;
+			double (&out)[channelsOf(CORE)] = m == 0 ? outA : outB;
+			const double2 w01 = *reinterpret_cast<const double2 *>(&ab.w[0]), w23 = *reinterpret_cast<const double2 *>(&ab.w[2]);
+			const int flags = ab.flags;
+			const double wk[4] = { w01.x, w01.y, w23.x, w23.y };
+			const double ok[4] = { oddWeight(w01.x, flags, 0), oddWeight(w01.y, flags, 1), oddWeight(w23.x, flags, 2), oddWeight(w23.y, flags, 3) };
+			double raw[4] = { 0.0, 0.0, 0.0, 0.0 };
+			#pragma unroll
+			for (int k = 0; k < 4; ++k)
+			{
+				const int kk = (m == 1 && (k == 1 || k == 2)) ? 3 - k : k; // support k of the partner reads what support 3-k of `a` loaded
+				if (CORE == SU2) { raw[0] += wk[k] * lo[kk].x; raw[1] += ok[k] * lo[kk].y; }
+				else { raw[0] += wk[k] * lo[kk].x; raw[1] += wk[k] * lo[kk].y; raw[2] += wk[k] * hi[kk].x; raw[3] += ok[k] * hi[kk].y; }
+			}
+			if (CORE == SU2) { out[0] = raw[0]; out[1] = raw[1]; }
+			else
+			{
+				#pragma unroll
+				for (int c = 0; c < 3; ++c)
+				{
+					const int sc = (perm >> (2 * c)) & 3;
+					out[c] = sc == 0 ? raw[0] : (sc == 1 ? raw[1] : raw[2]);
+				}
+				out[3] = raw[3];
+			}
+		}
+	}
+
 	// frequency arguments of access buffer b of channel ch at integration frequency wp
 	// S: SU2FrgCore.cpp:202-206, T: :233-239 (+ locals :269-275), U: :309-313
 	struct ItemFrequencies { double s, t, u, w1p, w1, w2p, w2; };
@@ -1202,8 +1261,18 @@ namespace pffrg
 					for (int node = g; node < nb; node += cfg.groups)
 					{
 						double A[4][C];
-						#pragma unroll
-						for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, abTable[node * nbuf + b], siteFwd, siteInv, permFwd, permInv, A[b]);
+						const AccessBuffer *ab = abTable + node * nbuf;
+						if (PFFRG_MIRROR && tPass && mirroredPair(ab[0], ab[2]) && mirroredPair(ab[1], ab[3]))
+						{
+							// 8 row loads instead of 16, decided before any load is issued so that they still form one burst
+							gatherTwo<CORE>(P, v4, ab[0], ab[2], siteFwd, siteInv, permFwd, permInv, A[0], A[2]);
+							gatherTwo<CORE>(P, v4, ab[1], ab[3], siteFwd, siteInv, permFwd, permInv, A[1], A[3]);
+						}
+						else
+						{
+							#pragma unroll
+							for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, ab[b], siteFwd, siteInv, permFwd, permInv, A[b]);
+						}
 						const double W = bW[node];
 						double K[C];
 						if (!tPass)

@@ -28,13 +28,15 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             {"PFFRG_SUBCTAS": "4", "PFFRG_THREADS": "128", "PFFRG_JIT_NBT": "32", "PFFRG_JIT_NB": "16"},
             {"PFFRG_SUBCTAS": "3", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"},
             # thread-block clusters whose CTAs rendezvous before every RPA phase (grid padded to whole clusters)
-            {"PFFRG_CLUSTER": "2"}, {"PFFRG_CLUSTER": "4", "PFFRG_SUBCTAS": "2", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}]
+            {"PFFRG_CLUSTER": "2"}, {"PFFRG_CLUSTER": "4", "PFFRG_SUBCTAS": "2", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"},
+            # t channel: buffers 2, 3 formed from the rows loaded for buffers 0, 1 (gatherTwo)
+            {"PFFRG_MIRROR": "1"}]
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
 @pytest.mark.parametrize("case", CASES)
 def test_one_step_flow_matches_reference(case, variant, monkeypatch):
-    if case.startswith("tri") and ("PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant or "PFFRG_SUBCTAS" in variant or "PFFRG_CLUSTER" in variant):
+    if case.startswith("tri") and ("PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant or "PFFRG_SUBCTAS" in variant or "PFFRG_CLUSTER" in variant or "PFFRG_MIRROR" in variant):
         pytest.skip("the TRI core has no run-time compiled variant")
     for k, x in variant.items():
         monkeypatch.setenv(k, x)
