@@ -129,6 +129,12 @@ int pffrg_item_range(pffrg_handle h, int64_t *begin, int64_t *end); /* this rank
  * Item costs follow the exact quadrature node counts of src/lib/Integrator.hpp:138-287, so every rank gets the same load. */
 int pffrg_plan_partition(int core, int n_frequencies, const double *frequencies, int n_sites, int64_t rpa_terms, double cutoff,
                          int n_ranks, int64_t *bounds /* [n_ranks + 1] */);
+/* The same with feedback, as the library applies it from the second step of a multi-GPU run on (replaces the throughput-adaptive
+ * chunk sizes of src/lib/LoadManager.hpp:796-852): `prev_bounds` [n_ranks + 1] and `prev_ms` [n_ranks] are the boundaries and the
+ * measured flow-kernel times of the previous step; the modelled cost of an item is weighted by the measured time per modelled
+ * unit of the previous interval it lies in. PFFRG_BALANCE=0 keeps the static split. */
+int pffrg_plan_partition_feedback(int core, int n_frequencies, const double *frequencies, int n_sites, int64_t rpa_terms, double cutoff,
+                                  int n_ranks, const int64_t *prev_bounds, const double *prev_ms, int64_t *bounds /* [n_ranks + 1] */);
 
 /* state transfer: replaces direct access to {SU2,XYZ,TRI}EffectiveAction's arrays and EffectiveAction::cutoff
  * (src/SU2/SU2EffectiveAction.hpp:38-60, src/EffectiveAction.hpp:59). `v4` holds pffrg_num_vertex_arrays pointers. */

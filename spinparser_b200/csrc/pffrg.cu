@@ -148,6 +148,8 @@ struct pffrg_context
 	int rank = 0, nRanks = 1;
 	ncclComm_t comm = nullptr;
 	std::vector<int64_t> bounds; // [nRanks + 1] item boundaries of the current step
+	std::vector<double> rankTimes; // flow-kernel time of every rank in the last step (feedback of the partition), empty before the first
+	DeviceArray<double> dTimes; double *hTimes = nullptr; bool balance = true;
 	int64_t userBegin = 0, userEnd = 0;
 	int64_t curBegin = 0, curEnd = 0;
 
@@ -637,46 +639,103 @@ namespace
 	// Contiguous cost-balanced item ranges (replaces the dynamic master/worker chunking of src/lib/LoadManager.hpp:796-852).
 	// Items are ordered su-major, t-minor; the cost of item (so, uo, t) is n(so) + n(uo) ladder evaluations and n(t)
 	// t-channel evaluations, n(x) the quadrature node count of transfer frequency x at the current cutoff.
-	std::vector<int64_t> planPartition(int core, int nw, double L, double rpaTerms, const std::vector<int> &counts, int nRanks)
+	// Modelled cost of the items [0, item): items are ordered su-major, t-minor; item (so, uo, t) costs n(so) + n(uo) ladder
+	// evaluations and n(t) t-channel evaluations, n(x) the quadrature node count of transfer frequency x at the current cutoff.
+	struct CostModel
 	{
-		const CoreModel m = modelOf(core);
-		const double costSU = (16.0 * m.C + m.ladderTerms) * L;
-		const double costT = (16.0 * m.C + m.localTerms) * L + 2.0 * m.rpaTerms * rpaTerms;
-		const int64_t nf = (int64_t)nw * nw * (nw + 1) / 2;
-		std::vector<double> prefix((size_t)nf / nw + 1, 0.0); // cost per su block (all t of one (s,u))
-		double sumT = 0.0; for (int t = 0; t < nw; ++t) sumT += counts[t];
-		int64_t su = 0;
-		for (int so = 0; so < nw; ++so)
-			for (int uo = 0; uo <= so; ++uo, ++su)
-				prefix[su + 1] = prefix[su] + nw * (counts[so] + counts[uo]) * costSU + sumT * costT;
-		const double total = prefix.back();
+		int nw; double costSU, costT;
+		std::vector<double> prefix;  // cost of the su blocks [0, b)
+		std::vector<double> prefixT; // sum_{t' < t} n(t')
+		const std::vector<int> *counts;
+		CostModel(int core, int nw_, double L, double rpaTerms, const std::vector<int> &c) : nw(nw_), counts(&c)
+		{
+			const CoreModel m = modelOf(core);
+			costSU = (16.0 * m.C + m.ladderTerms) * L;
+			costT = (16.0 * m.C + m.localTerms) * L + 2.0 * m.rpaTerms * rpaTerms;
+			prefixT.assign(nw + 1, 0.0);
+			for (int t = 0; t < nw; ++t) prefixT[t + 1] = prefixT[t] + c[t];
+			prefix.assign((size_t)nw * (nw + 1) / 2 + 1, 0.0);
+			int64_t su = 0;
+			for (int so = 0; so < nw; ++so)
+				for (int uo = 0; uo <= so; ++uo, ++su)
+					prefix[su + 1] = prefix[su] + nw * (double)(c[so] + c[uo]) * costSU + prefixT[nw] * costT;
+		}
+		int64_t items() const { return (int64_t)(prefix.size() - 1) * nw; }
+		double upTo(int64_t item) const
+		{
+			const int64_t blk = item / nw; const int t = (int)(item - blk * nw);
+			if (t == 0) return prefix[blk];
+			int so = (int)((std::sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
+			while ((int64_t)(so + 1) * (so + 2) / 2 <= blk) ++so;
+			while ((int64_t)so * (so + 1) / 2 > blk) --so;
+			const int uo = (int)(blk - (int64_t)so * (so + 1) / 2);
+			return prefix[blk] + t * (double)((*counts)[so] + (*counts)[uo]) * costSU + prefixT[t] * costT;
+		}
+	};
+
+	// Contiguous cost-balanced item ranges (replaces the dynamic master/worker chunking of src/lib/LoadManager.hpp:796-852).
+	// Without feedback the modelled cost is split evenly. With feedback -- the item boundaries and the measured flow-kernel times of
+	// the previous step, identical on all ranks -- the modelled cost is weighted by the measured time per modelled unit of the
+	// previous rank interval an item lies in (a piecewise constant density): what the model does not know (cache locality of the
+	// gathers varies along the item axis; measured on 4 GPUs: 52 ms on the first rank against 63 ms on the slowest at pyrochlore-r8
+	// with equal modelled cost) is corrected from one step to the next, the way the reference's LoadManager adapts its chunk sizes
+	// to the measured throughput of its workers.
+	std::vector<int64_t> planPartition(int core, int nw, double L, double rpaTerms, const std::vector<int> &counts, int nRanks,
+	                                   const std::vector<int64_t> *prevBounds = nullptr, const std::vector<double> *prevTimes = nullptr)
+	{
+		const CostModel model(core, nw, L, rpaTerms, counts);
+		const int64_t nf = model.items();
+		// density pieces: [edge[k], edge[k+1]) with weight rho[k]
+		std::vector<int64_t> edge = { 0, nf };
+		std::vector<double> rho = { 1.0 };
+		if (prevBounds && prevTimes && (int)prevBounds->size() == nRanks + 1 && (int)prevTimes->size() == nRanks && nRanks > 1)
+		{
+			std::vector<double> r(nRanks, 0.0); double mean = 0.0; int valid = 0;
+			for (int k = 0; k < nRanks; ++k)
+			{
+				const double c = model.upTo((*prevBounds)[k + 1]) - model.upTo((*prevBounds)[k]);
+				if (c > 0.0 && (*prevTimes)[k] > 0.0) { r[k] = (*prevTimes)[k] / c; mean += r[k]; ++valid; }
+			}
+			if (valid == nRanks)
+			{
+				mean /= nRanks;
+				for (double &x : r) x = std::min(2.0, std::max(0.5, x / mean)); // bounded correction
+				edge = *prevBounds; edge.front() = 0; edge.back() = nf; rho = r;
+			}
+		}
+		auto weightedUpTo = [&](int64_t item)
+		{
+			double w = 0.0;
+			for (size_t k = 0; k + 1 < edge.size(); ++k)
+			{
+				if (item <= edge[k]) break;
+				w += rho[k] * (model.upTo(std::min(item, edge[k + 1])) - model.upTo(edge[k]));
+			}
+			return w;
+		};
+		const double total = weightedUpTo(nf);
 		std::vector<int64_t> bounds(nRanks + 1, 0);
 		bounds[nRanks] = nf;
 		for (int r = 1; r < nRanks; ++r)
 		{
 			const double target = total * r / nRanks;
-			int64_t b = std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin();
-			b = std::min<int64_t>(std::max<int64_t>(b, 0), nf / nw);
-			// refine inside the su block: items of one block differ only through their t index
-			int64_t item = std::min<int64_t>(b * nw, nf);
-			if (b > 0)
+			int64_t lo = bounds[r - 1], hi = nf; // smallest item count whose weighted cost reaches the target
+			while (lo < hi)
 			{
-				double acc = prefix[b - 1]; const int64_t blk = b - 1;
-				int so = (int)((std::sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
-				while ((int64_t)(so + 1) * (so + 2) / 2 <= blk) ++so;
-				while ((int64_t)so * (so + 1) / 2 > blk) --so;
-				int uo = (int)(blk - (int64_t)so * (so + 1) / 2);
-				item = blk * nw;
-				for (int t = 0; t < nw && acc < target; ++t, ++item) acc += (counts[so] + counts[uo]) * costSU + counts[t] * costT;
+				const int64_t mid = (lo + hi) / 2;
+				if (weightedUpTo(mid) < target) lo = mid + 1; else hi = mid;
 			}
-			bounds[r] = std::max(item, bounds[r - 1]);
+			bounds[r] = lo;
 		}
 		return bounds;
 	}
 
 	void partitionItems(pffrg_context *h, const std::vector<int> &counts)
 	{
-		h->bounds = planPartition(h->core, h->nw, h->L, (double)h->uniquePairs, counts, h->nRanks);
+		// feedback from the previous step's kernel times (multi-GPU runs; PFFRG_BALANCE=0 keeps the static split)
+		const bool feedback = h->nRanks > 1 && h->balance && (int)h->rankTimes.size() == h->nRanks && (int)h->bounds.size() == h->nRanks + 1;
+		const std::vector<int64_t> prev = h->bounds;
+		h->bounds = planPartition(h->core, h->nw, h->L, (double)h->uniquePairs, counts, h->nRanks, feedback ? &prev : nullptr, feedback ? &h->rankTimes : nullptr);
 	}
 
 	void fillStats(pffrg_context *h, const std::vector<int> &counts, int64_t begin, int64_t end)
@@ -901,6 +960,7 @@ int pffrg_destroy(pffrg_handle h)
 	h->dCount.release(); h->dNodeW.release(); h->dNodeWt.release(); h->dNan.release(); h->dStaging.release();
 	h->dChiPartial.release(); h->dChi.release(); h->dChiCount.release();
 	if (h->hNan) cudaFreeHost(h->hNan);
+	if (h->hTimes) cudaFreeHost(h->hTimes);
 	for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;
@@ -932,6 +992,8 @@ int pffrg_comm_init(pffrg_handle h, const void *id, int rank, int nRanks)
 	ncclUniqueId uid; memcpy(&uid, id, sizeof(uid));
 	if (!nccl().ok) return fail(PFFRG_ERR_NCCL, "%s", nccl().error.c_str());
 	NCCL_TRY(nccl().CommInitRank(&h->comm, nRanks, uid, rank));
+	if (const char *e = getenv("PFFRG_BALANCE")) h->balance = atoi(e) != 0;
+	h->rankTimes.clear();
 	h->rank = rank; h->nRanks = nRanks;
 	h->bounds.assign(nRanks + 1, 0); h->bounds[nRanks] = h->nf;
 	return PFFRG_OK;
@@ -1072,9 +1134,20 @@ int pffrg_finalize_step(pffrg_handle h, double newCutoff)
 	setScalarKernel<<<1, 1, 0, h->stream>>>(h->dCutoff.p, newCutoff);
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
-	if (h->nRanks > 1 && !(h->userEnd > h->userBegin)) { int rc = exchangeSlices(h, h->dV4.p); if (rc != PFFRG_OK) return rc; }
+	const bool sharded = h->nRanks > 1 && !(h->userEnd > h->userBegin);
+	if (sharded) { int rc = exchangeSlices(h, h->dV4.p); if (rc != PFFRG_OK) return rc; }
+	if (sharded && h->balance)
+	{
+		// every rank's flow-kernel time of this step -> all ranks (a sum over vectors with one non-zero entry each)
+		if (!h->hTimes) { CUDA_TRY(cudaMallocHost(&h->hTimes, sizeof(double) * h->nRanks)); CUDA_TRY(h->dTimes.alloc(h->nRanks)); }
+		for (int r = 0; r < h->nRanks; ++r) h->hTimes[r] = r == h->rank ? (double)h->stats.ms_v4_flow : 0.0;
+		CUDA_TRY(cudaMemcpyAsync(h->dTimes.p, h->hTimes, sizeof(double) * h->nRanks, cudaMemcpyHostToDevice, h->stream));
+		NCCL_TRY(nccl().AllReduce(h->dTimes.p, h->dTimes.p, h->nRanks, ncclDouble, ncclSum, h->comm, h->stream));
+		CUDA_TRY(cudaMemcpyAsync(h->hTimes, h->dTimes.p, sizeof(double) * h->nRanks, cudaMemcpyDeviceToHost, h->stream));
+	}
 	CUDA_TRY(cudaEventRecord(h->ev[6], h->stream));
 	CUDA_TRY(cudaStreamSynchronize(h->stream));
+	if (sharded && h->balance) h->rankTimes.assign(h->hTimes, h->hTimes + h->nRanks);
 	h->stats.ms_finalize = elapsed(h->ev[4], h->ev[6]);
 	h->stats.ms_exchange = elapsed(h->ev[5], h->ev[6]);
 	h->stats.launches += 3;
@@ -1168,6 +1241,19 @@ int pffrg_plan_partition(int core, int nFrequencies, const double *frequencies, 
 	std::vector<int> counts(nFrequencies);
 	for (int i = 0; i < nFrequencies; ++i) counts[i] = nodeCount(frequencies, nFrequencies, cutoff, frequencies[i]);
 	const std::vector<int64_t> b = planPartition(core, nFrequencies, nSites, (double)rpaTerms, counts, nRanks);
+	std::copy(b.begin(), b.end(), bounds);
+	return PFFRG_OK;
+}
+
+int pffrg_plan_partition_feedback(int core, int nFrequencies, const double *frequencies, int nSites, int64_t rpaTerms, double cutoff, int nRanks,
+                                  const int64_t *prevBounds, const double *prevMs, int64_t *bounds)
+{
+	if (core < 0 || core > 2 || nFrequencies < 2 || !frequencies || nSites < 1 || nRanks < 1 || !bounds || !prevBounds || !prevMs) return fail(PFFRG_ERR_ARGUMENT, "bad argument");
+	std::vector<int> counts(nFrequencies);
+	for (int i = 0; i < nFrequencies; ++i) counts[i] = nodeCount(frequencies, nFrequencies, cutoff, frequencies[i]);
+	const std::vector<int64_t> pb(prevBounds, prevBounds + nRanks + 1);
+	const std::vector<double> pt(prevMs, prevMs + nRanks);
+	const std::vector<int64_t> b = planPartition(core, nFrequencies, nSites, (double)rpaTerms, counts, nRanks, &pb, &pt);
 	std::copy(b.begin(), b.end(), bounds);
 	return PFFRG_OK;
 }

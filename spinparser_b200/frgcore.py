@@ -323,5 +323,16 @@ def plan_partition(identifier: str, tables: ProblemTables, cutoff: float, n_rank
     return list(bounds)
 
 
+def plan_partition_feedback(identifier: str, tables: ProblemTables, cutoff: float, prev_bounds: Sequence[int], prev_ms: Sequence[float]) -> List[int]:
+    """Boundaries of the next step given the previous step's boundaries and measured flow-kernel times per rank
+    (``pffrg_plan_partition_feedback``; pure host logic, no GPU)."""
+    n_ranks = len(prev_ms)
+    bounds = (C.c_int64 * (n_ranks + 1))()
+    check(lib.pffrg_plan_partition_feedback(_capi.CORE_IDS[identifier], tables.n_frequencies, tables.frequencies.ctypes.data_as(C.POINTER(C.c_double)),
+                                            tables.n_sites, int(tables.overlap_offsets[-1]), float(cutoff), n_ranks,
+                                            (C.c_int64 * (n_ranks + 1))(*[int(b) for b in prev_bounds]), (C.c_double * n_ranks)(*[float(t) for t in prev_ms]), bounds))
+    return list(bounds)
+
+
 def device_count() -> int:
     return int(lib.pffrg_device_count())

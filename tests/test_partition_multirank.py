@@ -101,3 +101,40 @@ def test_two_rank_sharded_step_reproduces_the_reference_state(case, tmp_path):
     for c in range(n):
         want = d["step10/state/v4_%d" % c] + step * d["step10/flow/v4_%d" % c]
         np.testing.assert_allclose(got[0][c], want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("ranks", [2, 4, 8])
+def test_feedback_partition_converges_on_position_dependent_cost(ranks):
+    """pffrg_plan_partition_feedback: when the true cost per item deviates from the model along the item axis (cache locality of
+    the gathers does, measured on 4 GPUs), feeding the measured times of one step into the next partition evens the ranks out."""
+    from spinparser_b200 import ProblemTables, read_pfd
+    from spinparser_b200.frgcore import plan_partition, plan_partition_feedback
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_port import OraclePort
+    d = read_pfd(os.path.join(ROOT, "bench_data", "cubic_r7_su2_nw64.tables.pfd"))
+    tables = ProblemTables.from_pfd(d)
+    port = OraclePort(d)
+    nw, nf = tables.n_frequencies, tables.n_items
+    cutoff = float(d["cutoff"][214])
+    n = np.array([port.node_count(cutoff, float(w)) for w in port.mesh], dtype=np.float64)
+    so, uo = np.tril_indices(nw)
+    order = np.argsort(so * (so + 1) // 2 + uo)
+    so, uo = so[order], uo[order]
+    x = np.arange(nf) / nf
+    true_cost = (n[so][:, None] + n[uo][:, None] + 3.0 * n[None, :]).reshape(-1) * (0.75 + 0.6 * x ** 2)  # late items are slower than modelled
+    prefix = np.concatenate([[0.0], np.cumsum(true_cost)])
+
+    def times(bounds):
+        return np.array([prefix[b] - prefix[a] for a, b in zip(bounds, bounds[1:])])
+
+    bounds = plan_partition("SU2", tables, cutoff, ranks)
+    first = times(bounds)
+    for _ in range(4):
+        bounds = plan_partition_feedback("SU2", tables, cutoff, bounds, times(bounds))
+        assert bounds[0] == 0 and bounds[-1] == nf and all(a <= b for a, b in zip(bounds, bounds[1:]))
+    last = times(bounds)
+    assert first.max() / first.mean() > 1.10, "the scenario must start out unbalanced"
+    assert last.max() / last.mean() < 1.02, (first.max() / first.mean(), last.max() / last.mean(), bounds)
+    # equal times are a fixed point, and the static split is reproduced by uniform feedback
+    again = plan_partition_feedback("SU2", tables, cutoff, bounds, times(bounds))
+    assert max(abs(a - b) for a, b in zip(again, bounds)) <= nf // 200
