@@ -112,6 +112,19 @@ def profiled_traffic(workload):
     return rec.get("dram_bytes_per_launch") if rec and not rec.get("captured_items") else None
 
 
+def profiled_limits(workload):
+    """What the committed full capture says binds the flow kernel (percent of the unit's peak, from profiles/ncu_summary.json):
+    context for `roofline`, not a live measurement. Empty when there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            rec = json.load(f).get(workload) or {}
+        keys = {"l1_lsu_wavefronts_pct": "l1_data_pipe_wavefronts", "fp64_pipe_pct": "fp64_pipe", "issue_active_pct": "issue_slots",
+                "gcc_instruction_requests_pct": "gpc_instruction_cache_requests", "gcc_fill_pct": "gpc_instruction_cache_fill"}
+        return {name: round(float(rec[k]), 1) for k, name in keys.items() if rec.get(k) is not None}
+    except Exception:  # never let a reporting extra break the bench line
+        return {}
+
+
 def load_tables(workload):
     return read_pfd(os.path.join(ROOT, "bench_data", workload + ".tables.pfd"))
 
@@ -354,7 +367,7 @@ def main():
             "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
             "breakdown_ms": {k: statistics.mean(st[k] for _, _, st in records) for k in ("ms_v2_flow", "ms_node_table", "ms_v4_flow", "ms_finalize", "ms_exchange")},
             "launch_shape": {k: records[0][2][k] for k in ("jit_rpa", "threads", "smem_bytes", "node_batch", "rpa_batch", "rpa_warps", "min_blocks", "sub_ctas", "autotuned_shapes", "jit_compile_ms")},
-            "roofline": {"bound": "hbm", "kernel": "pffrg::v4FlowKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.workload),
+            "roofline": {"bound": "hbm", "kernel": "pffrg::v4FlowKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.workload), "profiled_pct_of_peak": profiled_limits(args.workload),
                          "peak_source": peak_src, "note": "achieved = algorithmic gather+output bytes (SURVEY 8d: 128*L*C per kernel evaluation + 24*L*C per item) / kernel time, per GPU; gathers that hit in L2 do not reach DRAM, so `traffic` (ncu dram bytes per launch) is far below the algorithmic bytes and frac can exceed 1",
                          "fp64_tflops_achieved": alg_flops / world / (kernel_ms_avg * 1e-3) / 1e12,
                          "fp64_tflops_peak_measured": fp64_peak, "fp64_frac": alg_flops / world / (kernel_ms_avg * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None},
