@@ -138,3 +138,84 @@ def test_feedback_partition_converges_on_position_dependent_cost(ranks):
     # equal times are a fixed point, and the static split is reproduced by uniform feedback
     again = plan_partition_feedback("SU2", tables, cutoff, bounds, times(bounds))
     assert max(abs(a - b) for a, b in zip(again, bounds)) <= nf // 200
+
+
+def _two_steps(port, d, world, rank, dist, tables):
+    """Two cutoff steps of the sharded flow as the library runs them: static split in the first step, measured times of every rank
+    shared by a sum over one-hot vectors (pffrg_finalize_step), feedback-balanced split in the second."""
+    import time
+    import torch
+    from spinparser_b200.frgcore import plan_partition, plan_partition_feedback
+    cut = [float(x) for x in d["cutoff"][10:13]]
+    v2 = np.ascontiguousarray(d["step10/state/v2"]).copy()
+    v4 = [np.ascontiguousarray(d[f"step10/state/v4_{c}"]).copy() for c in range(port.n_arrays)]
+    per_item = port.array_len // port.nf
+    bounds, history = None, []
+    for k in range(2):
+        if bounds is None:
+            bounds = plan_partition(port.core, tables, cut[k], world)
+        else:
+            bounds = plan_partition_feedback(port.core, tables, cut[k], bounds, times)
+        history.append(list(bounds))
+        begin, end = bounds[rank], bounds[rank + 1]
+        f2 = port.v2_flow(cut[k], v2, v4)
+        t0 = time.perf_counter()
+        mine = port.v4_flow(cut[k], v2, f2, v4, np.arange(begin, end, dtype=np.int32))
+        elapsed = time.perf_counter() - t0
+        if dist is not None:
+            vec = torch.zeros(world, dtype=torch.float64)
+            vec[rank] = elapsed * 1e3
+            dist.all_reduce(vec)
+            times = vec.tolist()
+        else:
+            times = [elapsed * 1e3]
+        v2 = v2 + (cut[k + 1] - cut[k]) * f2
+        for c in range(port.n_arrays):
+            state = torch.from_numpy(v4[c])
+            lo, hi = begin * per_item, end * per_item
+            state[lo:hi] += (cut[k + 1] - cut[k]) * torch.from_numpy(mine[c][lo:hi])
+            for r in range(world if dist is not None else 0):
+                a, b = bounds[r] * per_item, bounds[r + 1] * per_item
+                if b > a:
+                    piece = state[a:b].clone()
+                    dist.broadcast(piece, src=r)
+                    state[a:b] = piece
+    return v2, v4, history
+
+
+def _worker_two_steps(rank, world, port_no, case, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_port import OraclePort
+    from spinparser_b200 import ProblemTables
+    from spinparser_b200.pfd import read_pfd
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = read_pfd(os.path.join(ROOT, "tests", "golden", case + ".f64.pfd"))
+    port = OraclePort(d)
+    v2, v4, history = _two_steps(port, d, world, rank, dist, ProblemTables.from_pfd(d))
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), v2=v2, v4=np.stack(v4), bounds=np.array(history))
+    dist.destroy_process_group()
+
+
+def test_two_rank_feedback_partition_over_two_steps(tmp_path):
+    """world_size 2 on gloo: the second step's split comes from the first step's measured times; both ranks derive the same
+    boundaries from the shared times and end in the state of an unsharded two-step run, bit for bit."""
+    import torch.multiprocessing as mp
+    from oracle_port import OraclePort
+    from spinparser_b200 import ProblemTables
+    case = "su2_square_r3_nw10"
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port_no = s.getsockname()[1]
+    mp.spawn(_worker_two_steps, args=(2, port_no, case, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(tmp_path / f"rank{r}.npz") for r in range(2)]
+    assert np.array_equal(got[0]["bounds"], got[1]["bounds"]), "ranks derived different partitions"
+    b = got[0]["bounds"]
+    assert b.shape == (2, 3) and (b[:, 0] == 0).all() and (b[:, 2] == b[0, 2]).all() and (np.diff(b, axis=1) >= 0).all()
+    assert np.array_equal(got[0]["v4"], got[1]["v4"]) and np.array_equal(got[0]["v2"], got[1]["v2"])
+    d = golden(case)
+    v2, v4, _ = _two_steps(OraclePort(d), d, 1, 0, None, ProblemTables.from_pfd(d))
+    assert np.array_equal(got[0]["v2"], v2)
+    assert np.array_equal(got[0]["v4"], np.stack(v4)), "sharded two-step state differs from the unsharded one"
