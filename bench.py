@@ -4,10 +4,13 @@
 A "step" is one cutoff step of the flow equations: computeStep (self-energy flow, quadrature node table, vertex flow of
 all Nw^2(Nw+1)/2 frequency triples x L sites x C channels) + finalizeStep (Euler update, multi-GPU exchange).
 
-Workload (BASELINE.json configs[1]): examples/cubic-J1J2.xml geometry -- SU2 core, cubic lattice range 7 (L = 31
-representatives, 575 sites in range, 8311 overlap terms), 64 positive frequencies (133 120 work items, 8.25 M vertex
-entries), cutoff grid 50 * 0.98^k. The timed steps start at k = 211 (cutoff 0.704, ~62 quadrature nodes per item and
-channel) from the PHYSICAL state reached by running the flow from the bare couplings on the GPU (untimed setup).
+Default workload (BASELINE.json config 5, the largest single-GPU configuration and the only one whose vertex exceeds the L2):
+pyrochlore Heisenberg -- SU2 core, pyrochlore lattice range 8 (L = 103 representatives, 49 334 overlap terms), 64 positive
+frequencies (133 120 work items, 27.4 M vertex entries, 222 MB FP64 vertex), cutoff grid 50 * 0.98^k. `--workload` selects the other
+configurations (cubic-J1J2 = configs[1], square-Heisenberg = configs[0], kagome-DM on the TRI core, Kitaev honeycomb on the XYZ core).
+The timed steps start at k = 211 (cutoff 0.704, ~62 quadrature nodes per item and channel) from the PHYSICAL state reached by
+running the flow from the bare couplings on the GPU (untimed setup). The reference arm (--impl reference) times the reference's own
+CPU core on the same cutoff steps.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--start-step S]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
@@ -40,6 +43,71 @@ WORKLOADS = {
     "kagome_dm_r7_tri_nw64": "kagome-DM (TRI, kagome r=7, L=34, Nw=64, 133120 items, 72.4M vertex entries)",
 }
 N_CH = {"SU2": 2, "XYZ": 4, "TRI": 16}
+DEFAULT_WORKLOAD = "pyrochlore_r8_su2_nw64"
+# CPU legs: every n-th work item, n coprime to Nw (items are su-major / t-minor: a stride sharing a factor with Nw would only ever
+# visit a few t values), sized for 10-30 s of CPU work per pass on a 16-core host
+CPU_STRIDE = {"cubic_r7_su2_nw64": 17, "square_r4_su2_nw32": 3, "pyrochlore_r8_su2_nw64": 67, "honeycomb_kitaev_r7_xyz_nw64": 17, "kagome_dm_r7_tri_nw64": 131}
+
+
+def node_counts(d, cutoff):
+    """Quadrature nodes (kernel evaluations) per channel for every transfer frequency of the mesh at this cutoff: the conventional
+    single-scale terms plus the nodes of the three Katanin segments (src/SU2/SU2FrgCore.cpp:351-392 x src/lib/Integrator.hpp:138-287,
+    node counts as in SURVEY.md 8a). Pure host arithmetic on the mesh (no device, no oracle): used to scale a strided CPU sample to the
+    whole step by the exact ratio of kernel evaluations."""
+    mesh = [float(x) for x in d["frequency"]]
+    nw = len(mesh)
+
+    def first_greater(w):
+        lo, hi = 1, nw
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if mesh[mid] > w:
+                hi = mid
+            else:
+                lo = mid + 1
+        return lo
+
+    def greater_pos(w):
+        if w <= mesh[0]:
+            return 0
+        i = first_greater(w)
+        return i if i < nw else nw - 1
+
+    def lesser_pos(w):
+        if w <= mesh[0]:
+            return 0
+        i = first_greater(w)
+        return i - 1 if i < nw else nw - 1
+
+    lesser = lambda w: -(greater_pos(-w) + 1) if w < 0 else lesser_pos(w)
+    greater = lambda w: -(lesser_pos(-w) + 1) if w < 0 else greater_pos(w)
+    out = []
+    for x in mesh:
+        n = 1 + (1 if x > 2.0 * cutoff else 0)
+        if -(x + cutoff) > -mesh[-1]:
+            umax = lesser(-(x + cutoff))
+            n += (umax + nw) + 2 if umax != -nw else 2
+        if x - cutoff > cutoff:
+            umin, umax = greater(cutoff - x), lesser(-cutoff)
+            n += (umax - umin) + 3 if umax >= umin else 2
+        if cutoff < mesh[-1]:
+            umin = greater(cutoff)
+            n += (nw - 1 - umin) + 2 if umin != nw - 1 else 2
+        out.append(n)
+    return out
+
+
+def evaluations_of_items(counts, items):
+    """Kernel evaluations (s + t + u channel) of the listed work items; item = su * Nw + t, su = so (so + 1) / 2 + uo."""
+    nw = len(counts)
+    c = np.asarray(counts, dtype=np.int64)
+    items = np.asarray(items, dtype=np.int64)
+    su, t = items // nw, items % nw
+    so = ((np.sqrt(8.0 * su + 1.0) - 1.0) * 0.5).astype(np.int64)
+    so = np.where((so + 1) * (so + 2) // 2 <= su, so + 1, so)
+    so = np.where(so * (so + 1) // 2 > su, so - 1, so)
+    uo = su - so * (so + 1) // 2
+    return int((c[so] + c[uo] + c[t]).sum())
 
 
 def measured_peaks():
@@ -101,26 +169,13 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def profiled_traffic(workload):
-    """DRAM bytes per launch of the flow kernel from the committed `ncu --set full` capture of this workload
-    (profiles/ncu_summary.json, written by tools/ncu_summary.py), or None when there is none."""
-    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
-    if not os.path.exists(path):
-        return None
-    with open(path) as f:
-        rec = json.load(f).get(workload)
-    return rec.get("dram_bytes_per_launch") if rec and not rec.get("captured_items") else None
-
-
-def profiled_limits(workload):
-    """What the committed full capture says binds the flow kernel (percent of the unit's peak, from profiles/ncu_summary.json):
-    context for `roofline`, not a live measurement. Empty when there is no capture."""
+def profiled_record(workload):
+    """Summary of the committed `ncu --set full` capture of this workload's flow kernel (profiles/ncu_summary.json, written by
+    tools/ncu_summary.py): context for `roofline` (DRAM bytes per launch, L1 data-pipe wavefronts, ...), not a live measurement.
+    Empty when there is no capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-            rec = json.load(f).get(workload) or {}
-        keys = {"l1_lsu_wavefronts_pct": "l1_data_pipe_wavefronts", "fp64_pipe_pct": "fp64_pipe", "issue_active_pct": "issue_slots",
-                "gcc_instruction_requests_pct": "gpc_instruction_cache_requests", "gcc_fill_pct": "gpc_instruction_cache_fill"}
-        return {name: round(float(rec[k]), 1) for k, name in keys.items() if rec.get(k) is not None}
+            return json.load(f).get(workload) or {}
     except Exception:  # never let a reporting extra break the bench line
         return {}
 
@@ -140,51 +195,80 @@ def synthetic_state(d, seed=20261017):
     return rng.uniform(0.0, 0.5, nw), [rng.uniform(-0.1, 0.1, length) for _ in range(n_arrays)]
 
 
-def time_reference_cpu(workload, d, start_step, v2, v4, stride, repeat, warmup):
+def time_reference_cpu(workload, d, step, v2, v4, stride, repeat, warmup, offset=0, want_rows=False):
     """Time the reference's own CPU core (oracle/_ref/oracle32 = unmodified reference sources, FP32 as shipped, OpenMP
     `parallel for schedule(guided)` over work items as in src/lib/LoadManager.hpp:551-557) on every `stride`-th work item of
-    one step. Falls back to the plain-C port (FP64) when the reference binary was not built. Returns (seconds per full step, info)."""
+    cutoff step `step`, starting from the given state. The sample is scaled to the whole step by the exact ratio of kernel
+    evaluations (quadrature nodes of the s, t and u channel of every item, `node_counts`). Falls back to the plain-C port (FP64)
+    when the reference binary was not built. Returns (seconds per full step for every timed pass, info, sampled flow rows or None)."""
     nw, L = len(d["frequency"]), int(d["lattice/size"])
     nf = nw * nw * (nw + 1) // 2
+    core = bytes(d["core"]).decode()
+    per = L * (16 if core == "TRI" else 1)
     cores = os.cpu_count() or 1
+    items = np.arange(offset, nf, stride, dtype=np.int32)
+    counts = node_counts(d, float(d["cutoff"][step]))
+    scale = evaluations_of_items(counts, np.arange(nf)) / evaluations_of_items(counts, items)
     binary = os.path.join(ROOT, "oracle", "_ref", "oracle32")
     if os.path.exists(binary):
         with tempfile.TemporaryDirectory() as tmp:
-            state = os.path.join(tmp, "state.pfd")
+            state, out = os.path.join(tmp, "state.pfd"), os.path.join(tmp, "out.pfd")
             write_pfd(state, {"v2": np.asarray(v2, dtype=np.float64), **{f"v4_{c}": np.asarray(a, dtype=np.float64) for c, a in enumerate(v4)}})
             cmd = [binary, "-r", os.path.join(ROOT, "oracle", "res"), os.path.join(ROOT, "bench_data", "tasks", workload + ".xml"),
-                   "--mode", "time", "--load-state", state, "--start-step", str(start_step), "--time-stride", str(stride),
-                   "--time-repeat", str(repeat), "--time-warmup", str(warmup), "--no-lattice", "--threads", str(cores)]
-            out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
-        rec = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
-        per_pass = rec["seconds"]
-        scale = rec["items_total"] / rec["items"]
-        return [s * scale for s in per_pass], {"kind": "reference", "cores": rec["threads"], "dtype": "f32",
-                                                "sample": f"every {stride}th work item ({rec['items']} of {rec['items_total']}), {warmup} warm-up + {repeat} timed passes of one cutoff step, scaled by {scale:.1f}"}
+                   "--mode", "time", "--time-compact", "--load-state", state, "--start-step", str(step), "--time-stride", str(stride), "--time-offset", str(offset),
+                   "--time-repeat", str(repeat), "--time-warmup", str(warmup), "--no-lattice", "--threads", str(cores)] + (["--out", out] if want_rows else [])
+            stdout = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
+            rows = None
+            if want_rows:
+                r = read_pfd(out)
+                assert np.array_equal(r["time/itemIds"], items)
+                rows = (items, np.asarray(r["time/flow/v2"], dtype=np.float64), [np.asarray(r[f"time/flowItems/v4_{c}"], dtype=np.float64).reshape(len(items), per) for c in range(len(v4))])
+        rec = json.loads([ln for ln in stdout.splitlines() if ln.startswith("{")][-1])
+        assert rec["items"] == len(items)
+        return [sec * scale for sec in rec["seconds"]], {"kind": "reference", "cores": rec["threads"], "dtype": "f32", "items": len(items), "scale": scale,
+                                                          "sample": f"every {stride}th work item of cutoff step {step} ({len(items)} of {nf}; stride coprime to Nw), {warmup} warm-up + {repeat} timed passes, "
+                                                                    f"scaled by the exact ratio of kernel evaluations ({scale:.2f})"}, rows
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_port import OraclePort
     port = OraclePort(d)
-    cutoff = float(d["cutoff"][start_step])
-    items = np.arange(0, nf, stride, dtype=np.int32)
-    times = []
+    cutoff = float(d["cutoff"][step])
+    times, rows = [], None
+    v2 = np.ascontiguousarray(v2, dtype=np.float64)
+    v4 = [np.ascontiguousarray(a, dtype=np.float64) for a in v4]
     for rep in range(warmup + repeat):
         t0 = time.perf_counter()
         f2 = port.v2_flow(cutoff, v2, v4)
-        port.v4_flow(cutoff, v2, f2, v4, items)
+        full = port.v4_flow(cutoff, v2, f2, v4, items)
         if rep >= warmup:
-            times.append((time.perf_counter() - t0) * nf / len(items))
-    return times, {"kind": "port", "cores": cores, "dtype": "f64",
-                   "sample": f"every {stride}th work item ({len(items)} of {nf}), {warmup} warm-up + {repeat} timed passes, scaled"}
+            times.append((time.perf_counter() - t0) * scale)
+        if want_rows:
+            rows = (items, f2, [a.reshape(-1, per)[items] for a in full])
+    return times, {"kind": "port", "cores": cores, "dtype": "f64", "items": len(items), "scale": scale,
+                   "sample": f"every {stride}th work item of cutoff step {step} ({len(items)} of {nf}), {warmup} warm-up + {repeat} timed passes, scaled by the exact ratio of kernel evaluations ({scale:.2f})"}, rows
+
+
+def workload_config(args, d, first_step, steps):
+    """`config` of the JSON line: identical for both arms (what is computed, not how)."""
+    cutoffs = [float(x) for x in d["cutoff"]]
+    return {"workload": WORKLOADS[args.workload], "core": bytes(d["core"]).decode(), "n_frequencies": len(d["frequency"]), "n_sites": int(d["lattice/size"]),
+            "cutoff_steps": [first_step, first_step + steps - 1], "cutoff": [cutoffs[first_step], cutoffs[first_step + steps - 1]]}
 
 
 def run_reference(args, d):
-    """--impl reference: the reference CPU core on this box's host cores, same workload / metric / unit."""
+    """--impl reference: the reference CPU core on this box's host cores, same workload, metric, unit and cutoff steps as our arm.
+    Step i of the K timed steps is a bounded sample of cutoff step start + i (a different sample offset for every step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     v2, v4 = synthetic_state(d)
-    times, info = time_reference_cpu(args.workload, d, args.start_step, v2, v4, args.cpu_stride, args.steps, args.warmup)
-    sec = sum(times) / len(times)
+    stride = args.cpu_stride or CPU_STRIDE[args.workload]
+    per_step, info = [], None
+    for w in range(args.warmup):
+        time_reference_cpu(args.workload, d, args.start_step, v2, v4, stride, 1, 0, offset=w % stride)
+    for i in range(args.steps):
+        times, info, _ = time_reference_cpu(args.workload, d, args.start_step + i, v2, v4, stride, 1, 0, offset=i % stride)
+        per_step.append(times[0])
+    sec = sum(per_step) / len(per_step)
     core = bytes(d["core"]).decode()
     nw, L = len(d["frequency"]), int(d["lattice/size"])
     nf = nw * nw * (nw + 1) // 2
@@ -192,8 +276,9 @@ def run_reference(args, d):
     line = {
         "impl": "reference", "metric": "pf-FRG cutoff steps/s", "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": info["dtype"], "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "cutoff_step": args.start_step, "cutoff": float(d["cutoff"][args.start_step]),
-                   "state": "seeded synthetic vertex (step cost is state independent)", "device": "host CPU"},
+        "config": workload_config(args, d, args.start_step, args.steps),
+        "notes": {"state": "seeded synthetic vertex (the cost of a step depends on the mesh and the cutoff only, not on the values)", "device": "host CPU",
+                  "extrapolated": "ms_per_step is the sampled time scaled to the full step; the run itself is bounded"},
         "vertex_entries_per_s": N_CH[core] * L * nf * value,
         "cpu_baseline": {"value": value, "unit": "steps/s", **{k: info[k] for k in ("cores", "kind", "sample")}},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -208,9 +293,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cubic_r7_su2_nw64", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--start-step", type=int, default=211)
-    ap.add_argument("--cpu-stride", type=int, default=16, help="CPU baseline: time every n-th work item")
+    ap.add_argument("--cpu-stride", type=int, default=0, help="CPU legs: time every n-th work item (default: per workload, coprime to Nw)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--items", type=int, default=0, help="profiling runs: restrict every step to the first N work items (not a benchmark)")
@@ -265,12 +350,14 @@ def main():
     step = 0
     if args.synthetic_state:
         sv2, sv4 = synthetic_state(d)
-        core.setState(cutoffs[args.start_step], sv2, sv4)
-        step = args.start_step
+        step = max(0, args.start_step - (args.warmup + 2))
+        core.setState(cutoffs[step], sv2, sv4)
     else:
         core.setInitialCondition(list(d["bare"]), cutoffs[0])
     t_setup = time.perf_counter()
-    while step < args.start_step:
+    untimed = args.warmup + 2  # warm-up steps + the two steps the clock sampler needs to come up
+    setup_target = step if args.synthetic_state else max(0, args.start_step - untimed)
+    while step < setup_target:
         if core.computeStep():
             raise SystemExit(f"flow diverged during setup at step {step}")
         step += 1
@@ -290,7 +377,7 @@ def main():
         core.finalizeStep(cutoffs[step])
         e1.record(stream)
         st2 = core.stats()
-        st["ms_finalize"], st["ms_exchange"] = st2["ms_finalize"], st2["ms_exchange"]
+        st["ms_finalize"], st["ms_exchange"], st["launches"] = st2["ms_finalize"], st2["ms_exchange"], st2["launches"]
         if diverged:
             raise SystemExit(f"flow diverged at step {step}")
         return e0, e1, st
@@ -314,7 +401,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     step_ms = torch.tensor([e0.elapsed_time(e1) for e0, e1, _ in records], dtype=torch.float64, device=f"cuda:{local}")
     kern_ms = torch.tensor([st["ms_v4_flow"] for _, _, st in records], dtype=torch.float64, device=f"cuda:{local}")
-    sums = torch.tensor([sum(st[k] for _, _, st in records) for k in ("kernel_evals", "alg_bytes", "alg_flops")], dtype=torch.float64, device=f"cuda:{local}")
+    sums = torch.tensor([sum(st[k] for _, _, st in records) for k in ("kernel_evals", "alg_bytes", "alg_flops", "exec_flops")], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
@@ -323,7 +410,8 @@ def main():
     ms_per_step = total_ms / args.steps
     value = 1e3 / ms_per_step
     kernel_ms_avg = float(kern_ms.mean())
-    evals, alg_bytes, alg_flops = (float(x) / args.steps for x in sums)
+    evals, alg_bytes, alg_flops, exec_flops = (float(x) / args.steps for x in sums)
+    launches = sum(st["launches"] for _, _, st in records)  # this rank's kernels (library counter): v2 flow, node table, vertex flow, Euler x2, cutoff
 
     # ---- end to end through the public API with HOST buffers: upload state, step, download state, every step
     host = core.pinnedEffectiveAction()
@@ -347,41 +435,80 @@ def main():
     state_bytes = 8 * (nw + C * L * nf)
     state_dev_mb = 8e-6 * C * ((L + 3) // 4 * 4) * nf
 
+    # ---- parity inside the bench job + CPU baseline: the reference's own CPU core (FP32 as shipped) evaluates a strided sample of
+    # the NEXT cutoff step from the GPU's current state; the GPU evaluates the same step; the sampled rows must agree to FP32 accuracy
+    parity, cpu_baseline = None, None
+    if world == 1 and not args.no_cpu_baseline and args.items == 0:
+        host_state = core.flowingFunctional()
+        stride = args.cpu_stride or CPU_STRIDE[args.workload]
+        times, info, rows = time_reference_cpu(args.workload, d, step, host_state.v2, host_state.v4, stride, 1, 1, want_rows=True)
+        cpu_baseline = {"value": 1.0 / (sum(times) / len(times)), "unit": "steps/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"], "cutoff_step": step, "cutoff": cutoffs[step]}
+        if core.computeStep():
+            raise SystemExit("flow diverged in the parity leg")
+        gpu_flow = core.flow()
+        items, ref_v2, ref_rows = rows
+        per = L * (16 if core_name == "TRI" else 1)
+        tol = 1e-5 if info["dtype"] == "f32" else 1e-10  # FP32 reference arithmetic (its own golden tolerance, test/scripted/assets/test_eval.py:14) / FP64 port
+        worst = float(np.abs(gpu_flow.v2 - ref_v2).max() / max(np.abs(ref_v2).max(), 1e-300))
+        for c, want in enumerate(ref_rows):
+            got = gpu_flow.v4[c].reshape(-1, per)[items]
+            worst = max(worst, float(np.abs(got - want).max() / np.abs(want).max()))
+        parity = {"items": int(len(items)), "max_normwise": worst, "tolerance": tol, "against": f"{info['kind']} CPU core ({info['dtype']}) from the GPU's own state at cutoff step {step}", "ok": bool(worst <= tol)}
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         from spinparser_b200._capi import lib as _lib
         fp64_peak = float(_lib.pffrg_fp64_peak(local))  # measured here: 16-chain DFMA loop on every SM
-        achieved = alg_bytes / world / (kernel_ms_avg * 1e-3) / 1e9  # per GPU: this rank's share over its kernel time
+        t_kernel = kernel_ms_avg * 1e-3
+        alg_gbs = alg_bytes / world / t_kernel / 1e9  # per GPU: this rank's share over its kernel time
+        exec_tflops = exec_flops / world / t_kernel / 1e12
+        prof = profiled_record(args.workload) if world == 1 else {}
+        # what can bind the flow kernel: DRAM traffic (ncu capture), the FP64 pipe (live: flops as executed / measured DFMA peak), the L1
+        # data pipe (ncu capture: LSU wavefronts, 128 B per clock and SM). `bound` is the largest fraction; the contractual figure from
+        # ALGORITHMIC bytes is kept as `alg_hbm` (gathers that hit in L1 / L2 never reach DRAM, so it can exceed 1 and is no HBM fraction).
+        candidates = {"fp64": {"achieved": exec_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": exec_tflops / fp64_peak if fp64_peak > 0 else None, "source": "live: executed flops / kernel time; peak = DFMA loop measured in this run"}}
+        traffic = None
+        if prof.get("dram_bytes_per_launch") and prof.get("duration_ms_under_ncu"):
+            traffic = prof["dram_bytes_per_launch"]
+            dram_gbs = traffic / (prof["duration_ms_under_ncu"] * 1e-3) / 1e9
+            candidates["hbm"] = {"achieved": dram_gbs, "peak": peak, "unit": "GB/s", "frac": dram_gbs / peak, "source": f"profiles/{prof.get('source')}: dram__bytes_read.sum + dram__bytes_write.sum per launch / launch duration under ncu"}
+        if prof.get("l1_lsu_wavefronts_pct") is not None:
+            l1_peak = 148 * 128 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e9 if clocks else 148 * 128 * 1.965e3
+            candidates["l1"] = {"achieved": prof["l1_lsu_wavefronts_pct"] / 100 * l1_peak, "peak": l1_peak, "unit": "GB/s", "frac": prof["l1_lsu_wavefronts_pct"] / 100,
+                                "source": f"profiles/{prof.get('source')}: l1tex__data_pipe_lsu_wavefronts, % of peak (one 128-byte wavefront per clock and SM)"}
+        bound = max((k for k in candidates if candidates[k]["frac"] is not None), key=lambda k: candidates[k]["frac"])
         line = {
             "metric": "pf-FRG cutoff steps/s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "cutoff_steps": [first_timed, first_timed + args.steps - 1],
-                       "cutoff": [cutoffs[first_timed], cutoffs[first_timed + args.steps - 1]],
-                       **({"PROFILING_ONLY_item_range": [0, args.items]} if args.items > 0 else {}),
-                       "state": "seeded synthetic vertex" if args.synthetic_state else f"physical: flow run on the GPU from the bare couplings for {first_timed} steps ({t_setup:.1f} s for the first {args.start_step}, untimed)",
-                       "parallelism": f"work items sharded over {world} GPU(s), vertex replicated, ncclBroadcast exchange of the updated slices",
-                       "l2": f"flushed between timed iterations (256 MiB write; device vertex {state_dev_mb:.0f} MB vs 126 MB L2)", "timing": "CUDA events on the library stream per step, max over ranks"},
+            "config": workload_config(args, d, first_timed, args.steps),
+            "notes": {**({"PROFILING_ONLY_item_range": [0, args.items]} if args.items > 0 else {}),
+                      "state": "seeded synthetic vertex" if args.synthetic_state else f"physical: flow run on the GPU from the bare couplings for {first_timed} steps ({t_setup:.1f} s of setup, untimed)",
+                      "parallelism": f"work items sharded over {world} GPU(s), vertex replicated, exchange of the updated slices over NVLink",
+                      "l2": f"flushed between timed iterations (256 MiB write; device vertex {state_dev_mb:.0f} MB vs 126 MB L2)", "timing": "CUDA events on the library stream per step, max over ranks"},
             "vertex_entries_per_s": C * L * nf * value,
             "kernel_evals_per_step": evals,
-            "alg_gb_per_step": alg_bytes / 1e9, "alg_gflop_per_step": alg_flops / 1e9,
+            "alg_gb_per_step": alg_bytes / 1e9, "alg_gflop_per_step": alg_flops / 1e9, "exec_gflop_per_step": exec_flops / 1e9,
             "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
             "breakdown_ms": {k: statistics.mean(st[k] for _, _, st in records) for k in ("ms_v2_flow", "ms_node_table", "ms_v4_flow", "ms_finalize", "ms_exchange")},
-            "launch_shape": {k: records[0][2][k] for k in ("jit_rpa", "threads", "smem_bytes", "node_batch", "rpa_batch", "rpa_warps", "min_blocks", "sub_ctas", "autotuned_shapes", "jit_compile_ms")},
-            "roofline": {"bound": "hbm", "kernel": "pffrg::v4FlowKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.workload), "profiled_pct_of_peak": profiled_limits(args.workload),
-                         "peak_source": peak_src, "note": "achieved = algorithmic gather+output bytes (SURVEY 8d: 128*L*C per kernel evaluation + 24*L*C per item) / kernel time, per GPU; gathers that hit in L2 do not reach DRAM, so `traffic` (ncu dram bytes per launch) is far below the algorithmic bytes and frac can exceed 1",
-                         "fp64_tflops_achieved": alg_flops / world / (kernel_ms_avg * 1e-3) / 1e12,
-                         "fp64_tflops_peak_measured": fp64_peak, "fp64_frac": alg_flops / world / (kernel_ms_avg * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None},
+            "launch_shape": {k: records[0][2][k] for k in ("jit_rpa", "gram_rows", "rpa_terms_merged", "threads", "smem_bytes", "node_batch", "rpa_batch", "rpa_warps", "min_blocks", "sub_ctas", "autotuned_shapes", "jit_compile_ms")},
+            "roofline": {"bound": bound, "kernel": "pffrg_v4flow_jit" if records[0][2]["jit_rpa"] else "pffrg::v4FlowKernel", **{k: candidates[bound][k] for k in ("achieved", "peak", "unit", "frac")},
+                         "traffic": traffic, "candidates": candidates,
+                         "alg_hbm": {"achieved": alg_gbs, "peak": peak, "unit": "GB/s", "frac": alg_gbs / peak, "peak_source": peak_src,
+                                     "what": "ALGORITHMIC gather + output bytes (SURVEY 8d: 128*L*C per kernel evaluation + 24*L*C per item) / kernel time, per GPU"},
+                         "alg_fp64": {"achieved": alg_flops / world / t_kernel / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "what": "flops of the reference formulation (every overlap term per node)"},
+                         "profile_capture": {k: prof.get(k) for k in ("source", "duration_ms_under_ncu", "captured_items", "l1_hit_pct", "l2_hit_pct", "fp64_pipe_pct", "issue_active_pct", "warps_active_pct", "registers_per_thread")} if prof else None},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
                     "what": "setState(pinned host arrays) + computeStep + finalizeStep + flowingFunctional(download) per step, wall clock, max over ranks"},
-            "gpu_launches": 6 * args.steps,
+            "gpu_launches": launches,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            host_state = core.flowingFunctional()
-            times, info = time_reference_cpu(args.workload, d, step, host_state.v2, host_state.v4, args.cpu_stride, 1, 1)
-            line["cpu_baseline"] = {"value": 1.0 / (sum(times) / len(times)), "unit": "steps/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
-                                    "cutoff": cutoffs[step]}
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        if parity:
+            line["parity"] = parity
         print(json.dumps(line), flush=True)
+        if parity and not parity["ok"]:
+            raise SystemExit(f"PARITY FAILURE inside the bench run: max norm-wise deviation {parity['max_normwise']:.3e} > {parity['tolerance']:.0e}")
     core.close()
     if world > 1:
         dist.destroy_process_group()

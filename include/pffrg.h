@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PFFRG_ABI_VERSION 1
+#define PFFRG_ABI_VERSION 2
 
 typedef enum pffrg_status
 {
@@ -97,6 +97,10 @@ typedef struct pffrg_stats
 	int32_t min_blocks;     /*   CTAs per SM the kernel was compiled for */
 	int32_t autotuned_shapes; /* launch shapes compiled and timed in pffrg_create (0/1: no autotuning) */
 	int32_t sub_ctas;       /* work items per CTA of the run-time compiled kernel (sub-CTAs sharing one RPA phase); fills the former tail padding */
+	int32_t gram_rows;      /* > 0: the RPA phase runs in its Gram form (rpaGram) with this many rows of the Gram matrix per block */
+	int32_t rpa_terms_merged; /* overlap terms after merging equal (rid1, rid2[, permutations]) pairs: what the RPA phase walks */
+	double exec_flops;      /* FP64 flops the kernels execute for this rank's share: as alg_flops, but the RPA term counted as implemented
+	                           (merged terms per node for the straight-line / word-stream forms; L^2 per node + merged terms per RPA phase for the Gram form) */
 } pffrg_stats;
 
 /* library / environment ------------------------------------------------------------------------------------------ */
@@ -183,6 +187,14 @@ int pffrg_jit_compile_check(const pffrg_desc *desc, int64_t *cubin_bytes);
  * Writes up to `capacity` rows {out channel, sign, first factor channel, second factor channel} and returns the number of
  * terms per buffer pair (256, or 64 for the RPA). Used by the parity tests to compare against the reference term by term. */
 int pffrg_tri_terms(int region, int32_t *terms, int capacity);
+
+/* Term tables of the Gram form of the SU2 RPA lattice sum as the kernel walks them (rpaGram, pffrg_kernels.cuh): the sum over the
+ * quadrature nodes of R[rid] = sum_i A[rid1_i] B[rid2_i] (Lattice::getOverlap(rid), src/Lattice.hpp:46-150, evaluated per node at
+ * src/SU2/SU2FrgCore.cpp:250-266) is taken as sum_i G[rid1_i][rid2_i] over the Gram matrix G = sum_nodes A (x) B, rows worked off in
+ * blocks of `rows_per_block`. Writes up to `capacity` 16-bit words ((rid1 - block * rows_per_block) * Lp + rid2) | multiplicity <<
+ * offset_bits, Lp = n_sites rounded up to 4, and seg[block * n_sites + rid] = first word of (block, rid) (blocks * n_sites + 1
+ * entries). Returns the number of words. Host only; used by the CPU tests. */
+int pffrg_gram_tables(const pffrg_desc *desc, int rows_per_block, int offset_bits, uint16_t *terms, int capacity, int32_t *seg);
 
 /* measured FP64 multiply-add peak of a device in TFLOP/s (a 16-chain DFMA loop on every SM; ~10 ms): the denominator of the
  * FP64 roofline bench.py reports next to the HBM one. Returns a negative value on failure. */

@@ -99,8 +99,8 @@ namespace harness
 	{
 		std::string taskFile, resourcePath, out, loadState, mode = "run";
 		std::vector<int> dumpSteps;
-		int maxSteps = -1, startStep = 0, threads = 0, timeStride = 1, timeRepeat = 1, timeWarmup = 1;
-		bool measure = true, verbose = false, dumpLattice = true;
+		int maxSteps = -1, startStep = 0, threads = 0, timeStride = 1, timeRepeat = 1, timeWarmup = 1, timeOffset = 0;
+		bool measure = true, verbose = false, dumpLattice = true, timeCompact = false;
 	};
 	static Options opt;
 
@@ -228,6 +228,8 @@ CommandLineOptions::CommandLineOptions(int argc, char **argv)
 		else if (a == "--time-stride") opt.timeStride = std::stoi(next());
 		else if (a == "--time-repeat") opt.timeRepeat = std::stoi(next());
 		else if (a == "--time-warmup") opt.timeWarmup = std::stoi(next());
+		else if (a == "--time-offset") opt.timeOffset = std::stoi(next());
+		else if (a == "--time-compact") opt.timeCompact = true;
 		else if (a == "--no-measure") opt.measure = false;
 		else if (a == "--no-lattice") opt.dumpLattice = false;
 		else if (a.size() && a[0] == '-') throw Exception(Exception::Type::ArgumentError, "unknown option " + a);
@@ -318,7 +320,7 @@ int SpinParser::run(int argc, char **argv)
 			*flow.cutoff = *state.cutoff;
 			auto v2item = [&](int i) { if (core == "SU2") static_cast<SU2FrgCore *>(_frgCore)->_calculateVertexSingleParticle(i); else if (core == "XYZ") static_cast<XYZFrgCore *>(_frgCore)->_calculateVertexSingleParticle(i); else static_cast<TRIFrgCore *>(_frgCore)->_calculateVertexSingleParticle(i); };
 			auto v4item = [&](int i) { if (core == "SU2") static_cast<SU2FrgCore *>(_frgCore)->_calculateVertexTwoParticle(i); else if (core == "XYZ") static_cast<XYZFrgCore *>(_frgCore)->_calculateVertexTwoParticle(i); else static_cast<TRIFrgCore *>(_frgCore)->_calculateVertexTwoParticle(i); };
-			std::vector<int> items; for (int i = 0; i < nf; i += opt.timeStride) items.push_back(i);
+			std::vector<int> items; for (int i = opt.timeOffset; i < nf; i += opt.timeStride) items.push_back(i);
 			std::vector<double> times;
 			for (int rep = 0; rep < opt.timeWarmup + opt.timeRepeat; ++rep)
 			{
@@ -333,7 +335,19 @@ int SpinParser::run(int argc, char **argv)
 			w.doubles("time/seconds", times);
 			w.scalar("time/items", (double)items.size()); w.scalar("time/itemsTotal", (double)nf); w.scalar("time/threads", (double)omp_get_max_threads());
 			w.ints("time/itemIds", items);
-			dumpState(w, "time/flow", flow);
+			if (opt.timeCompact)
+			{
+				// only the sampled items' rows (size-parity tests at the benchmark sizes: the full arrays are hundreds of MB)
+				const size_t per = flow.v4size / (size_t)nf;
+				w.reals("time/flow/v2", flow.v2, { (uint64_t)flow.v2size });
+				for (int c = 0; c < flow.nChannelArrays; ++c)
+				{
+					std::vector<real> rows(items.size() * per);
+					for (size_t k = 0; k < items.size(); ++k) std::copy(flow.v4[c] + (size_t)items[k] * per, flow.v4[c] + (size_t)(items[k] + 1) * per, rows.begin() + k * per);
+					w.reals("time/flowItems/v4_" + std::to_string(c), rows.data(), { (uint64_t)items.size(), (uint64_t)per });
+				}
+			}
+			else dumpState(w, "time/flow", flow);
 			printf("{\"core\": \"%s\", \"items\": %d, \"items_total\": %d, \"threads\": %d, \"seconds\": [", core.c_str(), (int)items.size(), nf, omp_get_max_threads());
 			for (size_t i = 0; i < times.size(); ++i) printf("%s%.6f", i ? ", " : "", times[i]);
 			printf("]}\n");

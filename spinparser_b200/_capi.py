@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpffrg.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 CORE_IDS = {"SU2": 0, "XYZ": 1, "TRI": 2}
 F32, F64 = 0, 1
 UNIQUE_ID_BYTES = 128
@@ -23,7 +23,7 @@ SYMBOLS = [
     "pffrg_num_vertex_arrays", "pffrg_vertex_array_length", "pffrg_num_items", "pffrg_comm_unique_id",
     "pffrg_comm_init", "pffrg_item_range", "pffrg_set_state", "pffrg_set_initial_condition", "pffrg_get_state", "pffrg_get_flow",
     "pffrg_compute_step", "pffrg_finalize_step", "pffrg_synchronize", "pffrg_num_channels", "pffrg_measure_correlation", "pffrg_set_item_range", "pffrg_get_stats",
-    "pffrg_stream", "pffrg_fp64_peak", "pffrg_host_alloc", "pffrg_host_free", "pffrg_host_register", "pffrg_host_unregister", "pffrg_jit_compile_check", "pffrg_tri_terms", "pffrg_plan_partition", "pffrg_plan_partition_feedback",
+    "pffrg_stream", "pffrg_fp64_peak", "pffrg_host_alloc", "pffrg_host_free", "pffrg_host_register", "pffrg_host_unregister", "pffrg_jit_compile_check", "pffrg_tri_terms", "pffrg_gram_tables", "pffrg_plan_partition", "pffrg_plan_partition_feedback",
 ]
 
 
@@ -56,6 +56,7 @@ class Stats(C.Structure):
         ("kernel_evals", C.c_int64), ("kernel_evals_t", C.c_int64), ("items", C.c_int64),
         ("alg_bytes", C.c_double), ("alg_flops", C.c_double), ("launches", C.c_int32), ("jit_rpa", C.c_int32), ("jit_compile_ms", C.c_double),
         ("threads", C.c_int32), ("smem_bytes", C.c_int32), ("node_batch", C.c_int32), ("rpa_batch", C.c_int32), ("rpa_warps", C.c_int32), ("min_blocks", C.c_int32), ("autotuned_shapes", C.c_int32), ("sub_ctas", C.c_int32),
+        ("gram_rows", C.c_int32), ("rpa_terms_merged", C.c_int32), ("exec_flops", C.c_double),
     ]
 
     def as_dict(self):
@@ -104,6 +105,7 @@ def _load() -> C.CDLL:
     lib.pffrg_host_unregister.argtypes = [vp]
     lib.pffrg_jit_compile_check.argtypes = [C.POINTER(Desc), C.POINTER(C.c_int64)]
     lib.pffrg_tri_terms.argtypes = [C.c_int, _ip, C.c_int]
+    lib.pffrg_gram_tables.argtypes = [C.POINTER(Desc), C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, _ip]
     lib.pffrg_plan_partition.argtypes = [C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_double, C.c_int, C.POINTER(C.c_int64)]
     lib.pffrg_plan_partition_feedback.argtypes = [C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_double, C.c_int, C.POINTER(C.c_int64), _dp, C.POINTER(C.c_int64)]
     if lib.pffrg_abi_version() != ABI_VERSION:

@@ -120,6 +120,8 @@ struct pffrg_context
 	DeviceArray<int> dSitesRid, dInvRid, dSitesPerm, dInvPerm, dRngFwd, dRngInv, dSlotOff;
 	DeviceArray<int4> dTasks;
 	DeviceArray<unsigned> dWords;
+	DeviceArray<unsigned short> dGramTerms; DeviceArray<int> dGramSeg; // Gram form of the RPA phase (rpaGram), when selected
+	int gramRows = 0;                                                 // rows per Gram block (0: not in use)
 	DeviceArray<unsigned short> dMeshStart; int meshShift = 52, meshKeyBase = 0, meshKeys = 0;
 	// lattice-specialised flow kernel (NVRTC), see pffrg_jit.cpp
 	cudaLibrary_t jitLibrary = nullptr;
@@ -161,6 +163,7 @@ struct pffrg_context
 		P.nw = nw; P.L = L; P.Lp = Lp; P.RL = RL; P.nf = (int)nf;
 		P.mesh = dMesh.p; P.sites_rid = dSitesRid.p; P.inv_rid = dInvRid.p; P.sites_perm = dSitesPerm.p; P.inv_perm = dInvPerm.p;
 		P.rpa_tasks = dTasks.p; P.rpa_slot_off = dSlotOff.p; P.rpa_words = dWords.p;
+		P.gram_terms = dGramTerms.p; P.gram_seg = dGramSeg.p;
 		P.nrange = (int)dRngFwd.n; P.rng_fwd = dRngFwd.p; P.rng_inv = dRngInv.p; P.spin = spin;
 		P.meshIndex.start = dMeshStart.p; P.meshIndex.shift = meshShift; P.meshIndex.keyBase = meshKeyBase; P.meshIndex.nKeys = meshKeys;
 		return P;
@@ -201,6 +204,11 @@ namespace
 	}
 
 	template <int CORE, int NB> size_t flowSmemBytes(int nw, int L, int groups, int nbt, int subs) { return FlowSmem<CORE, NB>(nw, L, groups, nbt, subs).total; }
+	// shared memory of the SU2 kernel with the Gram form of the RPA phase: gramRows rows of the Gram matrix next to nbt staged nodes
+	size_t gramSmemBytes(int nb, int nw, int L, int Lp, int groups, int nbt, int gramRows)
+	{
+		return nb == 32 ? FlowSmem<SU2, 32>(nw, L, groups, nbt, 1, gramRows, Lp).total : nb == 16 ? FlowSmem<SU2, 16>(nw, L, groups, nbt, 1, gramRows, Lp).total : FlowSmem<SU2, 8>(nw, L, groups, nbt, 1, gramRows, Lp).total;
+	}
 	// nbt = nodes staged per RPA phase (0: same as the gather batch nb)
 	size_t flowSmemBytes(int core, int nb, int nw, int L, int groups, int nbt = 0, int subs = 1)
 	{
@@ -214,7 +222,55 @@ namespace
 	// warps (one per SM sub-partition when there are four), each on its own group of 16 (SU2) or 32 staged nodes, so the
 	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Environment overrides for tuning runs:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_TILES, PFFRG_JIT_MINBLOCKS.
-	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; };
+	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0, gramOffsetBits = 0; };
+
+	// Launch shape of the kernel with the Gram form of the RPA phase (rpaGram, pffrg_kernels.cuh): the GEMM threads form a PT x 16 grid
+	// with up to four rows per thread, i.e. blocks of PB = 4 PT rows (64 with 256 threads); the staged nodes (nbt, as many as fit: the
+	// overlap list is walked once per RPA phase) and one block of the Gram matrix share the shared memory. Two CTAs per SM where 32
+	// staged nodes still fit. Environment overrides: PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_MINBLOCKS, PFFRG_GRAM_TM.
+	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax)
+	{
+		JitShape best = { 0, 0, 0, 0, 0 };
+		const int gemmThreads = threads / 64 * 64;
+		if (gemmThreads < 64) return best;
+		const int PT = gemmThreads / 16;
+		int TM = std::max(1, std::min(4, 64 / PT));
+		if (const char *e = getenv("PFFRG_GRAM_TM")) TM = std::min(8, std::max(1, atoi(e)));
+		TM = std::min(TM, (Lp + PT - 1) / PT);
+		const int PB = PT * TM;
+		int bits = 1; while ((1 << bits) < PB * Lp) ++bits;
+		if (bits > 15) return best;
+		const size_t half = (smemMax + 1024) / 2 - 1024;
+		int forcedNb = 0, forcedNbt = 0, forcedCtas = 0;
+		if (const char *e = getenv("PFFRG_JIT_NB")) forcedNb = atoi(e);
+		if (const char *e = getenv("PFFRG_JIT_NBT")) forcedNbt = atoi(e);
+		if (const char *e = getenv("PFFRG_JIT_MINBLOCKS")) forcedCtas = std::max(1, atoi(e));
+		const int nbts[] = { 64, 48, 32, 24, 16, 8 };
+		for (int pass = 0; pass < 2 && !best.nb; ++pass)
+		{
+			const int ctas = forcedCtas ? forcedCtas : 2 - pass;
+			if (!forcedCtas && ctas == 2 && threads > 256) continue; // the block update needs more than 64 registers per thread
+			const size_t budget = ctas >= 2 ? (smemMax + 1024) / ctas - 1024 : smemMax;
+			for (int nbt : nbts)
+			{
+				if (forcedNbt ? nbt != forcedNbt : (ctas == 2 && nbt < 32)) continue;
+				for (int nb : { 16, 8 })
+				{
+					if (best.nb || nbt % nb || (forcedNb && nb != forcedNb)) continue;
+					const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, PB);
+					if (smem <= budget) { best = { nb, nbt, threads / 32, ctas, smem }; best.gramRows = PB; best.gramThreads = gemmThreads; best.gramOffsetBits = bits; }
+				}
+			}
+			if (forcedCtas) break;
+		}
+		(void)half;
+		return best;
+	}
+
+	// Term tables of rpaGram: for every block of PB rows of the Gram matrix and every representative site the merged overlap terms
+	// (rid1, rid2, multiplicity) with rid1 in the block, as 16-bit words (rid1 - block * PB) * Lp + rid2 | multiplicity << bits
+	// (multiplicities that do not fit are split).
+	void buildGramTables(const pffrg_desc *d, int L, int Lp, int PB, int bits, std::vector<unsigned short> &terms, std::vector<int> &seg);
 	JitShape chooseJitShape(int core, int nw, int L, int groups, int warps, size_t smemMax)
 	{
 		const int lanes = core == SU2 ? 16 : 32;
@@ -225,6 +281,7 @@ namespace
 		for (int pass = 0; pass < 6 && !best.nb; ++pass)
 		{
 			const int nodeGroups = order[pass][0], ctas = order[pass][1];
+			if (warps < nodeGroups) continue; // every node group needs a warp of its own (rpaSpecialised: grp = warp % nodeGroups)
 			const int nbt = nodeGroups * lanes;
 			// two output tiles (instruction streams) per node group, at least four RPA warps. Measured: pyrochlore-r8 (4 groups)
 			// 316 ms with one tile, 272 ms with two; honeycomb-r7 XYZ (2 groups) 32.7 ms with two tiles, 43.1 ms with four
@@ -241,7 +298,7 @@ namespace
 			const int nbt = std::max(lanes, atoi(e) / lanes * lanes);
 			int nb = std::min(32, nbt);
 			if (const char *f = getenv("PFFRG_JIT_NB")) nb = atoi(f);
-			if ((nb == 8 || nb == 16 || nb == 32) && nbt % nb == 0)
+			if ((nb == 8 || nb == 16 || nb == 32) && nbt % nb == 0 && warps >= nbt / lanes)
 			{
 				const size_t smem = flowSmemBytes(core, nb, nw, L, groups, nbt);
 				if (smem <= smemMax) best = { nb, nbt, std::min(warps, std::max(4, 2 * (nbt / lanes))) / (nbt / lanes) * (nbt / lanes), smem <= half ? 2 : 1, smem };
@@ -346,9 +403,36 @@ namespace
 		return s;
 	}
 
+	bool wantGram(int core, int64_t uniquePairs)
+	{
+		if (core != SU2) return false;
+		long minTerms = 8000;
+		if (const char *e = getenv("PFFRG_GRAM_MIN_TERMS")) minTerms = atol(e);
+		const char *form = getenv("PFFRG_RPA");
+		return form ? std::string(form) == "gram" : uniquePairs > minTerms;
+	}
+
+	std::string gramDefines(const JitShape &s)
+	{
+		return "#define PFFRG_GRAM 1\n#define PFFRG_GRAM_THREADS " + std::to_string(s.gramThreads) + "\n#define PFFRG_GRAM_PB " + std::to_string(s.gramRows) +
+		       "\n#define PFFRG_GRAM_OFFSET_BITS " + std::to_string(s.gramOffsetBits) + "\n";
+	}
+
 	int compileCandidate(pffrg_context *h, const pffrg_desc *d, JitCandidate &c)
 	{
+		if (c.shape.gramRows > 0)
+		{
+			std::vector<char> cubin;
+			const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, 1, 1, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, std::string(), cubin, gramDefines(c.shape));
+			if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the flow kernel (Gram form) failed: %s", err.c_str());
+			CUDA_TRY(cudaLibraryLoadData(&c.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+			CUDA_TRY(cudaLibraryGetKernel(&c.kernel, c.library, "pffrg_v4flow_jit"));
+			CUDA_TRY(cudaFuncSetAttribute((const void *)c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.shape.smem));
+			return PFFRG_OK;
+		}
 		RpaProgram prog = buildRpaProgram(d, h->core, c.shape.nbt * c.shape.subs, c.shape.rpaWarps);
+		if (prog.warps < std::max(1, prog.nb / prog.lanesPerVariant) || prog.warps > c.threads / 32)
+			return fail(PFFRG_ERR_STATE, "launch shape with %d RPA warps for %d node groups (%d threads): staged nodes would be dropped", prog.warps, prog.nb / prog.lanesPerVariant, c.threads);
 		prog.maxAccumulators = defaultAccumulators(c.threads, c.shape.minBlocks);
 		prog.cluster = c.shape.cluster;
 		applyJitKnobs(prog);
@@ -366,6 +450,7 @@ namespace
 		h->jitLibrary = c.library; h->jitKernel = c.kernel;
 		h->threads = c.threads; h->groups = c.groups;
 		h->nb = c.shape.nb; h->nbt = c.shape.nbt; h->rpaWarps = c.shape.rpaWarps; h->minBlocks = c.shape.minBlocks; h->smemBytes = c.shape.smem; h->subs = c.shape.subs; h->cluster = c.shape.cluster;
+		h->gramRows = c.shape.gramRows;
 	}
 
 	// Compile and load the lattice-specialised kernel. Controlled by the environment: PFFRG_JIT=0 disables it,
@@ -386,6 +471,28 @@ namespace
 		if (h->core == TRI) return PFFRG_OK;
 		const auto t0 = std::chrono::steady_clock::now();
 		std::vector<JitCandidate> candidates;
+		// Form of the RPA phase (SU2): PFFRG_RPA=gram -- Gram matrix over the staged nodes + one walk of the overlap list per phase
+		// (rpaGram; no generated code, any lattice size); PFFRG_RPA=code -- lattice-specialised straight-line code. Default: the Gram form
+		// for lattices with more than PFFRG_GRAM_MIN_TERMS (8000) merged overlap terms, where the straight-line code no longer fits the
+		// instruction caches.
+		if (h->core == SU2)
+		{
+			const char *form = getenv("PFFRG_RPA");
+			if (wantGram(h->core, h->uniquePairs))
+			{
+				JitShape shape = chooseGramShape(h->nw, h->L, h->Lp, h->groups, h->threads, smemMax);
+				if (!shape.nb) return form ? fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_RPA=gram: no launch shape fits (threads %d, L %d)", h->threads, h->L) : PFFRG_OK;
+				JitCandidate c = { h->threads, h->groups, shape, nullptr, nullptr, 0.f };
+				const int rc = compileCandidate(h, d, c);
+				if (rc != PFFRG_OK) return rc;
+				std::vector<unsigned short> terms; std::vector<int> seg;
+				buildGramTables(d, h->L, h->Lp, shape.gramRows, shape.gramOffsetBits, terms, seg);
+				CUDA_TRY(h->dGramTerms.upload(terms)); CUDA_TRY(h->dGramSeg.upload(seg));
+				adoptCandidate(h, c);
+				h->jitCompileMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+				return PFFRG_OK;
+			}
+		}
 		JitShape first = chooseJitShape(h->core, h->nw, h->L, h->groups, h->threads / 32, smemMax);
 		if (!first.nb) return PFFRG_OK;
 		int firstThreads = h->threads;
@@ -628,6 +735,28 @@ namespace
 		return p;
 	}
 
+	void buildGramTables(const pffrg_desc *d, int L, int Lp, int PB, int bits, std::vector<unsigned short> &terms, std::vector<int> &seg)
+	{
+		const int blocks = (Lp + PB - 1) / PB, maxMult = (1 << (16 - bits)) - 1;
+		std::vector<std::map<std::tuple<int, int, int, int>, int>> merged(L);
+		for (int rid = 0; rid < L; ++rid) merged[rid] = mergedOverlap(d, SU2, rid);
+		seg.assign((size_t)blocks * L + 1, 0);
+		terms.clear();
+		for (int blk = 0; blk < blocks; ++blk)
+			for (int rid = 0; rid < L; ++rid)
+			{
+				seg[(size_t)blk * L + rid] = (int)terms.size();
+				for (auto &kv : merged[rid])
+				{
+					const int p = std::get<0>(kv.first), q = std::get<3>(kv.first);
+					if (p / PB != blk) continue;
+					for (int m = kv.second; m > 0; m -= maxMult)
+						terms.push_back((unsigned short)(((p - blk * PB) * Lp + q) | (std::min(m, maxMult) << bits)));
+				}
+			}
+		seg.back() = (int)terms.size();
+	}
+
 	// node counts per mesh frequency at the current cutoff (host copy of what nodeTableKernel enumerates)
 	std::vector<int> hostNodeCounts(const pffrg_context *h)
 	{
@@ -763,6 +892,22 @@ namespace
 		const double fmaSU = 16.0 * L * C + m.ladderTerms * L;
 		const double fmaT = 16.0 * L * C + (double)m.rpaTerms * h->overlapTotal + m.localTerms * L;
 		h->stats.alg_flops = 2.0 * ((double)(nS + nU) * fmaSU + (double)nT * fmaT);
+		// as executed: merged overlap terms; Gram form: an L x L update per node and one walk of the merged terms per RPA phase
+		double rpaFma = (double)nT * m.rpaTerms * (double)h->uniquePairs;
+		if (h->gramRows > 0)
+		{
+			std::vector<int64_t> prefixR(nw + 1, 0); // RPA phases of the t values below an index
+			for (int t = 0; t < nw; ++t) prefixR[t + 1] = prefixR[t] + (counts[t] + h->nbt - 1) / h->nbt;
+			int64_t phases = 0, blk = 0;
+			for (int so = 0; so < nw; ++so)
+				for (int uo = 0; uo <= so; ++uo, ++blk)
+				{
+					const int64_t lo = std::max<int64_t>(begin, blk * nw), hi = std::min<int64_t>(end, (blk + 1) * nw);
+					if (hi > lo) phases += prefixR[hi - blk * nw] - prefixR[lo - blk * nw];
+				}
+			rpaFma = (double)nT * C * L * L + (double)phases * C * (double)h->uniquePairs;
+		}
+		h->stats.exec_flops = 2.0 * ((double)(nS + nU) * fmaSU + (double)nT * (16.0 * L * C + m.localTerms * L) + rpaFma);
 	}
 
 	int exchangeSlices(pffrg_context *h, double *buffer)
@@ -955,7 +1100,7 @@ int pffrg_destroy(pffrg_handle h)
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->comm) nccl().CommDestroy(h->comm);
 	h->dMesh.release(); h->dSitesRid.release(); h->dInvRid.release(); h->dSitesPerm.release(); h->dInvPerm.release(); h->dRngFwd.release(); h->dRngInv.release();
-	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release(); h->dMeshStart.release();
+	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release(); h->dMeshStart.release(); h->dGramTerms.release(); h->dGramSeg.release();
 	if (h->jitLibrary) cudaLibraryUnload(h->jitLibrary); h->dV4.release(); h->dFlow4.release(); h->dV2.release(); h->dFlow2.release(); h->dCutoff.release();
 	h->dCount.release(); h->dNodeW.release(); h->dNodeWt.release(); h->dNan.release(); h->dStaging.release();
 	h->dChiPartial.release(); h->dChi.release(); h->dChiCount.release();
@@ -1200,6 +1345,7 @@ int pffrg_get_stats(pffrg_handle h, pffrg_stats *out)
 	out->jit_compile_ms = h->jitCompileMs;
 	out->threads = h->threads; out->smem_bytes = (int32_t)h->smemBytes; out->node_batch = h->nb; out->rpa_batch = h->jitKernel ? h->nbt * h->subs : h->nb; out->sub_ctas = h->jitKernel ? h->subs : 1;
 	out->autotuned_shapes = h->autotuned;
+	out->gram_rows = h->gramRows; out->rpa_terms_merged = (int32_t)h->uniquePairs;
 	out->rpa_warps = h->jitKernel ? h->rpaWarps : h->threads / 32; out->min_blocks = h->jitKernel ? h->minBlocks : (h->core == TRI ? 1 : 2);
 	return PFFRG_OK;
 }
@@ -1213,6 +1359,22 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	const int L = d->n_sites;
 	const LaunchGeometry geo = chooseGeometry(L);
 	const int groups = geo.groups, threads = geo.threads;
+	int64_t uniquePairs = 0;
+	for (int rid = 0; rid < L; ++rid) uniquePairs += (int64_t)mergedOverlap(d, d->core, rid).size();
+	if (wantGram(d->core, uniquePairs))
+	{
+		const int Lp = paddedSites(L);
+		const JitShape g = chooseGramShape(d->n_frequencies, L, Lp, groups, threads, 227 * 1024);
+		if (!g.nb) return fail(PFFRG_ERR_UNSUPPORTED, "no launch shape for the Gram form of the RPA phase");
+		std::vector<char> cubin;
+		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g));
+		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
+		std::vector<unsigned short> terms; std::vector<int> seg;
+		buildGramTables(d, L, Lp, g.gramRows, g.gramOffsetBits, terms, seg);
+		if (getenv("PFFRG_JIT_VERBOSE")) fprintf(stderr, "[pffrg gram] threads %d nb %d nbt %d ctas %d smem %zu rows/block %d gemm threads %d offset bits %d terms %zu\n", threads, g.nb, g.nbt, g.minBlocks, g.smem, g.gramRows, g.gramThreads, g.gramOffsetBits, terms.size());
+		if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
+		return PFFRG_OK;
+	}
 	JitShape shape = chooseJitShape(d->core, d->n_frequencies, L, groups, threads / 32, 227 * 1024);
 	if (!shape.nb) return fail(PFFRG_ERR_UNSUPPORTED, "lattice too large for the specialised kernel");
 	int subs = 1;
@@ -1300,6 +1462,18 @@ int pffrg_tri_terms(int region, int32_t *terms, int capacity)
 			}
 	if (!consistent) return fail(PFFRG_ERR_STATE, "TRI spin algebra produced an imaginary coefficient");
 	return n;
+}
+
+int pffrg_gram_tables(const pffrg_desc *d, int rowsPerBlock, int offsetBits, uint16_t *terms, int capacity, int32_t *seg)
+{
+	if (!d || d->n_sites < 1 || !d->overlap_offsets || rowsPerBlock < 1 || offsetBits < 1 || offsetBits > 15 || !seg || (!terms && capacity > 0)) return fail(PFFRG_ERR_ARGUMENT, "bad argument");
+	const int L = d->n_sites, Lp = paddedSites(L);
+	if ((long)rowsPerBlock * Lp > (1l << offsetBits)) return fail(PFFRG_ERR_ARGUMENT, "offset_bits too small for %d rows of %d", rowsPerBlock, Lp);
+	std::vector<unsigned short> t; std::vector<int> s;
+	buildGramTables(d, L, Lp, rowsPerBlock, offsetBits, t, s);
+	std::copy(s.begin(), s.end(), seg);
+	std::copy(t.begin(), t.begin() + std::min<size_t>(t.size(), (size_t)std::max(capacity, 0)), terms);
+	return (int)t.size();
 }
 
 double pffrg_fp64_peak(int device)

@@ -27,6 +27,8 @@ namespace pffrg
 		const int4 *rpa_tasks;   // {rid, wordBegin, wordEnd, 0}, ordered by RPA slot
 		const int *rpa_slot_off; // [nslots + 1]
 		const unsigned *rpa_words; // term stream of the generic RPA phase, see rpaGeneric
+		const unsigned short *gram_terms; // Gram form of the RPA sum (rpaGram): offset into the Gram block | multiplicity << gramOffsetBits
+		const int *gram_seg;     // [blocks * L + 1] term ranges per (row block, rid)
 		int nrange;
 		const int *rng_fwd;      // [nrange]
 		const int *rng_inv;      // [nrange]
@@ -323,12 +325,14 @@ namespace pffrg
 	{
 		static constexpr int C = channelsOf(CORE);
 		static constexpr int NBP = NB + 1;
-		size_t mesh, bw, bW, lerp, ab, loc, wmat, privateBytes, st, part, partStride, rpa, staged, total;
+		size_t mesh, bw, bW, lerp, ab, loc, wmat, privateBytes, st, part, partStride, rpa, staged, gram, total;
 		int rpaCopies;
 		// nbt = nodes staged per RPA phase and sub-CTA (a multiple of NB; NB itself in the precompiled kernels); subs = sub-CTAs
 		// per CTA (run-time compiled kernel only): each has its own tables (offsets below are relative to its private block of
 		// privateBytes), all share ONE staging area of subs * nbt nodes and one RPA phase
-		__host__ __device__ FlowSmem(int nw, int L, int groups, int nbt = NB, int subs = 1)
+		// gramRows > 0 (run-time compiled SU2 kernel, rpaGram): the operands are staged node-major as channel pairs, st[buffer][node][Lp] of
+		// double2, and a block of gramRows x Lp entries of the Gram matrix (double2) lives next to them
+		__host__ __device__ FlowSmem(int nw, int L, int groups, int nbt = NB, int subs = 1, int gramRows = 0, int Lp = 0)
 		{
 			size_t o = 0;
 			mesh = o; o += sizeof(double) * nw;
@@ -343,7 +347,8 @@ namespace pffrg
 			o = alignUp(o, 16);
 			privateBytes = o; o *= subs;
 			// the per-group partial sums of the epilogue reuse the staging area (dead by then)
-			const size_t stBytes = (CORE == TRI && NB == 8) ? sizeof(double) * 4 * tri8BufferStride(L) : sizeof(double) * RpaStage<CORE>::buffers * C * L * (subs * nbt + 1);
+			const size_t stBytes = gramRows > 0 ? sizeof(double) * 2 * C * Lp * (subs * nbt)
+			                     : (CORE == TRI && NB == 8) ? sizeof(double) * 4 * tri8BufferStride(L) : sizeof(double) * RpaStage<CORE>::buffers * C * L * (subs * nbt + 1);
 			partStride = sizeof(double) * groups * C * L;
 			const size_t partBytes = partStride * subs;
 			st = o; part = o; o += stBytes > partBytes ? stBytes : partBytes;
@@ -352,6 +357,8 @@ namespace pffrg
 			rpaCopies = subs * nbt / (CORE == SU2 ? 16 : 32); if (rpaCopies < 2) rpaCopies = 2;
 			rpa = o; o += sizeof(double) * C * L * rpaCopies;
 			staged = o; if (subs > 1) o += sizeof(int) * 4; // nodes staged by each sub-CTA for the coming RPA phase
+			o = alignUp(o, 16);
+			gram = o; o += sizeof(double) * C * (size_t)gramRows * Lp;
 			total = alignUp(o, 16);
 		}
 	};
@@ -1001,7 +1008,7 @@ namespace pffrg
 		}
 	}
 
-#ifdef PFFRG_JIT_RPA
+#if defined(PFFRG_JIT_RPA) && !defined(PFFRG_GRAM)
 	// generated per lattice (pffrg_jit.cpp): the RPA sum of one batch for the outputs owned by `warp`
 	static __device__ __forceinline__ void rpaSpecialised(int warp, int lane, int nb, const double *st, double *rpaOut);
 #endif
@@ -1099,6 +1106,129 @@ namespace pffrg
 		}
 	}
 
+#ifdef PFFRG_GRAM
+	// ================================================================================================================
+	// Gram-matrix form of the RPA lattice sum (SU2; run-time compiled kernel with PFFRG_GRAM, see pffrg.cu chooseGramShape).
+	//
+	// The reference evaluates, per quadrature node k, R_c[rid] = sum_i A_c,k[rid1_i] B_c,k[rid2_i] over the overlap list of every
+	// representative site (src/SU2/SU2FrgCore.cpp:250-266): overlapTotal multiply-adds per node and channel. The node sum commutes
+	// with the lattice sum:
+	//     sum_k R_c,k[rid] = sum_i G_c[rid1_i][rid2_i],     G_c[p][q] = sum_k A_c,k[p] B_c,k[q]   (an L x L Gram matrix),
+	// so the per-node work becomes a dense, regular L x L rank-1 update (L^2 multiply-adds: 10 609 instead of 40 355 merged terms at
+	// pyrochlore-r8, 961 instead of 3 453 at cubic-r7) and the overlap list is walked once per RPA phase instead of once per node.
+	// No generated code: nothing to stream through the instruction caches, no limit on the lattice size.
+	//
+	//  - GEMM: the operands of the staged nodes lie node-major, st[buffer][node][Lp] of double2 {spin, density}. Threads form a
+	//    PT x 16 grid (a warp = 4 x 8); thread (tp, tq) accumulates G[rowBase + tp + PT i][tq + 16 j], i < TM, j < TN, for both
+	//    channels in registers: per node TM + TN 16-byte shared loads (contiguous across the lanes, broadcast across the other
+	//    lane index) feed 2 TM TN FP64 multiply-adds.
+	//  - The rows are worked off in blocks of PB = PT * TM rows: the block is written to shared memory (Gs[row][q] of double2) and
+	//    reduced at once: warp w owns the representative sites w, w + warps, ...; its lanes stride over the site's terms of this
+	//    block (16-bit words: offset into Gs | multiplicity), one 16-byte load + two multiply-adds per term, then a shuffle
+	//    reduction and a single-writer update of the output.
+	// ================================================================================================================
+	namespace gramcfg
+	{
+		constexpr int Lp = PFFRG_CONST_LP;
+		constexpr int NT = PFFRG_GRAM_THREADS;         // threads taking part in the GEMM (a multiple of 64)
+		constexpr int PT = NT / 16;                    // thread rows
+		constexpr int TM = PFFRG_GRAM_PB / PT;         // rows per thread in a full block
+		constexpr int PB = PFFRG_GRAM_PB;              // rows per block
+		constexpr int TN = (Lp + 15) / 16;             // columns per thread
+		constexpr int NBLK = (Lp + PB - 1) / PB;
+		constexpr int LAST_ROWS = Lp - (NBLK - 1) * PB;
+		constexpr int TM_LAST = (LAST_ROWS + PT - 1) / PT;
+		constexpr int OFFSET_BITS = PFFRG_GRAM_OFFSET_BITS; // bits of a term word that address Gs
+		static_assert(NT % 64 == 0 && PB % PT == 0 && TM >= 1 && PB * Lp <= (1 << OFFSET_BITS), "Gram geometry");
+	}
+
+	template <int TMB>
+	__device__ __forceinline__ void gramBlock(const double2 *__restrict__ stA, const double2 *__restrict__ stB, int nb, int rowBase, int rows, double2 *__restrict__ Gs, int tp, int tq)
+	{
+		using namespace gramcfg;
+		double2 acc[TMB][TN];
+		int pa[TMB], qb[TN];
+		#pragma unroll
+		for (int i = 0; i < TMB; ++i) pa[i] = min(rowBase + tp + PT * i, Lp - 1); // rows / columns past the end repeat the last one (never stored)
+		#pragma unroll
+		for (int j = 0; j < TN; ++j) qb[j] = min(tq + 16 * j, Lp - 1);
+		#pragma unroll
+		for (int i = 0; i < TMB; ++i)
+		{
+			#pragma unroll
+			for (int j = 0; j < TN; ++j) acc[i][j] = make_double2(0.0, 0.0);
+		}
+		#pragma unroll 2
+		for (int k = 0; k < nb; ++k)
+		{
+			const double2 *A = stA + k * Lp, *B = stB + k * Lp;
+			double2 a[TMB], b[TN];
+			#pragma unroll
+			for (int i = 0; i < TMB; ++i) a[i] = A[pa[i]];
+			#pragma unroll
+			for (int j = 0; j < TN; ++j) b[j] = B[qb[j]];
+			#pragma unroll
+			for (int i = 0; i < TMB; ++i)
+			{
+				#pragma unroll
+				for (int j = 0; j < TN; ++j) { acc[i][j].x = fma(a[i].x, b[j].x, acc[i][j].x); acc[i][j].y = fma(a[i].y, b[j].y, acc[i][j].y); }
+			}
+		}
+		__syncthreads(); // the reduction of the previous block has read Gs
+		#pragma unroll
+		for (int i = 0; i < TMB; ++i)
+		{
+			if (tp + PT * i >= rows) continue;
+			#pragma unroll
+			for (int j = 0; j < TN; ++j) if (tq + 16 * j < Lp) Gs[(tp + PT * i) * Lp + tq + 16 * j] = acc[i][j];
+		}
+	}
+
+	// reduction of one row block: rpaOut[c * L + rid] += sum over the block's terms of rid of multiplicity * Gs[offset].c
+	__device__ __forceinline__ void gramReduce(const Problem &P, int blk, const double2 *__restrict__ Gs, double *rpaOut, int warp, int lane, int warps)
+	{
+		using namespace gramcfg;
+		constexpr int L = PFFRG_CONST_L;
+		const int *seg = P.gram_seg + blk * L;
+		for (int rid = warp; rid < L; rid += warps)
+		{
+			const int begin = __ldg(seg + rid), end = __ldg(seg + rid + 1);
+			double sx = 0.0, sy = 0.0;
+			#pragma unroll 4
+			for (int i = begin + lane; i < end; i += 32)
+			{
+				const unsigned w = __ldg(P.gram_terms + i);
+				const double2 g = Gs[w & ((1u << OFFSET_BITS) - 1u)];
+				const double m = (double)(int)(w >> OFFSET_BITS);
+				sx = fma(m, g.x, sx); sy = fma(m, g.y, sy);
+			}
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+			if (lane == 0 && end > begin) { rpaOut[rid] += sx; rpaOut[L + rid] += sy; }
+		}
+	}
+
+	// RPA phase over `nb` staged nodes. All threads of the CTA call it (CTA barriers inside).
+	__device__ __forceinline__ void rpaGram(const Problem &P, const double2 *__restrict__ st2, int nodeCapacity, int nb, double2 *__restrict__ Gs, double *rpaOut)
+	{
+		using namespace gramcfg;
+		const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = blockDim.x >> 5;
+		const int tp = (warp >> 1) * 4 + (lane >> 3), tq = (warp & 1) * 8 + (lane & 7);
+		const bool gemm = tid < NT;
+		const double2 *stA = st2, *stB = st2 + (size_t)nodeCapacity * Lp;
+		#pragma unroll 1
+		for (int blk = 0; blk < NBLK - 1; ++blk)
+		{
+			if (gemm) gramBlock<TM>(stA, stB, nb, blk * PB, PB, Gs, tp, tq); else __syncthreads();
+			__syncthreads();
+			gramReduce(P, blk, Gs, rpaOut, warp, lane, warps);
+		}
+		if (gemm) gramBlock<TM_LAST>(stA, stB, nb, (NBLK - 1) * PB, LAST_ROWS, Gs, tp, tq); else __syncthreads();
+		__syncthreads();
+		gramReduce(P, NBLK - 1, Gs, rpaOut, warp, lane, warps);
+	}
+#endif
+
 	// SUB > 1 (run-time compiled kernel only): the CTA is made of SUB independent sub-CTAs, each working on its own item
 	// (consecutive items) with its own tables and its own barriers; they meet only for the RPA phase, which then runs ONE pass
 	// of the straight-line code over the nodes staged by all of them. The code of that phase is streamed through the
@@ -1114,7 +1244,14 @@ namespace pffrg
 		static_assert(NBT % NB == 0 && (JIT || NBT == NB), "the precompiled kernels stage one gather batch per RPA phase");
 		static_assert(SUB >= 1 && SUB <= 4 && (SUB == 1 || JIT), "sub-CTAs exist in the run-time compiled kernel only");
 		extern __shared__ __align__(16) unsigned char smemRaw[];
+#ifdef PFFRG_GRAM
+		static_assert(CORE == SU2 && SUB == 1 && CL == 1 && JIT, "the Gram form of the RPA phase exists for the SU2 core, one work item per CTA");
+		constexpr bool GRAM = true;
+		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT, SUB, gramcfg::PB, gramcfg::Lp);
+#else
+		constexpr bool GRAM = false;
 		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT, SUB);
+#endif
 		const int nthreads = blockDim.x / SUB;                       // threads of one sub-CTA
 		const int sub = SUB == 1 ? 0 : threadIdx.x / nthreads;
 		const int tid = threadIdx.x - sub * nthreads;
@@ -1134,6 +1271,12 @@ namespace pffrg
 		const int L = sizeL(P), nw = sizeNw(P);
 		for (int i = tid; i < nw; i += nthreads) mesh[i] = P.mesh[i];
 		for (int i = threadIdx.x; i < lay.rpaCopies * C * L; i += blockDim.x) rpaOut[i] = 0.0;
+#ifdef PFFRG_GRAM
+		// padding sites of the node-major staging rows: read by the Gram update (their products are never used), never written below
+		if (gramcfg::Lp > L)
+			for (int i = threadIdx.x; i < 2 * NBTT * (gramcfg::Lp - L); i += blockDim.x)
+				reinterpret_cast<double2 *>(st)[(i / (gramcfg::Lp - L)) * gramcfg::Lp + L + i % (gramcfg::Lp - L)] = make_double2(0.0, 0.0);
+#endif
 
 		// work item -> (s, t, u), expandIterator SU2VertexTwoParticle.hpp:136-158
 		const int itemFirst = itemBegin + blockIdx.x * SUB, itemEnd = itemBegin + cfg.items;
@@ -1292,7 +1435,14 @@ namespace pffrg
 								if (CORE == SU2) { opA[c] = W * (c == 0 ? 2.0 : 8.0) * P.spin * A[2][c]; opB[c] = A[3][c]; }
 								else { opA[c] = W * 4.0 * A[0][c]; opB[c] = A[1][c]; }
 							}
-							if (JIT)
+							if (GRAM)
+							{
+								// node-major channel pairs: st2[buffer][node][Lp]
+								double2 *st2 = reinterpret_cast<double2 *>(st);
+								st2[(stageOff + node) * sizeLp(P) + j] = make_double2(opA[0], opA[1]);
+								st2[(NBTT + stageOff + node) * sizeLp(P) + j] = make_double2(opB[0], opB[1]);
+							}
+							else if (JIT)
 							{
 								#pragma unroll
 								for (int c = 0; c < C; ++c)
@@ -1324,7 +1474,10 @@ namespace pffrg
 				__syncthreads();
 				clusterRendezvous<CL>();
 				// ---- phase 2: RPA lattice sum over the staged nodes (of all sub-CTAs)
-#ifdef PFFRG_JIT_RPA
+#ifdef PFFRG_GRAM
+				if (GRAM) rpaGram(P, reinterpret_cast<const double2 *>(st), NBTT, staged, reinterpret_cast<double2 *>(smemRaw + lay.gram), rpaOut);
+				else
+#elif defined(PFFRG_JIT_RPA)
 				if (JIT)
 				{
 					// node group of this warp -> the sub-CTA whose nodes it works on: columns [h * NBT, h * NBT + staged_h) are live

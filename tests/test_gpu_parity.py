@@ -30,7 +30,13 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             # thread-block clusters whose CTAs rendezvous before every RPA phase (grid padded to whole clusters)
             {"PFFRG_CLUSTER": "2"}, {"PFFRG_CLUSTER": "4", "PFFRG_SUBCTAS": "2", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"},
             # t channel: buffers 2, 3 formed from the rows loaded for buffers 0, 1 (gatherTwo)
-            {"PFFRG_MIRROR": "1"}]
+            {"PFFRG_MIRROR": "1"},
+            # small CTAs on their own: fewer warps than the preferred number of node groups (the shape search must skip those)
+            {"PFFRG_THREADS": "64"}, {"PFFRG_THREADS": "96"},
+            # SU2: Gram form of the RPA phase (rpaGram) -- default shape, several RPA phases per item, other thread grids / block sizes
+            {"PFFRG_RPA": "gram"}, {"PFFRG_RPA": "gram", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}, {"PFFRG_RPA": "gram", "PFFRG_THREADS": "128"},
+            {"PFFRG_RPA": "gram", "PFFRG_THREADS": "512", "PFFRG_GRAM_TM": "1"}, {"PFFRG_RPA": "gram", "PFFRG_THREADS": "96", "PFFRG_JIT_NBT": "8", "PFFRG_JIT_NB": "8"},
+            {"PFFRG_RPA": "gram", "PFFRG_GRAM_TM": "1", "PFFRG_JIT_MINBLOCKS": "1"}]
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
@@ -38,10 +44,14 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
 def test_one_step_flow_matches_reference(case, variant, monkeypatch):
     if case.startswith("tri") and ("PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant or "PFFRG_SUBCTAS" in variant or "PFFRG_CLUSTER" in variant or "PFFRG_MIRROR" in variant):
         pytest.skip("the TRI core has no run-time compiled variant")
+    if "PFFRG_RPA" in variant and not case.startswith("su2"):
+        pytest.skip("the Gram form of the RPA phase exists for the SU2 core")
     for k, x in variant.items():
         monkeypatch.setenv(k, x)
     d = golden(case)
     name, core = _core(d)
+    if variant.get("PFFRG_RPA") == "gram":
+        assert core.stats()["jit_rpa"] == 1
     n = core.n_arrays
     cut = d["cutoff"]
     for step in dumped_steps(d):

@@ -20,7 +20,7 @@ for f in sorted(glob.glob("gpurun_out/${TAG}_bench_*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         r = d.get("roofline", {})
-        print(f.split("_bench_")[1][:-5], "| steps/s %.3f" % d["value"], "| ms/step %.2f" % d["ms_per_step"], "| e2e %.3f" % (d["e2e"]["value"] or 0), "| hbm frac %s" % r.get("frac"), "| fp64 %s" % r.get("fp64_tflops_achieved"), "| cpu", (d.get("cpu_baseline") or {}).get("value"), "|", d.get("launch_shape"))
+        print(f.split("_bench_")[1][:-5], "| steps/s %.3f" % d["value"], "| ms/step %.2f" % d["ms_per_step"], "| e2e %.3f" % (d["e2e"]["value"] or 0), "| bound %s frac %s" % (r.get("bound"), r.get("frac")), "| alg-hbm %s" % (r.get("alg_hbm") or {}).get("frac"), "| parity", d.get("parity"), "| cpu", (d.get("cpu_baseline") or {}).get("value"), "|", d.get("launch_shape"))
     except Exception as e:
         print(f, "FAILED", e)
 PY

@@ -10,7 +10,7 @@ for cfg in "$@"; do
 import json,sys
 try:
     d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-    print('$WL | $cfg |', 'v4 ms %.2f' % d['breakdown_ms']['ms_v4_flow'], '| step ms %.2f' % d['ms_per_step'], '| TF64 %.2f' % d['roofline']['fp64_tflops_achieved'], '|', d['launch_shape'])
+    print('$WL | $cfg |', 'v4 ms %.2f' % d['breakdown_ms']['ms_v4_flow'], '| step ms %.2f' % d['ms_per_step'], '| TF64 exec %.2f' % d['roofline']['candidates']['fp64']['achieved'], '|', d['launch_shape'])
 except Exception as e:
     print('$WL | $cfg | FAILED', e, open('gpurun_out/${TAG}_sweep.err').read()[-300:])
 " >> $OUT
