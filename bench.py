@@ -41,12 +41,15 @@ WORKLOADS = {
     "pyrochlore_r8_su2_nw64": "pyrochlore-Heisenberg (SU2, pyrochlore r=8, L=103, Nw=64, 133120 items, 27.4M vertex entries)",
     "honeycomb_kitaev_r7_xyz_nw64": "honeycomb-Kitaev (XYZ, honeycomb r=7, L=18, Nw=64, 133120 items, 9.6M vertex entries)",
     "kagome_dm_r7_tri_nw64": "kagome-DM (TRI, kagome r=7, L=34, Nw=64, 133120 items, 72.4M vertex entries)",
+    "pyrochlore_r10_su2_nw64": "pyrochlore-Heisenberg (SU2, pyrochlore r=10, L=185, Nw=64, 133120 items, 49.3M vertex entries)",
+    "honeycomb_kitaev_r10_xyz_nw64": "honeycomb-Kitaev (XYZ, honeycomb r=10, L=33, Nw=64, 133120 items, 17.6M vertex entries)",
 }
 N_CH = {"SU2": 2, "XYZ": 4, "TRI": 16}
 DEFAULT_WORKLOAD = "pyrochlore_r8_su2_nw64"
 # CPU legs: every n-th work item, n coprime to Nw (items are su-major / t-minor: a stride sharing a factor with Nw would only ever
 # visit a few t values), sized for 10-30 s of CPU work per pass on a 16-core host
-CPU_STRIDE = {"cubic_r7_su2_nw64": 17, "square_r4_su2_nw32": 3, "pyrochlore_r8_su2_nw64": 67, "honeycomb_kitaev_r7_xyz_nw64": 17, "kagome_dm_r7_tri_nw64": 131}
+CPU_STRIDE = {"cubic_r7_su2_nw64": 17, "square_r4_su2_nw32": 3, "pyrochlore_r8_su2_nw64": 67, "honeycomb_kitaev_r7_xyz_nw64": 17,
+              "kagome_dm_r7_tri_nw64": 131, "pyrochlore_r10_su2_nw64": 131, "honeycomb_kitaev_r10_xyz_nw64": 33}
 
 
 def node_counts(d, cutoff):

@@ -122,6 +122,7 @@ struct pffrg_context
 	DeviceArray<unsigned> dWords;
 	DeviceArray<unsigned short> dGramTerms; DeviceArray<int> dGramSeg; // Gram form of the RPA phase (rpaGram), when selected
 	int gramRows = 0;                                                 // rows per Gram block (0: not in use)
+	int itemOrder = 0;                                                // FlowConfig::order of the run-time compiled kernel (PFFRG_ORDER=t: t-major)
 	DeviceArray<unsigned short> dMeshStart; int meshShift = 52, meshKeyBase = 0, meshKeys = 0;
 	// lattice-specialised flow kernel (NVRTC), see pffrg_jit.cpp
 	cudaLibrary_t jitLibrary = nullptr;
@@ -234,7 +235,9 @@ namespace
 		const int gemmThreads = threads / 64 * 64;
 		if (gemmThreads < 64) return best;
 		const int PT = gemmThreads / 16;
+		const int TN = (Lp + 15) / 16;
 		int TM = std::max(1, std::min(4, 64 / PT));
+		TM = std::max(1, std::min(TM, 28 / TN)); // accumulators per thread: 2 TM TN doubles, kept within the register file
 		if (const char *e = getenv("PFFRG_GRAM_TM")) TM = std::min(8, std::max(1, atoi(e)));
 		TM = std::min(TM, (Lp + PT - 1) / PT);
 		const int PB = PT * TM;
@@ -318,7 +321,7 @@ namespace
 		auto kernel = v4FlowKernel<CORE, NB>;
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes);
 		if (e != cudaSuccess) return e;
-		FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes; cfg.items = (int)count;
+		FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes; cfg.items = (int)count; cfg.order = 0;
 		kernel<<<(unsigned)count, h->threads, h->smemBytes, h->stream>>>(h->problem(), h->nodeTable(), cfg, h->dV4.p, h->dFlow4.p, (int)begin, h->dNan.p);
 		return cudaGetLastError();
 	}
@@ -361,9 +364,11 @@ namespace
 		{
 			Problem P = h->problem(); NodeTable N = h->nodeTable();
 			FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes; cfg.items = (int)count;
+			cfg.order = (h->subs == 1 && h->cluster == 1) ? h->itemOrder : 0;
 			const double *v4 = h->dV4.p; double *flow = h->dFlow4.p; int itemBegin = (int)begin; int *nan = h->dNan.p;
 			void *args[] = { &P, &N, &cfg, &v4, &flow, &itemBegin, &nan };
-			const int64_t ctas = (count + h->subs - 1) / h->subs; // padded to whole clusters (the kernel carries __cluster_dims__)
+			int64_t ctas = (count + h->subs - 1) / h->subs; // padded to whole clusters (the kernel carries __cluster_dims__)
+			if (cfg.order == 1) ctas = ((begin + count - 1) / h->nw - begin / h->nw + 1) * h->nw; // t-major: whole (s,u) blocks
 			return cudaLaunchKernel((const void *)h->jitKernel, dim3((unsigned)((ctas + h->cluster - 1) / h->cluster * h->cluster)), dim3(h->threads), args, h->smemBytes, h->stream);
 		}
 		if (h->core == SU2) return h->nb == 32 ? launchFlow<SU2, 32>(h, begin, count) : h->nb == 16 ? launchFlow<SU2, 16>(h, begin, count) : launchFlow<SU2, 8>(h, begin, count);
@@ -1087,6 +1092,7 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 		return code;
 	}
 	h->bounds = { 0, h->nf };
+	if (const char *e = getenv("PFFRG_ORDER")) h->itemOrder = (e[0] == 't' || e[0] == '1') ? 1 : 0;
 	const int jitStatus = setupJit(h, d, (size_t)prop.sharedMemPerBlockOptin);
 	if (jitStatus != PFFRG_OK) { pffrg_destroy(h); return jitStatus; }
 	*out = h;

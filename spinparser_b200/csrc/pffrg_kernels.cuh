@@ -278,6 +278,9 @@ namespace pffrg
 		int nslots;      // RPA slots of the generic phase 2 = warps * (32 / NB)
 		int smemBytes;
 		int items;       // work items of this launch (a CTA of SUB sub-CTAs covers SUB consecutive items; the last one may be partial)
+		int order;       // 0: CTA b works on item itemBegin + b; 1: t-major -- CTA b works on (su0 + b % nsu) * Nw + b / nsu, su0 / nsu the (s,u) blocks the
+		                 // launch touches (grid = nsu * Nw CTAs, those outside the item range idle): CTAs that run at the same time share the transfer
+		                 // frequency t, so their t-channel gathers (rows (s', t, u') for all s', u') hit the same 1/Nw of the vertex in L2
 	};
 
 	// Cluster-wide rendezvous before an RPA phase (CL = CTAs per thread-block cluster > 1; the run-time compiled kernel carries __cluster_dims__):
@@ -1279,8 +1282,16 @@ namespace pffrg
 #endif
 
 		// work item -> (s, t, u), expandIterator SU2VertexTwoParticle.hpp:136-158
-		const int itemFirst = itemBegin + blockIdx.x * SUB, itemEnd = itemBegin + cfg.items;
-		const bool valid = itemFirst + sub < itemEnd; // a sub-CTA past the end (partial last CTA, padding CTAs of a cluster) only takes part in the barriers
+		const int itemEnd = itemBegin + cfg.items;
+		int itemFirst = itemBegin + blockIdx.x * SUB;
+		bool inRange = true;
+		if (SUB == 1 && CL == 1 && cfg.order == 1)
+		{
+			const int su0 = itemBegin / sizeNw(P), nsu = (itemEnd - 1) / sizeNw(P) - su0 + 1;
+			itemFirst = (su0 + (int)(blockIdx.x % nsu)) * sizeNw(P) + (int)(blockIdx.x / nsu);
+			inRange = itemFirst >= itemBegin;
+		}
+		const bool valid = inRange && itemFirst + sub < itemEnd; // a sub-CTA past the end (partial last CTA, padding CTAs of a cluster) only takes part in the barriers
 		const int item = valid ? itemFirst + sub : itemEnd - 1;
 		const int su = item / nw, ti = item - su * nw;
 		int so = (int)((sqrt(8.0 * su + 1.0) - 1.0) * 0.5);

@@ -36,7 +36,9 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             # SU2: Gram form of the RPA phase (rpaGram) -- default shape, several RPA phases per item, other thread grids / block sizes
             {"PFFRG_RPA": "gram"}, {"PFFRG_RPA": "gram", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}, {"PFFRG_RPA": "gram", "PFFRG_THREADS": "128"},
             {"PFFRG_RPA": "gram", "PFFRG_THREADS": "512", "PFFRG_GRAM_TM": "1"}, {"PFFRG_RPA": "gram", "PFFRG_THREADS": "96", "PFFRG_JIT_NBT": "8", "PFFRG_JIT_NB": "8"},
-            {"PFFRG_RPA": "gram", "PFFRG_GRAM_TM": "1", "PFFRG_JIT_MINBLOCKS": "1"}]
+            {"PFFRG_RPA": "gram", "PFFRG_GRAM_TM": "1", "PFFRG_JIT_MINBLOCKS": "1"},
+            # t-major CTA -> work item map (CTAs that run at the same time share the transfer frequency t)
+            {"PFFRG_ORDER": "t", "PFFRG_CLUSTER": "1"}, {"PFFRG_ORDER": "t", "PFFRG_RPA": "gram"}]
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
@@ -75,7 +77,8 @@ def test_one_step_flow_matches_reference(case, variant, monkeypatch):
     core.close()
 
 
-@pytest.mark.parametrize("variant", [{}, {"PFFRG_CLUSTER": "4"}, {"PFFRG_SUBCTAS": "3", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8", "PFFRG_CLUSTER": "2"}],
+@pytest.mark.parametrize("variant", [{}, {"PFFRG_CLUSTER": "4"}, {"PFFRG_SUBCTAS": "3", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8", "PFFRG_CLUSTER": "2"},
+                                     {"PFFRG_ORDER": "t", "PFFRG_CLUSTER": "1"}, {"PFFRG_ORDER": "t", "PFFRG_RPA": "gram"}],
                          ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
 @pytest.mark.parametrize("case", ["su2_kagome_r4_nw8", "xyz_kagome_r4_nw8"])
 def test_item_range_with_padded_grid(case, variant, monkeypatch):
