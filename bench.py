@@ -333,11 +333,17 @@ def main():
     C = N_CH[core_name]
     cutoffs = [float(x) for x in d["cutoff"]]
     opts = {"spin": str(float(d["spinLength"]))} if core_name == "SU2" else {}
-    core = FrgCoreFactory.newFrgCore(core_name, ProblemTables.from_pfd(d), opts, device=local)
     if world > 1:
-        ids = [core.uniqueId() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        core.initCommunicator(ids[0], rank, world)
+        # rank 0 tunes the launch shape, the other ranks adopt its choice: one shape on all ranks (bit-identical sharding)
+        core = FrgCoreFactory.newFrgCore(core_name, ProblemTables.from_pfd(d), opts, device=local) if rank == 0 else None
+        shared = [(core.uniqueId(), core.shapeEnvironment()) if rank == 0 else None]
+        dist.broadcast_object_list(shared, src=0)
+        if rank != 0:
+            os.environ.update(shared[0][1])
+            core = FrgCoreFactory.newFrgCore(core_name, ProblemTables.from_pfd(d), opts, device=local)
+        core.initCommunicator(shared[0][0], rank, world)
+    else:
+        core = FrgCoreFactory.newFrgCore(core_name, ProblemTables.from_pfd(d), opts, device=local)
 
     if args.items > 0:
         core.setItemRange(0, min(args.items, nf))
@@ -423,18 +429,24 @@ def main():
     for _ in range(args.e2e_steps):
         barrier()
         t0 = time.perf_counter()
-        core.setState(host.cutoff, host.v2, host.v4)
+        core.setState(host.cutoff, host.v2, host.v4, sharded=world > 1)
         if core.computeStep():
             raise SystemExit("flow diverged in the end-to-end leg")
         step += 1
         core.finalizeStep(cutoffs[step])
-        core.flowingFunctional(into=host)
+        if world > 1:
+            core.flowingFunctional(into=host, items=core.uploadSlice())  # every rank reads back its share of the rows
+        else:
+            core.flowingFunctional(into=host)
         barrier()
         e2e_times.append(time.perf_counter() - t0)
     e2e_t = torch.tensor(e2e_times, dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = 1.0 / float(e2e_t.mean()) if args.e2e_steps else None
+    if world > 1 and args.e2e_steps:
+        # the host copies are only partially refreshed by the slice downloads: bring them back in line for what follows
+        core.flowingFunctional(into=host)
     state_bytes = 8 * (nw + C * L * nf)
     state_dev_mb = 8e-6 * C * ((L + 3) // 4 * 4) * nf
 
@@ -501,7 +513,8 @@ def main():
                          "alg_fp64": {"achieved": alg_flops / world / t_kernel / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "what": "flops of the reference formulation (every overlap term per node)"},
                          "profile_capture": {k: prof.get(k) for k in ("source", "duration_ms_under_ncu", "captured_items", "l1_hit_pct", "l2_hit_pct", "fp64_pipe_pct", "issue_active_pct", "warps_active_pct", "registers_per_thread")} if prof else None},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
-                    "what": "setState(pinned host arrays) + computeStep + finalizeStep + flowingFunctional(download) per step, wall clock, max over ranks"},
+                    "what": "setState(pinned host arrays) + computeStep + finalizeStep + flowingFunctional(download) per step, wall clock, max over ranks"
+                            + ("; every rank holds the full host state, uploads 1/N of the rows (distributed over NVLink) and reads back its 1/N of the result: bytes are the totals over all ranks" if world > 1 else "")},
             "gpu_launches": launches,
             "clocks": clocks,
         }

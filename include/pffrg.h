@@ -144,6 +144,14 @@ int pffrg_plan_partition_feedback(int core, int n_frequencies, const double *fre
  * (src/SU2/SU2EffectiveAction.hpp:38-60, src/EffectiveAction.hpp:59). `v4` holds pffrg_num_vertex_arrays pointers. */
 int pffrg_set_state(pffrg_handle h, double cutoff, const void *v2, const void *const *v4, int dtype);
 int pffrg_get_state(pffrg_handle h, double *cutoff, void *v2, void *const *v4, int dtype);
+/* Multi-GPU runs in which every rank holds the same host state (as the MPI ranks of the reference do): each rank uploads only the
+ * rows [begin, end) of pffrg_upload_slice (an even split of the work items) and the slices are distributed over NVLink (peer-memory
+ * stores), instead of every rank pushing the whole vertex through PCIe. Collective; falls back to pffrg_set_state on one GPU.
+ * pffrg_get_state_slice downloads the rows [begin, end) of the state into the corresponding rows of the host arrays (the other rows
+ * are left untouched): a rank that only needs its share of the result (or the master rank, the whole) reads just that. */
+int pffrg_upload_slice(pffrg_handle h, int64_t *begin, int64_t *end);
+int pffrg_set_state_sharded(pffrg_handle h, double cutoff, const void *v2, const void *const *v4, int dtype);
+int pffrg_get_state_slice(pffrg_handle h, double *cutoff, void *v2, void *const *v4, int dtype, int64_t begin, int64_t end);
 /* Initial condition built on the device (SU2EffectiveAction(cutoff, spinModel, core), src/SU2/SU2EffectiveAction.hpp:38-60; XYZ
  * :37-62, TRI :38-63): every frequency entry of channel c at representative r is bare[c * n_sites + r] -- the bare coupling already
  * divided by the normalization (and multiplied by 1/4 for XYZ/TRI) -- and the self energy is zero. Replaces building and uploading
@@ -188,17 +196,21 @@ int pffrg_jit_compile_check(const pffrg_desc *desc, int64_t *cubin_bytes);
  * terms per buffer pair (256, or 64 for the RPA). Used by the parity tests to compare against the reference term by term. */
 int pffrg_tri_terms(int region, int32_t *terms, int capacity);
 
-/* Term tables of the Gram form of the SU2 RPA lattice sum as the kernel walks them (rpaGram, pffrg_kernels.cuh): the sum over the
- * quadrature nodes of R[rid] = sum_i A[rid1_i] B[rid2_i] (Lattice::getOverlap(rid), src/Lattice.hpp:46-150, evaluated per node at
- * src/SU2/SU2FrgCore.cpp:250-266) is taken as sum_i G[rid1_i][rid2_i] over the Gram matrix G = sum_nodes A (x) B, rows worked off in
- * blocks of `rows_per_block`. Writes up to `capacity` 16-bit words ((rid1 - block * rows_per_block) * Lp + rid2) | multiplicity <<
- * offset_bits, Lp = n_sites rounded up to 4, and seg[block * n_sites + rid] = first word of (block, rid) (blocks * n_sites + 1
- * entries). Returns the number of words. Host only; used by the CPU tests. */
-int pffrg_gram_tables(const pffrg_desc *desc, int rows_per_block, int offset_bits, uint16_t *terms, int capacity, int32_t *seg);
+/* Term tables of the Gram form of the SU2 RPA lattice sum as the kernel walks them (rpaGram / gramReduce, pffrg_kernels.cuh): the sum
+ * over the quadrature nodes of R[rid] = sum_i A[rid1_i] B[rid2_i] (Lattice::getOverlap(rid), src/Lattice.hpp:46-150, evaluated per node
+ * at src/SU2/SU2FrgCore.cpp:250-266) is taken as sum_i G[rid1_i][rid2_i] over the Gram matrix G = sum_nodes A (x) B, rows worked off in
+ * blocks of `rows_per_block`. Writes up to `capacity` 32-bit words ((rid1 - block * rows_per_block) * Lp + rid2) | rid << 14 |
+ * multiplicity << 22, Lp = n_sites rounded up to 4, sorted by rid, every rid list padded to a multiple of 8 words, and
+ * seg[2 * (block * warps + w)] = {begin, end} of the word range warp w reduces (whole chunks of 256 words); *conflict_degree
+ * (optional) = average shared-memory bank-conflict degree of the walk (1 = conflict free). Returns the number of words. Host only; used
+ * by the CPU tests. */
+int pffrg_gram_tables(const pffrg_desc *desc, int rows_per_block, int warps, uint32_t *terms, int capacity, int32_t *seg, double *conflict_degree);
 
 /* measured FP64 multiply-add peak of a device in TFLOP/s (a 16-chain DFMA loop on every SM; ~10 ms): the denominator of the
  * FP64 roofline bench.py reports next to the HBM one. Returns a negative value on failure. */
 double pffrg_fp64_peak(int device);
+/* the same for the FP64 tensor-core path (mma.sync m8n8k4 f64), TFLOP/s; negative on failure */
+double pffrg_dmma_peak(int device);
 
 /* page-locked host memory for the arrays passed to set_state / get_state / get_flow (plain memory works too, but
  * transfers from pinned buffers run at full PCIe speed). Returns NULL on failure. */

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <chrono>
 #include <cstdlib>
+#include <unistd.h>
 #include <map>
 #include <numeric>
 #include <string>
@@ -44,6 +45,7 @@ namespace
 		ncclResult_t (*GroupEnd)() = nullptr;
 		ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 		ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+		ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 		const char *(*GetErrorString)(ncclResult_t) = nullptr;
 		std::string error;
 		bool ok = false;
@@ -63,6 +65,7 @@ namespace
 			a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
 			a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
 			a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+			a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
 			a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
 			a.ok = a.error.empty();
 			return a;
@@ -120,7 +123,7 @@ struct pffrg_context
 	DeviceArray<int> dSitesRid, dInvRid, dSitesPerm, dInvPerm, dRngFwd, dRngInv, dSlotOff;
 	DeviceArray<int4> dTasks;
 	DeviceArray<unsigned> dWords;
-	DeviceArray<unsigned short> dGramTerms; DeviceArray<int> dGramSeg; // Gram form of the RPA phase (rpaGram), when selected
+	DeviceArray<unsigned> dGramTerms; DeviceArray<int> dGramSeg; // Gram form of the RPA phase (rpaGram), when selected
 	int gramRows = 0;                                                 // rows per Gram block (0: not in use)
 	int itemOrder = 0;                                                // FlowConfig::order of the run-time compiled kernel (PFFRG_ORDER=t: t-major)
 	DeviceArray<unsigned short> dMeshStart; int meshShift = 52, meshKeyBase = 0, meshKeys = 0;
@@ -153,6 +156,17 @@ struct pffrg_context
 	std::vector<int64_t> bounds; // [nRanks + 1] item boundaries of the current step
 	std::vector<double> rankTimes; // flow-kernel time of every rank in the last step (feedback of the partition), empty before the first
 	DeviceArray<double> dTimes; double *hTimes = nullptr; bool balance = true;
+	// exchange over peer memory (see eulerPushKernel): second state buffer, the mapped buffers of all ranks, arrival counters
+	DeviceArray<double> dV4b; int cur = 0;           // cur: which of dV4 / dV4b holds the current state
+	DeviceArray<SyncBlock> dSync; unsigned long long epoch = 0;
+	bool p2p = false;
+	double *peerV4[2][MAX_RANKS] = {}; SyncBlock *peerSync[MAX_RANKS] = {}; void *ipcOpened[3 * MAX_RANKS] = {}; int nIpcOpened = 0;
+	int *hFlags = nullptr;                           // pinned: [0] a peer did not arrive in time
+	bool timesPending = false;                       // hTimes is being filled by the last finalize_step
+	bool finalizePending = false;                    // the last finalize_step has not been synchronised with the host yet
+	DeviceArray<double> dVecStaging;                 // self-energy transfers in the caller's precision
+	double *v4cur() const { return cur ? dV4b.p : dV4.p; }
+	double *v4next() const { return cur ? dV4.p : dV4b.p; }
 	int64_t userBegin = 0, userEnd = 0;
 	int64_t curBegin = 0, curEnd = 0;
 
@@ -164,7 +178,7 @@ struct pffrg_context
 		P.nw = nw; P.L = L; P.Lp = Lp; P.RL = RL; P.nf = (int)nf;
 		P.mesh = dMesh.p; P.sites_rid = dSitesRid.p; P.inv_rid = dInvRid.p; P.sites_perm = dSitesPerm.p; P.inv_perm = dInvPerm.p;
 		P.rpa_tasks = dTasks.p; P.rpa_slot_off = dSlotOff.p; P.rpa_words = dWords.p;
-		P.gram_terms = dGramTerms.p; P.gram_seg = dGramSeg.p;
+		P.gram_terms = dGramTerms.p; P.gram_seg = reinterpret_cast<const int2 *>(dGramSeg.p);
 		P.nrange = (int)dRngFwd.n; P.rng_fwd = dRngFwd.p; P.rng_inv = dRngInv.p; P.spin = spin;
 		P.meshIndex.start = dMeshStart.p; P.meshIndex.shift = meshShift; P.meshIndex.keyBase = meshKeyBase; P.meshIndex.nKeys = meshKeys;
 		return P;
@@ -241,8 +255,8 @@ namespace
 		if (const char *e = getenv("PFFRG_GRAM_TM")) TM = std::min(8, std::max(1, atoi(e)));
 		TM = std::min(TM, (Lp + PT - 1) / PT);
 		const int PB = PT * TM;
-		int bits = 1; while ((1 << bits) < PB * Lp) ++bits;
-		if (bits > 15) return best;
+		const int bits = 14; // a term word addresses the Gram block with 14 bits
+		if (PB * Lp > (1 << bits)) return best;
 		const size_t half = (smemMax + 1024) / 2 - 1024;
 		int forcedNb = 0, forcedNbt = 0, forcedCtas = 0;
 		if (const char *e = getenv("PFFRG_JIT_NB")) forcedNb = atoi(e);
@@ -270,10 +284,8 @@ namespace
 		return best;
 	}
 
-	// Term tables of rpaGram: for every block of PB rows of the Gram matrix and every representative site the merged overlap terms
-	// (rid1, rid2, multiplicity) with rid1 in the block, as 16-bit words (rid1 - block * PB) * Lp + rid2 | multiplicity << bits
-	// (multiplicities that do not fit are split).
-	void buildGramTables(const pffrg_desc *d, int L, int Lp, int PB, int bits, std::vector<unsigned short> &terms, std::vector<int> &seg);
+	// Term tables of rpaGram / gramReduce (pffrg_kernels.cuh), see the definition below
+	void buildGramTables(const pffrg_desc *d, int L, int Lp, int PB, int warps, std::vector<unsigned> &terms, std::vector<int> &seg, double *conflictDegree = nullptr);
 	JitShape chooseJitShape(int core, int nw, int L, int groups, int warps, size_t smemMax)
 	{
 		const int lanes = core == SU2 ? 16 : 32;
@@ -322,7 +334,7 @@ namespace
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes);
 		if (e != cudaSuccess) return e;
 		FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes; cfg.items = (int)count; cfg.order = 0;
-		kernel<<<(unsigned)count, h->threads, h->smemBytes, h->stream>>>(h->problem(), h->nodeTable(), cfg, h->dV4.p, h->dFlow4.p, (int)begin, h->dNan.p);
+		kernel<<<(unsigned)count, h->threads, h->smemBytes, h->stream>>>(h->problem(), h->nodeTable(), cfg, h->v4cur(), h->dFlow4.p, (int)begin, h->dNan.p);
 		return cudaGetLastError();
 	}
 
@@ -365,7 +377,7 @@ namespace
 			Problem P = h->problem(); NodeTable N = h->nodeTable();
 			FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes; cfg.items = (int)count;
 			cfg.order = (h->subs == 1 && h->cluster == 1) ? h->itemOrder : 0;
-			const double *v4 = h->dV4.p; double *flow = h->dFlow4.p; int itemBegin = (int)begin; int *nan = h->dNan.p;
+			const double *v4 = h->v4cur(); double *flow = h->dFlow4.p; int itemBegin = (int)begin; int *nan = h->dNan.p;
 			void *args[] = { &P, &N, &cfg, &v4, &flow, &itemBegin, &nan };
 			int64_t ctas = (count + h->subs - 1) / h->subs; // padded to whole clusters (the kernel carries __cluster_dims__)
 			if (cfg.order == 1) ctas = ((begin + count - 1) / h->nw - begin / h->nw + 1) * h->nw; // t-major: whole (s,u) blocks
@@ -420,7 +432,7 @@ namespace
 	std::string gramDefines(const JitShape &s)
 	{
 		return "#define PFFRG_GRAM 1\n#define PFFRG_GRAM_THREADS " + std::to_string(s.gramThreads) + "\n#define PFFRG_GRAM_PB " + std::to_string(s.gramRows) +
-		       "\n#define PFFRG_GRAM_OFFSET_BITS " + std::to_string(s.gramOffsetBits) + "\n";
+		       "\n";
 	}
 
 	int compileCandidate(pffrg_context *h, const pffrg_desc *d, JitCandidate &c)
@@ -490,8 +502,8 @@ namespace
 				JitCandidate c = { h->threads, h->groups, shape, nullptr, nullptr, 0.f };
 				const int rc = compileCandidate(h, d, c);
 				if (rc != PFFRG_OK) return rc;
-				std::vector<unsigned short> terms; std::vector<int> seg;
-				buildGramTables(d, h->L, h->Lp, shape.gramRows, shape.gramOffsetBits, terms, seg);
+				std::vector<unsigned> terms; std::vector<int> seg;
+				buildGramTables(d, h->L, h->Lp, shape.gramRows, h->threads / 32, terms, seg);
 				CUDA_TRY(h->dGramTerms.upload(terms)); CUDA_TRY(h->dGramSeg.upload(seg));
 				adoptCandidate(h, c);
 				h->jitCompileMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -740,26 +752,89 @@ namespace
 		return p;
 	}
 
-	void buildGramTables(const pffrg_desc *d, int L, int Lp, int PB, int bits, std::vector<unsigned short> &terms, std::vector<int> &seg)
+	// Term tables of gramReduce. For every block of PB rows of the Gram matrix: one flat array of 32-bit words
+	//     (rid1 - block * PB) * Lp + rid2  |  rid << 14  |  multiplicity << 22
+	// of the merged overlap terms (rid1, rid2, multiplicity) of all representative sites rid with rid1 in the block, sorted by rid.
+	// - every rid list is padded to a multiple of 8 words (multiplicity 0), so that the 8 consecutive words a lane reads belong to one rid;
+	// - the rids are dealt to the `warps` warps of the CTA as contiguous ranges of about equal length; every range starts on a multiple
+	//   of 256 words and is padded to whole chunks of 256 words: seg[2 * (block * warps + w)] = {begin, end};
+	// - inside a list the words are ordered so that in every step k the 8 lanes of a quarter warp (words 64 Q + 8 l + k, l = 0..7, of a
+	//   chunk) address 8 different 16-byte bank groups of the Gram block (offset mod 8) where the list allows it.
+	// conflictDegree (optional): average number of words per occupied bank group over all (chunk, quarter, step) sets; 1 = conflict free.
+	void buildGramTables(const pffrg_desc *d, int L, int Lp, int PB, int warps, std::vector<unsigned> &terms, std::vector<int> &seg, double *conflictDegree)
 	{
-		const int blocks = (Lp + PB - 1) / PB, maxMult = (1 << (16 - bits)) - 1;
+		const int blocks = (Lp + PB - 1) / PB, maxMult = 1023;
 		std::vector<std::map<std::tuple<int, int, int, int>, int>> merged(L);
 		for (int rid = 0; rid < L; ++rid) merged[rid] = mergedOverlap(d, SU2, rid);
-		seg.assign((size_t)blocks * L + 1, 0);
+		seg.assign((size_t)2 * blocks * warps, 0);
 		terms.clear();
+		double sets = 0.0, degree = 0.0;
 		for (int blk = 0; blk < blocks; ++blk)
+		{
+			// the words of every rid in this block, by bank class
+			std::vector<std::vector<std::vector<unsigned>>> byClass(L, std::vector<std::vector<unsigned>>(8));
+			std::vector<int> padded(L, 0);
+			long total = 0;
 			for (int rid = 0; rid < L; ++rid)
 			{
-				seg[(size_t)blk * L + rid] = (int)terms.size();
+				int n = 0;
 				for (auto &kv : merged[rid])
 				{
 					const int p = std::get<0>(kv.first), q = std::get<3>(kv.first);
 					if (p / PB != blk) continue;
-					for (int m = kv.second; m > 0; m -= maxMult)
-						terms.push_back((unsigned short)(((p - blk * PB) * Lp + q) | (std::min(m, maxMult) << bits)));
+					const unsigned offset = (unsigned)((p - blk * PB) * Lp + q);
+					for (int m = kv.second; m > 0; m -= maxMult) { byClass[rid][offset & 7u].push_back(offset | ((unsigned)rid << 14) | ((unsigned)std::min(m, maxMult) << 22)); ++n; }
 				}
+				padded[rid] = (n + 7) / 8 * 8;
+				total += padded[rid];
 			}
-		seg.back() = (int)terms.size();
+			int rid = 0; long done = 0;
+			for (int w = 0; w < warps; ++w)
+			{
+				while (terms.size() % 256) terms.push_back(0u); // (only after a range that was padded below: a no-op)
+				const size_t begin = terms.size();
+				seg[2 * ((size_t)blk * warps + w)] = (int)begin;
+				// rids of this warp: up to the next multiple of total / warps (the last warp takes the rest)
+				const long target = (w + 1 == warps) ? total : total * (w + 1) / warps;
+				int lastRid = rid < L ? rid : L - 1;
+				while (rid < L && (done < target || padded[rid] == 0))
+				{
+					// lay out the list of `rid` position by position; class masks of the (chunk, quarter, step) sets it touches
+					std::map<size_t, unsigned> used; // set id -> classes taken (by this list; sets shared with the previous list start empty: rare)
+					for (int i = 0; i < padded[rid]; ++i)
+					{
+						const size_t pos = terms.size() - begin;
+						const size_t set = (pos / 64) * 8 + pos % 8;
+						unsigned &mask = used[set];
+						int best = -1;
+						for (int c = 0; c < 8; ++c)
+							if (!byClass[rid][c].empty() && !(mask & (1u << c)) && (best < 0 || byClass[rid][c].size() > byClass[rid][best].size())) best = c;
+						if (best < 0) for (int c = 0; c < 8; ++c) if (!byClass[rid][c].empty() && (best < 0 || byClass[rid][c].size() > byClass[rid][best].size())) best = c;
+						if (best >= 0) { terms.push_back(byClass[rid][best].back()); byClass[rid][best].pop_back(); mask |= 1u << best; }
+						else
+						{
+							// padding word: multiplicity 0, a free bank class
+							int c = 0; while (c < 7 && (mask & (1u << c))) ++c;
+							terms.push_back((unsigned)((c < PB * Lp) ? c : 0) | ((unsigned)rid << 14));
+							mask |= 1u << c;
+						}
+					}
+					done += padded[rid]; lastRid = rid; ++rid;
+				}
+				while ((terms.size() - begin) % 256) terms.push_back((unsigned)lastRid << 14);
+				seg[2 * ((size_t)blk * warps + w) + 1] = (int)terms.size();
+				// conflict statistics of this range
+				for (size_t base = begin; base < terms.size(); base += 64)
+					for (int k = 0; k < 8; ++k)
+					{
+						int count[8] = { 0 }, occupied = 0;
+						for (int l = 0; l < 8; ++l) ++count[terms[base + 8 * l + k] & 7u];
+						for (int c = 0; c < 8; ++c) occupied += count[c] > 0;
+						sets += 1.0; degree += 8.0 / occupied;
+					}
+			}
+		}
+		if (conflictDegree) *conflictDegree = sets > 0 ? degree / sets : 1.0;
 	}
 
 	// node counts per mesh frequency at the current cutoff (host copy of what nodeTableKernel enumerates)
@@ -929,62 +1004,167 @@ namespace
 		return PFFRG_OK;
 	}
 
+	// rows [rowBegin, rowBegin + rows) of the vertex between the host arrays (reference layout) and a device buffer (device layout)
 	template <typename T>
-	int importArrays(pffrg_context *h, const void *const *src, double *dst)
+	int importArrays(pffrg_context *h, const void *const *src, double *dst, int64_t rowBegin, int64_t rows)
 	{
-		const size_t len = (size_t)h->nf * h->L * (h->core == TRI ? 16 : 1);
-		if (h->dStaging.n < len) CUDA_TRY(h->dStaging.alloc(len));
+		const size_t per = (size_t)h->L * (h->core == TRI ? 16 : 1), len = (size_t)rows * per;
+		if (rows <= 0) return PFFRG_OK;
+		if (h->dStaging.n * sizeof(double) < len * sizeof(T)) CUDA_TRY(h->dStaging.alloc((len * sizeof(T) + 7) / 8));
 		T *staging = reinterpret_cast<T *>(h->dStaging.p);
 		for (int a = 0; a < h->nArrays; ++a)
 		{
 			if (!src[a]) return fail(PFFRG_ERR_ARGUMENT, "vertex array %d is null", a);
-			CUDA_TRY(cudaMemcpyAsync(staging, src[a], len * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-			importKernel<T><<<1184, 256, 0, h->stream>>>(staging, dst, (size_t)h->nf, h->L, h->Lp, h->RL, vectorWidth(h->core), h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
+			CUDA_TRY(cudaMemcpyAsync(staging, static_cast<const T *>(src[a]) + (size_t)rowBegin * per, len * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+			importKernel<T><<<1184, 256, 0, h->stream>>>(staging, dst, (size_t)rowBegin, (size_t)rows, h->L, h->Lp, h->RL, vectorWidth(h->core), h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
 			CUDA_TRY(cudaGetLastError());
 		}
-		CUDA_TRY(cudaStreamSynchronize(h->stream));
 		return PFFRG_OK;
 	}
 
 	template <typename T>
-	int exportArrays(pffrg_context *h, const double *src, void *const *dst)
+	int exportArrays(pffrg_context *h, const double *src, void *const *dst, int64_t rowBegin, int64_t rows)
 	{
-		const size_t len = (size_t)h->nf * h->L * (h->core == TRI ? 16 : 1);
-		if (h->dStaging.n < len) CUDA_TRY(h->dStaging.alloc(len));
+		const size_t per = (size_t)h->L * (h->core == TRI ? 16 : 1), len = (size_t)rows * per;
+		if (rows <= 0) return PFFRG_OK;
+		if (h->dStaging.n * sizeof(double) < len * sizeof(T)) CUDA_TRY(h->dStaging.alloc((len * sizeof(T) + 7) / 8));
 		T *staging = reinterpret_cast<T *>(h->dStaging.p);
 		for (int a = 0; a < h->nArrays; ++a)
 		{
 			if (!dst[a]) continue;
-			exportKernel<T><<<1184, 256, 0, h->stream>>>(src, staging, (size_t)h->nf, h->L, h->Lp, h->RL, vectorWidth(h->core), h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
+			exportKernel<T><<<1184, 256, 0, h->stream>>>(src, staging, (size_t)rowBegin, (size_t)rows, h->L, h->Lp, h->RL, vectorWidth(h->core), h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
 			CUDA_TRY(cudaGetLastError());
-			CUDA_TRY(cudaMemcpyAsync(dst[a], staging, len * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
-			CUDA_TRY(cudaStreamSynchronize(h->stream));
+			CUDA_TRY(cudaMemcpyAsync(static_cast<T *>(dst[a]) + (size_t)rowBegin * per, staging, len * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
 		}
+		CUDA_TRY(cudaStreamSynchronize(h->stream));
 		return PFFRG_OK;
 	}
 
 	template <typename T>
 	int importVector(pffrg_context *h, const void *src, double *dst, int n)
 	{
-		DeviceArray<T> staging; CUDA_TRY(staging.alloc(n));
-		CUDA_TRY(cudaMemcpyAsync(staging.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-		convertKernel<T><<<1, 128, 0, h->stream>>>(staging.p, dst, n);
-		CUDA_TRY(cudaStreamSynchronize(h->stream));
-		staging.release();
+		if (h->dVecStaging.n < (size_t)n) CUDA_TRY(h->dVecStaging.alloc(n));
+		T *staging = reinterpret_cast<T *>(h->dVecStaging.p);
+		CUDA_TRY(cudaMemcpyAsync(staging, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+		convertKernel<T><<<1, 128, 0, h->stream>>>(staging, dst, n);
+		CUDA_TRY(cudaGetLastError());
 		return PFFRG_OK;
 	}
 	template <typename T>
 	int exportVector(pffrg_context *h, const double *src, void *dst, int n)
 	{
-		DeviceArray<T> staging; CUDA_TRY(staging.alloc(n));
-		convertBackKernel<T><<<1, 128, 0, h->stream>>>(src, staging.p, n);
-		CUDA_TRY(cudaMemcpyAsync(dst, staging.p, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+		if (h->dVecStaging.n < (size_t)n) CUDA_TRY(h->dVecStaging.alloc(n));
+		T *staging = reinterpret_cast<T *>(h->dVecStaging.p);
+		convertBackKernel<T><<<1, 128, 0, h->stream>>>(src, staging, n);
+		CUDA_TRY(cudaMemcpyAsync(dst, staging, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
 		CUDA_TRY(cudaStreamSynchronize(h->stream));
-		staging.release();
+		return PFFRG_OK;
+	}
+
+	// ---- exchange over peer memory ------------------------------------------------------------------------------------------
+	PushTargets pushTargets(const pffrg_context *h, int buffer, size_t offset, bool includeSelf)
+	{
+		PushTargets T; T.n = 0;
+		if (includeSelf) T.dst[T.n++] = h->peerV4[buffer][h->rank] + offset;
+		for (int r = 0; r < h->nRanks; ++r) if (r != h->rank) T.dst[T.n++] = h->peerV4[buffer][r] + offset;
+		return T;
+	}
+	// all ranks have reached this point of their streams (and what they stored into peer memory before it has arrived)
+	int peerBarrier(pffrg_context *h, double ms)
+	{
+		PeerSyncs S; S.n = h->nRanks;
+		for (int r = 0; r < h->nRanks; ++r) S.block[r] = h->peerSync[r];
+		++h->epoch;
+		signalPeersKernel<<<1, 32, 0, h->stream>>>(S, h->rank, h->epoch, ms);
+		CUDA_TRY(cudaGetLastError());
+		long long timeoutClocks = 60ll * 2000000000ll; // ~60 s at 2 GHz
+		if (const char *e = getenv("PFFRG_PEER_TIMEOUT_S")) timeoutClocks = std::max(1ll, atoll(e)) * 2000000000ll;
+		waitPeersKernel<<<1, 32, 0, h->stream>>>(h->dSync.p, h->nRanks, h->epoch, timeoutClocks, h->hFlags);
+		CUDA_TRY(cudaGetLastError());
+		return PFFRG_OK;
+	}
+	int checkPeerTimeout(pffrg_context *h)
+	{
+		if (h->hFlags && h->hFlags[0]) return fail(PFFRG_ERR_NCCL, "rank %d: a peer rank did not reach the exchange in time (PFFRG_PEER_TIMEOUT_S)", h->rank);
+		return PFFRG_OK;
+	}
+
+	// Map the state buffers and sync blocks of all ranks (CUDA IPC; ranks living in this process are addressed directly). Collective.
+	// Any failure on any rank leaves ALL ranks on the NCCL exchange.
+	int setupPeerExchange(pffrg_context *h)
+	{
+		struct Blob { long long pid; void *ptr[3]; cudaIpcMemHandle_t handle[3]; int ok; int pad; };
+		const int n = h->nRanks;
+		if (n > MAX_RANKS) return PFFRG_OK;
+		if (const char *e = getenv("PFFRG_EXCHANGE")) if (std::string(e) == "nccl") return PFFRG_OK;
+		Blob mine; memset(&mine, 0, sizeof mine);
+		mine.pid = (long long)getpid(); mine.ok = 1;
+		if (h->dV4b.alloc(h->v4Elements()) != cudaSuccess || h->dSync.alloc(1) != cudaSuccess || cudaMemset(h->dSync.p, 0, sizeof(SyncBlock)) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+		if (mine.ok && !h->hFlags) { if (cudaMallocHost(&h->hFlags, 2 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; } else h->hFlags[0] = h->hFlags[1] = 0; }
+		mine.ptr[0] = h->dV4.p; mine.ptr[1] = h->dV4b.p; mine.ptr[2] = h->dSync.p;
+		for (int k = 0; k < 3 && mine.ok; ++k) if (cudaIpcGetMemHandle(&mine.handle[k], mine.ptr[k]) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+		DeviceArray<char> dBlobs; std::vector<Blob> all(n);
+		CUDA_TRY(dBlobs.alloc(sizeof(Blob) * (n + 1)));
+		CUDA_TRY(cudaMemcpyAsync(dBlobs.p + sizeof(Blob) * n, &mine, sizeof(Blob), cudaMemcpyHostToDevice, h->stream));
+		NCCL_TRY(nccl().AllGather(dBlobs.p + sizeof(Blob) * n, dBlobs.p, sizeof(Blob), ncclChar, h->comm, h->stream));
+		CUDA_TRY(cudaMemcpyAsync(all.data(), dBlobs.p, sizeof(Blob) * n, cudaMemcpyDeviceToHost, h->stream));
+		CUDA_TRY(cudaStreamSynchronize(h->stream));
+		int ok = 1;
+		for (int r = 0; r < n; ++r) ok &= all[r].ok;
+		for (int r = 0; r < n && ok; ++r)
+		{
+			void *p[3] = { nullptr, nullptr, nullptr };
+			if (r == h->rank) { for (int k = 0; k < 3; ++k) p[k] = mine.ptr[k]; }
+			else if (all[r].pid == mine.pid)
+			{
+				// another handle of this process: direct peer access
+				cudaPointerAttributes attr;
+				if (cudaPointerGetAttributes(&attr, all[r].ptr[0]) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+				if (attr.device != h->device) { const cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0; cudaGetLastError(); }
+				for (int k = 0; k < 3; ++k) p[k] = all[r].ptr[k];
+			}
+			else
+				for (int k = 0; k < 3 && ok; ++k)
+				{
+					if (cudaIpcOpenMemHandle(&p[k], all[r].handle[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+					else h->ipcOpened[h->nIpcOpened++] = p[k];
+				}
+			h->peerV4[0][r] = static_cast<double *>(p[0]); h->peerV4[1][r] = static_cast<double *>(p[1]); h->peerSync[r] = static_cast<SyncBlock *>(p[2]);
+		}
+		// collective decision
+		DeviceArray<int> dOk; CUDA_TRY(dOk.alloc(1));
+		CUDA_TRY(cudaMemcpyAsync(dOk.p, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+		NCCL_TRY(nccl().AllReduce(dOk.p, dOk.p, 1, ncclInt, ncclMin, h->comm, h->stream));
+		CUDA_TRY(cudaMemcpyAsync(&ok, dOk.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+		CUDA_TRY(cudaStreamSynchronize(h->stream));
+		dBlobs.release(); dOk.release();
+		h->p2p = ok != 0;
+		if (!h->p2p)
+		{
+			for (int k = 0; k < h->nIpcOpened; ++k) cudaIpcCloseMemHandle(h->ipcOpened[k]);
+			h->nIpcOpened = 0; cudaGetLastError();
+			h->dV4b.release(); h->cur = 0;
+			if (getenv("PFFRG_JIT_VERBOSE")) fprintf(stderr, "[pffrg] rank %d: peer-memory exchange unavailable, using the NCCL exchange\n", h->rank);
+		}
 		return PFFRG_OK;
 	}
 
 	float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
+}
+
+namespace
+{
+	// results of the last finalize_step that were left on the stream: event timings, the ranks' kernel times, peer timeouts
+	int collectFinalize(pffrg_context *h)
+	{
+		if (!h->finalizePending) return PFFRG_OK;
+		CUDA_TRY(cudaEventSynchronize(h->ev[6]));
+		h->stats.ms_finalize = elapsed(h->ev[4], h->ev[6]);
+		h->stats.ms_exchange = elapsed(h->ev[5], h->ev[6]);
+		if (h->timesPending) h->rankTimes.assign(h->hTimes, h->hTimes + h->nRanks);
+		h->finalizePending = false; h->timesPending = false;
+		return checkPeerTimeout(h);
+	}
 }
 
 extern "C" {
@@ -1104,7 +1284,10 @@ int pffrg_destroy(pffrg_handle h)
 	if (!h) return PFFRG_OK;
 	cudaSetDevice(h->device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
+	for (int k = 0; k < h->nIpcOpened; ++k) cudaIpcCloseMemHandle(h->ipcOpened[k]);
 	if (h->comm) nccl().CommDestroy(h->comm);
+	h->dV4b.release(); h->dSync.release(); h->dVecStaging.release(); h->dTimes.release();
+	if (h->hFlags) cudaFreeHost(h->hFlags);
 	h->dMesh.release(); h->dSitesRid.release(); h->dInvRid.release(); h->dSitesPerm.release(); h->dInvPerm.release(); h->dRngFwd.release(); h->dRngInv.release();
 	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release(); h->dMeshStart.release(); h->dGramTerms.release(); h->dGramSeg.release();
 	if (h->jitLibrary) cudaLibraryUnload(h->jitLibrary); h->dV4.release(); h->dFlow4.release(); h->dV2.release(); h->dFlow2.release(); h->dCutoff.release();
@@ -1147,6 +1330,7 @@ int pffrg_comm_init(pffrg_handle h, const void *id, int rank, int nRanks)
 	h->rankTimes.clear();
 	h->rank = rank; h->nRanks = nRanks;
 	h->bounds.assign(nRanks + 1, 0); h->bounds[nRanks] = h->nf;
+	if (nRanks > 1) { const int rc = setupPeerExchange(h); if (rc != PFFRG_OK) return rc; }
 	return PFFRG_OK;
 }
 
@@ -1171,7 +1355,7 @@ int pffrg_set_state(pffrg_handle h, double cutoff, const void *v2, const void *c
 	if (!h || !v2 || !v4) return fail(PFFRG_ERR_ARGUMENT, "null argument");
 	if (dtype != PFFRG_F32 && dtype != PFFRG_F64) return fail(PFFRG_ERR_ARGUMENT, "unknown dtype %d", dtype);
 	CUDA_TRY(cudaSetDevice(h->device));
-	int rc = dtype == PFFRG_F64 ? importArrays<double>(h, v4, h->dV4.p) : importArrays<float>(h, v4, h->dV4.p);
+	int rc = dtype == PFFRG_F64 ? importArrays<double>(h, v4, h->v4cur(), 0, h->nf) : importArrays<float>(h, v4, h->v4cur(), 0, h->nf);
 	if (rc != PFFRG_OK) return rc;
 	rc = dtype == PFFRG_F64 ? importVector<double>(h, v2, h->dV2.p, h->nw) : importVector<float>(h, v2, h->dV2.p, h->nw);
 	if (rc != PFFRG_OK) return rc;
@@ -1182,6 +1366,58 @@ int pffrg_set_state(pffrg_handle h, double cutoff, const void *v2, const void *c
 	return PFFRG_OK;
 }
 
+int pffrg_upload_slice(pffrg_handle h, int64_t *begin, int64_t *end)
+{
+	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");
+	if (begin) *begin = h->nf * h->rank / h->nRanks;
+	if (end) *end = h->nf * (h->rank + 1) / h->nRanks;
+	return PFFRG_OK;
+}
+
+int pffrg_set_state_sharded(pffrg_handle h, double cutoff, const void *v2, const void *const *v4, int dtype)
+{
+	if (!h || !v2 || !v4) return fail(PFFRG_ERR_ARGUMENT, "null argument");
+	if (h->nRanks <= 1 || !h->p2p) return pffrg_set_state(h, cutoff, v2, v4, dtype);
+	if (dtype != PFFRG_F32 && dtype != PFFRG_F64) return fail(PFFRG_ERR_ARGUMENT, "unknown dtype %d", dtype);
+	CUDA_TRY(cudaSetDevice(h->device));
+	{ const int rc = collectFinalize(h); if (rc != PFFRG_OK) return rc; }
+	int64_t begin = 0, end = 0; pffrg_upload_slice(h, &begin, &end);
+	// every rank is done reading the buffer that is about to be overwritten
+	int rc = peerBarrier(h, 0.0);
+	if (rc != PFFRG_OK) return rc;
+	rc = dtype == PFFRG_F64 ? importArrays<double>(h, v4, h->v4cur(), begin, end - begin) : importArrays<float>(h, v4, h->v4cur(), begin, end - begin);
+	if (rc != PFFRG_OK) return rc;
+	const size_t off = (size_t)begin * h->RL, cnt = (size_t)(end - begin) * h->RL;
+	if (cnt > 0)
+	{
+		const unsigned blocks = (unsigned)std::min<size_t>(1184, (cnt / 2 + 255) / 256);
+		copyPushKernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const double2 *>(h->v4cur() + off), cnt / 2, pushTargets(h, h->cur, off, false));
+		CUDA_TRY(cudaGetLastError());
+	}
+	rc = peerBarrier(h, 0.0);
+	if (rc != PFFRG_OK) return rc;
+	rc = dtype == PFFRG_F64 ? importVector<double>(h, v2, h->dV2.p, h->nw) : importVector<float>(h, v2, h->dV2.p, h->nw);
+	if (rc != PFFRG_OK) return rc;
+	h->cutoff = cutoff;
+	setScalarKernel<<<1, 1, 0, h->stream>>>(h->dCutoff.p, cutoff);
+	CUDA_TRY(cudaStreamSynchronize(h->stream));
+	h->haveState = true; h->haveFlow = false;
+	return checkPeerTimeout(h);
+}
+
+int pffrg_get_state_slice(pffrg_handle h, double *cutoff, void *v2, void *const *v4, int dtype, int64_t begin, int64_t end)
+{
+	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");
+	if (!h->haveState) return fail(PFFRG_ERR_STATE, "no state has been set");
+	if (dtype != PFFRG_F32 && dtype != PFFRG_F64) return fail(PFFRG_ERR_ARGUMENT, "unknown dtype %d", dtype);
+	if (begin < 0 || end > h->nf || end < begin) return fail(PFFRG_ERR_ARGUMENT, "item range [%lld, %lld) outside [0, %lld)", (long long)begin, (long long)end, (long long)h->nf);
+	CUDA_TRY(cudaSetDevice(h->device));
+	if (cutoff) *cutoff = h->cutoff;
+	if (v2) { int rc = dtype == PFFRG_F64 ? exportVector<double>(h, h->dV2.p, v2, h->nw) : exportVector<float>(h, h->dV2.p, v2, h->nw); if (rc != PFFRG_OK) return rc; }
+	if (v4) { int rc = dtype == PFFRG_F64 ? exportArrays<double>(h, h->v4cur(), v4, begin, end - begin) : exportArrays<float>(h, h->v4cur(), v4, begin, end - begin); if (rc != PFFRG_OK) return rc; }
+	return PFFRG_OK;
+}
+
 int pffrg_set_initial_condition(pffrg_handle h, double cutoff, const double *bare)
 {
 	if (!h || !bare) return fail(PFFRG_ERR_ARGUMENT, "null argument");
@@ -1189,7 +1425,7 @@ int pffrg_set_initial_condition(pffrg_handle h, double cutoff, const double *bar
 	const size_t entries = (size_t)h->C * h->L;
 	if (h->dStaging.n < entries) CUDA_TRY(h->dStaging.alloc(entries));
 	CUDA_TRY(cudaMemcpyAsync(h->dStaging.p, bare, entries * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-	initialConditionKernel<<<1184, 256, 0, h->stream>>>(h->dV4.p, h->dStaging.p, (size_t)h->nf, h->L, h->Lp, h->RL, vectorWidth(h->core));
+	initialConditionKernel<<<1184, 256, 0, h->stream>>>(h->v4cur(), h->dStaging.p, (size_t)h->nf, h->L, h->Lp, h->RL, vectorWidth(h->core));
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemsetAsync(h->dV2.p, 0, h->nw * sizeof(double), h->stream));
 	h->cutoff = cutoff;
@@ -1207,7 +1443,7 @@ int pffrg_get_state(pffrg_handle h, double *cutoff, void *v2, void *const *v4, i
 	CUDA_TRY(cudaSetDevice(h->device));
 	if (cutoff) *cutoff = h->cutoff;
 	if (v2) { int rc = dtype == PFFRG_F64 ? exportVector<double>(h, h->dV2.p, v2, h->nw) : exportVector<float>(h, h->dV2.p, v2, h->nw); if (rc != PFFRG_OK) return rc; }
-	if (v4) { int rc = dtype == PFFRG_F64 ? exportArrays<double>(h, h->dV4.p, v4) : exportArrays<float>(h, h->dV4.p, v4); if (rc != PFFRG_OK) return rc; }
+	if (v4) { int rc = dtype == PFFRG_F64 ? exportArrays<double>(h, h->v4cur(), v4, 0, h->nf) : exportArrays<float>(h, h->v4cur(), v4, 0, h->nf); if (rc != PFFRG_OK) return rc; }
 	return PFFRG_OK;
 }
 
@@ -1224,7 +1460,7 @@ int pffrg_get_flow(pffrg_handle h, void *v2flow, void *const *v4flow, int dtype)
 		h->flowGathered = true;
 	}
 	if (v2flow) { int rc = dtype == PFFRG_F64 ? exportVector<double>(h, h->dFlow2.p, v2flow, h->nw) : exportVector<float>(h, h->dFlow2.p, v2flow, h->nw); if (rc != PFFRG_OK) return rc; }
-	if (v4flow) { int rc = dtype == PFFRG_F64 ? exportArrays<double>(h, h->dFlow4.p, v4flow) : exportArrays<float>(h, h->dFlow4.p, v4flow); if (rc != PFFRG_OK) return rc; }
+	if (v4flow) { int rc = dtype == PFFRG_F64 ? exportArrays<double>(h, h->dFlow4.p, v4flow, 0, h->nf) : exportArrays<float>(h, h->dFlow4.p, v4flow, 0, h->nf); if (rc != PFFRG_OK) return rc; }
 	return PFFRG_OK;
 }
 
@@ -1233,6 +1469,7 @@ int pffrg_compute_step(pffrg_handle h, int *diverged)
 	if (!h) return fail(PFFRG_ERR_ARGUMENT, "null handle");
 	if (!h->haveState) return fail(PFFRG_ERR_STATE, "compute_step before set_state");
 	CUDA_TRY(cudaSetDevice(h->device));
+	{ const int rc = collectFinalize(h); if (rc != PFFRG_OK) return rc; }
 	const std::vector<int> counts = hostNodeCounts(h);
 	partitionItems(h, counts);
 	int64_t begin = h->bounds[h->rank], end = h->bounds[h->rank + 1];
@@ -1243,9 +1480,9 @@ int pffrg_compute_step(pffrg_handle h, int *diverged)
 	CUDA_TRY(cudaMemsetAsync(h->dNan.p, 0, sizeof(int), h->stream));
 	CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
 	const size_t smemV2 = sizeof(double) * (h->nw + 128);
-	if (h->core == SU2) v2FlowKernel<SU2><<<h->nw, 128, smemV2, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->dFlow2.p);
-	else if (h->core == XYZ) v2FlowKernel<XYZ><<<h->nw, 128, smemV2, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->dFlow2.p);
-	else v2FlowKernel<TRI><<<h->nw, 128, smemV2, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->dFlow2.p);
+	if (h->core == SU2) v2FlowKernel<SU2><<<h->nw, 128, smemV2, h->stream>>>(P, h->v4cur(), h->dV2.p, h->dCutoff.p, h->dFlow2.p);
+	else if (h->core == XYZ) v2FlowKernel<XYZ><<<h->nw, 128, smemV2, h->stream>>>(P, h->v4cur(), h->dV2.p, h->dCutoff.p, h->dFlow2.p);
+	else v2FlowKernel<TRI><<<h->nw, 128, smemV2, h->stream>>>(P, h->v4cur(), h->dV2.p, h->dCutoff.p, h->dFlow2.p);
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
 	nodeTableKernel<<<h->nw, 128, sizeof(double) * (3 * h->nw + 2 * h->nodeStride), h->stream>>>(P, h->nodeTable(), h->dV2.p, h->dFlow2.p, h->dCutoff.p);
@@ -1264,7 +1501,7 @@ int pffrg_compute_step(pffrg_handle h, int *diverged)
 	h->haveFlow = true;
 	h->flowGathered = (h->nRanks <= 1);
 	if (diverged) *diverged = *h->hNan ? 1 : 0;
-	return PFFRG_OK;
+	return checkPeerTimeout(h);
 }
 
 int pffrg_finalize_step(pffrg_handle h, double newCutoff)
@@ -1277,31 +1514,58 @@ int pffrg_finalize_step(pffrg_handle h, double newCutoff)
 	eulerKernel<<<1, 128, 0, h->stream>>>(h->dV2.p, h->dFlow2.p, (size_t)h->nw, h->dCutoff.p, newCutoff);
 	CUDA_TRY(cudaGetLastError());
 	const size_t off = (size_t)h->curBegin * h->RL, cnt = (size_t)(h->curEnd - h->curBegin) * h->RL;
-	if (cnt > 0)
-	{
-		eulerKernel<<<1184, 256, 0, h->stream>>>(h->dV4.p + off, h->dFlow4.p + off, cnt, h->dCutoff.p, newCutoff);
-		CUDA_TRY(cudaGetLastError());
-	}
-	setScalarKernel<<<1, 1, 0, h->stream>>>(h->dCutoff.p, newCutoff);
-	CUDA_TRY(cudaGetLastError());
-	CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
 	const bool sharded = h->nRanks > 1 && !(h->userEnd > h->userBegin);
-	if (sharded) { int rc = exchangeSlices(h, h->dV4.p); if (rc != PFFRG_OK) return rc; }
-	if (sharded && h->balance)
+	h->stats.launches += 2;
+	if (sharded && h->p2p)
 	{
-		// every rank's flow-kernel time of this step -> all ranks (a sum over vectors with one non-zero entry each)
-		if (!h->hTimes) { CUDA_TRY(cudaMallocHost(&h->hTimes, sizeof(double) * h->nRanks)); CUDA_TRY(h->dTimes.alloc(h->nRanks)); }
-		for (int r = 0; r < h->nRanks; ++r) h->hTimes[r] = r == h->rank ? (double)h->stats.ms_v4_flow : 0.0;
-		CUDA_TRY(cudaMemcpyAsync(h->dTimes.p, h->hTimes, sizeof(double) * h->nRanks, cudaMemcpyHostToDevice, h->stream));
-		NCCL_TRY(nccl().AllReduce(h->dTimes.p, h->dTimes.p, h->nRanks, ncclDouble, ncclSum, h->comm, h->stream));
-		CUDA_TRY(cudaMemcpyAsync(h->hTimes, h->dTimes.p, sizeof(double) * h->nRanks, cudaMemcpyDeviceToHost, h->stream));
+		// Euler update of the own slice + its distribution in one kernel: the new values go into the slice of EVERY rank's next-state
+		// buffer over NVLink (the ranks still read the old state until they have all arrived)
+		if (cnt > 0)
+		{
+			const unsigned blocks = (unsigned)std::min<size_t>(1184, (cnt / 2 + 255) / 256);
+			eulerPushKernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const double2 *>(h->v4cur() + off), reinterpret_cast<const double2 *>(h->dFlow4.p + off), cnt / 2, h->dCutoff.p, newCutoff, pushTargets(h, 1 - h->cur, off, true));
+			CUDA_TRY(cudaGetLastError());
+			++h->stats.launches;
+		}
+		setScalarKernel<<<1, 1, 0, h->stream>>>(h->dCutoff.p, newCutoff);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
+		{ const int rc = peerBarrier(h, (double)h->stats.ms_v4_flow); if (rc != PFFRG_OK) return rc; }
+		h->stats.launches += 2;
+		h->cur ^= 1;
+		if (h->balance)
+		{
+			if (!h->hTimes) CUDA_TRY(cudaMallocHost(&h->hTimes, sizeof(double) * MAX_RANKS));
+			CUDA_TRY(cudaMemcpyAsync(h->hTimes, h->dSync.p->times, sizeof(double) * h->nRanks, cudaMemcpyDeviceToHost, h->stream));
+		}
+	}
+	else
+	{
+		if (cnt > 0)
+		{
+			eulerKernel<<<1184, 256, 0, h->stream>>>(h->v4cur() + off, h->dFlow4.p + off, cnt, h->dCutoff.p, newCutoff);
+			CUDA_TRY(cudaGetLastError());
+			++h->stats.launches;
+		}
+		setScalarKernel<<<1, 1, 0, h->stream>>>(h->dCutoff.p, newCutoff);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
+		if (sharded) { int rc = exchangeSlices(h, h->v4cur()); if (rc != PFFRG_OK) return rc; }
+		if (sharded && h->balance)
+		{
+			// every rank's flow-kernel time of this step -> all ranks (a sum over vectors with one non-zero entry each)
+			if (!h->hTimes) { CUDA_TRY(cudaMallocHost(&h->hTimes, sizeof(double) * MAX_RANKS)); }
+			if (!h->dTimes.p) CUDA_TRY(h->dTimes.alloc(MAX_RANKS));
+			for (int r = 0; r < h->nRanks; ++r) h->hTimes[r] = r == h->rank ? (double)h->stats.ms_v4_flow : 0.0;
+			CUDA_TRY(cudaMemcpyAsync(h->dTimes.p, h->hTimes, sizeof(double) * h->nRanks, cudaMemcpyHostToDevice, h->stream));
+			NCCL_TRY(nccl().AllReduce(h->dTimes.p, h->dTimes.p, h->nRanks, ncclDouble, ncclSum, h->comm, h->stream));
+			CUDA_TRY(cudaMemcpyAsync(h->hTimes, h->dTimes.p, sizeof(double) * h->nRanks, cudaMemcpyDeviceToHost, h->stream));
+		}
 	}
 	CUDA_TRY(cudaEventRecord(h->ev[6], h->stream));
-	CUDA_TRY(cudaStreamSynchronize(h->stream));
-	if (sharded && h->balance) h->rankTimes.assign(h->hTimes, h->hTimes + h->nRanks);
-	h->stats.ms_finalize = elapsed(h->ev[4], h->ev[6]);
-	h->stats.ms_exchange = elapsed(h->ev[5], h->ev[6]);
-	h->stats.launches += 3;
+	// no host synchronisation here: the times (and the event timings) are collected by the next call that needs them
+	h->finalizePending = true;
+	h->timesPending = sharded && h->balance;
 	h->cutoff = newCutoff;
 	h->haveFlow = false;
 	return PFFRG_OK;
@@ -1324,9 +1588,9 @@ int pffrg_measure_correlation(pffrg_handle h, double *chi)
 	const Problem P = h->problem();
 	const int groups = std::max(1, 256 / h->L);
 	const size_t smem = sizeof(double) * ((size_t)2 * h->nw + 2 * h->nodeStride + (size_t)groups * entries);
-	if (h->core == SU2) { CUDA_TRY(cudaFuncSetAttribute(correlationKernel<SU2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); correlationKernel<SU2><<<h->nodeStride, 256, smem, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->nodeStride, h->dChiPartial.p, h->dChiCount.p); }
-	else if (h->core == XYZ) { CUDA_TRY(cudaFuncSetAttribute(correlationKernel<XYZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); correlationKernel<XYZ><<<h->nodeStride, 256, smem, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->nodeStride, h->dChiPartial.p, h->dChiCount.p); }
-	else { CUDA_TRY(cudaFuncSetAttribute(correlationKernel<TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); correlationKernel<TRI><<<h->nodeStride, 256, smem, h->stream>>>(P, h->dV4.p, h->dV2.p, h->dCutoff.p, h->nodeStride, h->dChiPartial.p, h->dChiCount.p); }
+	if (h->core == SU2) { CUDA_TRY(cudaFuncSetAttribute(correlationKernel<SU2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); correlationKernel<SU2><<<h->nodeStride, 256, smem, h->stream>>>(P, h->v4cur(), h->dV2.p, h->dCutoff.p, h->nodeStride, h->dChiPartial.p, h->dChiCount.p); }
+	else if (h->core == XYZ) { CUDA_TRY(cudaFuncSetAttribute(correlationKernel<XYZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); correlationKernel<XYZ><<<h->nodeStride, 256, smem, h->stream>>>(P, h->v4cur(), h->dV2.p, h->dCutoff.p, h->nodeStride, h->dChiPartial.p, h->dChiCount.p); }
+	else { CUDA_TRY(cudaFuncSetAttribute(correlationKernel<TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); correlationKernel<TRI><<<h->nodeStride, 256, smem, h->stream>>>(P, h->v4cur(), h->dV2.p, h->dCutoff.p, h->nodeStride, h->dChiPartial.p, h->dChiCount.p); }
 	CUDA_TRY(cudaGetLastError());
 	correlationSumKernel<<<(entries + 127) / 128, 128, 0, h->stream>>>(h->dChiPartial.p, h->dChiCount.p, entries, h->dChi.p);
 	CUDA_TRY(cudaGetLastError());
@@ -1346,6 +1610,7 @@ int pffrg_synchronize(pffrg_handle h)
 int pffrg_get_stats(pffrg_handle h, pffrg_stats *out)
 {
 	if (!h || !out) return fail(PFFRG_ERR_ARGUMENT, "null argument");
+	if (h->finalizePending) { CUDA_TRY(cudaSetDevice(h->device)); const int rc = collectFinalize(h); if (rc != PFFRG_OK) return rc; }
 	*out = h->stats;
 	out->jit_rpa = h->jitKernel ? 1 : 0;
 	out->jit_compile_ms = h->jitCompileMs;
@@ -1375,9 +1640,9 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 		std::vector<char> cubin;
 		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g));
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
-		std::vector<unsigned short> terms; std::vector<int> seg;
-		buildGramTables(d, L, Lp, g.gramRows, g.gramOffsetBits, terms, seg);
-		if (getenv("PFFRG_JIT_VERBOSE")) fprintf(stderr, "[pffrg gram] threads %d nb %d nbt %d ctas %d smem %zu rows/block %d gemm threads %d offset bits %d terms %zu\n", threads, g.nb, g.nbt, g.minBlocks, g.smem, g.gramRows, g.gramThreads, g.gramOffsetBits, terms.size());
+		std::vector<unsigned> terms; std::vector<int> seg; double conflicts = 0.0;
+		buildGramTables(d, L, Lp, g.gramRows, threads / 32, terms, seg, &conflicts);
+		if (getenv("PFFRG_JIT_VERBOSE")) fprintf(stderr, "[pffrg gram] threads %d nb %d nbt %d ctas %d smem %zu rows/block %d gemm threads %d words %zu (merged terms %lld) bank-conflict degree %.3f\n", threads, g.nb, g.nbt, g.minBlocks, g.smem, g.gramRows, g.gramThreads, terms.size(), (long long)uniquePairs, conflicts);
 		if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
 		return PFFRG_OK;
 	}
@@ -1470,13 +1735,13 @@ int pffrg_tri_terms(int region, int32_t *terms, int capacity)
 	return n;
 }
 
-int pffrg_gram_tables(const pffrg_desc *d, int rowsPerBlock, int offsetBits, uint16_t *terms, int capacity, int32_t *seg)
+int pffrg_gram_tables(const pffrg_desc *d, int rowsPerBlock, int warps, uint32_t *terms, int capacity, int32_t *seg, double *conflictDegree)
 {
-	if (!d || d->n_sites < 1 || !d->overlap_offsets || rowsPerBlock < 1 || offsetBits < 1 || offsetBits > 15 || !seg || (!terms && capacity > 0)) return fail(PFFRG_ERR_ARGUMENT, "bad argument");
+	if (!d || d->n_sites < 1 || d->n_sites > 256 || !d->overlap_offsets || rowsPerBlock < 1 || warps < 1 || warps > 32 || !seg || (!terms && capacity > 0)) return fail(PFFRG_ERR_ARGUMENT, "bad argument");
 	const int L = d->n_sites, Lp = paddedSites(L);
-	if ((long)rowsPerBlock * Lp > (1l << offsetBits)) return fail(PFFRG_ERR_ARGUMENT, "offset_bits too small for %d rows of %d", rowsPerBlock, Lp);
-	std::vector<unsigned short> t; std::vector<int> s;
-	buildGramTables(d, L, Lp, rowsPerBlock, offsetBits, t, s);
+	if ((long)rowsPerBlock * Lp > (1l << 14)) return fail(PFFRG_ERR_ARGUMENT, "%d rows of %d do not fit the 14 offset bits of a term word", rowsPerBlock, Lp);
+	std::vector<unsigned> t; std::vector<int> s;
+	buildGramTables(d, L, Lp, rowsPerBlock, warps, t, s, conflictDegree);
 	std::copy(s.begin(), s.end(), seg);
 	std::copy(t.begin(), t.begin() + std::min<size_t>(t.size(), (size_t)std::max(capacity, 0)), terms);
 	return (int)t.size();
@@ -1504,6 +1769,32 @@ double pffrg_fp64_peak(int device)
 	}
 	cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
 	if (cudaGetLastError() != cudaSuccess) { fail(PFFRG_ERR_CUDA, "FP64 probe failed"); return -1.0; }
+	return best;
+}
+
+double pffrg_dmma_peak(int device)
+{
+	if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); fail(PFFRG_ERR_CUDA, "cudaSetDevice(%d) failed", device); return -1.0; }
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+	double *out = nullptr; cudaEvent_t e0, e1;
+	if (cudaMalloc(&out, sizeof(double)) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	const int blocks = prop.multiProcessorCount * 8, iterations = 4000;
+	double best = 0.0;
+	for (int rep = 0; rep < 4; ++rep)
+	{
+		cudaEventRecord(e0);
+		dmmaPeakKernel<<<blocks, 256>>>(out, iterations, 1.0000001, 0.9999999);
+		cudaEventRecord(e1);
+		cudaEventSynchronize(e1);
+		float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+		// one m8n8k4 = 256 multiply-adds per warp
+		const double tflops = 2.0 * 256.0 * 8.0 * iterations * (256.0 / 32.0) * blocks / (ms * 1e-3) / 1e12;
+		if (rep > 0 && tflops > best) best = tflops;
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+	if (cudaGetLastError() != cudaSuccess) { fail(PFFRG_ERR_CUDA, "FP64 tensor-core probe failed"); return -1.0; }
 	return best;
 }
 

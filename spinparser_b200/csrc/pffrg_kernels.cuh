@@ -27,8 +27,8 @@ namespace pffrg
 		const int4 *rpa_tasks;   // {rid, wordBegin, wordEnd, 0}, ordered by RPA slot
 		const int *rpa_slot_off; // [nslots + 1]
 		const unsigned *rpa_words; // term stream of the generic RPA phase, see rpaGeneric
-		const unsigned short *gram_terms; // Gram form of the RPA sum (rpaGram): offset into the Gram block | multiplicity << gramOffsetBits
-		const int *gram_seg;     // [blocks * L + 1] term ranges per (row block, rid)
+		const unsigned *gram_terms; // Gram form of the RPA sum (rpaGram): words offset into the Gram block | rid << 14 | multiplicity << 22
+		const int2 *gram_seg;    // [blocks * warps] word range of (row block, warp), whole chunks of 256 words
 		int nrange;
 		const int *rng_fwd;      // [nrange]
 		const int *rng_inv;      // [nrange]
@@ -1126,9 +1126,7 @@ namespace pffrg
 	//    channels in registers: per node TM + TN 16-byte shared loads (contiguous across the lanes, broadcast across the other
 	//    lane index) feed 2 TM TN FP64 multiply-adds.
 	//  - The rows are worked off in blocks of PB = PT * TM rows: the block is written to shared memory (Gs[row][q] of double2) and
-	//    reduced at once: warp w owns the representative sites w, w + warps, ...; its lanes stride over the site's terms of this
-	//    block (16-bit words: offset into Gs | multiplicity), one 16-byte load + two multiply-adds per term, then a shuffle
-	//    reduction and a single-writer update of the output.
+	//    reduced at once (gramReduce below): every warp owns a contiguous range of whole rid lists of the block's term array.
 	// ================================================================================================================
 	namespace gramcfg
 	{
@@ -1141,8 +1139,7 @@ namespace pffrg
 		constexpr int NBLK = (Lp + PB - 1) / PB;
 		constexpr int LAST_ROWS = Lp - (NBLK - 1) * PB;
 		constexpr int TM_LAST = (LAST_ROWS + PT - 1) / PT;
-		constexpr int OFFSET_BITS = PFFRG_GRAM_OFFSET_BITS; // bits of a term word that address Gs
-		static_assert(NT % 64 == 0 && PB % PT == 0 && TM >= 1 && PB * Lp <= (1 << OFFSET_BITS), "Gram geometry");
+		static_assert(NT % 64 == 0 && PB % PT == 0 && TM >= 1 && PB * Lp <= (1 << 14), "Gram geometry");
 	}
 
 	template <int TMB>
@@ -1187,27 +1184,45 @@ namespace pffrg
 		}
 	}
 
-	// reduction of one row block: rpaOut[c * L + rid] += sum over the block's terms of rid of multiplicity * Gs[offset].c
+	// Reduction of one row block: rpaOut[c * L + rid] += sum over the block's terms of rid of multiplicity * Gs[offset].c.
+	// The terms of a block are one flat array of 32-bit words (offset | rid << 14 | multiplicity << 22), sorted by rid; every warp owns a
+	// contiguous range of whole rid lists (single writer per output), padded to whole chunks of 256 words. A lane reads 8 consecutive
+	// words per chunk (two 16-byte loads, the next chunk's in flight while this one is worked off); every rid list is padded to a
+	// multiple of 8 words, so the 8 words of a lane belong to ONE rid: 8 loads from Gs and 16 multiply-adds per lane, then one segmented
+	// scan over the lanes (rids ascend with the lane index) and the last lane of every segment updates the output. The host orders the
+	// words of a list so that the 8 lanes of a quarter warp hit 8 different 16-byte bank groups of Gs in every step (buildGramTables).
+	constexpr unsigned GRAM_OFFSET_MASK = (1u << 14) - 1u;
 	__device__ __forceinline__ void gramReduce(const Problem &P, int blk, const double2 *__restrict__ Gs, double *rpaOut, int warp, int lane, int warps)
 	{
-		using namespace gramcfg;
 		constexpr int L = PFFRG_CONST_L;
-		const int *seg = P.gram_seg + blk * L;
-		for (int rid = warp; rid < L; rid += warps)
+		const int2 range = __ldg(P.gram_seg + blk * warps + warp);
+		const int chunks = (range.y - range.x) >> 8;
+		if (chunks <= 0) return;
+		const uint4 *words = reinterpret_cast<const uint4 *>(P.gram_terms + range.x) + 2 * lane;
+		uint4 n0 = __ldg(words), n1 = __ldg(words + 1);
+		#pragma unroll 1
+		for (int c = 0; c < chunks; ++c)
 		{
-			const int begin = __ldg(seg + rid), end = __ldg(seg + rid + 1);
-			double sx = 0.0, sy = 0.0;
-			#pragma unroll 4
-			for (int i = begin + lane; i < end; i += 32)
-			{
-				const unsigned w = __ldg(P.gram_terms + i);
-				const double2 g = Gs[w & ((1u << OFFSET_BITS) - 1u)];
-				const double m = (double)(int)(w >> OFFSET_BITS);
-				sx = fma(m, g.x, sx); sy = fma(m, g.y, sy);
-			}
+			const uint4 w0 = n0, w1 = n1;
+			if (c + 1 < chunks) { n0 = __ldg(words + 64 * (c + 1)); n1 = __ldg(words + 64 * (c + 1) + 1); }
+			const unsigned w[8] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
+			const int rid = (int)((w[0] >> 14) & 255u);
+			double2 g[8];
 			#pragma unroll
-			for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
-			if (lane == 0 && end > begin) { rpaOut[rid] += sx; rpaOut[L + rid] += sy; }
+			for (int k = 0; k < 8; ++k) g[k] = Gs[w[k] & GRAM_OFFSET_MASK];
+			double sx = 0.0, sy = 0.0;
+			#pragma unroll
+			for (int k = 0; k < 8; ++k) { const double m = (double)(int)(w[k] >> 22); sx = fma(m, g[k].x, sx); sy = fma(m, g[k].y, sy); }
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const double ox = __shfl_up_sync(0xffffffffu, sx, d), oy = __shfl_up_sync(0xffffffffu, sy, d);
+				const int orid = __shfl_up_sync(0xffffffffu, rid, d);
+				if (lane >= d && orid == rid) { sx += ox; sy += oy; }
+			}
+			const int nextRid = __shfl_down_sync(0xffffffffu, rid, 1);
+			if (lane == 31 || nextRid != rid) { rpaOut[rid] += sx; rpaOut[L + rid] += sy; }
+			__syncwarp(); // the next chunk of this warp may continue the same rid
 		}
 	}
 
@@ -1548,6 +1563,72 @@ namespace pffrg
 
 	__global__ void setScalarKernel(double *p, double v) { *p = v; }
 
+	// ================================================================================================================
+	// Multi-GPU exchange over peer memory (NVLink / NVSwitch): one process per GPU, every rank maps the state buffers of all
+	// ranks (CUDA IPC). The Euler update of a rank's slice and its distribution are ONE kernel: the new values are stored into
+	// the slice of EVERY rank's next-state buffer (the state is double buffered: work items still in flight on another GPU read
+	// the old state from anywhere in (s,t,u)). Replaces finalizeStep's MPI_Bcast (src/lib/LoadManager.hpp:240 issued from
+	// src/SU2/SU2FrgCore.cpp:136). Arrival is signalled through per-rank epoch counters in peer memory.
+	// ================================================================================================================
+	constexpr int MAX_RANKS = 16;
+	struct PushTargets { double *dst[MAX_RANKS]; int n; };
+	struct SyncBlock
+	{
+		unsigned long long arrived[MAX_RANKS]; // arrived[r]: last exchange epoch whose data from rank r is complete in THIS rank's memory
+		double times[MAX_RANKS];               // flow-kernel time of rank r in the step of that epoch (feedback of the partition)
+	};
+	struct PeerSyncs { SyncBlock *block[MAX_RANKS]; int n; };
+
+	// new = old + (newCutoff - cutoff) * flow on n doubles (n even, 16-byte aligned), stored to every target
+	__global__ void __launch_bounds__(256) eulerPushKernel(const double2 *__restrict__ old, const double2 *__restrict__ flow, size_t n2, const double *cutoffPtr, double newCutoff, PushTargets T)
+	{
+		const double step = newCutoff - *cutoffPtr;
+		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+		{
+			const double2 o = old[i], f = __ldg(flow + i);
+			const double2 v = make_double2(o.x + step * f.x, o.y + step * f.y);
+			#pragma unroll 4
+			for (int d = 0; d < T.n; ++d) reinterpret_cast<double2 *>(T.dst[d])[i] = v;
+		}
+		__threadfence_system(); // this thread's peer stores are performed before the kernel ends (the arrival signal follows in stream order)
+	}
+	// plain distribution of a slice (sharded upload): every target but the first (the rank's own buffer, which is the source)
+	__global__ void __launch_bounds__(256) copyPushKernel(const double2 *__restrict__ src, size_t n2, PushTargets T)
+	{
+		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+		{
+			const double2 v = src[i];
+			#pragma unroll 4
+			for (int d = 0; d < T.n; ++d) reinterpret_cast<double2 *>(T.dst[d])[i] = v;
+		}
+		__threadfence_system();
+	}
+	// one thread per rank: publish this rank's kernel time and epoch in that rank's sync block
+	__global__ void signalPeersKernel(PeerSyncs S, int me, unsigned long long epoch, double ms)
+	{
+		const int r = threadIdx.x;
+		if (r >= S.n) return;
+		S.block[r]->times[me] = ms;
+		__threadfence_system();
+		asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(&S.block[r]->arrived[me]), "l"(epoch) : "memory");
+	}
+	// one thread per rank: wait until that rank's epoch has arrived here. A rank that never arrives (a crashed peer) ends the
+	// wait after `timeoutClocks` and raises *timeoutFlag (pinned host memory), which the next host synchronisation reports.
+	__global__ void waitPeersKernel(const SyncBlock *mine, int n, unsigned long long epoch, long long timeoutClocks, int *timeoutFlag)
+	{
+		const int r = threadIdx.x;
+		if (r >= n) return;
+		const long long t0 = clock64();
+		unsigned long long seen = 0;
+		for (;;)
+		{
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(&mine->arrived[r]) : "memory");
+			if (seen >= epoch) break;
+			if (clock64() - t0 > timeoutClocks) { *timeoutFlag = 1; __threadfence_system(); break; }
+			__nanosleep(200);
+		}
+	}
+
 	// frequency-independent initial vertex: v4[row][c][j] = bare[c][j]
 	__global__ void initialConditionKernel(double *__restrict__ v4, const double *__restrict__ bare, size_t rows, int L, int Lp, int RL, int vw)
 	{
@@ -1576,27 +1657,49 @@ namespace pffrg
 		if (s == 1.2345) out[0] = s; // never true: keeps the chains alive
 	}
 
+	// FP64 tensor-core throughput probe (pffrg_dmma_peak): 8 independent accumulator tiles per warp, nothing but DMMA m8n8k4 in the loop
+	__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
+	{
+		asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+	}
+	__global__ void __launch_bounds__(256) dmmaPeakKernel(double *out, int iterations, double a, double b)
+	{
+		double c[8][2];
+		#pragma unroll
+		for (int i = 0; i < 8; ++i) { c[i][0] = a + i; c[i][1] = b + threadIdx.x; }
+		for (int it = 0; it < iterations; ++it)
+		{
+			#pragma unroll
+			for (int i = 0; i < 8; ++i) dmma884(c[i], a, b);
+		}
+		double s = 0.0;
+		#pragma unroll
+		for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+		if (s == 1.2345) out[0] = s; // never true: keeps the chains alive
+	}
+
 	// reference array (one channel, [row][L], or TRI [row][16][L]) -> device layout; T = float or double
+	// `src` / `dst` in reference layout start at row 0 of the staging array, which holds the rows [rowBegin, rowBegin + rows) of the vertex
 	template <typename T>
-	__global__ void importKernel(const T *__restrict__ src, double *__restrict__ dst, size_t rows, int L, int Lp, int RL, int vw, int cFirst, int cCount)
+	__global__ void importKernel(const T *__restrict__ src, double *__restrict__ dst, size_t rowBegin, size_t rows, int L, int Lp, int RL, int vw, int cFirst, int cCount)
 	{
 		const size_t n = rows * cCount * L;
 		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 		{
 			const size_t row = i / ((size_t)cCount * L);
 			const int r = (int)(i - row * cCount * L), c = r / L, j = r - c * L;
-			dst[row * RL + channelOffset(vw, cFirst + c, Lp) + j * vw] = (double)src[i];
+			dst[(rowBegin + row) * RL + channelOffset(vw, cFirst + c, Lp) + j * vw] = (double)src[i];
 		}
 	}
 	template <typename T>
-	__global__ void exportKernel(const double *__restrict__ src, T *__restrict__ dst, size_t rows, int L, int Lp, int RL, int vw, int cFirst, int cCount)
+	__global__ void exportKernel(const double *__restrict__ src, T *__restrict__ dst, size_t rowBegin, size_t rows, int L, int Lp, int RL, int vw, int cFirst, int cCount)
 	{
 		const size_t n = rows * cCount * L;
 		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 		{
 			const size_t row = i / ((size_t)cCount * L);
 			const int r = (int)(i - row * cCount * L), c = r / L, j = r - c * L;
-			dst[i] = (T)src[row * RL + channelOffset(vw, cFirst + c, Lp) + j * vw];
+			dst[i] = (T)src[(rowBegin + row) * RL + channelOffset(vw, cFirst + c, Lp) + j * vw];
 		}
 	}
 	template <typename T>

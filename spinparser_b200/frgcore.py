@@ -197,11 +197,21 @@ class FrgCore:
             return _capi.F32
         raise PffrgError(-1, f"unsupported dtype {dtype}")
 
-    def setState(self, cutoff: float, v2: np.ndarray, v4: Sequence[np.ndarray]) -> None:
+    def setState(self, cutoff: float, v2: np.ndarray, v4: Sequence[np.ndarray], sharded: bool = False) -> None:
+        """Upload a state. ``sharded=True`` (multi-GPU runs in which every rank holds the same host state, like the MPI ranks of the
+        reference): every rank uploads only its share of the rows and the shares are distributed over NVLink
+        (``pffrg_set_state_sharded``; collective)."""
         code = self._dtype_code(v2.dtype)
         if any(a.dtype != v2.dtype for a in v4) or v2.size != self.tables.n_frequencies:
             raise PffrgError(-1, "state arrays must share one dtype and match the mesh size")
-        check(lib.pffrg_set_state(self._h, float(cutoff), v2.ctypes.data, self._ptrs(v4), code))
+        fn = lib.pffrg_set_state_sharded if sharded else lib.pffrg_set_state
+        check(fn(self._h, float(cutoff), v2.ctypes.data, self._ptrs(v4), code))
+
+    def uploadSlice(self):
+        """Work items [begin, end) this rank uploads in ``setState(..., sharded=True)`` (an even split)."""
+        b, e = C.c_int64(), C.c_int64()
+        check(lib.pffrg_upload_slice(self._h, C.byref(b), C.byref(e)))
+        return b.value, e.value
 
     def setInitialCondition(self, bare_couplings: Sequence[np.ndarray], cutoff: float) -> None:
         """Initial condition of ``SU2EffectiveAction`` (src/SU2/SU2EffectiveAction.hpp:38-60) and the XYZ/TRI equivalents:
@@ -209,9 +219,11 @@ class FrgCore:
         normalization and, for XYZ/TRI, multiplied by 1/4); the self energy starts at zero. Built on the device
         (``pffrg_set_initial_condition``)."""
         L, n_ch = self.tables.n_sites, N_CHANNELS[self.identifier]
-        bare = np.zeros((n_ch, L), dtype=np.float64)
-        for c, values in enumerate(bare_couplings):
-            bare[c] = values
+        # one array per channel, or (TRI) the first row of the reference's single array, [mu][nu][rid]
+        flat = np.concatenate([np.ravel(np.asarray(v, dtype=np.float64)) for v in bare_couplings])
+        if flat.size != n_ch * L:
+            raise PffrgError(-1, f"expected {n_ch} x {L} bare couplings, got {flat.size}")
+        bare = np.ascontiguousarray(flat.reshape(n_ch, L))
         check(lib.pffrg_set_initial_condition(self._h, float(cutoff), bare.ctypes.data_as(C.POINTER(C.c_double))))
 
     def pinnedEffectiveAction(self, dtype=np.float64) -> EffectiveAction:
@@ -235,11 +247,15 @@ class FrgCore:
         ea.v4 = [pinned(self.array_length) for _ in range(self.n_arrays)]
         return ea
 
-    def flowingFunctional(self, dtype=np.float64, into: Optional[EffectiveAction] = None) -> EffectiveAction:
-        """Download the current state (``FrgCore::flowingFunctional``, src/FrgCore.hpp:93-96)."""
+    def flowingFunctional(self, dtype=np.float64, into: Optional[EffectiveAction] = None, items: Optional[Sequence[int]] = None) -> EffectiveAction:
+        """Download the current state (``FrgCore::flowingFunctional``, src/FrgCore.hpp:93-96). ``items=(begin, end)`` with ``into``:
+        only the rows of those work items are transferred (``pffrg_get_state_slice``); the other rows of ``into`` are left as they are."""
         if into is not None:
             cutoff = C.c_double()
-            check(lib.pffrg_get_state(self._h, C.byref(cutoff), into.v2.ctypes.data, self._ptrs(into.v4), self._dtype_code(into.v2.dtype)))
+            if items is not None:
+                check(lib.pffrg_get_state_slice(self._h, C.byref(cutoff), into.v2.ctypes.data, self._ptrs(into.v4), self._dtype_code(into.v2.dtype), int(items[0]), int(items[1])))
+            else:
+                check(lib.pffrg_get_state(self._h, C.byref(cutoff), into.v2.ctypes.data, self._ptrs(into.v4), self._dtype_code(into.v2.dtype)))
             into.cutoff = cutoff.value
             return into
         ea = EffectiveAction(self.identifier, self.tables.n_frequencies, self.tables.n_sites, dtype)
@@ -282,6 +298,20 @@ class FrgCore:
         s = _capi.Stats()
         check(lib.pffrg_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def shapeEnvironment(self) -> Dict[str, str]:
+        """Environment settings that make ``pffrg_create`` arrive at this core's launch shape without autotuning: the ranks of a
+        sharded run must all use ONE shape (rank 0 tunes, the others adopt its choice), otherwise their summation orders differ in
+        the last bit and the sharded state is no longer bit-identical to the single-GPU one."""
+        st = self.stats()
+        env = {"PFFRG_AUTOTUNE": "0"}
+        if st["jit_rpa"] and st["autotuned_shapes"] > 1:
+            subs = max(1, st["sub_ctas"])
+            env.update({"PFFRG_THREADS": str(st["threads"] // subs), "PFFRG_JIT_NBT": str(st["rpa_batch"] // subs), "PFFRG_JIT_NB": str(st["node_batch"]),
+                        "PFFRG_JIT_MINBLOCKS": str(st["min_blocks"])})
+            if subs > 1:
+                env["PFFRG_SUBCTAS"] = str(subs)
+        return env
 
     @property
     def stream(self) -> int:

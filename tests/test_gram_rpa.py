@@ -14,22 +14,23 @@ import pytest
 from conftest import golden
 
 
-def _tables(d, rows_per_block, bits):
+def _tables(d, rows_per_block, warps):
     from spinparser_b200 import ProblemTables, _capi
     from spinparser_b200.frgcore import make_descriptor
     t = ProblemTables.from_pfd(d)
     L = t.n_sites
     Lp = (L + 3) // 4 * 4
     blocks = (Lp + rows_per_block - 1) // rows_per_block
-    seg = np.zeros(blocks * L + 1, dtype=np.int32)
+    seg = np.zeros(2 * blocks * warps, dtype=np.int32)
     desc = make_descriptor("SU2", t)
-    n = _capi.check(_capi.lib.pffrg_gram_tables(C.byref(desc), rows_per_block, bits, None, 0, seg.ctypes.data_as(C.POINTER(C.c_int32))))
-    terms = np.zeros(n, dtype=np.uint16)
-    assert _capi.lib.pffrg_gram_tables(C.byref(desc), rows_per_block, bits, terms.ctypes.data_as(C.POINTER(C.c_uint16)), n, seg.ctypes.data_as(C.POINTER(C.c_int32))) == n
-    return t, L, Lp, blocks, terms, seg
+    degree = C.c_double(0.0)
+    n = _capi.check(_capi.lib.pffrg_gram_tables(C.byref(desc), rows_per_block, warps, None, 0, seg.ctypes.data_as(C.POINTER(C.c_int32)), None))
+    terms = np.zeros(n, dtype=np.uint32)
+    assert _capi.lib.pffrg_gram_tables(C.byref(desc), rows_per_block, warps, terms.ctypes.data_as(C.POINTER(C.c_uint32)), n, seg.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(degree)) == n
+    return t, L, Lp, blocks, terms, seg.reshape(blocks * warps, 2), degree.value
 
 
-def _emulate(L, Lp, threads, tm, nodes, A, B, terms, seg, bits):
+def _emulate(L, Lp, threads, tm, nodes, A, B, terms, seg):
     """The block update and the reduction with the kernel's index arithmetic (gramcfg / gramBlock / gramReduce)."""
     NT = threads // 64 * 64
     PT = NT // 16
@@ -37,11 +38,12 @@ def _emulate(L, Lp, threads, tm, nodes, A, B, terms, seg, bits):
     PB = PT * TM
     TN = (Lp + 15) // 16
     blocks = (Lp + PB - 1) // PB
+    warps = threads // 32
     out = np.zeros(L)
     for blk in range(blocks):
         rows = PB if blk < blocks - 1 else Lp - (blocks - 1) * PB
         tmb = TM if blk < blocks - 1 else (rows + PT - 1) // PT
-        Gs = np.full(PB * Lp, np.nan)  # entries the kernel does not store must never be read
+        Gs = np.full(PB * Lp, np.nan)  # entries the kernel does not store must never be read with a non-zero multiplicity
         for tid in range(NT):
             warp, lane = tid >> 5, tid & 31
             tp, tq = (warp >> 1) * 4 + (lane >> 3), (warp & 1) * 8 + (lane & 7)
@@ -52,9 +54,20 @@ def _emulate(L, Lp, threads, tm, nodes, A, B, terms, seg, bits):
                     acc = float(np.dot(A[:nodes, pa], B[:nodes, qb]))
                     if tp + PT * i < rows and tq + 16 * j < Lp:
                         Gs[(tp + PT * i) * Lp + tq + 16 * j] = acc
-        for rid in range(L):
-            w = terms[seg[blk * L + rid]:seg[blk * L + rid + 1]].astype(np.int64)
-            out[rid] += float(np.sum((w >> bits) * Gs[w & ((1 << bits) - 1)]))
+        owner = {}
+        for warp in range(warps):
+            begin, end = seg[blk * warps + warp]
+            assert begin % 256 == 0 and (end - begin) % 256 == 0 and end >= begin
+            for chunk in range((end - begin) // 256):
+                for lane in range(32):
+                    w = terms[begin + 256 * chunk + 8 * lane:begin + 256 * chunk + 8 * lane + 8].astype(np.int64)
+                    rid = int((w[0] >> 14) & 255)
+                    mult = w >> 22
+                    assert np.all(((w >> 14) & 255)[mult > 0] == rid), "the 8 words of a lane belong to one rid"
+                    assert owner.setdefault(rid, warp) == warp or not mult.any(), "single writer per output and block"
+                    g = Gs[w & 0x3FFF]
+                    assert not np.isnan(g[mult > 0]).any()
+                    out[rid] += float(np.sum(np.where(mult > 0, mult * np.nan_to_num(g), 0.0)))
     return out, PB
 
 
@@ -66,13 +79,12 @@ def test_gram_tables_reproduce_the_overlap_sum(case, threads, tm):
     Lp0 = (L0 + 3) // 4 * 4
     PT = (threads // 64 * 64) // 16
     PB = PT * min(tm, (Lp0 + PT - 1) // PT)
-    bits = max(1, int(np.ceil(np.log2(PB * Lp0))))
-    t, L, Lp, blocks, terms, seg = _tables(d, PB, bits)
+    t, L, Lp, blocks, terms, seg, degree = _tables(d, PB, threads // 32)
     rng = np.random.default_rng(5)
     nodes = 11
     A = np.zeros((16, Lp)); B = np.zeros((16, Lp))
     A[:, :L] = rng.uniform(-1, 1, (16, L)); B[:, :L] = rng.uniform(-1, 1, (16, L))
-    got, pb = _emulate(L, Lp, threads, tm, nodes, A, B, terms, seg, bits)
+    got, pb = _emulate(L, Lp, threads, tm, nodes, A, B, terms, seg)
     assert pb == PB
     want = np.zeros(L)
     off, r1, r2 = t.overlap_offsets, t.overlap_rid1, t.overlap_rid2
@@ -81,15 +93,18 @@ def test_gram_tables_reproduce_the_overlap_sum(case, threads, tm):
             want[rid] += float(np.dot(A[:nodes, r1[i]], B[:nodes, r2[i]]))
     assert np.allclose(got, want, rtol=1e-12, atol=1e-12), np.abs(got - want).max()
     # every overlap entry is represented exactly once (multiplicities add up)
-    assert int(np.sum(terms.astype(np.int64) >> bits)) == int(off[-1])
+    assert int(np.sum(terms.astype(np.int64) >> 22)) == int(off[-1])
+    assert 1.0 <= degree <= 8.0
 
 
-def test_large_multiplicities_are_split():
-    """With few multiplicity bits a merged term is emitted as several words."""
-    d = golden("su2_kagome_r7_nw6")
-    L = int(d["lattice/size"]); Lp = (L + 3) // 4 * 4
-    bits = 15
-    assert 16 * Lp <= 1 << bits
-    t, L, Lp, blocks, terms, seg = _tables(d, 16, bits)
-    assert int((terms >> bits).max()) == 1
-    assert int(np.sum(terms.astype(np.int64) >> bits)) == int(t.overlap_offsets[-1])
+def test_term_order_of_the_benchmark_lattice_is_nearly_conflict_free():
+    """pyrochlore-r8 (L = 103, 40 355 merged terms): the word order keeps the 8 lanes of a quarter warp on different 16-byte bank groups."""
+    import os
+    from conftest import ROOT
+    from spinparser_b200 import read_pfd
+    d = read_pfd(os.path.join(ROOT, "bench_data", "pyrochlore_r8_su2_nw64.tables.pfd"))
+    t, L, Lp, blocks, terms, seg, degree = _tables(d, 64, 8)
+    assert blocks == 2 and L == 103
+    assert int(np.sum(terms.astype(np.int64) >> 22)) == int(t.overlap_offsets[-1])
+    assert len(terms) < 1.15 * 40355, "padding overhead of the term array"
+    assert degree < 1.4, degree  # a random order gives ~2.5

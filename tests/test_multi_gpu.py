@@ -35,11 +35,11 @@ name = bytes(d["core"]).decode()
 opts = {"spin": str(float(d["spinLength"]))} if name == "SU2" else {}
 n = {"SU2": 2, "XYZ": 4, "TRI": 1}[name]
 cut = [float(x) for x in d["cutoff"]]
-start = 10
+start = int(sys.argv[4])
 v2 = np.ascontiguousarray(d[f"step{start}/state/v2"]); v4 = [np.ascontiguousarray(d[f"step{start}/state/v4_{c}"]) for c in range(n)]
 
 def run(core, sharded):
-    core.setState(cut[start], v2, v4)
+    core.setState(cut[start], v2, v4, sharded=sharded and os.environ.get("TEST_SHARDED_UPLOAD") == "1")
     ranges = []
     for k in range(steps):
         assert not core.computeStep()
@@ -49,11 +49,23 @@ def run(core, sharded):
         core.finalizeStep(cut[start + k + 1])
     return core.flowingFunctional(), flow, ranges
 
-core = FrgCoreFactory.newFrgCore(name, ProblemTables.from_pfd(d), opts, device=local)
-ids = [core.uniqueId() if rank == 0 else None]
+# launch shape: rank 0 creates its core first (autotuning when PFFRG_AUTOTUNE=1 is set), the others adopt its shape (as bench.py does)
+core = FrgCoreFactory.newFrgCore(name, ProblemTables.from_pfd(d), opts, device=local) if rank == 0 else None
+ids = [(core.uniqueId(), core.shapeEnvironment()) if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
-core.initCommunicator(ids[0], rank, world)
+os.environ.update(ids[0][1])  # rank 0 too: its single-GPU comparison core below must use the same shape
+if rank != 0:
+    core = FrgCoreFactory.newFrgCore(name, ProblemTables.from_pfd(d), opts, device=local)
+core.initCommunicator(ids[0][0], rank, world)
 state, flow, ranges = run(core, True)
+# download of a slice only: the rows of this rank's upload share, into a host copy that is otherwise stale (zeros)
+b, e = core.uploadSlice()
+from spinparser_b200.frgcore import EffectiveAction
+part = EffectiveAction(name, len(v2), int(d["lattice/size"]))
+core.flowingFunctional(into=part, items=(b, e))
+per = len(v4[0]) // (len(v2) * len(v2) * (len(v2) + 1) // 2)
+for c in range(n):
+    assert np.array_equal(part.v4[c][b * per:e * per], state.v4[c][b * per:e * per]) and not part.v4[c][:b * per].any() and not part.v4[c][e * per:].any()
 core.close()
 nf = len(v4[0]) // (int(d["lattice/size"]) * (16 if name == "TRI" else 1))
 all_ranges = [None] * world
@@ -86,16 +98,28 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("case", ["su2_square_r3_nw10", "xyz_honeycomb_kitaev_r3_nw10", "tri_honeycomb_kg_r3_nw8"])
-def test_sharded_flow_equals_single_gpu_flow(case, tmp_path):
+# exchange of the updated slices: fused Euler + peer-memory stores over NVLink (default), the NCCL broadcast group (PFFRG_EXCHANGE=nccl);
+# upload of 1/N of the rows per rank + distribution over NVLink; launch shape autotuned on rank 0 and adopted by the other ranks
+MODES = {"p2p": {}, "nccl": {"PFFRG_EXCHANGE": "nccl"}, "sharded_upload": {"TEST_SHARDED_UPLOAD": "1"}, "autotune": {"PFFRG_AUTOTUNE": "1"},
+         "gram": {"PFFRG_RPA": "gram"}}
+
+
+@pytest.mark.parametrize("case,mode", [("su2_square_r3_nw10", "p2p"), ("xyz_honeycomb_kitaev_r3_nw10", "p2p"), ("tri_honeycomb_kg_r3_nw8", "p2p"),
+                                       ("su2_kagome_r4_nw8", "nccl"), ("xyz_kagome_r4_nw8", "sharded_upload"), ("su2_kagome_r7_nw6", "autotune"),
+                                       ("su2_kagome_r7_nw6", "gram")])
+def test_sharded_flow_equals_single_gpu_flow(case, mode, tmp_path):
     from spinparser_b200.frgcore import device_count
     world = min(device_count(), 8)
     if world < 2:
         pytest.skip("needs at least two GPUs")
+    from conftest import dumped_steps, golden
+    start = [k for k in dumped_steps(golden(case)) if k > 0][0]
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), str(script), ROOT, case, "3"]
-    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", str(_free_port()), str(script), ROOT, case, "3", str(start)]
+    env = dict(os.environ)
+    env.update(MODES[mode])
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "MULTI_GPU_OK" in proc.stdout
