@@ -99,7 +99,7 @@ namespace harness
 	{
 		std::string taskFile, resourcePath, out, loadState, mode = "run";
 		std::vector<int> dumpSteps;
-		int maxSteps = -1, startStep = 0, threads = 0, timeStride = 1, timeRepeat = 1, timeWarmup = 1, timeOffset = 0;
+		int maxSteps = -1, startStep = 0, threads = 0, timeStride = 1, timeRepeat = 1, timeWarmup = 1, timeOffset = 0, resumeAfter = -1;
 		bool measure = true, verbose = false, dumpLattice = true, timeCompact = false;
 	};
 	static Options opt;
@@ -230,6 +230,8 @@ CommandLineOptions::CommandLineOptions(int argc, char **argv)
 		else if (a == "--time-warmup") opt.timeWarmup = std::stoi(next());
 		else if (a == "--time-offset") opt.timeOffset = std::stoi(next());
 		else if (a == "--time-compact") opt.timeCompact = true;
+		else if (a == "--resume-after") opt.resumeAfter = std::stoi(next());
+		else if (a == "--checkpoint-time") _checkpointTime = std::stoi(next());
 		else if (a == "--no-measure") opt.measure = false;
 		else if (a == "--no-lattice") opt.dumpLattice = false;
 		else if (a.size() && a[0] == '-') throw Exception(Exception::Type::ArgumentError, "unknown option " + a);
@@ -250,7 +252,7 @@ std::string CommandLineOptions::resourcePath() const { return _resourcePath; }
 SpinParser *SpinParser::_spinParserInstance = nullptr;
 SpinParser *SpinParser::spinParser() { if (_spinParserInstance == nullptr) _spinParserInstance = new SpinParser; return _spinParserInstance; }
 FrgCore *SpinParser::getFrgCore() const { return _frgCore; }
-SpinParser::SpinParser() { _isMasterRank = true; _commandLineOptions = nullptr; _taskFileParser = nullptr; _loadManager = HMP::newLoadManager(); _frgCore = nullptr; }
+SpinParser::SpinParser() { _isMasterRank = !getenv("PFFRG_RANK") || atoi(getenv("PFFRG_RANK")) == 0; _commandLineOptions = nullptr; _taskFileParser = nullptr; _loadManager = HMP::newLoadManager(); _frgCore = nullptr; }
 SpinParser::~SpinParser() { delete _commandLineOptions; delete _frgCore; }
 bool SpinParser::isMasterRank() const { return _isMasterRank; }
 ComputationStatus SpinParser::getComputationStatus() const { return _computationStatus; }
@@ -355,27 +357,62 @@ int SpinParser::run(int argc, char **argv)
 			return 0;
 		}
 
-		// Euler loop, src/SpinParser.cpp:141-172
+		// Euler loop, src/SpinParser.cpp:141-172 (restated here: SpinParser.cpp itself is not compiled). --resume-after N: a checkpoint is
+		// written after N steps (SpinParser::writeCheckpoint, :224-233, its vertex part); after the run the checkpoint is read back
+		// (:131-135) and the flow repeated from there without measurements: "resumed/final" must equal "final".
 		auto wants = [&](int s) { return std::find(opt.dumpSteps.begin(), opt.dumpSteps.end(), s) != opt.dumpSteps.end(); };
 		std::vector<double> stepSeconds;
-		int done = 0;
-		while (cutoff != FrgCommon::cutoff().last())
+		_computationStatus.checkpointTime = Timestamp::time();
+		auto runLoop = [&](CutoffIterator cutoff, int step, bool measure, bool first)
 		{
-			if (opt.maxSteps >= 0 && done >= opt.maxSteps) break;
-			if (wants(step)) dumpState(w, "step" + std::to_string(step) + "/state", state);
-			auto tic = std::chrono::steady_clock::now();
-			_frgCore->computeStep();
-			stepSeconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - tic).count());
-			if (opt.measure) _frgCore->takeMeasurements();
-			if (wants(step)) dumpState(w, "step" + std::to_string(step) + "/flow", flow);
-			if (_frgCore->_flow->isDiverged()) { w.scalar("divergedAtStep", step); break; }
-			++cutoff; ++step; ++done;
-			_frgCore->finalizeStep(*cutoff);
-		}
-		if (opt.measure) _frgCore->takeMeasurements();
+			int done = 0;
+			while (cutoff != FrgCommon::cutoff().last())
+			{
+				if (opt.maxSteps >= 0 && done >= opt.maxSteps) break;
+				if (first && wants(step)) dumpState(w, "step" + std::to_string(step) + "/state", state);
+				auto tic = std::chrono::steady_clock::now();
+				_frgCore->computeStep();
+				if (first) stepSeconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - tic).count());
+				if (measure) _frgCore->takeMeasurements();
+				if (first && wants(step)) dumpState(w, "step" + std::to_string(step) + "/flow", flow);
+				if (_frgCore->_flow->isDiverged()) { if (first) w.scalar("divergedAtStep", step); break; }
+				++cutoff; ++step; ++done;
+				_frgCore->finalizeStep(*cutoff);
+				if (Timestamp::isOlder(_computationStatus.checkpointTime, _commandLineOptions->checkpointTime()) || (first && done == opt.resumeAfter))
+				{
+					_computationStatus.checkpointTime = Timestamp::time();
+					_frgCore->_flowingFunctional->writeCheckpoint(_fileset.checkpointFile);
+					if (first) w.scalar("checkpointAtStep", step);
+				}
+			}
+			if (measure) _frgCore->takeMeasurements();
+			return step;
+		};
+		step = runLoop(cutoff, step, opt.measure, true);
 		dumpState(w, "final", state);
 		w.scalar("finalStep", step);
 		w.doubles("stepSeconds", stepSeconds);
+		if (opt.resumeAfter >= 0)
+		{
+			if (!_frgCore->_flowingFunctional->readCheckpoint(_fileset.checkpointFile)) throw Exception(Exception::Type::IOError, "no checkpoint to resume from");
+			CutoffIterator resumed = FrgCommon::cutoff().find(_frgCore->_flowingFunctional->cutoff);
+			int resumedStep = 0; for (auto i = FrgCommon::cutoff().begin(); i != resumed; ++i) ++resumedStep;
+			w.scalar("resumed/fromStep", resumedStep);
+			const int last = runLoop(resumed, resumedStep, false, false);
+			dumpState(w, "resumed/final", state);
+			w.scalar("resumed/finalStep", last);
+		}
+		// post-processing stage of deferred measurements, src/SpinParser.cpp:199-214: every state FrgCore::takeMeasurements appended to
+		// the data file is read back and measured
+		bool postprocessing = _commandLineOptions->deferMeasurements();
+		for (auto m : _frgCore->_measurements) if (m->isDeferred()) postprocessing = true;
+		if (postprocessing && opt.measure)
+		{
+			_computationStatus.statusIdentifier = ComputationStatus::Identifier::Postprocessing;
+			int n = 0;
+			while (_frgCore->_flowingFunctional->readCheckpoint(_fileset.dataFile, n++)) _frgCore->takeMeasurements();
+			w.scalar("postprocessedStates", n - 1);
+		}
 		dumpH5(w);
 		w.close();
 	}

@@ -237,35 +237,39 @@ namespace
 	// warps (one per SM sub-partition when there are four), each on its own group of 16 (SU2) or 32 staged nodes, so the
 	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Environment overrides for tuning runs:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_TILES, PFFRG_JIT_MINBLOCKS.
-	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0, gramOffsetBits = 0; };
+	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0; };
 
-	// Launch shape of the kernel with the Gram form of the RPA phase (rpaGram, pffrg_kernels.cuh): the GEMM threads form a PT x 16 grid
-	// with up to four rows per thread, i.e. blocks of PB = 4 PT rows (64 with 256 threads); the staged nodes (nbt, as many as fit: the
-	// overlap list is walked once per RPA phase) and one block of the Gram matrix share the shared memory. Two CTAs per SM where 32
-	// staged nodes still fit. Environment overrides: PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_MINBLOCKS, PFFRG_GRAM_TM.
-	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax)
+	// tiles of the busiest warp when nw warps share the rt x ct 8x8 tiles of a Gram block (gramcfg::bestRowWarps, pffrg_kernels.cuh)
+	int gramBusiestTiles(int rt, int ct, int nw)
+	{
+		int best = 1 << 30;
+		for (int wp = 1; wp <= nw; ++wp) if (nw % wp == 0) best = std::min(best, ((rt + wp - 1) / wp) * ((ct + nw / wp - 1) / (nw / wp)));
+		return best;
+	}
+
+	// Launch shape of the kernel with the Gram form of the RPA phase (rpaGram, pffrg_kernels.cuh): the staged nodes (nbt, as many as fit:
+	// the overlap list is walked once per RPA phase) and one block of PB rows of the Gram matrix (a multiple of 8, at most 64, at most 16
+	// accumulator tiles per warp) share the shared memory. Two CTAs per SM where 32 staged nodes still fit. Environment overrides:
+	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_MINBLOCKS, PFFRG_GRAM_PB.
+	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs)
 	{
 		JitShape best = { 0, 0, 0, 0, 0 };
-		const int gemmThreads = threads / 64 * 64;
-		if (gemmThreads < 64) return best;
-		const int PT = gemmThreads / 16;
-		const int TN = (Lp + 15) / 16;
-		int TM = std::max(1, std::min(4, 64 / PT));
-		TM = std::max(1, std::min(TM, 28 / TN)); // accumulators per thread: 2 TM TN doubles, kept within the register file
-		if (const char *e = getenv("PFFRG_GRAM_TM")) TM = std::min(8, std::max(1, atoi(e)));
-		TM = std::min(TM, (Lp + PT - 1) / PT);
-		const int PB = PT * TM;
-		const int bits = 14; // a term word addresses the Gram block with 14 bits
-		if (PB * Lp > (1 << bits)) return best;
-		const size_t half = (smemMax + 1024) / 2 - 1024;
-		int forcedNb = 0, forcedNbt = 0, forcedCtas = 0;
+		const int gemmThreads = threads / 32 * 32, warps = gemmThreads / 32, ct = (Lp + 7) / 8;
+		if (warps < 1) return best;
+		int forcedNb = 0, forcedNbt = 0, forcedCtas = 0, forcedPb = 0;
 		if (const char *e = getenv("PFFRG_JIT_NB")) forcedNb = atoi(e);
 		if (const char *e = getenv("PFFRG_JIT_NBT")) forcedNbt = atoi(e);
 		if (const char *e = getenv("PFFRG_JIT_MINBLOCKS")) forcedCtas = std::max(1, atoi(e));
+		if (const char *e = getenv("PFFRG_GRAM_PB")) forcedPb = std::max(8, atoi(e) / 8 * 8);
+		const int pbMax = std::min(64, (Lp + 7) / 8 * 8);
 		const int nbts[] = { 64, 48, 32, 24, 16, 8 };
-		for (int pass = 0; pass < 2 && !best.nb; ++pass)
+		// Every shape that fits is rated with a coarse model of what the choice costs per work item (clocks; ~64 t-channel nodes per item):
+		// every RPA phase walks the term array once (~200 clocks per chunk of 256 words and warp) and pays two barriers and a store of the
+		// block per row block (~1500 clocks); small gather batches cost gather throughput (measured: pyrochlore-r8 +15 % with batches of 8).
+		double bestCost = 0.0;
+		for (int ctas = 2; ctas >= 1; --ctas)
 		{
-			const int ctas = forcedCtas ? forcedCtas : 2 - pass;
+			if (forcedCtas && ctas != forcedCtas) continue;
 			if (!forcedCtas && ctas == 2 && threads > 256) continue; // the block update needs more than 64 registers per thread
 			const size_t budget = ctas >= 2 ? (smemMax + 1024) / ctas - 1024 : smemMax;
 			for (int nbt : nbts)
@@ -273,14 +277,23 @@ namespace
 				if (forcedNbt ? nbt != forcedNbt : (ctas == 2 && nbt < 32)) continue;
 				for (int nb : { 16, 8 })
 				{
-					if (best.nb || nbt % nb || (forcedNb && nb != forcedNb)) continue;
-					const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, PB);
-					if (smem <= budget) { best = { nb, nbt, threads / 32, ctas, smem }; best.gramRows = PB; best.gramThreads = gemmThreads; best.gramOffsetBits = bits; }
+					if (nbt % nb || (forcedNb && nb != forcedNb)) continue;
+					for (int pb = pbMax; pb >= 8; pb -= 8)
+					{
+						if (forcedPb && pb != std::min(forcedPb, pbMax)) continue;
+						if ((long)pb * (Lp + 1) > (1l << 14)) continue;           // a term word addresses the Gram block with 14 bits
+						const int blocks = (Lp + pb - 1) / pb, lastRt = (Lp - (blocks - 1) * pb + 7) / 8;
+						if (gramBusiestTiles(pb / 8, ct, warps) > 16 || gramBusiestTiles(lastRt, ct, warps) > 16) continue;
+						const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, pb);
+						if (smem > budget) continue;
+						const double phases = (64 + nbt - 1) / nbt;
+						double cost = phases * (1.06 * (double)uniquePairs / 256.0 / warps * 200.0 + blocks * 1500.0) + (nb == 8 ? 15000.0 : 0.0);
+						if (ctas == 2) cost *= 0.8; // two resident CTAs overlap their phases
+						if (!best.nb || cost < bestCost) { best = { nb, nbt, threads / 32, ctas, smem }; best.gramRows = pb; best.gramThreads = gemmThreads; bestCost = cost; }
+					}
 				}
 			}
-			if (forcedCtas) break;
 		}
-		(void)half;
 		return best;
 	}
 
@@ -331,6 +344,7 @@ namespace
 	cudaError_t launchFlow(pffrg_context *h, int64_t begin, int64_t count)
 	{
 		auto kernel = v4FlowKernel<CORE, NB>;
+		if (h->threads > 256) return cudaErrorInvalidConfiguration; // __launch_bounds__(256) of the precompiled kernels
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes);
 		if (e != cudaSuccess) return e;
 		FlowConfig cfg; cfg.groups = h->groups; cfg.stride = h->stride; cfg.nslots = h->nslots; cfg.smemBytes = (int)h->smemBytes; cfg.items = (int)count; cfg.order = 0;
@@ -343,13 +357,13 @@ namespace
 	// threads of a CTA: `groups` groups of `stride` threads, one group per quadrature node at a time (used by pffrg_create and
 	// by the device-less pffrg_jit_compile_check, which must arrive at the same kernel)
 	struct LaunchGeometry { int stride, groups, threads; };
-	LaunchGeometry chooseGeometry(int L)
+	LaunchGeometry chooseGeometry(int L, bool runtimeCompiled)
 	{
 		LaunchGeometry g;
 		const int padded = (L + 31) / 32 * 32;
 		g.stride = (padded - L) * 4 <= padded ? padded : L;
 		if (const char *e = getenv("PFFRG_PAD_GROUPS")) g.stride = atoi(e) ? padded : L; // tuning override
-		int threadTarget = 256; // PFFRG_THREADS: tuning override (values above 256 only work with the run-time compiled kernel)
+		int threadTarget = (runtimeCompiled && g.stride > 128) ? 384 : 256; // two groups (nodes in flight) also for L > 128; PFFRG_THREADS: tuning override (values above 256 only work with the run-time compiled kernel)
 		if (const char *e = getenv("PFFRG_THREADS")) threadTarget = std::min(1024, std::max(64, atoi(e)));
 		g.groups = std::max(1, threadTarget / g.stride);
 		g.threads = std::max(64, (g.groups * g.stride + 31) / 32 * 32);
@@ -497,7 +511,7 @@ namespace
 			const char *form = getenv("PFFRG_RPA");
 			if (wantGram(h->core, h->uniquePairs))
 			{
-				JitShape shape = chooseGramShape(h->nw, h->L, h->Lp, h->groups, h->threads, smemMax);
+				JitShape shape = chooseGramShape(h->nw, h->L, h->Lp, h->groups, h->threads, smemMax, h->uniquePairs);
 				if (!shape.nb) return form ? fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_RPA=gram: no launch shape fits (threads %d, L %d)", h->threads, h->L) : PFFRG_OK;
 				JitCandidate c = { h->threads, h->groups, shape, nullptr, nullptr, 0.f };
 				const int rc = compileCandidate(h, d, c);
@@ -782,7 +796,7 @@ namespace
 				{
 					const int p = std::get<0>(kv.first), q = std::get<3>(kv.first);
 					if (p / PB != blk) continue;
-					const unsigned offset = (unsigned)((p - blk * PB) * Lp + q);
+					const unsigned offset = (unsigned)((p - blk * PB) * (Lp + 1) + q); // row stride of the Gram block: gramcfg::LpG
 					for (int m = kv.second; m > 0; m -= maxMult) { byClass[rid][offset & 7u].push_back(offset | ((unsigned)rid << 14) | ((unsigned)std::min(m, maxMult) << 22)); ++n; }
 				}
 				padded[rid] = (n + 7) / 8 * 8;
@@ -815,7 +829,7 @@ namespace
 						{
 							// padding word: multiplicity 0, a free bank class
 							int c = 0; while (c < 7 && (mask & (1u << c))) ++c;
-							terms.push_back((unsigned)((c < PB * Lp) ? c : 0) | ((unsigned)rid << 14));
+							terms.push_back((unsigned)c | ((unsigned)rid << 14)); // (offsets 0..7 exist: a block has at least 8 rows)
 							mask |= 1u << c;
 						}
 					}
@@ -1222,7 +1236,8 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	// launch configuration: k groups of L threads; batch width NB chosen so that at least two CTAs fit per SM
 	// a group of threads covers the L sites of one quadrature node; groups are padded to whole warps when that idles at
 	// most a quarter of the lanes (then every warp gathers from one node only: fewer cache lines per load, uniform table reads)
-	const LaunchGeometry geo = chooseGeometry(L);
+	const char *jitEnv = getenv("PFFRG_JIT");
+	const LaunchGeometry geo = chooseGeometry(L, d->core == SU2 && !(jitEnv && atoi(jitEnv) == 0));
 	h->stride = geo.stride; h->groups = geo.groups; h->threads = geo.threads;
 	// SU2/XYZ: two CTAs per SM (100 KB each); the TRI core stages four 16-channel RPA operand buffers and runs one CTA per SM
 	h->nb = 32;
@@ -1628,14 +1643,15 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	if (!d || d->n_sites < 1 || d->n_sites > 256 || d->core < 0 || d->core > 1 || !d->overlap_offsets) return fail(PFFRG_ERR_ARGUMENT, "bad descriptor");
 	// same launch configuration as pffrg_create
 	const int L = d->n_sites;
-	const LaunchGeometry geo = chooseGeometry(L);
+	const char *jitEnv = getenv("PFFRG_JIT");
+	const LaunchGeometry geo = chooseGeometry(L, d->core == SU2 && !(jitEnv && atoi(jitEnv) == 0));
 	const int groups = geo.groups, threads = geo.threads;
 	int64_t uniquePairs = 0;
 	for (int rid = 0; rid < L; ++rid) uniquePairs += (int64_t)mergedOverlap(d, d->core, rid).size();
 	if (wantGram(d->core, uniquePairs))
 	{
 		const int Lp = paddedSites(L);
-		const JitShape g = chooseGramShape(d->n_frequencies, L, Lp, groups, threads, 227 * 1024);
+		const JitShape g = chooseGramShape(d->n_frequencies, L, Lp, groups, threads, 227 * 1024, uniquePairs);
 		if (!g.nb) return fail(PFFRG_ERR_UNSUPPORTED, "no launch shape for the Gram form of the RPA phase");
 		std::vector<char> cubin;
 		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g));
@@ -1739,7 +1755,7 @@ int pffrg_gram_tables(const pffrg_desc *d, int rowsPerBlock, int warps, uint32_t
 {
 	if (!d || d->n_sites < 1 || d->n_sites > 256 || !d->overlap_offsets || rowsPerBlock < 1 || warps < 1 || warps > 32 || !seg || (!terms && capacity > 0)) return fail(PFFRG_ERR_ARGUMENT, "bad argument");
 	const int L = d->n_sites, Lp = paddedSites(L);
-	if ((long)rowsPerBlock * Lp > (1l << 14)) return fail(PFFRG_ERR_ARGUMENT, "%d rows of %d do not fit the 14 offset bits of a term word", rowsPerBlock, Lp);
+	if ((long)rowsPerBlock * (Lp + 1) > (1l << 14) || rowsPerBlock % 8) return fail(PFFRG_ERR_ARGUMENT, "%d rows of %d do not fit the 14 offset bits of a term word (or not a multiple of 8)", rowsPerBlock, Lp + 1);
 	std::vector<unsigned> t; std::vector<int> s;
 	buildGramTables(d, L, Lp, rowsPerBlock, warps, t, s, conflictDegree);
 	std::copy(s.begin(), s.end(), seg);

@@ -350,7 +350,7 @@ namespace pffrg
 			o = alignUp(o, 16);
 			privateBytes = o; o *= subs;
 			// the per-group partial sums of the epilogue reuse the staging area (dead by then)
-			const size_t stBytes = gramRows > 0 ? sizeof(double) * 2 * C * Lp * (subs * nbt)
+			const size_t stBytes = gramRows > 0 ? sizeof(double) * 2 * C * (Lp + 2) * (subs * nbt)
 			                     : (CORE == TRI && NB == 8) ? sizeof(double) * 4 * tri8BufferStride(L) : sizeof(double) * RpaStage<CORE>::buffers * C * L * (subs * nbt + 1);
 			partStride = sizeof(double) * groups * C * L;
 			const size_t partBytes = partStride * subs;
@@ -361,7 +361,7 @@ namespace pffrg
 			rpa = o; o += sizeof(double) * C * L * rpaCopies;
 			staged = o; if (subs > 1) o += sizeof(int) * 4; // nodes staged by each sub-CTA for the coming RPA phase
 			o = alignUp(o, 16);
-			gram = o; o += sizeof(double) * C * (size_t)gramRows * Lp;
+			gram = o; o += gramRows > 0 ? sizeof(double) * C * (size_t)gramRows * (Lp + 1) : 0; // strides: gramcfg::LpS, gramcfg::LpG
 			total = alignUp(o, 16);
 		}
 	};
@@ -1121,66 +1121,114 @@ namespace pffrg
 	// pyrochlore-r8, 961 instead of 3 453 at cubic-r7) and the overlap list is walked once per RPA phase instead of once per node.
 	// No generated code: nothing to stream through the instruction caches, no limit on the lattice size.
 	//
-	//  - GEMM: the operands of the staged nodes lie node-major, st[buffer][node][Lp] of double2 {spin, density}. Threads form a
-	//    PT x 16 grid (a warp = 4 x 8); thread (tp, tq) accumulates G[rowBase + tp + PT i][tq + 16 j], i < TM, j < TN, for both
-	//    channels in registers: per node TM + TN 16-byte shared loads (contiguous across the lanes, broadcast across the other
-	//    lane index) feed 2 TM TN FP64 multiply-adds.
-	//  - The rows are worked off in blocks of PB = PT * TM rows: the block is written to shared memory (Gs[row][q] of double2) and
+	//  - Block update: the operands of the staged nodes lie node-major, st[buffer][node][LpS] of double2 {spin, density}; the update runs on
+	//    the FP64 tensor cores (gramBlock below).
+	//  - The rows are worked off in blocks of PB rows: the block is written to shared memory (Gs[row][q] of double2, row stride LpG) and
 	//    reduced at once (gramReduce below): every warp owns a contiguous range of whole rid lists of the block's term array.
 	// ================================================================================================================
 	namespace gramcfg
 	{
 		constexpr int Lp = PFFRG_CONST_LP;
-		constexpr int NT = PFFRG_GRAM_THREADS;         // threads taking part in the GEMM (a multiple of 64)
-		constexpr int PT = NT / 16;                    // thread rows
-		constexpr int TM = PFFRG_GRAM_PB / PT;         // rows per thread in a full block
-		constexpr int PB = PFFRG_GRAM_PB;              // rows per block
-		constexpr int TN = (Lp + 15) / 16;             // columns per thread
+		constexpr int LpS = Lp + 2;                    // node stride of the staged operands in double2: = 2 mod 4, so the 4 nodes x 2 sites of a quarter
+		                                               // warp's fragment load fall into 8 different 16-byte bank groups
+		constexpr int LpG = Lp + 1;                    // row stride of the Gram block in double2 (odd: the accumulator stores of a quarter warp -- 2 rows x
+		                                               // 4 column pairs -- are conflict free)
+		constexpr int NT = PFFRG_GRAM_THREADS;         // threads taking part in the block update (whole warps)
+		constexpr int NW = NT / 32;
+		constexpr int PB = PFFRG_GRAM_PB;              // rows per block (a multiple of 8)
 		constexpr int NBLK = (Lp + PB - 1) / PB;
 		constexpr int LAST_ROWS = Lp - (NBLK - 1) * PB;
-		constexpr int TM_LAST = (LAST_ROWS + PT - 1) / PT;
-		static_assert(NT % 64 == 0 && PB % PT == 0 && TM >= 1 && PB * Lp <= (1 << 14), "Gram geometry");
+		constexpr int CT = (Lp + 7) / 8;               // 8-column tiles
+		static_assert(NT % 32 == 0 && NW >= 1 && PB % 8 == 0 && PB * LpG <= (1 << 14), "Gram geometry");
+
+		// the NW warps as a WP x WQ grid over the RT x CT tiles of a block: the split with the fewest tiles on the busiest warp
+		constexpr int tilesOfBusiest(int rt, int wp) { return ((rt + wp - 1) / wp) * ((CT + NW / wp - 1) / (NW / wp)); }
+		constexpr int bestRowWarps(int rt)
+		{
+			int best = 1;
+			for (int wp = 1; wp <= NW; ++wp)
+			{
+				if (NW % wp) continue;
+				const int t = tilesOfBusiest(rt, wp), tb = tilesOfBusiest(rt, best);
+				const int loads = (rt + wp - 1) / wp + (CT + NW / wp - 1) / (NW / wp), loadsBest = (rt + best - 1) / best + (CT + NW / best - 1) / (NW / best);
+				if (t < tb || (t == tb && loads < loadsBest)) best = wp;
+			}
+			return best;
+		}
 	}
 
-	template <int TMB>
-	__device__ __forceinline__ void gramBlock(const double2 *__restrict__ stA, const double2 *__restrict__ stB, int nb, int rowBase, int rows, double2 *__restrict__ Gs, int tp, int tq)
+	// D (8x8) += A (8x4, row major) B (4x8, column major) on the FP64 tensor cores. Fragments (PTX ISA, mma.m8n8k4 .f64): lane l holds
+	// A[l / 4][l % 4], B[l % 4][l / 4] and D[l / 4][2 (l % 4) + {0, 1}].
+	__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+	{
+		asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+	}
+
+	// One block of RT row tiles of the Gram matrix, both channels: G_c[p][q] = sum_k A_c,k[p] B_c,k[q] as m8n8k4 tensor-core updates with
+	// M = representative site p, N = representative site q, K = staged node. Warp (wp, wq) owns the tiles (wp MI + mi, wq + WQ ni): per
+	// step of four nodes it loads MI + NI fragments (16 bytes per lane = the operand of both channels; a quarter warp reads 4 nodes x 2
+	// sites from 8 different bank groups) for 2 MI NI updates of 256 multiply-adds each -- the register-tiled FP64 FMA form of this
+	// update moved 4 x more shared-memory wavefronts and was bound by them (ncu: 4 wavefronts per 16-byte load, whatever the lanes share).
+	template <int RT>
+	__device__ __forceinline__ void gramBlock(const double2 *__restrict__ stA, const double2 *__restrict__ stB, int nb, int rowBase, double2 *__restrict__ Gs, int warp, int lane)
 	{
 		using namespace gramcfg;
-		double2 acc[TMB][TN];
-		int pa[TMB], qb[TN];
+		constexpr int WP = bestRowWarps(RT), WQ = NW / WP;
+		constexpr int MI = (RT + WP - 1) / WP, NI = (CT + WQ - 1) / WQ;
+		static_assert(MI * NI <= 16, "accumulator tiles per warp");
+		const int wp = warp / WQ, wq = warp - wp * WQ;
+		const int fr = lane >> 2, fk = lane & 3; // fragment row (site within the tile), fragment k (node within the step)
+		double acc[MI][NI][2][2];
 		#pragma unroll
-		for (int i = 0; i < TMB; ++i) pa[i] = min(rowBase + tp + PT * i, Lp - 1); // rows / columns past the end repeat the last one (never stored)
-		#pragma unroll
-		for (int j = 0; j < TN; ++j) qb[j] = min(tq + 16 * j, Lp - 1);
-		#pragma unroll
-		for (int i = 0; i < TMB; ++i)
+		for (int i = 0; i < MI; ++i)
 		{
 			#pragma unroll
-			for (int j = 0; j < TN; ++j) acc[i][j] = make_double2(0.0, 0.0);
+			for (int j = 0; j < NI; ++j) { acc[i][j][0][0] = 0.0; acc[i][j][0][1] = 0.0; acc[i][j][1][0] = 0.0; acc[i][j][1][1] = 0.0; }
 		}
-		#pragma unroll 2
-		for (int k = 0; k < nb; ++k)
+		// sites past the end of the lattice repeat the last one (their rows / columns are never stored)
+		int pa[MI], qb[NI];
+		#pragma unroll
+		for (int i = 0; i < MI; ++i) pa[i] = min(rowBase + 8 * (wp * MI + i) + fr, Lp - 1);
+		#pragma unroll
+		for (int j = 0; j < NI; ++j) qb[j] = min(8 * (wq + WQ * j) + fr, Lp - 1);
+		#pragma unroll 1
+		for (int k0 = 0; k0 < nb; k0 += 4)
 		{
-			const double2 *A = stA + k * Lp, *B = stB + k * Lp;
-			double2 a[TMB], b[TN];
+			const bool live = k0 + fk < nb; // the last step of a phase may hold fewer than four nodes
+			const double2 *A = stA + (k0 + fk) * LpS, *B = stB + (k0 + fk) * LpS;
+			double2 a[MI], b[NI];
 			#pragma unroll
-			for (int i = 0; i < TMB; ++i) a[i] = A[pa[i]];
+			for (int i = 0; i < MI; ++i) a[i] = live ? A[pa[i]] : make_double2(0.0, 0.0);
 			#pragma unroll
-			for (int j = 0; j < TN; ++j) b[j] = B[qb[j]];
+			for (int j = 0; j < NI; ++j) b[j] = live ? B[qb[j]] : make_double2(0.0, 0.0);
 			#pragma unroll
-			for (int i = 0; i < TMB; ++i)
+			for (int i = 0; i < MI; ++i)
 			{
+				if (wp * MI + i >= RT) continue; // warp-uniform
 				#pragma unroll
-				for (int j = 0; j < TN; ++j) { acc[i][j].x = fma(a[i].x, b[j].x, acc[i][j].x); acc[i][j].y = fma(a[i].y, b[j].y, acc[i][j].y); }
+				for (int j = 0; j < NI; ++j)
+				{
+					if (wq + WQ * j >= CT) continue;
+					dmma884(acc[i][j][0][0], acc[i][j][0][1], a[i].x, b[j].x);
+					dmma884(acc[i][j][1][0], acc[i][j][1][1], a[i].y, b[j].y);
+				}
 			}
 		}
 		__syncthreads(); // the reduction of the previous block has read Gs
 		#pragma unroll
-		for (int i = 0; i < TMB; ++i)
+		for (int i = 0; i < MI; ++i)
 		{
-			if (tp + PT * i >= rows) continue;
+			if (wp * MI + i >= RT) continue;
+			const int row = 8 * (wp * MI + i) + fr; // within the block
+			if (rowBase + row >= Lp) continue;
 			#pragma unroll
-			for (int j = 0; j < TN; ++j) if (tq + 16 * j < Lp) Gs[(tp + PT * i) * Lp + tq + 16 * j] = acc[i][j];
+			for (int j = 0; j < NI; ++j)
+			{
+				if (wq + WQ * j >= CT) continue;
+				const int col = 8 * (wq + WQ * j) + 2 * fk;
+				if (col < Lp) Gs[row * LpG + col] = make_double2(acc[i][j][0][0], acc[i][j][1][0]);
+				if (col + 1 < Lp) Gs[row * LpG + col + 1] = make_double2(acc[i][j][0][1], acc[i][j][1][1]);
+			}
 		}
 	}
 
@@ -1199,30 +1247,56 @@ namespace pffrg
 		const int chunks = (range.y - range.x) >> 8;
 		if (chunks <= 0) return;
 		const uint4 *words = reinterpret_cast<const uint4 *>(P.gram_terms + range.x) + 2 * lane;
-		uint4 n0 = __ldg(words), n1 = __ldg(words + 1);
+		// two chunks per iteration: two independent dependency chains (products, scan) in flight
+		uint4 n[2][2];
+		#pragma unroll
+		for (int u = 0; u < 2; ++u) if (u < chunks) { n[u][0] = __ldg(words + 64 * u); n[u][1] = __ldg(words + 64 * u + 1); }
 		#pragma unroll 1
-		for (int c = 0; c < chunks; ++c)
+		for (int c = 0; c < chunks; c += 2)
 		{
-			const uint4 w0 = n0, w1 = n1;
-			if (c + 1 < chunks) { n0 = __ldg(words + 64 * (c + 1)); n1 = __ldg(words + 64 * (c + 1) + 1); }
-			const unsigned w[8] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
-			const int rid = (int)((w[0] >> 14) & 255u);
-			double2 g[8];
+			int rid[2]; double sx[2], sy[2];
+			const bool second = c + 1 < chunks;
+			uint4 w4[2][2];
 			#pragma unroll
-			for (int k = 0; k < 8; ++k) g[k] = Gs[w[k] & GRAM_OFFSET_MASK];
-			double sx = 0.0, sy = 0.0;
+			for (int u = 0; u < 2; ++u) { w4[u][0] = n[u][0]; w4[u][1] = n[u][1]; }
 			#pragma unroll
-			for (int k = 0; k < 8; ++k) { const double m = (double)(int)(w[k] >> 22); sx = fma(m, g[k].x, sx); sy = fma(m, g[k].y, sy); }
+			for (int u = 0; u < 2; ++u) if (c + 2 + u < chunks) { n[u][0] = __ldg(words + 64 * (c + 2 + u)); n[u][1] = __ldg(words + 64 * (c + 2 + u) + 1); }
+			#pragma unroll
+			for (int u = 0; u < 2; ++u)
+			{
+				const unsigned w[8] = { w4[u][0].x, w4[u][0].y, w4[u][0].z, w4[u][0].w, w4[u][1].x, w4[u][1].y, w4[u][1].z, w4[u][1].w };
+				rid[u] = (int)((w[0] >> 14) & 255u);
+				double2 g[8];
+				#pragma unroll
+				for (int k = 0; k < 8; ++k) g[k] = Gs[(u == 0 || second) ? (w[k] & GRAM_OFFSET_MASK) : 0u];
+				double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0; // two partial chains per channel
+				#pragma unroll
+				for (int k = 0; k < 8; k += 2)
+				{
+					const double m0 = (double)(int)(w[k] >> 22), m1 = (double)(int)(w[k + 1] >> 22);
+					ax = fma(m0, g[k].x, ax); ay = fma(m0, g[k].y, ay);
+					bx = fma(m1, g[k + 1].x, bx); by = fma(m1, g[k + 1].y, by);
+				}
+				sx[u] = ax + bx; sy[u] = ay + by;
+			}
 			#pragma unroll
 			for (int d = 1; d < 32; d <<= 1)
 			{
-				const double ox = __shfl_up_sync(0xffffffffu, sx, d), oy = __shfl_up_sync(0xffffffffu, sy, d);
-				const int orid = __shfl_up_sync(0xffffffffu, rid, d);
-				if (lane >= d && orid == rid) { sx += ox; sy += oy; }
+				#pragma unroll
+				for (int u = 0; u < 2; ++u)
+				{
+					const double ox = __shfl_up_sync(0xffffffffu, sx[u], d), oy = __shfl_up_sync(0xffffffffu, sy[u], d);
+					const int orid = __shfl_up_sync(0xffffffffu, rid[u], d);
+					if (lane >= d && orid == rid[u]) { sx[u] += ox; sy[u] += oy; }
+				}
 			}
-			const int nextRid = __shfl_down_sync(0xffffffffu, rid, 1);
-			if (lane == 31 || nextRid != rid) { rpaOut[rid] += sx; rpaOut[L + rid] += sy; }
-			__syncwarp(); // the next chunk of this warp may continue the same rid
+			#pragma unroll
+			for (int u = 0; u < 2; ++u)
+			{
+				const int nextRid = __shfl_down_sync(0xffffffffu, rid[u], 1);
+				if ((u == 0 || second) && (lane == 31 || nextRid != rid[u])) { rpaOut[rid[u]] += sx[u]; rpaOut[L + rid[u]] += sy[u]; }
+				__syncwarp(); // the next chunk of this warp may continue the same rid
+			}
 		}
 	}
 
@@ -1231,17 +1305,16 @@ namespace pffrg
 	{
 		using namespace gramcfg;
 		const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = blockDim.x >> 5;
-		const int tp = (warp >> 1) * 4 + (lane >> 3), tq = (warp & 1) * 8 + (lane & 7);
 		const bool gemm = tid < NT;
-		const double2 *stA = st2, *stB = st2 + (size_t)nodeCapacity * Lp;
+		const double2 *stA = st2, *stB = st2 + (size_t)nodeCapacity * LpS;
 		#pragma unroll 1
 		for (int blk = 0; blk < NBLK - 1; ++blk)
 		{
-			if (gemm) gramBlock<TM>(stA, stB, nb, blk * PB, PB, Gs, tp, tq); else __syncthreads();
+			if (gemm) gramBlock<PB / 8>(stA, stB, nb, blk * PB, Gs, warp, lane); else __syncthreads();
 			__syncthreads();
 			gramReduce(P, blk, Gs, rpaOut, warp, lane, warps);
 		}
-		if (gemm) gramBlock<TM_LAST>(stA, stB, nb, (NBLK - 1) * PB, LAST_ROWS, Gs, tp, tq); else __syncthreads();
+		if (gemm) gramBlock<(LAST_ROWS + 7) / 8>(stA, stB, nb, (NBLK - 1) * PB, Gs, warp, lane); else __syncthreads();
 		__syncthreads();
 		gramReduce(P, NBLK - 1, Gs, rpaOut, warp, lane, warps);
 	}
@@ -1291,9 +1364,8 @@ namespace pffrg
 		for (int i = threadIdx.x; i < lay.rpaCopies * C * L; i += blockDim.x) rpaOut[i] = 0.0;
 #ifdef PFFRG_GRAM
 		// padding sites of the node-major staging rows: read by the Gram update (their products are never used), never written below
-		if (gramcfg::Lp > L)
-			for (int i = threadIdx.x; i < 2 * NBTT * (gramcfg::Lp - L); i += blockDim.x)
-				reinterpret_cast<double2 *>(st)[(i / (gramcfg::Lp - L)) * gramcfg::Lp + L + i % (gramcfg::Lp - L)] = make_double2(0.0, 0.0);
+		for (int i = threadIdx.x; i < 2 * NBTT * (gramcfg::LpS - L); i += blockDim.x)
+			reinterpret_cast<double2 *>(st)[(i / (gramcfg::LpS - L)) * gramcfg::LpS + L + i % (gramcfg::LpS - L)] = make_double2(0.0, 0.0);
 #endif
 
 		// work item -> (s, t, u), expandIterator SU2VertexTwoParticle.hpp:136-158
@@ -1463,10 +1535,10 @@ namespace pffrg
 							}
 							if (GRAM)
 							{
-								// node-major channel pairs: st2[buffer][node][Lp]
+								// node-major channel pairs: st2[buffer][node][LpS], LpS = Lp + 2 (gramcfg)
 								double2 *st2 = reinterpret_cast<double2 *>(st);
-								st2[(stageOff + node) * sizeLp(P) + j] = make_double2(opA[0], opA[1]);
-								st2[(NBTT + stageOff + node) * sizeLp(P) + j] = make_double2(opB[0], opB[1]);
+								st2[(stageOff + node) * (sizeLp(P) + 2) + j] = make_double2(opA[0], opA[1]);
+								st2[(NBTT + stageOff + node) * (sizeLp(P) + 2) + j] = make_double2(opB[0], opB[1]);
 							}
 							else if (JIT)
 							{
@@ -1658,7 +1730,7 @@ namespace pffrg
 	}
 
 	// FP64 tensor-core throughput probe (pffrg_dmma_peak): 8 independent accumulator tiles per warp, nothing but DMMA m8n8k4 in the loop
-	__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
+	__device__ __forceinline__ void dmmaProbe(double (&c)[2], double a, double b)
 	{
 		asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 	}
@@ -1670,7 +1742,7 @@ namespace pffrg
 		for (int it = 0; it < iterations; ++it)
 		{
 			#pragma unroll
-			for (int i = 0; i < 8; ++i) dmma884(c[i], a, b);
+			for (int i = 0; i < 8; ++i) dmmaProbe(c[i], a, b);
 		}
 		double s = 0.0;
 		#pragma unroll

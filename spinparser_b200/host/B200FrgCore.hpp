@@ -15,21 +15,35 @@
 //                   host -- the load-managed measurement stacks exactly like src/SU2/SU2FrgCore.cpp:96-108 does;
 //                   _flow receives the self-energy flow and the divergence signal (NaN), and the full vertex flow
 //                   when syncFlow is set.
-//   finalizeStep()  Euler update on the GPU (state stays resident in FP64), then the updated state is copied back into
-//                   the reference's arrays (page-locked in place) unless syncState is off.
+//   finalizeStep()  Euler update on the GPU (state stays resident in FP64). The reference's host arrays (page-locked in place) are
+//                   refreshed only when somebody is about to read them (syncState=lazy, the default): host-side measurements and the
+//                   deferred-measurement dump of FrgCore::takeMeasurements (src/FrgCore.hpp:36-68), the periodic and the final
+//                   checkpoint of SpinParser::runCore (src/SpinParser.cpp:163-183), a diverged flow. syncState=always copies after
+//                   every step. The host cutoff is always advanced (the driver loop reads it).
+//
+// Several GPUs: one process per GPU, as the reference runs one MPI rank per node. In an MPI build the ranks are the MPI ranks
+// (the NCCL id travels by MPI_Bcast); without MPI the ranks are given by the environment (PFFRG_RANK, PFFRG_NRANKS, PFFRG_ID_FILE:
+// rank 0 writes the id to that file, the others wait for it). Every rank runs the host program; the work items of every step are
+// sharded and the updated slices exchanged over NVLink inside pffrg_finalize_step.
 //
 // The real type of the host arrays is `float` as in the reference; a build that redefines float as double (the FP64
 // parity oracle of this repository) is handled by sizeof.
 #pragma once
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "pffrg.h"
+#ifndef DISABLE_MPI
+#include <mpi.h>
+#endif
 
 #include "FrgCommon.hpp"
 #include "SpinParser.hpp"
@@ -152,21 +166,27 @@ namespace b200
 	// src/SU2/SU2FrgCore.cpp:23-28)
 	struct AdapterOptions
 	{
-		int device = 0;
-		bool syncState = true;  // copy the updated state into the reference's host arrays after every finalizeStep
+		int device = -1;        // -1: the local rank of a multi-GPU run, else 0
+		bool syncState = false; // true ("always"): copy the updated state into the reference's host arrays after every finalizeStep;
+		                        // false ("lazy", default): only when the host arrays are about to be read
 		bool syncFlow = false;  // copy the full vertex flow into _flow after every computeStep
 		bool deviceMeasurement = true; // correlation measurements on the GPU (B200MeasurementCorrelation) instead of the reference's host code
 		static AdapterOptions extract(std::map<std::string, std::string> &options)
 		{
 			AdapterOptions a;
 			if (const char *e = getenv("SPINPARSER_B200_DEVICE")) a.device = atoi(e);
-			if (const char *e = getenv("SPINPARSER_B200_SYNC_STATE")) a.syncState = atoi(e) != 0;
+			auto always = [](const std::string &v) { return v == "true" || v == "1" || v == "always"; };
+			if (const char *e = getenv("SPINPARSER_B200_SYNC_STATE")) a.syncState = always(e);
 			if (const char *e = getenv("SPINPARSER_B200_SYNC_FLOW")) a.syncFlow = atoi(e) != 0;
 			if (const char *e = getenv("SPINPARSER_B200_MEASUREMENT")) a.deviceMeasurement = std::string(e) != "host";
 			auto take = [&](const char *key, std::string &out) { auto it = options.find(key); if (it == options.end()) return false; out = it->second; options.erase(it); return true; };
 			std::string v;
 			if (take("device", v)) a.device = std::stoi(v);
-			if (take("syncState", v)) a.syncState = (v == "true" || v == "1");
+			if (take("syncState", v))
+			{
+				if (!always(v) && v != "false" && v != "0" && v != "lazy") throw Exception(Exception::Type::InitializationError, "Unknown syncState policy '" + v + "'.");
+				a.syncState = always(v);
+			}
 			if (take("syncFlow", v)) a.syncFlow = (v == "true" || v == "1");
 			if (take("measurement", v))
 			{
@@ -179,6 +199,9 @@ namespace b200
 		static std::map<std::string, std::string> strip(std::map<std::string, std::string> options) { extract(options); return options; }
 	};
 
+	// measurements that read the DEVICE state (B200MeasurementCorrelation): the host arrays need not be refreshed for them
+	struct DeviceMeasurement { virtual ~DeviceMeasurement() {} };
+
 	template <class RefCore>
 	class B200FrgCore : public RefCore
 	{
@@ -188,9 +211,13 @@ namespace b200
 		{
 			std::map<std::string, std::string> copy = options;
 			_options = AdapterOptions::extract(copy);
+			int rank = 0, nRanks = 1;
+			rankLayout(rank, nRanks);
+			if (_options.device < 0) { const int devices = pffrg_device_count(); _options.device = devices > 0 ? rank % devices : 0; }
 			const ProblemTables tables;
 			const pffrg_desc desc = tables.descriptor(CoreTraits<RefCore>::id, CoreTraits<RefCore>::spinLength(*this), _options.device);
 			check(pffrg_create(&desc, &_handle), "pffrg_create");
+			if (nRanks > 1) joinRanks(rank, nRanks);
 			_state = CoreTraits<RefCore>::arrays(this->_flowingFunctional);
 			_flowArrays = CoreTraits<RefCore>::arrays(this->_flow);
 			if ((int64_t)_state.v4Size != pffrg_vertex_array_length(_handle) || _state.nArrays != pffrg_num_vertex_arrays(_handle))
@@ -209,27 +236,48 @@ namespace b200
 		void computeStep() override
 		{
 			this->_flow->cutoff = this->_flowingFunctional->cutoff;
-			// the host arrays are the truth whenever somebody else wrote them (construction, readCheckpoint): detected by the cutoff
-			if (!_deviceCurrent || !((double)this->_flowingFunctional->cutoff == _deviceCutoff)) uploadState();
+			// the host arrays are the truth whenever somebody else wrote them (construction, readCheckpoint): detected by the cutoff and
+			// by a fingerprint of the arrays taken when host and device were last known to agree
+			if (hostWasModified()) uploadState();
 
-			// load-managed measurements read the host state at this cutoff; they run on the host while the GPU computes the flow
+			// who reads the host arrays in the takeMeasurements() that follows this call (src/FrgCore.hpp:36-68)?
+			const bool deferAll = SpinParser::spinParser()->getCommandLineOptions()->deferMeasurements();
+			const float cutoff = this->_flowingFunctional->cutoff;
+			bool hostReaders = false;
 			std::vector<HMP::StackIdentifier> managed;
 			for (auto m : this->_measurements)
+			{
+				const bool inRange = cutoff <= m->maxCutoff() && cutoff >= m->minCutoff();
+				if (deferAll || m->isDeferred()) hostReaders = true; // the state is appended to the data file after every step
+				else if (inRange && !isDeviceMeasurement(m)) hostReaders = true;
 				if (m->isLoadManaged()) { auto s = m->getLoadManagedStacks(); managed.insert(managed.end(), s.begin(), s.end()); }
-			if (!managed.empty() && !_options.syncState) throw Exception(Exception::Type::InitializationError, "B200FrgCore: load-managed measurements need syncState");
+			}
+			if (hostReaders || !managed.empty()) ensureHostCurrent();
+
+			// load-managed measurements read the host state at this cutoff. Without MPI they run on a helper thread while the GPU computes
+			// the flow; in an MPI build LoadManager::calculate talks to the other ranks and must stay on the thread that initialised MPI
+			// (MPI_Init: thread level SINGLE, src/main.cpp:10), so it runs first.
 			std::exception_ptr measurementError;
 			std::thread measurementThread;
 			if (!managed.empty())
+			{
+#ifndef DISABLE_MPI
+				SpinParser::spinParser()->getLoadManager()->calculate(managed.data(), int(managed.size()));
+#else
 				measurementThread = std::thread([&] {
 					try { SpinParser::spinParser()->getLoadManager()->calculate(managed.data(), int(managed.size())); }
 					catch (...) { measurementError = std::current_exception(); }
 				});
+#endif
+			}
 
 			int diverged = 0;
 			const int rc = pffrg_compute_step(_handle, &diverged);
 			if (measurementThread.joinable()) measurementThread.join();
 			check(rc, "pffrg_compute_step");
 			if (measurementError) std::rethrow_exception(measurementError);
+			// a diverged flow ends the driver loop: the final measurements and the last checkpoint read the host arrays
+			if (diverged) ensureHostCurrent();
 
 			void *v4[4] = { _flowArrays.v4[0], _flowArrays.v4[1], _flowArrays.v4[2], _flowArrays.v4[3] };
 			check(pffrg_get_flow(_handle, _flowArrays.v2, _options.syncFlow ? v4 : nullptr, dtype()), "pffrg_get_flow");
@@ -242,24 +290,36 @@ namespace b200
 		{
 			check(pffrg_finalize_step(_handle, (double)newCutoff), "pffrg_finalize_step");
 			_deviceCutoff = (double)newCutoff;
-			if (_options.syncState) downloadState();
+			_hostCurrent = false;
 			this->_flowingFunctional->cutoff = newCutoff;
+			// who reads the host arrays before the next computeStep()? The checkpoint of the driver loop when it is due
+			// (src/SpinParser.cpp:163-168; two seconds of margin against the clock moving on between this test and the driver's), and
+			// after the last step the final measurements and the last checkpoint (:172-183).
+			const ComputationStatus status = SpinParser::spinParser()->getComputationStatus();
+			const bool checkpointDue = (Timestamp::time() - status.checkpointTime).total_seconds() + 2 > SpinParser::spinParser()->getCommandLineOptions()->checkpointTime();
+			const bool lastStep = newCutoff == *FrgCommon::cutoff().last();
+			if (_options.syncState || checkpointDue || lastStep) ensureHostCurrent();
 		}
 
-		// copy the device state into the reference's host arrays (needed before measurements / checkpoints when syncState is off)
+		// copy the device state into the reference's host arrays
 		void downloadState()
 		{
 			void *v4[4] = { _state.v4[0], _state.v4[1], _state.v4[2], _state.v4[3] };
 			double cutoff = 0.0;
 			check(pffrg_get_state(_handle, &cutoff, _state.v2, v4, dtype()), "pffrg_get_state");
+			_hostCurrent = true;
+			_hostFingerprint = fingerprint();
 		}
+		// ... unless they already hold the device state
+		void ensureHostCurrent() { if (_deviceCurrent && !_hostCurrent) downloadState(); }
+		bool hostIsCurrent() const { return _hostCurrent; }
 
 		// correlations chi[c * L + rid] of `state` (the flowing functional), computed on the device; uploads the state first when
 		// the host copy is the newer one (post-processing of deferred measurements reads checkpoints into the host arrays)
 		void measureCorrelation(const EffectiveAction &state, std::vector<double> &chi)
 		{
 			if (&state != this->_flowingFunctional) throw Exception(Exception::Type::ArgumentError, "B200FrgCore::measureCorrelation: only the flowing functional can be measured");
-			if (!_deviceCurrent || !((double)state.cutoff == _deviceCutoff)) uploadState();
+			if (hostWasModified()) uploadState();
 			chi.assign(size_t(pffrg_num_channels(_handle)) * FrgCommon::lattice().size, 0.0);
 			check(pffrg_measure_correlation(_handle, chi.data()), "pffrg_measure_correlation");
 		}
@@ -277,7 +337,74 @@ namespace b200
 			const void *v4[4] = { _state.v4[0], _state.v4[1], _state.v4[2], _state.v4[3] };
 			check(pffrg_set_state(_handle, (double)this->_flowingFunctional->cutoff, _state.v2, v4, dtype()), "pffrg_set_state");
 			_deviceCutoff = (double)this->_flowingFunctional->cutoff;
-			_deviceCurrent = true;
+			_deviceCurrent = true; _hostCurrent = true;
+			_hostFingerprint = fingerprint();
+		}
+
+		// Did anybody write the host arrays since host and device last agreed (construction, EffectiveAction::readCheckpoint -- also of a
+		// checkpoint at the very cutoff the device is at)? The cutoff and a fingerprint of the arrays decide: the whole self energy and
+		// a strided sample of every vertex array. While the host copy is merely stale (lazy synchronisation) nobody has written it, the
+		// fingerprint still matches, and the stale copy is NOT uploaded.
+		bool hostWasModified() const
+		{
+			if (!_deviceCurrent) return true;
+			if (!((double)this->_flowingFunctional->cutoff == _deviceCutoff)) return true;
+			return fingerprint() != _hostFingerprint;
+		}
+		unsigned long long fingerprint() const
+		{
+			unsigned long long hash = 1469598103934665603ull;
+			auto mix = [&](const real &x) { unsigned char b[sizeof(real)]; memcpy(b, &x, sizeof(real)); for (unsigned char c : b) { hash ^= c; hash *= 1099511628211ull; } };
+			for (int i = 0; i < _state.v2Size; ++i) mix(_state.v2[i]);
+			const size_t stride = _state.v4Size > 8192 ? _state.v4Size / 8192 : 1;
+			for (int c = 0; c < _state.nArrays; ++c) { for (size_t i = 0; i < _state.v4Size; i += stride) mix(_state.v4[c][i]); mix(_state.v4[c][_state.v4Size - 1]); }
+			return hash;
+		}
+
+		static bool isDeviceMeasurement(const Measurement *m) { return dynamic_cast<const DeviceMeasurement *>(m) != nullptr; }
+
+		// ranks of a multi-GPU run: the MPI ranks, or (no MPI) PFFRG_RANK / PFFRG_NRANKS
+		static void rankLayout(int &rank, int &nRanks)
+		{
+			rank = 0; nRanks = 1;
+#ifndef DISABLE_MPI
+			MPI_Comm_rank(MPI_COMM_WORLD, &rank); MPI_Comm_size(MPI_COMM_WORLD, &nRanks);
+#else
+			if (const char *e = getenv("PFFRG_NRANKS")) nRanks = std::max(1, atoi(e));
+			if (const char *e = getenv("PFFRG_RANK")) rank = atoi(e);
+			if (rank < 0 || rank >= nRanks) throw Exception(Exception::Type::InitializationError, "B200FrgCore: PFFRG_RANK outside [0, PFFRG_NRANKS)");
+#endif
+		}
+		// rank 0 creates the communicator id and ships it to the other ranks; then every rank joins (pffrg_comm_init)
+		void joinRanks(int rank, int nRanks)
+		{
+			unsigned char id[PFFRG_UNIQUE_ID_BYTES];
+			if (rank == 0) check(pffrg_comm_unique_id(id), "pffrg_comm_unique_id");
+#ifndef DISABLE_MPI
+			MPI_Bcast(id, PFFRG_UNIQUE_ID_BYTES, MPI_BYTE, 0, MPI_COMM_WORLD);
+#else
+			const char *path = getenv("PFFRG_ID_FILE");
+			if (!path) throw Exception(Exception::Type::InitializationError, "B200FrgCore: PFFRG_NRANKS > 1 needs PFFRG_ID_FILE (a path all ranks can reach)");
+			if (rank == 0)
+			{
+				const std::string tmp = std::string(path) + ".tmp";
+				FILE *f = fopen(tmp.c_str(), "wb");
+				if (!f || fwrite(id, 1, sizeof id, f) != sizeof id) throw Exception(Exception::Type::IOError, "B200FrgCore: cannot write " + tmp);
+				fclose(f);
+				if (rename(tmp.c_str(), path) != 0) throw Exception(Exception::Type::IOError, std::string("B200FrgCore: cannot create ") + path);
+			}
+			else
+			{
+				const auto t0 = std::chrono::steady_clock::now();
+				for (;;)
+				{
+					if (FILE *f = fopen(path, "rb")) { const size_t n = fread(id, 1, sizeof id, f); fclose(f); if (n == sizeof id) break; }
+					if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) throw Exception(Exception::Type::IOError, std::string("B200FrgCore: no communicator id appeared in ") + path);
+					std::this_thread::sleep_for(std::chrono::milliseconds(20));
+				}
+			}
+#endif
+			check(pffrg_comm_init(_handle, id, rank, nRanks), "pffrg_comm_init");
 		}
 
 		static void check(int rc, const char *what)
@@ -290,5 +417,7 @@ namespace b200
 		HostArrays _state, _flowArrays;
 		double _deviceCutoff;
 		bool _deviceCurrent;
+		bool _hostCurrent = true;                 // the host arrays hold the device state (or the device has none yet)
+		unsigned long long _hostFingerprint = 0;  // of the host arrays when host and device last agreed
 	};
 }

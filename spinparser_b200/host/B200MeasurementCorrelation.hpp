@@ -40,7 +40,7 @@ namespace b200
 	};
 
 	template <class RefCore>
-	class B200MeasurementCorrelation : public Measurement
+	class B200MeasurementCorrelation : public Measurement, public DeviceMeasurement
 	{
 	public:
 		B200MeasurementCorrelation(const std::string &outfile, const float minCutoff, const float maxCutoff, const bool defer)
