@@ -196,6 +196,12 @@ int pffrg_jit_compile_check(const pffrg_desc *desc, int64_t *cubin_bytes);
  * terms per buffer pair (256, or 64 for the RPA). Used by the parity tests to compare against the reference term by term. */
 int pffrg_tri_terms(int region, int32_t *terms, int capacity);
 
+/* Device-internal order of the representative sites: order[k] = the reference's site index stored at position k of the device
+ * layout. The two members of every pair {j, getInvertedSites()[j]} (src/Lattice.hpp:157-161) are neighbours, so that gathers with the
+ * site-exchange flag (src/SU2/SU2VertexTwoParticle.hpp:369-387) touch the same cache lines as plain ones; site 0 stays first. Returns 1
+ * if the order differs from the reference's, 0 if not. Host only; the order never shows at the boundary. */
+int pffrg_site_order(const pffrg_desc *desc, int32_t *order /* [n_sites] */);
+
 /* Term tables of the Gram form of the SU2 RPA lattice sum as the kernel walks them (rpaGram / gramReduce, pffrg_kernels.cuh): the sum
  * over the quadrature nodes of R[rid] = sum_i A[rid1_i] B[rid2_i] (Lattice::getOverlap(rid), src/Lattice.hpp:46-150, evaluated per node
  * at src/SU2/SU2FrgCore.cpp:250-266) is taken as sum_i G[rid1_i][rid2_i] over the Gram matrix G = sum_nodes A (x) B, rows worked off in

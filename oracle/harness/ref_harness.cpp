@@ -377,8 +377,10 @@ int SpinParser::run(int argc, char **argv)
 				if (first && wants(step)) dumpState(w, "step" + std::to_string(step) + "/flow", flow);
 				if (_frgCore->_flow->isDiverged()) { if (first) w.scalar("divergedAtStep", step); break; }
 				++cutoff; ++step; ++done;
+				// --resume-after: make the periodic checkpoint of the driver loop due after this step (the last one was "long ago")
+				if (first && done == opt.resumeAfter) _computationStatus.checkpointTime = Timestamp::time() + boost::posix_time::time_duration(-24 * 365 * 100, 0, 0, 0);
 				_frgCore->finalizeStep(*cutoff);
-				if (Timestamp::isOlder(_computationStatus.checkpointTime, _commandLineOptions->checkpointTime()) || (first && done == opt.resumeAfter))
+				if (Timestamp::isOlder(_computationStatus.checkpointTime, _commandLineOptions->checkpointTime()))
 				{
 					_computationStatus.checkpointTime = Timestamp::time();
 					_frgCore->_flowingFunctional->writeCheckpoint(_fileset.checkpointFile);

@@ -126,6 +126,8 @@ struct pffrg_context
 	DeviceArray<unsigned> dGramTerms; DeviceArray<int> dGramSeg; // Gram form of the RPA phase (rpaGram), when selected
 	int gramRows = 0;                                                 // rows per Gram block (0: not in use)
 	int itemOrder = 0;                                                // FlowConfig::order of the run-time compiled kernel (PFFRG_ORDER=t: t-major)
+	std::vector<int> siteNewOf, siteOrder;                            // device-internal site order (RelabelledDesc); empty: the reference order
+	DeviceArray<int> dSiteNewOf;
 	DeviceArray<unsigned short> dMeshStart; int meshShift = 52, meshKeyBase = 0, meshKeys = 0;
 	// lattice-specialised flow kernel (NVRTC), see pffrg_jit.cpp
 	cudaLibrary_t jitLibrary = nullptr;
@@ -609,6 +611,78 @@ namespace
 		return PFFRG_OK;
 	}
 
+	// Device-internal order of the representative sites. A gather with the site/pair exchange flag reads, for site j, the entry of the
+	// inverted site inv[j] (Lattice::getInvertedSites, src/SU2/SU2VertexTwoParticle.hpp:369-387): a permutation of the sites that moves
+	// half of them on kagome / honeycomb / pyrochlore lattices and scatters a warp's 16-byte loads over up to 13 cache lines instead of 4
+	// (ncu, pyrochlore-r8: 1.8 x the ideal number of L1 wavefronts over all gathers). Inversion is an involution, so the sites are
+	// relabelled such that the two members of every pair {j, inv[j]} are neighbours (never straddling a 128-byte line): an exchanged
+	// gather then touches the same lines as a plain one. Site 0 (the reference site: site-0 buffers, self-energy flow, correlations)
+	// keeps index 0. All tables are relabelled once at creation; the reference order only exists at the boundary (import / export
+	// kernels, bare couplings, correlation output). PFFRG_RELABEL=0 keeps the reference order.
+	struct RelabelledDesc
+	{
+		std::vector<int> order, newOf; // order[new] = old, newOf[old] = new
+		std::vector<int32_t> sitesRid, sitesPerm, invRid, invPerm, ovOff, ovRid1, ovRid2, ovPerm1, ovPerm2, rngFwd, rngInv;
+		pffrg_desc view;
+		bool identity = true;
+		explicit RelabelledDesc(const pffrg_desc *d)
+		{
+			const int L = d->n_sites;
+			order.resize(L); newOf.assign(L, -1);
+			bool relabel = true;
+			if (const char *e = getenv("PFFRG_RELABEL")) relabel = atoi(e) != 0;
+			// involution check (anything else keeps the reference order)
+			for (int j = 0; j < L && relabel; ++j) if (d->inverted_rid[d->inverted_rid[j]] != j) relabel = false;
+			if (relabel && L > 0 && d->inverted_rid[0] != 0) relabel = false;
+			if (relabel)
+			{
+				std::vector<int> singles, pairs;
+				for (int j = 0; j < L; ++j)
+				{
+					const int k = d->inverted_rid[j];
+					if (k == j) singles.push_back(j);
+					else if (j < k) { pairs.push_back(j); pairs.push_back(k); }
+				}
+				// singles first (site 0 leads), an even number of them so that the pairs start on an even index; a surplus single goes last
+				int n = 0, surplus = -1;
+				if (singles.size() % 2 == 1 && !pairs.empty() && singles.size() > 1) { surplus = singles.back(); singles.pop_back(); }
+				for (int j : singles) order[n++] = j;
+				if (singles.size() % 2 == 1 && !pairs.empty()) { /* only site 0 is self-inverse: the pairs start at index 1 (one straddling pair per 8) */ }
+				for (int j : pairs) order[n++] = j;
+				if (surplus >= 0) order[n++] = surplus;
+			}
+			else for (int j = 0; j < L; ++j) order[j] = j;
+			for (int n = 0; n < L; ++n) { newOf[order[n]] = n; if (order[n] != n) identity = false; }
+
+			sitesRid.resize(L); invRid.resize(L); sitesPerm.resize(3 * L); invPerm.resize(3 * L);
+			ovOff.assign(L + 1, 0);
+			for (int n = 0; n < L; ++n)
+			{
+				const int j = order[n];
+				sitesRid[n] = newOf[d->sites_rid[j]]; invRid[n] = newOf[d->inverted_rid[j]];
+				for (int k = 0; k < 3; ++k) { sitesPerm[3 * n + k] = d->sites_perm[3 * j + k]; invPerm[3 * n + k] = d->inverted_perm[3 * j + k]; }
+				ovOff[n + 1] = ovOff[n] + (d->overlap_offsets[j + 1] - d->overlap_offsets[j]);
+			}
+			const int total = ovOff[L];
+			ovRid1.resize(total); ovRid2.resize(total); ovPerm1.resize(3 * (size_t)total); ovPerm2.resize(3 * (size_t)total);
+			for (int n = 0; n < L; ++n)
+			{
+				const int j = order[n];
+				for (int i = d->overlap_offsets[j], o = ovOff[n]; i < d->overlap_offsets[j + 1]; ++i, ++o)
+				{
+					ovRid1[o] = newOf[d->overlap_rid1[i]]; ovRid2[o] = newOf[d->overlap_rid2[i]];
+					for (int k = 0; k < 3; ++k) { ovPerm1[3 * (size_t)o + k] = d->overlap_perm1[3 * (size_t)i + k]; ovPerm2[3 * (size_t)o + k] = d->overlap_perm2[3 * (size_t)i + k]; }
+				}
+			}
+			rngFwd.resize(d->n_range); rngInv.resize(d->n_range);
+			for (int k = 0; k < d->n_range; ++k) { rngFwd[k] = newOf[d->range_fwd_rid[k]]; rngInv[k] = newOf[d->range_inv_rid[k]]; }
+			view = *d;
+			view.sites_rid = sitesRid.data(); view.sites_perm = sitesPerm.data(); view.inverted_rid = invRid.data(); view.inverted_perm = invPerm.data();
+			view.overlap_offsets = ovOff.data(); view.overlap_rid1 = ovRid1.data(); view.overlap_rid2 = ovRid2.data(); view.overlap_perm1 = ovPerm1.data(); view.overlap_perm2 = ovPerm2.data();
+			view.range_fwd_rid = rngFwd.data(); view.range_inv_rid = rngInv.data();
+		}
+	};
+
 	// (rid1, perm1, perm2, rid2) -> multiplicity of the overlap terms of one representative site (Lattice::getOverlap(rid),
 	// src/Lattice.hpp:46-150); SU2 ignores the spin permutations
 	std::map<std::tuple<int, int, int, int>, int> mergedOverlap(const pffrg_desc *d, int core, int rid)
@@ -1030,7 +1104,7 @@ namespace
 		{
 			if (!src[a]) return fail(PFFRG_ERR_ARGUMENT, "vertex array %d is null", a);
 			CUDA_TRY(cudaMemcpyAsync(staging, static_cast<const T *>(src[a]) + (size_t)rowBegin * per, len * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-			importKernel<T><<<1184, 256, 0, h->stream>>>(staging, dst, (size_t)rowBegin, (size_t)rows, h->L, h->Lp, h->RL, vectorWidth(h->core), h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
+			importKernel<T><<<1184, 256, 0, h->stream>>>(staging, dst, (size_t)rowBegin, (size_t)rows, h->L, h->Lp, h->RL, vectorWidth(h->core), h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1, h->dSiteNewOf.p);
 			CUDA_TRY(cudaGetLastError());
 		}
 		return PFFRG_OK;
@@ -1046,7 +1120,7 @@ namespace
 		for (int a = 0; a < h->nArrays; ++a)
 		{
 			if (!dst[a]) continue;
-			exportKernel<T><<<1184, 256, 0, h->stream>>>(src, staging, (size_t)rowBegin, (size_t)rows, h->L, h->Lp, h->RL, vectorWidth(h->core), h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1);
+			exportKernel<T><<<1184, 256, 0, h->stream>>>(src, staging, (size_t)rowBegin, (size_t)rows, h->L, h->Lp, h->RL, vectorWidth(h->core), h->core == TRI ? 0 : a, h->core == TRI ? 16 : 1, h->dSiteNewOf.p);
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaMemcpyAsync(static_cast<T *>(dst[a]) + (size_t)rowBegin * per, staging, len * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
 		}
@@ -1224,7 +1298,11 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
 	if (prop.major < 10) return fail(PFFRG_ERR_CUDA, "device %d is sm_%d%d; libpffrg is built for sm_100a only", d->device, prop.major, prop.minor);
 
+	const pffrg_desc *original = d;
+	const RelabelledDesc relabelled(original);
+	d = &relabelled.view; // from here on: the device-internal site order
 	pffrg_context *h = new pffrg_context();
+	if (!relabelled.identity) { h->siteNewOf = relabelled.newOf; h->siteOrder = relabelled.order; }
 	const CoreModel m = modelOf(d->core);
 	h->core = d->core; h->nw = d->n_frequencies; h->L = L; h->Lp = paddedSites(L); h->C = m.C; h->RL = m.C * h->Lp; h->nArrays = m.arrays;
 	h->nf = (int64_t)h->nw * h->nw * (h->nw + 1) / 2;
@@ -1268,6 +1346,7 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	ok(h->dRngFwd.upload(std::vector<int>(d->range_fwd_rid, d->range_fwd_rid + d->n_range)));
 	ok(h->dRngInv.upload(std::vector<int>(d->range_inv_rid, d->range_inv_rid + d->n_range)));
 	ok(h->dTasks.upload(tasks)); ok(h->dSlotOff.upload(slotOff)); ok(h->dWords.upload(words));
+	if (!h->siteNewOf.empty()) ok(h->dSiteNewOf.upload(h->siteNewOf));
 	ok(h->dV4.alloc(h->v4Elements())); ok(h->dFlow4.alloc(h->v4Elements()));
 	ok(h->dV2.alloc(h->nw)); ok(h->dFlow2.alloc(h->nw)); ok(h->dCutoff.alloc(1));
 	h->nodeStride = 2 * h->nw + 8;
@@ -1304,7 +1383,7 @@ int pffrg_destroy(pffrg_handle h)
 	h->dV4b.release(); h->dSync.release(); h->dVecStaging.release(); h->dTimes.release();
 	if (h->hFlags) cudaFreeHost(h->hFlags);
 	h->dMesh.release(); h->dSitesRid.release(); h->dInvRid.release(); h->dSitesPerm.release(); h->dInvPerm.release(); h->dRngFwd.release(); h->dRngInv.release();
-	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release(); h->dMeshStart.release(); h->dGramTerms.release(); h->dGramSeg.release();
+	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release(); h->dMeshStart.release(); h->dGramTerms.release(); h->dGramSeg.release(); h->dSiteNewOf.release();
 	if (h->jitLibrary) cudaLibraryUnload(h->jitLibrary); h->dV4.release(); h->dFlow4.release(); h->dV2.release(); h->dFlow2.release(); h->dCutoff.release();
 	h->dCount.release(); h->dNodeW.release(); h->dNodeWt.release(); h->dNan.release(); h->dStaging.release();
 	h->dChiPartial.release(); h->dChi.release(); h->dChiCount.release();
@@ -1439,6 +1518,13 @@ int pffrg_set_initial_condition(pffrg_handle h, double cutoff, const double *bar
 	CUDA_TRY(cudaSetDevice(h->device));
 	const size_t entries = (size_t)h->C * h->L;
 	if (h->dStaging.n < entries) CUDA_TRY(h->dStaging.alloc(entries));
+	std::vector<double> ordered;
+	if (!h->siteOrder.empty())
+	{
+		ordered.resize(entries);
+		for (int c = 0; c < h->C; ++c) for (int n = 0; n < h->L; ++n) ordered[(size_t)c * h->L + n] = bare[(size_t)c * h->L + h->siteOrder[n]];
+		bare = ordered.data();
+	}
 	CUDA_TRY(cudaMemcpyAsync(h->dStaging.p, bare, entries * sizeof(double), cudaMemcpyHostToDevice, h->stream));
 	initialConditionKernel<<<1184, 256, 0, h->stream>>>(h->v4cur(), h->dStaging.p, (size_t)h->nf, h->L, h->Lp, h->RL, vectorWidth(h->core));
 	CUDA_TRY(cudaGetLastError());
@@ -1611,6 +1697,12 @@ int pffrg_measure_correlation(pffrg_handle h, double *chi)
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemcpyAsync(chi, h->dChi.p, sizeof(double) * entries, cudaMemcpyDeviceToHost, h->stream));
 	CUDA_TRY(cudaStreamSynchronize(h->stream));
+	if (!h->siteNewOf.empty())
+	{
+		// device-internal site order -> the reference's
+		const std::vector<double> device(chi, chi + entries);
+		for (int c = 0; c < h->C; ++c) for (int j = 0; j < h->L; ++j) chi[(size_t)c * h->L + j] = device[(size_t)c * h->L + h->siteNewOf[j]];
+	}
 	return PFFRG_OK;
 }
 
@@ -1646,6 +1738,8 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	const char *jitEnv = getenv("PFFRG_JIT");
 	const LaunchGeometry geo = chooseGeometry(L, d->core == SU2 && !(jitEnv && atoi(jitEnv) == 0));
 	const int groups = geo.groups, threads = geo.threads;
+	const RelabelledDesc relabelled(d);
+	d = &relabelled.view; // as pffrg_create
 	int64_t uniquePairs = 0;
 	for (int rid = 0; rid < L; ++rid) uniquePairs += (int64_t)mergedOverlap(d, d->core, rid).size();
 	if (wantGram(d->core, uniquePairs))
@@ -1749,6 +1843,14 @@ int pffrg_tri_terms(int region, int32_t *terms, int capacity)
 			}
 	if (!consistent) return fail(PFFRG_ERR_STATE, "TRI spin algebra produced an imaginary coefficient");
 	return n;
+}
+
+int pffrg_site_order(const pffrg_desc *d, int32_t *order)
+{
+	if (!d || d->n_sites < 1 || !d->inverted_rid || !d->sites_rid || !d->sites_perm || !d->inverted_perm || !d->overlap_offsets || !d->range_fwd_rid || !d->range_inv_rid || !order) return fail(PFFRG_ERR_ARGUMENT, "bad argument");
+	const RelabelledDesc r(d);
+	std::copy(r.order.begin(), r.order.end(), order);
+	return r.identity ? 0 : 1;
 }
 
 int pffrg_gram_tables(const pffrg_desc *d, int rowsPerBlock, int warps, uint32_t *terms, int capacity, int32_t *seg, double *conflictDegree)

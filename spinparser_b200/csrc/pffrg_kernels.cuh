@@ -444,8 +444,33 @@ namespace pffrg
 		}
 	}
 
+	// SU2: the two halves of gatherSite. gatherLoadSU2 issues the four 16-byte row loads of one access buffer, gatherCombineSU2 forms the
+	// interpolated {spin, density} pair from them. Split so that the loads of the NEXT quadrature node can be in flight while the
+	// current one is combined (software pipeline of the gather loop, PFFRG_PIPELINE).
+	__device__ __forceinline__ void gatherLoadSU2(const Problem &P, const double *__restrict__ v4, const AccessBuffer &ab, int siteFwd, int siteInv, double2 (&v)[4])
+	{
+		const int4 rows = *reinterpret_cast<const int4 *>(&ab.row[0]);
+		const int site = (ab.flags & AB_EXCHANGE) ? siteInv : siteFwd;
+		const int rk[4] = { rows.x, rows.y, rows.z, rows.w };
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const double2 *>(v4 + (size_t)((unsigned)rk[k] * (unsigned)sizeRL(P) + 2u * (unsigned)site)));
+	}
+	__device__ __forceinline__ void gatherCombineSU2(const AccessBuffer &ab, const double2 (&v)[4], double (&out)[2])
+	{
+		const double2 w01 = *reinterpret_cast<const double2 *>(&ab.w[0]), w23 = *reinterpret_cast<const double2 *>(&ab.w[2]);
+		const int flags = ab.flags;
+		const double wk[4] = { w01.x, w01.y, w23.x, w23.y };
+		const double ok[4] = { oddWeight(w01.x, flags, 0), oddWeight(w01.y, flags, 1), oddWeight(w23.x, flags, 2), oddWeight(w23.y, flags, 3) };
+		out[0] = 0.0; out[1] = 0.0;
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) { out[0] += wk[k] * v[k].x; out[1] += ok[k] * v[k].y; }
+	}
+
 #ifndef PFFRG_MIRROR
 #define PFFRG_MIRROR 0 // A/B switch of the run-time compiled kernel, see gatherTwo
+#endif
+#ifndef PFFRG_PIPELINE
+#define PFFRG_PIPELINE 0 // run-time compiled SU2 kernel: row loads of the next quadrature node in flight while the current one is combined
 #endif
 	// The t channel's gathered buffers come in mirrored pairs: buffer 2 is buffer 0 with the s and u arguments exchanged, buffer 3
 	// is buffer 1 with (s, u) -> (-u, -s) (src/SU2/SU2FrgCore.cpp:233-239). Only s >= u is stored, so both members of a pair read
@@ -1499,11 +1524,38 @@ namespace pffrg
 				}
 				else if (worker)
 				{
+					[[maybe_unused]] double2 pending[4][4]; // PFFRG_PIPELINE: the 16 rows of the node this thread works on next
+					if constexpr (CORE == SU2 && PFFRG_PIPELINE != 0)
+					{
+						if (g < nb)
+						{
+							#pragma unroll
+							for (int b = 0; b < 4; ++b) gatherLoadSU2(P, v4, abTable[g * nbuf + b], siteFwd, siteInv, pending[b]);
+						}
+					}
 					for (int node = g; node < nb; node += cfg.groups)
 					{
 						double A[4][C];
 						const AccessBuffer *ab = abTable + node * nbuf;
-						if (PFFRG_MIRROR && tPass && mirroredPair(ab[0], ab[2]) && mirroredPair(ab[1], ab[3]))
+						if constexpr (CORE == SU2 && PFFRG_PIPELINE != 0)
+						{
+							double2 current[4][4];
+							#pragma unroll
+							for (int b = 0; b < 4; ++b)
+							{
+								#pragma unroll
+								for (int k = 0; k < 4; ++k) current[b][k] = pending[b][k];
+							}
+							const int next = node + cfg.groups;
+							if (next < nb)
+							{
+								#pragma unroll
+								for (int b = 0; b < 4; ++b) gatherLoadSU2(P, v4, abTable[next * nbuf + b], siteFwd, siteInv, pending[b]);
+							}
+							#pragma unroll
+							for (int b = 0; b < 4; ++b) gatherCombineSU2(ab[b], current[b], reinterpret_cast<double (&)[2]>(A[b]));
+						}
+						else if (PFFRG_MIRROR && tPass && mirroredPair(ab[0], ab[2]) && mirroredPair(ab[1], ab[3]))
 						{
 							// 8 row loads instead of 16, decided before any load is issued so that they still form one burst
 							gatherTwo<CORE>(P, v4, ab[0], ab[2], siteFwd, siteInv, permFwd, permInv, A[0], A[2]);
@@ -1753,25 +1805,27 @@ namespace pffrg
 	// reference array (one channel, [row][L], or TRI [row][16][L]) -> device layout; T = float or double
 	// `src` / `dst` in reference layout start at row 0 of the staging array, which holds the rows [rowBegin, rowBegin + rows) of the vertex
 	template <typename T>
-	__global__ void importKernel(const T *__restrict__ src, double *__restrict__ dst, size_t rowBegin, size_t rows, int L, int Lp, int RL, int vw, int cFirst, int cCount)
+	__global__ void importKernel(const T *__restrict__ src, double *__restrict__ dst, size_t rowBegin, size_t rows, int L, int Lp, int RL, int vw, int cFirst, int cCount, const int *__restrict__ siteMap)
 	{
 		const size_t n = rows * cCount * L;
 		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 		{
 			const size_t row = i / ((size_t)cCount * L);
 			const int r = (int)(i - row * cCount * L), c = r / L, j = r - c * L;
-			dst[(rowBegin + row) * RL + channelOffset(vw, cFirst + c, Lp) + j * vw] = (double)src[i];
+			const int site = siteMap ? siteMap[j] : j; // device-internal site order (RelabelledDesc, pffrg.cu)
+			dst[(rowBegin + row) * RL + channelOffset(vw, cFirst + c, Lp) + site * vw] = (double)src[i];
 		}
 	}
 	template <typename T>
-	__global__ void exportKernel(const double *__restrict__ src, T *__restrict__ dst, size_t rowBegin, size_t rows, int L, int Lp, int RL, int vw, int cFirst, int cCount)
+	__global__ void exportKernel(const double *__restrict__ src, T *__restrict__ dst, size_t rowBegin, size_t rows, int L, int Lp, int RL, int vw, int cFirst, int cCount, const int *__restrict__ siteMap)
 	{
 		const size_t n = rows * cCount * L;
 		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 		{
 			const size_t row = i / ((size_t)cCount * L);
 			const int r = (int)(i - row * cCount * L), c = r / L, j = r - c * L;
-			dst[i] = (T)src[(rowBegin + row) * RL + channelOffset(vw, cFirst + c, Lp) + j * vw];
+			const int site = siteMap ? siteMap[j] : j;
+			dst[i] = (T)src[(rowBegin + row) * RL + channelOffset(vw, cFirst + c, Lp) + site * vw];
 		}
 	}
 	template <typename T>

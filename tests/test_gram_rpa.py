@@ -131,3 +131,30 @@ def test_term_order_of_the_benchmark_lattice_is_nearly_conflict_free():
     assert int(np.sum(terms.astype(np.int64) >> 22)) == int(t.overlap_offsets[-1])
     assert len(terms) < 1.15 * 40355, "padding overhead of the term array"
     assert degree < 1.5, degree  # a random order gives ~2.5
+
+
+@pytest.mark.parametrize("case", ["su2_square_r3_nw10", "su2_kagome_r4_nw8", "su2_kagome_r7_nw6", "xyz_honeycomb_kitaev_r3_nw10", "tri_kagome_dm_r3_nw6", "bench:pyrochlore_r8_su2_nw64"])
+def test_device_site_order_pairs_inverted_sites(case):
+    """pffrg_site_order: a permutation with site 0 first in which j and getInvertedSites()[j] are neighbours within one 128-byte line
+    (8 sites of 16 bytes), so that gathers with the site-exchange flag are as coalesced as plain ones."""
+    import os
+    from conftest import ROOT
+    from spinparser_b200 import ProblemTables, _capi, read_pfd
+    from spinparser_b200.frgcore import make_descriptor
+    d = read_pfd(os.path.join(ROOT, "bench_data", case[6:] + ".tables.pfd")) if case.startswith("bench:") else golden(case)
+    t = ProblemTables.from_pfd(d)
+    L = t.n_sites
+    order = np.zeros(L, dtype=np.int32)
+    core = bytes(d["core"]).decode()
+    changed = _capi.check(_capi.lib.pffrg_site_order(C.byref(make_descriptor(core, t)), order.ctypes.data_as(C.POINTER(C.c_int32))))
+    assert sorted(order) == list(range(L)) and order[0] == 0
+    new_of = np.argsort(order)
+    inv = t.inverted_rid
+    moved = int((inv != np.arange(L)).sum())
+    assert changed == (0 if np.array_equal(order, np.arange(L)) else 1)
+    straddling = 0
+    for j in range(L):
+        a, b = int(new_of[j]), int(new_of[inv[j]])
+        assert abs(a - b) <= 1, "pair members are neighbours"
+        straddling += a // 8 != b // 8
+    assert straddling <= max(2, moved // 8), (straddling, moved)

@@ -102,3 +102,87 @@ def test_b200_backend_fails_loudly_without_gpu(tmp_path):
 def test_unknown_backend_and_identifier_are_rejected(tmp_path):
     proc, _ = _run("spinparser64_b200", CASES[0], "tpu", tmp_path)
     assert proc.returncode != 0 and "Unknown FRG core backend" in proc.stderr
+
+
+# ---- checkpoint / resume and deferred measurements through the adapter (the reference's test/scripted/test_checkpoint.sh and
+# test_defer.sh): the harness restates the driver loop of src/SpinParser.cpp:141-217 (periodic checkpoint when it is due, resume from
+# the checkpoint, post-processing stage that reads every deferred state back), the vertex I/O is the reference's own
+# {SU2,XYZ,TRI}EffectiveAction::writeCheckpoint / readCheckpoint. With the B200 cores the host arrays are refreshed lazily: these tests
+# fail if a checkpoint or a deferred dump ever pairs the new cutoff with a stale vertex.
+def _resume_case(backend, case, tmp_path):
+    proc, got = _run("spinparser64_b200", case, backend, tmp_path, extra=("--resume-after", "20", "--no-measure"))
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert int(got["checkpointAtStep"]) == 20 and int(got["resumed/fromStep"]) == 20
+    assert float(got["resumed/finalStep"]) == float(got["finalStep"])
+    want = golden(case)
+    for k in want:
+        if k.startswith("final/v"):
+            # the resumed flow repeats the uninterrupted one bit for bit (FP64 host arrays: the checkpoint loses nothing) ...
+            assert np.array_equal(np.asarray(got["resumed/" + k]), np.asarray(got[k])), k
+            # ... and both equal the unmodified reference's final vertex
+            b = np.asarray(want[k])
+            assert np.abs(np.asarray(got[k]) - b).max() <= 1e-9 * np.abs(b).max() + 1e-300, k
+
+
+def test_checkpoint_resume_stock_cores(tmp_path):
+    _resume_case("cpu", CASES[0], tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_checkpoint_resume_gpu_cores(case, tmp_path):
+    _resume_case("b200", case, tmp_path)
+
+
+def _defer_case(backend, case, tmp_path, measurement="device"):
+    proc, got = _run("spinparser64_b200", case, backend, tmp_path, extra=("--defer",), measurement=measurement)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    want = golden(case)
+    assert int(got["postprocessedStates"]) == int(want["finalStep"]) + 1
+    return _compare(got, want, rel=1e-8, floor_rel=1e-10)
+
+
+def test_deferred_measurements_stock_cores(tmp_path):
+    _defer_case("cpu", CASES[0], tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("measurement", ["device", "host"])
+@pytest.mark.parametrize("case", CASES)
+def test_deferred_measurements_gpu_cores(case, measurement, tmp_path):
+    """-d / --defer: every step's state is appended to the data file by FrgCore::takeMeasurements (src/FrgCore.hpp:58-66) and measured in
+    the post-processing stage -- on the GPU (the state read back from the file is uploaded again) or by the reference's host classes."""
+    _defer_case("b200", case, tmp_path, measurement)
+
+
+@pytest.mark.gpu
+def test_two_ranks_through_the_adapter(tmp_path):
+    """Two processes of the reference host program, one GPU each (PFFRG_RANK / PFFRG_NRANKS / PFFRG_ID_FILE, the stand-in for the MPI
+    ranks of the reference in this MPI-less image): the work items of every step are sharded, the slices exchanged inside
+    pffrg_finalize_step; both ranks end with the reference's final vertex and rank 0 writes the reference's measurement output."""
+    from spinparser_b200.frgcore import device_count
+    from spinparser_b200.pfd import read_pfd
+    if device_count() < 2:
+        pytest.skip("needs two GPUs")
+    case = CASES[0]
+    exe = os.path.join(REF, "spinparser64_b200")
+    procs, outs = [], []
+    for rank in range(2):
+        out = str(tmp_path / f"rank{rank}.pfd")
+        work = tmp_path / f"rank{rank}"
+        work.mkdir()
+        env = dict(os.environ, SPINPARSER_BACKEND="b200", PFFRG_RANK=str(rank), PFFRG_NRANKS="2", PFFRG_ID_FILE=str(tmp_path / "nccl.id"))
+        cmd = [exe, "-r", os.path.join(ROOT, "oracle", "res"), os.path.join(GOLDEN, "tasks", case + ".xml"), "--out", out, "--no-lattice"]
+        procs.append(subprocess.Popen(cmd, env=env, cwd=str(work), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        outs.append(out)
+    for p in procs:
+        _, err = p.communicate(timeout=600)
+        assert p.returncode == 0, err[-2000:]
+    want = golden(case)
+    got0, got1 = read_pfd(outs[0]), read_pfd(outs[1])
+    _compare(got0, want, rel=1e-8, floor_rel=1e-10)
+    for k in want:
+        if k.startswith("final/v"):
+            assert np.array_equal(np.asarray(got0[k]), np.asarray(got1[k])), k
+            b = np.asarray(want[k])
+            assert np.abs(np.asarray(got0[k]) - b).max() <= 1e-9 * np.abs(b).max() + 1e-300, k
