@@ -281,10 +281,16 @@ namespace pffrg
 	// generateAccessBuffer (SU2VertexTwoParticle.hpp:399-490, TRIVertexTwoParticle.hpp:401-504) from two interpolation records;
 	// `exactIndex` is the mesh index of the on-mesh argument (offset() of a mesh value is its own index, FrequencyDiscretization.hpp:306-316)
 	template <int CORE>
+	__device__ __forceinline__ void assembleFromRecords(int nw, int ch, int b, int exactIndex, int recipe, const LerpRecord &r1, const LerpRecord &r2, AccessBuffer &ab);
+	template <int CORE>
 	__device__ __forceinline__ void assembleAccessBuffer(int nw, int ch, int b, int exactIndex, const LerpRecord *rec /* [4] */, AccessBuffer &ab)
 	{
 		const int recipe = bufferRecipe(ch, b);
-		const LerpRecord r1 = rec[recipe & 3], r2 = rec[(recipe >> 3) & 3];
+		assembleFromRecords<CORE>(nw, ch, b, exactIndex, recipe, rec[recipe & 3], rec[(recipe >> 3) & 3], ab);
+	}
+	template <int CORE>
+	__device__ __forceinline__ void assembleFromRecords(int nw, int ch, int b, int exactIndex, int recipe, const LerpRecord &r1, const LerpRecord &r2, AccessBuffer &ab)
+	{
 		const bool neg1 = (recipe & 4) ? r1.pos != 0 : r1.neg != 0, neg2 = (recipe & 32) ? r2.pos != 0 : r2.neg != 0;
 		const bool local = ch == CH_T && b >= 4;
 		bool sNeg, tNeg, uNeg;

@@ -469,6 +469,9 @@ namespace pffrg
 #ifndef PFFRG_MIRROR
 #define PFFRG_MIRROR 0 // A/B switch of the run-time compiled kernel, see gatherTwo
 #endif
+#ifndef PFFRG_MERGED_TABLES
+#define PFFRG_MERGED_TABLES 0 // run-time compiled kernel: access buffers in one step (every buffer does its own two mesh searches)
+#endif
 #ifndef PFFRG_PIPELINE
 #define PFFRG_PIPELINE 0 // run-time compiled SU2 kernel: row loads of the next quadrature node in flight while the current one is combined
 #endif
@@ -1466,6 +1469,28 @@ namespace pffrg
 				const int nb = min(batch, hi - b0);
 				const int stageOff = sub * NBT + staged;
 				subSync(); // previous batch fully consumed
+#if PFFRG_MERGED_TABLES
+				// ---- phase 0: access buffers, one thread per (node, buffer): its two interpolation records (a bucketed mesh search each; computed
+				// per buffer instead of once per node and shared through shared memory -- a barrier and a round trip less per batch), then the
+				// sector map, weights and rows
+				for (int idx = tid; idx < nb * nbuf; idx += nthreads)
+				{
+					const int node = idx / nbuf, b = idx - node * nbuf;
+					const int gn = b0 + node;
+					const int ch = tPass ? CH_T : (gn < nFirst ? CH_S : CH_U);
+					const double wp = gn < nFirst ? nodeW0[gn] : nodeW1[gn - nFirst];
+					if (b == 0)
+					{
+						const double wt = gn < nFirst ? nodeWt0[gn] : nodeWt1[gn - nFirst];
+						bW[node] = (CORE == SU2 && ch == CH_U) ? -wt : wt;
+					}
+					const int recipe = bufferRecipe(ch, b);
+					LerpRecord r1, r2;
+					makeLerpRecord(mesh, nw, P.meshIndex, nodeQuantity(ch, recipe & 3, f.w1p, f.w1, f.w2p, f.w2, wp), r1);
+					makeLerpRecord(mesh, nw, P.meshIndex, nodeQuantity(ch, (recipe >> 3) & 3, f.w1p, f.w1, f.w2p, f.w2, wp), r2);
+					assembleFromRecords<CORE>(nw, ch, b, ch == CH_S ? so : (ch == CH_T ? ti : uo), recipe, r1, r2, abTable[idx]);
+				}
+#else
 				// ---- phase 0: access buffers. Step A: the four interpolated frequencies of every node (one mesh search each)
 				for (int idx = tid; idx < nb * 4; idx += nthreads)
 				{
@@ -1489,6 +1514,7 @@ namespace pffrg
 					const int ch = tPass ? CH_T : ((b0 + node) < nFirst ? CH_S : CH_U);
 					assembleAccessBuffer<CORE>(nw, ch, b, ch == CH_S ? so : (ch == CH_T ? ti : uo), lerp + 4 * node, abTable[idx]);
 				}
+#endif
 				subSync();
 				if (tPass)
 				{
