@@ -196,6 +196,15 @@ int pffrg_jit_compile_check(const pffrg_desc *desc, int64_t *cubin_bytes);
  * terms per buffer pair (256, or 64 for the RPA). Used by the parity tests to compare against the reference term by term. */
 int pffrg_tri_terms(int region, int32_t *terms, int capacity);
 
+/* Tables of the Gram form of the TRI RPA phase as the kernel walks them (rpaTriGram / triGramReduce, pffrg_kernels.cuh): the sum over
+ * quadrature nodes and buffer pairs of R^{mu nu}[rid] = sum_i sum_k 2 eta(mu,k,nu) A^{p1 mu,p1 k}[rid1_i] B^{p2 k,p2 nu}[rid2_i]
+ * (src/TRI/TRIFrgCore.cpp:733-1252) taken over the Gram blocks G^{(c1,c2)} = sum A^{c1} (x) B^{c2}. blocks[round * resident + slot] =
+ * c1 | c2 << 4 (0xffff: none); per round one pass of words (slot * GBLK + rid1 * GS + rid2) | out << 13 | minus << 23 | multiplicity << 24
+ * with out = (4 mu + nu) * n_sites + rid, GS = 8 ceil(n_sites / 8) + 1, GBLK = (GS - 1) GS; seg[2 * (round * warps + w)] = {begin, end}.
+ * *rounds receives the number of rounds; returns the number of words. Host only; used by the CPU tests. */
+int pffrg_trigram_tables(const pffrg_desc *desc, int resident, int warps, uint16_t *blocks, int block_capacity, uint32_t *terms, int capacity,
+                         int32_t *seg, int seg_capacity, int32_t *rounds);
+
 /* Device-internal order of the representative sites: order[k] = the reference's site index stored at position k of the device
  * layout. The two members of every pair {j, getInvertedSites()[j]} (src/Lattice.hpp:157-161) are neighbours, so that gathers with the
  * site-exchange flag (src/SU2/SU2VertexTwoParticle.hpp:369-387) touch the same cache lines as plain ones; site 0 stays first. Returns 1

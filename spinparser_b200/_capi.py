@@ -23,7 +23,7 @@ SYMBOLS = [
     "pffrg_num_vertex_arrays", "pffrg_vertex_array_length", "pffrg_num_items", "pffrg_comm_unique_id",
     "pffrg_comm_init", "pffrg_item_range", "pffrg_set_state", "pffrg_set_initial_condition", "pffrg_get_state", "pffrg_get_flow",
     "pffrg_compute_step", "pffrg_finalize_step", "pffrg_synchronize", "pffrg_num_channels", "pffrg_measure_correlation", "pffrg_set_item_range", "pffrg_get_stats",
-    "pffrg_stream", "pffrg_fp64_peak", "pffrg_dmma_peak", "pffrg_host_alloc", "pffrg_host_free", "pffrg_host_register", "pffrg_host_unregister", "pffrg_jit_compile_check", "pffrg_tri_terms", "pffrg_gram_tables", "pffrg_site_order", "pffrg_upload_slice", "pffrg_set_state_sharded", "pffrg_get_state_slice", "pffrg_plan_partition", "pffrg_plan_partition_feedback",
+    "pffrg_stream", "pffrg_fp64_peak", "pffrg_dmma_peak", "pffrg_host_alloc", "pffrg_host_free", "pffrg_host_register", "pffrg_host_unregister", "pffrg_jit_compile_check", "pffrg_tri_terms", "pffrg_gram_tables", "pffrg_trigram_tables", "pffrg_site_order", "pffrg_upload_slice", "pffrg_set_state_sharded", "pffrg_get_state_slice", "pffrg_plan_partition", "pffrg_plan_partition_feedback",
 ]
 
 
@@ -110,6 +110,7 @@ def _load() -> C.CDLL:
     lib.pffrg_upload_slice.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.pffrg_set_state_sharded.argtypes = [vp, C.c_double, vp, C.POINTER(vp), C.c_int]
     lib.pffrg_get_state_slice.argtypes = [vp, C.POINTER(C.c_double), vp, C.POINTER(vp), C.c_int, C.c_int64, C.c_int64]
+    lib.pffrg_trigram_tables.argtypes = [C.POINTER(Desc), C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, C.POINTER(C.c_uint32), C.c_int, _ip, C.c_int, _ip]
     lib.pffrg_site_order.argtypes = [C.POINTER(Desc), _ip]
     lib.pffrg_gram_tables.argtypes = [C.POINTER(Desc), C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int, _ip, _dp]
     lib.pffrg_plan_partition.argtypes = [C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_double, C.c_int, C.POINTER(C.c_int64)]

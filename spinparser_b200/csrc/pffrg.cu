@@ -124,7 +124,9 @@ struct pffrg_context
 	DeviceArray<int4> dTasks;
 	DeviceArray<unsigned> dWords;
 	DeviceArray<unsigned> dGramTerms; DeviceArray<int> dGramSeg; // Gram form of the RPA phase (rpaGram), when selected
-	int gramRows = 0;                                                 // rows per Gram block (0: not in use)
+	int gramRows = 0;                                                 // rows per Gram block (0: not in use); TRI Gram form: resident channel-pair blocks
+	DeviceArray<unsigned short> dTriBlocks; int triRounds = 0;         // TRI Gram form: channel pairs per (round, slot)
+	int64_t triBlockCount = 0, gramWords = 0;                          // Gram forms: needed channel-pair blocks (TRI), words walked per RPA phase
 	int itemOrder = 0;                                                // FlowConfig::order of the run-time compiled kernel (PFFRG_ORDER=t: t-major)
 	std::vector<int> siteNewOf, siteOrder;                            // device-internal site order (RelabelledDesc); empty: the reference order
 	DeviceArray<int> dSiteNewOf;
@@ -181,6 +183,7 @@ struct pffrg_context
 		P.mesh = dMesh.p; P.sites_rid = dSitesRid.p; P.inv_rid = dInvRid.p; P.sites_perm = dSitesPerm.p; P.inv_perm = dInvPerm.p;
 		P.rpa_tasks = dTasks.p; P.rpa_slot_off = dSlotOff.p; P.rpa_words = dWords.p;
 		P.gram_terms = dGramTerms.p; P.gram_seg = reinterpret_cast<const int2 *>(dGramSeg.p);
+		P.trigram_blocks = dTriBlocks.p; P.trigram_rounds = triRounds;
 		P.nrange = (int)dRngFwd.n; P.rng_fwd = dRngFwd.p; P.rng_inv = dRngInv.p; P.spin = spin;
 		P.meshIndex.start = dMeshStart.p; P.meshIndex.shift = meshShift; P.meshIndex.keyBase = meshKeyBase; P.meshIndex.nKeys = meshKeys;
 		return P;
@@ -299,6 +302,7 @@ namespace
 		return best;
 	}
 
+	void buildTriGramTables(const pffrg_desc *d, int L, int resident, int warps, std::vector<unsigned short> &blocks, std::vector<unsigned> &terms, std::vector<int> &seg, double *conflictDegree = nullptr);
 	// Term tables of rpaGram / gramReduce (pffrg_kernels.cuh), see the definition below
 	void buildGramTables(const pffrg_desc *d, int L, int Lp, int PB, int warps, std::vector<unsigned> &terms, std::vector<int> &seg, double *conflictDegree = nullptr);
 	JitShape chooseJitShape(int core, int nw, int L, int groups, int warps, size_t smemMax)
@@ -451,8 +455,47 @@ namespace
 		       "\n";
 	}
 
+	// TRI Gram form (rpaTriGram): gather batch = staged nodes = 8; as many resident channel-pair blocks as the shared memory holds
+	// (offsets of a term word: 13 bits; at most 16 tiles per warp). PFFRG_TRIGRAM_RESIDENT overrides the number of blocks.
+	JitShape chooseTriGramShape(int nw, int L, int groups, int threads, size_t smemMax)
+	{
+		JitShape best = { 0, 0, 0, 0, 0 };
+		const int LT = (L + 7) / 8, LpT = 8 * LT, GBLK = LpT * (LpT + 1), warps = threads / 32;
+		if (16 * L > 1024 || warps < 1) return best;
+		int forced = 0;
+		if (const char *e = getenv("PFFRG_TRIGRAM_RESIDENT")) forced = std::max(1, atoi(e));
+		for (int resident = 16; resident >= 1 && !best.nb; --resident)
+		{
+			if (forced && resident != forced) continue;
+			if (resident * GBLK > (1 << 13) || (resident * LT * LT + warps - 1) / warps > 16) continue;
+			const size_t smem = FlowSmem<TRI, 8>(nw, L, groups, 8, 1, resident, LpT).total;
+			if (smem <= smemMax) { best = { 8, 8, warps, 1, smem }; best.gramRows = resident; best.gramThreads = warps * 32; }
+		}
+		return best;
+	}
+	std::string triGramDefines(const JitShape &s)
+	{
+		return "#define PFFRG_TRIGRAM 1\n#define PFFRG_TRIGRAM_RESIDENT " + std::to_string(s.gramRows) + "\n#define PFFRG_GRAM_THREADS " + std::to_string(s.gramThreads) + "\n";
+	}
+	bool wantTriGram(int core)
+	{
+		if (core != TRI) return false;
+		const char *form = getenv("PFFRG_RPA");
+		return form ? std::string(form) == "gram" : true;
+	}
+
 	int compileCandidate(pffrg_context *h, const pffrg_desc *d, JitCandidate &c)
 	{
+		if (c.shape.gramRows > 0 && h->core == TRI)
+		{
+			std::vector<char> cubin;
+			const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, 1, 1, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, std::string(), cubin, triGramDefines(c.shape));
+			if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the TRI flow kernel (Gram form) failed: %s", err.c_str());
+			CUDA_TRY(cudaLibraryLoadData(&c.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+			CUDA_TRY(cudaLibraryGetKernel(&c.kernel, c.library, "pffrg_v4flow_jit"));
+			CUDA_TRY(cudaFuncSetAttribute((const void *)c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.shape.smem));
+			return PFFRG_OK;
+		}
 		if (c.shape.gramRows > 0)
 		{
 			std::vector<char> cubin;
@@ -500,9 +543,27 @@ namespace
 		long maxTerms = 60000, tuneTerms = 12000;
 		if (const char *e = getenv("PFFRG_JIT_MAX_TERMS")) maxTerms = atol(e);
 		if (const char *e = getenv("PFFRG_AUTOTUNE_MAX_TERMS")) tuneTerms = atol(e);
-		// TRI: table-driven RPA phase (rpaTri), precompiled kernels (cluster pairs were measured there too: kagome-r7 950 vs 955 ms, not kept)
-		if (h->core == TRI) return PFFRG_OK;
 		const auto t0 = std::chrono::steady_clock::now();
+		// TRI: Gram form of the RPA phase in a run-time compiled kernel (rpaTriGram; PFFRG_RPA=table keeps the precompiled kernels with the
+		// table-driven phase rpaTri8). A lattice it does not fit (more than 64 representatives, shared memory) stays on the precompiled kernels.
+		if (h->core == TRI)
+		{
+			if (!wantTriGram(h->core) || h->nb != 8) return PFFRG_OK;
+			JitShape shape = chooseTriGramShape(h->nw, h->L, h->groups, h->threads, smemMax);
+			if (!shape.nb) return getenv("PFFRG_RPA") ? fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_RPA=gram: the TRI Gram form does not fit this lattice (L %d)", h->L) : PFFRG_OK;
+			JitCandidate c = { h->threads, h->groups, shape, nullptr, nullptr, 0.f };
+			const int rc = compileCandidate(h, d, c);
+			if (rc != PFFRG_OK) return rc;
+			std::vector<unsigned short> blocks; std::vector<unsigned> terms; std::vector<int> seg;
+			buildTriGramTables(d, h->L, shape.gramRows, h->threads / 32, blocks, terms, seg);
+			CUDA_TRY(h->dTriBlocks.upload(blocks)); CUDA_TRY(h->dGramTerms.upload(terms)); CUDA_TRY(h->dGramSeg.upload(seg));
+			h->triRounds = (int)(blocks.size() / shape.gramRows);
+			h->triBlockCount = (int64_t)std::count_if(blocks.begin(), blocks.end(), [](unsigned short b) { return b != 0xffff; });
+			h->gramWords = (int64_t)terms.size();
+			adoptCandidate(h, c);
+			h->jitCompileMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+			return PFFRG_OK;
+		}
 		std::vector<JitCandidate> candidates;
 		// Form of the RPA phase (SU2): PFFRG_RPA=gram -- Gram matrix over the staged nodes + one walk of the overlap list per phase
 		// (rpaGram; no generated code, any lattice size); PFFRG_RPA=code -- lattice-specialised straight-line code. Default: the Gram form
@@ -521,6 +582,7 @@ namespace
 				std::vector<unsigned> terms; std::vector<int> seg;
 				buildGramTables(d, h->L, h->Lp, shape.gramRows, h->threads / 32, terms, seg);
 				CUDA_TRY(h->dGramTerms.upload(terms)); CUDA_TRY(h->dGramSeg.upload(seg));
+				h->gramWords = (int64_t)terms.size();
 				adoptCandidate(h, c);
 				h->jitCompileMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 				return PFFRG_OK;
@@ -840,14 +902,74 @@ namespace
 		return p;
 	}
 
-	// Term tables of gramReduce. For every block of PB rows of the Gram matrix: one flat array of 32-bit words
-	//     (rid1 - block * PB) * Lp + rid2  |  rid << 14  |  multiplicity << 22
-	// of the merged overlap terms (rid1, rid2, multiplicity) of all representative sites rid with rid1 in the block, sorted by rid.
-	// - every rid list is padded to a multiple of 8 words (multiplicity 0), so that the 8 consecutive words a lane reads belong to one rid;
-	// - the rids are dealt to the `warps` warps of the CTA as contiguous ranges of about equal length; every range starts on a multiple
-	//   of 256 words and is padded to whole chunks of 256 words: seg[2 * (block * warps + w)] = {begin, end};
-	// - inside a list the words are ordered so that in every step k the 8 lanes of a quarter warp (words 64 Q + 8 l + k, l = 0..7, of a
-	//   chunk) address 8 different 16-byte bank groups of the Gram block (offset mod 8) where the list allows it.
+	// Word stream of one reduction pass (gramReduce / triGramReduce): `lists[k]` = the words of output key k (ascending keys = ascending lane
+	// index inside a chunk). Appended to `terms`:
+	// - every list is padded to a multiple of 8 words with padWord(key, class) (multiplicity 0), so that the 8 consecutive words a lane reads
+	//   belong to one key;
+	// - the keys are dealt to the `warps` warps as contiguous ranges of about equal length; every range starts on a multiple of 256 words and
+	//   is padded to whole chunks of 256 words: ranges[2 w] = {begin, end};
+	// - inside a list the words are ordered so that in every step k the lanes that are served together (a quarter warp for 16-byte entries,
+	//   classBits = 3; a half warp for 8-byte entries, classBits = 4; words 8 l + k of the group) address different bank groups of the
+	//   Gram block (offset mod 2^classBits) where the list allows it. Returns (sets, sum of conflict degrees) for the statistics.
+	template <typename PadWord>
+	std::pair<double, double> layoutReductionPass(std::vector<std::vector<unsigned>> &lists, int classBits, unsigned offsetMask, int warps, PadWord padWord,
+	                                                std::vector<unsigned> &terms, int *ranges)
+	{
+		const int classes = 1 << classBits, group = 8 * classes; // words served together per step: `classes` lanes x 8 words
+		const int nKeys = (int)lists.size();
+		std::vector<int> padded(nKeys, 0);
+		long total = 0;
+		for (int k = 0; k < nKeys; ++k) { padded[k] = ((int)lists[k].size() + 7) / 8 * 8; total += padded[k]; }
+		double sets = 0.0, degree = 0.0;
+		int key = 0; long done = 0;
+		for (int w = 0; w < warps; ++w)
+		{
+			while (terms.size() % 256) terms.push_back(0u);
+			const size_t begin = terms.size();
+			ranges[2 * w] = (int)begin;
+			const long target = (w + 1 == warps) ? total : total * (w + 1) / warps;
+			int lastKey = key < nKeys ? key : nKeys - 1;
+			while (key < nKeys && (done < target || padded[key] == 0))
+			{
+				std::vector<std::vector<unsigned>> byClass(classes);
+				for (unsigned word : lists[key]) byClass[(word & offsetMask) & (classes - 1)].push_back(word);
+				std::map<size_t, unsigned> used; // set id -> classes taken by this list
+				for (int i = 0; i < padded[key]; ++i)
+				{
+					const size_t pos = terms.size() - begin;
+					unsigned &mask = used[(pos / group) * 8 + pos % 8];
+					int best = -1;
+					for (int c = 0; c < classes; ++c)
+						if (!byClass[c].empty() && !(mask & (1u << c)) && (best < 0 || byClass[c].size() > byClass[best].size())) best = c;
+					if (best < 0) for (int c = 0; c < classes; ++c) if (!byClass[c].empty() && (best < 0 || byClass[c].size() > byClass[best].size())) best = c;
+					if (best >= 0) { terms.push_back(byClass[best].back()); byClass[best].pop_back(); mask |= 1u << best; }
+					else
+					{
+						int c = 0; while (c < classes - 1 && (mask & (1u << c))) ++c;
+						terms.push_back(padWord(key, c));
+						mask |= 1u << c;
+					}
+				}
+				done += padded[key]; lastKey = key; ++key;
+			}
+			while ((terms.size() - begin) % 256) terms.push_back(padWord(lastKey < 0 ? 0 : lastKey, 0));
+			ranges[2 * w + 1] = (int)terms.size();
+			for (size_t base = begin; base < terms.size(); base += group)
+				for (int k = 0; k < 8; ++k)
+				{
+					std::vector<int> count(classes, 0); int occupied = 0;
+					for (int l = 0; l < classes; ++l) ++count[(terms[base + 8 * l + k] & offsetMask) & (classes - 1)];
+					for (int c = 0; c < classes; ++c) occupied += count[c] > 0;
+					sets += 1.0; degree += (double)classes / occupied;
+				}
+		}
+		return { sets, degree };
+	}
+
+	// Term tables of gramReduce (SU2). For every block of PB rows of the Gram matrix: one pass of 32-bit words
+	//     (rid1 - block * PB) * (Lp + 1) + rid2  |  rid << 14  |  multiplicity << 22
+	// of the merged overlap terms (rid1, rid2, multiplicity) of all representative sites rid with rid1 in the block, laid out by
+	// layoutReductionPass: seg[2 * (block * warps + w)] = {begin, end} of the word range warp w reduces.
 	// conflictDegree (optional): average number of words per occupied bank group over all (chunk, quarter, step) sets; 1 = conflict free.
 	void buildGramTables(const pffrg_desc *d, int L, int Lp, int PB, int warps, std::vector<unsigned> &terms, std::vector<int> &seg, double *conflictDegree)
 	{
@@ -859,68 +981,69 @@ namespace
 		double sets = 0.0, degree = 0.0;
 		for (int blk = 0; blk < blocks; ++blk)
 		{
-			// the words of every rid in this block, by bank class
-			std::vector<std::vector<std::vector<unsigned>>> byClass(L, std::vector<std::vector<unsigned>>(8));
-			std::vector<int> padded(L, 0);
-			long total = 0;
+			std::vector<std::vector<unsigned>> lists(L);
 			for (int rid = 0; rid < L; ++rid)
-			{
-				int n = 0;
 				for (auto &kv : merged[rid])
 				{
 					const int p = std::get<0>(kv.first), q = std::get<3>(kv.first);
 					if (p / PB != blk) continue;
 					const unsigned offset = (unsigned)((p - blk * PB) * (Lp + 1) + q); // row stride of the Gram block: gramcfg::LpG
-					for (int m = kv.second; m > 0; m -= maxMult) { byClass[rid][offset & 7u].push_back(offset | ((unsigned)rid << 14) | ((unsigned)std::min(m, maxMult) << 22)); ++n; }
+					for (int m = kv.second; m > 0; m -= maxMult) lists[rid].push_back(offset | ((unsigned)rid << 14) | ((unsigned)std::min(m, maxMult) << 22));
 				}
-				padded[rid] = (n + 7) / 8 * 8;
-				total += padded[rid];
-			}
-			int rid = 0; long done = 0;
-			for (int w = 0; w < warps; ++w)
+			// padding words: multiplicity 0, a free bank class (offsets 0..7 exist: a block has at least 8 rows)
+			const auto stats = layoutReductionPass(lists, 3, (1u << 14) - 1u, warps, [](int rid, int c) { return (unsigned)c | ((unsigned)rid << 14); }, terms, seg.data() + (size_t)2 * blk * warps);
+			sets += stats.first; degree += stats.second;
+		}
+		if (conflictDegree) *conflictDegree = sets > 0 ? degree / sets : 1.0;
+	}
+
+	// Tables of the Gram form of the TRI RPA phase (rpaTriGram / triGramReduce, pffrg_kernels.cuh). The needed channel pairs (c1, c2) =
+	// ((p1 mu, p1 k), (p2 k, p2 nu)) over all overlap terms and (mu, k, nu) are worked off in rounds of `resident` blocks (most terms first):
+	// blocks[round * resident + slot] = c1 | c2 << 4 (0xffff: none). Per round one pass of words
+	//     slot * GBLK + rid1 * GS + rid2  |  out << 13  |  minus << 23  |  multiplicity << 24,      out = (4 mu + nu) * L + rid,
+	// with eta(mu,k,nu) = tri::rpa(mu,k,nu).sign (src/TRI/TRIFrgCore.cpp:739-1252; the factor 2 and the node weight are folded into the
+	// staged operand A) and terms of equal (block, rid1, rid2, out) merged.
+	void buildTriGramTables(const pffrg_desc *d, int L, int resident, int warps, std::vector<unsigned short> &blocks, std::vector<unsigned> &terms, std::vector<int> &seg, double *conflictDegree)
+	{
+		const int LT = (L + 7) / 8, LpT = 8 * LT, GS = LpT + 1, GBLK = LpT * GS;
+		// (c1 | c2 << 4) -> (rid1, rid2, out) -> signed multiplicity
+		std::map<int, std::map<std::tuple<int, int, int>, int>> byBlock;
+		for (int rid = 0; rid < L; ++rid)
+			for (auto &kv : mergedOverlap(d, TRI, rid))
 			{
-				while (terms.size() % 256) terms.push_back(0u); // (only after a range that was padded below: a no-op)
-				const size_t begin = terms.size();
-				seg[2 * ((size_t)blk * warps + w)] = (int)begin;
-				// rids of this warp: up to the next multiple of total / warps (the last warp takes the rest)
-				const long target = (w + 1 == warps) ? total : total * (w + 1) / warps;
-				int lastRid = rid < L ? rid : L - 1;
-				while (rid < L && (done < target || padded[rid] == 0))
+				const int r1 = std::get<0>(kv.first), p1 = std::get<1>(kv.first), p2 = std::get<2>(kv.first), r2 = std::get<3>(kv.first);
+				auto perm = [](int p, int i) { return i == 3 ? 3 : (p >> (2 * i)) & 3; };
+				for (int mu = 0; mu < 4; ++mu) for (int k = 0; k < 4; ++k) for (int nu = 0; nu < 4; ++nu)
 				{
-					// lay out the list of `rid` position by position; class masks of the (chunk, quarter, step) sets it touches
-					std::map<size_t, unsigned> used; // set id -> classes taken (by this list; sets shared with the previous list start empty: rare)
-					for (int i = 0; i < padded[rid]; ++i)
-					{
-						const size_t pos = terms.size() - begin;
-						const size_t set = (pos / 64) * 8 + pos % 8;
-						unsigned &mask = used[set];
-						int best = -1;
-						for (int c = 0; c < 8; ++c)
-							if (!byClass[rid][c].empty() && !(mask & (1u << c)) && (best < 0 || byClass[rid][c].size() > byClass[rid][best].size())) best = c;
-						if (best < 0) for (int c = 0; c < 8; ++c) if (!byClass[rid][c].empty() && (best < 0 || byClass[rid][c].size() > byClass[rid][best].size())) best = c;
-						if (best >= 0) { terms.push_back(byClass[rid][best].back()); byClass[rid][best].pop_back(); mask |= 1u << best; }
-						else
-						{
-							// padding word: multiplicity 0, a free bank class
-							int c = 0; while (c < 7 && (mask & (1u << c))) ++c;
-							terms.push_back((unsigned)c | ((unsigned)rid << 14)); // (offsets 0..7 exist: a block has at least 8 rows)
-							mask |= 1u << c;
-						}
-					}
-					done += padded[rid]; lastRid = rid; ++rid;
+					const int c1 = 4 * perm(p1, mu) + perm(p1, k), c2 = 4 * perm(p2, k) + perm(p2, nu);
+					byBlock[c1 | (c2 << 4)][std::make_tuple(r1, r2, (4 * mu + nu) * L + rid)] += (int)tri::rpa(mu, k, nu).sign * kv.second;
 				}
-				while ((terms.size() - begin) % 256) terms.push_back((unsigned)lastRid << 14);
-				seg[2 * ((size_t)blk * warps + w) + 1] = (int)terms.size();
-				// conflict statistics of this range
-				for (size_t base = begin; base < terms.size(); base += 64)
-					for (int k = 0; k < 8; ++k)
-					{
-						int count[8] = { 0 }, occupied = 0;
-						for (int l = 0; l < 8; ++l) ++count[terms[base + 8 * l + k] & 7u];
-						for (int c = 0; c < 8; ++c) occupied += count[c] > 0;
-						sets += 1.0; degree += 8.0 / occupied;
-					}
 			}
+		std::vector<int> order;
+		for (auto &kv : byBlock) order.push_back(kv.first);
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return byBlock[a].size() > byBlock[b].size(); });
+		const int rounds = ((int)order.size() + resident - 1) / resident;
+		blocks.assign((size_t)rounds * resident, (unsigned short)0xffff);
+		seg.assign((size_t)2 * rounds * warps, 0);
+		terms.clear();
+		double sets = 0.0, degree = 0.0;
+		for (int round = 0; round < rounds; ++round)
+		{
+			std::vector<std::vector<unsigned>> lists((size_t)16 * L);
+			for (int slot = 0; slot < resident && round * resident + slot < (int)order.size(); ++slot)
+			{
+				const int pair = order[round * resident + slot];
+				blocks[(size_t)round * resident + slot] = (unsigned short)pair;
+				for (auto &kv : byBlock[pair])
+				{
+					const int r1 = std::get<0>(kv.first), r2 = std::get<1>(kv.first), out = std::get<2>(kv.first);
+					const unsigned offset = (unsigned)(slot * GBLK + r1 * GS + r2);
+					for (int m = std::abs(kv.second); m > 0; m -= 255)
+						lists[out].push_back(offset | ((unsigned)out << 13) | ((kv.second < 0 ? 1u : 0u) << 23) | ((unsigned)std::min(m, 255) << 24));
+				}
+			}
+			const auto stats = layoutReductionPass(lists, 4, (1u << 13) - 1u, warps, [](int out, int c) { return (unsigned)c | ((unsigned)out << 13); }, terms, seg.data() + (size_t)2 * round * warps);
+			sets += stats.first; degree += stats.second;
 		}
 		if (conflictDegree) *conflictDegree = sets > 0 ? degree / sets : 1.0;
 	}
@@ -1032,7 +1155,11 @@ namespace
 		// feedback from the previous step's kernel times (multi-GPU runs; PFFRG_BALANCE=0 keeps the static split)
 		const bool feedback = h->nRanks > 1 && h->balance && (int)h->rankTimes.size() == h->nRanks && (int)h->bounds.size() == h->nRanks + 1;
 		const std::vector<int64_t> prev = h->bounds;
-		h->bounds = planPartition(h->core, h->nw, h->L, (double)h->uniquePairs, counts, h->nRanks, feedback ? &prev : nullptr, feedback ? &h->rankTimes : nullptr);
+		// RPA work per t-channel node in units of the cost model (overlap terms of the indexed forms)
+		double rpaTerms = (double)h->uniquePairs;
+		if (h->gramRows > 0 && h->core == SU2) rpaTerms = (double)h->L * h->L;
+		if (h->gramRows > 0 && h->core == TRI) { const double LpT = (double)((h->L + 7) / 8 * 8); rpaTerms = (double)h->triBlockCount * LpT * LpT * 2.0 / 128.0; }
+		h->bounds = planPartition(h->core, h->nw, h->L, rpaTerms, counts, h->nRanks, feedback ? &prev : nullptr, feedback ? &h->rankTimes : nullptr);
 	}
 
 	void fillStats(pffrg_context *h, const std::vector<int> &counts, int64_t begin, int64_t end)
@@ -1073,7 +1200,12 @@ namespace
 					const int64_t lo = std::max<int64_t>(begin, blk * nw), hi = std::min<int64_t>(end, (blk + 1) * nw);
 					if (hi > lo) phases += prefixR[hi - blk * nw] - prefixR[lo - blk * nw];
 				}
-			rpaFma = (double)nT * C * L * L + (double)phases * C * (double)h->uniquePairs;
+			if (h->core == TRI)
+			{
+				const double LpT = (double)((h->L + 7) / 8 * 8);
+				rpaFma = (double)nT * 2.0 * (double)h->triBlockCount * LpT * LpT + (double)phases * (double)h->gramWords;
+			}
+			else rpaFma = (double)nT * C * L * L + (double)phases * C * (double)h->uniquePairs;
 		}
 		h->stats.exec_flops = 2.0 * ((double)(nS + nU) * fmaSU + (double)nT * (16.0 * L * C + m.localTerms * L) + rpaFma);
 	}
@@ -1322,6 +1454,8 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	const int minNb = h->core == TRI ? 4 : 8;
 	const size_t smemTarget = h->core == TRI ? 200 * 1024 : 100 * 1024;
 	while (h->nb > minNb && flowSmemBytes(h->core, h->nb, h->nw, L, h->groups) > smemTarget) h->nb >>= 1;
+	// TRI core with the Gram form of the RPA phase (run-time compiled, rpaTriGram): gather batch = staged nodes = 8
+	if (h->core == TRI && wantTriGram(h->core) && !(jitEnv && atoi(jitEnv) == 0) && 16 * L <= 1024) h->nb = 8;
 	// PFFRG_NB: force the gather batch of the precompiled kernels (tests exercise every kernel variant on small lattices)
 	if (const char *e = getenv("PFFRG_NB")) { const int v = atoi(e); if ((v == 32 || v == 16 || v == 8 || (v == 4 && h->core == TRI)) && v <= h->nb) h->nb = v; }
 	h->smemBytes = flowSmemBytes(h->core, h->nb, h->nw, L, h->groups);
@@ -1383,7 +1517,7 @@ int pffrg_destroy(pffrg_handle h)
 	h->dV4b.release(); h->dSync.release(); h->dVecStaging.release(); h->dTimes.release();
 	if (h->hFlags) cudaFreeHost(h->hFlags);
 	h->dMesh.release(); h->dSitesRid.release(); h->dInvRid.release(); h->dSitesPerm.release(); h->dInvPerm.release(); h->dRngFwd.release(); h->dRngInv.release();
-	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release(); h->dMeshStart.release(); h->dGramTerms.release(); h->dGramSeg.release(); h->dSiteNewOf.release();
+	h->dSlotOff.release(); h->dTasks.release(); h->dWords.release(); h->dMeshStart.release(); h->dGramTerms.release(); h->dGramSeg.release(); h->dSiteNewOf.release(); h->dTriBlocks.release();
 	if (h->jitLibrary) cudaLibraryUnload(h->jitLibrary); h->dV4.release(); h->dFlow4.release(); h->dV2.release(); h->dFlow2.release(); h->dCutoff.release();
 	h->dCount.release(); h->dNodeW.release(); h->dNodeWt.release(); h->dNan.release(); h->dStaging.release();
 	h->dChiPartial.release(); h->dChi.release(); h->dChiCount.release();
@@ -1732,7 +1866,7 @@ void *pffrg_stream(pffrg_handle h) { return h ? (void *)h->stream : nullptr; }
 
 int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 {
-	if (!d || d->n_sites < 1 || d->n_sites > 256 || d->core < 0 || d->core > 1 || !d->overlap_offsets) return fail(PFFRG_ERR_ARGUMENT, "bad descriptor");
+	if (!d || d->n_sites < 1 || d->n_sites > 256 || d->core < 0 || d->core > 2 || !d->overlap_offsets) return fail(PFFRG_ERR_ARGUMENT, "bad descriptor");
 	// same launch configuration as pffrg_create
 	const int L = d->n_sites;
 	const char *jitEnv = getenv("PFFRG_JIT");
@@ -1742,6 +1876,21 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	d = &relabelled.view; // as pffrg_create
 	int64_t uniquePairs = 0;
 	for (int rid = 0; rid < L; ++rid) uniquePairs += (int64_t)mergedOverlap(d, d->core, rid).size();
+	if (d->core == TRI)
+	{
+		if (!wantTriGram(d->core)) return fail(PFFRG_ERR_UNSUPPORTED, "the TRI core has no run-time compiled kernel with PFFRG_RPA=table");
+		const int Lp = paddedSites(L);
+		const JitShape g = chooseTriGramShape(d->n_frequencies, L, groups, threads, 227 * 1024);
+		if (!g.nb) return fail(PFFRG_ERR_UNSUPPORTED, "the TRI Gram form does not fit this lattice");
+		std::vector<char> cubin;
+		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, triGramDefines(g));
+		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
+		std::vector<unsigned short> blocks; std::vector<unsigned> terms; std::vector<int> seg; double conflicts = 0.0;
+		buildTriGramTables(d, L, g.gramRows, threads / 32, blocks, terms, seg, &conflicts);
+		if (getenv("PFFRG_JIT_VERBOSE")) fprintf(stderr, "[pffrg tri gram] threads %d smem %zu resident blocks %d rounds %zu words %zu bank-conflict degree %.3f\n", threads, g.smem, g.gramRows, blocks.size() / g.gramRows, terms.size(), conflicts);
+		if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
+		return PFFRG_OK;
+	}
 	if (wantGram(d->core, uniquePairs))
 	{
 		const int Lp = paddedSites(L);
@@ -1843,6 +1992,18 @@ int pffrg_tri_terms(int region, int32_t *terms, int capacity)
 			}
 	if (!consistent) return fail(PFFRG_ERR_STATE, "TRI spin algebra produced an imaginary coefficient");
 	return n;
+}
+
+int pffrg_trigram_tables(const pffrg_desc *d, int resident, int warps, uint16_t *blocks, int blockCapacity, uint32_t *terms, int capacity, int32_t *seg, int segCapacity, int32_t *rounds)
+{
+	if (!d || d->n_sites < 1 || 16 * d->n_sites > 1024 || !d->overlap_offsets || resident < 1 || warps < 1 || warps > 32 || !rounds) return fail(PFFRG_ERR_ARGUMENT, "bad argument");
+	std::vector<unsigned short> b; std::vector<unsigned> t; std::vector<int> s;
+	buildTriGramTables(d, d->n_sites, resident, warps, b, t, s);
+	*rounds = (int)(b.size() / resident);
+	if (blocks) std::copy(b.begin(), b.begin() + std::min<size_t>(b.size(), (size_t)std::max(blockCapacity, 0)), blocks);
+	if (terms) std::copy(t.begin(), t.begin() + std::min<size_t>(t.size(), (size_t)std::max(capacity, 0)), terms);
+	if (seg) std::copy(s.begin(), s.begin() + std::min<size_t>(s.size(), (size_t)std::max(segCapacity, 0)), seg);
+	return (int)t.size();
 }
 
 int pffrg_site_order(const pffrg_desc *d, int32_t *order)

@@ -29,6 +29,8 @@ namespace pffrg
 		const unsigned *rpa_words; // term stream of the generic RPA phase, see rpaGeneric
 		const unsigned *gram_terms; // Gram form of the RPA sum (rpaGram): words offset into the Gram block | rid << 14 | multiplicity << 22
 		const int2 *gram_seg;    // [blocks * warps] word range of (row block, warp), whole chunks of 256 words
+		const unsigned short *trigram_blocks; // TRI Gram form: channel pair c1 | c2 << 4 resident in (round, slot), 0xffff = none
+		int trigram_rounds;
 		int nrange;
 		const int *rng_fwd;      // [nrange]
 		const int *rng_inv;      // [nrange]
@@ -323,6 +325,25 @@ namespace pffrg
 	constexpr int TRI8_NBP = 9, TRI8_RID_STRIDE = 16 * TRI8_NBP + 1;
 	__host__ __device__ inline int tri8BufferStride(int L) { int bs = L * TRI8_RID_STRIDE; while ((bs & 7) != 4) ++bs; return bs; }
 
+#ifdef PFFRG_TRIGRAM
+	// Gram form of the TRI RPA phase (rpaTriGram below): geometry of the staged operands and of the resident blocks of the Gram matrix.
+	namespace trigram
+	{
+		constexpr int L = PFFRG_CONST_L;
+		constexpr int LT = (L + 7) / 8;                  // 8 x 8 tiles per dimension of one (c1, c2) block
+		constexpr int LpT = 8 * LT;                      // sites per channel in the staged operands (tiles never straddle a channel)
+		constexpr int KS = 16 * LpT + 4;                 // doubles per staged (node, buffer pair) row: = 4 mod 16, so the 4 rows x 4 sites a half warp
+		                                                 // reads in a fragment load fall into 16 different 8-byte banks
+		constexpr int GS = LpT + 1;                      // row stride of a resident block (odd: conflict-free accumulator stores)
+		constexpr int GBLK = LpT * GS;                   // doubles per resident block
+		constexpr int RES = PFFRG_TRIGRAM_RESIDENT;      // (c1, c2) blocks resident per round
+		constexpr int NW = PFFRG_GRAM_THREADS / 32;      // warps of the block update
+		constexpr int TILES = RES * LT * LT;             // tiles per round
+		constexpr int TPW = (TILES + NW - 1) / NW;       // tiles per warp
+		static_assert(RES * GBLK <= (1 << 13) && 16 * L <= 1024 && TPW <= 16, "TRI Gram geometry");
+	}
+#endif
+
 	template <int CORE, int NB>
 	struct FlowSmem
 	{
@@ -350,7 +371,9 @@ namespace pffrg
 			o = alignUp(o, 16);
 			privateBytes = o; o *= subs;
 			// the per-group partial sums of the epilogue reuse the staging area (dead by then)
-			const size_t stBytes = gramRows > 0 ? sizeof(double) * 2 * C * (Lp + 2) * (subs * nbt)
+			// TRI Gram form: gramRows = resident (c1, c2) blocks, Lp = sites per channel of the staged operands (trigram::LpT)
+			const size_t stBytes = (gramRows > 0 && CORE == TRI) ? sizeof(double) * 2 * (2 * (size_t)nbt) * (16 * Lp + 4)
+			                     : gramRows > 0 ? sizeof(double) * 2 * C * (Lp + 2) * (subs * nbt)
 			                     : (CORE == TRI && NB == 8) ? sizeof(double) * 4 * tri8BufferStride(L) : sizeof(double) * RpaStage<CORE>::buffers * C * L * (subs * nbt + 1);
 			partStride = sizeof(double) * groups * C * L;
 			const size_t partBytes = partStride * subs;
@@ -361,7 +384,7 @@ namespace pffrg
 			rpa = o; o += sizeof(double) * C * L * rpaCopies;
 			staged = o; if (subs > 1) o += sizeof(int) * 4; // nodes staged by each sub-CTA for the coming RPA phase
 			o = alignUp(o, 16);
-			gram = o; o += gramRows > 0 ? sizeof(double) * C * (size_t)gramRows * (Lp + 1) : 0; // strides: gramcfg::LpS, gramcfg::LpG
+			gram = o; o += gramRows <= 0 ? 0 : CORE == TRI ? sizeof(double) * (size_t)gramRows * Lp * (Lp + 1) : sizeof(double) * C * (size_t)gramRows * (Lp + 1); // strides: gramcfg::LpS, gramcfg::LpG / trigram::GS
 			total = alignUp(o, 16);
 		}
 	};
@@ -739,6 +762,16 @@ namespace pffrg
 					triChaliceApply(A0, wmat + (node * 4 + 2 * pr) * 32, K);
 					triInverseChaliceApply(A1, wmat + (node * 4 + 2 * pr + 1) * 32, K);
 					// RPA operands of the pairs (0,1) and (2,3); the prefactor 2 (TRIFrgCore.cpp:741-746) and the node weight are folded into A
+#ifdef PFFRG_TRIGRAM
+					if (true)
+					{
+						// node-major rows st[operand][node * 2 + pair][channel][LpT]: lanes = sites, coalesced 8-byte stores
+						double *s0 = st + (size_t)(node * 2 + pr) * trigram::KS + j, *s1 = s0 + (size_t)(2 * NB) * trigram::KS;
+						#pragma unroll
+						for (int c = 0; c < 16; ++c) { s0[c * trigram::LpT] = 2.0 * W * A0[c]; s1[c * trigram::LpT] = A1[c]; }
+					}
+					else
+#endif
 					if (NB == 8)
 					{
 						double *s0 = st + (2 * pr) * tri8BufferStride(L) + j * TRI8_RID_STRIDE + node, *s1 = s0 + tri8BufferStride(L);
@@ -1039,7 +1072,7 @@ namespace pffrg
 		}
 	}
 
-#if defined(PFFRG_JIT_RPA) && !defined(PFFRG_GRAM)
+#if defined(PFFRG_JIT_RPA) && !defined(PFFRG_GRAM) && !defined(PFFRG_TRIGRAM)
 	// generated per lattice (pffrg_jit.cpp): the RPA sum of one batch for the outputs owned by `warp`
 	static __device__ __forceinline__ void rpaSpecialised(int warp, int lane, int nb, const double *st, double *rpaOut);
 #endif
@@ -1348,6 +1381,142 @@ namespace pffrg
 	}
 #endif
 
+#ifdef PFFRG_TRIGRAM
+	// ================================================================================================================
+	// Gram form of the TRI RPA phase (run-time compiled TRI kernel). The reference evaluates, per quadrature node and for the buffer pairs
+	// (0,1) and (2,3), R^{mu nu}[rid] = sum_i sum_k 2 eta(mu,k,nu) A^{p1 mu, p1 k}[rid1_i] B^{p2 k, p2 nu}[rid2_i] over the overlap list
+	// (src/TRI/TRIFrgCore.cpp:733-1252; p1, p2 the overlap's spin permutations): 128 indexed multiply-adds per overlap term and node, bound
+	// by shared-memory bandwidth in rpaTri8. As for SU2 the sums over the nodes AND over the two buffer pairs commute with the lattice sum:
+	//     sum_{node, pair} R[...] = sum_i sum_k eta G^{(c1, c2)}[rid1_i][rid2_i],   G^{(c1,c2)}[p][q] = sum_{node, pair} A^{c1}[p] B^{c2}[q],
+	// c1 = (p1 mu, p1 k), c2 = (p2 k, p2 nu). Only the channel pairs (c1, c2) the lattice's permutations produce are needed (96 of 256 on
+	// kagome-DM: 111 k multiply-adds per node and pair as dense 8x8x4 tensor-core updates instead of 159 k indexed ones). The needed blocks
+	// are worked off in rounds of RES resident blocks: update (K = staged nodes x 2 pairs) -> store -> reduce with signed term words
+	// (offset | output << 13 | sign << 23 | multiplicity << 24; triGramReduce) -> next round.
+	// ================================================================================================================
+	__device__ __forceinline__ void dmmaTri(double &d0, double &d1, double a, double b)
+	{
+		asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+	}
+
+	// as gramReduce, for scalar entries and signed words; outputs rpaOut[out], out = channel * L + rid. A lane's 8 words belong to one output.
+	__device__ __forceinline__ void triGramReduce(const Problem &P, int round, const double *__restrict__ Gs, double *rpaOut, int warp, int lane, int warps)
+	{
+		const int2 range = __ldg(P.gram_seg + round * warps + warp);
+		const int chunks = (range.y - range.x) >> 8;
+		if (chunks <= 0) return;
+		const uint4 *words = reinterpret_cast<const uint4 *>(P.gram_terms + range.x) + 2 * lane;
+		uint4 n[2][2];
+		#pragma unroll
+		for (int u = 0; u < 2; ++u) if (u < chunks) { n[u][0] = __ldg(words + 64 * u); n[u][1] = __ldg(words + 64 * u + 1); }
+		#pragma unroll 1
+		for (int c = 0; c < chunks; c += 2)
+		{
+			int out[2]; double sum[2];
+			const bool second = c + 1 < chunks;
+			uint4 w4[2][2];
+			#pragma unroll
+			for (int u = 0; u < 2; ++u) { w4[u][0] = n[u][0]; w4[u][1] = n[u][1]; }
+			#pragma unroll
+			for (int u = 0; u < 2; ++u) if (c + 2 + u < chunks) { n[u][0] = __ldg(words + 64 * (c + 2 + u)); n[u][1] = __ldg(words + 64 * (c + 2 + u) + 1); }
+			#pragma unroll
+			for (int u = 0; u < 2; ++u)
+			{
+				const unsigned w[8] = { w4[u][0].x, w4[u][0].y, w4[u][0].z, w4[u][0].w, w4[u][1].x, w4[u][1].y, w4[u][1].z, w4[u][1].w };
+				out[u] = (int)((w[0] >> 13) & 1023u);
+				double g[8];
+				#pragma unroll
+				for (int k = 0; k < 8; ++k) g[k] = Gs[(u == 0 || second) ? (w[k] & 8191u) : 0u];
+				double a = 0.0, b = 0.0;
+				#pragma unroll
+				for (int k = 0; k < 8; k += 2)
+				{
+					// signed multiplicity: bit 23 = minus
+					const double m0 = (double)((int)(w[k] >> 24) * (1 - 2 * (int)((w[k] >> 23) & 1u))), m1 = (double)((int)(w[k + 1] >> 24) * (1 - 2 * (int)((w[k + 1] >> 23) & 1u)));
+					a = fma(m0, g[k], a); b = fma(m1, g[k + 1], b);
+				}
+				sum[u] = a + b;
+			}
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				#pragma unroll
+				for (int u = 0; u < 2; ++u)
+				{
+					const double o = __shfl_up_sync(0xffffffffu, sum[u], d);
+					const int oo = __shfl_up_sync(0xffffffffu, out[u], d);
+					if (lane >= d && oo == out[u]) sum[u] += o;
+				}
+			}
+			#pragma unroll
+			for (int u = 0; u < 2; ++u)
+			{
+				const int next = __shfl_down_sync(0xffffffffu, out[u], 1);
+				if ((u == 0 || second) && (lane == 31 || next != out[u])) rpaOut[out[u]] += sum[u];
+				__syncwarp();
+			}
+		}
+	}
+
+	// RPA phase over `nb` staged nodes (all threads of the CTA; CTA barriers inside). P.trigram_blocks[round * RES + slot] = c1 | c2 << 4 of the
+	// block resident in `slot` during `round` (0xffff: none); P.trigram_rounds rounds.
+	__device__ __forceinline__ void rpaTriGram(const Problem &P, const double *__restrict__ st, int nodeCapacity, int nb, double *__restrict__ Gs, double *rpaOut)
+	{
+		using namespace trigram;
+		const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = blockDim.x >> 5;
+		const bool gemm = warp < NW;
+		const int fr = lane >> 2, fk = lane & 3;
+		const double *stA = st, *stB = st + (size_t)(2 * nodeCapacity) * KS;
+		const int kEnd = 2 * nb; // staged rows: node * 2 + pair
+		#pragma unroll 1
+		for (int round = 0; round < P.trigram_rounds; ++round)
+		{
+			if (gemm)
+			{
+				// this warp's tiles: a contiguous range of the (slot, row tile, column tile) list, so that consecutive tiles share operand A
+				double acc[TPW][2];
+				int offA[TPW], offB[TPW], store[TPW];
+				#pragma unroll
+				for (int i = 0; i < TPW; ++i)
+				{
+					const int t = warp * TPW + i;
+					acc[i][0] = 0.0; acc[i][1] = 0.0;
+					const int slot = t / (LT * LT), rem = t - slot * (LT * LT), ti = rem / LT, tj = rem - ti * LT;
+					const int pair = (t < TILES) ? (int)__ldg(P.trigram_blocks + round * RES + slot) : 0xffff;
+					if (pair == 0xffff) { offA[i] = -1; offB[i] = 0; store[i] = 0; continue; }
+					offA[i] = (pair & 15) * LpT + 8 * ti + fr;
+					offB[i] = (pair >> 4) * LpT + 8 * tj + fr;
+					store[i] = slot * GBLK + (8 * ti + fr) * GS + 8 * tj + 2 * fk;
+				}
+				#pragma unroll 1
+				for (int k0 = 0; k0 < kEnd; k0 += 4)
+				{
+					const bool live = k0 + fk < kEnd;
+					const double *A = stA + (size_t)(k0 + fk) * KS, *B = stB + (size_t)(k0 + fk) * KS;
+					double a = 0.0; int loaded = -2;
+					#pragma unroll
+					for (int i = 0; i < TPW; ++i)
+					{
+						if (offA[i] < 0) continue; // warp-uniform
+						if (offA[i] != loaded) { a = live ? A[offA[i]] : 0.0; loaded = offA[i]; }
+						const double b = live ? B[offB[i]] : 0.0;
+						dmmaTri(acc[i][0], acc[i][1], a, b);
+					}
+				}
+				__syncthreads(); // the reduction of the previous round has read Gs
+				#pragma unroll
+				for (int i = 0; i < TPW; ++i)
+				{
+					if (offA[i] < 0) continue;
+					Gs[store[i]] = acc[i][0]; Gs[store[i] + 1] = acc[i][1];
+				}
+			}
+			else __syncthreads();
+			__syncthreads();
+			triGramReduce(P, round, Gs, rpaOut, warp, lane, warps);
+		}
+	}
+#endif
+
 	// SUB > 1 (run-time compiled kernel only): the CTA is made of SUB independent sub-CTAs, each working on its own item
 	// (consecutive items) with its own tables and its own barriers; they meet only for the RPA phase, which then runs ONE pass
 	// of the straight-line code over the nodes staged by all of them. The code of that phase is streamed through the
@@ -1367,6 +1536,10 @@ namespace pffrg
 		static_assert(CORE == SU2 && SUB == 1 && CL == 1 && JIT, "the Gram form of the RPA phase exists for the SU2 core, one work item per CTA");
 		constexpr bool GRAM = true;
 		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT, SUB, gramcfg::PB, gramcfg::Lp);
+#elif defined(PFFRG_TRIGRAM)
+		static_assert(CORE == TRI && SUB == 1 && CL == 1 && JIT && NBT == NB, "the TRI Gram form stages one gather batch per RPA phase");
+		constexpr bool GRAM = false;
+		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT, SUB, trigram::RES, trigram::LpT);
 #else
 		constexpr bool GRAM = false;
 		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT, SUB);
@@ -1394,6 +1567,14 @@ namespace pffrg
 		// padding sites of the node-major staging rows: read by the Gram update (their products are never used), never written below
 		for (int i = threadIdx.x; i < 2 * NBTT * (gramcfg::LpS - L); i += blockDim.x)
 			reinterpret_cast<double2 *>(st)[(i / (gramcfg::LpS - L)) * gramcfg::LpS + L + i % (gramcfg::LpS - L)] = make_double2(0.0, 0.0);
+#endif
+#ifdef PFFRG_TRIGRAM
+		// padding sites [L, LpT) of every staged channel row (and the 4 doubles between the rows): read by the fragment loads, never written
+		for (int i = threadIdx.x; i < 2 * 2 * NBTT * trigram::KS; i += blockDim.x)
+		{
+			const int within = i % trigram::KS;
+			if (within >= 16 * trigram::LpT || within % trigram::LpT >= L) st[i] = 0.0;
+		}
 #endif
 
 		// work item -> (s, t, u), expandIterator SU2VertexTwoParticle.hpp:136-158
@@ -1652,6 +1833,9 @@ namespace pffrg
 				// ---- phase 2: RPA lattice sum over the staged nodes (of all sub-CTAs)
 #ifdef PFFRG_GRAM
 				if (GRAM) rpaGram(P, reinterpret_cast<const double2 *>(st), NBTT, staged, reinterpret_cast<double2 *>(smemRaw + lay.gram), rpaOut);
+				else
+#elif defined(PFFRG_TRIGRAM)
+				if (JIT) rpaTriGram(P, st, NBTT, staged, reinterpret_cast<double *>(smemRaw + lay.gram), rpaOut);
 				else
 #elif defined(PFFRG_JIT_RPA)
 				if (JIT)

@@ -38,7 +38,9 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             {"PFFRG_RPA": "gram", "PFFRG_THREADS": "512", "PFFRG_GRAM_TM": "1"}, {"PFFRG_RPA": "gram", "PFFRG_THREADS": "96", "PFFRG_JIT_NBT": "8", "PFFRG_JIT_NB": "8"},
             {"PFFRG_RPA": "gram", "PFFRG_GRAM_TM": "1", "PFFRG_JIT_MINBLOCKS": "1"},
             # t-major CTA -> work item map (CTAs that run at the same time share the transfer frequency t)
-            {"PFFRG_ORDER": "t", "PFFRG_CLUSTER": "1"}, {"PFFRG_ORDER": "t", "PFFRG_RPA": "gram"}]
+            {"PFFRG_ORDER": "t", "PFFRG_CLUSTER": "1"}, {"PFFRG_ORDER": "t", "PFFRG_RPA": "gram"},
+            # TRI: the table-driven RPA phase of the precompiled kernels instead of the Gram form; Gram form with 1 / 2 resident blocks
+            {"PFFRG_RPA": "table"}, {"PFFRG_TRIGRAM_RESIDENT": "1"}, {"PFFRG_TRIGRAM_RESIDENT": "2", "PFFRG_THREADS": "128"}]
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
@@ -46,14 +48,20 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
 def test_one_step_flow_matches_reference(case, variant, monkeypatch):
     if case.startswith("tri") and ("PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant or "PFFRG_SUBCTAS" in variant or "PFFRG_CLUSTER" in variant or "PFFRG_MIRROR" in variant):
         pytest.skip("the TRI core has no run-time compiled variant")
-    if "PFFRG_RPA" in variant and not case.startswith("su2"):
-        pytest.skip("the Gram form of the RPA phase exists for the SU2 core")
+    if "PFFRG_RPA" in variant and case.startswith("xyz"):
+        pytest.skip("the XYZ core has one form of the RPA phase")
+    if case.startswith("tri") and variant.get("PFFRG_RPA") == "gram" and len(variant) > 1:
+        pytest.skip("SU2 shape knobs")
+    if not case.startswith("tri") and (variant.get("PFFRG_RPA") == "table" or "PFFRG_TRIGRAM_RESIDENT" in variant):
+        pytest.skip("TRI only")
     for k, x in variant.items():
         monkeypatch.setenv(k, x)
     d = golden(case)
     name, core = _core(d)
-    if variant.get("PFFRG_RPA") == "gram":
-        assert core.stats()["jit_rpa"] == 1
+    if variant.get("PFFRG_RPA") == "gram" or (case.startswith("tri") and (not variant or "PFFRG_TRIGRAM_RESIDENT" in variant)):
+        assert core.stats()["jit_rpa"] == 1 and core.stats()["gram_rows"] > 0
+    if variant.get("PFFRG_RPA") == "table" or variant.get("PFFRG_JIT") == "0":
+        assert core.stats()["gram_rows"] == 0
     n = core.n_arrays
     cut = d["cutoff"]
     for step in dumped_steps(d):

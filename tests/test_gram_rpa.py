@@ -158,3 +158,68 @@ def test_device_site_order_pairs_inverted_sites(case):
         assert abs(a - b) <= 1, "pair members are neighbours"
         straddling += a // 8 != b // 8
     assert straddling <= max(2, moved // 8), (straddling, moved)
+
+
+@pytest.mark.parametrize("case,resident,warps", [("tri_kagome_dm_r3_nw6", 3, 8), ("tri_honeycomb_kg_r3_nw8", 2, 8), ("tri_kagome_dm_r3_nw6", 16, 4)])
+def test_tri_gram_tables_reproduce_the_overlap_sum(case, resident, warps):
+    """TRI: R^{mu nu}[rid] = sum_i sum_k eta(mu,k,nu) A^{p1 mu,p1 k}[rid1_i] B^{p2 k,p2 nu}[rid2_i] (the loop rpaTri8 walks, eta from the
+    spin algebra the kernels use) against the Gram blocks G^{(c1,c2)} = sum_rows A^{c1} (x) B^{c2} reduced with the signed term words of
+    pffrg_trigram_tables, walked chunk by chunk and lane by lane like triGramReduce."""
+    from spinparser_b200 import ProblemTables, _capi
+    from spinparser_b200.frgcore import make_descriptor
+    d = golden(case)
+    t = ProblemTables.from_pfd(d)
+    L = t.n_sites
+    LpT = (L + 7) // 8 * 8
+    GS, GBLK = LpT + 1, LpT * (LpT + 1)
+    desc = make_descriptor("TRI", t)
+    rounds = C.c_int32(0)
+    n = _capi.check(_capi.lib.pffrg_trigram_tables(C.byref(desc), resident, warps, None, 0, None, 0, None, 0, C.byref(rounds)))
+    blocks = np.zeros(rounds.value * resident, dtype=np.uint16)
+    terms = np.zeros(n, dtype=np.uint32)
+    seg = np.zeros(2 * rounds.value * warps, dtype=np.int32)
+    assert _capi.lib.pffrg_trigram_tables(C.byref(desc), resident, warps, blocks.ctypes.data_as(C.POINTER(C.c_uint16)), len(blocks), terms.ctypes.data_as(C.POINTER(C.c_uint32)), n,
+                                          seg.ctypes.data_as(C.POINTER(C.c_int32)), len(seg), C.byref(rounds)) == n
+    seg = seg.reshape(rounds.value * warps, 2)
+    # eta(mu, k, nu) as the kernels derive it (region 4 of pffrg_tri_terms: rows {out, sign, 4 mu + k, 4 k + nu})
+    rows = np.zeros((64, 4), dtype=np.int32)
+    assert _capi.lib.pffrg_tri_terms(4, rows.ctypes.data_as(C.POINTER(C.c_int32)), 64) == 64
+    eta = {(int(r[2]) // 4, int(r[2]) % 4, int(r[3]) % 4): int(r[1]) for r in rows}
+    rng = np.random.default_rng(11)
+    K = 6
+    A = rng.uniform(-1, 1, (K, 16, LpT)); B = rng.uniform(-1, 1, (K, 16, LpT))
+    A[:, :, L:] = 0.0; B[:, :, L:] = 0.0
+    want = np.zeros(16 * L)
+    off, r1, r2, p1, p2 = t.overlap_offsets, t.overlap_rid1, t.overlap_rid2, t.overlap_perm1, t.overlap_perm2
+    perm = lambda p, i: 3 if i == 3 else int(p[i])
+    for rid in range(L):
+        for i in range(off[rid], off[rid + 1]):
+            for mu in range(4):
+                for k in range(4):
+                    for nu in range(4):
+                        c1, c2 = 4 * perm(p1[i], mu) + perm(p1[i], k), 4 * perm(p2[i], k) + perm(p2[i], nu)
+                        want[(4 * mu + nu) * L + rid] += eta[(mu, k, nu)] * float(np.dot(A[:, c1, r1[i]], B[:, c2, r2[i]]))
+    got = np.zeros(16 * L)
+    for rnd in range(rounds.value):
+        Gs = np.full(resident * GBLK, np.nan)
+        for slot in range(resident):
+            pair = int(blocks[rnd * resident + slot])
+            if pair == 0xFFFF:
+                continue
+            G = np.einsum("kp,kq->pq", A[:, pair & 15, :], B[:, pair >> 4, :])
+            for p in range(LpT):
+                Gs[slot * GBLK + p * GS:slot * GBLK + p * GS + LpT] = G[p]
+        owner = {}
+        for w in range(warps):
+            begin, end = seg[rnd * warps + w]
+            assert begin % 256 == 0 and (end - begin) % 256 == 0
+            for pos in range(begin, end, 8):
+                wd = terms[pos:pos + 8].astype(np.int64)
+                out = int((wd[0] >> 13) & 1023)
+                mult = (wd >> 24) * (1 - 2 * ((wd >> 23) & 1))
+                assert np.all(((wd >> 13) & 1023)[mult != 0] == out)
+                assert owner.setdefault(out, w) == w or not mult.any()
+                g = Gs[wd & 8191]
+                assert not np.isnan(g[mult != 0]).any()
+                got[out] += float(np.sum(np.where(mult != 0, mult * np.nan_to_num(g), 0.0)))
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12), np.abs(got - want).max()
