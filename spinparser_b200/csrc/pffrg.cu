@@ -477,11 +477,15 @@ namespace
 	{
 		return "#define PFFRG_TRIGRAM 1\n#define PFFRG_TRIGRAM_RESIDENT " + std::to_string(s.gramRows) + "\n#define PFFRG_GRAM_THREADS " + std::to_string(s.gramThreads) + "\n";
 	}
+	// Off by default: measured on B200 (kagome-DM r7, Nw 64) the Gram form takes 1249 ms per step against 993 ms of the table-driven phase.
+	// A TRI node stages 20 KB of operands, so only 8 nodes (K = 16 with the two buffer pairs) fit per RPA phase next to 3 of the 96 needed
+	// channel-pair blocks: 32 rounds of update -> store -> reduce per phase with 4 tensor-core steps each, and the per-round instruction
+	// overhead (ncu: 790 warp instructions per 40 DMMA, 625 in the reduction) outweighs the saved multiply-adds. PFFRG_RPA=gram selects it.
 	bool wantTriGram(int core)
 	{
 		if (core != TRI) return false;
 		const char *form = getenv("PFFRG_RPA");
-		return form ? std::string(form) == "gram" : true;
+		return form && std::string(form) == "gram";
 	}
 
 	int compileCandidate(pffrg_context *h, const pffrg_desc *d, JitCandidate &c)

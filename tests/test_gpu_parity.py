@@ -40,7 +40,7 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             # t-major CTA -> work item map (CTAs that run at the same time share the transfer frequency t)
             {"PFFRG_ORDER": "t", "PFFRG_CLUSTER": "1"}, {"PFFRG_ORDER": "t", "PFFRG_RPA": "gram"},
             # TRI: the table-driven RPA phase of the precompiled kernels instead of the Gram form; Gram form with 1 / 2 resident blocks
-            {"PFFRG_RPA": "table"}, {"PFFRG_TRIGRAM_RESIDENT": "1"}, {"PFFRG_TRIGRAM_RESIDENT": "2", "PFFRG_THREADS": "128"}]
+            {"PFFRG_RPA": "table"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "1"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "2", "PFFRG_THREADS": "128"}]
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
@@ -50,7 +50,7 @@ def test_one_step_flow_matches_reference(case, variant, monkeypatch):
         pytest.skip("the TRI core has no run-time compiled variant")
     if "PFFRG_RPA" in variant and case.startswith("xyz"):
         pytest.skip("the XYZ core has one form of the RPA phase")
-    if case.startswith("tri") and variant.get("PFFRG_RPA") == "gram" and len(variant) > 1:
+    if case.startswith("tri") and variant.get("PFFRG_RPA") == "gram" and len(variant) > 1 and "PFFRG_TRIGRAM_RESIDENT" not in variant:
         pytest.skip("SU2 shape knobs")
     if not case.startswith("tri") and (variant.get("PFFRG_RPA") == "table" or "PFFRG_TRIGRAM_RESIDENT" in variant):
         pytest.skip("TRI only")
@@ -58,7 +58,7 @@ def test_one_step_flow_matches_reference(case, variant, monkeypatch):
         monkeypatch.setenv(k, x)
     d = golden(case)
     name, core = _core(d)
-    if variant.get("PFFRG_RPA") == "gram" or (case.startswith("tri") and (not variant or "PFFRG_TRIGRAM_RESIDENT" in variant)):
+    if variant.get("PFFRG_RPA") == "gram":
         assert core.stats()["jit_rpa"] == 1 and core.stats()["gram_rows"] > 0
     if variant.get("PFFRG_RPA") == "table" or variant.get("PFFRG_JIT") == "0":
         assert core.stats()["gram_rows"] == 0

@@ -31,7 +31,7 @@ WORKLOADS = {
     "cubic_r7_su2_nw64": (211, [], [{}, {"PFFRG_AUTOTUNE": "1"}, {"PFFRG_RPA": "gram"}]),
     "honeycomb_kitaev_r7_xyz_nw64": (211, [], [{}, {"PFFRG_AUTOTUNE": "1"}]),
     "pyrochlore_r8_su2_nw64": (211, [], [{}, {"PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}]),
-    "kagome_dm_r7_tri_nw64": (120, [211], [{}]),
+    "kagome_dm_r7_tri_nw64": (120, [211], [{}, {"PFFRG_RPA": "gram"}]),
 }
 
 
