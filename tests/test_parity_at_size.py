@@ -96,13 +96,15 @@ def test_flow_at_benchmark_size_matches_reference(workload, monkeypatch):
     state = core.flowingFunctional()
     assert state.cutoff == cutoffs[state_step] and not state.isDiverged()
     report = {}
+    current = variants[0]
     for step in [state_step] + extra_steps:
         want2, want4, what = reference_flow_rows(workload, d, step, state.v2, state.v4, items)
         for k, env in enumerate(variants):
             if k > 0 or step != state_step:
-                if k > 0:
+                if env != current:
                     core.close()
                     name, core = _core(d, env, monkeypatch)
+                    current = env
                 core.setState(cutoffs[step], state.v2, state.v4)
             assert not core.computeStep()
             flow = core.flow()
