@@ -495,6 +495,9 @@ namespace pffrg
 #ifndef PFFRG_MERGED_TABLES
 #define PFFRG_MERGED_TABLES 0 // run-time compiled kernel: access buffers in one step (every buffer does its own two mesh searches)
 #endif
+#ifndef PFFRG_FUSED_LOCALS
+#define PFFRG_FUSED_LOCALS 0 // run-time compiled SU2 / XYZ kernel: the thread that assembles a site-0 buffer also forms its site-0 values (one barrier phase less per t batch)
+#endif
 #ifndef PFFRG_PIPELINE
 #define PFFRG_PIPELINE 0 // run-time compiled SU2 kernel: row loads of the next quadrature node in flight while the current one is combined
 #endif
@@ -1694,10 +1697,35 @@ namespace pffrg
 					const int node = idx / nbuf, b = idx - node * nbuf;
 					const int ch = tPass ? CH_T : ((b0 + node) < nFirst ? CH_S : CH_U);
 					assembleAccessBuffer<CORE>(nw, ch, b, ch == CH_S ? so : (ch == CH_T ? ti : uo), lerp + 4 * node, abTable[idx]);
+					if constexpr (CORE != TRI && PFFRG_FUSED_LOCALS != 0)
+					{
+						// site-0 values of the buffer just assembled (getValueLocal, phase 0b below): channel pairs of site 0 with 16-byte loads
+						if (tPass && b >= 4)
+						{
+							const AccessBuffer &ab = abTable[idx];
+							double v[C];
+							#pragma unroll
+							for (int c = 0; c < C; ++c) v[c] = 0.0;
+							#pragma unroll
+							for (int k = 0; k < 4; ++k)
+							{
+								const double2 *row = reinterpret_cast<const double2 *>(v4 + (size_t)ab.row[k] * sizeRL(P));
+								#pragma unroll
+								for (int pl = 0; pl < C / 2; ++pl)
+								{
+									const double2 x = __ldg(row + pl * sizeLp(P));
+									v[2 * pl] += supportSign<CORE>(ab.flags, k, 2 * pl) * ab.w[k] * x.x;
+									v[2 * pl + 1] += supportSign<CORE>(ab.flags, k, 2 * pl + 1) * ab.w[k] * x.y;
+								}
+							}
+							#pragma unroll
+							for (int c = 0; c < C; ++c) loc[(node * 4 + (b - 4)) * C + c] = v[c];
+						}
+					}
 				}
 #endif
 				subSync();
-				if (tPass)
+				if (tPass && !(CORE != TRI && PFFRG_FUSED_LOCALS != 0 && PFFRG_MERGED_TABLES == 0))
 				{
 					// ---- phase 0b: site-0 values of buffers 4..7 (getValueLocal)
 					for (int idx = tid; idx < nb * 4 * C; idx += nthreads)

@@ -40,13 +40,14 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             # t-major CTA -> work item map (CTAs that run at the same time share the transfer frequency t)
             {"PFFRG_ORDER": "t", "PFFRG_CLUSTER": "1"}, {"PFFRG_ORDER": "t", "PFFRG_RPA": "gram"},
             # TRI: the table-driven RPA phase of the precompiled kernels instead of the Gram form; Gram form with 1 / 2 resident blocks
+            {"PFFRG_FUSED_LOCALS": "1"}, {"PFFRG_FUSED_LOCALS": "1", "PFFRG_RPA": "gram"},
             {"PFFRG_RPA": "table"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "1"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "2", "PFFRG_THREADS": "128"}]
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
 @pytest.mark.parametrize("case", CASES)
 def test_one_step_flow_matches_reference(case, variant, monkeypatch):
-    if case.startswith("tri") and ("PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant or "PFFRG_SUBCTAS" in variant or "PFFRG_CLUSTER" in variant or "PFFRG_MIRROR" in variant):
+    if case.startswith("tri") and ("PFFRG_FUSED_LOCALS" in variant or "PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant or "PFFRG_SUBCTAS" in variant or "PFFRG_CLUSTER" in variant or "PFFRG_MIRROR" in variant):
         pytest.skip("the TRI core has no run-time compiled variant")
     if "PFFRG_RPA" in variant and case.startswith("xyz"):
         pytest.skip("the XYZ core has one form of the RPA phase")
@@ -190,4 +191,27 @@ def test_call_sequence_violations_are_reported():
     assert err.value.code == -4
     with pytest.raises(PffrgError):
         core.setState(1.0, np.zeros(3), [np.zeros(5), np.zeros(5)])  # wrong sizes are rejected on the host side
+    core.close()
+
+
+@pytest.mark.parametrize("case", ["su2_square_r3_nw10", "xyz_honeycomb_kitaev_r3_nw10", "tri_kagome_dm_r3_nw6"])
+def test_divergence_is_reported(case):
+    """A vertex that overflows in the flow equations: compute_step reports `diverged` (the reference finds NaN in `_flow`,
+    SU2EffectiveAction.hpp:212-230, and stops the loop, SpinParser.cpp:151-155); a finite state does not."""
+    d = golden(case)
+    name, core = _core(d)
+    n = core.n_arrays
+    step = dumped_steps(d)[-1]
+    pre = f"step{step}/"
+    v2 = np.ascontiguousarray(d[pre + "state/v2"])
+    v4 = [np.ascontiguousarray(d[pre + f"state/v4_{c}"]) for c in range(n)]
+    core.setState(float(d[pre + "state/cutoff"]), v2, v4)
+    assert core.computeStep() is False
+    core.setState(float(d[pre + "state/cutoff"]), v2, [a * 1e160 for a in v4])
+    assert core.computeStep() is True
+    flow = core.flow()
+    assert any(np.isnan(a).any() for a in flow.v4)
+    # and the core recovers with a finite state
+    core.setState(float(d[pre + "state/cutoff"]), v2, v4)
+    assert core.computeStep() is False
     core.close()

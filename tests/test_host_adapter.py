@@ -186,3 +186,40 @@ def test_two_ranks_through_the_adapter(tmp_path):
             assert np.array_equal(np.asarray(got0[k]), np.asarray(got1[k])), k
             b = np.asarray(want[k])
             assert np.abs(np.asarray(got0[k]) - b).max() <= 1e-9 * np.abs(b).max() + 1e-300, k
+
+
+def _diverging_task(tmp_path):
+    """The first golden task with a coupling large enough to overflow the flow equations in the first step."""
+    text = open(os.path.join(GOLDEN, "tasks", CASES[0] + ".xml")).read().replace("<j>1.0</j>", "<j>1.0e160</j>")
+    assert "1.0e160" in text
+    path = tmp_path / "diverging.xml"
+    path.write_text(text)
+    return str(path)
+
+
+def _run_task(binary, task, backend, tmp_path):
+    from spinparser_b200.pfd import read_pfd
+    out = str(tmp_path / f"diverging.{backend}.pfd")
+    env = dict(os.environ, SPINPARSER_BACKEND=backend)
+    proc = subprocess.run([os.path.join(REF, binary), "-r", os.path.join(ROOT, "oracle", "res"), task, "--out", out, "--no-lattice"], env=env, cwd=str(tmp_path), capture_output=True, text=True)
+    return proc, (read_pfd(out) if proc.returncode == 0 else None)
+
+
+def test_diverging_flow_stops_the_stock_driver(tmp_path):
+    proc, got = _run_task("spinparser64_b200", _diverging_task(tmp_path), "cpu", tmp_path)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert int(got["divergedAtStep"]) == 0 and int(got["finalStep"]) == 0
+
+
+@pytest.mark.gpu
+def test_diverging_flow_stops_the_driver_with_gpu_cores(tmp_path):
+    """`diverged` of pffrg_compute_step -> NaN in `_flow` -> `_flow->isDiverged()` ends the loop (SpinParser.cpp:151-155) at the same step as
+    with the stock cores; the final measurement / state dump read the synchronised host arrays."""
+    task = _diverging_task(tmp_path)
+    proc, got = _run_task("spinparser64_b200", task, "b200", tmp_path)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert int(got["divergedAtStep"]) == 0 and int(got["finalStep"]) == 0
+    proc, want = _run_task("spinparser64_b200", task, "cpu", tmp_path)
+    for k in want:
+        if k.startswith("final/v"):
+            assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k

@@ -87,6 +87,25 @@ if rank == 0:
         err = np.abs(flow.v4[c] - want)
         assert (err <= 1e-10 * np.abs(want) + 1e-12 * np.abs(want).max()).all(), "sharded flow differs from the reference dump"
     print("MULTI_GPU_OK", world, name, [r[0] for r in all_ranges])
+# divergence on ONE rank's slice must be reported by ALL ranks (the NaN flag is max-reduced; the reference's ranks all see the
+# broadcast flow and stop together, SpinParser.cpp:151-155)
+core = FrgCoreFactory.newFrgCore(name, ProblemTables.from_pfd(d), opts, device=local)
+ids = [core.uniqueId() if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+core.initCommunicator(ids[0], rank, world)
+bad = [a.copy() for a in v4]
+per = len(v4[0]) // nf
+for a in bad:
+    a[(nf - 3) * per:] *= 1e160  # the last work items: the last rank's share
+core.setState(cut[start], v2, bad)
+diverged = core.computeStep()
+first, last = core.itemRange()
+flags = [None] * world
+dist.all_gather_object(flags, (bool(diverged), first, last))
+if rank == 0:
+    assert all(f[0] for f in flags), flags
+    print("MULTI_GPU_DIVERGENCE_OK", flags)
+core.close()
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -122,4 +141,4 @@ def test_sharded_flow_equals_single_gpu_flow(case, mode, tmp_path):
     env.update(MODES[mode])
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
-    assert "MULTI_GPU_OK" in proc.stdout
+    assert "MULTI_GPU_OK" in proc.stdout and "MULTI_GPU_DIVERGENCE_OK" in proc.stdout
