@@ -225,9 +225,10 @@ namespace
 
 	template <int CORE, int NB> size_t flowSmemBytes(int nw, int L, int groups, int nbt, int subs) { return FlowSmem<CORE, NB>(nw, L, groups, nbt, subs).total; }
 	// shared memory of the SU2 kernel with the Gram form of the RPA phase: gramRows rows of the Gram matrix next to nbt staged nodes
-	size_t gramSmemBytes(int nb, int nw, int L, int Lp, int groups, int nbt, int gramRows)
+	size_t gramSmemBytes(int nb, int nw, int L, int Lp, int groups, int nbt, int gramRows, int tableCopies = 1)
 	{
-		return nb == 32 ? FlowSmem<SU2, 32>(nw, L, groups, nbt, 1, gramRows, Lp).total : nb == 16 ? FlowSmem<SU2, 16>(nw, L, groups, nbt, 1, gramRows, Lp).total : FlowSmem<SU2, 8>(nw, L, groups, nbt, 1, gramRows, Lp).total;
+		return nb == 32 ? FlowSmem<SU2, 32>(nw, L, groups, nbt, 1, gramRows, Lp, tableCopies).total : nb == 16 ? FlowSmem<SU2, 16>(nw, L, groups, nbt, 1, gramRows, Lp, tableCopies).total
+		                : FlowSmem<SU2, 8>(nw, L, groups, nbt, 1, gramRows, Lp, tableCopies).total;
 	}
 	// nbt = nodes staged per RPA phase (0: same as the gather batch nb)
 	size_t flowSmemBytes(int core, int nb, int nw, int L, int groups, int nbt = 0, int subs = 1)
@@ -242,7 +243,7 @@ namespace
 	// warps (one per SM sub-partition when there are four), each on its own group of 16 (SU2) or 32 staged nodes, so the
 	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Environment overrides for tuning runs:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_TILES, PFFRG_JIT_MINBLOCKS.
-	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0; };
+	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0; bool producer = false; };
 
 	// tiles of the busiest warp when nw warps share the rt x ct 8x8 tiles of a Gram block (gramcfg::bestRowWarps, pffrg_kernels.cuh)
 	int gramBusiestTiles(int rt, int ct, int nw)
@@ -256,7 +257,8 @@ namespace
 	// the overlap list is walked once per RPA phase) and one block of PB rows of the Gram matrix (a multiple of 8, at most 64, at most 16
 	// accumulator tiles per warp) share the shared memory. Two CTAs per SM where 32 staged nodes still fit. Environment overrides:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_MINBLOCKS, PFFRG_GRAM_PB.
-	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs)
+	// `threads` = worker threads; producer: one more warp builds the access buffers a batch ahead (two table blocks), one CTA per SM
+	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs, bool producer = false)
 	{
 		JitShape best = { 0, 0, 0, 0, 0 };
 		const int gemmThreads = threads / 32 * 32, warps = gemmThreads / 32, ct = (Lp + 7) / 8;
@@ -276,6 +278,7 @@ namespace
 		{
 			if (forcedCtas && ctas != forcedCtas) continue;
 			if (!forcedCtas && ctas == 2 && threads > 256) continue; // the block update needs more than 64 registers per thread
+
 			const size_t budget = ctas >= 2 ? (smemMax + 1024) / ctas - 1024 : smemMax;
 			for (int nbt : nbts)
 			{
@@ -289,12 +292,12 @@ namespace
 						if ((long)pb * (Lp + 1) > (1l << 14)) continue;           // a term word addresses the Gram block with 14 bits
 						const int blocks = (Lp + pb - 1) / pb, lastRt = (Lp - (blocks - 1) * pb + 7) / 8;
 						if (gramBusiestTiles(pb / 8, ct, warps) > 16 || gramBusiestTiles(lastRt, ct, warps) > 16) continue;
-						const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, pb);
+						const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, pb, producer ? 2 : 1);
 						if (smem > budget) continue;
 						const double phases = (64 + nbt - 1) / nbt;
-						double cost = phases * (1.06 * (double)uniquePairs / 256.0 / warps * 200.0 + blocks * 1500.0) + (nb == 8 ? 15000.0 : 0.0);
+						double cost = phases * (1.06 * (double)uniquePairs / 256.0 / warps * 200.0 + blocks * 1500.0) + ((nb == 8 && !producer) ? 15000.0 : 0.0); // (with a producer warp the access-buffer phases of small batches are off the critical path)
 						if (ctas == 2) cost *= 0.8; // two resident CTAs overlap their phases
-						if (!best.nb || cost < bestCost) { best = { nb, nbt, threads / 32, ctas, smem }; best.gramRows = pb; best.gramThreads = gemmThreads; bestCost = cost; }
+						if (!best.nb || cost < bestCost) { best = { nb, nbt, threads / 32, ctas, smem }; best.gramRows = pb; best.gramThreads = gemmThreads; best.producer = producer; bestCost = cost; }
 					}
 				}
 			}
@@ -452,7 +455,13 @@ namespace
 	std::string gramDefines(const JitShape &s)
 	{
 		return "#define PFFRG_GRAM 1\n#define PFFRG_GRAM_THREADS " + std::to_string(s.gramThreads) + "\n#define PFFRG_GRAM_PB " + std::to_string(s.gramRows) +
-		       "\n";
+		       "\n" + (s.producer ? std::string("#define PFFRG_PRODUCER 1\n") : std::string());
+	}
+	// producer warp for the Gram kernel (v4FlowBodyProducer): opt-in with PFFRG_PRODUCER=1 while it is being measured
+	bool wantProducer()
+	{
+		const char *e = getenv("PFFRG_PRODUCER");
+		return e && atoi(e) != 0;
 	}
 
 	// TRI Gram form (rpaTriGram): gather batch = staged nodes = 8; as many resident channel-pair blocks as the shared memory holds
@@ -578,13 +587,16 @@ namespace
 			const char *form = getenv("PFFRG_RPA");
 			if (wantGram(h->core, h->uniquePairs))
 			{
-				JitShape shape = chooseGramShape(h->nw, h->L, h->Lp, h->groups, h->threads, smemMax, h->uniquePairs);
+				const int workers = h->threads / 32 * 32;
+				JitShape shape = { 0, 0, 0, 0, 0 };
+				if (wantProducer() && workers + 32 <= 1024) shape = chooseGramShape(h->nw, h->L, h->Lp, h->groups, workers, smemMax, h->uniquePairs, true);
+				if (!shape.nb) shape = chooseGramShape(h->nw, h->L, h->Lp, h->groups, h->threads, smemMax, h->uniquePairs);
 				if (!shape.nb) return form ? fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_RPA=gram: no launch shape fits (threads %d, L %d)", h->threads, h->L) : PFFRG_OK;
-				JitCandidate c = { h->threads, h->groups, shape, nullptr, nullptr, 0.f };
+				JitCandidate c = { shape.producer ? workers + 32 : h->threads, h->groups, shape, nullptr, nullptr, 0.f };
 				const int rc = compileCandidate(h, d, c);
 				if (rc != PFFRG_OK) return rc;
 				std::vector<unsigned> terms; std::vector<int> seg;
-				buildGramTables(d, h->L, h->Lp, shape.gramRows, h->threads / 32, terms, seg);
+				buildGramTables(d, h->L, h->Lp, shape.gramRows, shape.producer ? workers / 32 : h->threads / 32, terms, seg);
 				CUDA_TRY(h->dGramTerms.upload(terms)); CUDA_TRY(h->dGramSeg.upload(seg));
 				h->gramWords = (int64_t)terms.size();
 				adoptCandidate(h, c);
@@ -1898,10 +1910,13 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	if (wantGram(d->core, uniquePairs))
 	{
 		const int Lp = paddedSites(L);
-		const JitShape g = chooseGramShape(d->n_frequencies, L, Lp, groups, threads, 227 * 1024, uniquePairs);
+		const int workers = threads / 32 * 32;
+		JitShape g = { 0, 0, 0, 0, 0 };
+		if (wantProducer() && workers + 32 <= 1024) g = chooseGramShape(d->n_frequencies, L, Lp, groups, workers, 227 * 1024, uniquePairs, true);
+		if (!g.nb) g = chooseGramShape(d->n_frequencies, L, Lp, groups, threads, 227 * 1024, uniquePairs);
 		if (!g.nb) return fail(PFFRG_ERR_UNSUPPORTED, "no launch shape for the Gram form of the RPA phase");
 		std::vector<char> cubin;
-		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g));
+		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, g.producer ? workers + 32 : threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g));
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
 		std::vector<unsigned> terms; std::vector<int> seg; double conflicts = 0.0;
 		buildGramTables(d, L, Lp, g.gramRows, threads / 32, terms, seg, &conflicts);

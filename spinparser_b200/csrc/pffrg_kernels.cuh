@@ -356,7 +356,8 @@ namespace pffrg
 		// privateBytes), all share ONE staging area of subs * nbt nodes and one RPA phase
 		// gramRows > 0 (run-time compiled SU2 kernel, rpaGram): the operands are staged node-major as channel pairs, st[buffer][node][Lp] of
 		// double2, and a block of gramRows x Lp entries of the Gram matrix (double2) lives next to them
-		__host__ __device__ FlowSmem(int nw, int L, int groups, int nbt = NB, int subs = 1, int gramRows = 0, int Lp = 0)
+		// tableCopies = 2 (producer-warp kernel): two private table blocks, so that the producer warp fills one while the workers gather from the other
+		__host__ __device__ FlowSmem(int nw, int L, int groups, int nbt = NB, int subs = 1, int gramRows = 0, int Lp = 0, int tableCopies = 1)
 		{
 			size_t o = 0;
 			mesh = o; o += sizeof(double) * nw;
@@ -369,7 +370,7 @@ namespace pffrg
 			o = alignUp(o, 16);
 			wmat = o; o += (CORE == TRI) ? sizeof(double) * NB * 4 * 32 : 0; // TRI: contracted site-0 matrices, see triLocalMatrices
 			o = alignUp(o, 16);
-			privateBytes = o; o *= subs;
+			privateBytes = o; o *= subs * tableCopies;
 			// the per-group partial sums of the epilogue reuse the staging area (dead by then)
 			// TRI Gram form: gramRows = resident (c1, c2) blocks, Lp = sites per channel of the staged operands (trigram::LpT)
 			const size_t stBytes = (gramRows > 0 && CORE == TRI) ? sizeof(double) * 2 * (2 * (size_t)nbt) * (16 * Lp + 4)
@@ -1174,6 +1175,13 @@ namespace pffrg
 	}
 
 #ifdef PFFRG_GRAM
+	// Barrier over the threads that run the RPA phase: the whole CTA, or -- with a producer warp (PFFRG_PRODUCER, v4FlowBodyProducer) -- the
+	// PFFRG_GRAM_THREADS worker threads on named barrier 5 (the producer warp builds access buffers meanwhile).
+#ifdef PFFRG_PRODUCER
+	__device__ __forceinline__ void gramCtaSync() { asm volatile("bar.sync 5, %0;" :: "n"(PFFRG_GRAM_THREADS) : "memory"); }
+#else
+	__device__ __forceinline__ void gramCtaSync() { __syncthreads(); }
+#endif
 	// ================================================================================================================
 	// Gram-matrix form of the RPA lattice sum (SU2; run-time compiled kernel with PFFRG_GRAM, see pffrg.cu chooseGramShape).
 	//
@@ -1278,7 +1286,7 @@ namespace pffrg
 				}
 			}
 		}
-		__syncthreads(); // the reduction of the previous block has read Gs
+		gramCtaSync(); // the reduction of the previous block has read Gs
 		#pragma unroll
 		for (int i = 0; i < MI; ++i)
 		{
@@ -1368,18 +1376,22 @@ namespace pffrg
 	__device__ __forceinline__ void rpaGram(const Problem &P, const double2 *__restrict__ st2, int nodeCapacity, int nb, double2 *__restrict__ Gs, double *rpaOut)
 	{
 		using namespace gramcfg;
+#ifdef PFFRG_PRODUCER
+		const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = NW; // called by the NT worker threads only
+#else
 		const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = blockDim.x >> 5;
+#endif
 		const bool gemm = tid < NT;
 		const double2 *stA = st2, *stB = st2 + (size_t)nodeCapacity * LpS;
 		#pragma unroll 1
 		for (int blk = 0; blk < NBLK - 1; ++blk)
 		{
-			if (gemm) gramBlock<PB / 8>(stA, stB, nb, blk * PB, Gs, warp, lane); else __syncthreads();
-			__syncthreads();
+			if (gemm) gramBlock<PB / 8>(stA, stB, nb, blk * PB, Gs, warp, lane); else gramCtaSync();
+			gramCtaSync();
 			gramReduce(P, blk, Gs, rpaOut, warp, lane, warps);
 		}
-		if (gemm) gramBlock<(LAST_ROWS + 7) / 8>(stA, stB, nb, (NBLK - 1) * PB, Gs, warp, lane); else __syncthreads();
-		__syncthreads();
+		if (gemm) gramBlock<(LAST_ROWS + 7) / 8>(stA, stB, nb, (NBLK - 1) * PB, Gs, warp, lane); else gramCtaSync();
+		gramCtaSync();
 		gramReduce(P, NBLK - 1, Gs, rpaOut, warp, lane, warps);
 	}
 #endif
@@ -1905,6 +1917,190 @@ namespace pffrg
 		}
 		if (bad) atomicOr(nanFlag, 1);
 	}
+
+#if defined(PFFRG_GRAM) && defined(PFFRG_PRODUCER)
+	// ================================================================================================================
+	// SU2 flow kernel with the Gram form of the RPA phase and a PRODUCER WARP. In v4FlowBody the access-buffer phases of every gather
+	// batch (mesh searches, sector map / weights / rows, site-0 values) are short serial steps between CTA barriers in which a few
+	// dozen threads work and the others wait: 14 % of the samples at pyrochlore-r8, 28 % at cubic-r7, most of it barrier wait. Here the
+	// last warp of the CTA does nothing but build these tables, one batch ahead of the worker warps, into the second of two table
+	// blocks; the workers never wait for table work, and the producer also runs through the workers' RPA phases. Hand-over with named
+	// barriers: FULL[b] (6 + b): the producer arrives after filling block b, the workers sync before they gather from it;
+	// EMPTY[b] (8 + b): the workers arrive when they are done with block b, the producer syncs before it refills it; worker-only barrier 5.
+	// Same arithmetic as v4FlowBody<SU2, NB, NBT, true> (the code of phases 0, 0b, 1 and the epilogue is the same, minus the
+	// options that body offers).
+	// ================================================================================================================
+	__device__ __forceinline__ void namedSync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+	__device__ __forceinline__ void namedArrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+
+	template <int NB, int NBT>
+	__device__ __forceinline__ void v4FlowBodyProducer(const Problem &P, const NodeTable &N, const FlowConfig &cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
+	{
+		constexpr int CORE = SU2, C = 2;
+		constexpr int NWORK = PFFRG_GRAM_THREADS; // worker threads = threads of the Gram update; the producer warp follows them
+		extern __shared__ __align__(16) unsigned char smemRaw[];
+		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT, 1, gramcfg::PB, gramcfg::Lp, 2);
+		const int tid = threadIdx.x;
+		const bool producer = tid >= NWORK;
+		const int lane = tid & 31;
+		double *mesh = reinterpret_cast<double *>(smemRaw + lay.mesh); // (of table block 0; block 1's copy is unused)
+		auto tableBase = [&](int buf) { return smemRaw + (size_t)buf * lay.privateBytes; };
+		double *st = reinterpret_cast<double *>(smemRaw + lay.st);
+		double *part = reinterpret_cast<double *>(smemRaw + lay.part);
+		double *rpaOut = reinterpret_cast<double *>(smemRaw + lay.rpa);
+		const int L = sizeL(P), nw = sizeNw(P), total = NWORK + 32;
+
+		for (int i = tid; i < nw; i += blockDim.x) mesh[i] = P.mesh[i];
+		for (int i = tid; i < lay.rpaCopies * C * L; i += blockDim.x) rpaOut[i] = 0.0;
+		for (int i = tid; i < 2 * NBT * (gramcfg::LpS - L); i += blockDim.x)
+			reinterpret_cast<double2 *>(st)[(i / (gramcfg::LpS - L)) * gramcfg::LpS + L + i % (gramcfg::LpS - L)] = make_double2(0.0, 0.0);
+
+		const int itemEnd = itemBegin + cfg.items;
+		const int itemFirst = itemBegin + blockIdx.x;
+		const bool valid = itemFirst < itemEnd;
+		const int item = valid ? itemFirst : itemEnd - 1;
+		const int su = item / nw, ti = item - su * nw;
+		int so = (int)((sqrt(8.0 * su + 1.0) - 1.0) * 0.5);
+		while ((so + 1) * (so + 2) / 2 <= su) ++so;
+		while (so * (so + 1) / 2 > su) --so;
+		const int uo = su - so * (so + 1) / 2;
+		__syncthreads(); // the only barrier over all threads
+		ItemFrequencies f;
+		f.s = mesh[so]; f.t = mesh[ti]; f.u = mesh[uo];
+		f.w1p = 0.5 * (f.s + f.t + f.u); f.w1 = 0.5 * (f.s - f.t + f.u); f.w2p = 0.5 * (f.s - f.t - f.u); f.w2 = 0.5 * (f.s + f.t - f.u);
+
+		const int g = tid / cfg.stride, j = tid - g * cfg.stride;
+		const bool worker = !producer && g < cfg.groups && j < L;
+		int siteFwd = 0, siteInv = 0;
+		if (worker) { siteFwd = P.sites_rid[j]; siteInv = P.inv_rid[j]; }
+		double acc[C] = { 0.0, 0.0 };
+		int batchNo = 0; // batches handed over so far (the same sequence on both sides)
+
+		#pragma unroll 1
+		for (int pass = 0; pass < 2; ++pass)
+		{
+			const bool tPass = pass == 1;
+			const int nFirst = N.count[tPass ? ti : so];
+			const int nNodes = !valid ? 0 : (tPass ? nFirst : nFirst + N.count[uo]);
+			const double *nodeW0 = N.wp + (size_t)(tPass ? ti : so) * N.stride, *nodeWt0 = N.wt + (size_t)(tPass ? ti : so) * N.stride;
+			const double *nodeW1 = N.wp + (size_t)uo * N.stride, *nodeWt1 = N.wt + (size_t)uo * N.stride;
+			const int nbuf = tPass ? 8 : 4;
+			const int batch = tPass ? NB : 2 * NB;
+			const int rounds = tPass ? (nNodes + NBT - 1) / NBT : 1;
+			#pragma unroll 1
+			for (int rd = 0; rd < rounds; ++rd)
+			{
+				const int lo = tPass ? rd * NBT : 0, hi = tPass ? min(nNodes, lo + NBT) : nNodes;
+				int staged = 0;
+				#pragma unroll 1
+				for (int b0 = lo; b0 < hi; b0 += batch, ++batchNo)
+				{
+					const int nb = min(batch, hi - b0);
+					const int buf = batchNo & 1;
+					unsigned char *tb = tableBase(buf);
+					double *bW = reinterpret_cast<double *>(tb + lay.bW);
+					LerpRecord *lerp = reinterpret_cast<LerpRecord *>(tb + lay.lerp);
+					AccessBuffer *abTable = reinterpret_cast<AccessBuffer *>(tb + lay.ab);
+					double *loc = reinterpret_cast<double *>(tb + lay.loc);
+					if (producer)
+					{
+						if (batchNo >= 2) namedSync(8 + buf, total); // the workers are done with this block
+						// ---- phase 0, step A: the four interpolated frequencies of every node (one mesh search each)
+						for (int idx = lane; idx < nb * 4; idx += 32)
+						{
+							const int node = idx >> 2, q = idx & 3;
+							const int gn = b0 + node;
+							const int ch = tPass ? CH_T : (gn < nFirst ? CH_S : CH_U);
+							const double wp = gn < nFirst ? nodeW0[gn] : nodeW1[gn - nFirst];
+							if (q == 0)
+							{
+								const double wt = gn < nFirst ? nodeWt0[gn] : nodeWt1[gn - nFirst];
+								bW[node] = ch == CH_U ? -wt : wt; // SU2: the u channel enters with a minus sign (SU2FrgCore.cpp:366,370,376)
+							}
+							makeLerpRecord(mesh, nw, P.meshIndex, nodeQuantity(ch, q, f.w1p, f.w1, f.w2p, f.w2, wp), lerp[idx]);
+						}
+						__syncwarp();
+						// ---- step B: assemble the buffers; site-0 values of the t channel's buffers 4..7 (getValueLocal) right away
+						for (int idx = lane; idx < nb * nbuf; idx += 32)
+						{
+							const int node = idx / nbuf, b = idx - node * nbuf;
+							const int ch = tPass ? CH_T : ((b0 + node) < nFirst ? CH_S : CH_U);
+							assembleAccessBuffer<CORE>(nw, ch, b, ch == CH_S ? so : (ch == CH_T ? ti : uo), lerp + 4 * node, abTable[idx]);
+							if (tPass && b >= 4)
+							{
+								const AccessBuffer &ab = abTable[idx];
+								double v0 = 0.0, v1 = 0.0;
+								#pragma unroll
+								for (int k = 0; k < 4; ++k)
+								{
+									const double2 x = __ldg(reinterpret_cast<const double2 *>(v4 + (size_t)ab.row[k] * sizeRL(P)));
+									v0 += supportSign<CORE>(ab.flags, k, 0) * ab.w[k] * x.x;
+									v1 += supportSign<CORE>(ab.flags, k, 1) * ab.w[k] * x.y;
+								}
+								loc[(node * 4 + (b - 4)) * C] = v0; loc[(node * 4 + (b - 4)) * C + 1] = v1;
+							}
+						}
+						__syncwarp();
+						namedArrive(6 + buf, total); // block `buf` is ready
+					}
+					else
+					{
+						namedSync(6 + buf, total); // wait for the producer
+						// ---- phase 1: gathers + bilinear forms
+						if (worker)
+						{
+							for (int node = g; node < nb; node += cfg.groups)
+							{
+								double A[4][C];
+								const AccessBuffer *ab = abTable + node * nbuf;
+								#pragma unroll
+								for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, ab[b], siteFwd, siteInv, PERM_IDENTITY, PERM_IDENTITY, A[b]);
+								const double W = bW[node];
+								double K[C];
+								if (!tPass) ladderTerms<CORE>((b0 + node) < nFirst ? CH_S : CH_U, A, K);
+								else
+								{
+									chaliceTerms<CORE>(A, loc + node * 4 * C, K);
+									// RPA operands: buffers 2 and 3 with prefactors 2S (spin) and 8S (density), SU2FrgCore.cpp:257-266; node weight folded into A
+									double2 *st2 = reinterpret_cast<double2 *>(st);
+									st2[(staged + node) * gramcfg::LpS + j] = make_double2(W * 2.0 * P.spin * A[2][0], W * 8.0 * P.spin * A[2][1]);
+									st2[(NBT + staged + node) * gramcfg::LpS + j] = make_double2(A[3][0], A[3][1]);
+								}
+								acc[0] += W * K[0]; acc[1] += W * K[1];
+							}
+						}
+						namedArrive(8 + buf, total); // done with block `buf`
+					}
+					if (tPass) staged += nb;
+				}
+				if (tPass && !producer)
+				{
+					gramCtaSync(); // all operands of this round are staged
+					rpaGram(P, reinterpret_cast<const double2 *>(st), NBT, staged, reinterpret_cast<double2 *>(smemRaw + lay.gram), rpaOut);
+					gramCtaSync(); // the staging area may be overwritten by the next round
+				}
+			}
+		}
+		if (producer) return;
+
+		// ---- epilogue (workers)
+		gramCtaSync();
+		if (worker) { part[(g * C) * L + j] = acc[0]; part[(g * C + 1) * L + j] = acc[1]; }
+		gramCtaSync();
+		bool bad = false;
+		for (int e = tid; valid && e < C * L; e += NWORK)
+		{
+			double v = 0.0;
+			for (int k = 0; k < lay.rpaCopies; ++k) v += rpaOut[k * C * L + e];
+			for (int gg = 0; gg < cfg.groups; ++gg) v += part[gg * C * L + e];
+			v /= TWO_PI;
+			const int c = e / L, jj = e - c * L;
+			flow[(size_t)item * sizeRL(P) + channelOffset(vectorWidth(CORE), c, sizeLp(P)) + jj * vectorWidth(CORE)] = v;
+			bad |= (v != v);
+		}
+		if (bad) atomicOr(nanFlag, 1);
+	}
+#endif
 
 #ifndef PFFRG_JIT_RPA
 	template <int CORE, int NB>
