@@ -243,7 +243,7 @@ namespace
 	// warps (one per SM sub-partition when there are four), each on its own group of 16 (SU2) or 32 staged nodes, so the
 	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Environment overrides for tuning runs:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_TILES, PFFRG_JIT_MINBLOCKS.
-	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0; bool producer = false; };
+	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0; int producer = 0; /* producer warps */ };
 
 	// tiles of the busiest warp when nw warps share the rt x ct 8x8 tiles of a Gram block (gramcfg::bestRowWarps, pffrg_kernels.cuh)
 	int gramBusiestTiles(int rt, int ct, int nw)
@@ -258,7 +258,7 @@ namespace
 	// accumulator tiles per warp) share the shared memory. Two CTAs per SM where 32 staged nodes still fit. Environment overrides:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_MINBLOCKS, PFFRG_GRAM_PB.
 	// `threads` = worker threads; producer: one more warp builds the access buffers a batch ahead (two table blocks), one CTA per SM
-	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs, bool producer = false)
+	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs, int producer = 0)
 	{
 		JitShape best = { 0, 0, 0, 0, 0 };
 		const int gemmThreads = threads / 32 * 32, warps = gemmThreads / 32, ct = (Lp + 7) / 8;
@@ -295,7 +295,7 @@ namespace
 						const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, pb, producer ? 2 : 1);
 						if (smem > budget) continue;
 						const double phases = (64 + nbt - 1) / nbt;
-						double cost = phases * (1.06 * (double)uniquePairs / 256.0 / warps * 200.0 + blocks * 1500.0) + ((nb == 8 && !producer) ? 15000.0 : 0.0); // (with a producer warp the access-buffer phases of small batches are off the critical path)
+						double cost = phases * (1.06 * (double)uniquePairs / 256.0 / warps * 200.0 + blocks * 1500.0) + (nb == 8 ? (producer ? 6000.0 : 15000.0) : 0.0); // (with producer warps the access-buffer phases are off the critical path; measured +4 % with batches of 8)
 						if (ctas == 2) cost *= 0.8; // two resident CTAs overlap their phases
 						if (!best.nb || cost < bestCost) { best = { nb, nbt, threads / 32, ctas, smem }; best.gramRows = pb; best.gramThreads = gemmThreads; best.producer = producer; bestCost = cost; }
 					}
@@ -455,13 +455,13 @@ namespace
 	std::string gramDefines(const JitShape &s)
 	{
 		return "#define PFFRG_GRAM 1\n#define PFFRG_GRAM_THREADS " + std::to_string(s.gramThreads) + "\n#define PFFRG_GRAM_PB " + std::to_string(s.gramRows) +
-		       "\n" + (s.producer ? std::string("#define PFFRG_PRODUCER 1\n") : std::string());
+		       "\n" + (s.producer ? "#define PFFRG_PRODUCER " + std::to_string(s.producer) + "\n" : std::string());
 	}
 	// producer warp for the Gram kernel (v4FlowBodyProducer): opt-in with PFFRG_PRODUCER=1 while it is being measured
-	bool wantProducer()
+	int wantProducer() // number of producer warps (0: none)
 	{
 		const char *e = getenv("PFFRG_PRODUCER");
-		return e && atoi(e) != 0;
+		return e ? std::min(4, std::max(0, atoi(e))) : 0;
 	}
 
 	// TRI Gram form (rpaTriGram): gather batch = staged nodes = 8; as many resident channel-pair blocks as the shared memory holds
@@ -589,10 +589,10 @@ namespace
 			{
 				const int workers = h->threads / 32 * 32;
 				JitShape shape = { 0, 0, 0, 0, 0 };
-				if (wantProducer() && workers + 32 <= 1024) shape = chooseGramShape(h->nw, h->L, h->Lp, h->groups, workers, smemMax, h->uniquePairs, true);
+				if (wantProducer() && workers + 32 * wantProducer() <= 1024) shape = chooseGramShape(h->nw, h->L, h->Lp, h->groups, workers, smemMax, h->uniquePairs, wantProducer());
 				if (!shape.nb) shape = chooseGramShape(h->nw, h->L, h->Lp, h->groups, h->threads, smemMax, h->uniquePairs);
 				if (!shape.nb) return form ? fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_RPA=gram: no launch shape fits (threads %d, L %d)", h->threads, h->L) : PFFRG_OK;
-				JitCandidate c = { shape.producer ? workers + 32 : h->threads, h->groups, shape, nullptr, nullptr, 0.f };
+				JitCandidate c = { shape.producer ? workers + 32 * shape.producer : h->threads, h->groups, shape, nullptr, nullptr, 0.f };
 				const int rc = compileCandidate(h, d, c);
 				if (rc != PFFRG_OK) return rc;
 				std::vector<unsigned> terms; std::vector<int> seg;
@@ -1912,11 +1912,11 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 		const int Lp = paddedSites(L);
 		const int workers = threads / 32 * 32;
 		JitShape g = { 0, 0, 0, 0, 0 };
-		if (wantProducer() && workers + 32 <= 1024) g = chooseGramShape(d->n_frequencies, L, Lp, groups, workers, 227 * 1024, uniquePairs, true);
+		if (wantProducer() && workers + 32 * wantProducer() <= 1024) g = chooseGramShape(d->n_frequencies, L, Lp, groups, workers, 227 * 1024, uniquePairs, wantProducer());
 		if (!g.nb) g = chooseGramShape(d->n_frequencies, L, Lp, groups, threads, 227 * 1024, uniquePairs);
 		if (!g.nb) return fail(PFFRG_ERR_UNSUPPORTED, "no launch shape for the Gram form of the RPA phase");
 		std::vector<char> cubin;
-		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, g.producer ? workers + 32 : threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g));
+		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, g.producer ? workers + 32 * g.producer : threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g));
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
 		std::vector<unsigned> terms; std::vector<int> seg; double conflicts = 0.0;
 		buildGramTables(d, L, Lp, g.gramRows, threads / 32, terms, seg, &conflicts);

@@ -1937,18 +1937,20 @@ namespace pffrg
 	__device__ __forceinline__ void v4FlowBodyProducer(const Problem &P, const NodeTable &N, const FlowConfig &cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
 	{
 		constexpr int CORE = SU2, C = 2;
-		constexpr int NWORK = PFFRG_GRAM_THREADS; // worker threads = threads of the Gram update; the producer warp follows them
+		constexpr int NWORK = PFFRG_GRAM_THREADS; // worker threads = threads of the Gram update; the producer warp(s) follow them
+		constexpr int NPROD = 32 * PFFRG_PRODUCER; // producer threads (PFFRG_PRODUCER = number of producer warps)
 		extern __shared__ __align__(16) unsigned char smemRaw[];
 		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT, 1, gramcfg::PB, gramcfg::Lp, 2);
 		const int tid = threadIdx.x;
 		const bool producer = tid >= NWORK;
-		const int lane = tid & 31;
+		const int ptid = tid - NWORK; // index among the producer threads
+		auto producerSync = [&]() { if (NPROD == 32) __syncwarp(); else namedSync(10, NPROD); };
 		double *mesh = reinterpret_cast<double *>(smemRaw + lay.mesh); // (of table block 0; block 1's copy is unused)
 		auto tableBase = [&](int buf) { return smemRaw + (size_t)buf * lay.privateBytes; };
 		double *st = reinterpret_cast<double *>(smemRaw + lay.st);
 		double *part = reinterpret_cast<double *>(smemRaw + lay.part);
 		double *rpaOut = reinterpret_cast<double *>(smemRaw + lay.rpa);
-		const int L = sizeL(P), nw = sizeNw(P), total = NWORK + 32;
+		const int L = sizeL(P), nw = sizeNw(P), total = NWORK + NPROD;
 
 		for (int i = tid; i < nw; i += blockDim.x) mesh[i] = P.mesh[i];
 		for (int i = tid; i < lay.rpaCopies * C * L; i += blockDim.x) rpaOut[i] = 0.0;
@@ -2006,7 +2008,7 @@ namespace pffrg
 					{
 						if (batchNo >= 2) namedSync(8 + buf, total); // the workers are done with this block
 						// ---- phase 0, step A: the four interpolated frequencies of every node (one mesh search each)
-						for (int idx = lane; idx < nb * 4; idx += 32)
+						for (int idx = ptid; idx < nb * 4; idx += NPROD)
 						{
 							const int node = idx >> 2, q = idx & 3;
 							const int gn = b0 + node;
@@ -2019,9 +2021,9 @@ namespace pffrg
 							}
 							makeLerpRecord(mesh, nw, P.meshIndex, nodeQuantity(ch, q, f.w1p, f.w1, f.w2p, f.w2, wp), lerp[idx]);
 						}
-						__syncwarp();
+						producerSync();
 						// ---- step B: assemble the buffers; site-0 values of the t channel's buffers 4..7 (getValueLocal) right away
-						for (int idx = lane; idx < nb * nbuf; idx += 32)
+						for (int idx = ptid; idx < nb * nbuf; idx += NPROD)
 						{
 							const int node = idx / nbuf, b = idx - node * nbuf;
 							const int ch = tPass ? CH_T : ((b0 + node) < nFirst ? CH_S : CH_U);
@@ -2040,8 +2042,7 @@ namespace pffrg
 								loc[(node * 4 + (b - 4)) * C] = v0; loc[(node * 4 + (b - 4)) * C + 1] = v1;
 							}
 						}
-						__syncwarp();
-						namedArrive(6 + buf, total); // block `buf` is ready
+						namedArrive(6 + buf, total); // block `buf` is ready (the barrier orders this thread's table writes before the workers' reads)
 					}
 					else
 					{

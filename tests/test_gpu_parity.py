@@ -43,7 +43,7 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             {"PFFRG_FUSED_LOCALS": "1"}, {"PFFRG_FUSED_LOCALS": "1", "PFFRG_RPA": "gram"},
             # SU2 Gram kernel with a producer warp that builds the access buffers one batch ahead of the workers
             {"PFFRG_RPA": "gram", "PFFRG_PRODUCER": "1"}, {"PFFRG_RPA": "gram", "PFFRG_PRODUCER": "1", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"},
-            {"PFFRG_RPA": "gram", "PFFRG_PRODUCER": "1", "PFFRG_THREADS": "128", "PFFRG_JIT_MINBLOCKS": "2"},
+            {"PFFRG_RPA": "gram", "PFFRG_PRODUCER": "1", "PFFRG_THREADS": "128", "PFFRG_JIT_MINBLOCKS": "2"}, {"PFFRG_RPA": "gram", "PFFRG_PRODUCER": "2"},
             {"PFFRG_RPA": "table"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "1"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "2", "PFFRG_THREADS": "128"}]
 
 
