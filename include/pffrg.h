@@ -214,11 +214,11 @@ int pffrg_site_order(const pffrg_desc *desc, int32_t *order /* [n_sites] */);
 /* Term tables of the Gram form of the SU2 RPA lattice sum as the kernel walks them (rpaGram / gramReduce, pffrg_kernels.cuh): the sum
  * over the quadrature nodes of R[rid] = sum_i A[rid1_i] B[rid2_i] (Lattice::getOverlap(rid), src/Lattice.hpp:46-150, evaluated per node
  * at src/SU2/SU2FrgCore.cpp:250-266) is taken as sum_i G[rid1_i][rid2_i] over the Gram matrix G = sum_nodes A (x) B, rows worked off in
- * blocks of `rows_per_block`. Writes up to `capacity` 32-bit words ((rid1 - block * rows_per_block) * Lp + rid2) | rid << 14 |
- * multiplicity << 22, Lp = n_sites rounded up to 4, sorted by rid, every rid list padded to a multiple of 8 words, and
- * seg[2 * (block * warps + w)] = {begin, end} of the word range warp w reduces (whole chunks of 256 words); *conflict_degree
- * (optional) = average shared-memory bank-conflict degree of the walk (1 = conflict free). Returns the number of words. Host only; used
- * by the CPU tests. */
+ * blocks of `rows_per_block`. Writes up to `capacity` 32-bit words ((rid1 - block * rows_per_block) * (Lp + 1) + rid2) | rid << 14 |
+ * multiplicity << 22 | flush << 31, Lp = n_sites rounded up to 4. Whole rid lists are dealt to the warps; a warp's lists are padded to
+ * groups of 4 words, concatenated, and lane l walks the groups [l T4, (l + 1) T4) serially (stored as [group][lane][4]); the last word
+ * of a list's last group carries the flush flag. seg[2 * (block * warps + w)] = {first word, T4}; *conflict_degree (optional) = average
+ * shared-memory bank-conflict degree of the walk (1 = conflict free). Returns the number of words. Host only; used by the CPU tests. */
 int pffrg_gram_tables(const pffrg_desc *desc, int rows_per_block, int warps, uint32_t *terms, int capacity, int32_t *seg, double *conflict_degree);
 
 /* measured FP64 multiply-add peak of a device in TFLOP/s (a 16-chain DFMA loop on every SM; ~10 ms): the denominator of the

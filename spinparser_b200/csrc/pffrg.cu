@@ -243,7 +243,7 @@ namespace
 	// warps (one per SM sub-partition when there are four), each on its own group of 16 (SU2) or 32 staged nodes, so the
 	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Environment overrides for tuning runs:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_TILES, PFFRG_JIT_MINBLOCKS.
-	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0; int producer = 0; /* producer warps */ };
+	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0; int producer = 0; /* producer warps */ int splitGather = 0; /* warp-specialised kernel: gather threads (0: not split) */ int regsGather = 0, regsRpa = 0, regsProducer = 0; };
 
 	// tiles of the busiest warp when nw warps share the rt x ct 8x8 tiles of a Gram block (gramcfg::bestRowWarps, pffrg_kernels.cuh)
 	int gramBusiestTiles(int rt, int ct, int nw)
@@ -258,7 +258,7 @@ namespace
 	// accumulator tiles per warp) share the shared memory. Two CTAs per SM where 32 staged nodes still fit. Environment overrides:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_MINBLOCKS, PFFRG_GRAM_PB.
 	// `threads` = worker threads; producer: one more warp builds the access buffers a batch ahead (two table blocks), one CTA per SM
-	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs, int producer = 0)
+	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs, int producer = 0, int maxCtas = 2)
 	{
 		JitShape best = { 0, 0, 0, 0, 0 };
 		const int gemmThreads = threads / 32 * 32, warps = gemmThreads / 32, ct = (Lp + 7) / 8;
@@ -271,12 +271,12 @@ namespace
 		const int pbMax = std::min(64, (Lp + 7) / 8 * 8);
 		const int nbts[] = { 64, 48, 32, 24, 16, 8 };
 		// Every shape that fits is rated with a coarse model of what the choice costs per work item (clocks; ~64 t-channel nodes per item):
-		// every RPA phase walks the term array once (~200 clocks per chunk of 256 words and warp) and pays two barriers and a store of the
+		// every RPA phase walks the term array once (~60 clocks per group of 128 words and warp) and pays two barriers and a store of the
 		// block per row block (~1500 clocks); small gather batches cost gather throughput (measured: pyrochlore-r8 +15 % with batches of 8).
 		double bestCost = 0.0;
 		for (int ctas = 2; ctas >= 1; --ctas)
 		{
-			if (forcedCtas && ctas != forcedCtas) continue;
+			if ((forcedCtas && ctas != forcedCtas) || ctas > maxCtas) continue;
 			if (!forcedCtas && ctas == 2 && threads > 256) continue; // the block update needs more than 64 registers per thread
 
 			const size_t budget = ctas >= 2 ? (smemMax + 1024) / ctas - 1024 : smemMax;
@@ -295,7 +295,7 @@ namespace
 						const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, pb, producer ? 2 : 1);
 						if (smem > budget) continue;
 						const double phases = (64 + nbt - 1) / nbt;
-						double cost = phases * (1.06 * (double)uniquePairs / 256.0 / warps * 200.0 + blocks * 1500.0) + (nb == 8 ? (producer ? 6000.0 : 15000.0) : 0.0); // (with producer warps the access-buffer phases are off the critical path; measured +4 % with batches of 8)
+						double cost = phases * (1.03 * (double)uniquePairs / 128.0 / warps * 60.0 + blocks * 1500.0) + (nb == 8 ? (producer ? 6000.0 : 15000.0) : 0.0); // (with producer warps the access-buffer phases are off the critical path; measured +4 % with batches of 8)
 						if (ctas == 2) cost *= 0.8; // two resident CTAs overlap their phases
 						if (!best.nb || cost < bestCost) { best = { nb, nbt, threads / 32, ctas, smem }; best.gramRows = pb; best.gramThreads = gemmThreads; best.producer = producer; bestCost = cost; }
 					}
@@ -455,13 +455,62 @@ namespace
 	std::string gramDefines(const JitShape &s)
 	{
 		return "#define PFFRG_GRAM 1\n#define PFFRG_GRAM_THREADS " + std::to_string(s.gramThreads) + "\n#define PFFRG_GRAM_PB " + std::to_string(s.gramRows) +
-		       "\n" + (s.producer ? "#define PFFRG_PRODUCER " + std::to_string(s.producer) + "\n" : std::string());
+		       "\n" + (s.producer ? "#define PFFRG_PRODUCER " + std::to_string(s.producer) + "\n" : std::string()) +
+		       (s.splitGather ? "#define PFFRG_SPLIT 1\n#define PFFRG_SPLIT_GATHER_THREADS " + std::to_string(s.splitGather) + "\n#define PFFRG_SPLIT_REGS_GATHER " + std::to_string(s.regsGather) +
+		                        "\n#define PFFRG_SPLIT_REGS_RPA " + std::to_string(s.regsRpa) + "\n#define PFFRG_SPLIT_REGS_PRODUCER " + std::to_string(s.regsProducer) + "\n" : std::string());
 	}
 	// producer warp for the Gram kernel (v4FlowBodyProducer): opt-in with PFFRG_PRODUCER=1 while it is being measured
 	int wantProducer() // number of producer warps (0: none)
 	{
 		const char *e = getenv("PFFRG_PRODUCER");
 		return e ? std::min(4, std::max(0, atoi(e))) : 0;
+	}
+
+	// Warp-specialised Gram kernel (v4FlowBodySplit, pffrg_kernels.cuh): gather warps, RPA warps and producer warps as separate warp groups
+	// of one CTA. Opt-in with PFFRG_SPLIT=1 while it is being measured. PFFRG_SPLIT_RPA_THREADS (128), PFFRG_SPLIT_REGS_RPA / _PRODUCER override
+	// the partition of the register file.
+	bool wantSplit()
+	{
+		const char *e = getenv("PFFRG_SPLIT");
+		return e && atoi(e) != 0;
+	}
+
+	// Launch of the SU2 kernel with the Gram form of the RPA phase: shape, threads per CTA and the number of warps that walk the term array
+	struct GramLaunch { JitShape shape; int threads; int reduceWarps; };
+	GramLaunch chooseGramLaunch(int nw, int L, int Lp, int groups, int stride, int threads, size_t smemMax, int64_t uniquePairs)
+	{
+		GramLaunch g = { { 0, 0, 0, 0, 0 }, threads, threads / 32 };
+		const int workers = threads / 32 * 32;
+		if (wantSplit())
+		{
+			const int gather = (groups * stride + 127) / 128 * 128;
+			int rpa = 128, producer = std::max(1, wantProducer() ? wantProducer() : 2);
+			if (const char *e = getenv("PFFRG_SPLIT_RPA_THREADS")) rpa = std::max(128, atoi(e) / 128 * 128);
+			const int total = gather + rpa + 128;
+			if (total <= 1024)
+			{
+				JitShape s = chooseGramShape(nw, L, Lp, groups, rpa, smemMax, uniquePairs, producer, 1); // one CTA per SM: the warp groups re-partition its whole register file
+				// register file: what the launch allocates (registers per thread of the whole CTA, a multiple of 8) is re-partitioned
+				const int pool = 65536 / total / 8 * 8 * total;
+				int regsProducer = 40, regsRpa = 200;
+				if (const char *e = getenv("PFFRG_SPLIT_REGS_PRODUCER")) regsProducer = std::max(24, atoi(e) / 8 * 8);
+				if (const char *e = getenv("PFFRG_SPLIT_REGS_RPA")) regsRpa = std::max(24, atoi(e) / 8 * 8);
+				const int regsGather = std::min(256, (pool - 128 * regsProducer - rpa * regsRpa) / gather / 8 * 8);
+				if (s.nb && regsGather >= 96)
+				{
+					s.splitGather = gather; s.regsGather = regsGather; s.regsRpa = regsRpa; s.regsProducer = regsProducer;
+					g.shape = s; g.threads = total; g.reduceWarps = rpa / 32;
+					return g;
+				}
+			}
+		}
+		if (wantProducer() && workers + 32 * wantProducer() <= 1024)
+		{
+			g.shape = chooseGramShape(nw, L, Lp, groups, workers, smemMax, uniquePairs, wantProducer());
+			if (g.shape.nb) { g.threads = workers + 32 * g.shape.producer; g.reduceWarps = workers / 32; return g; }
+		}
+		g.shape = chooseGramShape(nw, L, Lp, groups, threads, smemMax, uniquePairs);
+		return g;
 	}
 
 	// TRI Gram form (rpaTriGram): gather batch = staged nodes = 8; as many resident channel-pair blocks as the shared memory holds
@@ -587,16 +636,14 @@ namespace
 			const char *form = getenv("PFFRG_RPA");
 			if (wantGram(h->core, h->uniquePairs))
 			{
-				const int workers = h->threads / 32 * 32;
-				JitShape shape = { 0, 0, 0, 0, 0 };
-				if (wantProducer() && workers + 32 * wantProducer() <= 1024) shape = chooseGramShape(h->nw, h->L, h->Lp, h->groups, workers, smemMax, h->uniquePairs, wantProducer());
-				if (!shape.nb) shape = chooseGramShape(h->nw, h->L, h->Lp, h->groups, h->threads, smemMax, h->uniquePairs);
+				const GramLaunch launch = chooseGramLaunch(h->nw, h->L, h->Lp, h->groups, h->stride, h->threads, smemMax, h->uniquePairs);
+				const JitShape &shape = launch.shape;
 				if (!shape.nb) return form ? fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_RPA=gram: no launch shape fits (threads %d, L %d)", h->threads, h->L) : PFFRG_OK;
-				JitCandidate c = { shape.producer ? workers + 32 * shape.producer : h->threads, h->groups, shape, nullptr, nullptr, 0.f };
+				JitCandidate c = { launch.threads, h->groups, shape, nullptr, nullptr, 0.f };
 				const int rc = compileCandidate(h, d, c);
 				if (rc != PFFRG_OK) return rc;
 				std::vector<unsigned> terms; std::vector<int> seg;
-				buildGramTables(d, h->L, h->Lp, shape.gramRows, shape.producer ? workers / 32 : h->threads / 32, terms, seg);
+				buildGramTables(d, h->L, h->Lp, shape.gramRows, launch.reduceWarps, terms, seg);
 				CUDA_TRY(h->dGramTerms.upload(terms)); CUDA_TRY(h->dGramSeg.upload(seg));
 				h->gramWords = (int64_t)terms.size();
 				adoptCandidate(h, c);
@@ -982,14 +1029,22 @@ namespace
 		return { sets, degree };
 	}
 
-	// Term tables of gramReduce (SU2). For every block of PB rows of the Gram matrix: one pass of 32-bit words
-	//     (rid1 - block * PB) * (Lp + 1) + rid2  |  rid << 14  |  multiplicity << 22
-	// of the merged overlap terms (rid1, rid2, multiplicity) of all representative sites rid with rid1 in the block, laid out by
-	// layoutReductionPass: seg[2 * (block * warps + w)] = {begin, end} of the word range warp w reduces.
-	// conflictDegree (optional): average number of words per occupied bank group over all (chunk, quarter, step) sets; 1 = conflict free.
+	// Term tables of gramReduce (SU2), "lane-serial" layout. For every block of PB rows of the Gram matrix the merged overlap terms
+	// (rid1, rid2, multiplicity) of all representative sites rid with rid1 in the block become 32-bit words
+	//     (rid1 - block * PB) * (Lp + 1) + rid2  |  rid << 14  |  multiplicity << 22  |  flush << 31.
+	// Whole rid lists are dealt to the warps (longest first, to the least loaded warp: single writer per output and block). Inside a warp
+	// every rid list is padded to whole groups of 4 words and the groups of all its lists are concatenated; lane l walks the groups
+	// [l T4, (l + 1) T4) of that sequence SERIALLY, accumulating in registers; the last group of a rid carries the flush flag (the lane adds
+	// its sum to the output and starts over), and what a lane holds at the end of its range (a rid that continues in the next lane) is
+	// combined by one segmented scan per (block, warp). No cross-lane traffic per term, no padding beyond the groups of 4: the previous
+	// layout (8 words per lane and chunk + a 5-level scan per chunk) cost 27 instructions per term and lane, this one ~8.
+	// Stored as [group][lane][4 words] (one coalesced 16-byte load per lane and group); seg[2 (block * warps + w)] = {first word, T4}.
+	// Inside a lane's piece of a rid list the words are ordered so that the 8 lanes of a quarter warp address different 16-byte bank
+	// groups of the Gram block (offset mod 8) in every step where the lists allow it.
+	// conflictDegree (optional): average number of words per occupied bank group over all (quarter warp, step) sets; 1 = conflict free.
 	void buildGramTables(const pffrg_desc *d, int L, int Lp, int PB, int warps, std::vector<unsigned> &terms, std::vector<int> &seg, double *conflictDegree)
 	{
-		const int blocks = (Lp + PB - 1) / PB, maxMult = 1023;
+		const int blocks = (Lp + PB - 1) / PB, maxMult = 511;
 		std::vector<std::map<std::tuple<int, int, int, int>, int>> merged(L);
 		for (int rid = 0; rid < L; ++rid) merged[rid] = mergedOverlap(d, SU2, rid);
 		seg.assign((size_t)2 * blocks * warps, 0);
@@ -1006,9 +1061,76 @@ namespace
 					const unsigned offset = (unsigned)((p - blk * PB) * (Lp + 1) + q); // row stride of the Gram block: gramcfg::LpG
 					for (int m = kv.second; m > 0; m -= maxMult) lists[rid].push_back(offset | ((unsigned)rid << 14) | ((unsigned)std::min(m, maxMult) << 22));
 				}
-			// padding words: multiplicity 0, a free bank class (offsets 0..7 exist: a block has at least 8 rows)
-			const auto stats = layoutReductionPass(lists, 3, (1u << 14) - 1u, warps, [](int rid, int c) { return (unsigned)c | ((unsigned)rid << 14); }, terms, seg.data() + (size_t)2 * blk * warps);
-			sets += stats.first; degree += stats.second;
+			// whole lists to warps: longest first, to the least loaded warp
+			std::vector<int> order;
+			for (int rid = 0; rid < L; ++rid) if (!lists[rid].empty()) order.push_back(rid);
+			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lists[a].size() > lists[b].size(); });
+			std::vector<std::vector<int>> owned(warps);
+			std::vector<long> load(warps, 0);
+			for (int rid : order)
+			{
+				const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+				owned[w].push_back(rid); load[w] += ((long)lists[rid].size() + 3) / 4;
+			}
+			for (int w = 0; w < warps; ++w)
+			{
+				std::sort(owned[w].begin(), owned[w].end());
+				// the sequence of groups: (rid, last group of its list?)
+				std::vector<std::pair<int, bool>> groups;
+				for (int rid : owned[w])
+				{
+					const int n = ((int)lists[rid].size() + 3) / 4;
+					for (int g = 0; g < n; ++g) groups.push_back({ rid, g + 1 == n });
+				}
+				const int T4 = ((int)groups.size() + 31) / 32;
+				const size_t begin = terms.size();
+				seg[2 * ((size_t)blk * warps + w)] = (int)begin; seg[2 * ((size_t)blk * warps + w) + 1] = T4;
+				terms.resize(begin + (size_t)T4 * 128, 0u);
+				const int padRid = owned[w].empty() ? 0 : owned[w].back();
+				// remaining words of every list by bank class
+				std::map<int, std::vector<std::vector<unsigned>>> pool;
+				for (int rid : owned[w]) { auto &byClass = pool[rid]; byClass.resize(8); for (unsigned word : lists[rid]) byClass[word & 7u].push_back(word); }
+				std::vector<unsigned char> used((size_t)4 * T4 * 4, 0); // [quarter][group][k] -> classes taken
+				for (int lane = 0; lane < 32; ++lane)
+					for (int g = 0; g < T4; ++g)
+					{
+						const size_t gi = (size_t)lane * T4 + g;
+						const bool real = gi < groups.size();
+						const int rid = real ? groups[gi].first : padRid;
+						for (int k = 0; k < 4; ++k)
+						{
+							unsigned char &mask = used[((size_t)(lane / 8) * T4 + g) * 4 + k];
+							unsigned word;
+							int best = -1;
+							if (real)
+							{
+								auto &byClass = pool[rid];
+								for (int c = 0; c < 8; ++c) if (!byClass[c].empty() && !(mask & (1u << c)) && (best < 0 || byClass[c].size() > byClass[best].size())) best = c;
+								if (best < 0) for (int c = 0; c < 8; ++c) if (!byClass[c].empty() && (best < 0 || byClass[c].size() > byClass[best].size())) best = c;
+								if (best >= 0) { word = byClass[best].back(); byClass[best].pop_back(); }
+							}
+							if (best < 0)
+							{
+								// padding word: multiplicity 0, a free bank class (offsets 0..7 exist: a block has at least 8 rows)
+								int c = 0; while (c < 7 && (mask & (1u << c))) ++c;
+								word = (unsigned)c | ((unsigned)rid << 14); best = c;
+							}
+							mask |= (unsigned char)(1u << best);
+							if (real && groups[gi].second && k == 3) word |= 1u << 31;
+							terms[begin + ((size_t)g * 32 + lane) * 4 + k] = word;
+						}
+					}
+				for (auto &kv : pool) for (auto &v : kv.second) if (!v.empty()) abort(); // every word placed (a list's groups hold all of its words)
+				for (int q = 0; q < 4; ++q)
+					for (int g = 0; g < T4; ++g)
+						for (int k = 0; k < 4; ++k)
+						{
+							int count[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, occupied = 0;
+							for (int l = 8 * q; l < 8 * q + 8; ++l) ++count[terms[begin + ((size_t)g * 32 + l) * 4 + k] & 7u];
+							for (int c = 0; c < 8; ++c) occupied += count[c] > 0;
+							sets += 1.0; degree += 8.0 / occupied;
+						}
+			}
 		}
 		if (conflictDegree) *conflictDegree = sets > 0 ? degree / sets : 1.0;
 	}
@@ -1910,16 +2032,14 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	if (wantGram(d->core, uniquePairs))
 	{
 		const int Lp = paddedSites(L);
-		const int workers = threads / 32 * 32;
-		JitShape g = { 0, 0, 0, 0, 0 };
-		if (wantProducer() && workers + 32 * wantProducer() <= 1024) g = chooseGramShape(d->n_frequencies, L, Lp, groups, workers, 227 * 1024, uniquePairs, wantProducer());
-		if (!g.nb) g = chooseGramShape(d->n_frequencies, L, Lp, groups, threads, 227 * 1024, uniquePairs);
+		const GramLaunch launch = chooseGramLaunch(d->n_frequencies, L, Lp, groups, geo.stride, threads, 227 * 1024, uniquePairs);
+		const JitShape &g = launch.shape;
 		if (!g.nb) return fail(PFFRG_ERR_UNSUPPORTED, "no launch shape for the Gram form of the RPA phase");
 		std::vector<char> cubin;
-		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, g.producer ? workers + 32 * g.producer : threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g));
+		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, launch.threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g));
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
 		std::vector<unsigned> terms; std::vector<int> seg; double conflicts = 0.0;
-		buildGramTables(d, L, Lp, g.gramRows, threads / 32, terms, seg, &conflicts);
+		buildGramTables(d, L, Lp, g.gramRows, launch.reduceWarps, terms, seg, &conflicts);
 		if (getenv("PFFRG_JIT_VERBOSE")) fprintf(stderr, "[pffrg gram] threads %d nb %d nbt %d ctas %d smem %zu rows/block %d gemm threads %d words %zu (merged terms %lld) bank-conflict degree %.3f\n", threads, g.nb, g.nbt, g.minBlocks, g.smem, g.gramRows, g.gramThreads, terms.size(), (long long)uniquePairs, conflicts);
 		if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
 		return PFFRG_OK;

@@ -1177,6 +1177,9 @@ namespace pffrg
 #ifdef PFFRG_GRAM
 	// Barrier over the threads that run the RPA phase: the whole CTA, or -- with a producer warp (PFFRG_PRODUCER, v4FlowBodyProducer) -- the
 	// PFFRG_GRAM_THREADS worker threads on named barrier 5 (the producer warp builds access buffers meanwhile).
+#ifndef PFFRG_SPLIT_GATHER_THREADS
+#define PFFRG_SPLIT_GATHER_THREADS 0 // warp-specialised kernel (PFFRG_SPLIT, v4FlowBodySplit): the RPA warps follow this many gather threads
+#endif
 #ifdef PFFRG_PRODUCER
 	__device__ __forceinline__ void gramCtaSync() { asm volatile("bar.sync 5, %0;" :: "n"(PFFRG_GRAM_THREADS) : "memory"); }
 #else
@@ -1305,71 +1308,70 @@ namespace pffrg
 	}
 
 	// Reduction of one row block: rpaOut[c * L + rid] += sum over the block's terms of rid of multiplicity * Gs[offset].c.
-	// The terms of a block are one flat array of 32-bit words (offset | rid << 14 | multiplicity << 22), sorted by rid; every warp owns a
-	// contiguous range of whole rid lists (single writer per output), padded to whole chunks of 256 words. A lane reads 8 consecutive
-	// words per chunk (two 16-byte loads, the next chunk's in flight while this one is worked off); every rid list is padded to a
-	// multiple of 8 words, so the 8 words of a lane belong to ONE rid: 8 loads from Gs and 16 multiply-adds per lane, then one segmented
-	// scan over the lanes (rids ascend with the lane index) and the last lane of every segment updates the output. The host orders the
-	// words of a list so that the 8 lanes of a quarter warp hit 8 different 16-byte bank groups of Gs in every step (buildGramTables).
+	// The terms of a block are 32-bit words (offset | rid << 14 | multiplicity << 22 | flush << 31). Every warp owns whole rid lists (single
+	// writer per output and block); its words are stored as [group][lane][4]: lane l walks ITS groups serially -- one coalesced 16-byte
+	// load of four words, four 16-byte loads from Gs, eight multiply-adds into registers -- and adds its sum to the output where a rid
+	// list ends (flush flag on the last word of the group; all words of a group belong to one rid). What a lane still holds at the end
+	// (a list that continues in the next lane) is combined by ONE segmented scan per call. The host pads every list to whole groups only
+	// and orders the words so that the 8 lanes of a quarter warp hit different 16-byte bank groups of Gs (buildGramTables, pffrg.cu).
 	constexpr unsigned GRAM_OFFSET_MASK = (1u << 14) - 1u;
 	__device__ __forceinline__ void gramReduce(const Problem &P, int blk, const double2 *__restrict__ Gs, double *rpaOut, int warp, int lane, int warps)
 	{
 		constexpr int L = PFFRG_CONST_L;
+		constexpr int PF = 4; // groups in flight from the term array (L2)
 		const int2 range = __ldg(P.gram_seg + blk * warps + warp);
-		const int chunks = (range.y - range.x) >> 8;
-		if (chunks <= 0) return;
-		const uint4 *words = reinterpret_cast<const uint4 *>(P.gram_terms + range.x) + 2 * lane;
-		// two chunks per iteration: two independent dependency chains (products, scan) in flight
-		uint4 n[2][2];
+		const int T4 = range.y;
+		if (T4 <= 0) return;
+		const uint4 *words = reinterpret_cast<const uint4 *>(P.gram_terms + range.x) + lane;
+		uint4 n[PF];
 		#pragma unroll
-		for (int u = 0; u < 2; ++u) if (u < chunks) { n[u][0] = __ldg(words + 64 * u); n[u][1] = __ldg(words + 64 * u + 1); }
+		for (int u = 0; u < PF; ++u) if (u < T4) n[u] = __ldg(words + 32 * u);
+		double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0; // two partial chains per channel
+		unsigned last = 0u;
 		#pragma unroll 1
-		for (int c = 0; c < chunks; c += 2)
+		for (int g0 = 0; g0 < T4; g0 += PF)
 		{
-			int rid[2]; double sx[2], sy[2];
-			const bool second = c + 1 < chunks;
-			uint4 w4[2][2];
 			#pragma unroll
-			for (int u = 0; u < 2; ++u) { w4[u][0] = n[u][0]; w4[u][1] = n[u][1]; }
-			#pragma unroll
-			for (int u = 0; u < 2; ++u) if (c + 2 + u < chunks) { n[u][0] = __ldg(words + 64 * (c + 2 + u)); n[u][1] = __ldg(words + 64 * (c + 2 + u) + 1); }
-			#pragma unroll
-			for (int u = 0; u < 2; ++u)
+			for (int u = 0; u < PF; ++u)
 			{
-				const unsigned w[8] = { w4[u][0].x, w4[u][0].y, w4[u][0].z, w4[u][0].w, w4[u][1].x, w4[u][1].y, w4[u][1].z, w4[u][1].w };
-				rid[u] = (int)((w[0] >> 14) & 255u);
-				double2 g[8];
-				#pragma unroll
-				for (int k = 0; k < 8; ++k) g[k] = Gs[(u == 0 || second) ? (w[k] & GRAM_OFFSET_MASK) : 0u];
-				double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0; // two partial chains per channel
-				#pragma unroll
-				for (int k = 0; k < 8; k += 2)
+				if (g0 + u < T4) // warp-uniform
 				{
-					const double m0 = (double)(int)(w[k] >> 22), m1 = (double)(int)(w[k + 1] >> 22);
-					ax = fma(m0, g[k].x, ax); ay = fma(m0, g[k].y, ay);
-					bx = fma(m1, g[k + 1].x, bx); by = fma(m1, g[k + 1].y, by);
+					const uint4 w4 = n[u];
+					if (g0 + PF + u < T4) n[u] = __ldg(words + 32 * (g0 + PF + u));
+					const unsigned w[4] = { w4.x, w4.y, w4.z, w4.w };
+					double2 g[4];
+					#pragma unroll
+					for (int k = 0; k < 4; ++k) g[k] = Gs[w[k] & GRAM_OFFSET_MASK];
+					const double m0 = (double)(int)((w[0] >> 22) & 511u), m1 = (double)(int)((w[1] >> 22) & 511u), m2 = (double)(int)((w[2] >> 22) & 511u), m3 = (double)(int)((w[3] >> 22) & 511u);
+					ax = fma(m0, g[0].x, ax); ay = fma(m0, g[0].y, ay);
+					bx = fma(m1, g[1].x, bx); by = fma(m1, g[1].y, by);
+					ax = fma(m2, g[2].x, ax); ay = fma(m2, g[2].y, ay);
+					bx = fma(m3, g[3].x, bx); by = fma(m3, g[3].y, by);
+					last = w[3];
+					if (w[3] >> 31)
+					{
+						// the list of this rid ends here (exactly one lane of one warp gets here per rid and block)
+						const int rid = (int)((w[3] >> 14) & 255u);
+						rpaOut[rid] += ax + bx; rpaOut[L + rid] += ay + by;
+						ax = 0.0; ay = 0.0; bx = 0.0; by = 0.0;
+					}
 				}
-				sx[u] = ax + bx; sy[u] = ay + by;
-			}
-			#pragma unroll
-			for (int d = 1; d < 32; d <<= 1)
-			{
-				#pragma unroll
-				for (int u = 0; u < 2; ++u)
-				{
-					const double ox = __shfl_up_sync(0xffffffffu, sx[u], d), oy = __shfl_up_sync(0xffffffffu, sy[u], d);
-					const int orid = __shfl_up_sync(0xffffffffu, rid[u], d);
-					if (lane >= d && orid == rid[u]) { sx[u] += ox; sy[u] += oy; }
-				}
-			}
-			#pragma unroll
-			for (int u = 0; u < 2; ++u)
-			{
-				const int nextRid = __shfl_down_sync(0xffffffffu, rid[u], 1);
-				if ((u == 0 || second) && (lane == 31 || nextRid != rid[u])) { rpaOut[rid[u]] += sx[u]; rpaOut[L + rid[u]] += sy[u]; }
-				__syncwarp(); // the next chunk of this warp may continue the same rid
 			}
 		}
+		__syncwarp();
+		// lists that continue in the next lane: segmented sum over runs of lanes holding the same rid (zero where a lane ended on a flush)
+		const int rid = (int)((last >> 14) & 255u);
+		double sx = ax + bx, sy = ay + by;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const double ox = __shfl_up_sync(0xffffffffu, sx, d), oy = __shfl_up_sync(0xffffffffu, sy, d);
+			const int orid = __shfl_up_sync(0xffffffffu, rid, d);
+			if (lane >= d && orid == rid) { sx += ox; sy += oy; }
+		}
+		const int nextRid = __shfl_down_sync(0xffffffffu, rid, 1);
+		if (lane == 31 || nextRid != rid) { rpaOut[rid] += sx; rpaOut[L + rid] += sy; }
+		__syncwarp();
 	}
 
 	// RPA phase over `nb` staged nodes. All threads of the CTA call it (CTA barriers inside).
@@ -1377,7 +1379,7 @@ namespace pffrg
 	{
 		using namespace gramcfg;
 #ifdef PFFRG_PRODUCER
-		const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = NW; // called by the NT worker threads only
+		const int tid = threadIdx.x - PFFRG_SPLIT_GATHER_THREADS, warp = tid >> 5, lane = tid & 31, warps = NW; // called by the NT worker (PFFRG_SPLIT: RPA) threads only
 #else
 		const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = blockDim.x >> 5;
 #endif
@@ -2090,6 +2092,225 @@ namespace pffrg
 		gramCtaSync();
 		bool bad = false;
 		for (int e = tid; valid && e < C * L; e += NWORK)
+		{
+			double v = 0.0;
+			for (int k = 0; k < lay.rpaCopies; ++k) v += rpaOut[k * C * L + e];
+			for (int gg = 0; gg < cfg.groups; ++gg) v += part[gg * C * L + e];
+			v /= TWO_PI;
+			const int c = e / L, jj = e - c * L;
+			flow[(size_t)item * sizeRL(P) + channelOffset(vectorWidth(CORE), c, sizeLp(P)) + jj * vectorWidth(CORE)] = v;
+			bad |= (v != v);
+		}
+		if (bad) atomicOr(nanFlag, 1);
+	}
+#endif
+
+
+#if defined(PFFRG_GRAM) && defined(PFFRG_SPLIT)
+	// ================================================================================================================
+	// WARP-SPECIALISED SU2 flow kernel (Gram form of the RPA phase). In v4FlowBody / v4FlowBodyProducer the same warps gather and then run
+	// the RPA phase, so the two alternate: while the Gram update occupies the FP64 tensor cores nothing is in flight to the L1 / L2, and
+	// while the gathers wait for their rows (long scoreboard) the FP64 pipes idle (ncu, pyrochlore-r8: gather 49 % of the samples, RPA
+	// phases 26 %, one CTA per SM). Here the CTA consists of three kinds of warps, each a whole number of warp groups of 128 threads so
+	// that the register file can be re-partitioned between them (setmaxnreg):
+	//   gather warps  [0, NG)            access buffers -> rows -> bilinear forms, accumulators in registers; t-channel nodes stage their RPA operands
+	//   RPA warps     [NG, NG + NR)      Gram update on the FP64 tensor cores + walk of the overlap list (rpaGram) over the staged nodes
+	//   producer warps (the last group)  build the access-buffer tables one batch ahead (as in v4FlowBodyProducer)
+	// Schedule of a work item: its t-channel nodes are worked off in R rounds of NBT nodes; the nodes of the s and u channels (no staging,
+	// two thirds of all gathers) are cut into R chunks, and chunk r is gathered WHILE the RPA warps work on round r:
+	//   gather:  [t round 0] arrive(FULL) [s/u chunk 0] sync(EMPTY) [t round 1] arrive(FULL) [s/u chunk 1] sync(EMPTY) ... epilogue
+	//   RPA:                 sync(FULL) rpaGram(round 0) arrive(EMPTY)          sync(FULL) rpaGram(round 1) arrive(EMPTY)
+	// so one staging area suffices. Named barriers: 5 RPA warps (inside rpaGram), 6/7 + 8/9 table blocks full / empty (gather + producer),
+	// 10 producer warps, 11 staging area full, 12 staging area empty (gather + RPA), 13 gather warps (epilogue).
+	// Same arithmetic per node as v4FlowBody<SU2, NB, NBT, true>; the nodes of an item enter its sums in a different order.
+	// ================================================================================================================
+	template <int V> struct RoleTag { static constexpr int value = V; };
+	template <int REGS> __device__ __forceinline__ void regsInc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(REGS)); }
+	template <int REGS> __device__ __forceinline__ void regsDec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(REGS)); }
+
+	template <int NB, int NBT>
+	__device__ __forceinline__ void v4FlowBodySplit(const Problem &P, const NodeTable &N, const FlowConfig &cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
+	{
+		constexpr int CORE = SU2, C = 2;
+		constexpr int NG = PFFRG_SPLIT_GATHER_THREADS; // gather threads (a multiple of 128; the first cfg.groups * cfg.stride of them work)
+		constexpr int NR = PFFRG_GRAM_THREADS;         // RPA threads (a multiple of 128)
+		constexpr int NPROD = 32 * PFFRG_PRODUCER;     // producer threads (1..4 warps of the last warp group)
+		constexpr int TBL = NG + NPROD, STG = NG + NR; // participants of the table / staging barriers
+		static_assert(NG % 128 == 0 && NR % 128 == 0 && NPROD >= 32 && NPROD <= 128, "warp groups");
+		extern __shared__ __align__(16) unsigned char smemRaw[];
+		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT, 1, gramcfg::PB, gramcfg::Lp, 2);
+		const int tid = threadIdx.x;
+		const int role = tid < NG ? 0 : (tid < NG + NR ? 1 : 2); // warp-group uniform
+		const int ptid = tid - NG - NR;
+		auto producerSync = [&]() { if (NPROD == 32) __syncwarp(); else namedSync(10, NPROD); };
+		double *mesh = reinterpret_cast<double *>(smemRaw + lay.mesh);
+		auto tableBase = [&](int buf) { return smemRaw + (size_t)buf * lay.privateBytes; };
+		double *st = reinterpret_cast<double *>(smemRaw + lay.st);
+		double *part = reinterpret_cast<double *>(smemRaw + lay.part);
+		double *rpaOut = reinterpret_cast<double *>(smemRaw + lay.rpa);
+		const int L = sizeL(P), nw = sizeNw(P);
+
+		for (int i = tid; i < nw; i += blockDim.x) mesh[i] = P.mesh[i];
+		for (int i = tid; i < lay.rpaCopies * C * L; i += blockDim.x) rpaOut[i] = 0.0;
+		for (int i = tid; i < 2 * NBT * (gramcfg::LpS - L); i += blockDim.x)
+			reinterpret_cast<double2 *>(st)[(i / (gramcfg::LpS - L)) * gramcfg::LpS + L + i % (gramcfg::LpS - L)] = make_double2(0.0, 0.0);
+
+		const int itemEnd = itemBegin + cfg.items;
+		const int itemFirst = itemBegin + blockIdx.x;
+		const bool valid = itemFirst < itemEnd;
+		const int item = valid ? itemFirst : itemEnd - 1;
+		const int su = item / nw, ti = item - su * nw;
+		int so = (int)((sqrt(8.0 * su + 1.0) - 1.0) * 0.5);
+		while ((so + 1) * (so + 2) / 2 <= su) ++so;
+		while (so * (so + 1) / 2 > su) --so;
+		const int uo = su - so * (so + 1) / 2;
+		__syncthreads(); // the only barrier over all threads
+
+		// the schedule (identical on all warps): R rounds of t-channel batches, each followed by a chunk of the s/u batches
+		const int nT = valid ? N.count[ti] : 0, nS = valid ? N.count[so] : 0, nSU = valid ? nS + N.count[uo] : 0;
+		const int R = valid ? max(1, (nT + NBT - 1) / NBT) : 0;
+		const int suBatches = (nSU + 2 * NB - 1) / (2 * NB);
+
+		if (role == 1)
+		{
+			// ---- RPA warps
+			regsInc<PFFRG_SPLIT_REGS_RPA>();
+			#pragma unroll 1
+			for (int r = 0; r < R; ++r)
+			{
+				namedSync(11, STG); // the operands of round r are staged
+				rpaGram(P, reinterpret_cast<const double2 *>(st), NBT, min(NBT, nT - r * NBT), reinterpret_cast<double2 *>(smemRaw + lay.gram), rpaOut);
+				namedArrive(12, STG); // the staging area may be overwritten; rpaOut holds the round (read after the last round only)
+			}
+			return;
+		}
+		ItemFrequencies f;
+		f.s = mesh[so]; f.t = mesh[ti]; f.u = mesh[uo];
+		f.w1p = 0.5 * (f.s + f.t + f.u); f.w1 = 0.5 * (f.s - f.t + f.u); f.w2p = 0.5 * (f.s - f.t - f.u); f.w2 = 0.5 * (f.s + f.t - f.u);
+		const int g = tid / cfg.stride, j = tid - g * cfg.stride;
+		const bool worker = role == 0 && g < cfg.groups && j < L;
+		double acc[C] = { 0.0, 0.0 };
+
+		// The schedule, instantiated once per role (ROLE = 2: producer warps, 0: gather warps) so that the two run separate code with
+		// their own register budgets (code reachable after setmaxnreg.dec has to fit the producer's 40 registers).
+		auto runSchedule = [&](auto roleTag)
+		{
+			constexpr int ROLE = decltype(roleTag)::value;
+			int siteFwd = 0, siteInv = 0;
+			if (ROLE == 0 && worker) { siteFwd = P.sites_rid[j]; siteInv = P.inv_rid[j]; }
+			int batchNo = 0; // batches handed over so far (the same sequence on both sides)
+			// one batch of nodes [b0, b0 + nb) of the t channel (operands staged at `staged`) or of the s/u node list
+			auto doBatch = [&](const bool tPass, const int b0, const int nb, const int staged)
+			{
+				const int nFirst = tPass ? nT : nS;
+				const int nbuf = tPass ? 8 : 4;
+				const int buf = batchNo & 1;
+				unsigned char *tb = tableBase(buf);
+				double *bW = reinterpret_cast<double *>(tb + lay.bW);
+				AccessBuffer *abTable = reinterpret_cast<AccessBuffer *>(tb + lay.ab);
+				double *loc = reinterpret_cast<double *>(tb + lay.loc);
+				if constexpr (ROLE == 2)
+				{
+					const double *nodeW0 = N.wp + (size_t)(tPass ? ti : so) * N.stride, *nodeWt0 = N.wt + (size_t)(tPass ? ti : so) * N.stride;
+					const double *nodeW1 = N.wp + (size_t)uo * N.stride, *nodeWt1 = N.wt + (size_t)uo * N.stride;
+					LerpRecord *lerp = reinterpret_cast<LerpRecord *>(tb + lay.lerp);
+					if (batchNo >= 2) namedSync(8 + buf, TBL); // the gather warps are done with this block
+					// ---- phase 0, step A: the four interpolated frequencies of every node (one mesh search each)
+					for (int idx = ptid; idx < nb * 4; idx += NPROD)
+					{
+						const int node = idx >> 2, q = idx & 3;
+						const int gn = b0 + node;
+						const int ch = tPass ? CH_T : (gn < nFirst ? CH_S : CH_U);
+						const double wp = gn < nFirst ? nodeW0[gn] : nodeW1[gn - nFirst];
+						if (q == 0)
+						{
+							const double wt = gn < nFirst ? nodeWt0[gn] : nodeWt1[gn - nFirst];
+							bW[node] = ch == CH_U ? -wt : wt; // SU2: the u channel enters with a minus sign (SU2FrgCore.cpp:366,370,376)
+						}
+						makeLerpRecord(mesh, nw, P.meshIndex, nodeQuantity(ch, q, f.w1p, f.w1, f.w2p, f.w2, wp), lerp[idx]);
+					}
+					producerSync();
+					// ---- step B: assemble the buffers; site-0 values of the t channel's buffers 4..7 (getValueLocal) right away
+					for (int idx = ptid; idx < nb * nbuf; idx += NPROD)
+					{
+						const int node = idx / nbuf, b = idx - node * nbuf;
+						const int ch = tPass ? CH_T : ((b0 + node) < nFirst ? CH_S : CH_U);
+						assembleAccessBuffer<CORE>(nw, ch, b, ch == CH_S ? so : (ch == CH_T ? ti : uo), lerp + 4 * node, abTable[idx]);
+						if (tPass && b >= 4)
+						{
+							const AccessBuffer &ab = abTable[idx];
+							double v0 = 0.0, v1 = 0.0;
+							#pragma unroll
+							for (int k = 0; k < 4; ++k)
+							{
+								const double2 x = __ldg(reinterpret_cast<const double2 *>(v4 + (size_t)ab.row[k] * sizeRL(P)));
+								v0 += supportSign<CORE>(ab.flags, k, 0) * ab.w[k] * x.x;
+								v1 += supportSign<CORE>(ab.flags, k, 1) * ab.w[k] * x.y;
+							}
+							loc[(node * 4 + (b - 4)) * C] = v0; loc[(node * 4 + (b - 4)) * C + 1] = v1;
+						}
+					}
+					namedArrive(6 + buf, TBL); // block `buf` is ready
+				}
+				else
+				{
+					namedSync(6 + buf, TBL); // wait for the producer
+					// ---- phase 1: gathers + bilinear forms
+					if (worker)
+					{
+						for (int node = g; node < nb; node += cfg.groups)
+						{
+							double A[4][C];
+							const AccessBuffer *ab = abTable + node * nbuf;
+							#pragma unroll
+							for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, ab[b], siteFwd, siteInv, PERM_IDENTITY, PERM_IDENTITY, A[b]);
+							const double W = bW[node];
+							double K[C];
+							if (!tPass) ladderTerms<CORE>((b0 + node) < nFirst ? CH_S : CH_U, A, K);
+							else
+							{
+								chaliceTerms<CORE>(A, loc + node * 4 * C, K);
+								// RPA operands: buffers 2 and 3 with prefactors 2S (spin) and 8S (density), SU2FrgCore.cpp:257-266; node weight folded into A
+								double2 *st2 = reinterpret_cast<double2 *>(st);
+								st2[(staged + node) * gramcfg::LpS + j] = make_double2(W * 2.0 * P.spin * A[2][0], W * 8.0 * P.spin * A[2][1]);
+								st2[(NBT + staged + node) * gramcfg::LpS + j] = make_double2(A[3][0], A[3][1]);
+							}
+							acc[0] += W * K[0]; acc[1] += W * K[1];
+						}
+					}
+					namedArrive(8 + buf, TBL); // done with block `buf`
+				}
+				++batchNo;
+			};
+			#pragma unroll 1
+			for (int r = 0; r < R; ++r)
+			{
+				const int lo = r * NBT, hi = min(nT, lo + NBT);
+				#pragma unroll 1
+				for (int b0 = lo; b0 < hi; b0 += NB) doBatch(true, b0, min(NB, hi - b0), b0 - lo);
+				if (ROLE == 0) namedArrive(11, STG); // round r is staged: the RPA warps take over
+				const int sbEnd = (r + 1) * suBatches / R;
+				#pragma unroll 1
+				for (int sb = r * suBatches / R; sb < sbEnd; ++sb) doBatch(false, sb * 2 * NB, min(2 * NB, nSU - sb * 2 * NB), 0);
+				if (ROLE == 0) namedSync(12, STG); // the RPA warps are done with the staging area
+			}
+		};
+		if (role == 2)
+		{
+			// ---- producer warps
+			regsDec<PFFRG_SPLIT_REGS_PRODUCER>();
+			if (ptid < NPROD) runSchedule(RoleTag<2>());
+			return;
+		}
+		// ---- gather warps
+		regsInc<PFFRG_SPLIT_REGS_GATHER>();
+		runSchedule(RoleTag<0>());
+
+		// ---- epilogue (gather warps; the partial sums reuse the staging area, dead after the last sync(EMPTY))
+		if (worker) { part[(g * C) * L + j] = acc[0]; part[(g * C + 1) * L + j] = acc[1]; }
+		namedSync(13, NG);
+		bool bad = false;
+		for (int e = tid; valid && e < C * L; e += NG)
 		{
 			double v = 0.0;
 			for (int k = 0; k < lay.rpaCopies; ++k) v += rpaOut[k * C * L + e];

@@ -44,6 +44,9 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             # SU2 Gram kernel with a producer warp that builds the access buffers one batch ahead of the workers
             {"PFFRG_RPA": "gram", "PFFRG_PRODUCER": "1"}, {"PFFRG_RPA": "gram", "PFFRG_PRODUCER": "1", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"},
             {"PFFRG_RPA": "gram", "PFFRG_PRODUCER": "1", "PFFRG_THREADS": "128", "PFFRG_JIT_MINBLOCKS": "2"}, {"PFFRG_RPA": "gram", "PFFRG_PRODUCER": "2"},
+            # warp-specialised SU2 Gram kernel (gather / RPA / producer warp groups): default, several RPA rounds per item, one gather group + one producer warp
+            {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1"}, {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1", "PFFRG_JIT_NBT": "8", "PFFRG_JIT_NB": "8"},
+            {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1", "PFFRG_THREADS": "128", "PFFRG_PRODUCER": "1"},
             {"PFFRG_RPA": "table"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "1"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "2", "PFFRG_THREADS": "128"}]
 
 
@@ -54,7 +57,7 @@ def test_one_step_flow_matches_reference(case, variant, monkeypatch):
         pytest.skip("the TRI core has no run-time compiled variant")
     if "PFFRG_RPA" in variant and case.startswith("xyz"):
         pytest.skip("the XYZ core has one form of the RPA phase")
-    if not case.startswith("su2") and "PFFRG_PRODUCER" in variant:
+    if not case.startswith("su2") and ("PFFRG_PRODUCER" in variant or "PFFRG_SPLIT" in variant):
         pytest.skip("SU2 only")
     if case.startswith("tri") and variant.get("PFFRG_RPA") == "gram" and len(variant) > 1 and "PFFRG_TRIGRAM_RESIDENT" not in variant:
         pytest.skip("SU2 shape knobs")

@@ -81,18 +81,38 @@ def _emulate(L, Lp, threads, PB, nodes, A, B, terms, seg):
         assert written == min(rows, Lp - blk * PB) * Lp
         owner = {}
         for warp in range(NW):
-            begin, end = seg[blk * NW + warp]
-            assert begin % 256 == 0 and (end - begin) % 256 == 0 and end >= begin
-            for chunk in range((end - begin) // 256):
-                for lane in range(32):
-                    w = terms[begin + 256 * chunk + 8 * lane:begin + 256 * chunk + 8 * lane + 8].astype(np.int64)
-                    rid = int((w[0] >> 14) & 255)
-                    mult = w >> 22
-                    assert np.all(((w >> 14) & 255)[mult > 0] == rid), "the 8 words of a lane belong to one rid"
-                    assert owner.setdefault(rid, warp) == warp or not mult.any(), "single writer per output and block"
-                    g = Gs[w & 0x3FFF]
-                    assert not np.isnan(g[mult > 0]).any()
-                    out[rid] += float(np.sum(np.where(mult > 0, mult * np.nan_to_num(g), 0.0)))
+            begin, T4 = seg[blk * NW + warp]
+            assert begin % 4 == 0 and T4 >= 0
+            words = terms[begin:begin + 128 * T4].astype(np.int64).reshape(T4, 32, 4)  # [group][lane][4]
+            trailing = []
+            for lane in range(32):
+                acc, last = 0.0, 0
+                for g in range(T4):
+                    w = words[g, lane]
+                    rid = int((w[3] >> 14) & 255)
+                    mult = (w >> 22) & 511
+                    assert np.all(((w >> 14) & 255) == rid), "the words of a group belong to one rid"
+                    assert not (w[:3] >> 31).any(), "flush flag on the last word of a group only"
+                    val = Gs[w & 0x3FFF]
+                    assert not np.isnan(val[mult > 0]).any()
+                    acc += float(np.sum(np.where(mult > 0, mult * np.nan_to_num(val), 0.0)))
+                    last = rid
+                    if mult.any() or (w[3] >> 31):
+                        assert owner.setdefault(rid, warp) == warp, "single writer per output and block"
+                    if w[3] >> 31:
+                        out[rid] += acc
+                        acc = 0.0
+                trailing.append((last, acc))
+            # what the lanes still hold: runs of equal rid over consecutive lanes (the segmented scan of gramReduce)
+            for lane, (rid, acc) in enumerate(trailing):
+                if acc != 0.0:
+                    assert owner.get(rid, warp) == warp
+                out[rid] += acc
+            seen, prev = set(), None
+            for r, a in trailing:
+                if r != prev:
+                    assert r not in seen or a == 0.0, "a rid's unfinished pieces sit in consecutive lanes"
+                    seen.add(r); prev = r
     return out
 
 
@@ -116,7 +136,7 @@ def test_gram_tables_reproduce_the_overlap_sum(case, threads, pb):
             want[rid] += float(np.dot(A[:nodes, r1[i]], B[:nodes, r2[i]]))
     assert np.allclose(got, want, rtol=1e-12, atol=1e-12), np.abs(got - want).max()
     # every overlap entry is represented exactly once (multiplicities add up)
-    assert int(np.sum(terms.astype(np.int64) >> 22)) == int(off[-1])
+    assert int(np.sum((terms.astype(np.int64) >> 22) & 511)) == int(off[-1])
     assert 1.0 <= degree <= 8.0
 
 
@@ -128,7 +148,7 @@ def test_term_order_of_the_benchmark_lattice_is_nearly_conflict_free():
     d = read_pfd(os.path.join(ROOT, "bench_data", "pyrochlore_r8_su2_nw64.tables.pfd"))
     t, L, Lp, blocks, terms, seg, degree = _tables(d, 56, 8)
     assert blocks == 2 and L == 103
-    assert int(np.sum(terms.astype(np.int64) >> 22)) == int(t.overlap_offsets[-1])
+    assert int(np.sum((terms.astype(np.int64) >> 22) & 511)) == int(t.overlap_offsets[-1])
     assert len(terms) < 1.15 * 40355, "padding overhead of the term array"
     assert degree < 1.5, degree  # a random order gives ~2.5
 

@@ -30,7 +30,7 @@ WORKLOADS = {
     "square_r4_su2_nw32": (100, [], [{}, {"PFFRG_AUTOTUNE": "1"}, {"PFFRG_RPA": "gram"}]),
     "cubic_r7_su2_nw64": (211, [], [{}, {"PFFRG_AUTOTUNE": "1"}, {"PFFRG_RPA": "gram"}]),
     "honeycomb_kitaev_r7_xyz_nw64": (211, [], [{}, {"PFFRG_AUTOTUNE": "1"}]),
-    "pyrochlore_r8_su2_nw64": (211, [], [{}, {"PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}, {"PFFRG_PRODUCER": "1"}]),
+    "pyrochlore_r8_su2_nw64": (211, [], [{}, {"PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}, {"PFFRG_PRODUCER": "1"}, {"PFFRG_SPLIT": "1"}]),
     "kagome_dm_r7_tri_nw64": (120, [211], [{}, {"PFFRG_RPA": "gram"}]),
 }
 
@@ -42,7 +42,7 @@ def _tables(workload):
 
 def _core(d, env, monkeypatch):
     from spinparser_b200 import FrgCoreFactory, ProblemTables
-    for k in ("PFFRG_AUTOTUNE", "PFFRG_RPA", "PFFRG_JIT_NBT", "PFFRG_JIT_NB", "PFFRG_PRODUCER"):
+    for k in ("PFFRG_AUTOTUNE", "PFFRG_RPA", "PFFRG_JIT_NBT", "PFFRG_JIT_NB", "PFFRG_PRODUCER", "PFFRG_SPLIT"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
