@@ -1244,8 +1244,8 @@ namespace pffrg
 	// step of four nodes it loads MI + NI fragments (16 bytes per lane = the operand of both channels; a quarter warp reads 4 nodes x 2
 	// sites from 8 different bank groups) for 2 MI NI updates of 256 multiply-adds each -- the register-tiled FP64 FMA form of this
 	// update moved 4 x more shared-memory wavefronts and was bound by them (ncu: 4 wavefronts per 16-byte load, whatever the lanes share).
-	template <int RT>
-	__device__ __forceinline__ void gramBlock(const double2 *__restrict__ stA, const double2 *__restrict__ stB, int nb, int rowBase, double2 *__restrict__ Gs, int warp, int lane)
+	template <int RT, class Hook>
+	__device__ __forceinline__ void gramBlock(const double2 *__restrict__ stA, const double2 *__restrict__ stB, int nb, int rowBase, double2 *__restrict__ Gs, int warp, int lane, Hook afterUpdate)
 	{
 		using namespace gramcfg;
 		constexpr int WP = bestRowWarps(RT), WQ = NW / WP;
@@ -1289,6 +1289,7 @@ namespace pffrg
 				}
 			}
 		}
+		afterUpdate(); // (the first term words of this block's reduction are requested here: their L2 latency passes behind the barriers and the store)
 		gramCtaSync(); // the reduction of the previous block has read Gs
 		#pragma unroll
 		for (int i = 0; i < MI; ++i)
@@ -1315,49 +1316,63 @@ namespace pffrg
 	// (a list that continues in the next lane) is combined by ONE segmented scan per call. The host pads every list to whole groups only
 	// and orders the words so that the 8 lanes of a quarter warp hit different 16-byte bank groups of Gs (buildGramTables, pffrg.cu).
 	constexpr unsigned GRAM_OFFSET_MASK = (1u << 14) - 1u;
-	__device__ __forceinline__ void gramReduce(const Problem &P, int blk, const double2 *__restrict__ Gs, double *rpaOut, int warp, int lane, int warps)
+#ifndef PFFRG_GRAM_PREFETCH
+#define PFFRG_GRAM_PREFETCH 8
+#endif
+	struct GramStream { const uint4 *words; int T4; uint4 n[PFFRG_GRAM_PREFETCH]; }; // the term words of one (block, warp) and the groups in flight
+	__device__ __forceinline__ void gramReducePrefetch(const Problem &P, int blk, int warp, int lane, int warps, GramStream &S)
+	{
+		const int2 range = __ldg(P.gram_seg + blk * warps + warp);
+		S.T4 = range.y;
+		S.words = reinterpret_cast<const uint4 *>(P.gram_terms + range.x) + lane;
+		if (S.T4 <= 0) return;
+		#pragma unroll
+		for (int u = 0; u < PFFRG_GRAM_PREFETCH; ++u) S.n[u] = __ldg(S.words + 32 * min(u, S.T4 - 1)); // (clamped: a re-load of the last group instead of a predicate)
+	}
+	__device__ __forceinline__ void gramReduce(GramStream &S, const double2 *__restrict__ Gs, double *rpaOut, int lane)
 	{
 		constexpr int L = PFFRG_CONST_L;
-		constexpr int PF = 4; // groups in flight from the term array (L2)
-		const int2 range = __ldg(P.gram_seg + blk * warps + warp);
-		const int T4 = range.y;
+		constexpr int PF = PFFRG_GRAM_PREFETCH; // groups in flight from the term array (L2: ~800 clocks, ~60 clocks of work per group)
+		const int T4 = S.T4;
 		if (T4 <= 0) return;
-		const uint4 *words = reinterpret_cast<const uint4 *>(P.gram_terms + range.x) + lane;
-		uint4 n[PF];
-		#pragma unroll
-		for (int u = 0; u < PF; ++u) if (u < T4) n[u] = __ldg(words + 32 * u);
+		const uint4 *words = S.words;
+		uint4 (&n)[PF] = S.n;
 		double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0; // two partial chains per channel
 		unsigned last = 0u;
+		auto group = [&](const uint4 w4)
+		{
+			const unsigned w[4] = { w4.x, w4.y, w4.z, w4.w };
+			double2 g[4];
+			#pragma unroll
+			for (int k = 0; k < 4; ++k) g[k] = Gs[w[k] & GRAM_OFFSET_MASK];
+			const double m0 = (double)(int)((w[0] >> 22) & 511u), m1 = (double)(int)((w[1] >> 22) & 511u), m2 = (double)(int)((w[2] >> 22) & 511u), m3 = (double)(int)((w[3] >> 22) & 511u);
+			ax = fma(m0, g[0].x, ax); ay = fma(m0, g[0].y, ay);
+			bx = fma(m1, g[1].x, bx); by = fma(m1, g[1].y, by);
+			ax = fma(m2, g[2].x, ax); ay = fma(m2, g[2].y, ay);
+			bx = fma(m3, g[3].x, bx); by = fma(m3, g[3].y, by);
+			last = w[3];
+			if (w[3] >> 31)
+			{
+				// the list of this rid ends here (exactly one lane of one warp gets here per rid and block)
+				const int rid = (int)((w[3] >> 14) & 255u);
+				rpaOut[rid] += ax + bx; rpaOut[L + rid] += ay + by;
+				ax = 0.0; ay = 0.0; bx = 0.0; by = 0.0;
+			}
+		};
+		int g0 = 0;
 		#pragma unroll 1
-		for (int g0 = 0; g0 < T4; g0 += PF)
+		for (; g0 + PF <= T4; g0 += PF)
 		{
 			#pragma unroll
 			for (int u = 0; u < PF; ++u)
 			{
-				if (g0 + u < T4) // warp-uniform
-				{
-					const uint4 w4 = n[u];
-					if (g0 + PF + u < T4) n[u] = __ldg(words + 32 * (g0 + PF + u));
-					const unsigned w[4] = { w4.x, w4.y, w4.z, w4.w };
-					double2 g[4];
-					#pragma unroll
-					for (int k = 0; k < 4; ++k) g[k] = Gs[w[k] & GRAM_OFFSET_MASK];
-					const double m0 = (double)(int)((w[0] >> 22) & 511u), m1 = (double)(int)((w[1] >> 22) & 511u), m2 = (double)(int)((w[2] >> 22) & 511u), m3 = (double)(int)((w[3] >> 22) & 511u);
-					ax = fma(m0, g[0].x, ax); ay = fma(m0, g[0].y, ay);
-					bx = fma(m1, g[1].x, bx); by = fma(m1, g[1].y, by);
-					ax = fma(m2, g[2].x, ax); ay = fma(m2, g[2].y, ay);
-					bx = fma(m3, g[3].x, bx); by = fma(m3, g[3].y, by);
-					last = w[3];
-					if (w[3] >> 31)
-					{
-						// the list of this rid ends here (exactly one lane of one warp gets here per rid and block)
-						const int rid = (int)((w[3] >> 14) & 255u);
-						rpaOut[rid] += ax + bx; rpaOut[L + rid] += ay + by;
-						ax = 0.0; ay = 0.0; bx = 0.0; by = 0.0;
-					}
-				}
+				const uint4 w4 = n[u];
+				n[u] = __ldg(words + 32 * min(g0 + PF + u, T4 - 1));
+				group(w4);
 			}
 		}
+		#pragma unroll
+		for (int u = 0; u < PF - 1; ++u) if (g0 + u < T4) group(n[u]); // (warp-uniform)
 		__syncwarp();
 		// lists that continue in the next lane: segmented sum over runs of lanes holding the same rid (zero where a lane ended on a flush)
 		const int rid = (int)((last >> 14) & 255u);
@@ -1385,16 +1400,19 @@ namespace pffrg
 #endif
 		const bool gemm = tid < NT;
 		const double2 *stA = st2, *stB = st2 + (size_t)nodeCapacity * LpS;
+		GramStream S;
 		#pragma unroll 1
 		for (int blk = 0; blk < NBLK - 1; ++blk)
 		{
-			if (gemm) gramBlock<PB / 8>(stA, stB, nb, blk * PB, Gs, warp, lane); else gramCtaSync();
+			auto prefetch = [&]() { gramReducePrefetch(P, blk, warp, lane, warps, S); };
+			if (gemm) gramBlock<PB / 8>(stA, stB, nb, blk * PB, Gs, warp, lane, prefetch); else { prefetch(); gramCtaSync(); }
 			gramCtaSync();
-			gramReduce(P, blk, Gs, rpaOut, warp, lane, warps);
+			gramReduce(S, Gs, rpaOut, lane);
 		}
-		if (gemm) gramBlock<(LAST_ROWS + 7) / 8>(stA, stB, nb, (NBLK - 1) * PB, Gs, warp, lane); else gramCtaSync();
+		auto prefetch = [&]() { gramReducePrefetch(P, NBLK - 1, warp, lane, warps, S); };
+		if (gemm) gramBlock<(LAST_ROWS + 7) / 8>(stA, stB, nb, (NBLK - 1) * PB, Gs, warp, lane, prefetch); else { prefetch(); gramCtaSync(); }
 		gramCtaSync();
-		gramReduce(P, NBLK - 1, Gs, rpaOut, warp, lane, warps);
+		gramReduce(S, Gs, rpaOut, lane);
 	}
 #endif
 
