@@ -518,7 +518,7 @@ def main():
             "alg_gb_per_step": alg_bytes / 1e9, "alg_gflop_per_step": alg_flops / 1e9, "exec_gflop_per_step": exec_flops / 1e9,
             "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
             "breakdown_ms": {k: statistics.mean(st[k] for _, _, st in records) for k in ("ms_v2_flow", "ms_node_table", "ms_v4_flow", "ms_finalize", "ms_exchange")},
-            "launch_shape": {k: records[0][2][k] for k in ("jit_rpa", "gram_rows", "rpa_terms_merged", "threads", "smem_bytes", "node_batch", "rpa_batch", "rpa_warps", "min_blocks", "sub_ctas", "autotuned_shapes", "jit_compile_ms")},
+            "launch_shape": {k: records[0][2][k] for k in ("jit_rpa", "gram_rows", "rpa_terms_merged", "threads", "smem_bytes", "node_batch", "rpa_batch", "rpa_warps", "min_blocks", "sub_ctas", "autotuned_shapes", "jit_compile_ms", "gather_threads", "producer_warps")},
             "roofline": {"bound": bound, "kernel": "pffrg_v4flow_jit" if records[0][2]["jit_rpa"] else "pffrg::v4FlowKernel", **{k: candidates[bound][k] for k in ("achieved", "peak", "unit", "frac")},
                          "traffic": traffic, "candidates": candidates,
                          "alg_hbm": {"achieved": alg_gbs, "peak": peak, "unit": "GB/s", "frac": alg_gbs / peak, "peak_source": peak_src,

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PFFRG_ABI_VERSION 2
+#define PFFRG_ABI_VERSION 3
 
 typedef enum pffrg_status
 {
@@ -101,6 +101,8 @@ typedef struct pffrg_stats
 	int32_t rpa_terms_merged; /* overlap terms after merging equal (rid1, rid2[, permutations]) pairs: what the RPA phase walks */
 	double exec_flops;      /* FP64 flops the kernels execute for this rank's share: as alg_flops, but the RPA term counted as implemented
 	                           (merged terms per node for the straight-line / word-stream forms; L^2 per node + merged terms per RPA phase for the Gram form) */
+	int32_t gather_threads; /* > 0: warp-specialised flow kernel (gather / RPA / producer warp groups in one CTA) with this many gather threads; */
+	int32_t producer_warps; /*   warps that build the access-buffer tables ahead of the gather warps (0: the gather warps build their own) */
 } pffrg_stats;
 
 /* library / environment ------------------------------------------------------------------------------------------ */

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpffrg.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 CORE_IDS = {"SU2": 0, "XYZ": 1, "TRI": 2}
 F32, F64 = 0, 1
 UNIQUE_ID_BYTES = 128
@@ -57,6 +57,7 @@ class Stats(C.Structure):
         ("alg_bytes", C.c_double), ("alg_flops", C.c_double), ("launches", C.c_int32), ("jit_rpa", C.c_int32), ("jit_compile_ms", C.c_double),
         ("threads", C.c_int32), ("smem_bytes", C.c_int32), ("node_batch", C.c_int32), ("rpa_batch", C.c_int32), ("rpa_warps", C.c_int32), ("min_blocks", C.c_int32), ("autotuned_shapes", C.c_int32), ("sub_ctas", C.c_int32),
         ("gram_rows", C.c_int32), ("rpa_terms_merged", C.c_int32), ("exec_flops", C.c_double),
+        ("gather_threads", C.c_int32), ("producer_warps", C.c_int32),
     ]
 
     def as_dict(self):

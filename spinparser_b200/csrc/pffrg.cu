@@ -125,6 +125,7 @@ struct pffrg_context
 	DeviceArray<unsigned> dWords;
 	DeviceArray<unsigned> dGramTerms; DeviceArray<int> dGramSeg; // Gram form of the RPA phase (rpaGram), when selected
 	int gramRows = 0;                                                 // rows per Gram block (0: not in use); TRI Gram form: resident channel-pair blocks
+	int splitGather = 0, producerWarps = 0;                           // warp-specialised kernel: gather threads (0: not split); producer warps
 	DeviceArray<unsigned short> dTriBlocks; int triRounds = 0;         // TRI Gram form: channel pairs per (round, slot)
 	int64_t triBlockCount = 0, gramWords = 0;                          // Gram forms: needed channel-pair blocks (TRI), words walked per RPA phase
 	int itemOrder = 0;                                                // FlowConfig::order of the run-time compiled kernel (PFFRG_ORDER=t: t-major)
@@ -243,7 +244,7 @@ namespace
 	// warps (one per SM sub-partition when there are four), each on its own group of 16 (SU2) or 32 staged nodes, so the
 	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Environment overrides for tuning runs:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_TILES, PFFRG_JIT_MINBLOCKS.
-	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0; int producer = 0; /* producer warps */ int splitGather = 0; /* warp-specialised kernel: gather threads (0: not split) */ int regsGather = 0, regsRpa = 0, regsProducer = 0; };
+	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0; int producer = 0; /* producer warps */ int splitGather = 0; /* warp-specialised kernel: gather threads (0: not split) */ int regsGather = 0, regsRpa = 0, regsProducer = 0, regsLaunch = 0; };
 
 	// tiles of the busiest warp when nw warps share the rt x ct 8x8 tiles of a Gram block (gramcfg::bestRowWarps, pffrg_kernels.cuh)
 	int gramBusiestTiles(int rt, int ct, int nw)
@@ -258,7 +259,7 @@ namespace
 	// accumulator tiles per warp) share the shared memory. Two CTAs per SM where 32 staged nodes still fit. Environment overrides:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_MINBLOCKS, PFFRG_GRAM_PB.
 	// `threads` = worker threads; producer: one more warp builds the access buffers a batch ahead (two table blocks), one CTA per SM
-	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs, int producer = 0, int maxCtas = 2)
+	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs, int producer = 0, int maxCtas = 2, int maxTiles = 16)
 	{
 		JitShape best = { 0, 0, 0, 0, 0 };
 		const int gemmThreads = threads / 32 * 32, warps = gemmThreads / 32, ct = (Lp + 7) / 8;
@@ -291,7 +292,7 @@ namespace
 						if (forcedPb && pb != std::min(forcedPb, pbMax)) continue;
 						if ((long)pb * (Lp + 1) > (1l << 14)) continue;           // a term word addresses the Gram block with 14 bits
 						const int blocks = (Lp + pb - 1) / pb, lastRt = (Lp - (blocks - 1) * pb + 7) / 8;
-						if (gramBusiestTiles(pb / 8, ct, warps) > 16 || gramBusiestTiles(lastRt, ct, warps) > 16) continue;
+						if (gramBusiestTiles(pb / 8, ct, warps) > maxTiles || gramBusiestTiles(lastRt, ct, warps) > maxTiles) continue; // (8 accumulator registers per tile)
 						const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, pb, producer ? 2 : 1);
 						if (smem > budget) continue;
 						const double phases = (64 + nbt - 1) / nbt;
@@ -457,7 +458,7 @@ namespace
 		return "#define PFFRG_GRAM 1\n#define PFFRG_GRAM_THREADS " + std::to_string(s.gramThreads) + "\n#define PFFRG_GRAM_PB " + std::to_string(s.gramRows) +
 		       "\n" + (s.producer ? "#define PFFRG_PRODUCER " + std::to_string(s.producer) + "\n" : std::string()) +
 		       (s.splitGather ? "#define PFFRG_SPLIT 1\n#define PFFRG_SPLIT_GATHER_THREADS " + std::to_string(s.splitGather) + "\n#define PFFRG_SPLIT_REGS_GATHER " + std::to_string(s.regsGather) +
-		                        "\n#define PFFRG_SPLIT_REGS_RPA " + std::to_string(s.regsRpa) + "\n#define PFFRG_SPLIT_REGS_PRODUCER " + std::to_string(s.regsProducer) + "\n" : std::string());
+		                        "\n#define PFFRG_SPLIT_REGS_LAUNCH " + std::to_string(s.regsLaunch) + "\n#define PFFRG_SPLIT_REGS_RPA " + std::to_string(s.regsRpa) + "\n#define PFFRG_SPLIT_REGS_PRODUCER " + std::to_string(s.regsProducer) + "\n" : std::string());
 	}
 	// producer warp for the Gram kernel (v4FlowBodyProducer): opt-in with PFFRG_PRODUCER=1 while it is being measured
 	int wantProducer() // number of producer warps (0: none)
@@ -467,39 +468,45 @@ namespace
 	}
 
 	// Warp-specialised Gram kernel (v4FlowBodySplit, pffrg_kernels.cuh): gather warps, RPA warps and producer warps as separate warp groups
-	// of one CTA. Opt-in with PFFRG_SPLIT=1 while it is being measured. PFFRG_SPLIT_RPA_THREADS (128), PFFRG_SPLIT_REGS_RPA / _PRODUCER override
-	// the partition of the register file.
-	bool wantSplit()
+	// of one CTA. Default for the lattices that get the Gram form by default (`large`: more than PFFRG_GRAM_MIN_TERMS merged overlap terms;
+	// measured on B200: pyrochlore-r8 89.4 -> 72.2 ms, pyrochlore-r10 213 -> 194 ms; cubic-r7 with PFFRG_RPA=gram 19.2 -> 20.0 ms);
+	// PFFRG_SPLIT=0 / 1 overrides. PFFRG_SPLIT_RPA_THREADS, PFFRG_SPLIT_REGS_RPA / _PRODUCER, PFFRG_PRODUCER (producer warps, default 4)
+	// override the shape.
+	bool wantSplit(bool large)
 	{
 		const char *e = getenv("PFFRG_SPLIT");
-		return e && atoi(e) != 0;
+		return e ? atoi(e) != 0 : large;
 	}
 
-	// Launch of the SU2 kernel with the Gram form of the RPA phase: shape, threads per CTA and the number of warps that walk the term array
-	struct GramLaunch { JitShape shape; int threads; int reduceWarps; };
-	GramLaunch chooseGramLaunch(int nw, int L, int Lp, int groups, int stride, int threads, size_t smemMax, int64_t uniquePairs)
+	// Launch of the SU2 kernel with the Gram form of the RPA phase: shape, threads per CTA, gather groups and the number of warps that walk the term array
+	struct GramLaunch { JitShape shape; int threads; int reduceWarps; int groups; };
+	GramLaunch chooseGramLaunch(int nw, int L, int Lp, int groups, int stride, int threads, size_t smemMax, int64_t uniquePairs, bool large)
 	{
-		GramLaunch g = { { 0, 0, 0, 0, 0 }, threads, threads / 32 };
+		GramLaunch g = { { 0, 0, 0, 0, 0 }, threads, threads / 32, groups };
 		const int workers = threads / 32 * 32;
-		if (wantSplit())
+		if (wantSplit(large))
 		{
-			const int gather = (groups * stride + 127) / 128 * 128;
-			int rpa = 128, producer = std::max(1, wantProducer() ? wantProducer() : 2);
+			// gather warps: at most 256 threads -- two nodes in flight up to 128 sites per group, one above (the register file is what bounds
+			// the loads in flight); RPA warps: one warp group, two where the Gram matrix is large (L > 128)
+			const int splitGroups = std::max(1, std::min(groups, 256 / stride));
+			const int gather = (splitGroups * stride + 127) / 128 * 128;
+			int rpa = stride > 128 ? 256 : 128, producer = wantProducer() ? wantProducer() : 4;
 			if (const char *e = getenv("PFFRG_SPLIT_RPA_THREADS")) rpa = std::max(128, atoi(e) / 128 * 128);
 			const int total = gather + rpa + 128;
 			if (total <= 1024)
 			{
-				JitShape s = chooseGramShape(nw, L, Lp, groups, rpa, smemMax, uniquePairs, producer, 1); // one CTA per SM: the warp groups re-partition its whole register file
 				// register file: what the launch allocates (registers per thread of the whole CTA, a multiple of 8) is re-partitioned
 				const int pool = 65536 / total / 8 * 8 * total;
-				int regsProducer = 40, regsRpa = 200;
+				int regsProducer = 40, regsRpa = rpa > 128 ? 120 : 200;
 				if (const char *e = getenv("PFFRG_SPLIT_REGS_PRODUCER")) regsProducer = std::max(24, atoi(e) / 8 * 8);
 				if (const char *e = getenv("PFFRG_SPLIT_REGS_RPA")) regsRpa = std::max(24, atoi(e) / 8 * 8);
 				const int regsGather = std::min(256, (pool - 128 * regsProducer - rpa * regsRpa) / gather / 8 * 8);
+				// one CTA per SM (the warp groups re-partition its whole register file); accumulator tiles of the block update as the RPA warps' registers allow
+				JitShape s = chooseGramShape(nw, L, Lp, splitGroups, rpa, smemMax, uniquePairs, producer, 1, std::min(16, (regsRpa - 56) / 8));
 				if (s.nb && regsGather >= 96)
 				{
-					s.splitGather = gather; s.regsGather = regsGather; s.regsRpa = regsRpa; s.regsProducer = regsProducer;
-					g.shape = s; g.threads = total; g.reduceWarps = rpa / 32;
+					s.splitGather = gather; s.regsLaunch = pool / total; s.regsGather = regsGather; s.regsRpa = regsRpa; s.regsProducer = regsProducer;
+					g.shape = s; g.threads = total; g.reduceWarps = rpa / 32; g.groups = splitGroups;
 					return g;
 				}
 			}
@@ -588,7 +595,7 @@ namespace
 		h->jitLibrary = c.library; h->jitKernel = c.kernel;
 		h->threads = c.threads; h->groups = c.groups;
 		h->nb = c.shape.nb; h->nbt = c.shape.nbt; h->rpaWarps = c.shape.rpaWarps; h->minBlocks = c.shape.minBlocks; h->smemBytes = c.shape.smem; h->subs = c.shape.subs; h->cluster = c.shape.cluster;
-		h->gramRows = c.shape.gramRows;
+		h->gramRows = c.shape.gramRows; h->splitGather = c.shape.splitGather; h->producerWarps = c.shape.producer;
 	}
 
 	// Compile and load the lattice-specialised kernel. Controlled by the environment: PFFRG_JIT=0 disables it,
@@ -636,10 +643,10 @@ namespace
 			const char *form = getenv("PFFRG_RPA");
 			if (wantGram(h->core, h->uniquePairs))
 			{
-				const GramLaunch launch = chooseGramLaunch(h->nw, h->L, h->Lp, h->groups, h->stride, h->threads, smemMax, h->uniquePairs);
+				const GramLaunch launch = chooseGramLaunch(h->nw, h->L, h->Lp, h->groups, h->stride, h->threads, smemMax, h->uniquePairs, !form);
 				const JitShape &shape = launch.shape;
 				if (!shape.nb) return form ? fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_RPA=gram: no launch shape fits (threads %d, L %d)", h->threads, h->L) : PFFRG_OK;
-				JitCandidate c = { launch.threads, h->groups, shape, nullptr, nullptr, 0.f };
+				JitCandidate c = { launch.threads, launch.groups, shape, nullptr, nullptr, 0.f };
 				const int rc = compileCandidate(h, d, c);
 				if (rc != PFFRG_OK) return rc;
 				std::vector<unsigned> terms; std::vector<int> seg;
@@ -1996,6 +2003,7 @@ int pffrg_get_stats(pffrg_handle h, pffrg_stats *out)
 	out->threads = h->threads; out->smem_bytes = (int32_t)h->smemBytes; out->node_batch = h->nb; out->rpa_batch = h->jitKernel ? h->nbt * h->subs : h->nb; out->sub_ctas = h->jitKernel ? h->subs : 1;
 	out->autotuned_shapes = h->autotuned;
 	out->gram_rows = h->gramRows; out->rpa_terms_merged = (int32_t)h->uniquePairs;
+	out->gather_threads = h->jitKernel ? h->splitGather : 0; out->producer_warps = h->jitKernel ? h->producerWarps : 0;
 	out->rpa_warps = h->jitKernel ? h->rpaWarps : h->threads / 32; out->min_blocks = h->jitKernel ? h->minBlocks : (h->core == TRI ? 1 : 2);
 	return PFFRG_OK;
 }
@@ -2032,7 +2040,7 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	if (wantGram(d->core, uniquePairs))
 	{
 		const int Lp = paddedSites(L);
-		const GramLaunch launch = chooseGramLaunch(d->n_frequencies, L, Lp, groups, geo.stride, threads, 227 * 1024, uniquePairs);
+		const GramLaunch launch = chooseGramLaunch(d->n_frequencies, L, Lp, groups, geo.stride, threads, 227 * 1024, uniquePairs, !getenv("PFFRG_RPA"));
 		const JitShape &g = launch.shape;
 		if (!g.nb) return fail(PFFRG_ERR_UNSUPPORTED, "no launch shape for the Gram form of the RPA phase");
 		std::vector<char> cubin;

@@ -2143,8 +2143,12 @@ namespace pffrg
 	// Same arithmetic per node as v4FlowBody<SU2, NB, NBT, true>; the nodes of an item enter its sums in a different order.
 	// ================================================================================================================
 	template <int V> struct RoleTag { static constexpr int value = V; };
-	template <int REGS> __device__ __forceinline__ void regsInc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(REGS)); }
-	template <int REGS> __device__ __forceinline__ void regsDec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(REGS)); }
+	// registers per thread of the calling warp group: released to / taken from the CTA's pool (PFFRG_SPLIT_REGS_LAUNCH = what the launch gave every thread)
+	template <int REGS> __device__ __forceinline__ void regsSet()
+	{
+		if constexpr (REGS > PFFRG_SPLIT_REGS_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(REGS));
+		else if constexpr (REGS < PFFRG_SPLIT_REGS_LAUNCH) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(REGS));
+	}
 
 	template <int NB, int NBT>
 	__device__ __forceinline__ void v4FlowBodySplit(const Problem &P, const NodeTable &N, const FlowConfig &cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
@@ -2192,7 +2196,7 @@ namespace pffrg
 		if (role == 1)
 		{
 			// ---- RPA warps
-			regsInc<PFFRG_SPLIT_REGS_RPA>();
+			regsSet<PFFRG_SPLIT_REGS_RPA>();
 			#pragma unroll 1
 			for (int r = 0; r < R; ++r)
 			{
@@ -2276,12 +2280,50 @@ namespace pffrg
 					// ---- phase 1: gathers + bilinear forms
 					if (worker)
 					{
+						// PFFRG_PIPELINE: the 16 row loads of the node this thread works on next are in flight while the current one is combined
+						// (64 more registers: for shapes with few gather warps that own a large share of the register file)
+						[[maybe_unused]] double2 pending[4][4];
+						if constexpr (PFFRG_PIPELINE != 0)
+						{
+							if (g < nb)
+							{
+								#pragma unroll
+								for (int b = 0; b < 4; ++b) gatherLoadSU2(P, v4, abTable[g * nbuf + b], siteFwd, siteInv, pending[b]);
+							}
+						}
 						for (int node = g; node < nb; node += cfg.groups)
 						{
 							double A[4][C];
 							const AccessBuffer *ab = abTable + node * nbuf;
-							#pragma unroll
-							for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, ab[b], siteFwd, siteInv, PERM_IDENTITY, PERM_IDENTITY, A[b]);
+							if constexpr (PFFRG_PIPELINE != 0)
+							{
+								double2 current[4][4];
+								#pragma unroll
+								for (int b = 0; b < 4; ++b)
+								{
+									#pragma unroll
+									for (int k = 0; k < 4; ++k) current[b][k] = pending[b][k];
+								}
+								const int next = node + cfg.groups;
+								if (next < nb)
+								{
+									#pragma unroll
+									for (int b = 0; b < 4; ++b) gatherLoadSU2(P, v4, abTable[next * nbuf + b], siteFwd, siteInv, pending[b]);
+								}
+								#pragma unroll
+								for (int b = 0; b < 4; ++b) gatherCombineSU2(ab[b], current[b], A[b]);
+							}
+							else if (PFFRG_MIRROR && tPass && mirroredPair(ab[0], ab[2]) && mirroredPair(ab[1], ab[3]))
+							{
+								// t channel: buffers 2, 3 read the rows of buffers 0, 1 (8 row loads instead of 16; warp-uniform decision)
+								gatherTwo<CORE>(P, v4, ab[0], ab[2], siteFwd, siteInv, PERM_IDENTITY, PERM_IDENTITY, A[0], A[2]);
+								gatherTwo<CORE>(P, v4, ab[1], ab[3], siteFwd, siteInv, PERM_IDENTITY, PERM_IDENTITY, A[1], A[3]);
+							}
+							else
+							{
+								#pragma unroll
+								for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, ab[b], siteFwd, siteInv, PERM_IDENTITY, PERM_IDENTITY, A[b]);
+							}
 							const double W = bW[node];
 							double K[C];
 							if (!tPass) ladderTerms<CORE>((b0 + node) < nFirst ? CH_S : CH_U, A, K);
@@ -2316,12 +2358,12 @@ namespace pffrg
 		if (role == 2)
 		{
 			// ---- producer warps
-			regsDec<PFFRG_SPLIT_REGS_PRODUCER>();
+			regsSet<PFFRG_SPLIT_REGS_PRODUCER>();
 			if (ptid < NPROD) runSchedule(RoleTag<2>());
 			return;
 		}
 		// ---- gather warps
-		regsInc<PFFRG_SPLIT_REGS_GATHER>();
+		regsSet<PFFRG_SPLIT_REGS_GATHER>();
 		runSchedule(RoleTag<0>());
 
 		// ---- epilogue (gather warps; the partial sums reuse the staging area, dead after the last sync(EMPTY))

@@ -30,7 +30,10 @@ WORKLOADS = {
     "square_r4_su2_nw32": (100, [], [{}, {"PFFRG_AUTOTUNE": "1"}, {"PFFRG_RPA": "gram"}]),
     "cubic_r7_su2_nw64": (211, [], [{}, {"PFFRG_AUTOTUNE": "1"}, {"PFFRG_RPA": "gram"}]),
     "honeycomb_kitaev_r7_xyz_nw64": (211, [], [{}, {"PFFRG_AUTOTUNE": "1"}]),
-    "pyrochlore_r8_su2_nw64": (211, [], [{}, {"PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}, {"PFFRG_PRODUCER": "1"}, {"PFFRG_SPLIT": "1"}]),
+    # default: the warp-specialised Gram kernel (gather / RPA / producer warp groups); then with several RPA rounds and small batches,
+    # the unsplit Gram kernel without and with a producer warp
+    "pyrochlore_r8_su2_nw64": (211, [], [{}, {"PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}, {"PFFRG_SPLIT": "0"}, {"PFFRG_SPLIT": "0", "PFFRG_PRODUCER": "1"}]),
+    "pyrochlore_r10_su2_nw64": (211, [], [{}, {"PFFRG_SPLIT": "0"}]),
     "kagome_dm_r7_tri_nw64": (120, [211], [{}, {"PFFRG_RPA": "gram"}]),
 }
 
