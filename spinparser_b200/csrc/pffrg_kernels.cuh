@@ -1317,7 +1317,7 @@ namespace pffrg
 	// and orders the words so that the 8 lanes of a quarter warp hit different 16-byte bank groups of Gs (buildGramTables, pffrg.cu).
 	constexpr unsigned GRAM_OFFSET_MASK = (1u << 14) - 1u;
 #ifndef PFFRG_GRAM_PREFETCH
-#define PFFRG_GRAM_PREFETCH 8
+#define PFFRG_GRAM_PREFETCH 4
 #endif
 	struct GramStream { const uint4 *words; int T4; uint4 n[PFFRG_GRAM_PREFETCH]; }; // the term words of one (block, warp) and the groups in flight
 	__device__ __forceinline__ void gramReducePrefetch(const Problem &P, int blk, int warp, int lane, int warps, GramStream &S)
