@@ -126,6 +126,8 @@ struct pffrg_context
 	DeviceArray<unsigned> dGramTerms; DeviceArray<int> dGramSeg; // Gram form of the RPA phase (rpaGram), when selected
 	int gramRows = 0;                                                 // rows per Gram block (0: not in use); TRI Gram form: resident channel-pair blocks
 	int splitGather = 0, producerWarps = 0;                           // warp-specialised kernel: gather threads (0: not split); producer warps
+	bool persistent = true;
+	int smCount = 0;                                                  // SMs of the device (grid of the persistent warp-specialised kernel)
 	DeviceArray<unsigned short> dTriBlocks; int triRounds = 0;         // TRI Gram form: channel pairs per (round, slot)
 	int64_t triBlockCount = 0, gramWords = 0;                          // Gram forms: needed channel-pair blocks (TRI), words walked per RPA phase
 	int itemOrder = 0;                                                // FlowConfig::order of the run-time compiled kernel (PFFRG_ORDER=t: t-major)
@@ -404,6 +406,8 @@ namespace
 			const double *v4 = h->v4cur(); double *flow = h->dFlow4.p; int itemBegin = (int)begin; int *nan = h->dNan.p;
 			void *args[] = { &P, &N, &cfg, &v4, &flow, &itemBegin, &nan };
 			int64_t ctas = (count + h->subs - 1) / h->subs; // padded to whole clusters (the kernel carries __cluster_dims__)
+			// warp-specialised kernel: persistent CTAs, one per SM, each working on every ctas-th item (v4FlowBodySplit); PFFRG_PERSISTENT=0: one CTA per item
+			if (h->splitGather > 0 && h->persistent && h->smCount > 0) ctas = std::min<int64_t>(ctas, h->smCount);
 			if (cfg.order == 1) ctas = ((begin + count - 1) / h->nw - begin / h->nw + 1) * h->nw; // t-major: whole (s,u) blocks
 			return cudaLaunchKernel((const void *)h->jitKernel, dim3((unsigned)((ctas + h->cluster - 1) / h->cluster * h->cluster)), dim3(h->threads), args, h->smemBytes, h->stream);
 		}
@@ -447,7 +451,7 @@ namespace
 	bool wantGram(int core, int64_t uniquePairs)
 	{
 		if (core != SU2) return false;
-		long minTerms = 8000;
+		long minTerms = 2000; // (cubic-r7, 3453 terms: straight-line code 17.9 ms, warp-specialised Gram kernel 16.3 ms; square-r4, 136 terms: 0.69 / 1.01 ms)
 		if (const char *e = getenv("PFFRG_GRAM_MIN_TERMS")) minTerms = atol(e);
 		const char *form = getenv("PFFRG_RPA");
 		return form ? std::string(form) == "gram" : uniquePairs > minTerms;
@@ -636,7 +640,7 @@ namespace
 		std::vector<JitCandidate> candidates;
 		// Form of the RPA phase (SU2): PFFRG_RPA=gram -- Gram matrix over the staged nodes + one walk of the overlap list per phase
 		// (rpaGram; no generated code, any lattice size); PFFRG_RPA=code -- lattice-specialised straight-line code. Default: the Gram form
-		// for lattices with more than PFFRG_GRAM_MIN_TERMS (8000) merged overlap terms, where the straight-line code no longer fits the
+		// for lattices with more than PFFRG_GRAM_MIN_TERMS (2000) merged overlap terms (as the warp-specialised kernel v4FlowBodySplit), where the straight-line code no longer fits the
 		// instruction caches.
 		if (h->core == SU2)
 		{
@@ -1574,6 +1578,7 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	CUDA_TRY(cudaSetDevice(d->device));
 	cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
 	if (prop.major < 10) return fail(PFFRG_ERR_CUDA, "device %d is sm_%d%d; libpffrg is built for sm_100a only", d->device, prop.major, prop.minor);
+	const int smCount = prop.multiProcessorCount;
 
 	const pffrg_desc *original = d;
 	const RelabelledDesc relabelled(original);
@@ -1583,7 +1588,8 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	const CoreModel m = modelOf(d->core);
 	h->core = d->core; h->nw = d->n_frequencies; h->L = L; h->Lp = paddedSites(L); h->C = m.C; h->RL = m.C * h->Lp; h->nArrays = m.arrays;
 	h->nf = (int64_t)h->nw * h->nw * (h->nw + 1) / 2;
-	h->device = d->device; h->spin = d->spin_length;
+	h->device = d->device; h->spin = d->spin_length; h->smCount = smCount;
+	if (const char *e = getenv("PFFRG_PERSISTENT")) h->persistent = atoi(e) != 0;
 	h->mesh.assign(d->frequencies, d->frequencies + h->nw);
 	h->overlapTotal = d->overlap_offsets[L];
 	if ((double)h->nf * h->RL > 2.0e9) { delete h; return fail(PFFRG_ERR_UNSUPPORTED, "vertex too large for 32-bit row offsets"); }

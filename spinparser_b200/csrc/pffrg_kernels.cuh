@@ -2177,50 +2177,69 @@ namespace pffrg
 		for (int i = tid; i < 2 * NBT * (gramcfg::LpS - L); i += blockDim.x)
 			reinterpret_cast<double2 *>(st)[(i / (gramcfg::LpS - L)) * gramcfg::LpS + L + i % (gramcfg::LpS - L)] = make_double2(0.0, 0.0);
 
+		// PERSISTENT CTAs: CTA b works on the items itemBegin + b, + gridDim.x, ... (the host launches one CTA per SM, or one per item). The
+		// producer warps run ahead into the next item, the gather warps go on with its first batch right after the epilogue, the barrier
+		// phases and the two table blocks simply continue: no CTA launch, prologue and pipeline ramp per item. A fixed stride samples the
+		// (smooth) cost of the items evenly, so the CTAs finish together.
 		const int itemEnd = itemBegin + cfg.items;
-		const int itemFirst = itemBegin + blockIdx.x;
-		const bool valid = itemFirst < itemEnd;
-		const int item = valid ? itemFirst : itemEnd - 1;
-		const int su = item / nw, ti = item - su * nw;
-		int so = (int)((sqrt(8.0 * su + 1.0) - 1.0) * 0.5);
-		while ((so + 1) * (so + 2) / 2 <= su) ++so;
-		while (so * (so + 1) / 2 > su) --so;
-		const int uo = su - so * (so + 1) / 2;
 		__syncthreads(); // the only barrier over all threads
-
-		// the schedule (identical on all warps): R rounds of t-channel batches, each followed by a chunk of the s/u batches
-		const int nT = valid ? N.count[ti] : 0, nS = valid ? N.count[so] : 0, nSU = valid ? nS + N.count[uo] : 0;
-		const int R = valid ? max(1, (nT + NBT - 1) / NBT) : 0;
-		const int suBatches = (nSU + 2 * NB - 1) / (2 * NB);
+		// item -> (s, t, u) indices and the schedule (identical on all warps): R rounds of t-channel batches, each followed by a chunk of the s/u batches
+		struct ItemPlan { int item, so, ti, uo, nT, nS, nSU, R, suBatches; };
+		auto planItem = [&](int item)
+		{
+			ItemPlan q;
+			q.item = item;
+			const int su = item / nw;
+			q.ti = item - su * nw;
+			int so = (int)((sqrt(8.0 * su + 1.0) - 1.0) * 0.5);
+			while ((so + 1) * (so + 2) / 2 <= su) ++so;
+			while (so * (so + 1) / 2 > su) --so;
+			q.so = so; q.uo = su - so * (so + 1) / 2;
+			q.nT = N.count[q.ti]; q.nS = N.count[q.so]; q.nSU = q.nS + N.count[q.uo];
+			q.R = max(1, (q.nT + NBT - 1) / NBT);
+			q.suBatches = (q.nSU + 2 * NB - 1) / (2 * NB);
+			return q;
+		};
 
 		if (role == 1)
 		{
 			// ---- RPA warps
 			regsSet<PFFRG_SPLIT_REGS_RPA>();
 			#pragma unroll 1
-			for (int r = 0; r < R; ++r)
+			for (int item = itemBegin + (int)blockIdx.x; item < itemEnd; item += (int)gridDim.x)
 			{
-				namedSync(11, STG); // the operands of round r are staged
-				rpaGram(P, reinterpret_cast<const double2 *>(st), NBT, min(NBT, nT - r * NBT), reinterpret_cast<double2 *>(smemRaw + lay.gram), rpaOut);
-				namedArrive(12, STG); // the staging area may be overwritten; rpaOut holds the round (read after the last round only)
+				const int nT = N.count[item % nw], R = max(1, (nT + NBT - 1) / NBT);
+				#pragma unroll 1
+				for (int r = 0; r < R; ++r)
+				{
+					namedSync(11, STG); // the operands of round r are staged
+					rpaGram(P, reinterpret_cast<const double2 *>(st), NBT, min(NBT, nT - r * NBT), reinterpret_cast<double2 *>(smemRaw + lay.gram), rpaOut);
+					namedArrive(12, STG); // the staging area may be overwritten; rpaOut holds the round (read after the item's last round only)
+				}
 			}
 			return;
 		}
-		ItemFrequencies f;
-		f.s = mesh[so]; f.t = mesh[ti]; f.u = mesh[uo];
-		f.w1p = 0.5 * (f.s + f.t + f.u); f.w1 = 0.5 * (f.s - f.t + f.u); f.w2p = 0.5 * (f.s - f.t - f.u); f.w2 = 0.5 * (f.s + f.t - f.u);
 		const int g = tid / cfg.stride, j = tid - g * cfg.stride;
 		const bool worker = role == 0 && g < cfg.groups && j < L;
-		double acc[C] = { 0.0, 0.0 };
 
 		// The schedule, instantiated once per role (ROLE = 2: producer warps, 0: gather warps) so that the two run separate code with
 		// their own register budgets (code reachable after setmaxnreg.dec has to fit the producer's 40 registers).
-		auto runSchedule = [&](auto roleTag)
+		auto runItems = [&](auto roleTag)
 		{
 			constexpr int ROLE = decltype(roleTag)::value;
 			int siteFwd = 0, siteInv = 0;
 			if (ROLE == 0 && worker) { siteFwd = P.sites_rid[j]; siteInv = P.inv_rid[j]; }
-			int batchNo = 0; // batches handed over so far (the same sequence on both sides)
+			int batchNo = 0; // batches handed over so far (the same sequence on both sides, continued over the items)
+			bool bad = false;
+			#pragma unroll 1
+			for (int item = itemBegin + (int)blockIdx.x; item < itemEnd; item += (int)gridDim.x)
+			{
+			const ItemPlan q = planItem(item);
+			const int so = q.so, ti = q.ti, uo = q.uo, nT = q.nT, nS = q.nS, nSU = q.nSU, R = q.R, suBatches = q.suBatches;
+			ItemFrequencies f;
+			f.s = mesh[so]; f.t = mesh[ti]; f.u = mesh[uo];
+			f.w1p = 0.5 * (f.s + f.t + f.u); f.w1 = 0.5 * (f.s - f.t + f.u); f.w2p = 0.5 * (f.s - f.t - f.u); f.w2 = 0.5 * (f.s + f.t - f.u);
+			double acc[C] = { 0.0, 0.0 };
 			// one batch of nodes [b0, b0 + nb) of the t channel (operands staged at `staged`) or of the s/u node list
 			auto doBatch = [&](const bool tPass, const int b0, const int nb, const int staged)
 			{
@@ -2240,16 +2259,16 @@ namespace pffrg
 					// ---- phase 0, step A: the four interpolated frequencies of every node (one mesh search each)
 					for (int idx = ptid; idx < nb * 4; idx += NPROD)
 					{
-						const int node = idx >> 2, q = idx & 3;
+						const int node = idx >> 2, qq = idx & 3;
 						const int gn = b0 + node;
 						const int ch = tPass ? CH_T : (gn < nFirst ? CH_S : CH_U);
 						const double wp = gn < nFirst ? nodeW0[gn] : nodeW1[gn - nFirst];
-						if (q == 0)
+						if (qq == 0)
 						{
 							const double wt = gn < nFirst ? nodeWt0[gn] : nodeWt1[gn - nFirst];
 							bW[node] = ch == CH_U ? -wt : wt; // SU2: the u channel enters with a minus sign (SU2FrgCore.cpp:366,370,376)
 						}
-						makeLerpRecord(mesh, nw, P.meshIndex, nodeQuantity(ch, q, f.w1p, f.w1, f.w2p, f.w2, wp), lerp[idx]);
+						makeLerpRecord(mesh, nw, P.meshIndex, nodeQuantity(ch, qq, f.w1p, f.w1, f.w2p, f.w2, wp), lerp[idx]);
 					}
 					producerSync();
 					// ---- step B: assemble the buffers; site-0 values of the t channel's buffers 4..7 (getValueLocal) right away
@@ -2354,33 +2373,39 @@ namespace pffrg
 				for (int sb = r * suBatches / R; sb < sbEnd; ++sb) doBatch(false, sb * 2 * NB, min(2 * NB, nSU - sb * 2 * NB), 0);
 				if (ROLE == 0) namedSync(12, STG); // the RPA warps are done with the staging area
 			}
+			if constexpr (ROLE == 0)
+			{
+				// ---- epilogue of the item (gather warps; the partial sums reuse the staging area, dead after the last sync(EMPTY))
+				if (worker) { part[(g * C) * L + j] = acc[0]; part[(g * C + 1) * L + j] = acc[1]; }
+				namedSync(13, NG);
+				for (int e = tid; e < C * L; e += NG)
+				{
+					double v = 0.0;
+					for (int k = 0; k < lay.rpaCopies; ++k) { v += rpaOut[k * C * L + e]; rpaOut[k * C * L + e] = 0.0; } // (cleared for the next item of this CTA)
+					for (int gg = 0; gg < cfg.groups; ++gg) v += part[gg * C * L + e];
+					v /= TWO_PI;
+					const int c = e / L, jj = e - c * L;
+					flow[(size_t)item * sizeRL(P) + channelOffset(vectorWidth(CORE), c, sizeLp(P)) + jj * vectorWidth(CORE)] = v;
+					bad |= (v != v);
+				}
+				namedSync(13, NG); // the partial sums are read: the next item may stage its operands over them ...
+				// ... and the padding sites they covered are zero again (read by the Gram update, never written by the gathers)
+				for (int i = tid; i < 2 * NBT * (gramcfg::LpS - L); i += NG)
+					reinterpret_cast<double2 *>(st)[(i / (gramcfg::LpS - L)) * gramcfg::LpS + L + i % (gramcfg::LpS - L)] = make_double2(0.0, 0.0);
+			}
+			}
+			if (ROLE == 0 && bad) atomicOr(nanFlag, 1);
 		};
 		if (role == 2)
 		{
 			// ---- producer warps
 			regsSet<PFFRG_SPLIT_REGS_PRODUCER>();
-			if (ptid < NPROD) runSchedule(RoleTag<2>());
+			if (ptid < NPROD) runItems(RoleTag<2>());
 			return;
 		}
 		// ---- gather warps
 		regsSet<PFFRG_SPLIT_REGS_GATHER>();
-		runSchedule(RoleTag<0>());
-
-		// ---- epilogue (gather warps; the partial sums reuse the staging area, dead after the last sync(EMPTY))
-		if (worker) { part[(g * C) * L + j] = acc[0]; part[(g * C + 1) * L + j] = acc[1]; }
-		namedSync(13, NG);
-		bool bad = false;
-		for (int e = tid; valid && e < C * L; e += NG)
-		{
-			double v = 0.0;
-			for (int k = 0; k < lay.rpaCopies; ++k) v += rpaOut[k * C * L + e];
-			for (int gg = 0; gg < cfg.groups; ++gg) v += part[gg * C * L + e];
-			v /= TWO_PI;
-			const int c = e / L, jj = e - c * L;
-			flow[(size_t)item * sizeRL(P) + channelOffset(vectorWidth(CORE), c, sizeLp(P)) + jj * vectorWidth(CORE)] = v;
-			bad |= (v != v);
-		}
-		if (bad) atomicOr(nanFlag, 1);
+		runItems(RoleTag<0>());
 	}
 #endif
 

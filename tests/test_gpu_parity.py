@@ -34,6 +34,7 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             # small CTAs on their own: fewer warps than the preferred number of node groups (the shape search must skip those)
             {"PFFRG_THREADS": "64"}, {"PFFRG_THREADS": "96"},
             # SU2: Gram form of the RPA phase (rpaGram) -- default shape, several RPA phases per item, other thread grids / block sizes
+            {"PFFRG_RPA": "code"}, {"PFFRG_RPA": "code", "PFFRG_CLUSTER": "2"}, # (lattices above PFFRG_GRAM_MIN_TERMS run the Gram form by default)
             {"PFFRG_RPA": "gram"}, {"PFFRG_RPA": "gram", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}, {"PFFRG_RPA": "gram", "PFFRG_THREADS": "128"},
             {"PFFRG_RPA": "gram", "PFFRG_THREADS": "512", "PFFRG_GRAM_TM": "1"}, {"PFFRG_RPA": "gram", "PFFRG_THREADS": "96", "PFFRG_JIT_NBT": "8", "PFFRG_JIT_NB": "8"},
             {"PFFRG_RPA": "gram", "PFFRG_GRAM_TM": "1", "PFFRG_JIT_MINBLOCKS": "1"},
@@ -46,7 +47,7 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             {"PFFRG_RPA": "gram", "PFFRG_PRODUCER": "1", "PFFRG_THREADS": "128", "PFFRG_JIT_MINBLOCKS": "2"}, {"PFFRG_RPA": "gram", "PFFRG_PRODUCER": "2"},
             # warp-specialised SU2 Gram kernel (gather / RPA / producer warp groups): default, several RPA rounds per item, one gather group + one producer warp
             {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1"}, {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1", "PFFRG_JIT_NBT": "8", "PFFRG_JIT_NB": "8"},
-            {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1", "PFFRG_THREADS": "128", "PFFRG_PRODUCER": "1"},
+            {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1", "PFFRG_THREADS": "128", "PFFRG_PRODUCER": "1"}, {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1", "PFFRG_PERSISTENT": "0"},
             {"PFFRG_RPA": "table"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "1"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "2", "PFFRG_THREADS": "128"}]
 
 
@@ -69,7 +70,7 @@ def test_one_step_flow_matches_reference(case, variant, monkeypatch):
     name, core = _core(d)
     if variant.get("PFFRG_RPA") == "gram":
         assert core.stats()["jit_rpa"] == 1 and core.stats()["gram_rows"] > 0
-    if variant.get("PFFRG_RPA") == "table" or variant.get("PFFRG_JIT") == "0":
+    if variant.get("PFFRG_RPA") in ("table", "code") or variant.get("PFFRG_JIT") == "0":
         assert core.stats()["gram_rows"] == 0
     n = core.n_arrays
     cut = d["cutoff"]
@@ -95,7 +96,8 @@ def test_one_step_flow_matches_reference(case, variant, monkeypatch):
 
 
 @pytest.mark.parametrize("variant", [{}, {"PFFRG_CLUSTER": "4"}, {"PFFRG_SUBCTAS": "3", "PFFRG_THREADS": "64", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8", "PFFRG_CLUSTER": "2"},
-                                     {"PFFRG_ORDER": "t", "PFFRG_CLUSTER": "1"}, {"PFFRG_ORDER": "t", "PFFRG_RPA": "gram"}],
+                                     {"PFFRG_ORDER": "t", "PFFRG_CLUSTER": "1"}, {"PFFRG_ORDER": "t", "PFFRG_RPA": "gram"},
+                                     {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1"}, {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1", "PFFRG_PERSISTENT": "0"}],
                          ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
 @pytest.mark.parametrize("case", ["su2_kagome_r4_nw8", "xyz_kagome_r4_nw8"])
 def test_item_range_with_padded_grid(case, variant, monkeypatch):

@@ -119,13 +119,14 @@ def _free_port():
 
 # exchange of the updated slices: fused Euler + peer-memory stores over NVLink (default), the NCCL broadcast group (PFFRG_EXCHANGE=nccl);
 # upload of 1/N of the rows per rank + distribution over NVLink; launch shape autotuned on rank 0 and adopted by the other ranks
-MODES = {"p2p": {}, "nccl": {"PFFRG_EXCHANGE": "nccl"}, "sharded_upload": {"TEST_SHARDED_UPLOAD": "1"}, "autotune": {"PFFRG_AUTOTUNE": "1"},
+# su2_kagome_r7_nw6 runs the warp-specialised Gram kernel with persistent CTAs by default ("p2p"); "autotune": its straight-line code kernel, tuned
+MODES = {"p2p": {}, "nccl": {"PFFRG_EXCHANGE": "nccl"}, "sharded_upload": {"TEST_SHARDED_UPLOAD": "1"}, "autotune": {"PFFRG_AUTOTUNE": "1", "PFFRG_RPA": "code"},
          "gram": {"PFFRG_RPA": "gram"}}
 
 
 @pytest.mark.parametrize("case,mode", [("su2_square_r3_nw10", "p2p"), ("xyz_honeycomb_kitaev_r3_nw10", "p2p"), ("tri_honeycomb_kg_r3_nw8", "p2p"),
                                        ("su2_kagome_r4_nw8", "nccl"), ("xyz_kagome_r4_nw8", "sharded_upload"), ("su2_kagome_r7_nw6", "autotune"),
-                                       ("su2_kagome_r7_nw6", "gram")])
+                                       ("su2_kagome_r7_nw6", "gram"), ("su2_kagome_r7_nw6", "p2p")])
 def test_sharded_flow_equals_single_gpu_flow(case, mode, tmp_path):
     from spinparser_b200.frgcore import device_count
     world = min(device_count(), 8)

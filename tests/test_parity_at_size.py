@@ -28,7 +28,8 @@ STRIDE = 131  # coprime to Nw = 64 and 32: the sample visits every t index and e
 # ~62 quadrature nodes per item) is evaluated on that state as well.
 WORKLOADS = {
     "square_r4_su2_nw32": (100, [], [{}, {"PFFRG_AUTOTUNE": "1"}, {"PFFRG_RPA": "gram"}]),
-    "cubic_r7_su2_nw64": (211, [], [{}, {"PFFRG_AUTOTUNE": "1"}, {"PFFRG_RPA": "gram"}]),
+    # default: the warp-specialised Gram kernel with persistent CTAs; then the lattice-specialised straight-line code (first shape and autotuned), the unsplit Gram kernel
+    "cubic_r7_su2_nw64": (211, [], [{}, {"PFFRG_RPA": "code"}, {"PFFRG_RPA": "code", "PFFRG_AUTOTUNE": "1"}, {"PFFRG_RPA": "gram"}, {"PFFRG_PERSISTENT": "0"}]),
     "honeycomb_kitaev_r7_xyz_nw64": (211, [], [{}, {"PFFRG_AUTOTUNE": "1"}]),
     # default: the warp-specialised Gram kernel (gather / RPA / producer warp groups); then with several RPA rounds and small batches,
     # the unsplit Gram kernel without and with a producer warp
@@ -45,7 +46,7 @@ def _tables(workload):
 
 def _core(d, env, monkeypatch):
     from spinparser_b200 import FrgCoreFactory, ProblemTables
-    for k in ("PFFRG_AUTOTUNE", "PFFRG_RPA", "PFFRG_JIT_NBT", "PFFRG_JIT_NB", "PFFRG_PRODUCER", "PFFRG_SPLIT"):
+    for k in ("PFFRG_AUTOTUNE", "PFFRG_RPA", "PFFRG_JIT_NBT", "PFFRG_JIT_NB", "PFFRG_PRODUCER", "PFFRG_SPLIT", "PFFRG_PERSISTENT"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
