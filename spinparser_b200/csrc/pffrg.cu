@@ -246,7 +246,7 @@ namespace
 	// warps (one per SM sub-partition when there are four), each on its own group of 16 (SU2) or 32 staged nodes, so the
 	// number of staged nodes nbt = nodeGroups * lanes decides the shared-memory footprint. Environment overrides for tuning runs:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_TILES, PFFRG_JIT_MINBLOCKS.
-	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0; int producer = 0; /* producer warps */ int splitGather = 0; /* warp-specialised kernel: gather threads (0: not split) */ int regsGather = 0, regsRpa = 0, regsProducer = 0, regsLaunch = 0; };
+	struct JitShape { int nb, nbt, rpaWarps, minBlocks; size_t smem; int subs = 1; int cluster = 1; int gramRows = 0, gramThreads = 0; int producer = 0; /* producer warps */ int splitGather = 0; /* warp-specialised kernel: gather threads (0: not split) */ int regsGather = 0, regsRpa = 0, regsProducer = 0, regsLaunch = 0; int tableCopies = 1; /* access-buffer table blocks (producer kernels: 2..4) */ };
 
 	// tiles of the busiest warp when nw warps share the rt x ct 8x8 tiles of a Gram block (gramcfg::bestRowWarps, pffrg_kernels.cuh)
 	int gramBusiestTiles(int rt, int ct, int nw)
@@ -261,21 +261,28 @@ namespace
 	// accumulator tiles per warp) share the shared memory. Two CTAs per SM where 32 staged nodes still fit. Environment overrides:
 	// PFFRG_JIT_NB, PFFRG_JIT_NBT, PFFRG_JIT_MINBLOCKS, PFFRG_GRAM_PB.
 	// `threads` = worker threads; producer: one more warp builds the access buffers a batch ahead (two table blocks), one CTA per SM
-	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs, int producer = 0, int maxCtas = 2, int maxTiles = 16)
+	// tableCopies: access-buffer table blocks (0: one, or two with producer warps; -1: the warp-specialised kernel -- two or three blocks and
+	// gather batches of up to 32 nodes, rated below)
+	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs, int producer = 0, int maxCtas = 2, int maxTiles = 16, int tableCopies = 0)
 	{
 		JitShape best = { 0, 0, 0, 0, 0 };
+		const bool split = tableCopies < 0;
+		if (tableCopies == 0) tableCopies = producer ? 2 : 1;
 		const int gemmThreads = threads / 32 * 32, warps = gemmThreads / 32, ct = (Lp + 7) / 8;
 		if (warps < 1) return best;
-		int forcedNb = 0, forcedNbt = 0, forcedCtas = 0, forcedPb = 0;
+		int forcedNb = 0, forcedNbt = 0, forcedCtas = 0, forcedPb = 0, forcedTables = 0;
 		if (const char *e = getenv("PFFRG_JIT_NB")) forcedNb = atoi(e);
 		if (const char *e = getenv("PFFRG_JIT_NBT")) forcedNbt = atoi(e);
 		if (const char *e = getenv("PFFRG_JIT_MINBLOCKS")) forcedCtas = std::max(1, atoi(e));
 		if (const char *e = getenv("PFFRG_GRAM_PB")) forcedPb = std::max(8, atoi(e) / 8 * 8);
+		if (const char *e = getenv("PFFRG_SPLIT_TABLES")) forcedTables = std::min(4, std::max(2, atoi(e)));
 		const int pbMax = std::min(64, (Lp + 7) / 8 * 8);
 		const int nbts[] = { 64, 48, 32, 24, 16, 8 };
 		// Every shape that fits is rated with a coarse model of what the choice costs per work item (clocks; ~64 t-channel nodes per item):
 		// every RPA phase walks the term array once (~60 clocks per group of 128 words and warp) and pays two barriers and a store of the
 		// block per row block (~1500 clocks); small gather batches cost gather throughput (measured: pyrochlore-r8 +15 % with batches of 8).
+		// Warp-specialised kernel (measured on B200): batches of 32 nodes instead of 16 -- pyrochlore-r8 70.3 -> 68.4 ms, cubic-r7 16.3 -> 15.6 ms;
+		// a third table block -- cubic-r7 15.6 -> 15.0 ms, nothing on pyrochlore-r8 (where it would cost rows of the Gram block).
 		double bestCost = 0.0;
 		for (int ctas = 2; ctas >= 1; --ctas)
 		{
@@ -286,21 +293,27 @@ namespace
 			for (int nbt : nbts)
 			{
 				if (forcedNbt ? nbt != forcedNbt : (ctas == 2 && nbt < 32)) continue;
-				for (int nb : { 16, 8 })
+				for (int nb : { 32, 16, 8 })
 				{
-					if (nbt % nb || (forcedNb && nb != forcedNb)) continue;
-					for (int pb = pbMax; pb >= 8; pb -= 8)
+					if (nbt % nb || (forcedNb ? nb != forcedNb : (nb == 32 && !split))) continue; // (batches of 32 nodes: warp-specialised kernel, or PFFRG_JIT_NB=32)
+					for (int tables = split ? 3 : tableCopies; tables >= (split ? 2 : tableCopies); --tables)
 					{
-						if (forcedPb && pb != std::min(forcedPb, pbMax)) continue;
-						if ((long)pb * (Lp + 1) > (1l << 14)) continue;           // a term word addresses the Gram block with 14 bits
-						const int blocks = (Lp + pb - 1) / pb, lastRt = (Lp - (blocks - 1) * pb + 7) / 8;
-						if (gramBusiestTiles(pb / 8, ct, warps) > maxTiles || gramBusiestTiles(lastRt, ct, warps) > maxTiles) continue; // (8 accumulator registers per tile)
-						const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, pb, producer ? 2 : 1);
-						if (smem > budget) continue;
-						const double phases = (64 + nbt - 1) / nbt;
-						double cost = phases * (1.03 * (double)uniquePairs / 128.0 / warps * 60.0 + blocks * 1500.0) + (nb == 8 ? (producer ? 6000.0 : 15000.0) : 0.0); // (with producer warps the access-buffer phases are off the critical path; measured +4 % with batches of 8)
-						if (ctas == 2) cost *= 0.8; // two resident CTAs overlap their phases
-						if (!best.nb || cost < bestCost) { best = { nb, nbt, threads / 32, ctas, smem }; best.gramRows = pb; best.gramThreads = gemmThreads; best.producer = producer; bestCost = cost; }
+						if (split && forcedTables && tables != std::min(forcedTables, 3) && !(forcedTables == 4 && tables == 3)) continue;
+						const int copies = (split && forcedTables == 4) ? 4 : tables;
+						for (int pb = pbMax; pb >= 8; pb -= 8)
+						{
+							if (forcedPb && pb != std::min(forcedPb, pbMax)) continue;
+							if ((long)pb * (Lp + 1) > (1l << 14)) continue;           // a term word addresses the Gram block with 14 bits
+							const int blocks = (Lp + pb - 1) / pb, lastRt = (Lp - (blocks - 1) * pb + 7) / 8;
+							if (gramBusiestTiles(pb / 8, ct, warps) > maxTiles || gramBusiestTiles(lastRt, ct, warps) > maxTiles) continue; // (8 accumulator registers per tile)
+							const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, pb, copies);
+							if (smem > budget) continue;
+							const double phases = (64 + nbt - 1) / nbt;
+							double cost = phases * (1.03 * (double)uniquePairs / 128.0 / warps * 60.0 + blocks * 1500.0) + (nb == 8 ? (producer ? 6000.0 : 15000.0) : 0.0); // (with producer warps the access-buffer phases are off the critical path; measured +4 % with batches of 8)
+							if (split) cost += (nb == 16 ? 3000.0 : 0.0) + (copies == 2 ? 1000.0 : 0.0);
+							if (ctas == 2) cost *= 0.8; // two resident CTAs overlap their phases
+							if (!best.nb || cost < bestCost) { best = { nb, nbt, threads / 32, ctas, smem }; best.gramRows = pb; best.gramThreads = gemmThreads; best.producer = producer; best.tableCopies = copies; bestCost = cost; }
+						}
 					}
 				}
 			}
@@ -462,7 +475,7 @@ namespace
 		return "#define PFFRG_GRAM 1\n#define PFFRG_GRAM_THREADS " + std::to_string(s.gramThreads) + "\n#define PFFRG_GRAM_PB " + std::to_string(s.gramRows) +
 		       "\n" + (s.producer ? "#define PFFRG_PRODUCER " + std::to_string(s.producer) + "\n" : std::string()) +
 		       (s.splitGather ? "#define PFFRG_SPLIT 1\n#define PFFRG_SPLIT_GATHER_THREADS " + std::to_string(s.splitGather) + "\n#define PFFRG_SPLIT_REGS_GATHER " + std::to_string(s.regsGather) +
-		                        "\n#define PFFRG_SPLIT_REGS_LAUNCH " + std::to_string(s.regsLaunch) + "\n#define PFFRG_SPLIT_REGS_RPA " + std::to_string(s.regsRpa) + "\n#define PFFRG_SPLIT_REGS_PRODUCER " + std::to_string(s.regsProducer) + "\n" : std::string());
+		                        "\n#define PFFRG_SPLIT_TABLES " + std::to_string(s.tableCopies) + "\n#define PFFRG_SPLIT_REGS_LAUNCH " + std::to_string(s.regsLaunch) + "\n#define PFFRG_SPLIT_REGS_RPA " + std::to_string(s.regsRpa) + "\n#define PFFRG_SPLIT_REGS_PRODUCER " + std::to_string(s.regsProducer) + "\n" : std::string());
 	}
 	// producer warp for the Gram kernel (v4FlowBodyProducer): opt-in with PFFRG_PRODUCER=1 while it is being measured
 	int wantProducer() // number of producer warps (0: none)
@@ -506,7 +519,7 @@ namespace
 				if (const char *e = getenv("PFFRG_SPLIT_REGS_RPA")) regsRpa = std::max(24, atoi(e) / 8 * 8);
 				const int regsGather = std::min(256, (pool - 128 * regsProducer - rpa * regsRpa) / gather / 8 * 8);
 				// one CTA per SM (the warp groups re-partition its whole register file); accumulator tiles of the block update as the RPA warps' registers allow
-				JitShape s = chooseGramShape(nw, L, Lp, splitGroups, rpa, smemMax, uniquePairs, producer, 1, std::min(16, (regsRpa - 56) / 8));
+				JitShape s = chooseGramShape(nw, L, Lp, splitGroups, rpa, smemMax, uniquePairs, producer, 1, std::min(16, (regsRpa - 56) / 8), -1);
 				if (s.nb && regsGather >= 96)
 				{
 					s.splitGather = gather; s.regsLaunch = pool / total; s.regsGather = regsGather; s.regsRpa = regsRpa; s.regsProducer = regsProducer;

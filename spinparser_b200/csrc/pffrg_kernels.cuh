@@ -2138,10 +2138,13 @@ namespace pffrg
 	// two thirds of all gathers) are cut into R chunks, and chunk r is gathered WHILE the RPA warps work on round r:
 	//   gather:  [t round 0] arrive(FULL) [s/u chunk 0] sync(EMPTY) [t round 1] arrive(FULL) [s/u chunk 1] sync(EMPTY) ... epilogue
 	//   RPA:                 sync(FULL) rpaGram(round 0) arrive(EMPTY)          sync(FULL) rpaGram(round 1) arrive(EMPTY)
-	// so one staging area suffices. Named barriers: 5 RPA warps (inside rpaGram), 6/7 + 8/9 table blocks full / empty (gather + producer),
+	// so one staging area suffices. Named barriers: 5 RPA warps (inside rpaGram), 6/7/14/1 + 8/9/15/2 table blocks full / empty (gather + producer),
 	// 10 producer warps, 11 staging area full, 12 staging area empty (gather + RPA), 13 gather warps (epilogue).
 	// Same arithmetic per node as v4FlowBody<SU2, NB, NBT, true>; the nodes of an item enter its sums in a different order.
 	// ================================================================================================================
+#ifndef PFFRG_SPLIT_TABLES
+#define PFFRG_SPLIT_TABLES 2
+#endif
 	template <int V> struct RoleTag { static constexpr int value = V; };
 	// registers per thread of the calling warp group: released to / taken from the CTA's pool (PFFRG_SPLIT_REGS_LAUNCH = what the launch gave every thread)
 	template <int REGS> __device__ __forceinline__ void regsSet()
@@ -2160,7 +2163,9 @@ namespace pffrg
 		constexpr int TBL = NG + NPROD, STG = NG + NR; // participants of the table / staging barriers
 		static_assert(NG % 128 == 0 && NR % 128 == 0 && NPROD >= 32 && NPROD <= 128, "warp groups");
 		extern __shared__ __align__(16) unsigned char smemRaw[];
-		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT, 1, gramcfg::PB, gramcfg::Lp, 2);
+		constexpr int TB = PFFRG_SPLIT_TABLES; // table blocks: the producer warps run up to TB - 1 batches ahead of the gather warps
+		static_assert(TB >= 2 && TB <= 4, "table blocks");
+		const FlowSmem<CORE, NB> lay(sizeNw(P), sizeL(P), cfg.groups, NBT, 1, gramcfg::PB, gramcfg::Lp, TB);
 		const int tid = threadIdx.x;
 		const int role = tid < NG ? 0 : (tid < NG + NR ? 1 : 2); // warp-group uniform
 		const int ptid = tid - NG - NR;
@@ -2245,7 +2250,8 @@ namespace pffrg
 			{
 				const int nFirst = tPass ? nT : nS;
 				const int nbuf = tPass ? 8 : 4;
-				const int buf = batchNo & 1;
+				const int buf = batchNo % TB;
+				const int barFull = buf == 0 ? 6 : buf == 1 ? 7 : buf == 2 ? 14 : 1, barEmpty = buf == 0 ? 8 : buf == 1 ? 9 : buf == 2 ? 15 : 2;
 				unsigned char *tb = tableBase(buf);
 				double *bW = reinterpret_cast<double *>(tb + lay.bW);
 				AccessBuffer *abTable = reinterpret_cast<AccessBuffer *>(tb + lay.ab);
@@ -2255,7 +2261,7 @@ namespace pffrg
 					const double *nodeW0 = N.wp + (size_t)(tPass ? ti : so) * N.stride, *nodeWt0 = N.wt + (size_t)(tPass ? ti : so) * N.stride;
 					const double *nodeW1 = N.wp + (size_t)uo * N.stride, *nodeWt1 = N.wt + (size_t)uo * N.stride;
 					LerpRecord *lerp = reinterpret_cast<LerpRecord *>(tb + lay.lerp);
-					if (batchNo >= 2) namedSync(8 + buf, TBL); // the gather warps are done with this block
+					if (batchNo >= TB) namedSync(barEmpty, TBL); // the gather warps are done with this block
 					// ---- phase 0, step A: the four interpolated frequencies of every node (one mesh search each)
 					for (int idx = ptid; idx < nb * 4; idx += NPROD)
 					{
@@ -2291,11 +2297,11 @@ namespace pffrg
 							loc[(node * 4 + (b - 4)) * C] = v0; loc[(node * 4 + (b - 4)) * C + 1] = v1;
 						}
 					}
-					namedArrive(6 + buf, TBL); // block `buf` is ready
+					namedArrive(barFull, TBL); // block `buf` is ready
 				}
 				else
 				{
-					namedSync(6 + buf, TBL); // wait for the producer
+					namedSync(barFull, TBL); // wait for the producer
 					// ---- phase 1: gathers + bilinear forms
 					if (worker)
 					{
@@ -2357,7 +2363,7 @@ namespace pffrg
 							acc[0] += W * K[0]; acc[1] += W * K[1];
 						}
 					}
-					namedArrive(8 + buf, TBL); // done with block `buf`
+					namedArrive(barEmpty, TBL); // done with block `buf`
 				}
 				++batchNo;
 			};
