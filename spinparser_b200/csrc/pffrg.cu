@@ -570,41 +570,43 @@ namespace
 		return form && std::string(form) == "gram";
 	}
 
+	// compile (or take from the on-disk cache) and load one kernel. A cache entry the driver rejects -- truncated by a crash, written by another
+	// toolkit -- is deleted and the kernel compiled afresh once.
+	int compileAndLoad(pffrg_context *h, JitCandidate &c, int subs, int cluster, const std::string &rpaSource, const std::string &defines, const char *what)
+	{
+		for (int attempt = 0; attempt < 2; ++attempt)
+		{
+			std::vector<char> cubin; std::string cacheHit;
+			const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, subs, cluster, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, rpaSource, cubin, defines, &cacheHit);
+			if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of %s failed: %s", what, err.c_str());
+			cudaError_t e = cudaLibraryLoadData(&c.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+			if (e == cudaSuccess) e = cudaLibraryGetKernel(&c.kernel, c.library, "pffrg_v4flow_jit");
+			if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.shape.smem);
+			if (e == cudaSuccess) return PFFRG_OK;
+			cudaGetLastError();
+			c.library = nullptr; c.kernel = nullptr;
+			if (attempt == 0 && !cacheHit.empty())
+			{
+				fprintf(stderr, "[pffrg] cached kernel %s rejected (%s): deleted, compiling afresh\n", cacheHit.c_str(), cudaGetErrorString(e));
+				std::remove(cacheHit.c_str());
+				continue;
+			}
+			return fail(PFFRG_ERR_CUDA, "loading %s failed: %s", what, cudaGetErrorString(e));
+		}
+		return fail(PFFRG_ERR_CUDA, "loading %s failed", what);
+	}
+
 	int compileCandidate(pffrg_context *h, const pffrg_desc *d, JitCandidate &c)
 	{
-		if (c.shape.gramRows > 0 && h->core == TRI)
-		{
-			std::vector<char> cubin;
-			const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, 1, 1, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, std::string(), cubin, triGramDefines(c.shape));
-			if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the TRI flow kernel (Gram form) failed: %s", err.c_str());
-			CUDA_TRY(cudaLibraryLoadData(&c.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-			CUDA_TRY(cudaLibraryGetKernel(&c.kernel, c.library, "pffrg_v4flow_jit"));
-			CUDA_TRY(cudaFuncSetAttribute((const void *)c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.shape.smem));
-			return PFFRG_OK;
-		}
-		if (c.shape.gramRows > 0)
-		{
-			std::vector<char> cubin;
-			const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, 1, 1, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, std::string(), cubin, gramDefines(c.shape));
-			if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the flow kernel (Gram form) failed: %s", err.c_str());
-			CUDA_TRY(cudaLibraryLoadData(&c.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-			CUDA_TRY(cudaLibraryGetKernel(&c.kernel, c.library, "pffrg_v4flow_jit"));
-			CUDA_TRY(cudaFuncSetAttribute((const void *)c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.shape.smem));
-			return PFFRG_OK;
-		}
+		if (c.shape.gramRows > 0 && h->core == TRI) return compileAndLoad(h, c, 1, 1, std::string(), triGramDefines(c.shape), "the TRI flow kernel (Gram form)");
+		if (c.shape.gramRows > 0) return compileAndLoad(h, c, 1, 1, std::string(), gramDefines(c.shape), "the flow kernel (Gram form)");
 		RpaProgram prog = buildRpaProgram(d, h->core, c.shape.nbt * c.shape.subs, c.shape.rpaWarps);
 		if (prog.warps < std::max(1, prog.nb / prog.lanesPerVariant) || prog.warps > c.threads / 32)
 			return fail(PFFRG_ERR_STATE, "launch shape with %d RPA warps for %d node groups (%d threads): staged nodes would be dropped", prog.warps, prog.nb / prog.lanesPerVariant, c.threads);
 		prog.maxAccumulators = defaultAccumulators(c.threads, c.shape.minBlocks);
 		prog.cluster = c.shape.cluster;
 		applyJitKnobs(prog);
-		std::vector<char> cubin;
-		const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, c.shape.subs, c.shape.cluster, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, generateRpaSource(prog), cubin);
-		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of the specialised flow kernel failed: %s", err.c_str());
-		CUDA_TRY(cudaLibraryLoadData(&c.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-		CUDA_TRY(cudaLibraryGetKernel(&c.kernel, c.library, "pffrg_v4flow_jit"));
-		CUDA_TRY(cudaFuncSetAttribute((const void *)c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.shape.smem));
-		return PFFRG_OK;
+		return compileAndLoad(h, c, c.shape.subs, c.shape.cluster, generateRpaSource(prog), std::string(), "the specialised flow kernel");
 	}
 
 	void adoptCandidate(pffrg_context *h, const JitCandidate &c)
@@ -622,10 +624,9 @@ namespace
 	// four per SM; CTAs of four and of two 128-thread sub-CTAs, i.e. several work items sharing one RPA phase) are compiled and timed on a block of work items in the middle of the item range at a mid-mesh cutoff; the
 	// fastest stays. Which shape wins depends on the lattice (measured: cubic-r7 the third, honeycomb-r7 the second, by 3-6 %).
 	// Without it, or with an explicit shape override (PFFRG_JIT_NBT, PFFRG_THREADS), the first shape is used without timing.
-	int setupJit(pffrg_context *h, const pffrg_desc *d, size_t smemMax)
+	int setupJit(pffrg_context *h, const pffrg_desc *d, size_t smemMax, bool jitEnabled)
 	{
-		const char *env = getenv("PFFRG_JIT");
-		if (env && atoi(env) == 0) return PFFRG_OK;
+		if (!jitEnabled) return PFFRG_OK;
 		long maxTerms = 60000, tuneTerms = 12000;
 		if (const char *e = getenv("PFFRG_JIT_MAX_TERMS")) maxTerms = atol(e);
 		if (const char *e = getenv("PFFRG_AUTOTUNE_MAX_TERMS")) tuneTerms = atol(e);
@@ -1561,8 +1562,12 @@ int pffrg_device_count(void)
 	return n;
 }
 
-int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
+namespace { thread_local bool g_jitSetupFailed = false; }
+
+// allowJit = false: the precompiled kernels only (the second attempt of pffrg_create after a failed run-time compilation)
+static int createHandle(const pffrg_desc *d, pffrg_handle *out, bool allowJit)
 {
+	g_jitSetupFailed = false;
 	if (!d || !out) return fail(PFFRG_ERR_ARGUMENT, "null descriptor or output pointer");
 	*out = nullptr;
 	if (d->abi_version != PFFRG_ABI_VERSION) return fail(PFFRG_ERR_ARGUMENT, "ABI version mismatch: caller %d, library %d", d->abi_version, PFFRG_ABI_VERSION);
@@ -1611,7 +1616,8 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	// a group of threads covers the L sites of one quadrature node; groups are padded to whole warps when that idles at
 	// most a quarter of the lanes (then every warp gathers from one node only: fewer cache lines per load, uniform table reads)
 	const char *jitEnv = getenv("PFFRG_JIT");
-	const LaunchGeometry geo = chooseGeometry(L, d->core == SU2 && !(jitEnv && atoi(jitEnv) == 0));
+	const bool jitEnabled = allowJit && !(jitEnv && atoi(jitEnv) == 0);
+	const LaunchGeometry geo = chooseGeometry(L, d->core == SU2 && jitEnabled);
 	h->stride = geo.stride; h->groups = geo.groups; h->threads = geo.threads;
 	// SU2/XYZ: two CTAs per SM (100 KB each); the TRI core stages four 16-channel RPA operand buffers and runs one CTA per SM
 	h->nb = 32;
@@ -1619,7 +1625,7 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	const size_t smemTarget = h->core == TRI ? 200 * 1024 : 100 * 1024;
 	while (h->nb > minNb && flowSmemBytes(h->core, h->nb, h->nw, L, h->groups) > smemTarget) h->nb >>= 1;
 	// TRI core with the Gram form of the RPA phase (run-time compiled, rpaTriGram): gather batch = staged nodes = 8
-	if (h->core == TRI && wantTriGram(h->core) && !(jitEnv && atoi(jitEnv) == 0) && 16 * L <= 1024) h->nb = 8;
+	if (h->core == TRI && wantTriGram(h->core) && jitEnabled && 16 * L <= 1024) h->nb = 8;
 	// PFFRG_NB: force the gather batch of the precompiled kernels (tests exercise every kernel variant on small lattices)
 	if (const char *e = getenv("PFFRG_NB")) { const int v = atoi(e); if ((v == 32 || v == 16 || v == 8 || (v == 4 && h->core == TRI)) && v <= h->nb) h->nb = v; }
 	h->smemBytes = flowSmemBytes(h->core, h->nb, h->nw, L, h->groups);
@@ -1665,10 +1671,24 @@ int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
 	}
 	h->bounds = { 0, h->nf };
 	if (const char *e = getenv("PFFRG_ORDER")) h->itemOrder = (e[0] == 't' || e[0] == '1') ? 1 : 0;
-	const int jitStatus = setupJit(h, d, (size_t)prop.sharedMemPerBlockOptin);
-	if (jitStatus != PFFRG_OK) { pffrg_destroy(h); return jitStatus; }
+	const int jitStatus = setupJit(h, d, (size_t)prop.sharedMemPerBlockOptin, jitEnabled);
+	if (jitStatus != PFFRG_OK) { pffrg_destroy(h); g_jitSetupFailed = true; return jitStatus; }
 	*out = h;
 	return PFFRG_OK;
+}
+
+// Run-time compilation can fail for reasons that have nothing to do with the lattice (no NVRTC at run time, a compiler error on another toolkit,
+// a full disk): the precompiled kernels can still run it, slower. So a failed setup of the run-time compiled kernel is reported on stderr and the
+// handle is built again without it -- unless the caller asked for a specific kernel form (PFFRG_RPA, PFFRG_SPLIT, ...) or for PFFRG_JIT_STRICT=1,
+// where the error stays an error.
+int pffrg_create(const pffrg_desc *d, pffrg_handle *out)
+{
+	const int rc = createHandle(d, out, true);
+	if (rc == PFFRG_OK || !g_jitSetupFailed) return rc;
+	const char *strict = getenv("PFFRG_JIT_STRICT");
+	if ((strict && atoi(strict) != 0) || getenv("PFFRG_RPA") || getenv("PFFRG_SPLIT") || getenv("PFFRG_SUBCTAS") || getenv("PFFRG_JIT_NBT")) return rc;
+	fprintf(stderr, "[pffrg] %s -- continuing with the precompiled kernels (PFFRG_JIT_STRICT=1 makes this an error)\n", pffrg_last_error());
+	return createHandle(d, out, false);
 }
 
 int pffrg_destroy(pffrg_handle h)

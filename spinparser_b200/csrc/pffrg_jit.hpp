@@ -38,5 +38,5 @@ namespace pffrg
 	// staged per RPA phase by each of the `subs` sub-CTAs of a CTA, `threads` = threads of the whole CTA, `cluster` = CTAs per thread-block cluster (they rendezvous before every RPA phase).
 	// `defines`: further preprocessor definitions (one per line), e.g. the PFFRG_GRAM_* set that selects the Gram form of the RPA phase
 	// (then rpaSource is empty).
-	std::string compileFlowKernel(int core, int nb, int nbt, int subs, int cluster, int threads, int minBlocks, const KernelSizes &sizes, const std::string &rpaSource, std::vector<char> &cubin, const std::string &defines = std::string());
+	std::string compileFlowKernel(int core, int nb, int nbt, int subs, int cluster, int threads, int minBlocks, const KernelSizes &sizes, const std::string &rpaSource, std::vector<char> &cubin, const std::string &defines = std::string(), std::string *cacheHit = nullptr);
 }

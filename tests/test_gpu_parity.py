@@ -225,3 +225,59 @@ def test_divergence_is_reported(case):
     core.setState(float(d[pre + "state/cutoff"]), v2, v4)
     assert core.computeStep() is False
     core.close()
+
+
+def _one_step_matches(core, d, case):
+    n = core.n_arrays
+    step = dumped_steps(d)[-1]
+    pre = f"step{step}/"
+    core.setState(float(d[pre + "state/cutoff"]), np.ascontiguousarray(d[pre + "state/v2"]), [np.ascontiguousarray(d[pre + f"state/v4_{c}"]) for c in range(n)])
+    assert not core.computeStep()
+    flow = core.flow()
+    for c in range(n):
+        assert_parity(flow.v4[c], d[pre + f"flow/v4_{c}"], f"{case} step {step} channel {c}")
+
+
+@pytest.mark.parametrize("case", ["su2_kagome_r7_nw6", "xyz_kagome_r4_nw8"])
+def test_failed_runtime_compilation_falls_back_to_the_precompiled_kernels(case, monkeypatch, capfd):
+    """A failure of the run-time compilation (no NVRTC, a compiler error, ...; injected here) is not a reason to refuse a lattice the
+    precompiled kernels can run: pffrg_create reports it on stderr and goes on without the specialised kernel. PFFRG_JIT_STRICT=1, or an
+    explicit request for a kernel form, keeps it an error."""
+    from spinparser_b200 import PffrgError
+    monkeypatch.setenv("PFFRG_JIT_INJECT_FAILURE", "1")
+    d = golden(case)
+    name, core = _core(d)
+    assert "continuing with the precompiled kernels" in capfd.readouterr().err
+    assert core.stats()["jit_rpa"] == 0 and core.stats()["gather_threads"] == 0
+    _one_step_matches(core, d, case)
+    core.close()
+    monkeypatch.setenv("PFFRG_JIT_STRICT", "1")
+    with pytest.raises(PffrgError, match="injected failure"):
+        _core(d)
+    monkeypatch.delenv("PFFRG_JIT_STRICT")
+    if case.startswith("su2"):
+        monkeypatch.setenv("PFFRG_RPA", "gram")
+        with pytest.raises(PffrgError, match="injected failure"):
+            _core(d)
+
+
+def test_rejected_cache_entry_is_deleted_and_compiled_afresh(monkeypatch, tmp_path, capfd):
+    """The on-disk kernel cache: an entry the driver rejects (truncated here) is deleted and the kernel compiled again."""
+    monkeypatch.setenv("PFFRG_CACHE_DIR", str(tmp_path))
+    case = "su2_kagome_r7_nw6"
+    d = golden(case)
+    name, core = _core(d)
+    assert core.stats()["jit_rpa"] == 1
+    core.close()
+    entries = list(tmp_path.glob("*.cubin"))
+    assert entries
+    sizes = {e: e.stat().st_size for e in entries}
+    for e in entries:
+        e.write_bytes(e.read_bytes()[:4096])
+    capfd.readouterr()
+    name, core = _core(d)
+    assert "compiling afresh" in capfd.readouterr().err
+    assert core.stats()["jit_rpa"] == 1
+    _one_step_matches(core, d, case)
+    core.close()
+    assert all(e.stat().st_size == sizes[e] for e in entries if e.exists()) and any(e.exists() for e in entries)
