@@ -99,6 +99,8 @@ namespace harness
 	{
 		std::string taskFile, resourcePath, out, loadState, mode = "run";
 		std::vector<int> dumpSteps;
+		std::string resumeFrom; // --resume <file>: start from a checkpoint file on disk (src/SpinParser.cpp:131-135), e.g. one written by an earlier process (a copy:
+		                        // the task-file parser of a fresh start removes <task>.checkpoint, src/TaskFileParser.cpp:74-100)
 		int maxSteps = -1, startStep = 0, threads = 0, timeStride = 1, timeRepeat = 1, timeWarmup = 1, timeOffset = 0, resumeAfter = -1;
 		bool measure = true, verbose = false, dumpLattice = true, timeCompact = false;
 	};
@@ -231,6 +233,7 @@ CommandLineOptions::CommandLineOptions(int argc, char **argv)
 		else if (a == "--time-offset") opt.timeOffset = std::stoi(next());
 		else if (a == "--time-compact") opt.timeCompact = true;
 		else if (a == "--resume-after") opt.resumeAfter = std::stoi(next());
+		else if (a == "--resume") opt.resumeFrom = next();
 		else if (a == "--checkpoint-time") _checkpointTime = std::stoi(next());
 		else if (a == "--no-measure") opt.measure = false;
 		else if (a == "--no-lattice") opt.dumpLattice = false;
@@ -313,6 +316,14 @@ int SpinParser::run(int argc, char **argv)
 		CutoffIterator cutoff = FrgCommon::cutoff().begin();
 		for (int i = 0; i < step; ++i) ++cutoff;
 		*state.cutoff = *cutoff;
+		if (!opt.resumeFrom.empty())
+		{
+			// src/SpinParser.cpp:131-135: continue from the checkpoint file (written by an earlier process through the same HDF5 calls)
+			if (!_frgCore->_flowingFunctional->readCheckpoint(opt.resumeFrom)) throw Exception(Exception::Type::IOError, "no checkpoint to resume from");
+			cutoff = FrgCommon::cutoff().find(_frgCore->_flowingFunctional->cutoff);
+			step = 0; for (auto i = FrgCommon::cutoff().begin(); i != cutoff; ++i) ++step;
+			w.scalar("resumedFromStep", step);
+		}
 
 		if (opt.mode == "time")
 		{

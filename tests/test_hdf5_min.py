@@ -1,0 +1,115 @@
+"""`.obs` / `.checkpoint` files WITHOUT libhdf5: spinparser_b200/host/hdf5_min.hpp serves the HDF5 calls of the
+reference's writers and readers and stores the files in the on-disk format of the reference's own golden files (superblock
+version 0, old-style groups, contiguous float datasets, version-1 attributes).
+
+* The UNMODIFIED reference (oracle/_ref/oracle32_pin, FP32 as shipped) run with H5MIN_DISK=1 writes `<task>.obs` files that the
+  independent, dependency-free reader tests/hdf5_v0.py (validated on the golden files, tests/test_reference_goldens.py) parses, and
+  every dataset, attribute and meta array equals the golden file test/scripted/assets/test_reference{1,2,3}.ref BIT FOR BIT.
+* The object headers it writes carry the same messages with the same bodies as the ones libhdf5 wrote into the golden files
+  (addresses and time stamps aside).
+* A checkpoint written by one process is read by another one (`--resume`, src/SpinParser.cpp:131-135) and the flow continues to the
+  same final state as an uninterrupted run.
+"""
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+REFERENCE = "/root/reference"
+ASSETS = os.path.join(REFERENCE, "test", "scripted", "assets")
+PIN = os.path.join(ROOT, "oracle", "_ref", "oracle32_pin")
+
+pytestmark = pytest.mark.skipif(not (os.path.isdir(ASSETS) and os.path.exists(PIN)), reason="needs the reference tree and oracle/_ref/oracle32_pin")
+
+
+def _run(tmp_path, xml_text, *extra, name="task"):
+    task = tmp_path / f"{name}.xml"
+    task.write_text(xml_text)
+    out = tmp_path / f"{name}.pfd"
+    env = dict(os.environ, H5MIN_DISK="1")
+    subprocess.run([PIN, "-r", os.path.join(REFERENCE, "res"), str(task), "--out", str(out), "--no-lattice", *extra], check=True, cwd=tmp_path, capture_output=True, env=env)
+    return out
+
+
+def _gen():
+    sys.path.insert(0, GOLDEN)
+    import make_reference_goldens as gen
+    return gen
+
+
+@pytest.mark.parametrize("run", ["ref1", "ref2", "ref3"])
+def test_obs_file_written_without_libhdf5_equals_the_golden_file(run, tmp_path):
+    from hdf5_v0 import read_hdf5
+    gen = _gen()
+    ref_file, lattice, model, couplings, cores = gen.TASKS[run]
+    _run(tmp_path, gen.task_xml(lattice, model, couplings, cores[0]))
+    obs = tmp_path / "task.obs"
+    assert obs.exists() and obs.read_bytes()[:8] == b"\x89HDF\r\n\x1a\n"
+    mine = read_hdf5(str(obs))
+    golden = read_hdf5(os.path.join(ASSETS, ref_file))
+    assert sorted(mine) == sorted(golden)
+    assert sum(1 for k in golden if k.endswith("/data") and "/measurement_" in k) in (68, 136, 340)
+    for path, values in golden.items():
+        assert mine[path].dtype == values.dtype and mine[path].shape == values.shape, path
+        assert np.array_equal(mine[path], values), path
+
+
+def test_object_headers_carry_the_messages_libhdf5_writes(tmp_path):
+    from hdf5_v0 import _File
+    gen = _gen()
+    ref_file, lattice, model, couplings, cores = gen.TASKS["ref1"]
+    _run(tmp_path, gen.task_xml(lattice, model, couplings, cores[0]))
+    files = [_File(open(p, "rb").read()) for p in (tmp_path / "task.obs", os.path.join(ASSETS, ref_file))]
+    # superblock: version 0, 8-byte offsets and lengths, the library's default B-tree ranks, no free-space / driver info
+    for f in files:
+        assert f.b[8:24] == files[1].b[8:24]
+        assert struct.unpack_from("<Q", f.b, 40)[0] == len(f.b)  # end-of-file address
+
+    def header_of(f, path):
+        addr = f.root_header
+        for name in [p for p in path.split("/") if p]:
+            msgs = dict(f.messages(addr))
+            addr = f.group_entries(*struct.unpack_from("<QQ", msgs[0x0011], 0))[name]
+        return addr
+
+    def messages(f, path):
+        return [(t, b) for t, b in f.messages(header_of(f, path)) if t not in (0x0010, 0x0000)]  # continuation blocks / padding are layout, not content
+
+    for path in ("/SU2CorZZ/data/measurement_3/data", "/SU2CorDD/meta/basis", "/SU2CorDD/meta/sites", "/SU2CorZZ/meta/latticeVectors"):
+        mine, theirs = messages(files[0], path), messages(files[1], path)
+        assert [t for t, _ in mine] == [t for t, _ in theirs] == [0x0001, 0x0003, 0x0005, 0x0008, 0x0012]
+        for (t, a), (_, b) in zip(mine, theirs):
+            if t == 0x0008:
+                assert a[:2] == b[:2] and a[10:18] == b[10:18]  # version 3, contiguous, the same size
+            elif t == 0x0012:
+                assert a[:4] == b[:4]
+            else:
+                assert a == b, (path, hex(t))
+    # a measurement group: symbol table + the cutoff attribute, attribute message identical
+    mine, theirs = messages(files[0], "/SU2CorZZ/data/measurement_3"), messages(files[1], "/SU2CorZZ/data/measurement_3")
+    assert sorted(t for t, _ in mine) == sorted(t for t, _ in theirs) == [0x000C, 0x0011]
+    assert dict(mine)[0x000C] == dict(theirs)[0x000C]
+
+
+def test_checkpoint_written_by_one_process_resumes_in_another(tmp_path):
+    from spinparser_b200.pfd import read_pfd
+    gen = _gen()
+    ref_file, lattice, model, couplings, cores = gen.TASKS["ref1"]
+    xml = gen.task_xml(lattice, model, couplings, cores[0])
+    full = read_pfd(str(_run(tmp_path, xml, "--no-measure", name="full")))
+    # first process: 12 steps, a checkpoint after every step; second process: --resume
+    _run(tmp_path, xml, "--no-measure", "--max-steps", "12", "--checkpoint-time", "-1", name="part")
+    checkpoint = tmp_path / "part.checkpoint"
+    assert checkpoint.exists() and checkpoint.read_bytes()[:8] == b"\x89HDF\r\n\x1a\n"
+    saved = tmp_path / "saved.checkpoint"  # (a fresh start of the reference's task-file parser removes <task>.checkpoint, src/TaskFileParser.cpp:74-100)
+    checkpoint.rename(saved)
+    resumed = read_pfd(str(_run(tmp_path, xml, "--no-measure", "--resume", str(saved), name="part")))
+    assert int(resumed["resumedFromStep"]) == 12
+    assert int(resumed["finalStep"]) == int(full["finalStep"])
+    for key in [k for k in full if k.startswith("final/")]:
+        assert np.array_equal(resumed[key], full[key]), key

@@ -223,3 +223,30 @@ def test_diverging_flow_stops_the_driver_with_gpu_cores(tmp_path):
     for k in want:
         if k.startswith("final/v"):
             assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("measurement", ["device", "host"])
+def test_obs_file_on_disk_without_libhdf5(measurement, tmp_path):
+    """With H5MIN_DISK=1 the HDF5 calls of the writers (the device measurement's own and the reference's) end in a real HDF5 file
+    (spinparser_b200/host/hdf5_min.hpp, superblock version 0 like the reference's golden files): the independent reader parses it and
+    finds exactly the datasets and attributes of the run."""
+    import shutil
+    from hdf5_v0 import read_hdf5
+    from spinparser_b200.pfd import read_pfd
+    case = CASES[0]
+    task = tmp_path / "task.xml"
+    shutil.copy(os.path.join(GOLDEN, "tasks", case + ".xml"), task)
+    out = tmp_path / "task.pfd"
+    env = dict(os.environ, SPINPARSER_BACKEND="b200", SPINPARSER_B200_MEASUREMENT=measurement, H5MIN_DISK="1")
+    proc = subprocess.run([os.path.join(REF, "spinparser32_b200"), "-r", os.path.join(ROOT, "oracle", "res"), str(task), "--out", str(out), "--no-lattice"],
+                          env=env, cwd=str(tmp_path), capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    obs = tmp_path / "task.obs"
+    assert obs.exists() and obs.read_bytes()[:8] == b"\x89HDF\r\n\x1a\n"
+    on_disk = read_hdf5(str(obs))
+    dumped = {k[len("h5/obs"):]: v for k, v in read_pfd(str(out)).items() if k.startswith("h5/obs/")}
+    assert len(on_disk) > 100 and sorted(on_disk) == sorted(dumped)
+    for k, v in dumped.items():
+        assert np.array_equal(on_disk[k].ravel(), np.asarray(v, dtype=on_disk[k].dtype).ravel()), k
+    _compare({"h5/obs" + k: v for k, v in on_disk.items()} | {"finalStep": read_pfd(str(out))["finalStep"]}, golden(case, "f32"), rel=0.0, floor_rel=0.0, floor_abs=1e-5)
