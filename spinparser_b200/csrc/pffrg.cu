@@ -227,9 +227,19 @@ namespace
 	}
 
 	template <int CORE, int NB> size_t flowSmemBytes(int nw, int L, int groups, int nbt, int subs) { return FlowSmem<CORE, NB>(nw, L, groups, nbt, subs).total; }
-	// shared memory of the SU2 kernel with the Gram form of the RPA phase: gramRows rows of the Gram matrix next to nbt staged nodes
-	size_t gramSmemBytes(int nb, int nw, int L, int Lp, int groups, int nbt, int gramRows, int tableCopies = 1)
+	// Operand geometry of the Gram form: SU2 -- the lattice's sites; XYZ -- the three spin channels of a site as virtual sites c L + j (the
+	// density channel rides in the second component of the c = 0 entries), outputs o = c L + rid and 3 L + rid (see gramcfg, pffrg_kernels.cuh)
+	struct GramGeometry { int lv, lp, lout; };
+	GramGeometry gramGeometry(int core, int L, int Lp)
 	{
+		if (core == XYZ) return { 3 * L, (3 * L + 3) / 4 * 4, 4 * L };
+		return { L, Lp, L };
+	}
+	// shared memory of the kernel with the Gram form of the RPA phase: gramRows rows of the Gram matrix next to nbt staged nodes (Lp: padded operand sites)
+	size_t gramSmemBytes(int nb, int nw, int L, int Lp, int groups, int nbt, int gramRows, int tableCopies = 1, int core = SU2)
+	{
+		if (core == XYZ) return nb == 32 ? FlowSmem<XYZ, 32>(nw, L, groups, nbt, 1, gramRows, Lp, tableCopies).total : nb == 16 ? FlowSmem<XYZ, 16>(nw, L, groups, nbt, 1, gramRows, Lp, tableCopies).total
+		                                : FlowSmem<XYZ, 8>(nw, L, groups, nbt, 1, gramRows, Lp, tableCopies).total;
 		return nb == 32 ? FlowSmem<SU2, 32>(nw, L, groups, nbt, 1, gramRows, Lp, tableCopies).total : nb == 16 ? FlowSmem<SU2, 16>(nw, L, groups, nbt, 1, gramRows, Lp, tableCopies).total
 		                : FlowSmem<SU2, 8>(nw, L, groups, nbt, 1, gramRows, Lp, tableCopies).total;
 	}
@@ -263,7 +273,7 @@ namespace
 	// `threads` = worker threads; producer: one more warp builds the access buffers a batch ahead (two table blocks), one CTA per SM
 	// tableCopies: access-buffer table blocks (0: one, or two with producer warps; -1: the warp-specialised kernel -- two or three blocks and
 	// gather batches of up to 32 nodes, rated below)
-	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs, int producer = 0, int maxCtas = 2, int maxTiles = 16, int tableCopies = 0)
+	JitShape chooseGramShape(int nw, int L, int Lp, int groups, int threads, size_t smemMax, int64_t uniquePairs, int producer = 0, int maxCtas = 2, int maxTiles = 16, int tableCopies = 0, int core = SU2)
 	{
 		JitShape best = { 0, 0, 0, 0, 0 };
 		const bool split = tableCopies < 0;
@@ -306,7 +316,7 @@ namespace
 							if ((long)pb * (Lp + 1) > (1l << 14)) continue;           // a term word addresses the Gram block with 14 bits
 							const int blocks = (Lp + pb - 1) / pb, lastRt = (Lp - (blocks - 1) * pb + 7) / 8;
 							if (gramBusiestTiles(pb / 8, ct, warps) > maxTiles || gramBusiestTiles(lastRt, ct, warps) > maxTiles) continue; // (8 accumulator registers per tile)
-							const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, pb, copies);
+							const size_t smem = gramSmemBytes(nb, nw, L, Lp, groups, nbt, pb, copies, core);
 							if (smem > budget) continue;
 							const double phases = (64 + nbt - 1) / nbt;
 							double cost = phases * (1.03 * (double)uniquePairs / 128.0 / warps * 60.0 + blocks * 1500.0) + (nb == 8 ? (producer ? 6000.0 : 15000.0) : 0.0); // (with producer warps the access-buffer phases are off the critical path; measured +4 % with batches of 8)
@@ -463,6 +473,8 @@ namespace
 
 	bool wantGram(int core, int64_t uniquePairs)
 	{
+		// XYZ: on request only (PFFRG_RPA=gram; warp-specialised kernel with the spin channels as virtual sites, at most 63 representative sites)
+		if (core == XYZ) { const char *f = getenv("PFFRG_RPA"); return f && std::string(f) == "gram"; }
 		if (core != SU2) return false;
 		long minTerms = 2000; // (cubic-r7, 3453 terms: straight-line code 17.9 ms, warp-specialised Gram kernel 16.3 ms; square-r4, 136 terms: 0.69 / 1.01 ms)
 		if (const char *e = getenv("PFFRG_GRAM_MIN_TERMS")) minTerms = atol(e);
@@ -470,9 +482,11 @@ namespace
 		return form ? std::string(form) == "gram" : uniquePairs > minTerms;
 	}
 
-	std::string gramDefines(const JitShape &s)
+	std::string gramDefines(const JitShape &s, int core = SU2, int L = 0, int Lp = 0)
 	{
-		return "#define PFFRG_GRAM 1\n#define PFFRG_GRAM_THREADS " + std::to_string(s.gramThreads) + "\n#define PFFRG_GRAM_PB " + std::to_string(s.gramRows) +
+		const GramGeometry geo = gramGeometry(core, L, Lp);
+		return (core == XYZ ? "#define PFFRG_GRAM_LP " + std::to_string(geo.lp) + "\n#define PFFRG_GRAM_LV " + std::to_string(geo.lv) + "\n#define PFFRG_GRAM_LOUT " + std::to_string(geo.lout) + "\n" : std::string()) +
+		       "#define PFFRG_GRAM 1\n#define PFFRG_GRAM_THREADS " + std::to_string(s.gramThreads) + "\n#define PFFRG_GRAM_PB " + std::to_string(s.gramRows) +
 		       "\n" + (s.producer ? "#define PFFRG_PRODUCER " + std::to_string(s.producer) + "\n" : std::string()) +
 		       (s.splitGather ? "#define PFFRG_SPLIT 1\n#define PFFRG_SPLIT_GATHER_THREADS " + std::to_string(s.splitGather) + "\n#define PFFRG_SPLIT_REGS_GATHER " + std::to_string(s.regsGather) +
 		                        "\n#define PFFRG_SPLIT_TABLES " + std::to_string(s.tableCopies) + "\n#define PFFRG_SPLIT_REGS_LAUNCH " + std::to_string(s.regsLaunch) + "\n#define PFFRG_SPLIT_REGS_RPA " + std::to_string(s.regsRpa) + "\n#define PFFRG_SPLIT_REGS_PRODUCER " + std::to_string(s.regsProducer) + "\n" : std::string());
@@ -497,17 +511,19 @@ namespace
 
 	// Launch of the SU2 kernel with the Gram form of the RPA phase: shape, threads per CTA, gather groups and the number of warps that walk the term array
 	struct GramLaunch { JitShape shape; int threads; int reduceWarps; int groups; };
-	GramLaunch chooseGramLaunch(int nw, int L, int Lp, int groups, int stride, int threads, size_t smemMax, int64_t uniquePairs, bool large)
+	GramLaunch chooseGramLaunch(int nw, int L, int Lp, int groups, int stride, int threads, size_t smemMax, int64_t uniquePairs, bool large, int core = SU2)
 	{
 		GramLaunch g = { { 0, 0, 0, 0, 0 }, threads, threads / 32, groups };
 		const int workers = threads / 32 * 32;
-		if (wantSplit(large))
+		const GramGeometry geo = gramGeometry(core, L, Lp);
+		if (core == XYZ && geo.lout > 255) return g; // an output index has 8 bits in a term word
+		if (wantSplit(large) || core == XYZ)
 		{
 			// gather warps: at most 256 threads -- two nodes in flight up to 128 sites per group, one above (the register file is what bounds
 			// the loads in flight); RPA warps: one warp group, two where the Gram matrix is large (L > 128)
 			const int splitGroups = std::max(1, std::min(groups, 256 / stride));
 			const int gather = (splitGroups * stride + 127) / 128 * 128;
-			int rpa = stride > 128 ? 256 : 128, producer = wantProducer() ? wantProducer() : 4;
+			int rpa = (stride > 128 || geo.lp > 128) ? 256 : 128, producer = wantProducer() ? wantProducer() : 4;
 			if (const char *e = getenv("PFFRG_SPLIT_RPA_THREADS")) rpa = std::max(128, atoi(e) / 128 * 128);
 			const int total = gather + rpa + 128;
 			if (total <= 1024)
@@ -519,7 +535,7 @@ namespace
 				if (const char *e = getenv("PFFRG_SPLIT_REGS_RPA")) regsRpa = std::max(24, atoi(e) / 8 * 8);
 				const int regsGather = std::min(256, (pool - 128 * regsProducer - rpa * regsRpa) / gather / 8 * 8);
 				// one CTA per SM (the warp groups re-partition its whole register file); accumulator tiles of the block update as the RPA warps' registers allow
-				JitShape s = chooseGramShape(nw, L, Lp, splitGroups, rpa, smemMax, uniquePairs, producer, 1, std::min(16, (regsRpa - 56) / 8), -1);
+				JitShape s = chooseGramShape(nw, L, geo.lp, splitGroups, rpa, smemMax, core == XYZ ? 4 * uniquePairs : uniquePairs, producer, 1, std::min(16, (regsRpa - 56) / 8), -1, core);
 				if (s.nb && regsGather >= 96)
 				{
 					s.splitGather = gather; s.regsLaunch = pool / total; s.regsGather = regsGather; s.regsRpa = regsRpa; s.regsProducer = regsProducer;
@@ -528,6 +544,7 @@ namespace
 				}
 			}
 		}
+		if (core == XYZ) return g; // the XYZ Gram form exists in the warp-specialised kernel only
 		if (wantProducer() && workers + 32 * wantProducer() <= 1024)
 		{
 			g.shape = chooseGramShape(nw, L, Lp, groups, workers, smemMax, uniquePairs, wantProducer());
@@ -599,7 +616,7 @@ namespace
 	int compileCandidate(pffrg_context *h, const pffrg_desc *d, JitCandidate &c)
 	{
 		if (c.shape.gramRows > 0 && h->core == TRI) return compileAndLoad(h, c, 1, 1, std::string(), triGramDefines(c.shape), "the TRI flow kernel (Gram form)");
-		if (c.shape.gramRows > 0) return compileAndLoad(h, c, 1, 1, std::string(), gramDefines(c.shape), "the flow kernel (Gram form)");
+		if (c.shape.gramRows > 0) return compileAndLoad(h, c, 1, 1, std::string(), gramDefines(c.shape, h->core, h->L, h->Lp), "the flow kernel (Gram form)");
 		RpaProgram prog = buildRpaProgram(d, h->core, c.shape.nbt * c.shape.subs, c.shape.rpaWarps);
 		if (prog.warps < std::max(1, prog.nb / prog.lanesPerVariant) || prog.warps > c.threads / 32)
 			return fail(PFFRG_ERR_STATE, "launch shape with %d RPA warps for %d node groups (%d threads): staged nodes would be dropped", prog.warps, prog.nb / prog.lanesPerVariant, c.threads);
@@ -656,19 +673,19 @@ namespace
 		// (rpaGram; no generated code, any lattice size); PFFRG_RPA=code -- lattice-specialised straight-line code. Default: the Gram form
 		// for lattices with more than PFFRG_GRAM_MIN_TERMS (2000) merged overlap terms (as the warp-specialised kernel v4FlowBodySplit), where the straight-line code no longer fits the
 		// instruction caches.
-		if (h->core == SU2)
+		if (h->core == SU2 || h->core == XYZ)
 		{
 			const char *form = getenv("PFFRG_RPA");
 			if (wantGram(h->core, h->uniquePairs))
 			{
-				const GramLaunch launch = chooseGramLaunch(h->nw, h->L, h->Lp, h->groups, h->stride, h->threads, smemMax, h->uniquePairs, !form);
+				const GramLaunch launch = chooseGramLaunch(h->nw, h->L, h->Lp, h->groups, h->stride, h->threads, smemMax, h->uniquePairs, !form, h->core);
 				const JitShape &shape = launch.shape;
 				if (!shape.nb) return form ? fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_RPA=gram: no launch shape fits (threads %d, L %d)", h->threads, h->L) : PFFRG_OK;
 				JitCandidate c = { launch.threads, launch.groups, shape, nullptr, nullptr, 0.f };
 				const int rc = compileCandidate(h, d, c);
 				if (rc != PFFRG_OK) return rc;
 				std::vector<unsigned> terms; std::vector<int> seg;
-				buildGramTables(d, h->L, h->Lp, shape.gramRows, launch.reduceWarps, terms, seg);
+				buildGramTables(d, h->L, gramGeometry(h->core, h->L, h->Lp).lp, shape.gramRows, launch.reduceWarps, terms, seg);
 				CUDA_TRY(h->dGramTerms.upload(terms)); CUDA_TRY(h->dGramSeg.upload(seg));
 				h->gramWords = (int64_t)terms.size();
 				adoptCandidate(h, c);
@@ -1070,15 +1087,29 @@ namespace
 	void buildGramTables(const pffrg_desc *d, int L, int Lp, int PB, int warps, std::vector<unsigned> &terms, std::vector<int> &seg, double *conflictDegree)
 	{
 		const int blocks = (Lp + PB - 1) / PB, maxMult = 511;
-		std::vector<std::map<std::tuple<int, int, int, int>, int>> merged(L);
-		for (int rid = 0; rid < L; ++rid) merged[rid] = mergedOverlap(d, SU2, rid);
+		const int core = d->core == XYZ ? XYZ : SU2;
+		// XYZ: operand index = channel * L + site, output = channel * L + rid for the spin channels (read from G.x), 3 L + rid for the density
+		// channel (from G.y, which is non-zero in the corner of the two c = 0 operand ranges only); what the other component of an entry adds
+		// to the other half of the outputs is never read (v4FlowBodySplit's epilogue)
+		const int outputs = core == XYZ ? 4 * L : L;
+		std::vector<std::map<std::tuple<int, int, int, int>, int>> merged(outputs); // per output: (operand p, 0, 0, operand q) -> multiplicity
+		for (int rid = 0; rid < L; ++rid)
+		{
+			if (core == SU2) { merged[rid] = mergedOverlap(d, SU2, rid); continue; }
+			for (auto &kv : mergedOverlap(d, XYZ, rid))
+			{
+				const int r1 = std::get<0>(kv.first), p1 = std::get<1>(kv.first), p2 = std::get<2>(kv.first), r2 = std::get<3>(kv.first);
+				for (int c = 0; c < 3; ++c) merged[c * L + rid][std::make_tuple(((p1 >> (2 * c)) & 3) * L + r1, 0, 0, ((p2 >> (2 * c)) & 3) * L + r2)] += kv.second;
+				merged[3 * L + rid][std::make_tuple(r1, 0, 0, r2)] += kv.second;
+			}
+		}
 		seg.assign((size_t)2 * blocks * warps, 0);
 		terms.clear();
 		double sets = 0.0, degree = 0.0;
 		for (int blk = 0; blk < blocks; ++blk)
 		{
-			std::vector<std::vector<unsigned>> lists(L);
-			for (int rid = 0; rid < L; ++rid)
+			std::vector<std::vector<unsigned>> lists(outputs);
+			for (int rid = 0; rid < outputs; ++rid)
 				for (auto &kv : merged[rid])
 				{
 					const int p = std::get<0>(kv.first), q = std::get<3>(kv.first);
@@ -1088,7 +1119,7 @@ namespace
 				}
 			// whole lists to warps: longest first, to the least loaded warp
 			std::vector<int> order;
-			for (int rid = 0; rid < L; ++rid) if (!lists[rid].empty()) order.push_back(rid);
+			for (int rid = 0; rid < outputs; ++rid) if (!lists[rid].empty()) order.push_back(rid);
 			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lists[a].size() > lists[b].size(); });
 			std::vector<std::vector<int>> owned(warps);
 			std::vector<long> load(warps, 0);
@@ -1321,6 +1352,7 @@ namespace
 		// RPA work per t-channel node in units of the cost model (overlap terms of the indexed forms)
 		double rpaTerms = (double)h->uniquePairs;
 		if (h->gramRows > 0 && h->core == SU2) rpaTerms = (double)h->L * h->L;
+		if (h->gramRows > 0 && h->core == XYZ) rpaTerms = 9.0 * h->L * h->L / 2.0; // (3 L)^2 double2 entries per node against 4 channels per term of the indexed form
 		if (h->gramRows > 0 && h->core == TRI) { const double LpT = (double)((h->L + 7) / 8 * 8); rpaTerms = (double)h->triBlockCount * LpT * LpT * 2.0 / 128.0; }
 		h->bounds = planPartition(h->core, h->nw, h->L, rpaTerms, counts, h->nRanks, feedback ? &prev : nullptr, feedback ? &h->rankTimes : nullptr);
 	}
@@ -2079,14 +2111,14 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 	if (wantGram(d->core, uniquePairs))
 	{
 		const int Lp = paddedSites(L);
-		const GramLaunch launch = chooseGramLaunch(d->n_frequencies, L, Lp, groups, geo.stride, threads, 227 * 1024, uniquePairs, !getenv("PFFRG_RPA"));
+		const GramLaunch launch = chooseGramLaunch(d->n_frequencies, L, Lp, groups, geo.stride, threads, 227 * 1024, uniquePairs, !getenv("PFFRG_RPA"), d->core);
 		const JitShape &g = launch.shape;
 		if (!g.nb) return fail(PFFRG_ERR_UNSUPPORTED, "no launch shape for the Gram form of the RPA phase");
 		std::vector<char> cubin;
-		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, launch.threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g));
+		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, launch.threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g, d->core, L, Lp));
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
 		std::vector<unsigned> terms; std::vector<int> seg; double conflicts = 0.0;
-		buildGramTables(d, L, Lp, g.gramRows, launch.reduceWarps, terms, seg, &conflicts);
+		buildGramTables(d, L, gramGeometry(d->core, L, Lp).lp, g.gramRows, launch.reduceWarps, terms, seg, &conflicts);
 		if (getenv("PFFRG_JIT_VERBOSE")) fprintf(stderr, "[pffrg gram] threads %d nb %d nbt %d ctas %d smem %zu rows/block %d gemm threads %d words %zu (merged terms %lld) bank-conflict degree %.3f\n", threads, g.nb, g.nbt, g.minBlocks, g.smem, g.gramRows, g.gramThreads, terms.size(), (long long)uniquePairs, conflicts);
 		if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
 		return PFFRG_OK;
@@ -2203,7 +2235,8 @@ int pffrg_site_order(const pffrg_desc *d, int32_t *order)
 int pffrg_gram_tables(const pffrg_desc *d, int rowsPerBlock, int warps, uint32_t *terms, int capacity, int32_t *seg, double *conflictDegree)
 {
 	if (!d || d->n_sites < 1 || d->n_sites > 256 || !d->overlap_offsets || rowsPerBlock < 1 || warps < 1 || warps > 32 || !seg || (!terms && capacity > 0)) return fail(PFFRG_ERR_ARGUMENT, "bad argument");
-	const int L = d->n_sites, Lp = paddedSites(L);
+	const int L = d->n_sites, Lp = gramGeometry(d->core, L, paddedSites(L)).lp; // (XYZ: three virtual sites per site)
+	if (d->core == XYZ && 4 * L > 255) return fail(PFFRG_ERR_UNSUPPORTED, "the XYZ Gram form handles at most 63 representative sites");
 	if ((long)rowsPerBlock * (Lp + 1) > (1l << 14) || rowsPerBlock % 8) return fail(PFFRG_ERR_ARGUMENT, "%d rows of %d do not fit the 14 offset bits of a term word (or not a multiple of 8)", rowsPerBlock, Lp + 1);
 	std::vector<unsigned> t; std::vector<int> s;
 	buildGramTables(d, L, Lp, rowsPerBlock, warps, t, s, conflictDegree);

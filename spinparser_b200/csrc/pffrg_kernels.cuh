@@ -374,7 +374,7 @@ namespace pffrg
 			// the per-group partial sums of the epilogue reuse the staging area (dead by then)
 			// TRI Gram form: gramRows = resident (c1, c2) blocks, Lp = sites per channel of the staged operands (trigram::LpT)
 			const size_t stBytes = (gramRows > 0 && CORE == TRI) ? sizeof(double) * 2 * (2 * (size_t)nbt) * (16 * Lp + 4)
-			                     : gramRows > 0 ? sizeof(double) * 2 * C * (Lp + 2) * (subs * nbt)
+			                     : gramRows > 0 ? sizeof(double) * 2 * 2 * (Lp + 2) * (subs * nbt)
 			                     : (CORE == TRI && NB == 8) ? sizeof(double) * 4 * tri8BufferStride(L) : sizeof(double) * RpaStage<CORE>::buffers * C * L * (subs * nbt + 1);
 			partStride = sizeof(double) * groups * C * L;
 			const size_t partBytes = partStride * subs;
@@ -385,7 +385,7 @@ namespace pffrg
 			rpa = o; o += sizeof(double) * C * L * rpaCopies;
 			staged = o; if (subs > 1) o += sizeof(int) * 4; // nodes staged by each sub-CTA for the coming RPA phase
 			o = alignUp(o, 16);
-			gram = o; o += gramRows <= 0 ? 0 : CORE == TRI ? sizeof(double) * (size_t)gramRows * Lp * (Lp + 1) : sizeof(double) * C * (size_t)gramRows * (Lp + 1); // strides: gramcfg::LpS, gramcfg::LpG / trigram::GS
+			gram = o; o += gramRows <= 0 ? 0 : CORE == TRI ? sizeof(double) * (size_t)gramRows * Lp * (Lp + 1) : sizeof(double) * 2 * (size_t)gramRows * (Lp + 1); // strides: gramcfg::LpS, gramcfg::LpG / trigram::GS
 			total = alignUp(o, 16);
 		}
 	};
@@ -1201,9 +1201,19 @@ namespace pffrg
 	//  - The rows are worked off in blocks of PB rows: the block is written to shared memory (Gs[row][q] of double2, row stride LpG) and
 	//    reduced at once (gramReduce below): every warp owns a contiguous range of whole rid lists of the block's term array.
 	// ================================================================================================================
+	// PFFRG_GRAM_LP / _LV / _LOUT: rows and columns of the Gram matrix (padded / live) and the stride between the two output channels of the
+	// reduction. SU2: the lattice's Lp, L, L. XYZ (warp-specialised kernel only): the three spin channels of a site are staged as three
+	// "virtual sites" c L + j holding {A_c, c == 0 ? A_density : 0}, so G.x covers all 9 spin channel pairs and G.y the density pair in
+	// its first L x L corner; outputs are o = c L + rid (spin, from G.x) and 3 L + rid (density, from G.y), LOUT = 4 L apart.
+#ifndef PFFRG_GRAM_LP
+#define PFFRG_GRAM_LP PFFRG_CONST_LP
+#define PFFRG_GRAM_LV PFFRG_CONST_L
+#define PFFRG_GRAM_LOUT PFFRG_CONST_L
+#endif
 	namespace gramcfg
 	{
-		constexpr int Lp = PFFRG_CONST_LP;
+		constexpr int Lp = PFFRG_GRAM_LP;
+		constexpr int LV = PFFRG_GRAM_LV;              // live operand entries per staged row (the rest is zero padding)
 		constexpr int LpS = Lp + 2;                    // node stride of the staged operands in double2: = 2 mod 4, so the 4 nodes x 2 sites of a quarter
 		                                               // warp's fragment load fall into 8 different 16-byte bank groups
 		constexpr int LpG = Lp + 1;                    // row stride of the Gram block in double2 (odd: the accumulator stores of a quarter warp -- 2 rows x
@@ -1331,7 +1341,7 @@ namespace pffrg
 	}
 	__device__ __forceinline__ void gramReduce(GramStream &S, const double2 *__restrict__ Gs, double *rpaOut, int lane)
 	{
-		constexpr int L = PFFRG_CONST_L;
+		constexpr int L = PFFRG_GRAM_LOUT;
 		constexpr int PF = PFFRG_GRAM_PREFETCH; // groups in flight from the term array (L2: ~800 clocks, ~60 clocks of work per group)
 		const int T4 = S.T4;
 		if (T4 <= 0) return;
@@ -2153,10 +2163,12 @@ namespace pffrg
 		else if constexpr (REGS < PFFRG_SPLIT_REGS_LAUNCH) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(REGS));
 	}
 
-	template <int NB, int NBT>
+	template <int CORE, int NB, int NBT>
 	__device__ __forceinline__ void v4FlowBodySplit(const Problem &P, const NodeTable &N, const FlowConfig &cfg, const double *__restrict__ v4, double *__restrict__ flow, int itemBegin, int *nanFlag)
 	{
-		constexpr int CORE = SU2, C = 2;
+		static_assert(CORE == SU2 || CORE == XYZ, "the warp-specialised kernel exists for the SU2 and the XYZ core");
+		constexpr int C = channelsOf(CORE);
+		constexpr int LV = gramcfg::LV;                // live entries of a staged operand row: L (SU2), 3 L virtual sites (XYZ)
 		constexpr int NG = PFFRG_SPLIT_GATHER_THREADS; // gather threads (a multiple of 128; the first cfg.groups * cfg.stride of them work)
 		constexpr int NR = PFFRG_GRAM_THREADS;         // RPA threads (a multiple of 128)
 		constexpr int NPROD = 32 * PFFRG_PRODUCER;     // producer threads (1..4 warps of the last warp group)
@@ -2178,9 +2190,9 @@ namespace pffrg
 		const int L = sizeL(P), nw = sizeNw(P);
 
 		for (int i = tid; i < nw; i += blockDim.x) mesh[i] = P.mesh[i];
-		for (int i = tid; i < lay.rpaCopies * C * L; i += blockDim.x) rpaOut[i] = 0.0;
-		for (int i = tid; i < 2 * NBT * (gramcfg::LpS - L); i += blockDim.x)
-			reinterpret_cast<double2 *>(st)[(i / (gramcfg::LpS - L)) * gramcfg::LpS + L + i % (gramcfg::LpS - L)] = make_double2(0.0, 0.0);
+		for (int i = tid; i < lay.rpaCopies * C * L; i += blockDim.x) rpaOut[i] = 0.0; // (XYZ: 2 * LOUT = 8 L entries, rpaCopies >= 2)
+		for (int i = tid; i < 2 * NBT * (gramcfg::LpS - LV); i += blockDim.x)
+			reinterpret_cast<double2 *>(st)[(i / (gramcfg::LpS - LV)) * gramcfg::LpS + LV + i % (gramcfg::LpS - LV)] = make_double2(0.0, 0.0);
 
 		// PERSISTENT CTAs: CTA b works on the items itemBegin + b, + gridDim.x, ... (the host launches one CTA per SM, or one per item). The
 		// producer warps run ahead into the next item, the gather warps go on with its first batch right after the epilogue, the barrier
@@ -2232,8 +2244,8 @@ namespace pffrg
 		auto runItems = [&](auto roleTag)
 		{
 			constexpr int ROLE = decltype(roleTag)::value;
-			int siteFwd = 0, siteInv = 0;
-			if (ROLE == 0 && worker) { siteFwd = P.sites_rid[j]; siteInv = P.inv_rid[j]; }
+			int siteFwd = 0, siteInv = 0, permFwd = PERM_IDENTITY, permInv = PERM_IDENTITY;
+			if (ROLE == 0 && worker) { siteFwd = P.sites_rid[j]; siteInv = P.inv_rid[j]; permFwd = P.sites_perm[j]; permInv = P.inv_perm[j]; }
 			int batchNo = 0; // batches handed over so far (the same sequence on both sides, continued over the items)
 			bool bad = false;
 			#pragma unroll 1
@@ -2244,7 +2256,9 @@ namespace pffrg
 			ItemFrequencies f;
 			f.s = mesh[so]; f.t = mesh[ti]; f.u = mesh[uo];
 			f.w1p = 0.5 * (f.s + f.t + f.u); f.w1 = 0.5 * (f.s - f.t + f.u); f.w2p = 0.5 * (f.s - f.t - f.u); f.w2 = 0.5 * (f.s + f.t - f.u);
-			double acc[C] = { 0.0, 0.0 };
+			double acc[C];
+			#pragma unroll
+			for (int c = 0; c < C; ++c) acc[c] = 0.0;
 			// one batch of nodes [b0, b0 + nb) of the t channel (operands staged at `staged`) or of the s/u node list
 			auto doBatch = [&](const bool tPass, const int b0, const int nb, const int staged)
 			{
@@ -2272,7 +2286,7 @@ namespace pffrg
 						if (qq == 0)
 						{
 							const double wt = gn < nFirst ? nodeWt0[gn] : nodeWt1[gn - nFirst];
-							bW[node] = ch == CH_U ? -wt : wt; // SU2: the u channel enters with a minus sign (SU2FrgCore.cpp:366,370,376)
+							bW[node] = (CORE == SU2 && ch == CH_U) ? -wt : wt; // SU2: the u channel enters with a minus sign (SU2FrgCore.cpp:366,370,376); the XYZ kernels carry it themselves
 						}
 						makeLerpRecord(mesh, nw, P.meshIndex, nodeQuantity(ch, qq, f.w1p, f.w1, f.w2p, f.w2, wp), lerp[idx]);
 					}
@@ -2286,15 +2300,23 @@ namespace pffrg
 						if (tPass && b >= 4)
 						{
 							const AccessBuffer &ab = abTable[idx];
-							double v0 = 0.0, v1 = 0.0;
+							double v[C];
+							#pragma unroll
+							for (int c = 0; c < C; ++c) v[c] = 0.0;
 							#pragma unroll
 							for (int k = 0; k < 4; ++k)
 							{
-								const double2 x = __ldg(reinterpret_cast<const double2 *>(v4 + (size_t)ab.row[k] * sizeRL(P)));
-								v0 += supportSign<CORE>(ab.flags, k, 0) * ab.w[k] * x.x;
-								v1 += supportSign<CORE>(ab.flags, k, 1) * ab.w[k] * x.y;
+								const double2 *row = reinterpret_cast<const double2 *>(v4 + (size_t)ab.row[k] * sizeRL(P));
+								#pragma unroll
+								for (int pl = 0; pl < C / 2; ++pl)
+								{
+									const double2 x = __ldg(row + pl * sizeLp(P));
+									v[2 * pl] += supportSign<CORE>(ab.flags, k, 2 * pl) * ab.w[k] * x.x;
+									v[2 * pl + 1] += supportSign<CORE>(ab.flags, k, 2 * pl + 1) * ab.w[k] * x.y;
+								}
 							}
-							loc[(node * 4 + (b - 4)) * C] = v0; loc[(node * 4 + (b - 4)) * C + 1] = v1;
+							#pragma unroll
+							for (int c = 0; c < C; ++c) loc[(node * 4 + (b - 4)) * C + c] = v[c];
 						}
 					}
 					namedArrive(barFull, TBL); // block `buf` is ready
@@ -2308,7 +2330,7 @@ namespace pffrg
 						// PFFRG_PIPELINE: the 16 row loads of the node this thread works on next are in flight while the current one is combined
 						// (64 more registers: for shapes with few gather warps that own a large share of the register file)
 						[[maybe_unused]] double2 pending[4][4];
-						if constexpr (PFFRG_PIPELINE != 0)
+						if constexpr (PFFRG_PIPELINE != 0 && CORE == SU2)
 						{
 							if (g < nb)
 							{
@@ -2320,7 +2342,7 @@ namespace pffrg
 						{
 							double A[4][C];
 							const AccessBuffer *ab = abTable + node * nbuf;
-							if constexpr (PFFRG_PIPELINE != 0)
+							if constexpr (PFFRG_PIPELINE != 0 && CORE == SU2)
 							{
 								double2 current[4][4];
 								#pragma unroll
@@ -2341,13 +2363,13 @@ namespace pffrg
 							else if (PFFRG_MIRROR && tPass && mirroredPair(ab[0], ab[2]) && mirroredPair(ab[1], ab[3]))
 							{
 								// t channel: buffers 2, 3 read the rows of buffers 0, 1 (8 row loads instead of 16; warp-uniform decision)
-								gatherTwo<CORE>(P, v4, ab[0], ab[2], siteFwd, siteInv, PERM_IDENTITY, PERM_IDENTITY, A[0], A[2]);
-								gatherTwo<CORE>(P, v4, ab[1], ab[3], siteFwd, siteInv, PERM_IDENTITY, PERM_IDENTITY, A[1], A[3]);
+								gatherTwo<CORE>(P, v4, ab[0], ab[2], siteFwd, siteInv, permFwd, permInv, A[0], A[2]);
+								gatherTwo<CORE>(P, v4, ab[1], ab[3], siteFwd, siteInv, permFwd, permInv, A[1], A[3]);
 							}
 							else
 							{
 								#pragma unroll
-								for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, ab[b], siteFwd, siteInv, PERM_IDENTITY, PERM_IDENTITY, A[b]);
+								for (int b = 0; b < 4; ++b) gatherSite<CORE>(P, v4, ab[b], siteFwd, siteInv, permFwd, permInv, A[b]);
 							}
 							const double W = bW[node];
 							double K[C];
@@ -2355,12 +2377,27 @@ namespace pffrg
 							else
 							{
 								chaliceTerms<CORE>(A, loc + node * 4 * C, K);
-								// RPA operands: buffers 2 and 3 with prefactors 2S (spin) and 8S (density), SU2FrgCore.cpp:257-266; node weight folded into A
 								double2 *st2 = reinterpret_cast<double2 *>(st);
-								st2[(staged + node) * gramcfg::LpS + j] = make_double2(W * 2.0 * P.spin * A[2][0], W * 8.0 * P.spin * A[2][1]);
-								st2[(NBT + staged + node) * gramcfg::LpS + j] = make_double2(A[3][0], A[3][1]);
+								if constexpr (CORE == SU2)
+								{
+									// RPA operands: buffers 2 and 3 with prefactors 2S (spin) and 8S (density), SU2FrgCore.cpp:257-266; node weight folded into A
+									st2[(staged + node) * gramcfg::LpS + j] = make_double2(W * 2.0 * P.spin * A[2][0], W * 8.0 * P.spin * A[2][1]);
+									st2[(NBT + staged + node) * gramcfg::LpS + j] = make_double2(A[3][0], A[3][1]);
+								}
+								else
+								{
+									// XYZ: buffers 0 and 1 with prefactor 4 (XYZFrgCore.cpp:297-322); spin channel c of site j = virtual site c L + j, the density
+									// channel rides in the second component of the c = 0 entries (zero elsewhere)
+									#pragma unroll
+									for (int c = 0; c < 3; ++c)
+									{
+										st2[(staged + node) * gramcfg::LpS + c * L + j] = make_double2(W * 4.0 * A[0][c], c == 0 ? W * 4.0 * A[0][3] : 0.0);
+										st2[(NBT + staged + node) * gramcfg::LpS + c * L + j] = make_double2(A[1][c], c == 0 ? A[1][3] : 0.0);
+									}
+								}
 							}
-							acc[0] += W * K[0]; acc[1] += W * K[1];
+							#pragma unroll
+							for (int c = 0; c < C; ++c) acc[c] += W * K[c];
 						}
 					}
 					namedArrive(barEmpty, TBL); // done with block `buf`
@@ -2382,22 +2419,35 @@ namespace pffrg
 			if constexpr (ROLE == 0)
 			{
 				// ---- epilogue of the item (gather warps; the partial sums reuse the staging area, dead after the last sync(EMPTY))
-				if (worker) { part[(g * C) * L + j] = acc[0]; part[(g * C + 1) * L + j] = acc[1]; }
+				if (worker)
+				{
+					#pragma unroll
+					for (int c = 0; c < C; ++c) part[(g * C + c) * L + j] = acc[c];
+				}
 				namedSync(13, NG);
 				for (int e = tid; e < C * L; e += NG)
 				{
 					double v = 0.0;
-					for (int k = 0; k < lay.rpaCopies; ++k) { v += rpaOut[k * C * L + e]; rpaOut[k * C * L + e] = 0.0; } // (cleared for the next item of this CTA)
+					if constexpr (CORE == SU2)
+					{
+						for (int k = 0; k < lay.rpaCopies; ++k) { v += rpaOut[k * C * L + e]; rpaOut[k * C * L + e] = 0.0; } // (cleared for the next item of this CTA)
+					}
+					else v = e < 3 * L ? rpaOut[e] : rpaOut[PFFRG_GRAM_LOUT + e]; // spin outputs from G.x, density outputs (3 L + rid) from G.y
 					for (int gg = 0; gg < cfg.groups; ++gg) v += part[gg * C * L + e];
 					v /= TWO_PI;
 					const int c = e / L, jj = e - c * L;
 					flow[(size_t)item * sizeRL(P) + channelOffset(vectorWidth(CORE), c, sizeLp(P)) + jj * vectorWidth(CORE)] = v;
 					bad |= (v != v);
 				}
+				if constexpr (CORE != SU2)
+				{
+					namedSync(13, NG);
+					for (int i = tid; i < 2 * PFFRG_GRAM_LOUT; i += NG) rpaOut[i] = 0.0; // all outputs of the reduction, used or not, cleared for the next item
+				}
 				namedSync(13, NG); // the partial sums are read: the next item may stage its operands over them ...
 				// ... and the padding sites they covered are zero again (read by the Gram update, never written by the gathers)
-				for (int i = tid; i < 2 * NBT * (gramcfg::LpS - L); i += NG)
-					reinterpret_cast<double2 *>(st)[(i / (gramcfg::LpS - L)) * gramcfg::LpS + L + i % (gramcfg::LpS - L)] = make_double2(0.0, 0.0);
+				for (int i = tid; i < 2 * NBT * (gramcfg::LpS - LV); i += NG)
+					reinterpret_cast<double2 *>(st)[(i / (gramcfg::LpS - LV)) * gramcfg::LpS + LV + i % (gramcfg::LpS - LV)] = make_double2(0.0, 0.0);
 			}
 			}
 			if (ROLE == 0 && bad) atomicOr(nanFlag, 1);

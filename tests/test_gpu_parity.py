@@ -51,14 +51,20 @@ VARIANTS = [{}, {"PFFRG_JIT": "0"}, {"PFFRG_JIT": "0", "PFFRG_NB": "8"}, {"PFFRG
             {"PFFRG_RPA": "table"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "1"}, {"PFFRG_RPA": "gram", "PFFRG_TRIGRAM_RESIDENT": "2", "PFFRG_THREADS": "128"}]
 
 
+# XYZ core: Gram form of the RPA phase (spin channels as virtual sites) in the warp-specialised kernel, PFFRG_RPA=gram
+XYZ_GRAM_VARIANTS = [{"PFFRG_RPA": "gram"}, {"PFFRG_RPA": "gram", "PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}, {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1"},
+                     {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1", "PFFRG_JIT_NBT": "8", "PFFRG_JIT_NB": "8"}, {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1", "PFFRG_PERSISTENT": "0"},
+                     {"PFFRG_RPA": "gram", "PFFRG_SPLIT": "1", "PFFRG_THREADS": "128", "PFFRG_PRODUCER": "1"}]
+
+
 @pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
 @pytest.mark.parametrize("case", CASES)
 def test_one_step_flow_matches_reference(case, variant, monkeypatch):
     if case.startswith("tri") and ("PFFRG_FUSED_LOCALS" in variant or "PFFRG_JIT_NBT" in variant or "PFFRG_AUTOTUNE" in variant or "PFFRG_SUBCTAS" in variant or "PFFRG_CLUSTER" in variant or "PFFRG_MIRROR" in variant):
         pytest.skip("the TRI core has no run-time compiled variant")
-    if "PFFRG_RPA" in variant and case.startswith("xyz"):
-        pytest.skip("the XYZ core has one form of the RPA phase")
-    if not case.startswith("su2") and ("PFFRG_PRODUCER" in variant or "PFFRG_SPLIT" in variant):
+    if case.startswith("xyz") and "PFFRG_RPA" in variant and variant not in XYZ_GRAM_VARIANTS:
+        pytest.skip("XYZ: the Gram form exists in the warp-specialised kernel only; SU2 shape knobs")
+    if not case.startswith("su2") and ("PFFRG_PRODUCER" in variant or "PFFRG_SPLIT" in variant) and not (case.startswith("xyz") and variant in XYZ_GRAM_VARIANTS):
         pytest.skip("SU2 only")
     if case.startswith("tri") and variant.get("PFFRG_RPA") == "gram" and len(variant) > 1 and "PFFRG_TRIGRAM_RESIDENT" not in variant:
         pytest.skip("SU2 shape knobs")

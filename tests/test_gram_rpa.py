@@ -243,3 +243,64 @@ def test_tri_gram_tables_reproduce_the_overlap_sum(case, resident, warps):
                 assert not np.isnan(g[mult != 0]).any()
                 got[out] += float(np.sum(np.where(mult != 0, mult * np.nan_to_num(g), 0.0)))
     assert np.allclose(got, want, rtol=1e-12, atol=1e-12), np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("warps,pb", [(4, 32), (8, 16), (4, 56)])
+@pytest.mark.parametrize("case", ["xyz_honeycomb_kitaev_r3_nw10", "xyz_kagome_r4_nw8"])
+def test_xyz_gram_tables_reproduce_the_overlap_sum(case, warps, pb):
+    """XYZ: R_c[rid] = sum_i A_{p1_i(c)}[rid1_i] B_{p2_i(c)}[rid2_i] for the spin channels (p1, p2 the overlap's spin permutations) and
+    R_d = sum_i A_d B_d (src/XYZ/XYZFrgCore.cpp:297-322). The kernel stages the three spin channels of a site as virtual sites c L + j
+    with the density channel in the second component of the c = 0 entries, forms one (3 L)^2 Gram matrix of pairs and walks term words
+    whose outputs are c L + rid (first component) and 3 L + rid (second component). Same walk as gramReduce, on random operands."""
+    from spinparser_b200 import ProblemTables, _capi
+    from spinparser_b200.frgcore import make_descriptor
+    d = golden(case)
+    t = ProblemTables.from_pfd(d)
+    L = t.n_sites
+    Lv, Lp, LOUT = 3 * L, (3 * L + 3) // 4 * 4, 4 * L
+    PB = min(pb, (Lp + 7) // 8 * 8)
+    blocks = (Lp + PB - 1) // PB
+    desc = make_descriptor("XYZ", t)
+    seg = np.zeros(2 * blocks * warps, dtype=np.int32)
+    n = _capi.check(_capi.lib.pffrg_gram_tables(C.byref(desc), PB, warps, None, 0, seg.ctypes.data_as(C.POINTER(C.c_int32)), None))
+    terms = np.zeros(n, dtype=np.uint32)
+    assert _capi.lib.pffrg_gram_tables(C.byref(desc), PB, warps, terms.ctypes.data_as(C.POINTER(C.c_uint32)), n, seg.ctypes.data_as(C.POINTER(C.c_int32)), None) == n
+    seg = seg.reshape(blocks * warps, 2)
+    rng = np.random.default_rng(9)
+    nodes = 7
+    A = rng.uniform(-1, 1, (nodes, 4, L)); B = rng.uniform(-1, 1, (nodes, 4, L))
+    # staged operands: [node][virtual site] -> (x, y)
+    Ax = np.zeros((nodes, Lp)); Ay = np.zeros((nodes, Lp)); Bx = np.zeros((nodes, Lp)); By = np.zeros((nodes, Lp))
+    for c in range(3):
+        Ax[:, c * L:(c + 1) * L] = A[:, c]; Bx[:, c * L:(c + 1) * L] = B[:, c]
+    Ay[:, :L] = A[:, 3]; By[:, :L] = B[:, 3]
+    Gx, Gy = Ax.T @ Bx, Ay.T @ By
+    out = np.zeros((2, 2 * LOUT))  # [component][output]
+    owner = {}
+    for blk in range(blocks):
+        for warp in range(warps):
+            begin, T4 = seg[blk * warps + warp]
+            words = terms[begin:begin + 128 * T4].astype(np.int64).reshape(T4, 32, 4)
+            for lane in range(32):
+                for g in range(T4):
+                    w = words[g, lane]
+                    o = int((w[3] >> 14) & 255)
+                    mult = (w >> 22) & 511
+                    assert np.all(((w >> 14) & 255) == o) and o < LOUT
+                    if mult.any():
+                        assert owner.setdefault((blk, o), warp) == warp
+                    off = w & 0x3FFF
+                    p, q = blk * PB + off // (Lp + 1), off % (Lp + 1)
+                    assert np.all(q[mult > 0] < Lv) and np.all(p[mult > 0] < Lv)
+                    out[0, o] += float(np.sum(mult * Gx[np.minimum(p, Lp - 1), np.minimum(q, Lp - 1)]))
+                    out[1, o] += float(np.sum(mult * Gy[np.minimum(p, Lp - 1), np.minimum(q, Lp - 1)]))
+    got = np.concatenate([out[0, :3 * L], out[1, 3 * L:4 * L]]).reshape(4, L)
+    want = np.zeros((4, L))
+    off, r1, r2, p1, p2 = t.overlap_offsets, t.overlap_rid1, t.overlap_rid2, t.overlap_perm1, t.overlap_perm2
+    for rid in range(L):
+        for i in range(off[rid], off[rid + 1]):
+            for c in range(3):
+                want[c, rid] += float(np.dot(A[:, int(p1[i][c]), r1[i]], B[:, int(p2[i][c]), r2[i]]))
+            want[3, rid] += float(np.dot(A[:, 3, r1[i]], B[:, 3, r2[i]]))
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12), np.abs(got - want).max()
+    assert int(np.sum((terms.astype(np.int64) >> 22) & 511)) == 4 * int(off[-1])
