@@ -473,9 +473,9 @@ namespace
 
 	bool wantGram(int core, int64_t uniquePairs)
 	{
-		// XYZ: on request only (PFFRG_RPA=gram; warp-specialised kernel with the spin channels as virtual sites, at most 63 representative sites)
-		if (core == XYZ) { const char *f = getenv("PFFRG_RPA"); return f && std::string(f) == "gram"; }
-		if (core != SU2) return false;
+		// XYZ: warp-specialised kernel with the spin channels as virtual sites (at most 63 representative sites; a lattice that does not fit
+		// stays on the straight-line code). Same threshold: honeycomb-r10 (3 323 merged terms) 79.2 -> 54.2 ms, honeycomb-r7 (944) 26.2 -> 26.1 ms
+		if (core != SU2 && core != XYZ) return false;
 		long minTerms = 2000; // (cubic-r7, 3453 terms: straight-line code 17.9 ms, warp-specialised Gram kernel 16.3 ms; square-r4, 136 terms: 0.69 / 1.01 ms)
 		if (const char *e = getenv("PFFRG_GRAM_MIN_TERMS")) minTerms = atol(e);
 		const char *form = getenv("PFFRG_RPA");
@@ -680,17 +680,21 @@ namespace
 			{
 				const GramLaunch launch = chooseGramLaunch(h->nw, h->L, h->Lp, h->groups, h->stride, h->threads, smemMax, h->uniquePairs, !form, h->core);
 				const JitShape &shape = launch.shape;
-				if (!shape.nb) return form ? fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_RPA=gram: no launch shape fits (threads %d, L %d)", h->threads, h->L) : PFFRG_OK;
-				JitCandidate c = { launch.threads, launch.groups, shape, nullptr, nullptr, 0.f };
-				const int rc = compileCandidate(h, d, c);
-				if (rc != PFFRG_OK) return rc;
-				std::vector<unsigned> terms; std::vector<int> seg;
-				buildGramTables(d, h->L, gramGeometry(h->core, h->L, h->Lp).lp, shape.gramRows, launch.reduceWarps, terms, seg);
-				CUDA_TRY(h->dGramTerms.upload(terms)); CUDA_TRY(h->dGramSeg.upload(seg));
-				h->gramWords = (int64_t)terms.size();
-				adoptCandidate(h, c);
-				h->jitCompileMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-				return PFFRG_OK;
+				if (!shape.nb && form) return fail(PFFRG_ERR_UNSUPPORTED, "PFFRG_RPA=gram: no launch shape fits (threads %d, L %d)", h->threads, h->L);
+				if (shape.nb)
+				{
+					JitCandidate c = { launch.threads, launch.groups, shape, nullptr, nullptr, 0.f };
+					const int rc = compileCandidate(h, d, c);
+					if (rc != PFFRG_OK) return rc;
+					std::vector<unsigned> terms; std::vector<int> seg;
+					buildGramTables(d, h->L, gramGeometry(h->core, h->L, h->Lp).lp, shape.gramRows, launch.reduceWarps, terms, seg);
+					CUDA_TRY(h->dGramTerms.upload(terms)); CUDA_TRY(h->dGramSeg.upload(seg));
+					h->gramWords = (int64_t)terms.size();
+					adoptCandidate(h, c);
+					h->jitCompileMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+					return PFFRG_OK;
+				}
+				// (no shape: the lattice stays on the straight-line code below)
 			}
 		}
 		JitShape first = chooseJitShape(h->core, h->nw, h->L, h->groups, h->threads / 32, smemMax);
@@ -2113,7 +2117,9 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 		const int Lp = paddedSites(L);
 		const GramLaunch launch = chooseGramLaunch(d->n_frequencies, L, Lp, groups, geo.stride, threads, 227 * 1024, uniquePairs, !getenv("PFFRG_RPA"), d->core);
 		const JitShape &g = launch.shape;
-		if (!g.nb) return fail(PFFRG_ERR_UNSUPPORTED, "no launch shape for the Gram form of the RPA phase");
+		if (!g.nb && getenv("PFFRG_RPA")) return fail(PFFRG_ERR_UNSUPPORTED, "no launch shape for the Gram form of the RPA phase");
+		if (g.nb)
+		{
 		std::vector<char> cubin;
 		const std::string err = compileFlowKernel(d->core, g.nb, g.nbt, 1, 1, launch.threads, g.minBlocks, KernelSizes{ L, Lp, channelsOf(d->core) * Lp, d->n_frequencies }, std::string(), cubin, gramDefines(g, d->core, L, Lp));
 		if (!err.empty()) return fail(PFFRG_ERR_CUDA, "%s", err.c_str());
@@ -2122,6 +2128,7 @@ int pffrg_jit_compile_check(const pffrg_desc *d, int64_t *cubinBytes)
 		if (getenv("PFFRG_JIT_VERBOSE")) fprintf(stderr, "[pffrg gram] threads %d nb %d nbt %d ctas %d smem %zu rows/block %d gemm threads %d words %zu (merged terms %lld) bank-conflict degree %.3f\n", threads, g.nb, g.nbt, g.minBlocks, g.smem, g.gramRows, g.gramThreads, terms.size(), (long long)uniquePairs, conflicts);
 		if (cubinBytes) *cubinBytes = (int64_t)cubin.size();
 		return PFFRG_OK;
+		}
 	}
 	JitShape shape = chooseJitShape(d->core, d->n_frequencies, L, groups, threads / 32, 227 * 1024);
 	if (!shape.nb) return fail(PFFRG_ERR_UNSUPPORTED, "lattice too large for the specialised kernel");

@@ -31,6 +31,8 @@ WORKLOADS = {
     # default: the warp-specialised Gram kernel with persistent CTAs; then the lattice-specialised straight-line code (first shape and autotuned), the unsplit Gram kernel
     "cubic_r7_su2_nw64": (211, [], [{}, {"PFFRG_RPA": "code"}, {"PFFRG_RPA": "code", "PFFRG_AUTOTUNE": "1"}, {"PFFRG_RPA": "gram"}, {"PFFRG_PERSISTENT": "0"}]),
     "honeycomb_kitaev_r7_xyz_nw64": (211, [], [{}, {"PFFRG_AUTOTUNE": "1"}, {"PFFRG_RPA": "gram"}]),
+    # large-range XYZ: the Gram form in the warp-specialised kernel by default (3 323 merged overlap terms), then the straight-line code
+    "honeycomb_kitaev_r10_xyz_nw64": (211, [], [{}, {"PFFRG_RPA": "code"}]),
     # default: the warp-specialised Gram kernel (gather / RPA / producer warp groups); then with several RPA rounds and small batches,
     # the unsplit Gram kernel without and with a producer warp
     "pyrochlore_r8_su2_nw64": (211, [], [{}, {"PFFRG_JIT_NBT": "16", "PFFRG_JIT_NB": "8"}, {"PFFRG_SPLIT": "0"}, {"PFFRG_SPLIT": "0", "PFFRG_PRODUCER": "1"}]),
