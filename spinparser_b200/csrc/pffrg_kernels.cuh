@@ -2136,21 +2136,24 @@ namespace pffrg
 
 #if defined(PFFRG_GRAM) && defined(PFFRG_SPLIT)
 	// ================================================================================================================
-	// WARP-SPECIALISED SU2 flow kernel (Gram form of the RPA phase). In v4FlowBody / v4FlowBodyProducer the same warps gather and then run
+	// WARP-SPECIALISED, PERSISTENT flow kernel (SU2 and XYZ cores, Gram form of the RPA phase). In v4FlowBody / v4FlowBodyProducer the same warps gather and then run
 	// the RPA phase, so the two alternate: while the Gram update occupies the FP64 tensor cores nothing is in flight to the L1 / L2, and
 	// while the gathers wait for their rows (long scoreboard) the FP64 pipes idle (ncu, pyrochlore-r8: gather 49 % of the samples, RPA
 	// phases 26 %, one CTA per SM). Here the CTA consists of three kinds of warps, each a whole number of warp groups of 128 threads so
 	// that the register file can be re-partitioned between them (setmaxnreg):
 	//   gather warps  [0, NG)            access buffers -> rows -> bilinear forms, accumulators in registers; t-channel nodes stage their RPA operands
 	//   RPA warps     [NG, NG + NR)      Gram update on the FP64 tensor cores + walk of the overlap list (rpaGram) over the staged nodes
-	//   producer warps (the last group)  build the access-buffer tables one batch ahead (as in v4FlowBodyProducer)
+	//   producer warps (the last group)  build the access-buffer tables up to PFFRG_SPLIT_TABLES - 1 batches ahead (as in v4FlowBodyProducer)
+	// A CTA is persistent: it works on the items itemBegin + blockIdx.x, + gridDim.x, ... (the host launches one CTA per SM).
 	// Schedule of a work item: its t-channel nodes are worked off in R rounds of NBT nodes; the nodes of the s and u channels (no staging,
 	// two thirds of all gathers) are cut into R chunks, and chunk r is gathered WHILE the RPA warps work on round r:
 	//   gather:  [t round 0] arrive(FULL) [s/u chunk 0] sync(EMPTY) [t round 1] arrive(FULL) [s/u chunk 1] sync(EMPTY) ... epilogue
 	//   RPA:                 sync(FULL) rpaGram(round 0) arrive(EMPTY)          sync(FULL) rpaGram(round 1) arrive(EMPTY)
 	// so one staging area suffices. Named barriers: 5 RPA warps (inside rpaGram), 6/7/14/1 + 8/9/15/2 table blocks full / empty (gather + producer),
 	// 10 producer warps, 11 staging area full, 12 staging area empty (gather + RPA), 13 gather warps (epilogue).
-	// Same arithmetic per node as v4FlowBody<SU2, NB, NBT, true>; the nodes of an item enter its sums in a different order.
+	// Same arithmetic per node as v4FlowBody<CORE, NB, NBT, true>; the nodes of an item enter its sums in a different order.
+	// XYZ: the lattice sum carries a spin permutation per overlap term (XYZFrgCore.cpp:297-322); its Gram form runs on the SU2 machinery with
+	// the three spin channels of a site staged as virtual sites (see gramcfg / PFFRG_GRAM_LV above and buildGramTables in pffrg.cu).
 	// ================================================================================================================
 #ifndef PFFRG_SPLIT_TABLES
 #define PFFRG_SPLIT_TABLES 2
