@@ -113,3 +113,36 @@ def test_checkpoint_written_by_one_process_resumes_in_another(tmp_path):
     assert int(resumed["finalStep"]) == int(full["finalStep"])
     for key in [k for k in full if k.startswith("final/")]:
         assert np.array_equal(resumed[key], full[key]), key
+
+
+def test_group_btree_keys_follow_the_library_convention(tmp_path):
+    """A group with more entries than one symbol-table node holds (34 measurements): as in the golden file, every child of the
+    B-tree node is a sorted SNOD of at most 2 K = 8 entries, key i + 1 is the heap offset of the LAST name of child i and key 0 the
+    empty name."""
+    from hdf5_v0 import _File
+    gen = _gen()
+    ref_file, lattice, model, couplings, cores = gen.TASKS["ref1"]
+    _run(tmp_path, gen.task_xml(lattice, model, couplings, cores[0]))
+    for path in (tmp_path / "task.obs", os.path.join(ASSETS, ref_file)):
+        f = _File(open(path, "rb").read())
+        b = f.b
+        addr = f.root_header
+        for name in ("SU2CorZZ", "data"):
+            addr = f.group_entries(*struct.unpack_from("<QQ", dict(f.messages(addr))[0x0011], 0))[name]
+        btree, heap = struct.unpack_from("<QQ", dict(f.messages(addr))[0x0011], 0)
+        heap_data = struct.unpack_from("<Q", b, heap + 24)[0]
+        name_at = lambda off: b[heap_data + off:b.index(b"\0", heap_data + off)].decode()
+        assert b[btree:btree + 4] == b"TREE" and b[btree + 4] == 0 and b[btree + 5] == 0
+        used = struct.unpack_from("<H", b, btree + 6)[0]
+        assert struct.unpack_from("<QQ", b, btree + 8) == (2 ** 64 - 1, 2 ** 64 - 1)
+        total, previous = 0, ""
+        for i in range(used):
+            key0, child, key1 = struct.unpack_from("<QQQ", b, btree + 24 + 16 * i)
+            assert b[child:child + 4] == b"SNOD"
+            count = struct.unpack_from("<H", b, child + 6)[0]
+            names = [name_at(struct.unpack_from("<Q", b, child + 8 + 40 * k)[0]) for k in range(count)]
+            assert 1 <= count <= 8 and names == sorted(names)
+            assert name_at(key0) == previous and name_at(key1) == names[-1] and previous < names[0]
+            previous = names[-1]
+            total += count
+        assert total == 34
