@@ -306,10 +306,10 @@ namespace
 				for (int nb : { 32, 16, 8 })
 				{
 					if (nbt % nb || (forcedNb ? nb != forcedNb : (nb == 32 && !split))) continue; // (batches of 32 nodes: warp-specialised kernel, or PFFRG_JIT_NB=32)
-					for (int tables = split ? 3 : tableCopies; tables >= (split ? 2 : tableCopies); --tables)
+					// table blocks: the warp-specialised kernel tries three, then two (PFFRG_SPLIT_TABLES = 2..4 forces one value); the others have a fixed number
+					const int firstCopies = !split ? tableCopies : forcedTables ? forcedTables : 3, lastCopies = !split ? tableCopies : forcedTables ? forcedTables : 2;
+					for (int copies = firstCopies; copies >= lastCopies; --copies)
 					{
-						if (split && forcedTables && tables != std::min(forcedTables, 3) && !(forcedTables == 4 && tables == 3)) continue;
-						const int copies = (split && forcedTables == 4) ? 4 : tables;
 						for (int pb = pbMax; pb >= 8; pb -= 8)
 						{
 							if (forcedPb && pb != std::min(forcedPb, pbMax)) continue;
@@ -596,11 +596,14 @@ namespace
 			std::vector<char> cubin; std::string cacheHit;
 			const std::string err = compileFlowKernel(h->core, c.shape.nb, c.shape.nbt, subs, cluster, c.threads, c.shape.minBlocks, KernelSizes{ h->L, h->Lp, h->RL, h->nw }, rpaSource, cubin, defines, &cacheHit);
 			if (!err.empty()) return fail(PFFRG_ERR_CUDA, "run-time compilation of %s failed: %s", what, err.c_str());
+			c.library = nullptr;
 			cudaError_t e = cudaLibraryLoadData(&c.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+			if (e != cudaSuccess) c.library = nullptr;
 			if (e == cudaSuccess) e = cudaLibraryGetKernel(&c.kernel, c.library, "pffrg_v4flow_jit");
 			if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.shape.smem);
 			if (e == cudaSuccess) return PFFRG_OK;
 			cudaGetLastError();
+			if (c.library) cudaLibraryUnload(c.library);
 			c.library = nullptr; c.kernel = nullptr;
 			if (attempt == 0 && !cacheHit.empty())
 			{
