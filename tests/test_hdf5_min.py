@@ -146,3 +146,37 @@ def test_group_btree_keys_follow_the_library_convention(tmp_path):
             previous = names[-1]
             total += count
         assert total == 34
+
+
+@pytest.mark.parametrize("real", ["float", "double"])
+def test_api_round_trip_without_reference_code(real, tmp_path):
+    """The layer on its own (tests/cpp/hdf5_min_roundtrip.cpp): a group of 300 children (38 symbol-table nodes under two levels of B-tree
+    nodes), an empty group, an array-typed dataset, attributes -- written, re-read from disk by the layer's own reader, extended,
+    written again, and read by the independent Python reader. H5MIN_REAL = float and double (the FP64 test build of the reference)."""
+    import shutil
+    from hdf5_v0 import read_hdf5
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    exe = tmp_path / "roundtrip"
+    subprocess.run([gxx, "-std=c++17", "-O1", f"-DH5MIN_REAL={real}", "-I", os.path.join(ROOT, "spinparser_b200", "host"),
+                    os.path.join(ROOT, "tests", "cpp", "hdf5_min_roundtrip.cpp"), "-o", str(exe)], check=True, capture_output=True)
+    path = tmp_path / "roundtrip.obs"
+    out = subprocess.run([str(exe), str(path)], check=True, capture_output=True, text=True).stdout.split()
+    assert [float(x) for x in out[:2]] == [299.0, 299.0 + 0.125 * 9] and abs(float(out[2]) - 50.0 / 18) < 1e-4  # (printed with %g)
+    assert out[3:] == ["300", "measurement_0", "0", "1", "0"]
+    d = read_hdf5(str(path))
+    dtype = np.float32 if real == "float" else np.float64
+    assert len([k for k in d if k.endswith("/data")]) == 300 and len([k for k in d if k.endswith("@cutoff")]) == 300
+    assert d["/Cor/meta/basis"].dtype == dtype and np.array_equal(d["/Cor/meta/basis"], np.array([[0, 0, 0], [0.5, 0.25, 1.5]], dtype=dtype))
+    for k in (0, 7, 150, 299):
+        assert np.array_equal(d[f"/Cor/data/measurement_{k}/data"], (k + 0.125 * np.arange(10, dtype=np.float64)).astype(dtype).reshape(2, 5))
+        assert d[f"/Cor/data/measurement_{k}@cutoff"][0] == dtype(50) / dtype(k + 1)
+    # two levels of B-tree nodes in the big group; the groups added before and after the re-read are there
+    from hdf5_v0 import _File
+    f = _File(open(path, "rb").read())
+    root = f.group_entries(*struct.unpack_from("<QQ", dict(f.messages(f.root_header))[0x0011], 0))
+    assert sorted(root) == ["Cor", "empty", "extra"]
+    cor = f.group_entries(*struct.unpack_from("<QQ", dict(f.messages(root["Cor"]))[0x0011], 0))
+    btree = struct.unpack_from("<Q", dict(f.messages(cor["data"]))[0x0011], 0)[0]
+    assert f.b[btree:btree + 4] == b"TREE" and f.b[btree + 5] == 1 and struct.unpack_from("<H", f.b, btree + 6)[0] == 2
